@@ -1,0 +1,410 @@
+// a4/a5: find_preserve + sys_comp on a resident vector; a6: comp_sub with explicit sub-weights.
+#include "compress.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// find_preserve (compress_utils.cpp:29-105) as threshold rounds: an element is preserved once
+// |v| >= R / n_left where R is the one-norm of what is not yet preserved.  The reference pops a heap
+// per rank and re-syncs R across ranks every round; one CTA-chunk here = one "rank".
+// Traffic per round: 8 B/element (values; keep flags are 1 B and stay in L2).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FR_COMP_BLOCK)
+find_preserve_kernel(const double *__restrict__ vals, size_t n, unsigned n_samp_in, uint8_t *__restrict__ keep,
+                     double *part_d, unsigned long long *part_c, CompState *st) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh_d[34];
+    __shared__ unsigned long long sh_c[34];
+    GridRed red{part_d, part_c, 0, (int)gridDim.x, sh_d, sh_c};
+    size_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + 31) & ~(size_t)31;
+    const size_t lo = (size_t)blockIdx.x * chunk < n ? (size_t)blockIdx.x * chunk : n;
+    const size_t hi = lo + chunk < n ? lo + chunk : n;
+
+    double s = 0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        s += fabs(vals[i]);
+        keep[i] = 0;
+    }
+    unsigned long long dummy = 0;
+    grid_reduce(grid, red, s, dummy);
+    const double glob_total = s;
+    double loc = s;
+    unsigned nrem = n_samp_in;
+    unsigned long long glob_sampled = 1, kept_total = 0;
+    bool recalc = false;
+    double R = 0;
+    unsigned rounds = 0;
+    while (glob_sampled > 0) {
+        R = loc;
+        double rem = 0;
+        unsigned long long cnt = 0;
+        if (R >= 0) {
+            const double thr = R / nrem;  // glob_one_norm / (*n_samp - loc_sampled), loc_sampled stale
+            for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+                if (!keep[i]) {
+                    double m = fabs(vals[i]);
+                    if (m >= thr) {
+                        keep[i] = 1;
+                        cnt++;
+                        rem += m;
+                    }
+                }
+            }
+        }
+        grid_reduce(grid, red, rem, cnt);
+        loc -= rem;
+        glob_sampled = cnt;
+        nrem -= (unsigned)cnt;
+        kept_total += cnt;
+        rounds++;
+        if (glob_sampled == 0 && !recalc) {
+            double t = 0;
+            for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+                if (!keep[i]) t += fabs(vals[i]);
+            grid_reduce(grid, red, t, dummy);
+            loc = t;
+            glob_sampled = 1;
+            recalc = true;
+        } else {
+            recalc = false;
+        }
+    }
+    double loc_final = 0;
+    if (R < 1e-9) {
+        nrem = 0;
+    } else {
+        double t = 0;
+        for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+            if (!keep[i]) t += fabs(vals[i]);
+        grid_reduce(grid, red, t, dummy);
+        loc_final = t;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->loc_norm = loc_final;
+        st->glob_norm = glob_total;
+        st->n_samp_left = nrem;
+        st->rounds = rounds;
+        st->n_kept = kept_total;
+        st->n_in = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sys_comp (compress_utils.cpp:278-327): chunked device-wide exclusive scan of |v| over the
+// non-preserved elements in storage order; element i keeps +-G/n iff a grid point rn0 + k*unit lies in
+// (lb_i, lb_i + |v_i|).  lbound0 / glob / n_samp describe this shard's place in the global
+// systematic grid (seed_sys :107-127).  Traffic: 2 reads + 1 write of 8 B per element.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FR_COMP_BLOCK)
+sys_comp_kernel(double *__restrict__ vals, size_t n, uint8_t *__restrict__ keep, const double *__restrict__ in_r4,
+                double lbound0_host, double glob_host, long long n_samp_host, double rn_uniform, double *part_d,
+                unsigned long long *part_c, CompState *out_st) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh_d[34];
+    __shared__ unsigned long long sh_c[34];
+    __shared__ double sh_sd[34];
+    __shared__ unsigned long long sh_sc[34];
+    GridRed red{part_d, part_c, 0, (int)gridDim.x, sh_d, sh_c};
+    size_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + 31) & ~(size_t)31;
+    const size_t lo = (size_t)blockIdx.x * chunk < n ? (size_t)blockIdx.x * chunk : n;
+    const size_t hi = lo + chunk < n ? lo + chunk : n;
+
+    // single shard: take norm and budget from the preceding find_preserve on the device
+    double G = glob_host, lbound0 = lbound0_host;
+    unsigned n_samp = (unsigned)n_samp_host;
+    if (n_samp_host < 0) {
+        G = in_r4[0];
+        n_samp = (unsigned)in_r4[2];
+        lbound0 = 0;
+    }
+    double rn0, unit;
+    if (n_samp > 0) {
+        rn0 = seed_sys_dev(lbound0, G, rn_uniform, n_samp);
+        unit = G / n_samp;
+    } else {
+        rn0 = INFINITY;
+        unit = INFINITY;
+    }
+    double cs = 0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+        if (!keep[i]) cs += fabs(vals[i]);
+    cs = block_sum(cs, sh_d);
+    double blk_lb, tot_lb;
+    unsigned long long e0, e1;
+    grid_excl_scan(grid, red, cs, 0ull, blk_lb, e0, tot_lb, e1, sh_sd, sh_sc);
+
+    double carry = lbound0 + blk_lb;
+    double new_norm = 0;
+    unsigned long long n_samples = 0;
+    for (size_t base = lo; base < hi; base += blockDim.x) {
+        size_t i = base + threadIdx.x;
+        bool act = i < hi;
+        double v = act ? vals[i] : 0.0;
+        bool kp = act ? keep[i] != 0 : true;
+        double m = kp ? 0.0 : fabs(v);
+        double ex, tot;
+        unsigned long long ec, tc;
+        block_excl_scan(m, 0ull, ex, ec, tot, tc, sh_sd, sh_sc);
+        if (act) {
+            if (kp) {
+                new_norm += fabs(v);
+                keep[i] = 0;
+            } else if (v != 0) {
+                double start = carry + ex;
+                double lbound = start + m;
+                long long k0 = sys_count_below(start, rn0, unit);
+                double g = fma((double)k0, unit, rn0);
+                if (g < lbound) {
+                    double nv = G / n_samp;
+                    vals[i] = v > 0 ? nv : -nv;
+                    new_norm += nv;
+                    n_samples++;
+                } else {
+                    vals[i] = 0;
+                    keep[i] = 1;
+                }
+            }
+        }
+        carry += tot;
+    }
+    grid_reduce(grid, red, new_norm, n_samples);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out_st->new_norm = new_norm;
+        out_st->n_out = n_samples;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// comp_sub with materialised sub-weights (the reference's calling convention)
+// ---------------------------------------------------------------------------------------------------
+struct MatProvider {
+    const double *values;
+    const uint32_t *ndiv;
+    const double *subw;
+    const uint16_t *sub_sizes;
+    size_t n, n_sub;
+    __device__ size_t count() const { return n; }
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns) const {
+        v = values[i];
+        nd = ndiv[i];
+        ns = sub_sizes ? sub_sizes[i] : (uint32_t)n_sub;
+    }
+    __device__ void row(size_t i, double *w) const {
+        for (size_t j = 0; j < n_sub; j++) w[j] = subw[i * n_sub + j];
+    }
+};
+
+__global__ void __launch_bounds__(FR_COMP_BLOCK)
+comp_sub_mat_kernel(MatProvider prov, CompSubBufs bufs, unsigned n_samp, double rn) {
+    comp_sub_engine(prov, bufs, n_samp, rn);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host wrappers
+// ---------------------------------------------------------------------------------------------------
+static int coop_launch(fries_ctx *c, const void *kernel, int grid, void **args) {
+    CUDA_TRY(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(FR_COMP_BLOCK), args, 0, c->stream));
+    c->launch_count++;
+    return FRIES_OK;
+}
+
+struct RedScratch {
+    double *pd;
+    unsigned long long *pc;
+    CompState *st;
+};
+// carve [2][grid] doubles + [2][grid] u64 + 2 CompState out of the context scratch, after `skip` bytes
+static int red_scratch(fries_ctx *c, int grid, size_t skip, RedScratch &r) {
+    size_t need = skip + (size_t)grid * 4 * 8 + 2 * sizeof(CompState) + 256;
+    FRIES_TRY(c->ensure_scratch(need));
+    char *p = (char *)c->d_scratch + ((skip + 255) & ~(size_t)255);
+    r.pd = (double *)p;
+    r.pc = (unsigned long long *)(p + (size_t)grid * 2 * 8);
+    r.st = (CompState *)(p + (size_t)grid * 4 * 8);
+    return FRIES_OK;
+}
+
+extern "C" int fries_find_preserve_dev(fries_ctx *c, const double *d_values, size_t count, unsigned n_samp,
+                                       uint8_t *d_keep, double *d_result4);
+extern "C" int fries_sys_comp_dev(fries_ctx *c, double *d_values, size_t count, const double *d_result4,
+                                  uint8_t *d_keep, double rand_num, double *d_new_norm);
+
+__global__ void state_to_result4(const CompState *st, double *r4) {
+    r4[0] = st->loc_norm;
+    r4[1] = st->glob_norm;
+    r4[2] = (double)st->n_samp_left;
+    r4[3] = (double)st->n_kept;
+}
+
+int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, unsigned n_samp, uint8_t *d_keep,
+                               CompState *d_st, double *pd, unsigned long long *pc, int grid) {
+    void *args[] = {(void *)&d_values, (void *)&count, (void *)&n_samp, (void *)&d_keep, (void *)&pd, (void *)&pc,
+                    (void *)&d_st};
+    ProfScope ps(c, "find_preserve");
+    return coop_launch(c, (const void *)find_preserve_kernel, grid, args);
+}
+
+int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, uint8_t *d_keep, const double *d_in,
+                          double lbound0, double glob, long long n_samp, double rn, CompState *d_out, double *pd,
+                          unsigned long long *pc, int grid) {
+    void *args[] = {(void *)&d_values, (void *)&count, (void *)&d_keep, (void *)&d_in, (void *)&lbound0, (void *)&glob,
+                    (void *)&n_samp,   (void *)&rn,    (void *)&pd,     (void *)&pc,   (void *)&d_out};
+    ProfScope ps(c, "sys_comp");
+    return coop_launch(c, (const void *)sys_comp_kernel, grid, args);
+}
+
+extern "C" int fries_find_preserve(fries_ctx *c, const double *h_values, size_t count, unsigned *n_samp,
+                                   double *glob_norm, uint8_t *h_keep, double *loc_norm) {
+    FRIES_REQUIRE(c && n_samp && glob_norm && loc_norm && (count == 0 || (h_values && h_keep)),
+                  "fries_find_preserve: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int grid = c->coop_grid((const void *)find_preserve_kernel, FR_COMP_BLOCK, 0);
+    DevBuf<double> vals;
+    DevBuf<uint8_t> keep;
+    FRIES_TRY(vals.alloc(count));
+    FRIES_TRY(keep.alloc(count));
+    RedScratch r;
+    FRIES_TRY(red_scratch(c, grid, 0, r));
+    CUDA_TRY(cudaMemcpyAsync(vals.p, h_values, count * 8, cudaMemcpyHostToDevice, c->stream));
+    FRIES_TRY(fries_find_preserve_launch(c, vals.p, count, *n_samp, keep.p, r.st, r.pd, r.pc, grid));
+    CompState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, r.st, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    if (count) CUDA_TRY(cudaMemcpyAsync(h_keep, keep.p, count, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *n_samp = st.n_samp_left;
+    *glob_norm = st.glob_norm;
+    *loc_norm = st.loc_norm;
+    return FRIES_OK;
+}
+
+extern "C" int fries_sys_comp(fries_ctx *c, double *h_values, size_t count, double *loc_norms, int n_ranks, int rank,
+                              unsigned n_samp, uint8_t *h_keep, double rand_num) {
+    FRIES_REQUIRE(c && loc_norms && (count == 0 || (h_values && h_keep)), "fries_sys_comp: NULL argument");
+    FRIES_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "fries_sys_comp: bad rank %d of %d", rank, n_ranks);
+    CUDA_TRY(cudaSetDevice(c->device));
+    int grid = c->coop_grid((const void *)sys_comp_kernel, FR_COMP_BLOCK, 0);
+    DevBuf<double> vals;
+    DevBuf<uint8_t> keep;
+    FRIES_TRY(vals.alloc(count));
+    FRIES_TRY(keep.alloc(count));
+    RedScratch r;
+    FRIES_TRY(red_scratch(c, grid, 0, r));
+    // seed_sys inputs, summed in rank order as the reference does (compress_utils.cpp:292-295,114-121)
+    double glob = 0, lbound0 = 0;
+    for (int p = 0; p < n_ranks; p++) glob += loc_norms[p];
+    for (int p = 0; p < rank; p++) lbound0 += loc_norms[p];
+    CUDA_TRY(cudaMemcpyAsync(vals.p, h_values, count * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(keep.p, h_keep, count, cudaMemcpyHostToDevice, c->stream));
+    FRIES_TRY(fries_sys_comp_launch(c, vals.p, count, keep.p, nullptr, lbound0, glob, (long long)n_samp, rand_num,
+                                    r.st + 1, r.pd, r.pc, grid));
+    CompState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, r.st + 1, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    if (count) {
+        CUDA_TRY(cudaMemcpyAsync(h_values, vals.p, count * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_keep, keep.p, count, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    loc_norms[rank] = st.new_norm;
+    return FRIES_OK;
+}
+
+extern "C" int fries_find_preserve_dev(fries_ctx *c, const double *d_values, size_t count, unsigned n_samp,
+                                       uint8_t *d_keep, double *d_result4) {
+    FRIES_REQUIRE(c && d_result4 && (count == 0 || (d_values && d_keep)), "fries_find_preserve_dev: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int grid = c->coop_grid((const void *)find_preserve_kernel, FR_COMP_BLOCK, 0);
+    RedScratch r;
+    FRIES_TRY(red_scratch(c, grid, 0, r));
+    FRIES_TRY(fries_find_preserve_launch(c, d_values, count, n_samp, d_keep, r.st, r.pd, r.pc, grid));
+    state_to_result4<<<1, 1, 0, c->stream>>>(r.st, d_result4);
+    c->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return FRIES_OK;
+}
+
+extern "C" int fries_sys_comp_dev(fries_ctx *c, double *d_values, size_t count, const double *d_result4,
+                                  uint8_t *d_keep, double rand_num, double *d_new_norm) {
+    FRIES_REQUIRE(c && d_result4 && (count == 0 || (d_values && d_keep)), "fries_sys_comp_dev: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int grid = c->coop_grid((const void *)sys_comp_kernel, FR_COMP_BLOCK, 0);
+    RedScratch r;
+    FRIES_TRY(red_scratch(c, grid, 0, r));
+    FRIES_TRY(fries_sys_comp_launch(c, d_values, count, d_keep, d_result4, 0.0, 0.0, -1LL, rand_num, r.st + 1, r.pd,
+                                    r.pc, grid));
+    if (d_new_norm) {
+        CUDA_TRY(cudaMemcpyAsync(d_new_norm, &r.st[1].new_norm, 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return FRIES_OK;
+}
+
+extern "C" int fries_comp_sub(fries_ctx *c, const double *h_values, size_t count, const uint32_t *h_ndiv,
+                              const double *h_sub_weights, size_t n_sub, const uint16_t *h_sub_sizes, unsigned n_samp,
+                              double rand_num, double *h_new_vals, uint64_t *h_new_idx, size_t out_cap, size_t *n_out,
+                              unsigned *n_samp_left, double *loc_norm) {
+    FRIES_REQUIRE(c && n_out && (count == 0 || (h_values && h_ndiv && h_sub_weights)), "fries_comp_sub: NULL argument");
+    FRIES_REQUIRE(n_sub >= 1 && n_sub <= FRIES_MAX_SUB, "fries_comp_sub: n_sub %zu not in 1..%d", n_sub, FRIES_MAX_SUB);
+    CUDA_TRY(cudaSetDevice(c->device));
+    int grid = c->coop_grid((const void *)comp_sub_mat_kernel, FR_COMP_BLOCK, 0);
+    size_t cn = count ? count : 1;
+    DevBuf<double> values, subw, veff, wtr, lb, oval;
+    DevBuf<uint32_t> ndiv, keep, kcnt, owidx, osub;
+    DevBuf<uint16_t> ssz;
+    DevBuf<uint8_t> nsub;
+    FRIES_TRY(values.alloc(cn));
+    FRIES_TRY(subw.alloc(cn * n_sub));
+    FRIES_TRY(veff.alloc(cn));
+    FRIES_TRY(wtr.alloc(cn));
+    FRIES_TRY(lb.alloc(cn));
+    FRIES_TRY(ndiv.alloc(cn));
+    FRIES_TRY(keep.alloc(cn));
+    FRIES_TRY(kcnt.alloc(cn));
+    FRIES_TRY(nsub.alloc(cn));
+    FRIES_TRY(oval.alloc(out_cap));
+    FRIES_TRY(owidx.alloc(out_cap));
+    FRIES_TRY(osub.alloc(out_cap));
+    if (h_sub_sizes) FRIES_TRY(ssz.alloc(cn));
+    RedScratch r;
+    FRIES_TRY(red_scratch(c, grid, 0, r));
+    if (count) {
+        CUDA_TRY(cudaMemcpyAsync(values.p, h_values, count * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(ndiv.p, h_ndiv, count * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(subw.p, h_sub_weights, count * n_sub * 8, cudaMemcpyHostToDevice, c->stream));
+        if (h_sub_sizes) CUDA_TRY(cudaMemcpyAsync(ssz.p, h_sub_sizes, count * 2, cudaMemcpyHostToDevice, c->stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(r.st, 0, sizeof(CompState), c->stream));
+    MatProvider prov{values.p, ndiv.p, subw.p, h_sub_sizes ? ssz.p : nullptr, count, n_sub};
+    CompSubBufs bufs{veff.p, wtr.p, lb.p, ndiv.p, keep.p, kcnt.p, nsub.p, oval.p, owidx.p, osub.p,
+                     (unsigned long long)out_cap, r.pd, r.pc, r.st};
+    // ndiv is both provider input and engine state: give the engine its own copy
+    DevBuf<uint32_t> ndiv_state;
+    FRIES_TRY(ndiv_state.alloc(cn));
+    bufs.ndiv = ndiv_state.p;
+    void *args[] = {(void *)&prov, (void *)&bufs, (void *)&n_samp, (void *)&rand_num};
+    {
+        ProfScope ps(c, "comp_sub");
+        FRIES_TRY(coop_launch(c, (const void *)comp_sub_mat_kernel, grid, args));
+    }
+    CompState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, r.st, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (st.overflow) {
+        fries_set_error("fries_comp_sub: %llu outputs did not fit out_cap %zu", st.overflow, out_cap);
+        return FRIES_ERR_CAPACITY;
+    }
+    size_t no = (size_t)st.n_out;
+    std::vector<uint32_t> widx(no ? no : 1);
+    std::vector<uint32_t> sub(no ? no : 1);
+    if (no) {
+        CUDA_TRY(cudaMemcpy(h_new_vals, oval.p, no * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(widx.data(), owidx.p, no * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(sub.data(), osub.p, no * 4, cudaMemcpyDeviceToHost));
+    }
+    for (size_t i = 0; i < no; i++) {
+        h_new_idx[2 * i] = widx[i];
+        h_new_idx[2 * i + 1] = sub[i];
+    }
+    *n_out = no;
+    if (n_samp_left) *n_samp_left = st.n_samp_left;
+    if (loc_norm) *loc_norm = st.loc_norm;
+    return FRIES_OK;
+}

@@ -1,0 +1,407 @@
+// Device-side stochastic compression engine (a4, a5, a6): persistent cooperative kernels.
+//
+// Every compression in the reference is "find the exactly-preserved set by a fixed-point iteration
+// on a global threshold, then systematically resample the rest with one uniform".  The reference
+// runs this per MPI rank with an Allgather per round (compress_utils.cpp:52-92, :153-265); here one
+// cooperative kernel (a CTA or two per SM, grid.sync between rounds) plays the role of the ranks:
+// each CTA owns a contiguous chunk of the input, per-round partial sums go through a
+// double-buffered array that every CTA re-reduces in a fixed order, so the result is deterministic
+// and identical in all CTAs.  The resampling step is a chunked device-wide prefix sum of the
+// residual weights; an element draws the grid points rn0 + k*unit that fall in its interval.
+#pragma once
+#include "common.cuh"
+
+#define FR_COMP_BLOCK 512
+
+struct CompState {
+    double loc_norm;             // residual one-norm after the keep phase (sum of wt_remain)
+    double glob_norm;            // one-norm before (find_preserve's *global_norm)
+    double new_norm;             // one-norm after resampling (sys_comp's loc_norms[rank] output)
+    unsigned n_samp_left;        // budget left after the keep phase
+    unsigned rounds;             // fixed-point rounds executed
+    unsigned long long n_kept;   // budget consumed by exact preservation
+    unsigned long long n_out;    // outputs written (comp_sub) / samples drawn (sys_comp)
+    unsigned long long n_in;     // inputs seen
+    unsigned long long overflow; // outputs that did not fit out_cap (dropped)
+    unsigned long long anomalies;// FP-tie events (two grid points in one sub-element, clamped sub index)
+};
+
+struct GridRed {
+    double *pd;               // [2][nb]
+    unsigned long long *pc;   // [2][nb]
+    int parity;
+    int nb;
+    double *shd;              // 33 doubles of shared memory
+    unsigned long long *shc;  // 33 u64
+};
+
+// all-CTA reduction of (d, c); result in every thread of every CTA, bit-identical.
+__device__ __forceinline__ void grid_reduce(cg::grid_group &grid, GridRed &r, double &d, unsigned long long &c) {
+    d = block_sum(d, r.shd);
+    c = block_sum_u64(c, r.shc);
+    if (threadIdx.x == 0) {
+        __stcg(&r.pd[r.parity * r.nb + blockIdx.x], d);
+        __stcg(&r.pc[r.parity * r.nb + blockIdx.x], c);
+    }
+    grid.sync();
+    double v = 0;
+    unsigned long long w = 0;
+    for (int i = threadIdx.x; i < r.nb; i += blockDim.x) {
+        v += __ldcg(&r.pd[r.parity * r.nb + i]);
+        w += __ldcg(&r.pc[r.parity * r.nb + i]);
+    }
+    d = block_sum(v, r.shd);
+    c = block_sum_u64(w, r.shc);
+    r.parity ^= 1;
+}
+
+// Exclusive prefix over CTAs of per-CTA values (d, c): every CTA evaluates the same fixed scan
+// network over the nb partials, so all CTAs agree bitwise on every boundary.
+__device__ __forceinline__ void grid_excl_scan(cg::grid_group &grid, GridRed &r, double d, unsigned long long c,
+                                               double &ex_d, unsigned long long &ex_c, double &tot_d,
+                                               unsigned long long &tot_c, double *sh_scan_d,
+                                               unsigned long long *sh_scan_c) {
+    if (threadIdx.x == 0) {
+        __stcg(&r.pd[r.parity * r.nb + blockIdx.x], d);
+        __stcg(&r.pc[r.parity * r.nb + blockIdx.x], c);
+    }
+    grid.sync();
+    double run_d = 0;
+    unsigned long long run_c = 0;
+    double my_d = 0;
+    unsigned long long my_c = 0;
+    for (int base = 0; base < r.nb; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        double a = i < r.nb ? __ldcg(&r.pd[r.parity * r.nb + i]) : 0.0;
+        unsigned long long b = i < r.nb ? __ldcg(&r.pc[r.parity * r.nb + i]) : 0ull;
+        double ea, ta;
+        unsigned long long ec, tc;
+        block_excl_scan(a, b, ea, ec, ta, tc, sh_scan_d, sh_scan_c);
+        if (i == (int)blockIdx.x) {
+            sh_scan_d[33] = run_d + ea;
+            sh_scan_c[33] = run_c + ec;
+        }
+        run_d += ta;
+        run_c += tc;
+    }
+    __syncthreads();
+    my_d = sh_scan_d[33];
+    my_c = sh_scan_c[33];
+    ex_d = my_d;
+    ex_c = my_c;
+    tot_d = run_d;
+    tot_c = run_c;
+    r.parity ^= 1;
+    __syncthreads();
+}
+
+// seed_sys compress_utils.cpp:107-127 for a rank whose lower ranks hold `lbound` of the `glob` norm
+__device__ __forceinline__ double seed_sys_dev(double lbound, double glob, double rn, unsigned n_samp) {
+    rn *= glob / n_samp;
+    rn += glob / n_samp * (int)(lbound * n_samp / glob);
+    if (rn < lbound) rn += glob / n_samp;
+    return rn;
+}
+
+struct CompSubBufs {
+    // per-input state (capacity >= number of inputs)
+    double *veff;
+    double *wt_remain;
+    double *lb;          // exclusive prefix of wt_remain (resampling lower bound)
+    uint32_t *ndiv;
+    uint32_t *keep;      // bit j = sub-element j preserved exactly (bit 0 for uniform rows)
+    uint32_t *kcnt;      // outputs this input emits
+    uint8_t *nsub;
+    // outputs
+    double *out_val;
+    uint32_t *out_widx;
+    uint32_t *out_sub;
+    unsigned long long out_cap;
+    // reduction scratch
+    double *part_d;               // [2][grid]
+    unsigned long long *part_c;   // [2][grid]
+    CompState *st;
+};
+
+// The hierarchical compression engine.  Provider P supplies
+//   size_t count();                                            number of inputs
+//   void prep(size_t i, double &v, uint32_t &ndiv, uint32_t &nsub);   effective weight + row shape
+//   void row(size_t i, double *w);                             the nsub sub-weights of input i
+// Restates comp_sub (compress_utils.cpp:797-820): find_keep_sub :130-276 then sys_sub :702-794.
+template <class P>
+__device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_in, double rn_uniform) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh_d[34];
+    __shared__ unsigned long long sh_c[34];
+    __shared__ double sh_sd[34];
+    __shared__ unsigned long long sh_sc[34];
+    GridRed red{b.part_d, b.part_c, 0, (int)gridDim.x, sh_d, sh_c};
+
+    const size_t n = prov.count();
+    size_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + 31) & ~(size_t)31;
+    const size_t lo = (size_t)blockIdx.x * chunk < n ? (size_t)blockIdx.x * chunk : n;
+    const size_t hi = lo + chunk < n ? lo + chunk : n;
+
+    // ---- phase 0: effective weights (find_keep_sub :134-137) ----
+    double s = 0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        double v;
+        uint32_t nd, ns;
+        prov.prep(i, v, nd, ns);
+        b.veff[i] = v;
+        b.wt_remain[i] = v;
+        b.ndiv[i] = nd;
+        b.nsub[i] = (uint8_t)ns;
+        b.keep[i] = 0;
+        s += v;
+    }
+    unsigned long long dummy = 0;
+    grid_reduce(grid, red, s, dummy);
+    double loc = s;
+
+    // ---- keep rounds (find_keep_sub :153-265) ----
+    unsigned nrem = n_samp_in;
+    unsigned long long glob_sampled = 1;
+    int last_pass = 0;
+    double R = 0;
+    unsigned rounds = 0;
+    unsigned long long kept_total = 0;
+    while (glob_sampled > 0) {
+        R = loc;
+        if (R < 0) break;
+        const double wt_factor = (double)nrem;
+        double rem = 0;
+        unsigned long long cnt = 0;
+        for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            double wr = b.wt_remain[i];
+            if (wr > 0) {
+                double v = b.veff[i];
+                uint32_t nd = b.ndiv[i];
+                double cw = v * wt_factor;
+                if (nd > 0) cw /= nd;
+                if (cw >= R) {
+                    if (nd > 0) {
+                        b.keep[i] = 1;
+                        b.wt_remain[i] = 0;
+                        cnt += nd;
+                        rem += v;
+                    } else {
+                        double w[FRIES_MAX_SUB];
+                        prov.row(i, w);
+                        uint32_t ns = b.nsub[i], kb = b.keep[i];
+                        uint32_t full = (ns / 8) * 8;
+                        double sub_remain = 0;
+                        for (uint32_t j = 0; j < ns; j++) {
+                            if (!((kb >> j) & 1u)) {
+                                double sm = cw * w[j];
+                                double eps = j < full ? 1e-12 : 1e-10;
+                                if (sm >= R && fabs(sm) > eps) {
+                                    kb |= 1u << j;
+                                    cnt++;
+                                } else {
+                                    sub_remain += sm;
+                                }
+                            }
+                        }
+                        b.keep[i] = kb;
+                        sub_remain /= wt_factor;
+                        double change = wr - sub_remain;
+                        b.wt_remain[i] = sub_remain;
+                        rem += change;
+                    }
+                }
+            }
+        }
+        grid_reduce(grid, red, rem, cnt);
+        loc -= rem;
+        glob_sampled = cnt;
+        nrem -= (unsigned)cnt;
+        kept_total += cnt;
+        rounds++;
+        if (last_pass && glob_sampled) last_pass = 0;
+        if (glob_sampled == 0 && !last_pass) {
+            last_pass = 1;
+            glob_sampled = 1;
+            double t = 0;
+            for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) t += b.wt_remain[i];
+            grid_reduce(grid, red, t, dummy);
+            loc = t;
+        }
+    }
+    double loc_final = 0;
+    if (R / nrem < 1e-8) {
+        nrem = 0;
+    } else {
+        double t = 0;
+        for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) t += b.wt_remain[i];
+        grid_reduce(grid, red, t, dummy);
+        loc_final = t;
+    }
+
+    // ---- resampling (sys_sub :702-794) ----
+    const double G = loc_final;
+    double rn0, unit;
+    if (nrem > 0) {
+        rn0 = seed_sys_dev(0.0, G, rn_uniform, nrem);
+        unit = G / nrem;
+    } else {
+        rn0 = INFINITY;
+        unit = INFINITY;
+    }
+
+    // pass 1: chunk sums of the residual weights -> canonical CTA boundaries
+    double cs = 0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        if (b.veff[i] != 0) cs += b.wt_remain[i];
+    }
+    cs = block_sum(cs, sh_d);
+    double blk_lb, tot_lb;
+    unsigned long long e0, e1;
+    grid_excl_scan(grid, red, cs, 0ull, blk_lb, e0, tot_lb, e1, sh_sd, sh_sc);
+
+    // pass 2: per-input lower bound + number of outputs
+    double carry = blk_lb;
+    unsigned long long my_out = 0;
+    unsigned long long anomalies = 0;
+    for (size_t base = lo; base < hi; base += blockDim.x) {
+        size_t i = base + threadIdx.x;
+        bool act = i < hi;
+        double v = act ? b.veff[i] : 0.0;
+        double wr = (act && v != 0) ? b.wt_remain[i] : 0.0;
+        double ex, tot;
+        unsigned long long ec, tc;
+        block_excl_scan(wr, 0ull, ex, ec, tot, tc, sh_sd, sh_sc);
+        if (act) {
+            double start = carry + ex;
+            b.lb[i] = start;
+            uint32_t k = 0;
+            if (v != 0) {
+                uint32_t nd = b.ndiv[i];
+                double lbound = start + wr;
+                if (nd > 0) {
+                    if (b.keep[i]) {
+                        k = nd;
+                    } else {
+                        long long k0 = sys_count_below(start, rn0, unit), k1 = sys_count_below(lbound, rn0, unit);
+                        k = (uint32_t)(k1 > k0 ? k1 - k0 : 0);
+                    }
+                } else {
+                    long long k0 = sys_count_below(start, rn0, unit);
+                    double g = fma((double)k0, unit, rn0);
+                    if (wr < v || g < lbound) {
+                        double w[FRIES_MAX_SUB];
+                        prov.row(i, w);
+                        uint32_t ns = b.nsub[i], kb = b.keep[i];
+                        double sub_lb = lbound - wr;
+                        for (uint32_t j = 0; j < ns; j++) {
+                            if (((kb >> j) & 1u) && w[j] != 0) {
+                                k++;
+                            } else {
+                                sub_lb += v * w[j];
+                                if (g < sub_lb && w[j] != 0) {
+                                    k++;
+                                    k0++;
+                                    g = fma((double)k0, unit, rn0);
+                                    if (g < sub_lb) anomalies++;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            b.kcnt[i] = k;
+            my_out += k;
+        }
+        carry += tot;
+    }
+    my_out = block_sum_u64(my_out, sh_c);
+    double d0, d1;
+    unsigned long long blk_off, tot_out;
+    grid_excl_scan(grid, red, 0.0, my_out, d0, blk_off, d1, tot_out, sh_sd, sh_sc);
+
+    // pass 3: emit
+    unsigned long long ocarry = blk_off;
+    unsigned long long overflow = 0;
+    const double samp_val = G / nrem;  // tmp_glob_norm / n_samp
+    for (size_t base = lo; base < hi; base += blockDim.x) {
+        size_t i = base + threadIdx.x;
+        bool act = i < hi;
+        uint32_t k = act ? b.kcnt[i] : 0;
+        double ex, tot;
+        unsigned long long ec, tc;
+        block_excl_scan(0.0, (unsigned long long)k, ex, ec, tot, tc, sh_sd, sh_sc);
+        if (act && k > 0) {
+            unsigned long long o = ocarry + ec;
+            double v = b.veff[i];
+            uint32_t nd = b.ndiv[i];
+            double start = b.lb[i];
+            double wr = b.wt_remain[i];
+            double lbound = start + wr;
+#define FR_EMIT(VAL, SUB)                              \
+    do {                                               \
+        if (o < b.out_cap) {                           \
+            b.out_val[o] = (VAL);                      \
+            b.out_widx[o] = (uint32_t)i;               \
+            b.out_sub[o] = (uint32_t)(SUB);             \
+        } else {                                       \
+            overflow++;                                \
+        }                                              \
+        o++;                                           \
+    } while (0)
+            if (nd > 0) {
+                if (b.keep[i]) {
+                    double each = v / nd;
+                    for (uint32_t j = 0; j < nd; j++) FR_EMIT(each, j);
+                } else {
+                    long long k0 = sys_count_below(start, rn0, unit);
+                    for (uint32_t t = 0; t < k; t++) {
+                        double g = fma((double)(k0 + t), unit, rn0);
+                        unsigned long long sub = (unsigned long long)((lbound - g) * nd / v);
+                        if (sub >= nd) {
+                            sub = nd - 1;
+                            anomalies++;
+                        }
+                        FR_EMIT(samp_val, sub);
+                    }
+                }
+            } else {
+                double w[FRIES_MAX_SUB];
+                prov.row(i, w);
+                uint32_t ns = b.nsub[i], kb = b.keep[i];
+                long long k0 = sys_count_below(start, rn0, unit);
+                double g = fma((double)k0, unit, rn0);
+                double sub_lb = lbound - wr;
+                for (uint32_t j = 0; j < ns; j++) {
+                    if (((kb >> j) & 1u) && w[j] != 0) {
+                        FR_EMIT(v * w[j], j);
+                    } else {
+                        sub_lb += v * w[j];
+                        if (g < sub_lb && w[j] != 0) {
+                            FR_EMIT(samp_val, j);
+                            k0++;
+                            g = fma((double)k0, unit, rn0);
+                        }
+                    }
+                }
+            }
+#undef FR_EMIT
+        }
+        ocarry += tc;
+    }
+    overflow = block_sum_u64(overflow, sh_c);
+    anomalies = block_sum_u64(anomalies, sh_c);
+    if (threadIdx.x == 0) {
+        if (overflow) atomicAdd(&b.st->overflow, overflow);
+        if (anomalies) atomicAdd(&b.st->anomalies, anomalies);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        b.st->loc_norm = loc_final;
+        b.st->glob_norm = s;
+        b.st->n_samp_left = nrem;
+        b.st->rounds = rounds;
+        b.st->n_kept = kept_total;
+        b.st->n_out = tot_out < b.out_cap ? tot_out : b.out_cap;
+        b.st->n_in = n;
+    }
+}

@@ -1,0 +1,89 @@
+// Device-resident determinant store (a2/a3): dense SoA storage + open-addressing index keyed by the
+// reference's det_hash.
+//
+// Layout in HBM (capacity C, n_vecs value rows, table size T = 2^k >= 2C):
+//   keys  u64[C]            determinant bit strings in storage order (DistVec::indices_)
+//   vals  f64[n_vecs][C]    value rows (DistVec::values_)
+//   diag  f64[C]            cached diagonal matrix elements, NaN = not yet computed (DistVec::matr_el_)
+//   tkeys u64[T], tpos u32[T]   linear-probing index: slot = hash_fxn(occ; vec_scrambler) & (T-1)
+// keys/vals/diag are double-buffered: deletion is a stable stream compaction into the other buffer
+// followed by a rebuild of the index (no tombstones).
+#pragma once
+#include "common.cuh"
+
+struct VecCounters {
+    unsigned long long n;               // curr_size
+    unsigned long long nonini_occ_add;  // DistVec::nonini_occ_add
+    unsigned long long overflow;        // insertions refused because the store is full
+    unsigned long long n_spawn_valid;   // elements seen by the last merge
+};
+
+struct VecView {
+    uint64_t *keys;
+    double *vals;  // row r at vals + r * cap
+    double *diag;
+    uint64_t *tkeys;
+    uint32_t *tpos;
+    uint64_t tmask;
+    size_t cap;
+    unsigned n_vecs;
+    const uint32_t *scr_vec;   // device, 64 entries
+    const uint32_t *scr_proc;  // device, 64 entries
+    VecCounters *cnt;
+};
+
+struct fries_vec {
+    fries_ctx *ctx = nullptr;
+    size_t cap = 0, tsize = 0;
+    unsigned n_bits = 0, n_elec = 0, n_vecs = 0;
+    int n_ranks = 1, rank = 0;
+    DevBuf<uint64_t> keys[2];
+    DevBuf<double> vals[2];
+    DevBuf<double> diag[2];
+    int cur = 0;
+    DevBuf<uint64_t> tkeys;
+    DevBuf<uint32_t> tpos;
+    DevBuf<uint32_t> scr;  // [0..63] vec scrambler, [64..127] proc scrambler
+    DevBuf<VecCounters> cnt;
+    DevBuf<uint32_t> slot_scratch;
+    DevBuf<double> red_d;               // reduction partials
+    DevBuf<unsigned long long> red_c;
+    size_t min_del_idx = 0;
+    fries_mol *diag_mol = nullptr;
+    double hf_en = 0;
+    uint64_t last_spawned = 0;
+    std::vector<uint32_t> h_scr_vec, h_scr_proc;
+
+    VecView view() {
+        VecView v;
+        v.keys = keys[cur].p;
+        v.vals = vals[cur].p;
+        v.diag = diag[cur].p;
+        v.tkeys = tkeys.p;
+        v.tpos = tpos.p;
+        v.tmask = tsize - 1;
+        v.cap = cap;
+        v.n_vecs = n_vecs;
+        v.scr_vec = scr.p;
+        v.scr_proc = scr.p + 64;
+        v.cnt = cnt.p;
+        return v;
+    }
+    int read_counters(VecCounters *out);
+};
+
+// find the storage position of `key` (flag bit already stripped); FRIES_NO_POS if absent.
+// HashTable::read(create = false) det_hash.hpp:60-94
+__device__ __forceinline__ uint32_t vec_lookup(const VecView &v, uint64_t key, const uint32_t *s_scr) {
+    uint64_t slot = fr_det_hash(key, s_scr) & v.tmask;
+    while (true) {
+        uint64_t cur = v.tkeys[slot];
+        if (cur == key) return v.tpos[slot];
+        if (cur == FRIES_EMPTY_KEY) return FRIES_NO_POS;
+        slot = (slot + 1) & v.tmask;
+    }
+}
+
+int fries_vec_merge_dev(fries_vec *vec, const uint64_t *d_keys, const double *d_vals, size_t n_max,
+                        const unsigned long long *d_n, unsigned origin, unsigned dest);
+int fries_vec_compact_dev(fries_vec *vec);

@@ -1,0 +1,219 @@
+/* fries_b200 -- C-ABI of the B200-native FRI hot path.
+ *
+ * This header is the drop-in boundary.  The reference (sgreene8/FRIES) has no
+ * FFI: its boundary is the C++ header API of libfries plus three `extern "C"` C units
+ * (FRIES/fci_utils.h, FRIES/det_store.h, FRIES/math_utils.h).  Every entry point below replaces
+ * one reference function (cited file:line, relative to the reference root); INTEGRATION.md shows
+ * the C++ shim a maintainer adds under the reference's own signatures.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns FRIES_OK (0) or a negative error code and
+ *    never throws; fries_last_error() returns the message of the last failure on this thread.
+ *  - a Slater determinant is one uint64_t "key": bit i = spin-orbital i occupied, i.e. the
+ *    little-endian load of the reference's uint8_t bit string (FRIES/det_store.h:23-26).  All
+ *    configurations in scope need <= 52 bits; bit 63 is reserved for the initiator flag that the
+ *    reference stores at bit n_bits of its Adder buffers (FRIES/vec_utils.hpp:965-967).
+ *  - pointers named h_* are HOST pointers, d_* are DEVICE pointers (cuda:device of the context).
+ *    Functions without a _dev suffix take host buffers and do their own host<->device copies (they
+ *    are the reference-facing calls); *_dev functions work on resident HBM buffers, asynchronously
+ *    on the context's stream.
+ *  - there is NO CPU fallback: every entry point fails with FRIES_ERR_CUDA when no sm_100 device is
+ *    usable.
+ */
+#ifndef FRIES_B200_H
+#define FRIES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRIES_OK 0
+#define FRIES_ERR_ARG (-1)
+#define FRIES_ERR_CUDA (-2)
+#define FRIES_ERR_CAPACITY (-3)
+#define FRIES_ERR_STATE (-4)
+
+#define FRIES_INI_FLAG (1ull << 63)
+#define FRIES_MAX_ELEC 32
+#define FRIES_MAX_SUB 32
+
+typedef struct fries_ctx fries_ctx;   /* device, stream, workspace */
+typedef struct fries_vec fries_vec;   /* device-resident DistVec<double> (FRIES/vec_utils.hpp:121-953) */
+typedef struct fries_mol fries_mol;   /* integrals, symmetry and HB-PP tables in HBM */
+typedef struct fries_hbpp fries_hbpp; /* HBCompressSys scratch (heat_bathPP.hpp:279-297) in HBM */
+
+const char *fries_last_error(void);
+int fries_version(void);
+
+/* ---- context ----------------------------------------------------------------------------------- */
+int fries_ctx_create(int device, fries_ctx **out);
+int fries_ctx_destroy(fries_ctx *ctx);
+/* run on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
+int fries_ctx_set_stream(fries_ctx *ctx, void *cuda_stream);
+int fries_ctx_sync(fries_ctx *ctx);
+int fries_ctx_sm_count(fries_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t fries_ctx_launch_count(fries_ctx *ctx);
+/* elapsed ms between two internal CUDA events recorded around the LAST call of the named kernel
+ * family when profiling is on (fries_ctx_set_profile).  name: "comp_sub", "merge", ... */
+int fries_ctx_set_profile(fries_ctx *ctx, int on);
+int fries_ctx_kernel_ms(fries_ctx *ctx, const char *name, double *total_ms, uint64_t *launches);
+
+/* ---- a1: hash and owner ---------------------------------------------------------------------------
+ * HashTable::hash_fxn FRIES/det_hash.hpp:160-170; DistVec::idx_to_proc FRIES/vec_utils.hpp:360-379;
+ * idx_to_hash :389-400.  scrambler has n_bits uint32 entries. d_hash / d_owner may be NULL. */
+int fries_hash_owner(fries_ctx *ctx, const uint64_t *h_keys, size_t n, const uint32_t *h_scrambler, int n_bits,
+                     int n_ranks, uint64_t *h_hash, int32_t *h_owner);
+int fries_hash_owner_dev(fries_ctx *ctx, const uint64_t *d_keys, size_t n, const uint32_t *h_scrambler, int n_bits,
+                         int n_ranks, uint64_t *d_hash, int32_t *d_owner);
+
+/* ---- a15: bit-string utilities (batch, one thread per item) ---------------------------------------
+ * op 0: sing_det_parity FRIES/fci_utils.c:46-51   (orbs n x 2; keys updated, sign out)
+ * op 1: doub_det_parity FRIES/fci_utils.c:67-75   (orbs n x 4; keys updated, sign out)
+ * op 2: sing_parity     FRIES/fci_utils.c:54-57   (keys unchanged)
+ * op 3: doub_parity     FRIES/fci_utils.c:86-94   (keys unchanged)
+ * op 4: bits_between    FRIES/math_utils.c:9-58   (orbs n x 2 = (a,b); result in sign) */
+int fries_bit_op(fries_ctx *ctx, int op, uint64_t *h_keys, const uint8_t *h_orbs, size_t n, int32_t *h_sign);
+
+/* ---- a4/a5: vector compression -----------------------------------------------------------------------
+ * find_preserve FRIES/compress_utils.cpp:29-105.  n_ranks/rank describe the position of this shard;
+ * with n_ranks == 1 no collective is used.  *n_samp in: budget, out: budget left.  keep: 0/1 bytes.
+ * Returns local residual one-norm in *loc_norm and the global one-norm in *glob_norm. */
+int fries_find_preserve(fries_ctx *ctx, const double *h_values, size_t count, unsigned *n_samp, double *glob_norm,
+                        uint8_t *h_keep, double *loc_norm);
+/* sys_comp FRIES/compress_utils.cpp:278-327 (+ seed_sys :107-127).  loc_norms[n_ranks] in/out,
+ * keep in: preserved flags, out: 1 = zeroed element ("delete me"). */
+int fries_sys_comp(fries_ctx *ctx, double *h_values, size_t count, double *loc_norms, int n_ranks, int rank,
+                   unsigned n_samp, uint8_t *h_keep, double rand_num);
+/* device-resident variants; d_result receives {loc_norm, glob_norm, (double)n_samp_left, n_kept} */
+int fries_find_preserve_dev(fries_ctx *ctx, const double *d_values, size_t count, unsigned n_samp, uint8_t *d_keep,
+                            double *d_result4);
+int fries_sys_comp_dev(fries_ctx *ctx, double *d_values, size_t count, const double *d_result4, uint8_t *d_keep,
+                       double rand_num, double *d_new_norm);
+
+/* ---- a6: hierarchical compression with explicit sub-weights -----------------------------------------
+ * comp_sub FRIES/compress_utils.cpp:797-820 = find_keep_sub :130-276 + sys_sub :702-794.
+ * sub_weights row-major count x n_sub (n_sub <= FRIES_MAX_SUB); sub_sizes may be NULL.
+ * new_idx is [n_out][2] uint64 (weight index, sub index) as in the reference. */
+int fries_comp_sub(fries_ctx *ctx, const double *h_values, size_t count, const uint32_t *h_ndiv,
+                   const double *h_sub_weights, size_t n_sub, const uint16_t *h_sub_sizes, unsigned n_samp,
+                   double rand_num, double *h_new_vals, uint64_t *h_new_idx, size_t out_cap, size_t *n_out,
+                   unsigned *n_samp_left, double *loc_norm);
+
+/* ---- molecular Hamiltonian tables -------------------------------------------------------------------
+ * n_orb: unfrozen spatial orbitals; n_elec: TOTAL electrons; n_frz: frozen electrons;
+ * h_hcore: (n_orb+n_frz/2)^2; h_eris_packed: SymmERIs layout FRIES/ndarr.hpp:206-244 over
+ * tot_orb = n_orb + n_frz/2 orbitals; h_symm: irreps (0..7) of the n_orb unfrozen orbitals.
+ * Builds SymmInfo (FRIES/Hamiltonians/molecule.hpp:265-280) and the HB-PP tables of set_up
+ * (FRIES/Hamiltonians/heat_bathPP.cpp:99-179) on the device. */
+int fries_mol_create(fries_ctx *ctx, unsigned n_orb, unsigned n_elec, unsigned n_frz, const double *h_hcore,
+                     const double *h_eris_packed, const uint8_t *h_symm, fries_mol **out);
+int fries_mol_destroy(fries_mol *mol);
+/* hb_info tables (heat_bathPP.hpp:25-34); any pointer may be NULL */
+int fries_mol_hb_tables(fries_mol *mol, double *h_d_diff, double *h_d_same, double *h_s_tens, double *h_s_norm,
+                        double *h_exch_sqrt, double *h_diag_sqrt, double *h_exch_norms);
+/* a12: diag_matrel FRIES/Hamiltonians/molecule.cpp:983-1029 */
+int fries_mol_diag(fries_mol *mol, const uint64_t *h_keys, size_t n, double *h_out);
+/* a13: sing_matr_el_nosgn molecule.cpp:76-105 (orbs n x 2), doub_matr_el_nosgn :26-42 (orbs n x 4) */
+int fries_mol_sing_el(fries_mol *mol, const uint64_t *h_keys, const uint8_t *h_orbs, size_t n, double *h_out);
+int fries_mol_doub_el(fries_mol *mol, const uint8_t *h_orbs, size_t n, double *h_out);
+/* a14: sing_ex_symm molecule.cpp:178-203 / doub_ex_symm :108-175 for n determinants, in the
+ * reference's enumeration order.  h_offsets[n+1] receives the start of each determinant's list in
+ * h_orbs (n_ex x 2 or x 4).  Pass h_orbs == NULL to only count. */
+int fries_mol_sing_ex(fries_mol *mol, const uint64_t *h_keys, size_t n, uint64_t *h_offsets, uint8_t *h_orbs,
+                      size_t cap);
+int fries_mol_doub_ex(fries_mol *mol, const uint64_t *h_keys, size_t n, uint64_t *h_offsets, uint8_t *h_orbs,
+                      size_t cap);
+/* a8/a9: HB-PP weight rows (heat_bathPP.cpp:182-412) and total weights (:414-598), one item per
+ * call row; `which` 0 o1 (a0 = exclude_first), 1 o2 (a0 = o1_idx), 2 o2_half (a0 = o1_idx),
+ * 3 u1 (a0 = o1_orb, a1 = exclude_first), 4 u2 (a0,a1,a2 = o1,o2,u1 orbitals), 5 u2_half (same).
+ * h_rows is n x FRIES_MAX_SUB, h_len / h_norm have n entries. */
+int fries_mol_hb_rows(fries_mol *mol, int which, const uint64_t *h_keys, const int32_t *h_args4, size_t n,
+                      double *h_rows, int32_t *h_len, double *h_norm);
+int fries_mol_hb_wt(fries_mol *mol, int normalized, const uint64_t *h_keys, const uint8_t *h_orbs, size_t n,
+                    double *h_out);
+
+/* ---- a10: apply_HBPP_sys FRIES/Hamiltonians/heat_bathPP.cpp:686-992 -----------------------------------
+ * Host-buffer form: determinants + weights in, compressed Hamiltonian samples out, driven by the 5
+ * uniforms the reference draws from mt19937 (:728,764,810,858,909).  spawn_cap = capacity of the
+ * scratch (reference: spawn_length).  Outputs in the reference's order. */
+int fries_apply_hbpp_sys(fries_mol *mol, const uint64_t *h_keys, const double *h_vals, size_t n, double p_doub,
+                         int new_hb, const double *h_uniforms5, unsigned n_samp, size_t spawn_cap, double *h_out_val,
+                         uint64_t *h_out_det, uint8_t *h_out_orbs, size_t out_cap, size_t *n_out);
+
+/* ---- a2/a3: the determinant store ---------------------------------------------------------------------
+ * DistVec<double> ctor FRIES/vec_utils.hpp:154-198: capacity, n_bits (= 2 n_orb), n_elec, n_vecs rows,
+ * proc_scrambler / vec_scrambler (n_bits uint32 each). */
+int fries_vec_create(fries_ctx *ctx, size_t capacity, unsigned n_bits, unsigned n_elec, unsigned n_vecs,
+                     const uint32_t *h_proc_scrambler, const uint32_t *h_vec_scrambler, int n_ranks, int rank,
+                     fries_vec **out);
+int fries_vec_destroy(fries_vec *vec);
+/* DistVec::add + perform_add(origin) with curr_vec_idx = dest (vec_utils.hpp:418-440,606-641,991-1019)
+ * for elements this rank owns.  ini flags: 0/1 bytes.  Elements are merged on the device. */
+int fries_vec_add(fries_vec *vec, const uint64_t *h_keys, const double *h_vals, const uint8_t *h_ini, size_t n,
+                  unsigned origin, unsigned dest);
+/* same with resident spawn buffers: d_keys carry FRIES_INI_FLAG in bit 63; key == ~0 is skipped */
+int fries_vec_add_dev(fries_vec *vec, const uint64_t *d_keys, const double *d_vals, size_t n, const uint32_t *d_n,
+                      unsigned origin, unsigned dest);
+int fries_vec_curr_size(fries_vec *vec, size_t *curr_size);
+int fries_vec_n_nonz(fries_vec *vec, size_t *n_nonz);               /* DistVec::n_nonz */
+int fries_vec_nonini_occ_add(fries_vec *vec, uint64_t *count);      /* DistVec::tot_sgn_coh :546-551 */
+/* copy out storage: keys[curr_size], vals[n_vecs][curr_size] (row-major with row stride curr_size) */
+int fries_vec_download(fries_vec *vec, uint64_t *h_keys, double *h_vals, size_t cap, size_t *n);
+/* DistVec::del_at_pos :458-476 for all flagged positions, followed by compaction of the storage
+ * (stable) and a rebuild of the hash index */
+int fries_vec_del(fries_vec *vec, const uint8_t *h_flags, size_t n);
+/* DistVec::dot :228-238 against a (replicated) trial vector */
+int fries_vec_dot(fries_vec *vec, const uint64_t *h_keys, const double *h_vals, size_t n, unsigned row, double *out);
+/* DistVec::local_norm :683-689 of a row */
+int fries_vec_local_norm(fries_vec *vec, unsigned row, double *out);
+int fries_vec_set_diag_mol(fries_vec *vec, fries_mol *mol, double hf_en); /* diag_calc_ = diag_matrel - hf_en */
+
+/* ---- a16: deterministic H.v (h_op_diag molecule.cpp:205-219 + h_op_offdiag :448-665) ---------------------
+ * row dest <- id_fac * row src + h_fac * H * row src, for all elements of the store. */
+int fries_h_apply(fries_vec *vec, fries_mol *mol, unsigned src, unsigned dest, double id_fac, double h_fac);
+/* number of off-diagonal elements generated by the last fries_h_apply (the spawned H.v elements) */
+int fries_h_apply_last_spawned(fries_vec *vec, uint64_t *n_spawned);
+
+/* ---- a17/a18 + drivers: one FRI iteration ---------------------------------------------------------------
+ * frisys_mol loop body FRIES_bin/frisys_mol.cpp:405-552 (steps 1-11 of SURVEY.md 3.1) on resident
+ * state.  uniforms6 = the 5 draws of apply_HBPP_sys followed by the vector-compression draw. */
+typedef struct {
+    double eps;          /* --epsilon */
+    double init_thresh;  /* --initiator */
+    double p_doub;       /* frisys_mol.cpp:217-220 */
+    int new_hb;          /* --distribution HB_unnorm */
+    unsigned matr_samp;  /* --mat_nonz */
+    unsigned target_nonz;/* --vec_nonz */
+    double en_shift;     /* current shift S */
+} fries_frisys_params;
+typedef struct {
+    double glob_norm;    /* one-norm before compression (frisys_mol.cpp:503-504) */
+    double numer, denom; /* projected energy pieces (:517-520) */
+    uint64_t n_kept;     /* target_nonz - n_samp after find_preserve (:506) */
+    uint64_t n_matrix_samples; /* comp_len after apply_HBPP_sys (:422) */
+    uint64_t n_spawned;  /* elements handed to DistVec::add (:461) */
+    uint64_t curr_size;  /* stored elements after the iteration */
+} fries_iter_stats;
+int fries_frisys_mol_setup(fries_vec *vec, fries_mol *mol, size_t spawn_cap, const uint64_t *h_trial_keys,
+                           const double *h_trial_vals, size_t n_trial, const uint64_t *h_htrial_keys,
+                           const double *h_htrial_vals, size_t n_htrial, fries_hbpp **out);
+int fries_hbpp_destroy(fries_hbpp *hb);
+int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
+                             const double *h_uniforms6, fries_iter_stats *stats);
+/* frifull_mol loop body FRIES_bin/frifull_mol.cpp:256-320 */
+typedef struct {
+    double eps;
+    unsigned target_nonz;
+    double en_shift;
+} fries_frifull_params;
+int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frifull_params *p,
+                              double uniform, fries_iter_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRIES_B200_H */
