@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference interfaces on top of the C-ABI (numpy host buffers in, numpy out).
+
+Names follow the reference: DistVec -> Vec (FRIES/vec_utils.hpp), find_preserve / sys_comp / comp_sub
+(FRIES/compress_utils.hpp), molecule + heat_bathPP routines -> Mol methods.  Every call goes to the CUDA
+library; nothing is computed in Python."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._capi import (FrifullParams, FrisysParams, IterStats, MAX_SUB, arr, check, lib, ptr)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        check(lib.fries_ctx_create(device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib.fries_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(lib.fries_ctx_sync(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.fries_ctx_launch_count(self.h))
+
+    @property
+    def sm_count(self) -> int:
+        return int(lib.fries_ctx_sm_count(self.h))
+
+    def set_profile(self, on: int):
+        check(lib.fries_ctx_set_profile(self.h, on))
+
+    def kernel_ms(self, name: str):
+        ms, n = C.c_double(0), C.c_uint64(0)
+        check(lib.fries_ctx_kernel_ms(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+# ---- a1 / a15 --------------------------------------------------------------------------------------------
+def hash_owner(ctx, keys, scrambler, n_ranks=1):
+    """HashTable::hash_fxn + DistVec::idx_to_proc (det_hash.hpp:160-170, vec_utils.hpp:360-379)."""
+    keys = arr(keys, np.uint64)
+    scr = arr(scrambler, np.uint32)
+    h = np.zeros(keys.size, np.uint64)
+    o = np.zeros(keys.size, np.int32)
+    check(lib.fries_hash_owner(ctx.h, ptr(keys), keys.size, ptr(scr), scr.size, n_ranks, ptr(h), ptr(o)))
+    return h, o
+
+
+def bit_op(ctx, op, keys, orbs):
+    keys = np.array(keys, np.uint64)
+    orbs = arr(orbs, np.uint8)
+    sign = np.zeros(keys.size, np.int32)
+    check(lib.fries_bit_op(ctx.h, op, ptr(keys), ptr(orbs), keys.size, ptr(sign)))
+    return keys, sign
+
+
+# ---- a4 / a5 / a6 ------------------------------------------------------------------------------------------
+def find_preserve(ctx, values, n_samp):
+    """compress_utils.cpp:29-105 -> (loc_norm, glob_norm, n_samp_left, keep[0/1])"""
+    v = arr(values, np.float64)
+    keep = np.zeros(v.size, np.uint8)
+    ns, gn, ln = C.c_uint(n_samp), C.c_double(0), C.c_double(0)
+    check(lib.fries_find_preserve(ctx.h, ptr(v), v.size, C.byref(ns), C.byref(gn), ptr(keep), C.byref(ln)))
+    return ln.value, gn.value, ns.value, keep
+
+
+def sys_comp(ctx, values, loc_norms, n_samp, keep, rand_num, n_ranks=1, rank=0):
+    """compress_utils.cpp:278-327 -> (values, delete flags, loc_norms)"""
+    v = np.array(values, np.float64)
+    k = np.array(keep, np.uint8)
+    ln = np.array(np.atleast_1d(loc_norms), np.float64)
+    check(lib.fries_sys_comp(ctx.h, ptr(v), v.size, ptr(ln), n_ranks, rank, n_samp, ptr(k), rand_num))
+    return v, k, ln
+
+
+def comp_sub(ctx, values, n_div, sub_weights, sub_sizes, n_samp, rand_num, out_cap):
+    """compress_utils.cpp:797-820 -> (new_vals, new_idx[n][2], n_samp_left, loc_norm)"""
+    v = arr(values, np.float64)
+    nd = arr(n_div, np.uint32)
+    sw = arr(sub_weights, np.float64)
+    ss = None if sub_sizes is None else arr(sub_sizes, np.uint16)
+    nv = np.zeros(out_cap)
+    ni = np.zeros((out_cap, 2), np.uint64)
+    n_out, left, ln = C.c_size_t(0), C.c_uint(0), C.c_double(0)
+    check(lib.fries_comp_sub(ctx.h, ptr(v), v.size, ptr(nd), ptr(sw), sw.shape[1], ptr(ss), n_samp, rand_num, ptr(nv),
+                             ptr(ni), out_cap, C.byref(n_out), C.byref(left), C.byref(ln)))
+    return nv[:n_out.value].copy(), ni[:n_out.value].copy(), left.value, ln.value
+
+
+# ---- molecular Hamiltonian ----------------------------------------------------------------------------------
+class Mol:
+    """Integrals + SymmInfo + hb_info resident on the GPU (molecule.hpp, heat_bathPP.hpp)."""
+
+    def __init__(self, ctx, n_orb, n_elec_total, n_frz, hcore, eris_packed, symm):
+        self.ctx = ctx
+        self.n_orb, self.n_elec_total, self.n_frz = n_orb, n_elec_total, n_frz
+        self.n_elec = n_elec_total - n_frz
+        hc, er, sy = arr(hcore, np.float64), arr(eris_packed, np.float64), arr(symm, np.uint8)
+        h = C.c_void_p()
+        check(lib.fries_mol_create(ctx.h, n_orb, n_elec_total, n_frz, ptr(hc), ptr(er), ptr(sy), C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_synth(cls, ctx, sm):
+        return cls(ctx, sm.n_orb, sm.n_elec_total, sm.n_frz, sm.hcore, sm.eris_packed, sm.symm)
+
+    def close(self):
+        if self.h:
+            lib.fries_mol_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def hb_tables(self):
+        M = self.n_orb
+        T = M * (M - 1) // 2
+        out = dict(d_diff=np.zeros(M * M), d_same=np.zeros(T), s_tens=np.zeros(M), s_norm=np.zeros(1),
+                   exch_sqrt=np.zeros(T), diag_sqrt=np.zeros(M), exch_norms=np.zeros(M))
+        check(lib.fries_mol_hb_tables(self.h, *[ptr(out[k]) for k in ("d_diff", "d_same", "s_tens", "s_norm", "exch_sqrt",
+                                                                       "diag_sqrt", "exch_norms")]))
+        return out
+
+    def diag(self, keys):
+        k = arr(keys, np.uint64)
+        out = np.zeros(k.size)
+        check(lib.fries_mol_diag(self.h, ptr(k), k.size, ptr(out)))
+        return out
+
+    def sing_el(self, keys, orbs):
+        k, o = arr(keys, np.uint64), arr(orbs, np.uint8)
+        out = np.zeros(k.size)
+        check(lib.fries_mol_sing_el(self.h, ptr(k), ptr(o), k.size, ptr(out)))
+        return out
+
+    def doub_el(self, orbs):
+        o = arr(orbs, np.uint8)
+        out = np.zeros(len(o))
+        check(lib.fries_mol_doub_el(self.h, ptr(o), len(o), ptr(out)))
+        return out
+
+    def _ex(self, fn, width, keys):
+        k = arr(keys, np.uint64)
+        off = np.zeros(k.size + 1, np.uint64)
+        check(fn(self.h, ptr(k), k.size, ptr(off), None, 0))
+        tot = int(off[-1])
+        orbs = np.zeros((max(tot, 1), width), np.uint8)
+        check(fn(self.h, ptr(k), k.size, ptr(off), ptr(orbs), tot))
+        return off, orbs[:tot]
+
+    def sing_ex(self, keys):
+        return self._ex(lib.fries_mol_sing_ex, 2, keys)
+
+    def doub_ex(self, keys):
+        return self._ex(lib.fries_mol_doub_ex, 4, keys)
+
+    def hb_rows(self, which, keys, args4):
+        k, a = arr(keys, np.uint64), arr(args4, np.int32)
+        rows = np.zeros((k.size, MAX_SUB))
+        ln = np.zeros(k.size, np.int32)
+        nm = np.zeros(k.size)
+        check(lib.fries_mol_hb_rows(self.h, which, ptr(k), ptr(a), k.size, ptr(rows), ptr(ln), ptr(nm)))
+        return rows, ln, nm
+
+    def hb_wt(self, normalized, keys, orbs):
+        k, o = arr(keys, np.uint64), arr(orbs, np.uint8)
+        out = np.zeros(k.size)
+        check(lib.fries_mol_hb_wt(self.h, int(normalized), ptr(k), ptr(o), k.size, ptr(out)))
+        return out
+
+    def apply_hbpp_sys(self, keys, vals, p_doub, new_hb, uniforms5, n_samp, spawn_cap):
+        """apply_HBPP_sys heat_bathPP.cpp:686-992 -> (vals, parent index, orbs[n][4])"""
+        k, v, u = arr(keys, np.uint64), arr(vals, np.float64), arr(uniforms5, np.float64)
+        ov = np.zeros(spawn_cap)
+        od = np.zeros(spawn_cap, np.uint64)
+        oo = np.zeros((spawn_cap, 4), np.uint8)
+        n = C.c_size_t(0)
+        check(lib.fries_apply_hbpp_sys(self.h, ptr(k), ptr(v), k.size, p_doub, int(new_hb), ptr(u), n_samp, spawn_cap,
+                                       ptr(ov), ptr(od), ptr(oo), spawn_cap, C.byref(n)))
+        return ov[:n.value].copy(), od[:n.value].copy(), oo[:n.value].copy()
+
+
+# ---- determinant store ----------------------------------------------------------------------------------------
+class Vec:
+    """DistVec<double> (FRIES/vec_utils.hpp:121-953) resident on one GPU."""
+
+    def __init__(self, ctx, capacity, n_bits, n_elec, n_vecs, proc_scrambler, vec_scrambler, n_ranks=1, rank=0):
+        self.ctx, self.capacity, self.n_bits, self.n_elec, self.n_vecs = ctx, capacity, n_bits, n_elec, n_vecs
+        ps, vs = arr(proc_scrambler, np.uint32), arr(vec_scrambler, np.uint32)
+        h = C.c_void_p()
+        check(lib.fries_vec_create(ctx.h, capacity, n_bits, n_elec, n_vecs, ptr(ps), ptr(vs), n_ranks, rank, C.byref(h)))
+        self.h = h
+        self.hb = None
+
+    def close(self):
+        if getattr(self, "hb", None):
+            lib.fries_hbpp_destroy(self.hb)
+            self.hb = None
+        if self.h:
+            lib.fries_vec_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add(self, keys, vals, ini, origin=0, dest=0):
+        """DistVec::add x n + perform_add(origin) with curr_vec_idx = dest"""
+        k, v, f = arr(keys, np.uint64), arr(vals, np.float64), arr(ini, np.uint8)
+        check(lib.fries_vec_add(self.h, ptr(k), ptr(v), ptr(f), k.size, origin, dest))
+
+    def curr_size(self) -> int:
+        n = C.c_size_t(0)
+        check(lib.fries_vec_curr_size(self.h, C.byref(n)))
+        return n.value
+
+    def nonini_occ_add(self) -> int:
+        n = C.c_uint64(0)
+        check(lib.fries_vec_nonini_occ_add(self.h, C.byref(n)))
+        return n.value
+
+    def download(self):
+        n = self.curr_size()
+        keys = np.zeros(max(n, 1), np.uint64)
+        vals = np.zeros((self.n_vecs, max(n, 1)))
+        m = C.c_size_t(0)
+        check(lib.fries_vec_download(self.h, ptr(keys), ptr(vals), max(n, 1), C.byref(m)))
+        return keys[:n], vals[:, :n]
+
+    def delete(self, flags):
+        f = arr(flags, np.uint8)
+        check(lib.fries_vec_del(self.h, ptr(f), f.size))
+
+    def dot(self, keys, vals, row=0) -> float:
+        k, v = arr(keys, np.uint64), arr(vals, np.float64)
+        out = C.c_double(0)
+        check(lib.fries_vec_dot(self.h, ptr(k), ptr(v), k.size, row, C.byref(out)))
+        return out.value
+
+    def local_norm(self, row=0) -> float:
+        out = C.c_double(0)
+        check(lib.fries_vec_local_norm(self.h, row, C.byref(out)))
+        return out.value
+
+    def set_diag_mol(self, mol, hf_en):
+        check(lib.fries_vec_set_diag_mol(self.h, mol.h, hf_en))
+
+    def h_apply(self, mol, src, dest, id_fac, h_fac) -> int:
+        """h_op_diag + h_op_offdiag (molecule.cpp:205-219, 448-665); returns the number of spawned elements"""
+        check(lib.fries_h_apply(self.h, mol.h, src, dest, id_fac, h_fac))
+        n = C.c_uint64(0)
+        check(lib.fries_h_apply_last_spawned(self.h, C.byref(n)))
+        return n.value
+
+    # ---- drivers' loop bodies ----
+    def frisys_setup(self, mol, spawn_cap, trial_keys, trial_vals, htrial_keys, htrial_vals):
+        tk, tv = arr(trial_keys, np.uint64), arr(trial_vals, np.float64)
+        hk, hv = arr(htrial_keys, np.uint64), arr(htrial_vals, np.float64)
+        h = C.c_void_p()
+        check(lib.fries_frisys_mol_setup(self.h, mol.h, spawn_cap, ptr(tk), ptr(tv), tk.size, ptr(hk), ptr(hv), hk.size,
+                                         C.byref(h)))
+        self.hb = h
+        self.mol = mol
+
+    def frisys_iterate(self, params: FrisysParams, uniforms6) -> IterStats:
+        u = arr(uniforms6, np.float64)
+        st = IterStats()
+        check(lib.fries_frisys_mol_iterate(self.h, self.mol.h, self.hb, C.byref(params), ptr(u), C.byref(st)))
+        return st
+
+    def frifull_iterate(self, params: FrifullParams, uniform: float) -> IterStats:
+        st = IterStats()
+        check(lib.fries_frifull_mol_iterate(self.h, self.mol.h, self.hb, C.byref(params), uniform, C.byref(st)))
+        return st

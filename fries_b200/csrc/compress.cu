@@ -8,9 +8,14 @@
 // Traffic per round: 8 B/element (values; keep flags are 1 B and stay in L2).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FR_COMP_BLOCK)
-find_preserve_kernel(const double *__restrict__ vals, size_t n, unsigned n_samp_in, uint8_t *__restrict__ keep,
-                     double *part_d, unsigned long long *part_c, CompState *st) {
+find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned long long *__restrict__ n_ptr,
+                     unsigned n_samp_in, uint8_t *__restrict__ keep, double *part_d, unsigned long long *part_c,
+                     CompState *st) {
     cg::grid_group grid = cg::this_grid();
+    if (n_ptr) {  // resident pipeline: the element count lives on the device
+        unsigned long long dn = *n_ptr;
+        if (dn < n) n = (size_t)dn;
+    }
     __shared__ double sh_d[34];
     __shared__ unsigned long long sh_c[34];
     GridRed red{part_d, part_c, 0, (int)gridDim.x, sh_d, sh_c};
@@ -95,10 +100,15 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, unsigned n_samp_
 // systematic grid (seed_sys :107-127).  Traffic: 2 reads + 1 write of 8 B per element.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FR_COMP_BLOCK)
-sys_comp_kernel(double *__restrict__ vals, size_t n, uint8_t *__restrict__ keep, const double *__restrict__ in_r4,
-                double lbound0_host, double glob_host, long long n_samp_host, double rn_uniform, double *part_d,
-                unsigned long long *part_c, CompState *out_st) {
+sys_comp_kernel(double *__restrict__ vals, size_t n, const unsigned long long *__restrict__ n_ptr,
+                uint8_t *__restrict__ keep, const double *__restrict__ in_r4, double lbound0_host, double glob_host,
+                long long n_samp_host, double rn_uniform, double *part_d, unsigned long long *part_c,
+                CompState *out_st) {
     cg::grid_group grid = cg::this_grid();
+    if (n_ptr) {
+        unsigned long long dn = *n_ptr;
+        if (dn < n) n = (size_t)dn;
+    }
     __shared__ double sh_d[34];
     __shared__ unsigned long long sh_c[34];
     __shared__ double sh_sd[34];
@@ -236,19 +246,22 @@ __global__ void state_to_result4(const CompState *st, double *r4) {
     r4[3] = (double)st->n_kept;
 }
 
-int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, unsigned n_samp, uint8_t *d_keep,
-                               CompState *d_st, double *pd, unsigned long long *pc, int grid) {
-    void *args[] = {(void *)&d_values, (void *)&count, (void *)&n_samp, (void *)&d_keep, (void *)&pd, (void *)&pc,
-                    (void *)&d_st};
+int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, const unsigned long long *d_n,
+                               unsigned n_samp, uint8_t *d_keep, CompState *d_st, double *pd, unsigned long long *pc,
+                               int grid) {
+    if (grid <= 0) grid = c->coop_grid((const void *)find_preserve_kernel, FR_COMP_BLOCK, 0);
+    void *args[] = {(void *)&d_values, (void *)&count, (void *)&d_n, (void *)&n_samp, (void *)&d_keep, (void *)&pd,
+                    (void *)&pc, (void *)&d_st};
     ProfScope ps(c, "find_preserve");
     return coop_launch(c, (const void *)find_preserve_kernel, grid, args);
 }
 
-int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, uint8_t *d_keep, const double *d_in,
-                          double lbound0, double glob, long long n_samp, double rn, CompState *d_out, double *pd,
-                          unsigned long long *pc, int grid) {
-    void *args[] = {(void *)&d_values, (void *)&count, (void *)&d_keep, (void *)&d_in, (void *)&lbound0, (void *)&glob,
-                    (void *)&n_samp,   (void *)&rn,    (void *)&pd,     (void *)&pc,   (void *)&d_out};
+int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, const unsigned long long *d_n, uint8_t *d_keep,
+                          const double *d_in, double lbound0, double glob, long long n_samp, double rn, CompState *d_out,
+                          double *pd, unsigned long long *pc, int grid) {
+    if (grid <= 0) grid = c->coop_grid((const void *)sys_comp_kernel, FR_COMP_BLOCK, 0);
+    void *args[] = {(void *)&d_values, (void *)&count, (void *)&d_n,  (void *)&d_keep, (void *)&d_in, (void *)&lbound0,
+                    (void *)&glob,     (void *)&n_samp, (void *)&rn,  (void *)&pd,     (void *)&pc,   (void *)&d_out};
     ProfScope ps(c, "sys_comp");
     return coop_launch(c, (const void *)sys_comp_kernel, grid, args);
 }
@@ -266,7 +279,7 @@ extern "C" int fries_find_preserve(fries_ctx *c, const double *h_values, size_t 
     RedScratch r;
     FRIES_TRY(red_scratch(c, grid, 0, r));
     CUDA_TRY(cudaMemcpyAsync(vals.p, h_values, count * 8, cudaMemcpyHostToDevice, c->stream));
-    FRIES_TRY(fries_find_preserve_launch(c, vals.p, count, *n_samp, keep.p, r.st, r.pd, r.pc, grid));
+    FRIES_TRY(fries_find_preserve_launch(c, vals.p, count, nullptr, *n_samp, keep.p, r.st, r.pd, r.pc, grid));
     CompState st;
     CUDA_TRY(cudaMemcpyAsync(&st, r.st, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     if (count) CUDA_TRY(cudaMemcpyAsync(h_keep, keep.p, count, cudaMemcpyDeviceToHost, c->stream));
@@ -295,7 +308,7 @@ extern "C" int fries_sys_comp(fries_ctx *c, double *h_values, size_t count, doub
     for (int p = 0; p < rank; p++) lbound0 += loc_norms[p];
     CUDA_TRY(cudaMemcpyAsync(vals.p, h_values, count * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(keep.p, h_keep, count, cudaMemcpyHostToDevice, c->stream));
-    FRIES_TRY(fries_sys_comp_launch(c, vals.p, count, keep.p, nullptr, lbound0, glob, (long long)n_samp, rand_num,
+    FRIES_TRY(fries_sys_comp_launch(c, vals.p, count, nullptr, keep.p, nullptr, lbound0, glob, (long long)n_samp, rand_num,
                                     r.st + 1, r.pd, r.pc, grid));
     CompState st;
     CUDA_TRY(cudaMemcpyAsync(&st, r.st + 1, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
@@ -315,7 +328,7 @@ extern "C" int fries_find_preserve_dev(fries_ctx *c, const double *d_values, siz
     int grid = c->coop_grid((const void *)find_preserve_kernel, FR_COMP_BLOCK, 0);
     RedScratch r;
     FRIES_TRY(red_scratch(c, grid, 0, r));
-    FRIES_TRY(fries_find_preserve_launch(c, d_values, count, n_samp, d_keep, r.st, r.pd, r.pc, grid));
+    FRIES_TRY(fries_find_preserve_launch(c, d_values, count, nullptr, n_samp, d_keep, r.st, r.pd, r.pc, grid));
     state_to_result4<<<1, 1, 0, c->stream>>>(r.st, d_result4);
     c->launch_count++;
     CUDA_TRY(cudaGetLastError());
@@ -329,7 +342,7 @@ extern "C" int fries_sys_comp_dev(fries_ctx *c, double *d_values, size_t count, 
     int grid = c->coop_grid((const void *)sys_comp_kernel, FR_COMP_BLOCK, 0);
     RedScratch r;
     FRIES_TRY(red_scratch(c, grid, 0, r));
-    FRIES_TRY(fries_sys_comp_launch(c, d_values, count, d_keep, d_result4, 0.0, 0.0, -1LL, rand_num, r.st + 1, r.pd,
+    FRIES_TRY(fries_sys_comp_launch(c, d_values, count, nullptr, d_keep, d_result4, 0.0, 0.0, -1LL, rand_num, r.st + 1, r.pd,
                                     r.pc, grid));
     if (d_new_norm) {
         CUDA_TRY(cudaMemcpyAsync(d_new_norm, &r.st[1].new_norm, 8, cudaMemcpyDeviceToDevice, c->stream));

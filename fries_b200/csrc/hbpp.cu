@@ -1,0 +1,465 @@
+// a10: apply_HBPP_sys (heat_bathPP.cpp:686-992) on the device.  See hbpp.cuh.
+#include "hbpp.cuh"
+
+extern __shared__ double fr_dyn_smem[];
+
+__device__ __forceinline__ uint32_t pk(unsigned p0, unsigned p1, unsigned p2, unsigned p3) {
+    return (p0 & 0xff) | ((p1 & 0xff) << 8) | ((p2 & 0xff) << 16) | ((p3 & 0xff) << 24);
+}
+
+// Provider of stage S of the hierarchy.  prep() restates the per-sample set-up loop that precedes each
+// comp_sub call in apply_HBPP_sys; row() regenerates the sub-weight row the reference stores in subwts.
+template <int S>
+struct HbProvider {
+    MolView m;  // tables in shared memory
+    HbStageIO io;
+
+    __device__ size_t count() const {
+        unsigned long long n = *io.n_in;
+        return n < io.in_cap ? (size_t)n : (size_t)io.in_cap;
+    }
+
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns) const {
+        const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+        if (S == 0) {  // singles vs doubles :713-727
+            double w = fabs(io.vals[i]);
+            v = w;
+            nd = w > 0 ? 0u : 1u;
+            ns = 2;
+            io.det[i] = (uint32_t)i;
+            io.path[i] = 0;
+            return;
+        }
+        const uint32_t widx = io.pw[i], sub = io.ps[i];
+        const uint32_t d = io.pdet[widx], pp = io.ppath[widx];
+        v = io.pv[i];
+        io.det[i] = d;
+        uint8_t occ[FRIES_MAX_ELEC + 1];
+        const uint64_t key = io.keys[d];
+        mol_occ_list(key, occ);
+        unsigned p0 = pp & 0xff, p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
+        double w[FRIES_MAX_SUB];
+        if (S == 1) {  // first occupied orbital :738-763
+            p0 = sub;
+            ns = ne - (io.new_hb ? 1 : 0);
+            if (p0 == 0) {
+                nd = 0;
+                double tot = hb_o1_probs(m, w, occ, io.new_hb);
+                if (io.new_hb) v *= tot;
+            } else {
+                uint8_t cnt[FR_N_IRREPS][2];
+                mol_count_symm_virt(m, occ, cnt);
+                unsigned n_occ = mol_count_sing_allowed(m, occ, cnt);
+                if (n_occ == 0) {
+                    nd = 1;
+                    v = 0;
+                } else {
+                    nd = n_occ;
+                }
+            }
+            io.path[i] = pk(p0, 0, 0, 0);
+        } else if (S == 2) {  // 2nd occupied (double) / virtual count (single) :772-809
+            p1 = sub;
+            ns = ne - (io.new_hb ? 1 : 0);
+            if (p1 >= ne) {
+                v = 0;
+                nd = 1;
+            } else if (p0 == 0) {
+                nd = 0;
+                if (io.new_hb) {
+                    p1++;
+                    ns = p1;
+                    v *= hb_o2_probs_half(m, w, occ, p1);
+                }
+            } else {
+                uint8_t cnt[FR_N_IRREPS][2];
+                mol_count_symm_virt(m, occ, cnt);
+                uint8_t ch = (uint8_t)p1;
+                unsigned n_virt = mol_count_sing_virt(m, occ, cnt, &ch);
+                p1 = ch;
+                if (n_virt == 0) {
+                    nd = 1;
+                    v = 0;
+                } else {
+                    nd = n_virt;
+                    p3 = n_virt;
+                }
+            }
+            io.path[i] = pk(p0, p1, 0, p3);
+        } else if (S == 3) {  // 1st virtual (double) :818-857
+            p2 = sub;
+            ns = M - ne / 2;
+            if (p0 == 0) {
+                if (p2 >= ne) {
+                    v = 0;
+                    nd = 1;
+                } else {
+                    nd = 0;
+                    int o1_spin = p1 / (ne / 2), o2_spin = occ[p2] / M;
+                    double tot = hb_u1_probs(m, w, occ[p1], occ, io.new_hb && (o1_spin == o2_spin));
+                    if (io.new_hb) v *= tot;
+                }
+                p3 = 0;
+            } else {
+                nd = 1;
+            }
+            io.path[i] = pk(p0, p1, p2, p3);
+        } else {  // S == 4: 2nd virtual (double) :866-908
+            ns = m.d.max_n_symm;
+            if (p0 == 0) {
+                unsigned u1 = mol_find_nth_virt(occ, p1 / (ne / 2), ne, M, sub);
+                if (u1 >= 2 * M || fr_read_bit(key, u1)) {
+                    v = 0;
+                    nd = 1;
+                } else {
+                    nd = 0;
+                    p3 = u1;
+                    unsigned len;
+                    double tot = io.new_hb ? hb_u2_probs_half(m, w, occ[p1], occ[p2], u1, key, &len)
+                                           : hb_u2_probs(m, w, occ[p1], occ[p2], u1, &len);
+                    ns = len;
+                    if (io.new_hb || tot == 0) v *= tot;
+                }
+            } else {
+                nd = 1;
+            }
+            io.path[i] = pk(p0, p1, p2, p3);
+        }
+    }
+
+    __device__ void row(size_t i, double *w) const {
+        if (S == 0) {
+            w[0] = io.p_doub;
+            w[1] = 1 - io.p_doub;
+            return;
+        }
+        const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+        const uint32_t pp = io.path[i];
+        const uint64_t key = io.keys[io.det[i]];
+        uint8_t occ[FRIES_MAX_ELEC + 1];
+        mol_occ_list(key, occ);
+        unsigned p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
+        if (S == 1) {
+            hb_o1_probs(m, w, occ, io.new_hb);
+        } else if (S == 2) {
+            if (io.new_hb)
+                hb_o2_probs_half(m, w, occ, p1);
+            else
+                hb_o2_probs(m, w, occ, p1);
+        } else if (S == 3) {
+            int o1_spin = p1 / (ne / 2), o2_spin = occ[p2] / M;
+            hb_u1_probs(m, w, occ[p1], occ, io.new_hb && (o1_spin == o2_spin));
+        } else {
+            unsigned len;
+            if (io.new_hb)
+                hb_u2_probs_half(m, w, occ[p1], occ[p2], p3, key, &len);
+            else
+                hb_u2_probs(m, w, occ[p1], occ[p2], p3, &len);
+        }
+    }
+};
+
+template <int S>
+__global__ void __launch_bounds__(FR_COMP_BLOCK)
+hbpp_stage_kernel(MolView gm, HbStageIO io, CompSubBufs bufs, unsigned n_samp, double rn) {
+    HbProvider<S> prov;
+    prov.m = mol_stage_shared(gm, fr_dyn_smem);
+    prov.io = io;
+    comp_sub_engine(prov, bufs, n_samp, rn);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// finalize :917-991 (+ the spawn loop body of frisys_mol.cpp:436-461 when sp.out_keys != nullptr).
+// One thread per sample; tables in shared memory, integrals through L2.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ n_ptr,
+                     unsigned long long in_cap, const double *__restrict__ pv, const uint32_t *__restrict__ pw,
+                     const uint32_t *__restrict__ ps, const uint32_t *__restrict__ pdet,
+                     const uint32_t *__restrict__ ppath, double p_doub, int new_hb, double *__restrict__ fin_val,
+                     uint32_t *__restrict__ fin_det, uint32_t *__restrict__ fin_orbs, HbSpawnArgs sp, CompState *st) {
+    MolView m = mol_stage_shared(gm, fr_dyn_smem);
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned long long n = *n_ptr;
+    if (n > in_cap) n = in_cap;
+    unsigned long long ok = 0;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t widx = pw[i], sub = ps[i];
+        const uint32_t d = pdet[widx], pp = ppath[widx];
+        const uint64_t key = keys[d];
+        uint8_t occ[FRIES_MAX_ELEC + 1];
+        mol_occ_list(key, occ);
+        unsigned p0 = pp & 0xff, p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
+        uint8_t orbs[4] = {0, 0, 0, 0};
+        double el = 0;
+        bool is_doub = p0 == 0;
+        if (is_doub) {
+            unsigned o1 = occ[p1], o2 = occ[p2], u1 = p3;
+            unsigned u2_symm = m.symm[o1 % M] ^ m.symm[o2 % M] ^ m.symm[u1 % M];
+            unsigned u2 = mol_lookup(m, u2_symm, sub + 1) + M * (o2 / M);
+            if (!fr_read_bit(key, u2) && u1 != u2) {
+                if (u1 > u2) {
+                    unsigned t = u1;
+                    u1 = u2;
+                    u2 = t;
+                }
+                if (o1 > o2) {
+                    unsigned t = o1;
+                    o1 = o2;
+                    o2 = t;
+                }
+                orbs[0] = (uint8_t)o1;
+                orbs[1] = (uint8_t)o2;
+                orbs[2] = (uint8_t)u1;
+                orbs[3] = (uint8_t)u2;
+                double tot = new_hb ? hb_unnorm_wt(m, orbs) : hb_norm_wt(m, orbs, occ, key);
+                el = mol_doub_el(m, orbs) * pv[i] / tot / p_doub;
+                if (fabs(el) > 1e-9)
+                    el *= fr_doub_parity(key, o1, o2, u1, u2);
+                else
+                    el = 0;
+            }
+        } else {
+            unsigned o1 = occ[p1];
+            unsigned u1 = mol_virt_from_idx(m, key, m.symm[o1 % M], M * (o1 / M), p2);
+            if (u1 != 255) {
+                orbs[0] = (uint8_t)o1;
+                orbs[1] = (uint8_t)u1;
+                uint8_t cnt[FR_N_IRREPS][2];
+                mol_count_symm_virt(m, occ, cnt);
+                unsigned n_occ = mol_count_sing_allowed(m, occ, cnt);
+                el = mol_sing_el(m, o1, u1, occ);
+                el *= pv[i] / (1 - p_doub) * n_occ * p3;
+                if (fabs(el) > 1e-9)
+                    el *= fr_sing_parity(key, o1, u1);
+                else
+                    el = 0;
+            }
+        }
+        if (el != 0) ok++;
+        if (sp.out_keys) {
+            // spawn loop body frisys_mol.cpp:436-461
+            uint64_t nk = FRIES_EMPTY_KEY;
+            double add = 0;
+            if (el != 0) {
+                double cv = sp.v0[d];
+                add = -sp.eps * el;
+                if (cv < 0) add *= -1;
+                nk = key;
+                if (is_doub)
+                    nk = (nk & ~((1ull << orbs[0]) | (1ull << orbs[1]))) | (1ull << orbs[2]) | (1ull << orbs[3]);
+                else
+                    nk = (nk & ~(1ull << orbs[0])) | (1ull << orbs[1]);
+                if (fabs(cv) >= sp.init_thresh) nk |= FRIES_INI_FLAG;
+            }
+            sp.out_keys[i] = nk;
+            sp.out_vals[i] = add;
+        } else {
+            fin_val[i] = el;
+            fin_det[i] = d;
+            fin_orbs[i] = pk(orbs[0], orbs[1], orbs[2], orbs[3]);
+        }
+    }
+    ok = warp_sum_u64(ok);
+    if ((threadIdx.x & 31) == 0 && ok) atomicAdd(&st->n_out, ok);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->n_in = n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int fries_hbpp_alloc(fries_ctx *c, size_t cap, fries_hbpp **out, bool stages) {
+    FRIES_REQUIRE(cap >= 1 && cap < 0x7fffffffull, "fries_hbpp: spawn capacity %zu out of range", cap);
+    fries_hbpp *hb = new fries_hbpp();
+    hb->ctx = c;
+    hb->cap = cap;
+    int rc = FRIES_OK;
+#define A(buf, n) if (rc == FRIES_OK) rc = hb->buf.alloc(n)
+    if (stages) {
+        A(veff, cap); A(wtr, cap); A(lb, cap); A(ndiv, cap); A(keep, cap); A(kcnt, cap); A(nsub, cap);
+        for (int b = 0; b < 2; b++) {
+            A(oval[b], cap); A(owidx[b], cap); A(osub[b], cap); A(det[b], cap); A(path[b], cap);
+        }
+        A(fin_val, cap); A(fin_det, cap); A(fin_orbs, cap);
+    }
+    A(part_d, 4 * 1024); A(part_c, 4 * 1024); A(st, 8); A(n_scalar, 4); A(scal, 64);
+#undef A
+    if (rc != FRIES_OK) {
+        delete hb;
+        return rc;
+    }
+    *out = hb;
+    return FRIES_OK;
+}
+
+extern "C" int fries_hbpp_destroy(fries_hbpp *hb) {
+    if (hb) {
+        cudaSetDevice(hb->ctx->device);
+        delete hb;
+    }
+    return FRIES_OK;
+}
+
+template <int S>
+static int launch_stage(fries_hbpp *hb, fries_mol *mol, HbStageIO &io, CompSubBufs &bufs, unsigned n_samp, double rn) {
+    fries_ctx *c = hb->ctx;
+    size_t smem = (size_t)mol->view.d.blob_doubles * 8;
+    if (hb->grid == 0) {
+        // one grid size for all stages: the smallest co-resident grid among them (set on first use)
+        int g = c->coop_grid((const void *)hbpp_stage_kernel<0>, FR_COMP_BLOCK, smem);
+        int t;
+        t = c->coop_grid((const void *)hbpp_stage_kernel<1>, FR_COMP_BLOCK, smem); g = t < g ? t : g;
+        t = c->coop_grid((const void *)hbpp_stage_kernel<2>, FR_COMP_BLOCK, smem); g = t < g ? t : g;
+        t = c->coop_grid((const void *)hbpp_stage_kernel<3>, FR_COMP_BLOCK, smem); g = t < g ? t : g;
+        t = c->coop_grid((const void *)hbpp_stage_kernel<4>, FR_COMP_BLOCK, smem); g = t < g ? t : g;
+        hb->grid = g;
+    }
+    MolView gm = mol->view;
+    void *args[] = {(void *)&gm, (void *)&io, (void *)&bufs, (void *)&n_samp, (void *)&rn};
+    static const char *names[] = {"hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4"};
+    ProfScope ps(c, names[S]);
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)hbpp_stage_kernel<S>, dim3(hb->grid), dim3(FR_COMP_BLOCK), args,
+                                         smem, c->stream));
+    c->launch_count++;
+    return FRIES_OK;
+}
+
+int fries_hbpp_stages_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, const double *d_vals,
+                          const unsigned long long *d_n, double p_doub, int new_hb, const double *u5, unsigned n_samp) {
+    fries_ctx *c = hb->ctx;
+    CUDA_TRY(cudaMemsetAsync(hb->st.p, 0, 8 * sizeof(CompState), c->stream));
+    for (int s = 0; s < 5; s++) {
+        int o = s & 1, p = o ^ 1;
+        HbStageIO io;
+        io.keys = d_keys;
+        io.vals = d_vals;
+        io.n_in = s == 0 ? d_n : &hb->st.p[s - 1].n_out;
+        io.pv = hb->oval[p].p;
+        io.pw = hb->owidx[p].p;
+        io.ps = hb->osub[p].p;
+        io.pdet = hb->det[p].p;
+        io.ppath = hb->path[p].p;
+        io.det = hb->det[o].p;
+        io.path = hb->path[o].p;
+        io.p_doub = p_doub;
+        io.new_hb = new_hb;
+        io.in_cap = hb->cap;
+        CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
+                         hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
+                         hb->part_d.p, hb->part_c.p, hb->st.p + s};
+        switch (s) {
+            case 0: FRIES_TRY(launch_stage<0>(hb, mol, io, bufs, n_samp, u5[0])); break;
+            case 1: FRIES_TRY(launch_stage<1>(hb, mol, io, bufs, n_samp, u5[1])); break;
+            case 2: FRIES_TRY(launch_stage<2>(hb, mol, io, bufs, n_samp, u5[2])); break;
+            case 3: FRIES_TRY(launch_stage<3>(hb, mol, io, bufs, n_samp, u5[3])); break;
+            case 4: FRIES_TRY(launch_stage<4>(hb, mol, io, bufs, n_samp, u5[4])); break;
+        }
+    }
+    return FRIES_OK;
+}
+
+int fries_hbpp_finalize_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, double p_doub, int new_hb,
+                            const HbSpawnArgs *spawn) {
+    fries_ctx *c = hb->ctx;
+    HbSpawnArgs sp{nullptr, 0, 0, nullptr, nullptr};
+    if (spawn) sp = *spawn;
+    size_t smem = (size_t)mol->view.d.blob_doubles * 8;
+    int grid = c->sm_count * 4;
+    ProfScope ps(c, "hbpp_finalize");
+    // stage 4 wrote outputs to buffer set 0 and its path state to set 0
+    hbpp_finalize_kernel<<<grid, 256, smem, c->stream>>>(mol->view, d_keys, &hb->st.p[4].n_out,
+                                                         (unsigned long long)hb->cap, hb->oval[0].p, hb->owidx[0].p,
+                                                         hb->osub[0].p, hb->det[0].p, hb->path[0].p, p_doub, new_hb,
+                                                         hb->fin_val.p, hb->fin_det.p, hb->fin_orbs.p, sp, hb->st.p + 5);
+    c->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return FRIES_OK;
+}
+
+extern "C" int fries_apply_hbpp_sys(fries_mol *mol, const uint64_t *h_keys, const double *h_vals, size_t n,
+                                    double p_doub, int new_hb, const double *h_uniforms5, unsigned n_samp,
+                                    size_t spawn_cap, double *h_out_val, uint64_t *h_out_det, uint8_t *h_out_orbs,
+                                    size_t out_cap, size_t *n_out) {
+    FRIES_REQUIRE(mol && h_uniforms5 && n_out && (n == 0 || (h_keys && h_vals)), "fries_apply_hbpp_sys: NULL argument");
+    FRIES_REQUIRE(n <= spawn_cap, "fries_apply_hbpp_sys: %zu inputs exceed the scratch capacity %zu", n, spawn_cap);
+    fries_ctx *c = mol->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    *n_out = 0;
+    if (n == 0) return FRIES_OK;
+    const MolDims &d = mol->view.d;
+    uint64_t half = (1ull << d.n_orb) - 1;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t k = h_keys[i];
+        FRIES_REQUIRE((k >> (2 * d.n_orb)) == 0 && (unsigned)__builtin_popcountll(k & half) == d.n_elec / 2 &&
+                          (unsigned)__builtin_popcountll(k >> d.n_orb) == d.n_elec / 2,
+                      "fries_apply_hbpp_sys: determinant %zu has the wrong electron count", i);
+    }
+    fries_hbpp *hb = nullptr;
+    FRIES_TRY(fries_hbpp_alloc(c, spawn_cap, &hb));
+    DevBuf<uint64_t> keys;
+    DevBuf<double> vals;
+    int rc = keys.alloc(n);
+    if (rc == FRIES_OK) rc = vals.alloc(n);
+    if (rc != FRIES_OK) {
+        fries_hbpp_destroy(hb);
+        return rc;
+    }
+    unsigned long long n64 = n;
+    auto fail = [&](int code) {
+        fries_hbpp_destroy(hb);
+        return code;
+    };
+#define CU(expr)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            fries_set_error("%s failed: %s", #expr, cudaGetErrorString(e__));                          \
+            return fail(FRIES_ERR_CUDA);                                                               \
+        }                                                                                              \
+    } while (0)
+    CU(cudaMemcpyAsync(keys.p, h_keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(vals.p, h_vals, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(hb->n_scalar.p, &n64, 8, cudaMemcpyHostToDevice, c->stream));
+    rc = fries_hbpp_stages_dev(hb, mol, keys.p, vals.p, hb->n_scalar.p, p_doub, new_hb, h_uniforms5, n_samp);
+    if (rc == FRIES_OK) rc = fries_hbpp_finalize_dev(hb, mol, keys.p, p_doub, new_hb, nullptr);
+    if (rc != FRIES_OK) return fail(rc);
+    CompState st[6];
+    CU(cudaMemcpyAsync(st, hb->st.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < 5; s++)
+        if (st[s].overflow) {
+            // the reference prints "insufficient memory allocated for matrix compression" (:732,768,814,862,913)
+            fries_set_error("fries_apply_hbpp_sys: stage %d produced %llu samples beyond spawn_cap %zu", s,
+                            st[s].overflow, spawn_cap);
+            return fail(FRIES_ERR_CAPACITY);
+        }
+    size_t m = (size_t)st[5].n_in;
+    std::vector<double> v(m ? m : 1);
+    std::vector<uint32_t> dd(m ? m : 1), oo(m ? m : 1);
+    if (m) {
+        CU(cudaMemcpyAsync(v.data(), hb->fin_val.p, m * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(dd.data(), hb->fin_det.p, m * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(oo.data(), hb->fin_orbs.p, m * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+#undef CU
+    // marshal the successful samples, in order, into the caller's arrays (num_success compaction :917-991)
+    size_t k = 0;
+    for (size_t i = 0; i < m; i++) {
+        if (v[i] == 0) continue;
+        if (k < out_cap) {
+            h_out_val[k] = v[i];
+            h_out_det[k] = dd[i];
+            memcpy(h_out_orbs + 4 * k, &oo[i], 4);
+        }
+        k++;
+    }
+    *n_out = k;
+    fries_hbpp_destroy(hb);
+    if (k > out_cap) {
+        fries_set_error("fries_apply_hbpp_sys: %zu samples, output buffers hold %zu", k, out_cap);
+        return FRIES_ERR_CAPACITY;
+    }
+    return FRIES_OK;
+}

@@ -1,0 +1,63 @@
+// a10: heat-bath Power-Pitzer hierarchical compression of H's columns (apply_HBPP_sys
+// heat_bathPP.cpp:686-992) as five persistent cooperative kernels + a finalize/spawn kernel.
+//
+// The reference materialises a spawn_length x n_states sub-weight matrix per stage (608 MB at
+// mat_nonz = 1e6) and walks it sequentially.  Here every stage is one instance of comp_sub_engine
+// (compress.cuh) whose provider recomputes a row of sub-weights on the fly from the parent
+// determinant (8 B key) and the 4-byte choice path, with the small HB-PP tables staged in shared
+// memory.  Per sample and stage the HBM traffic is the 40 B of SURVEY.md 8d (value, parent index,
+// path; read + written), not the n_states x 8 B row.
+#pragma once
+#include "compress.cuh"
+#include "molhost.cuh"
+
+struct HbStageIO {
+    const uint64_t *keys;            // parent determinants (storage order)
+    const double *vals;              // stage 0 input: vector values
+    const unsigned long long *n_in;  // number of inputs of this stage (device)
+    // outputs of the previous stage (inputs of this one)
+    const double *pv;
+    const uint32_t *pw, *ps;
+    const uint32_t *pdet, *ppath;
+    // per-item path state written by this stage
+    uint32_t *det, *path;
+    double p_doub;
+    int new_hb;
+    unsigned long long in_cap;       // inputs beyond this index were dropped by the previous stage
+};
+
+struct fries_hbpp {
+    fries_ctx *ctx = nullptr;
+    size_t cap = 0;
+    DevBuf<double> veff, wtr, lb, oval[2], fin_val;
+    DevBuf<uint32_t> ndiv, keep, kcnt, owidx[2], osub[2], det[2], path[2], fin_det, fin_orbs;
+    DevBuf<uint8_t> nsub;
+    DevBuf<double> part_d;
+    DevBuf<unsigned long long> part_c;
+    DevBuf<CompState> st;  // [0..4] stages, [5] finalize counters, [6] vector compression
+    DevBuf<unsigned long long> n_scalar;
+    // frisys/frifull driver state (iter.cu)
+    DevBuf<uint64_t> trial_keys, htrial_keys, spawn_keys;
+    DevBuf<double> trial_vals, htrial_vals, spawn_vals, scal;
+    DevBuf<uint8_t> keep_flags;
+    size_t n_trial = 0, n_htrial = 0;
+    int grid = 0;
+};
+
+// stages = false: only the reduction scratch and counters (spawn buffers are added by the caller)
+int fries_hbpp_alloc(fries_ctx *c, size_t spawn_cap, fries_hbpp **out, bool stages = true);
+extern "C" int fries_hbpp_destroy(fries_hbpp *hb);
+// run the five stages on resident inputs; results: st[4].n_out samples in oval[1]/owidx[1]/osub[1]
+// with paths det[0]/path[0] (stage 4 state) -- see hbpp.cu for the ping-pong convention
+int fries_hbpp_stages_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, const double *d_vals,
+                          const unsigned long long *d_n, double p_doub, int new_hb, const double *uniforms5,
+                          unsigned n_samp);
+// finalize (:917-991).  spawn == nullptr: write (value, parent, orbitals) per sample, value 0 = failed.
+struct HbSpawnArgs {
+    const double *v0;        // parent values (sign + initiator test), frisys_mol.cpp:441-449
+    double eps, init_thresh;
+    uint64_t *out_keys;      // new determinant | FRIES_INI_FLAG, FRIES_EMPTY_KEY for failed samples
+    double *out_vals;
+};
+int fries_hbpp_finalize_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, double p_doub, int new_hb,
+                            const HbSpawnArgs *spawn);

@@ -1,0 +1,557 @@
+// a16/a17/a18: deterministic H.v, spawning, death/cloning and the resident FRI iterations of
+// frisys_mol (FRIES_bin/frisys_mol.cpp:405-552) and frifull_mol (FRIES_bin/frifull_mol.cpp:256-320).
+#include "hbpp.cuh"
+#include "vec.cuh"
+
+extern __shared__ double fr_dyn_smem[];
+
+int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, const unsigned long long *d_n,
+                               unsigned n_samp, uint8_t *d_keep, CompState *d_st, double *pd, unsigned long long *pc,
+                               int grid);
+int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, const unsigned long long *d_n, uint8_t *d_keep,
+                          const double *d_in, double lbound0, double glob, long long n_samp, double rn, CompState *d_out,
+                          double *pd, unsigned long long *pc, int grid);
+int fries_vec_compact_flags_dev(fries_vec *vec, const uint8_t *d_flags);
+
+#define FR_NAN __longlong_as_double(0x7ff8000000000000ll)
+
+extern "C" int fries_vec_set_diag_mol(fries_vec *vec, fries_mol *mol, double hf_en) {
+    FRIES_REQUIRE(vec && mol, "fries_vec_set_diag_mol: NULL argument");
+    FRIES_REQUIRE(vec->n_bits == 2 * mol->view.d.n_orb && vec->n_elec == mol->view.d.n_elec,
+                  "fries_vec_set_diag_mol: vector (%u bits, %u electrons) does not match the molecule (%u, %u)",
+                  vec->n_bits, vec->n_elec, 2 * mol->view.d.n_orb, mol->view.d.n_elec);
+    vec->diag_mol = mol;
+    vec->hf_en = hf_en;
+    return FRIES_OK;
+}
+
+// DistVec::matr_el_at_pos vec_utils.hpp:672-677 with diag_calc_ = diag_matrel - hf_en
+__device__ __forceinline__ double diag_at(const MolView &m, const VecView &v, size_t i, double hf_en) {
+    double d = v.diag[i];
+    if (isnan(d)) {
+        uint8_t occ[FRIES_MAX_ELEC + 1];
+        mol_occ_list(v.keys[i], occ);
+        d = mol_diag(m, occ) - hf_en;
+        v.diag[i] = d;
+    }
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// death/cloning + add_vecs(0,1) + zero_vec(1): frisys_mol.cpp:488-499, one streaming pass.
+// 32 B/element: read v0, diag, v1; write v0 (v1 is rewritten only where it was nonzero).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+death_axpy_kernel(MolView gm, VecView v, double hf_en, double eps, double shift) {
+    MolView m = mol_stage_shared(gm, fr_dyn_smem);
+    unsigned long long n64 = v.cnt->n;
+    size_t n = n64 < v.cap ? (size_t)n64 : v.cap;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    double *v0 = v.vals, *v1 = v.vals + v.cap;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a = v0[i], b = v1[i];
+        if (a != 0) {
+            double d = diag_at(m, v, i, hf_en);
+            a *= 1 - eps * (d - shift);
+        }
+        a += b;
+        v0[i] = a;
+        if (b != 0) v1[i] = 0;
+    }
+}
+
+// h_op_diag molecule.cpp:205-219
+__global__ void __launch_bounds__(256)
+h_diag_kernel(MolView gm, VecView v, double hf_en, unsigned src, unsigned dst, double id_fac, double h_fac) {
+    MolView m = mol_stage_shared(gm, fr_dyn_smem);
+    unsigned long long n64 = v.cnt->n;
+    size_t n = n64 < v.cap ? (size_t)n64 : v.cap;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    const double *vs = v.vals + (size_t)src * v.cap;
+    double *vd = v.vals + (size_t)dst * v.cap;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a = vs[i];
+        double r = 0;
+        if (a != 0) r = a * (id_fac + h_fac * diag_at(m, v, i, hf_en));
+        vd[i] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// h_op_offdiag molecule.cpp:448-665 -- one warp per parent determinant.
+//
+// The reference materialises each parent's excitation list (sing_ex_symm / doub_ex_symm) and walks
+// it.  Here the 32 lanes of a warp split the (occupied pair, first virtual) triples of the parent;
+// for a triple the allowed second virtuals are one AND of the parent's virtual mask with the irrep
+// mask, so counting is a popcount and enumeration a ctz loop.  Pass A counts per lane, a warp scan
+// turns the counts into write offsets inside the parent's slot range, pass B writes
+// (new determinant | INI, sign * element * v * h_fac).  The order inside a parent differs from the
+// reference's list order; the merged vector does not depend on it.
+// ---------------------------------------------------------------------------------------------------
+struct ParentCtx {
+    uint64_t key;
+    uint32_t occ_a, occ_b, virt_a, virt_b;  // spatial-orbital masks per spin
+    uint32_t irr[FR_N_IRREPS];              // spatial orbitals of each irrep
+};
+
+__device__ __forceinline__ void parent_ctx(const MolView &m, uint64_t key, ParentCtx &p) {
+    const unsigned M = m.d.n_orb;
+    uint32_t all = (uint32_t)((1ull << M) - 1);
+    p.key = key;
+    p.occ_a = (uint32_t)(key & all);
+    p.occ_b = (uint32_t)((key >> M) & all);
+    p.virt_a = ~p.occ_a & all;
+    p.virt_b = ~p.occ_b & all;
+    for (unsigned r = 0; r < FR_N_IRREPS; r++) {
+        uint32_t mk = 0;
+        unsigned n = mol_lookup(m, r, 0);
+        for (unsigned s = 0; s < n; s++) mk |= 1u << mol_lookup(m, r, s + 1);
+        p.irr[r] = mk;
+    }
+}
+
+// n-th set bit (0-based) of a 32-bit mask
+__device__ __forceinline__ unsigned nth_bit(uint32_t mask, unsigned n) { return __fns(mask, 0, n + 1); }
+
+// Visit this lane's share of the off-diagonal connections of the parent.  F(is_double, o0, o1, v0, v1).
+template <class F>
+__device__ __forceinline__ unsigned lane_excitations(const MolView &m, const ParentCtx &p, unsigned lane, F &&f) {
+    const unsigned M = m.d.n_orb, h = m.d.n_elec / 2, nv = M - h;
+    unsigned cnt = 0;
+    // singles: (electron, spin) pairs over lanes
+    for (unsigned e = lane; e < 2 * h; e += 32) {
+        unsigned spin = e / h;
+        unsigned o = nth_bit(spin ? p.occ_b : p.occ_a, e % h);
+        uint32_t vm = (spin ? p.virt_b : p.virt_a) & p.irr[m.symm[o]];
+        while (vm) {
+            unsigned a = __ffs(vm) - 1;
+            vm &= vm - 1;
+            f(false, o + spin * M, a + spin * M, 0u, 0u);
+            cnt++;
+        }
+    }
+    // opposite-spin doubles: (i alpha, j beta, k alpha virtual) triples over lanes
+    unsigned n_ab = h * h * nv;
+    for (unsigned t = lane; t < n_ab; t += 32) {
+        unsigned k_i = t % nv, ij = t / nv, i = ij / h, j = ij % h;
+        unsigned io = nth_bit(p.occ_a, i), jo = nth_bit(p.occ_b, j), k = nth_bit(p.virt_a, k_i);
+        uint32_t lm = p.virt_b & p.irr[m.symm[io] ^ m.symm[jo] ^ m.symm[k]];
+        while (lm) {
+            unsigned l = __ffs(lm) - 1;
+            lm &= lm - 1;
+            f(true, io, jo + M, k, l + M);
+            cnt++;
+        }
+    }
+    // same-spin doubles
+    unsigned n_pair = h * (h - 1) / 2;
+    for (unsigned spin = 0; spin < 2; spin++) {
+        uint32_t om = spin ? p.occ_b : p.occ_a, vmask = spin ? p.virt_b : p.virt_a;
+        for (unsigned t = lane; t < n_pair * nv; t += 32) {
+            unsigned k_i = t % nv, pr = t / nv;
+            // pair index -> (i < j)
+            unsigned j = 1;
+            while (j * (j + 1) / 2 <= pr) j++;
+            unsigned i = pr - j * (j - 1) / 2;
+            unsigned io = nth_bit(om, i), jo = nth_bit(om, j), k = nth_bit(vmask, k_i);
+            uint32_t lm = vmask & p.irr[m.symm[io] ^ m.symm[jo] ^ m.symm[k]] & ~((2u << k) - 1u);
+            while (lm) {
+                unsigned l = __ffs(lm) - 1;
+                lm &= lm - 1;
+                f(true, io + spin * M, jo + spin * M, k + spin * M, l + spin * M);
+                cnt++;
+            }
+        }
+    }
+    return cnt;
+}
+
+// pass 1: number of connections per parent (0 for zero-valued parents)
+__global__ void __launch_bounds__(256)
+hv_count_kernel(MolView gm, VecView v, unsigned src, size_t n_parents, uint32_t *__restrict__ counts) {
+    MolView m = mol_stage_shared(gm, fr_dyn_smem);
+    const unsigned lane = threadIdx.x & 31;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < n_parents; p += nwarps) {
+        double val = v.vals[(size_t)src * v.cap + p];
+        unsigned c = 0;
+        if (val != 0) {
+            ParentCtx pc;
+            parent_ctx(m, v.keys[p], pc);
+            c = lane_excitations(m, pc, lane, [](bool, unsigned, unsigned, unsigned, unsigned) {});
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+        if (lane == 0) counts[p] = c;
+    }
+}
+
+// exclusive scan of u32 counts into u64 offsets (cooperative, deterministic)
+__global__ void __launch_bounds__(FR_COMP_BLOCK)
+scan_counts_kernel(const uint32_t *__restrict__ counts, size_t n, unsigned long long *__restrict__ offs,
+                   unsigned long long *total_out, double *part_d, unsigned long long *part_c) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh_d[34];
+    __shared__ unsigned long long sh_c[34];
+    __shared__ double sh_sd[34];
+    __shared__ unsigned long long sh_sc[34];
+    GridRed red{part_d, part_c, 0, (int)gridDim.x, sh_d, sh_c};
+    size_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + 31) & ~(size_t)31;
+    const size_t lo = (size_t)blockIdx.x * chunk < n ? (size_t)blockIdx.x * chunk : n;
+    const size_t hi = lo + chunk < n ? lo + chunk : n;
+    unsigned long long c = 0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) c += counts[i];
+    c = block_sum_u64(c, sh_c);
+    double d0, d1;
+    unsigned long long blk_off, total;
+    grid_excl_scan(grid, red, 0.0, c, d0, blk_off, d1, total, sh_sd, sh_sc);
+    unsigned long long carry = blk_off;
+    for (size_t base = lo; base < hi; base += blockDim.x) {
+        size_t i = base + threadIdx.x;
+        unsigned long long mine = i < hi ? counts[i] : 0ull;
+        double ex, tot;
+        unsigned long long ec, tc;
+        block_excl_scan(0.0, mine, ex, ec, tot, tc, sh_sd, sh_sc);
+        if (i < hi) offs[i] = carry + ec;
+        carry += tc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total_out = total;
+}
+
+// pass 2: write the connections whose global index falls in the window [win_lo, win_lo + win_len)
+__global__ void __launch_bounds__(256)
+hv_fill_kernel(MolView gm, VecView v, unsigned src, size_t n_parents, const uint32_t *__restrict__ counts,
+               const unsigned long long *__restrict__ offs, unsigned long long win_lo, unsigned long long win_len,
+               double h_fac, uint64_t *__restrict__ out_keys, double *__restrict__ out_vals) {
+    MolView m = mol_stage_shared(gm, fr_dyn_smem);
+    const unsigned lane = threadIdx.x & 31;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < n_parents; p += nwarps) {
+        unsigned cn = counts[p];
+        if (cn == 0) continue;
+        unsigned long long off = offs[p];
+        if (off + cn <= win_lo || off >= win_lo + win_len) continue;
+        double val = v.vals[(size_t)src * v.cap + p];
+        ParentCtx pc;
+        parent_ctx(m, v.keys[p], pc);
+        uint8_t occ[FRIES_MAX_ELEC + 1];
+        mol_occ_list(pc.key, occ);
+        unsigned mine = lane_excitations(m, pc, lane, [](bool, unsigned, unsigned, unsigned, unsigned) {});
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        unsigned long long pos = off + (incl - mine);
+        lane_excitations(m, pc, lane, [&](bool dbl, unsigned o0, unsigned o1, unsigned v0, unsigned v1) {
+            if (pos >= win_lo && pos < win_lo + win_len) {
+                uint64_t nk = pc.key;
+                double el;
+                if (dbl) {
+                    uint8_t ob[4] = {(uint8_t)o0, (uint8_t)o1, (uint8_t)v0, (uint8_t)v1};
+                    el = mol_doub_el(m, ob);
+                    el *= fr_doub_det_parity(nk, o0, o1, v0, v1);
+                } else {
+                    el = mol_sing_el(m, o0, o1, occ);
+                    el *= fr_sing_det_parity(nk, o0, o1);
+                }
+                el *= val * h_fac;  // matr_el *= curr_el * h_fac (molecule.cpp:601,655)
+                out_keys[pos - win_lo] = nk | FRIES_INI_FLAG;
+                out_vals[pos - win_lo] = el;
+            }
+            pos++;
+        });
+    }
+}
+
+struct HvScratch {
+    DevBuf<uint32_t> counts;
+    DevBuf<unsigned long long> offs, total;
+};
+
+// dest <- id_fac * src + h_fac * H * src.  Spawn buffers: hb->spawn_keys / spawn_vals (cap entries).
+static int h_apply_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned src, unsigned dest, double id_fac,
+                       double h_fac, bool do_diag, uint64_t *n_spawned) {
+    fries_ctx *c = vec->ctx;
+    FRIES_REQUIRE(src < vec->n_vecs && dest < vec->n_vecs && src != dest, "h_apply: need two different rows");
+    VecCounters cnt;
+    FRIES_TRY(vec->read_counters(&cnt));
+    size_t n_parents = (size_t)cnt.n;
+    if (n_spawned) *n_spawned = 0;
+    if (n_parents == 0) return FRIES_OK;
+    size_t smem = (size_t)mol->view.d.blob_doubles * 8;
+    VecView v = vec->view();
+    int grid = c->sm_count * 8;
+    if (do_diag) {
+        ProfScope ps(c, "h_diag");
+        h_diag_kernel<<<grid, 256, smem, c->stream>>>(mol->view, v, vec->hf_en, src, dest, id_fac, h_fac);
+        c->launch_count++;
+    }
+    HvScratch sc;
+    FRIES_TRY(sc.counts.alloc(n_parents));
+    FRIES_TRY(sc.offs.alloc(n_parents));
+    FRIES_TRY(sc.total.alloc(1));
+    {
+        ProfScope ps(c, "hv_count");
+        hv_count_kernel<<<grid, 256, smem, c->stream>>>(mol->view, v, src, n_parents, sc.counts.p);
+        c->launch_count++;
+    }
+    {
+        int sgrid = c->coop_grid((const void *)scan_counts_kernel, FR_COMP_BLOCK, 0);
+        const uint32_t *cp = sc.counts.p;
+        unsigned long long *op = sc.offs.p, *tp = sc.total.p;
+        double *pd = hb->part_d.p;
+        unsigned long long *pc = hb->part_c.p;
+        void *args[] = {(void *)&cp, (void *)&n_parents, (void *)&op, (void *)&tp, (void *)&pd, (void *)&pc};
+        ProfScope ps(c, "hv_scan");
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)scan_counts_kernel, dim3(sgrid), dim3(FR_COMP_BLOCK), args, 0,
+                                             c->stream));
+        c->launch_count++;
+    }
+    unsigned long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, sc.total.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (n_spawned) *n_spawned = total;
+    for (unsigned long long lo = 0; lo < total; lo += hb->cap) {
+        unsigned long long len = total - lo < hb->cap ? total - lo : hb->cap;
+        {
+            ProfScope ps(c, "hv_fill");
+            hv_fill_kernel<<<grid, 256, smem, c->stream>>>(mol->view, v, src, n_parents, sc.counts.p, sc.offs.p, lo, len,
+                                                           h_fac, hb->spawn_keys.p, hb->spawn_vals.p);
+            c->launch_count++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        // h_op_offdiag adds with ini_flag = 1 and perform_add(0) (molecule.cpp:602,608)
+        FRIES_TRY(fries_vec_merge_dev(vec, hb->spawn_keys.p, hb->spawn_vals.p, (size_t)len, nullptr, 0, dest));
+        v = vec->view();
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // scratch is freed on return
+    FRIES_TRY(vec->read_counters(&cnt));
+    if (cnt.overflow) {
+        fries_set_error("h_apply: determinant store is full (capacity %zu); %llu insertions dropped", vec->cap,
+                        cnt.overflow);
+        return FRIES_ERR_CAPACITY;
+    }
+    return FRIES_OK;
+}
+
+static int ensure_spawn(fries_hbpp *hb) {
+    FRIES_TRY(hb->spawn_keys.ensure(hb->cap));
+    FRIES_TRY(hb->spawn_vals.ensure(hb->cap));
+    return FRIES_OK;
+}
+
+extern "C" int fries_h_apply(fries_vec *vec, fries_mol *mol, unsigned src, unsigned dest, double id_fac, double h_fac) {
+    FRIES_REQUIRE(vec && mol, "fries_h_apply: NULL argument");
+    FRIES_REQUIRE(vec->n_bits == 2 * mol->view.d.n_orb && vec->n_elec == mol->view.d.n_elec,
+                  "fries_h_apply: vector does not match the molecule");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!vec->hv_scratch) {
+        size_t cap = vec->cap < (1u << 22) ? (1u << 22) : vec->cap;
+        FRIES_TRY(fries_hbpp_alloc(c, cap, &vec->hv_scratch, false));
+    }
+    FRIES_TRY(ensure_spawn(vec->hv_scratch));
+    uint64_t ns = 0;
+    FRIES_TRY(h_apply_dev(vec, mol, vec->hv_scratch, src, dest, id_fac, h_fac, true, &ns));
+    vec->last_spawned = ns;
+    return FRIES_OK;
+}
+extern "C" int fries_h_apply_last_spawned(fries_vec *vec, uint64_t *n) {
+    FRIES_REQUIRE(vec && n, "NULL argument");
+    *n = vec->last_spawned;
+    return FRIES_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// frisys_mol
+// ---------------------------------------------------------------------------------------------------
+extern "C" int fries_frisys_mol_setup(fries_vec *vec, fries_mol *mol, size_t spawn_cap, const uint64_t *h_trial_keys,
+                                      const double *h_trial_vals, size_t n_trial, const uint64_t *h_htrial_keys,
+                                      const double *h_htrial_vals, size_t n_htrial, fries_hbpp **out) {
+    FRIES_REQUIRE(vec && mol && out, "fries_frisys_mol_setup: NULL argument");
+    FRIES_REQUIRE(n_trial == 0 || (h_trial_keys && h_trial_vals), "fries_frisys_mol_setup: NULL trial vector");
+    FRIES_REQUIRE(n_htrial == 0 || (h_htrial_keys && h_htrial_vals), "fries_frisys_mol_setup: NULL H*trial vector");
+    FRIES_REQUIRE(vec->n_vecs >= 2, "fries_frisys_mol_setup: the vector needs two value rows");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    fries_hbpp *hb = nullptr;
+    FRIES_TRY(fries_hbpp_alloc(c, spawn_cap, &hb));
+    int rc = ensure_spawn(hb);
+    if (rc == FRIES_OK) rc = hb->trial_keys.alloc(n_trial);
+    if (rc == FRIES_OK) rc = hb->trial_vals.alloc(n_trial);
+    if (rc == FRIES_OK) rc = hb->htrial_keys.alloc(n_htrial);
+    if (rc == FRIES_OK) rc = hb->htrial_vals.alloc(n_htrial);
+    if (rc == FRIES_OK) rc = hb->keep_flags.alloc(vec->cap);
+    if (rc != FRIES_OK) {
+        fries_hbpp_destroy(hb);
+        return rc;
+    }
+    hb->n_trial = n_trial;
+    hb->n_htrial = n_htrial;
+    if (n_trial) {
+        CUDA_TRY(cudaMemcpyAsync(hb->trial_keys.p, h_trial_keys, n_trial * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(hb->trial_vals.p, h_trial_vals, n_trial * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (n_htrial) {
+        CUDA_TRY(cudaMemcpyAsync(hb->htrial_keys.p, h_htrial_keys, n_htrial * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(hb->htrial_vals.p, h_htrial_vals, n_htrial * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(hb->keep_flags.p, 0, vec->cap, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    vec->diag_mol = mol;
+    *out = hb;
+    return FRIES_OK;
+}
+
+__global__ void trial_dot_kernel(VecView v, const uint64_t *__restrict__ t_keys, const double *__restrict__ t_vals,
+                                 size_t n_trial, unsigned row, double *out);
+
+struct IterScalars {  // hb->scal layout (doubles)
+    enum { R4 = 0, NUMER = 4, DENOM = 5, NEW_NORM = 6, STATS = 8 };
+};
+
+__global__ void iter_stats_kernel(const CompState *st, const VecCounters *cnt, const double *scal, double *out) {
+    // out[0..]: glob_norm, numer, denom, n_kept, n_matrix_samples, curr_size, overflow flags, anomalies
+    out[0] = st[6].glob_norm;
+    out[1] = scal[IterScalars::NUMER];
+    out[2] = scal[IterScalars::DENOM];
+    out[3] = (double)st[6].n_kept;
+    out[4] = (double)st[5].n_out;
+    out[5] = (double)cnt->n;
+    unsigned long long ov = 0, an = 0;
+    for (int s = 0; s < 5; s++) {
+        ov += st[s].overflow;
+        an += st[s].anomalies;
+    }
+    out[6] = (double)ov;
+    out[7] = (double)cnt->overflow;
+    out[8] = (double)an;
+    out[9] = (double)st[6].n_samp_left;
+    out[10] = st[6].loc_norm;
+}
+
+__global__ void state_to_r4_kernel(const CompState *st, double *r4) {
+    r4[0] = st->loc_norm;
+    r4[1] = st->glob_norm;
+    r4[2] = (double)st->n_samp_left;
+    r4[3] = (double)st->n_kept;
+}
+
+static int compress_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, unsigned target_nonz, double uniform) {
+    // find_preserve -> sys_comp -> del_at_pos for the zeroed elements (frisys_mol.cpp:501-539)
+    fries_ctx *c = vec->ctx;
+    VecView v = vec->view();
+    double *vals = v.vals + (size_t)row * v.cap;
+    FRIES_TRY(fries_find_preserve_launch(c, vals, vec->cap, &vec->cnt.p->n, target_nonz, hb->keep_flags.p, hb->st.p + 6,
+                                         hb->part_d.p, hb->part_c.p, 0));
+    state_to_r4_kernel<<<1, 1, 0, c->stream>>>(hb->st.p + 6, hb->scal.p + IterScalars::R4);
+    c->launch_count++;
+    (void)uniform;
+    return FRIES_OK;
+}
+
+static int resample_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, double uniform) {
+    fries_ctx *c = vec->ctx;
+    VecView v = vec->view();
+    double *vals = v.vals + (size_t)row * v.cap;
+    FRIES_TRY(fries_sys_comp_launch(c, vals, vec->cap, &vec->cnt.p->n, hb->keep_flags.p, hb->scal.p + IterScalars::R4,
+                                    0.0, 0.0, -1LL, uniform, hb->st.p + 7, hb->part_d.p, hb->part_c.p, 0));
+    FRIES_TRY(fries_vec_compact_flags_dev(vec, hb->keep_flags.p));
+    return FRIES_OK;
+}
+
+static int dot_dev(fries_vec *vec, const uint64_t *tk, const double *tv, size_t n, unsigned row, double *d_out) {
+    fries_ctx *c = vec->ctx;
+    trial_dot_kernel<<<1, 1024, 0, c->stream>>>(vec->view(), tk, tv, n, row, d_out);
+    c->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return FRIES_OK;
+}
+
+static int read_stats(fries_vec *vec, fries_hbpp *hb, fries_iter_stats *stats, const char *who) {
+    fries_ctx *c = vec->ctx;
+    iter_stats_kernel<<<1, 1, 0, c->stream>>>(hb->st.p, vec->cnt.p, hb->scal.p, hb->scal.p + IterScalars::STATS);
+    c->launch_count++;
+    CUDA_TRY(cudaMemcpyAsync(c->h_pinned, hb->scal.p + IterScalars::STATS, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const double *h = c->h_pinned;
+    if (stats) {
+        stats->glob_norm = h[0];
+        stats->numer = h[1];
+        stats->denom = h[2];
+        stats->n_kept = (uint64_t)h[3];
+        stats->n_matrix_samples = (uint64_t)h[4];
+        stats->n_spawned = (uint64_t)h[4];
+        stats->curr_size = (uint64_t)h[5];
+    }
+    if (h[6] != 0) {
+        fries_set_error("%s: insufficient memory allocated for matrix compression (%g samples dropped; raise spawn_cap)",
+                        who, h[6]);
+        return FRIES_ERR_CAPACITY;
+    }
+    if (h[7] != 0) {
+        fries_set_error("%s: determinant store is full (capacity %zu); %g insertions dropped", who, vec->cap, h[7]);
+        return FRIES_ERR_CAPACITY;
+    }
+    return FRIES_OK;
+}
+
+extern "C" int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
+                                        const double *u6, fries_iter_stats *stats) {
+    FRIES_REQUIRE(vec && mol && hb && p && u6, "fries_frisys_mol_iterate: NULL argument");
+    FRIES_REQUIRE(vec->n_ranks == 1, "fries_frisys_mol_iterate: multi-rank vectors go through fries_frisys_mol_spawn/merge");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    VecView v = vec->view();
+    size_t smem = (size_t)mol->view.d.blob_doubles * 8;
+    // steps 2-3: hierarchical compression of H's columns
+    FRIES_TRY(fries_hbpp_stages_dev(hb, mol, v.keys, v.vals, &vec->cnt.p->n, p->p_doub, p->new_hb, u6, p->matr_samp));
+    // step 5: spawn (fused into finalize) and merge into row 1
+    HbSpawnArgs sp{v.vals, p->eps, p->init_thresh, hb->spawn_keys.p, hb->spawn_vals.p};
+    FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, v.keys, p->p_doub, p->new_hb, &sp));
+    FRIES_TRY(fries_vec_merge_dev(vec, hb->spawn_keys.p, hb->spawn_vals.p, hb->cap, &hb->st.p[4].n_out, 0, 1));
+    // step 7: death/cloning, add_vecs(0, 1), zero row 1
+    {
+        ProfScope ps(c, "death_axpy");
+        death_axpy_kernel<<<c->sm_count * 8, 256, smem, c->stream>>>(mol->view, v, vec->hf_en, p->eps, p->en_shift);
+        c->launch_count++;
+    }
+    // step 8: exact preservation
+    FRIES_TRY(compress_vector_dev(vec, hb, 0, p->target_nonz, u6[5]));
+    // step 10: projected energy (before resampling, frisys_mol.cpp:517-520)
+    FRIES_TRY(dot_dev(vec, hb->htrial_keys.p, hb->htrial_vals.p, hb->n_htrial, 0, hb->scal.p + IterScalars::NUMER));
+    FRIES_TRY(dot_dev(vec, hb->trial_keys.p, hb->trial_vals.p, hb->n_trial, 0, hb->scal.p + IterScalars::DENOM));
+    // step 11: systematic resampling + deletion of the zeroed elements
+    FRIES_TRY(resample_vector_dev(vec, hb, 0, u6[5]));
+    return read_stats(vec, hb, stats, "fries_frisys_mol_iterate");
+}
+
+// frifull_mol.cpp:256-320.  The vector alternates between rows: `src` is the row holding the current
+// iterate (vec_idx), the result lands in the other row.
+extern "C" int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frifull_params *p,
+                                         double uniform, fries_iter_stats *stats) {
+    FRIES_REQUIRE(vec && mol && hb && p, "fries_frifull_mol_iterate: NULL argument");
+    FRIES_REQUIRE(vec->n_ranks == 1, "fries_frifull_mol_iterate: single-rank entry point");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    unsigned src = vec->cur_row, dst = src ^ 1;
+    CUDA_TRY(cudaMemsetAsync(hb->st.p, 0, 8 * sizeof(CompState), c->stream));
+    FRIES_TRY(dot_dev(vec, hb->trial_keys.p, hb->trial_vals.p, hb->n_trial, src, hb->scal.p + IterScalars::DENOM));
+    FRIES_TRY(compress_vector_dev(vec, hb, src, p->target_nonz, uniform));
+    FRIES_TRY(resample_vector_dev(vec, hb, src, uniform));
+    uint64_t ns = 0;
+    FRIES_TRY(h_apply_dev(vec, mol, hb, src, dst, 1 + p->eps * p->en_shift, -p->eps, true, &ns));
+    vec->cur_row = dst;
+    FRIES_TRY(dot_dev(vec, hb->trial_keys.p, hb->trial_vals.p, hb->n_trial, dst, hb->scal.p + IterScalars::NUMER));
+    int rc = read_stats(vec, hb, stats, "fries_frifull_mol_iterate");
+    if (stats) {
+        // numer = ((1 + eps S) denom - <trial|v'>) / eps  (frifull_mol.cpp:294-296)
+        stats->numer = ((1 + p->eps * p->en_shift) * stats->denom - stats->numer) / p->eps;
+        stats->n_spawned = ns;
+        stats->n_matrix_samples = ns;
+    }
+    return rc;
+}

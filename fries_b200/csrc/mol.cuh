@@ -1,0 +1,597 @@
+// Molecular Hamiltonian on u64 determinants: Slater-Condon elements (a12/a13), symmetry bookkeeping
+// (a11), excitation enumeration (a14) and the heat-bath Power-Pitzer weight rows (a8/a9).
+//
+// Everything here is a pure __host__ __device__ inline function of a MolView, so the kernels in
+// mol.cu / hbpp.cu / iter.cu share one definition.  Reference: FRIES/Hamiltonians/molecule.cpp,
+// heat_bathPP.cpp, near_uniform.cpp, FRIES/fci_utils.c (cited per function).  Loop and summation
+// orders follow the reference so that FP64 results agree to the last bits, not just to 1e-12.
+#pragma once
+#include "common.cuh"
+
+#define FR_N_IRREPS 8  // molecule.hpp: n_irreps
+
+// tri-index macros of FRIES/math_utils.h:15-17
+#define FR_TRI_N(n) ((n) * ((n) + 1) / 2)
+#define FR_TRI_NODIAG(i, j) (FR_TRI_N((j)-1) + (i))
+#define FR_TRI_WDIAG(i, j) (FR_TRI_N(j) + (i))
+
+// Offsets (in doubles) of the small tables inside one contiguous blob, so that a kernel can stage
+// the whole blob in shared memory with one cooperative copy.
+struct MolDims {
+    uint32_t n_orb;     // M: unfrozen spatial orbitals
+    uint32_t n_elec;    // unfrozen electrons
+    uint32_t n_frz;     // frozen electrons
+    uint32_t tot_orb;   // M + n_frz / 2
+    uint32_t max_n_symm;
+    uint32_t blob_doubles;  // size of the small-table blob in doubles (incl. the byte tables)
+    uint32_t off_d_diff, off_d_same, off_s_tens, off_exch_sqrt, off_diag_sqrt, off_exch_norms, off_symm, off_lookup;
+    double s_norm;
+};
+
+struct MolView {
+    MolDims d;
+    const double *eris;   // SymmERIs packed (FRIES/ndarr.hpp:206-244), tot_orb orbitals
+    const double *hcore;  // tot_orb x tot_orb
+    const double *d_diff, *d_same, *s_tens, *exch_sqrt, *diag_sqrt, *exch_norms;  // hb_info heat_bathPP.hpp:25-34
+    const uint8_t *symm;    // [M] irreps
+    const uint8_t *lookup;  // [8][M + 1] gen_symm_lookup molecule.cpp:1050-1065
+};
+
+__host__ __device__ __forceinline__ void mol_bind_blob(MolView &m, const double *blob) {
+    m.d_diff = blob + m.d.off_d_diff;
+    m.d_same = blob + m.d.off_d_same;
+    m.s_tens = blob + m.d.off_s_tens;
+    m.exch_sqrt = blob + m.d.off_exch_sqrt;
+    m.diag_sqrt = blob + m.d.off_diag_sqrt;
+    m.exch_norms = blob + m.d.off_exch_norms;
+    m.symm = (const uint8_t *)(blob + m.d.off_symm);
+    m.lookup = (const uint8_t *)(blob + m.d.off_lookup);
+}
+
+__host__ __device__ __forceinline__ uint8_t mol_lookup(const MolView &m, unsigned irrep, unsigned col) {
+    return m.lookup[irrep * (m.d.n_orb + 1) + col];
+}
+
+// ---- SymmERIs::chemist / physicist ndarr.hpp:219-239 ------------------------------------------------
+__host__ __device__ __forceinline__ double eri_chem(const MolView &m, unsigned i1, unsigned i2, unsigned i3,
+                                                    unsigned i4) {
+    unsigned min1 = i1 < i2 ? i1 : i2, max1 = i1 < i2 ? i2 : i1;
+    unsigned p1 = FR_TRI_WDIAG(min1, max1);
+    unsigned min2 = i3 < i4 ? i3 : i4, max2 = i3 < i4 ? i4 : i3;
+    unsigned p2 = FR_TRI_WDIAG(min2, max2);
+    size_t minp = p1 < p2 ? p1 : p2, maxp = p1 < p2 ? p2 : p1;
+#ifdef __CUDA_ARCH__
+    return __ldg(&m.eris[FR_TRI_WDIAG(minp, maxp)]);
+#else
+    return m.eris[FR_TRI_WDIAG(minp, maxp)];
+#endif
+}
+__host__ __device__ __forceinline__ double eri_phys(const MolView &m, unsigned i1, unsigned i2, unsigned i3,
+                                                    unsigned i4) {
+    return eri_chem(m, i1, i3, i2, i4);
+}
+__host__ __device__ __forceinline__ double mol_hcore(const MolView &m, unsigned i, unsigned j) {
+#ifdef __CUDA_ARCH__
+    return __ldg(&m.hcore[i * m.d.tot_orb + j]);
+#else
+    return m.hcore[i * m.d.tot_orb + j];
+#endif
+}
+
+// ---- a12: diag_matrel molecule.cpp:983-1029 -----------------------------------------------------------
+__host__ __device__ inline double mol_diag(const MolView &m, const uint8_t *occ) {
+    const unsigned hf = m.d.n_frz / 2, ne = m.d.n_elec, M = m.d.n_orb;
+    double sum = 0;
+    for (unsigned j = 0; j < hf; j++) {
+        sum += mol_hcore(m, j, j) * 2;
+        sum += eri_phys(m, j, j, j, j);
+        for (unsigned k = j + 1; k < hf; k++) {
+            sum += eri_phys(m, j, k, j, k) * 4;
+            sum -= eri_phys(m, j, k, k, j) * 2;
+        }
+    }
+    for (unsigned j = 0; j < ne / 2; j++) {
+        unsigned e1 = occ[j] + hf;
+        sum += mol_hcore(m, e1, e1);
+        for (unsigned k = 0; k < hf; k++) {
+            sum += eri_phys(m, e1, k, e1, k) * 2;
+            sum -= eri_phys(m, e1, k, k, e1);
+        }
+        for (unsigned k = j + 1; k < ne / 2; k++) {
+            unsigned e2 = occ[k] + hf;
+            sum += eri_phys(m, e1, e2, e1, e2);
+            sum -= eri_phys(m, e1, e2, e2, e1);
+        }
+        for (unsigned k = ne / 2; k < ne; k++) {
+            unsigned e2 = occ[k] - M + hf;  // occ + n_frozen - n_orbs with n_orbs = tot_orb
+            sum += eri_phys(m, e1, e2, e1, e2);
+        }
+    }
+    for (unsigned j = ne / 2; j < ne; j++) {
+        unsigned e1 = occ[j] - M + hf;
+        sum += mol_hcore(m, e1, e1);
+        for (unsigned k = 0; k < hf; k++) {
+            sum += eri_phys(m, e1, k, e1, k) * 2;
+            sum -= eri_phys(m, e1, k, k, e1);
+        }
+        for (unsigned k = j + 1; k < ne; k++) {
+            unsigned e2 = occ[k] - M + hf;
+            sum += eri_phys(m, e1, e2, e1, e2);
+            sum -= eri_phys(m, e1, e2, e2, e1);
+        }
+    }
+    return sum;
+}
+
+// ---- a13: sing_matr_el_nosgn molecule.cpp:76-105, doub_matr_el_nosgn :26-42 -----------------------------
+__host__ __device__ inline double mol_sing_el(const MolView &m, unsigned o, unsigned v, const uint8_t *occ) {
+    const unsigned hf = m.d.n_frz / 2, ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned occ_spa = (o % M) + hf, unocc_spa = (v % M) + hf, occ_spin = o / M;
+    double el = mol_hcore(m, occ_spa, unocc_spa);
+    for (unsigned j = 0; j < hf; j++) {
+        el += eri_phys(m, occ_spa, j, unocc_spa, j) * 2;
+        el -= eri_phys(m, occ_spa, j, j, unocc_spa);
+    }
+    for (unsigned j = 0; j < ne / 2; j++) {
+        unsigned q = occ[j] + hf;
+        el += eri_phys(m, occ_spa, q, unocc_spa, q);
+        if (occ_spin == 0) el -= eri_phys(m, occ_spa, q, q, unocc_spa);
+    }
+    for (unsigned j = ne / 2; j < ne; j++) {
+        unsigned q = occ[j] - M + hf;
+        el += eri_phys(m, occ_spa, q, unocc_spa, q);
+        if (occ_spin == 1) el -= eri_phys(m, occ_spa, q, q, unocc_spa);
+    }
+    return el;
+}
+__host__ __device__ inline double mol_doub_el(const MolView &m, const uint8_t *orbs) {
+    const unsigned hf = m.d.n_frz / 2, M = m.d.n_orb;
+    bool same_sp = (orbs[0] / M) == (orbs[1] / M);
+    unsigned sp0 = (orbs[0] % M) + hf, sp1 = (orbs[1] % M) + hf, sp2 = (orbs[2] % M) + hf, sp3 = (orbs[3] % M) + hf;
+    double el = eri_phys(m, sp0, sp1, sp2, sp3);
+    if (same_sp) el -= eri_phys(m, sp0, sp1, sp3, sp2);
+    return el;
+}
+
+// ---- a11: symmetry bookkeeping ----------------------------------------------------------------------------
+// count_symm_virt near_uniform.cpp:14-28: unoccupied orbitals per (irrep, spin)
+__host__ __device__ inline void mol_count_symm_virt(const MolView &m, const uint8_t *occ, uint8_t cnt[FR_N_IRREPS][2]) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    for (unsigned i = 0; i < FR_N_IRREPS; i++) cnt[i][0] = cnt[i][1] = mol_lookup(m, i, 0);
+    unsigned i = 0;
+    for (; i < ne / 2; i++) cnt[m.symm[occ[i]]][0] -= 1;
+    for (; i < ne; i++) cnt[m.symm[occ[i] - M]][1] -= 1;
+}
+// count_sing_allowed near_uniform.cpp:316-327
+__host__ __device__ inline unsigned mol_count_sing_allowed(const MolView &m, const uint8_t *occ,
+                                                           const uint8_t cnt[FR_N_IRREPS][2]) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned n = 0;
+    for (unsigned e = 0; e < ne; e++)
+        if (cnt[m.symm[occ[e] % M]][e / (ne / 2)] != 0) n++;
+    return n;
+}
+// count_sing_virt near_uniform.cpp:330-347: occ_choice in: index among allowed electrons; out: electron index
+__host__ __device__ inline unsigned mol_count_sing_virt(const MolView &m, const uint8_t *occ,
+                                                        const uint8_t cnt[FR_N_IRREPS][2], uint8_t *occ_choice) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned n = 0;
+    for (unsigned e = 0; e < ne; e++) {
+        unsigned va = cnt[m.symm[occ[e] % M]][e / (ne / 2)];
+        if (va != 0) {
+            if (n == *occ_choice) {
+                *occ_choice = (uint8_t)e;
+                return va;
+            }
+            n++;
+        }
+    }
+    return 0;
+}
+// virt_from_idx near_uniform.cpp:419-433
+__host__ __device__ inline unsigned mol_virt_from_idx(const MolView &m, uint64_t det, unsigned irrep, unsigned spin_shift,
+                                                      unsigned index) {
+    unsigned n = mol_lookup(m, irrep, 0);
+    for (unsigned s = 0; s < n; s++) {
+        unsigned orb = spin_shift + mol_lookup(m, irrep, 1 + s);
+        if (!fr_read_bit(det, orb)) {
+            if (index == 0) return orb;
+            index--;
+        }
+    }
+    return 255;
+}
+// find_nth_virt fci_utils.c:138-148 (occ must be readable at index n_elec: callers pad with 255)
+__host__ __device__ inline unsigned mol_find_nth_virt(const uint8_t *occ, unsigned spin, unsigned n_elec, unsigned n_orb,
+                                                      unsigned n) {
+    unsigned virt = (n_orb * spin + n) & 0xff;
+    for (unsigned i = n_elec / 2 * spin; i < n_elec && occ[i] <= virt; i++) virt = (virt + 1) & 0xff;
+    return virt;
+}
+// count_singex molecule.cpp:914-933
+__host__ __device__ inline unsigned mol_count_singex(const MolView &m, uint64_t det, const uint8_t *occ) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned n = 0;
+    for (unsigned e = 0; e < ne; e++) {
+        unsigned orb = occ[e], irrep = m.symm[orb % M], spin = orb / M;
+        unsigned ns = mol_lookup(m, irrep, 0);
+        for (unsigned s = 0; s < ns; s++)
+            if (!fr_read_bit(det, mol_lookup(m, irrep, s + 1) + M * spin)) n++;
+    }
+    return n;
+}
+
+// ---- a14: sing_ex_symm molecule.cpp:178-203 / doub_ex_symm :108-175 ------------------------------------------
+// Visitors are called in the reference's enumeration order; returning the count.  F: void(o, v) / void(o0,o1,v0,v1)
+template <class F>
+__host__ __device__ inline unsigned mol_for_each_sing(const MolView &m, uint64_t det, const uint8_t *occ, F &&f) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned n = 0;
+    for (unsigned i = 0; i < ne / 2; i++) {
+        unsigned io = occ[i];
+        for (unsigned a = 0; a < M; a++)
+            if (!fr_read_bit(det, a) && m.symm[io] == m.symm[a]) {
+                f(io, a);
+                n++;
+            }
+    }
+    for (unsigned i = ne / 2; i < ne; i++) {
+        unsigned io = occ[i];
+        for (unsigned a = M; a < 2 * M; a++)
+            if (!fr_read_bit(det, a) && m.symm[io - M] == m.symm[a - M]) {
+                f(io, a);
+                n++;
+            }
+    }
+    return n;
+}
+template <class F>
+__host__ __device__ inline unsigned mol_for_each_doub(const MolView &m, uint64_t det, const uint8_t *occ, F &&f) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned n = 0;
+    for (unsigned i = 0; i < ne / 2; i++) {  // different spin
+        unsigned io = occ[i];
+        for (unsigned j = ne / 2; j < ne; j++) {
+            unsigned jo = occ[j];
+            unsigned sij = m.symm[io] ^ m.symm[jo - M];
+            for (unsigned k = 0; k < M; k++) {
+                if (fr_read_bit(det, k)) continue;
+                unsigned sijk = sij ^ m.symm[k];
+                for (unsigned l = M; l < 2 * M; l++)
+                    if (!fr_read_bit(det, l) && (sijk ^ m.symm[l - M]) == 0) {
+                        f(io, jo, k, l);
+                        n++;
+                    }
+            }
+        }
+    }
+    for (unsigned i = 0; i < ne / 2; i++) {  // up-up
+        unsigned io = occ[i];
+        for (unsigned j = i + 1; j < ne / 2; j++) {
+            unsigned jo = occ[j];
+            unsigned sij = m.symm[io] ^ m.symm[jo];
+            for (unsigned k = 0; k < M; k++) {
+                if (fr_read_bit(det, k)) continue;
+                unsigned sijk = sij ^ m.symm[k];
+                for (unsigned l = k + 1; l < M; l++)
+                    if (!fr_read_bit(det, l) && (sijk ^ m.symm[l]) == 0) {
+                        f(io, jo, k, l);
+                        n++;
+                    }
+            }
+        }
+    }
+    for (unsigned i = ne / 2; i < ne; i++) {  // down-down
+        unsigned io = occ[i];
+        for (unsigned j = i + 1; j < ne; j++) {
+            unsigned jo = occ[j];
+            unsigned sij = m.symm[io - M] ^ m.symm[jo - M];
+            for (unsigned k = M; k < 2 * M; k++) {
+                if (fr_read_bit(det, k)) continue;
+                unsigned sijk = sij ^ m.symm[k - M];
+                for (unsigned l = k + 1; l < 2 * M; l++)
+                    if (!fr_read_bit(det, l) && (sijk ^ m.symm[l - M]) == 0) {
+                        f(io, jo, k, l);
+                        n++;
+                    }
+            }
+        }
+    }
+    return n;
+}
+
+// ---- a8: HB-PP weight rows heat_bathPP.cpp:182-412.  Each returns the reference's return value -----------------
+// calc_o1_probs :182-200; row length n_elec - (exclude_first > 0)
+__host__ __device__ inline double hb_o1_probs(const MolView &m, double *p, const uint8_t *occ, int exclude_first) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned skip = exclude_first > 0;
+    double norm = 0;
+    for (unsigned i = skip; i < ne / 2; i++) {
+        p[i - skip] = m.s_tens[occ[i]];
+        norm += p[i - skip];
+    }
+    for (unsigned i = ne / 2; i < ne; i++) {
+        p[i - skip] = m.s_tens[occ[i] - M];
+        norm += p[i - skip];
+    }
+    double inv = 1. / norm;
+    for (unsigned i = skip; i < ne; i++) p[i - skip] *= inv;
+    return norm / m.d.s_norm;
+}
+// calc_o2_probs :203-233; row length n_elec
+__host__ __device__ inline double hb_o2_probs(const MolView &m, double *p, const uint8_t *occ, unsigned o1_idx) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned o1 = occ[o1_idx], o1_spin = o1 / M, o1s = o1 % M;
+    double norm = 0;
+    unsigned off = (1 - o1_spin) * ne / 2;
+    for (unsigned i = off; i < ne / 2 + off; i++) {
+        p[i] = m.d_diff[o1s * M + occ[i] % M];
+        norm += p[i];
+    }
+    off = o1_spin * ne / 2;
+    for (unsigned i = off; i < o1_idx; i++) {
+        p[i] = m.d_same[FR_TRI_NODIAG(occ[i] % M, o1s)];
+        norm += p[i];
+    }
+    for (unsigned i = o1_idx + 1; i < ne / 2 + off; i++) {
+        p[i] = m.d_same[FR_TRI_NODIAG(o1s, occ[i] % M)];
+        norm += p[i];
+    }
+    p[o1_idx] = 0;
+    double inv = 1. / norm;
+    for (unsigned i = 0; i < ne; i++) p[i] *= inv;
+    return norm / m.s_tens[o1s];
+}
+// calc_o2_probs_half :236-270; row length o1_idx
+__host__ __device__ inline double hb_o2_probs_half(const MolView &m, double *p, const uint8_t *occ, unsigned o1_idx) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned o1 = occ[o1_idx], o1_spin = o1 / M;
+    double norm = 0;
+    unsigned upper = ne / 2 > o1_idx ? o1_idx : ne / 2;
+    for (unsigned i = 0; i < upper; i++) {
+        if (o1_spin == 0)
+            p[i] = m.d_same[FR_TRI_NODIAG((unsigned)occ[i], o1)];
+        else
+            p[i] = m.d_diff[(o1 - M) * M + occ[i]];
+        norm += p[i];
+    }
+    for (unsigned i = ne / 2; i < o1_idx; i++) {
+        if (o1_spin == 0)
+            p[i] = m.d_diff[o1 * M + occ[i] - M];
+        else
+            p[i] = m.d_same[FR_TRI_NODIAG((unsigned)occ[i] - M, o1 - M)];
+        norm += p[i];
+    }
+    double inv = 1. / norm;
+    for (unsigned i = 0; i < o1_idx; i++) p[i] *= inv;
+    return norm / m.s_tens[o1 % M];
+}
+// calc_u1_probs :273-319; row length M - n_elec / 2.  occ must be readable at index n_elec.
+__host__ __device__ inline double hb_u1_probs(const MolView &m, double *p, unsigned o1_orb, const uint8_t *occ,
+                                              int exclude_first) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    unsigned o1_spin = o1_orb / M, o1s = o1_orb % M, offset = o1_spin * M;
+    double norm = 0;
+    unsigned pi = 0, oi = ne / 2 * o1_spin;
+    unsigned curr = occ[oi];
+    for (unsigned k = 0; k < o1s; k++) {
+        if (k + offset == curr) {
+            oi++;
+            curr = occ[oi];
+        } else {
+            p[pi] = m.exch_sqrt[FR_TRI_NODIAG(k, o1s)];
+            norm += p[pi];
+            pi++;
+        }
+    }
+    oi++;
+    curr = oi <= ne ? occ[oi] : 255;
+    for (unsigned k = o1s + 1; k < M; k++) {
+        if (k + offset == curr) {
+            if (oi < ne - 1) {
+                oi++;
+                curr = occ[oi];
+            }
+        } else {
+            p[pi] = m.exch_sqrt[FR_TRI_NODIAG(o1s, k)];
+            norm += p[pi];
+            pi++;
+        }
+    }
+    if (exclude_first) {
+        norm -= p[0];
+        p[0] = 0;
+    }
+    double inv = 1. / norm;
+    for (unsigned i = 0; i < pi; i++) p[i] *= inv;
+    return norm / m.exch_norms[o1s];
+}
+// calc_u2_probs :322-365
+__host__ __device__ inline double hb_u2_probs(const MolView &m, double *p, unsigned o1_orb, unsigned o2_orb,
+                                              unsigned u1_orb, unsigned *len) {
+    const unsigned M = m.d.n_orb;
+    unsigned o2s = o2_orb % M, u1s = u1_orb % M;
+    bool same = (o1_orb / M) == (o2_orb / M);
+    unsigned irrep = m.symm[o1_orb % M] ^ m.symm[o2s] ^ m.symm[u1s];
+    unsigned num = mol_lookup(m, irrep, 0);
+    *len = num;
+    double norm = 0;
+    for (unsigned i = 0; i < num; i++) {
+        unsigned u2 = mol_lookup(m, irrep, i + 1);
+        if ((same && u2 != u1s) || !same) {
+            if (o2s == u2) {
+                p[i] = m.diag_sqrt[o2s];
+            } else {
+                unsigned mn = o2s < u2 ? o2s : u2, mx = o2s > u2 ? o2s : u2;
+                p[i] = m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
+            }
+            norm += p[i];
+        } else {
+            p[i] = 0;
+        }
+    }
+    if (norm != 0) {
+        double inv = 1 / norm;
+        for (unsigned i = 0; i < num; i++) {
+            unsigned u2 = mol_lookup(m, irrep, i + 1);
+            if ((same && u2 != u1s) || !same) p[i] *= inv;
+        }
+    }
+    return norm / m.exch_norms[o2s];
+}
+// calc_u2_probs_half :368-412
+__host__ __device__ inline double hb_u2_probs_half(const MolView &m, double *p, unsigned o1_orb, unsigned o2_orb,
+                                                   unsigned u1_orb, uint64_t det, unsigned *len) {
+    const unsigned M = m.d.n_orb;
+    unsigned o2s = o2_orb % M, u1s = u1_orb % M, u2_spin = o2_orb / M;
+    bool same = (o1_orb / M) == u2_spin;
+    unsigned irrep = m.symm[o1_orb % M] ^ m.symm[o2s] ^ m.symm[u1s];
+    unsigned num = mol_lookup(m, irrep, 0);
+    double norm = 0;
+    unsigned i;
+    for (i = 0; i < num; i++) {
+        unsigned u2 = mol_lookup(m, irrep, i + 1);
+        if (same && u2 >= u1s) break;
+        if (((same && u2 != u1s) || !same) && !fr_read_bit(det, u2 + M * u2_spin)) {
+            if (o2s == u2) {
+                p[i] = m.diag_sqrt[o2s];
+            } else {
+                unsigned mn = o2s < u2 ? o2s : u2, mx = o2s > u2 ? o2s : u2;
+                p[i] = m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
+            }
+            norm += p[i];
+        } else {
+            p[i] = 0;
+        }
+    }
+    *len = i;
+    if (norm != 0) {
+        double inv = 1 / norm;
+        for (unsigned k = 0; k < i; k++) p[k] *= inv;
+    }
+    return norm / m.exch_norms[o2s];
+}
+
+// ---- a9: total weights -----------------------------------------------------------------------------------------
+// calc_unnorm_wt :414-439
+__host__ __device__ inline double hb_unnorm_wt(const MolView &m, const uint8_t *orbs) {
+    const unsigned M = m.d.n_orb;
+    unsigned o1 = orbs[0] % M, o2 = orbs[1] % M, u1 = orbs[2] % M, u2 = orbs[3] % M;
+    unsigned mn1 = o1 < u1 ? o1 : u1, mx1 = o1 > u1 ? o1 : u1, mn2 = o2 < u2 ? o2 : u2, mx2 = o2 > u2 ? o2 : u2;
+    bool same = (orbs[0] / M) == (orbs[1] / M);
+    // NOTE the reference evaluates I_J_TO_TRI_NODIAG with uint8_t operands promoted to int; when
+    // mn == mx (o == u as spatial orbitals, opposite-spin partner) TRI_N(j-1)+i indexes as written.
+    int o1u1 = FR_TRI_NODIAG((int)mn1, (int)mx1), o2u2 = FR_TRI_NODIAG((int)mn2, (int)mx2);
+    double w;
+    if (same) {
+        int o1o2 = FR_TRI_NODIAG((int)o1, (int)o2);
+        w = m.d_same[o1o2] * (m.exch_sqrt[o1u1] * m.exch_sqrt[o2u2]) / m.d.s_norm / m.exch_norms[o1] / m.exch_norms[o2];
+    } else {
+        w = (m.d_diff[o2 * M + o1]) * m.exch_sqrt[o1u1] * m.exch_sqrt[o2u2] / m.d.s_norm / m.exch_norms[o1] /
+            m.exch_norms[o2];
+    }
+    return w;
+}
+// calc_norm_wt :442-598
+__host__ __device__ inline double hb_norm_wt(const MolView &m, const uint8_t *orbs, const uint8_t *occ, uint64_t det) {
+    const unsigned M = m.d.n_orb, ne = m.d.n_elec;
+    int o1 = orbs[0] % M, o1_spin = orbs[0] / M, o2 = orbs[1] % M, o2_spin = orbs[1] / M;
+    int u1 = orbs[2] % M, u2 = orbs[3] % M;
+    int mn_o1u1 = o1 < u1 ? o1 : u1, mx_o1u1 = o1 > u1 ? o1 : u1, mn_o2u2 = o2 < u2 ? o2 : u2,
+        mx_o2u2 = o2 > u2 ? o2 : u2;
+    bool same = o1_spin == o2_spin;
+    uint8_t os[FRIES_MAX_ELEC + 1];
+    for (unsigned i = 0; i < ne; i++) os[i] = occ[i] % M;
+    os[ne] = 255;
+    double s_denom = 0;
+    for (unsigned i = 0; i < ne; i++) s_denom += m.s_tens[os[i]];
+    unsigned i;
+    double d1 = 0;
+    unsigned off = (1 - o1_spin) * ne / 2;
+    for (i = off; i < ne / 2 + off; i++) d1 += m.d_diff[o1 * M + os[i]];
+    off = o1_spin * ne / 2;
+    for (i = off; (int)os[i] < o1; i++) d1 += m.d_same[FR_TRI_NODIAG((int)os[i], o1)];
+    for (i++; i < ne / 2 + off; i++) d1 += m.d_same[FR_TRI_NODIAG(o1, (int)os[i])];
+    double d2 = 0;
+    off = (1 - o2_spin) * ne / 2;
+    for (i = off; i < ne / 2 + off; i++) d2 += m.d_diff[o2 * M + os[i]];
+    off = o2_spin * ne / 2;
+    for (i = off; (int)os[i] < o2; i++) d2 += m.d_same[FR_TRI_NODIAG((int)os[i], o2)];
+    for (i++; i < ne / 2 + off; i++) d2 += m.d_same[FR_TRI_NODIAG(o2, (int)os[i])];
+
+    double e1_virt = 0;
+    unsigned offset = o1_spin * M;
+    for (int k = 0; k < o1; k++)
+        if (!fr_read_bit(det, k + offset)) e1_virt += m.exch_sqrt[FR_TRI_NODIAG(k, o1)];
+    for (int k = o1 + 1; k < (int)M; k++)
+        if (!fr_read_bit(det, k + offset)) e1_virt += m.exch_sqrt[FR_TRI_NODIAG(o1, k)];
+    double e2_virt = 0;
+    offset = o2_spin * M;
+    for (int k = 0; k < o2; k++)
+        if (!fr_read_bit(det, k + offset)) e2_virt += m.exch_sqrt[FR_TRI_NODIAG(k, o2)];
+    for (int k = o2 + 1; k < (int)M; k++)
+        if (!fr_read_bit(det, k + offset)) e2_virt += m.exch_sqrt[FR_TRI_NODIAG(o2, k)];
+
+    unsigned u1_irrep = m.symm[u1], u2_irrep = m.symm[u2];
+    double e2_no1 = 0, e2_no2 = 0, e1_no1 = 0, e1_no2 = 0;
+    unsigned n = mol_lookup(m, u2_irrep, 0);
+    for (unsigned k = 0; k < n; k++) {
+        int so = mol_lookup(m, u2_irrep, k + 1);
+        if ((same && so != u1) || !same) {
+            if (o2 == so) {
+                e2_no1 += m.diag_sqrt[o2];
+            } else {
+                int mn = o2 < so ? o2 : so, mx = o2 > so ? o2 : so;
+                e2_no1 += m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
+            }
+            if (o1 == so) {
+                e1_no1 += m.diag_sqrt[o1];
+            } else {
+                int mn = o1 < so ? o1 : so, mx = o1 > so ? o1 : so;
+                e1_no1 += m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
+            }
+        }
+    }
+    n = mol_lookup(m, u1_irrep, 0);
+    for (unsigned k = 0; k < n; k++) {
+        int so = mol_lookup(m, u1_irrep, k + 1);
+        if ((same && so != u2) || !same) {
+            if (o2 == so) {
+                e2_no2 += m.diag_sqrt[o2];
+            } else {
+                int mn = o2 < so ? o2 : so, mx = o2 > so ? o2 : so;
+                e2_no2 += m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
+            }
+            if (o1 == so) {
+                e1_no2 += m.diag_sqrt[o1];
+            } else {
+                int mn = o1 < so ? o1 : so, mx = o1 > so ? o1 : so;
+                e1_no2 += m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
+            }
+        }
+    }
+    int o1u1 = FR_TRI_NODIAG(mn_o1u1, mx_o1u1), o2u2 = FR_TRI_NODIAG(mn_o2u2, mx_o2u2);
+    double w;
+    if (same) {
+        int mn_o1u2 = o1 < u2 ? o1 : u2, mx_o1u2 = o1 > u2 ? o1 : u2, mn_o2u1 = o2 < u1 ? o2 : u1,
+            mx_o2u1 = o2 > u1 ? o2 : u1;
+        int o1o2 = FR_TRI_NODIAG(o1, o2), o1u2 = FR_TRI_NODIAG(mn_o1u2, mx_o1u2), o2u1 = FR_TRI_NODIAG(mn_o2u1, mx_o2u1);
+        w = m.d_same[o1o2] / s_denom *
+            (m.s_tens[o1] / d1 / e1_virt *
+                 (m.exch_sqrt[o1u1] * m.exch_sqrt[o2u2] / e2_no1 + m.exch_sqrt[o1u2] * m.exch_sqrt[o2u1] / e2_no2) +
+             m.s_tens[o2] / d2 / e2_virt *
+                 (m.exch_sqrt[o2u1] * m.exch_sqrt[o1u2] / e1_no1 + m.exch_sqrt[o2u2] * m.exch_sqrt[o1u1] / e1_no2));
+    } else {
+        w = (m.s_tens[o1] * m.d_diff[o1 * M + o2] / d1 / e1_virt / e2_no1 +
+             m.s_tens[o2] * m.d_diff[o2 * M + o1] / d2 / e2_virt / e1_no2) *
+            m.exch_sqrt[o1u1] * m.exch_sqrt[o2u2] / s_denom;
+    }
+    return w;
+}
+
+// occupied list + sentinel (find_bits math_utils.c:62-98); returns the electron count
+__host__ __device__ __forceinline__ int mol_occ_list(uint64_t key, uint8_t *occ) {
+    int n = fr_occ_list(key, occ);
+    occ[n] = 255;
+    return n;
+}

@@ -279,9 +279,11 @@ extern "C" int fries_vec_create(fries_ctx *c, size_t capacity, unsigned n_bits, 
     return FRIES_OK;
 }
 
+extern "C" int fries_hbpp_destroy(struct fries_hbpp *hb);
 extern "C" int fries_vec_destroy(fries_vec *v) {
     if (v) {
         cudaSetDevice(v->ctx->device);
+        if (v->hv_scratch) fries_hbpp_destroy(v->hv_scratch);
         delete v;
     }
     return FRIES_OK;

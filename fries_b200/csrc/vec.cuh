@@ -52,6 +52,8 @@ struct fries_vec {
     fries_mol *diag_mol = nullptr;
     double hf_en = 0;
     uint64_t last_spawned = 0;
+    unsigned cur_row = 0;                  // frifull_mol: row holding the current iterate (vec_idx)
+    struct fries_hbpp *hv_scratch = nullptr;  // spawn buffers of the stand-alone fries_h_apply
     std::vector<uint32_t> h_scr_vec, h_scr_proc;
 
     VecView view() {

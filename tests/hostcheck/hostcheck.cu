@@ -1,0 +1,141 @@
+// TEST INFRASTRUCTURE ONLY -- never loaded by the product.
+//
+// This container has no GPU.  The __host__ __device__ inline functions of fries_b200/csrc/mol.cuh and
+// common.cuh (the pure arithmetic the kernels are made of) are compiled here FOR THE HOST so that the
+// CPU-only test tier can check them against the compiled reference before GPU time is spent.  The
+// kernels themselves (launch geometry, scans, atomics, staging) are only checked by the -m gpu tests.
+#include "../../fries_b200/csrc/mol.cuh"
+#include <vector>
+
+struct HcMol {
+    MolView v;
+    std::vector<double> eris, hcore, blob;
+};
+
+extern "C" {
+
+// tables (hb_info) are supplied by the caller (the GPU path builds them with its own kernels)
+void *hc_mol_create(unsigned n_orb, unsigned n_elec_total, unsigned n_frz, const double *hcore, const double *eris_packed,
+                    size_t n_packed, const uint8_t *symm, const double *d_diff, const double *d_same,
+                    const double *s_tens, double s_norm, const double *exch_sqrt, const double *diag_sqrt,
+                    const double *exch_norms) {
+    HcMol *h = new HcMol();
+    unsigned M = n_orb, T = n_orb + n_frz / 2, TT = M * (M - 1) / 2;
+    MolDims &d = h->v.d;
+    d.n_orb = M; d.n_elec = n_elec_total - n_frz; d.n_frz = n_frz; d.tot_orb = T; d.s_norm = s_norm;
+    unsigned off = 0;
+    d.off_d_diff = off; off += M * M;
+    d.off_d_same = off; off += TT;
+    d.off_s_tens = off; off += M;
+    d.off_exch_sqrt = off; off += TT;
+    d.off_diag_sqrt = off; off += M;
+    d.off_exch_norms = off; off += M;
+    d.off_symm = off; off += (M + 7) / 8;
+    d.off_lookup = off; off += (FR_N_IRREPS * (M + 1) + 7) / 8;
+    d.blob_doubles = off;
+    h->blob.assign(off, 0.0);
+    memcpy(&h->blob[d.off_d_diff], d_diff, M * M * 8);
+    memcpy(&h->blob[d.off_d_same], d_same, TT * 8);
+    memcpy(&h->blob[d.off_s_tens], s_tens, M * 8);
+    memcpy(&h->blob[d.off_exch_sqrt], exch_sqrt, TT * 8);
+    memcpy(&h->blob[d.off_diag_sqrt], diag_sqrt, M * 8);
+    memcpy(&h->blob[d.off_exch_norms], exch_norms, M * 8);
+    uint8_t *sy = (uint8_t *)&h->blob[d.off_symm], *lk = (uint8_t *)&h->blob[d.off_lookup];
+    memcpy(sy, symm, M);
+    d.max_n_symm = 0;
+    for (unsigned i = 0; i < M; i++) {
+        uint8_t s = symm[i], c = lk[s * (M + 1)];
+        lk[s * (M + 1) + 1 + c] = (uint8_t)i;
+        lk[s * (M + 1)] = c + 1;
+        if ((unsigned)c + 1 > d.max_n_symm) d.max_n_symm = c + 1;
+    }
+    h->eris.assign(eris_packed, eris_packed + n_packed);
+    h->hcore.assign(hcore, hcore + (size_t)T * T);
+    h->v.eris = h->eris.data();
+    h->v.hcore = h->hcore.data();
+    mol_bind_blob(h->v, h->blob.data());
+    return h;
+}
+void hc_mol_destroy(void *p) { delete (HcMol *)p; }
+
+uint64_t hc_hash(uint64_t key, const uint32_t *scr) { return fr_det_hash(key, scr); }
+int hc_bit_op(int op, uint64_t *key, const uint8_t *o) {
+    switch (op) {
+        case 0: return fr_sing_det_parity(*key, o[0], o[1]);
+        case 1: return fr_doub_det_parity(*key, o[0], o[1], o[2], o[3]);
+        case 2: return fr_sing_parity(*key, o[0], o[1]);
+        case 3: return fr_doub_parity(*key, o[0], o[1], o[2], o[3]);
+        case 4: return fr_bits_between(*key, o[0], o[1]);
+    }
+    return 0;
+}
+double hc_diag(void *p, uint64_t key) {
+    uint8_t occ[FRIES_MAX_ELEC + 1];
+    mol_occ_list(key, occ);
+    return mol_diag(((HcMol *)p)->v, occ);
+}
+double hc_sing_el(void *p, uint64_t key, const uint8_t *o) {
+    uint8_t occ[FRIES_MAX_ELEC + 1];
+    mol_occ_list(key, occ);
+    return mol_sing_el(((HcMol *)p)->v, o[0], o[1], occ);
+}
+double hc_doub_el(void *p, const uint8_t *o) { return mol_doub_el(((HcMol *)p)->v, o); }
+size_t hc_sing_ex(void *p, uint64_t key, uint8_t *out) {
+    uint8_t occ[FRIES_MAX_ELEC + 1];
+    mol_occ_list(key, occ);
+    size_t n = 0;
+    mol_for_each_sing(((HcMol *)p)->v, key, occ, [&](unsigned a, unsigned b) { out[2 * n] = a; out[2 * n + 1] = b; n++; });
+    return n;
+}
+size_t hc_doub_ex(void *p, uint64_t key, uint8_t *out) {
+    uint8_t occ[FRIES_MAX_ELEC + 1];
+    mol_occ_list(key, occ);
+    size_t n = 0;
+    mol_for_each_doub(((HcMol *)p)->v, key, occ, [&](unsigned a, unsigned b, unsigned k, unsigned l) {
+        out[4 * n] = a; out[4 * n + 1] = b; out[4 * n + 2] = k; out[4 * n + 3] = l; n++;
+    });
+    return n;
+}
+size_t hc_count_singex(void *p, uint64_t key) {
+    uint8_t occ[FRIES_MAX_ELEC + 1];
+    mol_occ_list(key, occ);
+    return mol_count_singex(((HcMol *)p)->v, key, occ);
+}
+int hc_find_nth_virt(const uint8_t *occ, int spin, int n_elec, int n_orb, int n) {
+    return mol_find_nth_virt(occ, spin, n_elec, n_orb, n);
+}
+double hc_hb_row(void *p, int which, uint64_t key, int a0, int a1, int a2, double *row, int *len) {
+    const MolView &m = ((HcMol *)p)->v;
+    uint8_t occ[FRIES_MAX_ELEC + 1];
+    mol_occ_list(key, occ);
+    unsigned L = 0;
+    double r = 0;
+    switch (which) {
+        case 0: r = hb_o1_probs(m, row, occ, a0); L = m.d.n_elec - (a0 > 0); break;
+        case 1: r = hb_o2_probs(m, row, occ, a0); L = m.d.n_elec; break;
+        case 2: r = hb_o2_probs_half(m, row, occ, a0); L = a0; break;
+        case 3: r = hb_u1_probs(m, row, a0, occ, a1); L = m.d.n_orb - m.d.n_elec / 2; break;
+        case 4: r = hb_u2_probs(m, row, a0, a1, a2, &L); break;
+        case 5: r = hb_u2_probs_half(m, row, a0, a1, a2, key, &L); break;
+    }
+    *len = (int)L;
+    return r;
+}
+double hc_hb_wt(void *p, int normalized, uint64_t key, const uint8_t *orbs) {
+    const MolView &m = ((HcMol *)p)->v;
+    uint8_t occ[FRIES_MAX_ELEC + 1];
+    mol_occ_list(key, occ);
+    return normalized ? hb_norm_wt(m, orbs, occ, key) : hb_unnorm_wt(m, orbs);
+}
+// symmetry counters for singles: returns n_occ allowed; *n_virt for the occ_choice-th allowed electron
+unsigned hc_sing_counts(void *p, uint64_t key, unsigned occ_choice, unsigned *elec_idx, unsigned *n_virt) {
+    const MolView &m = ((HcMol *)p)->v;
+    uint8_t occ[FRIES_MAX_ELEC + 1], cnt[FR_N_IRREPS][2];
+    mol_occ_list(key, occ);
+    mol_count_symm_virt(m, occ, cnt);
+    uint8_t ch = (uint8_t)occ_choice;
+    *n_virt = mol_count_sing_virt(m, occ, cnt, &ch);
+    *elec_idx = ch;
+    return mol_count_sing_allowed(m, occ, cnt);
+}
+}

@@ -1,0 +1,347 @@
+"""GPU tier: every C-ABI entry point against the reference's own code (oracle/_ref/libfries_ref.so, built from
+/root/reference by oracle/Makefile; it travels to the GPU box as a built artefact).
+
+Bars: bit-exact for integer / index work (hashes, owners, parities, enumeration order, kept sets, sampled index
+sets up to counted FP-boundary ties), 1e-12 relative for FP64 matrix elements and H.v."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import reflib
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not reflib.available(), reason="oracle/_ref not built")]
+
+REL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import fries_b200
+    c = fries_b200.Context(0)
+    yield c
+    c.close()
+
+
+def rand_dets(rng, n, n_orb, half):
+    a = np.argsort(rng.random((n, n_orb)), axis=1)[:, :half].astype(np.uint64)
+    b = np.argsort(rng.random((n, n_orb)), axis=1)[:, :half].astype(np.uint64)
+    return ((np.uint64(1) << a).sum(axis=1) | ((np.uint64(1) << b).sum(axis=1) << np.uint64(n_orb))).astype(np.uint64)
+
+
+# ---- a1 -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_ranks", [1, 2, 8])
+def test_hash_owner(ctx, n_ranks):
+    import fries_b200
+    rng = np.random.default_rng(0)
+    for n_orb, half, scr in [(4, 2, np.arange(1, 9, dtype=np.uint32)),  # tests/test_vector.cpp:192-224 scramblers
+                             (4, 2, np.arange(8, 0, -1, dtype=np.uint32)),
+                             (26, 5, rng.integers(0, 2**32, 52, dtype=np.uint64).astype(np.uint32))]:
+        keys = np.unique(rand_dets(rng, 100000 if n_orb > 4 else 200, n_orb, half))
+        h, o = fries_b200.hash_owner(ctx, keys, scr, n_ranks)
+        rh = np.zeros(keys.size, np.uint64)
+        ro = np.zeros(keys.size, np.int32)
+        reflib.lib().ref_hash_keys(keys, keys.size, 2 * n_orb, scr, n_ranks, rh, ro)
+        assert np.array_equal(h, rh) and np.array_equal(o, ro)
+    h, o = fries_b200.hash_owner(ctx, np.zeros(0, np.uint64), np.ones(8, np.uint32), 1)  # empty input
+    assert h.size == 0
+
+
+# ---- a15 ----------------------------------------------------------------------------------------------------
+def test_bit_ops(ctx):
+    import fries_b200
+    rng = np.random.default_rng(1)
+    n_orb, half = 26, 5
+    keys = rand_dets(rng, 4000, n_orb, half)
+    L = reflib.lib()
+    sing, doub = [], []
+    for k in keys:
+        occ = [i for i in range(2 * n_orb) if (int(k) >> i) & 1]
+        vir = [i for i in range(2 * n_orb) if not (int(k) >> i) & 1]
+        o = rng.choice(occ, 2, replace=False)
+        v = rng.choice(vir, 2, replace=False)
+        sing.append([o[0], v[0]])
+        doub.append([min(o), max(o), min(v), max(v)])
+    sing, doub = np.array(sing, np.uint8), np.array(doub, np.uint8)
+    for op, orbs, fn, upd in [(0, sing, L.ref_sing_det_parity, True), (1, doub, L.ref_doub_det_parity, True),
+                              (2, sing, L.ref_sing_parity, False), (3, doub, L.ref_doub_parity, False)]:
+        nk, sg = fries_b200.bit_op(ctx, op, keys, orbs)
+        for i in range(keys.size):
+            if upd:
+                kk = C.c_uint64(int(keys[i]))
+                assert fn(C.byref(kk), np.ascontiguousarray(orbs[i])) == sg[i]
+                assert kk.value == int(nk[i])
+            else:
+                assert fn(int(keys[i]), np.ascontiguousarray(orbs[i])) == sg[i]
+                assert nk[i] == keys[i]
+    ab = np.stack([rng.integers(0, 52, 4000), rng.integers(0, 52, 4000)], 1).astype(np.uint8)
+    ab = ab[ab[:, 0] != ab[:, 1]]
+    _, cnt = fries_b200.bit_op(ctx, 4, keys[:len(ab)], ab)
+    for i in range(len(ab)):
+        assert L.ref_bits_between(int(keys[i]), int(ab[i, 0]), int(ab[i, 1])) == cnt[i]
+
+
+# ---- a4 / a5 ------------------------------------------------------------------------------------------------
+def make_values(rng, n, kind):
+    if kind == "lognormal":
+        v = rng.lognormal(0, 2.5, n)
+    elif kind == "uniform":
+        v = rng.random(n)
+    else:  # a few giants + dust, like an FRI iterate
+        v = np.concatenate([rng.lognormal(6, 1, max(1, n // 100)), rng.lognormal(-3, 2, n - max(1, n // 100))])
+        rng.shuffle(v)
+    v *= rng.choice([-1.0, 1.0], n)
+    v[rng.random(n) < 0.05] = 0.0
+    return v
+
+
+@pytest.mark.parametrize("n,budget,kind", [(1, 1, "uniform"), (7, 3, "lognormal"), (1000, 100, "lognormal"),
+                                            (1000, 2000, "uniform"), (50000, 5000, "fri"), (300000, 30000, "fri"),
+                                            (300000, 250000, "lognormal")])
+def test_find_preserve_sys_comp(ctx, n, budget, kind):
+    import fries_b200
+    rng = np.random.default_rng(n + budget)
+    v = make_values(rng, n, kind)
+    r_loc, r_glob, r_left, r_keep = reflib.find_preserve(v, budget)
+    g_loc, g_glob, g_left, g_keep = fries_b200.find_preserve(ctx, v, budget)
+    assert np.array_equal(g_keep, r_keep), f"kept sets differ in {np.sum(g_keep != r_keep)} places"
+    assert g_left == r_left
+    assert g_glob == pytest.approx(r_glob, rel=REL)
+    assert g_loc == pytest.approx(r_loc, rel=REL, abs=1e-300)
+    for rn in (0.0, 0.37, 0.999999):
+        rv, rk, rnorm = reflib.sys_comp(v, r_loc, r_left, r_keep, rn)
+        gv, gk, gnorm = fries_b200.sys_comp(ctx, v, [g_loc], g_left, g_keep, rn)
+        ties = int(np.sum(gk != rk))
+        # an element whose interval boundary coincides with a grid point to ~1 ulp may flip: count and bound
+        assert ties <= max(2, n // 50000), f"{ties} sampled-set mismatches"
+        same = gk == rk
+        assert np.allclose(gv[same], rv[same], rtol=REL, atol=0)
+        assert gnorm[0] == pytest.approx(rnorm, rel=1e-9)
+        assert np.sum(gv != 0) == pytest.approx(np.sum(rv != 0), abs=2)
+
+
+def test_compression_identity_when_budget_exceeds_nnz(ctx):
+    """tests/test_compression.cpp:64-118"""
+    import fries_b200
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=10)
+    loc, glob, left, keep = fries_b200.find_preserve(ctx, v, 20)
+    out, dele, _ = fries_b200.sys_comp(ctx, v, [loc], left, keep, 0.5)
+    assert np.array_equal(out, v) and not dele.any()
+
+
+# ---- a6 -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,n_sub,budget,jagged", [(5, 2, 4, False), (200, 8, 50, False), (3000, 11, 700, True),
+                                                    (40000, 18, 9000, True), (40000, 2, 60000, False)])
+def test_comp_sub(ctx, n, n_sub, budget, jagged):
+    import fries_b200
+    rng = np.random.default_rng(n * 7 + n_sub)
+    v = rng.lognormal(0, 2, n)
+    v[rng.random(n) < 0.03] = 0
+    nd = np.where(rng.random(n) < 0.4, rng.integers(1, 30, n), 0).astype(np.uint32)
+    sw = rng.random((n, n_sub)) ** 3
+    sw[rng.random((n, n_sub)) < 0.1] = 0
+    ss = None
+    if jagged:
+        ss = rng.integers(1, n_sub + 1, n).astype(np.uint16)
+        for i in range(n):
+            sw[i, ss[i]:] = 0
+    tot = sw.sum(1, keepdims=True)
+    tot[tot == 0] = 1
+    sw = sw / tot
+    cap = 4 * max(budget, n) + 64
+    for rn in (0.123, 0.9):
+        rv, ri = reflib.comp_sub(v, nd, sw, ss, budget, rn, cap)
+        gv, gi, left, loc = fries_b200.comp_sub(ctx, v, nd, sw, ss, budget, rn, cap)
+        rset = {(int(a), int(b)): x for (a, b), x in zip(ri, rv)}
+        gset = {(int(a), int(b)): x for (a, b), x in zip(gi, gv)}
+        diff = set(rset) ^ set(gset)
+        assert len(diff) <= max(2, n // 10000), f"{len(diff)} index mismatches of {len(rset)}"
+        for k in set(rset) & set(gset):
+            assert gset[k] == pytest.approx(rset[k], rel=1e-10)
+        if not diff:
+            assert np.array_equal(gi, ri)  # same order as the reference
+
+
+# ---- molecular Hamiltonian --------------------------------------------------------------------------------------
+@pytest.fixture(scope="module", params=[("ne", 2, False), ("h2o", 3, True), ("n2", 7, True)])
+def mols(request, ctx):
+    import fries_b200
+    from fries_b200.synth import SynthMol
+    name, seed, frozen = request.param
+    sm = SynthMol(name, seed, frozen)
+    rm = reflib.RefMol(sm)
+    gm = fries_b200.Mol.from_synth(ctx, sm)
+    yield sm, rm, gm
+    gm.close()
+
+
+def test_hb_tables(mols):
+    sm, rm, gm = mols
+    rt, gt = rm.hb_tables(), gm.hb_tables()
+    for k in rt:
+        assert np.allclose(gt[k], rt[k], rtol=REL, atol=0), k
+
+
+def test_matrix_elements(mols):
+    sm, rm, gm = mols
+    rng = np.random.default_rng(5)
+    keys = np.concatenate([[sm.hf], sm.random_dets(300, rng, None)]).astype(np.uint64)
+    assert np.allclose(gm.diag(keys), rm.diag(keys), rtol=REL, atol=0)
+    so, se = gm.sing_ex(keys[:40])
+    do, de = gm.doub_ex(keys[:40])
+    for i, k in enumerate(keys[:40]):
+        assert np.array_equal(se[so[i]:so[i + 1]], rm.sing_ex(k))   # same excitations in the same order
+        assert np.array_equal(de[do[i]:do[i + 1]], rm.doub_ex(k))
+    skeys = np.repeat(keys[:40], np.diff(so).astype(np.int64))
+    assert np.allclose(gm.sing_el(skeys, se), rm.sing_el(skeys, se), rtol=REL, atol=1e-15)
+    assert np.allclose(gm.doub_el(de), rm.doub_el(de), rtol=REL, atol=1e-15)
+    dkeys = np.repeat(keys[:40], np.diff(do).astype(np.int64))
+    sel = rng.choice(len(de), 2000, replace=False)
+    for nrm in (0, 1):
+        g = gm.hb_wt(nrm, dkeys[sel], de[sel])
+        r = np.array([rm.hb_wt(nrm, dkeys[j], de[j]) for j in sel])
+        assert np.allclose(g, r, rtol=REL, atol=0)
+
+
+def test_hb_rows(mols):
+    sm, rm, gm = mols
+    rng = np.random.default_rng(6)
+    keys = sm.random_dets(60, rng, None)
+    M, ne = sm.n_orb, sm.n_elec
+    for which in range(6):
+        ks, args = [], []
+        for k in keys:
+            occ = [i for i in range(2 * M) if (int(k) >> i) & 1]
+            vir = [i for i in range(2 * M) if i not in occ]
+            for _ in range(6):
+                o1i, o2i = sorted(rng.choice(ne, 2, replace=False))[::-1]
+                u1 = int(rng.choice([x for x in vir if x // M == occ[o1i] // M]))
+                a = {0: [int(rng.integers(0, 2)), 0, 0, 0], 1: [int(o1i), 0, 0, 0], 2: [int(o1i), 0, 0, 0],
+                     3: [occ[o1i], int(rng.integers(0, 2)), 0, 0], 4: [occ[o1i], occ[o2i], u1, 0],
+                     5: [occ[o1i], occ[o2i], u1, 0]}[which]
+                ks.append(k)
+                args.append(a)
+        rows, ln, nm = gm.hb_rows(which, np.array(ks, np.uint64), np.array(args, np.int32))
+        for i, (k, a) in enumerate(zip(ks, args)):
+            r, rrow = rm.hb_row(which, k, a[0], a[1], a[2])
+            assert ln[i] == len(rrow)
+            assert np.allclose(rows[i, :ln[i]], rrow, rtol=REL, atol=0, equal_nan=True)
+            assert nm[i] == pytest.approx(r, rel=REL, nan_ok=True)
+
+
+@pytest.mark.parametrize("new_hb", [0, 1])
+@pytest.mark.parametrize("n_det,n_samp", [(1, 50), (500, 2000), (20000, 30000)])
+def test_apply_hbpp_sys(mols, new_hb, n_det, n_samp):
+    sm, rm, gm = mols
+    rng = np.random.default_rng(n_det + new_hb)
+    keys = np.concatenate([[sm.hf], sm.random_dets(n_det - 1, rng, 0)]).astype(np.uint64) if n_det > 1 else \
+        np.array([sm.hf], np.uint64)
+    vals = make_values(rng, n_det, "fri")
+    vals[0] = 100.0
+    p_doub = 0.97
+    cap = 4 * n_samp + 4 * n_det
+    for seed in (1, 2):
+        uni, rv, rd, ro = rm.apply_hbpp_sys(keys, vals, p_doub, new_hb, seed, n_samp, cap)
+        gv, gd, go = gm.apply_hbpp_sys(keys, vals, p_doub, new_hb, uni, n_samp, cap)
+        rset = {(int(d), tuple(o)): v for d, o, v in zip(rd, ro.tolist(), rv)}
+        gset = {(int(d), tuple(o)): v for d, o, v in zip(gd, go.tolist(), gv)}
+        diff = set(rset) ^ set(gset)
+        # five systematic-resampling stages: a boundary tie in an early stage moves a few downstream samples
+        assert len(diff) <= max(4, len(rset) // 2000), f"{len(diff)} of {len(rset)} samples differ"
+        for k in set(rset) & set(gset):
+            assert gset[k] == pytest.approx(rset[k], rel=1e-9)
+        if not diff:
+            assert np.array_equal(gd, rd) and np.array_equal(go, ro)
+
+
+# ---- a2 / a3 ------------------------------------------------------------------------------------------------------
+def test_vec_add_merge_delete(ctx):
+    import fries_b200
+    rng = np.random.default_rng(9)
+    n_orb, half = 26, 5
+    n_bits = 2 * n_orb
+    ps = rng.integers(0, 2**32, n_bits, dtype=np.uint64).astype(np.uint32)
+    vs = rng.integers(0, 2**32, n_bits, dtype=np.uint64).astype(np.uint32)
+    pool = np.unique(rand_dets(rng, 30000, n_orb, half))
+    L = reflib.lib()
+    rvec = L.ref_vec_create(100000, 50000, n_bits, 2 * half, 2, ps, vs)
+    gvec = fries_b200.Vec(ctx, 100000, n_bits, 2 * half, 2, ps, vs)
+    try:
+        for rnd, (origin, dest) in enumerate([(0, 0), (0, 1), (0, 1), (0, 0)]):
+            n = 40000
+            keys = rng.choice(pool, n)
+            keys[: n // 50] = pool[0]  # a hot determinant (hash-merge contention)
+            vals = rng.normal(size=n)
+            vals[rng.random(n) < 0.02] = 0
+            ini = (rng.random(n) < (1.0 if rnd == 0 else 0.5)).astype(np.uint8)
+            L.ref_vec_add(rvec, keys, vals, ini, n, origin, dest)
+            gvec.add(keys, vals, ini, origin, dest)
+            cs = L.ref_vec_curr_size(rvec)
+            rk = np.zeros(cs, np.uint64)
+            rv = np.zeros((2, cs))
+            L.ref_vec_dump(rvec, rk, rv.reshape(-1), 2)
+            gk, gv = gvec.download()
+            assert gvec.curr_size() == cs
+            ro, go = np.argsort(rk), np.argsort(gk)
+            assert np.array_equal(rk[ro], gk[go])
+            assert np.allclose(gv[:, go], rv[:, ro], rtol=1e-11, atol=1e-12)
+            assert gvec.nonini_occ_add() == L.ref_vec_nonini_occ_add(rvec)
+        # dot + norm
+        tk = rng.choice(pool, 500, replace=False)
+        tv = rng.normal(size=500)
+        gk, gv = gvec.download()
+        lut = dict(zip(gk.tolist(), gv[0].tolist()))
+        want = sum(lut.get(int(k), 0.0) * x for k, x in zip(tk, tv))
+        assert gvec.dot(tk, tv, 0) == pytest.approx(want, rel=1e-11)
+        assert gvec.local_norm(1) == pytest.approx(np.abs(gv[1]).sum(), rel=1e-12)
+        # delete: only flagged elements that are zero in every row go away (del_at_pos vec_utils.hpp:458-476)
+        flags = (rng.random(gk.size) < 0.5).astype(np.uint8)
+        gone = flags.astype(bool) & (gv[0] == 0) & (gv[1] == 0)
+        gvec.delete(flags)
+        k2, v2 = gvec.download()
+        assert np.array_equal(k2, gk[~gone]) and np.array_equal(v2, gv[:, ~gone])  # stable compaction
+        assert gvec.dot(tk, tv, 0) == pytest.approx(want, rel=1e-11)                 # index rebuilt
+    finally:
+        L.ref_vec_destroy(rvec)
+        gvec.close()
+
+
+def test_vec_rejects_wrong_electron_count(ctx):
+    import fries_b200
+    from fries_b200._capi import FriesError
+    s = np.arange(1, 9, dtype=np.uint32)
+    v = fries_b200.Vec(ctx, 16, 8, 4, 1, s, s)
+    with pytest.raises(FriesError):  # DistVec::idx_to_hash throws (vec_utils.hpp:389-399)
+        v.add(np.array([0b0111], np.uint64), np.ones(1), np.ones(1, np.uint8))
+    v.close()
+
+
+# ---- a16 ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_par", [1, 40])
+def test_h_apply(mols, ctx, n_par):
+    import fries_b200
+    sm, rm, gm = mols
+    rng = np.random.default_rng(12)
+    n_bits = sm.n_bits
+    ps = rng.integers(0, 2**32, n_bits, dtype=np.uint64).astype(np.uint32)
+    vs = rng.integers(0, 2**32, n_bits, dtype=np.uint64).astype(np.uint32)
+    keys = np.concatenate([[sm.hf], sm.random_dets(n_par - 1, rng, 0)]).astype(np.uint64) if n_par > 1 else \
+        np.array([sm.hf], np.uint64)
+    vals = rng.normal(size=n_par)
+    cap = 400000
+    rk, rv = rm.h_apply(keys, vals, 1.0, -0.01, cap, ps, vs)
+    vec = fries_b200.Vec(ctx, cap, n_bits, sm.n_elec, 2, ps, vs)
+    try:
+        vec.set_diag_mol(gm, 0.0)
+        vec.add(keys, vals, np.ones(n_par, np.uint8))
+        n_sp = vec.h_apply(gm, 0, 1, 1.0, -0.01)
+        gk, gv = vec.download()
+        ro, go = np.argsort(rk), np.argsort(gk)
+        assert np.array_equal(rk[ro], gk[go])
+        scale = np.abs(rv).max()
+        assert np.allclose(gv[1][go], rv[ro], rtol=REL, atol=REL * scale)
+        want = sum(len(rm.sing_ex(k)) + len(rm.doub_ex(k)) for k in keys)
+        assert n_sp == want
+    finally:
+        vec.close()
