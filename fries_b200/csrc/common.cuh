@@ -298,15 +298,26 @@ __device__ __forceinline__ void block_excl_scan(double a, unsigned long long c, 
     __syncthreads();
 }
 
-// number of systematic-sampling grid points g_k = rn0 + k*unit (k = 0,1,...) strictly below x
-// (the reference tests `rn_sys < lbound` with rn_sys += unit: compress_utils.cpp:313-318,745-755).
-__device__ __forceinline__ long long sys_count_below(double x, double rn0, double unit) {
-    if (!(x > rn0)) return 0;  // also handles rn0 = INFINITY (n_samp == 0)
-    double q = (x - rn0) / unit;
-    long long k = (long long)ceil(q);
-    if (k < 0) k = 0;
-    // make the count consistent with the FP grid fl(rn0 + k*unit)
-    while (k > 0 && !(fma((double)(k - 1), unit, rn0) < x)) k--;
-    while (fma((double)k, unit, rn0) < x) k++;
-    return k;
-}
+// The systematic-sampling grid g_k = rn0 + k * unit, k = 0 .. n - 1 (n = sampling budget).  The reference
+// walks it with a running `rn_sys += unit` and the test `rn_sys < lbound` (compress_utils.cpp:313-318,
+// 745-755); here an element asks how many grid points lie strictly below a bound.  Indices >= n do not
+// exist (in exact arithmetic g_n >= the total weight), which keeps a prefix sum that is one ulp above the
+// total from drawing an (n+1)-th sample.
+struct SysGrid {
+    double rn0, unit;
+    long long n;
+    __device__ __forceinline__ double point(long long k) const {
+        return k < n ? fma((double)k, unit, rn0) : INFINITY;
+    }
+    __device__ __forceinline__ long long count_below(double x) const {
+        if (n <= 0 || !(x > rn0)) return 0;
+        double q = (x - rn0) / unit;
+        long long k = q >= (double)n ? n : (long long)ceil(q);
+        if (k < 0) k = 0;
+        if (k > n) k = n;
+        // make the count consistent with the FP grid fl(rn0 + k*unit)
+        while (k > 0 && !(fma((double)(k - 1), unit, rn0) < x)) k--;
+        while (k < n && fma((double)k, unit, rn0) < x) k++;
+        return k;
+    }
+};

@@ -127,13 +127,23 @@ sys_comp_kernel(double *__restrict__ vals, size_t n, const unsigned long long *_
         n_samp = (unsigned)in_r4[2];
         lbound0 = 0;
     }
-    double rn0, unit;
+    SysGrid sg;
     if (n_samp > 0) {
-        rn0 = seed_sys_dev(lbound0, G, rn_uniform, n_samp);
-        unit = G / n_samp;
+        // seed_sys :107-127: this shard's first grid point is global grid index j0 (or j0 + 1)
+        sg.unit = G / n_samp;
+        long long j0 = (long long)(int)(lbound0 * n_samp / G);
+        double r = rn_uniform * sg.unit;
+        r += sg.unit * (int)(lbound0 * n_samp / G);
+        if (r < lbound0) {
+            r += sg.unit;
+            j0++;
+        }
+        sg.rn0 = r;
+        sg.n = (long long)n_samp - j0;
     } else {
-        rn0 = INFINITY;
-        unit = INFINITY;
+        sg.rn0 = INFINITY;
+        sg.unit = INFINITY;
+        sg.n = 0;
     }
     double cs = 0;
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
@@ -162,8 +172,7 @@ sys_comp_kernel(double *__restrict__ vals, size_t n, const unsigned long long *_
             } else if (v != 0) {
                 double start = carry + ex;
                 double lbound = start + m;
-                long long k0 = sys_count_below(start, rn0, unit);
-                double g = fma((double)k0, unit, rn0);
+                double g = sg.point(sg.count_below(start));
                 if (g < lbound) {
                     double nv = G / n_samp;
                     vals[i] = v > 0 ? nv : -nv;

@@ -241,13 +241,14 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
 
     // ---- resampling (sys_sub :702-794) ----
     const double G = loc_final;
-    double rn0, unit;
+    SysGrid sg;
+    sg.n = nrem;
     if (nrem > 0) {
-        rn0 = seed_sys_dev(0.0, G, rn_uniform, nrem);
-        unit = G / nrem;
+        sg.rn0 = seed_sys_dev(0.0, G, rn_uniform, nrem);
+        sg.unit = G / nrem;
     } else {
-        rn0 = INFINITY;
-        unit = INFINITY;
+        sg.rn0 = INFINITY;
+        sg.unit = INFINITY;
     }
 
     // pass 1: chunk sums of the residual weights -> canonical CTA boundaries
@@ -283,12 +284,12 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                     if (b.keep[i]) {
                         k = nd;
                     } else {
-                        long long k0 = sys_count_below(start, rn0, unit), k1 = sys_count_below(lbound, rn0, unit);
+                        long long k0 = sg.count_below(start), k1 = sg.count_below(lbound);
                         k = (uint32_t)(k1 > k0 ? k1 - k0 : 0);
                     }
                 } else {
-                    long long k0 = sys_count_below(start, rn0, unit);
-                    double g = fma((double)k0, unit, rn0);
+                    long long k0 = sg.count_below(start);
+                    double g = sg.point(k0);
                     if (wr < v || g < lbound) {
                         double w[FRIES_MAX_SUB];
                         prov.row(i, w);
@@ -302,7 +303,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                                 if (g < sub_lb && w[j] != 0) {
                                     k++;
                                     k0++;
-                                    g = fma((double)k0, unit, rn0);
+                                    g = sg.point(k0);
                                     if (g < sub_lb) anomalies++;
                                 }
                             }
@@ -354,9 +355,9 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                     double each = v / nd;
                     for (uint32_t j = 0; j < nd; j++) FR_EMIT(each, j);
                 } else {
-                    long long k0 = sys_count_below(start, rn0, unit);
+                    long long k0 = sg.count_below(start);
                     for (uint32_t t = 0; t < k; t++) {
-                        double g = fma((double)(k0 + t), unit, rn0);
+                        double g = sg.point(k0 + t);
                         unsigned long long sub = (unsigned long long)((lbound - g) * nd / v);
                         if (sub >= nd) {
                             sub = nd - 1;
@@ -369,8 +370,8 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                 double w[FRIES_MAX_SUB];
                 prov.row(i, w);
                 uint32_t ns = b.nsub[i], kb = b.keep[i];
-                long long k0 = sys_count_below(start, rn0, unit);
-                double g = fma((double)k0, unit, rn0);
+                long long k0 = sg.count_below(start);
+                double g = sg.point(k0);
                 double sub_lb = lbound - wr;
                 for (uint32_t j = 0; j < ns; j++) {
                     if (((kb >> j) & 1u) && w[j] != 0) {
@@ -380,7 +381,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                         if (g < sub_lb && w[j] != 0) {
                             FR_EMIT(samp_val, j);
                             k0++;
-                            g = fma((double)k0, unit, rn0);
+                            g = sg.point(k0);
                         }
                     }
                 }

@@ -1,0 +1,1193 @@
+/* fries_oracle.c -- plain-C restatement of the reference's algorithm for the FRI hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see fries_oracle.h).  Sequential, single-threaded, written to follow the
+ * reference's control flow and FP operation order so that results can be compared bit for bit with
+ * the compiled reference (oracle/_ref) -- tests/test_oracle_vs_ref.py does exactly that -- and with the
+ * golden vectors under tests/golden/.  Nothing here is shared with fries_b200/csrc.
+ */
+#include "fries_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define FO_PRIME 1099511628211ull
+#define TRI_N(n) ((n) * ((n) + 1) / 2)
+#define TRI_NODIAG(i, j) (TRI_N((j)-1) + (i))
+#define TRI_WDIAG(i, j) (TRI_N(j) + (i))
+
+/* ================================ L1 bit utilities ================================================= */
+
+/* find_bits math_utils.c:62-98: ascending positions of the set bits */
+int fo_find_bits(uint64_t key, uint8_t *occ) {
+    int n = 0;
+    for (int b = 0; b < 64; b++)
+        if ((key >> b) & 1ull) occ[n++] = (uint8_t)b;
+    return n;
+}
+
+/* bits_between math_utils.c:9-58: set bits strictly between positions a and b */
+unsigned fo_bits_between(uint64_t key, int a, int b) {
+    int lo = a < b ? a : b, hi = a < b ? b : a;
+    unsigned n = 0;
+    for (int p = lo + 1; p < hi; p++) n += (unsigned)((key >> p) & 1ull);
+    return n;
+}
+
+/* gen_hf_bitstring fci_utils.c:10-43: the n_elec/2 lowest alpha and beta spin orbitals */
+uint64_t fo_gen_hf_bitstring(unsigned n_orb, unsigned n_elec) {
+    uint64_t k = 0;
+    for (unsigned i = 0; i < n_elec / 2; i++) {
+        k |= 1ull << i;
+        k |= 1ull << (i + n_orb);
+    }
+    return k;
+}
+
+/* excite_sign fci_utils.c:128-135 */
+int fo_excite_sign(int cre, int des, uint64_t key) { return (fo_bits_between(key, cre, des) % 2 == 0) ? 1 : -1; }
+
+/* sing_det_parity fci_utils.c:46-51 */
+int fo_sing_det_parity(uint64_t *key, const uint8_t *orbs) {
+    *key &= ~(1ull << orbs[0]);
+    int sign = fo_excite_sign(orbs[0], orbs[1], *key);
+    *key |= 1ull << orbs[1];
+    return sign;
+}
+/* doub_det_parity fci_utils.c:67-75 */
+int fo_doub_det_parity(uint64_t *key, const uint8_t *orbs) {
+    *key &= ~(1ull << orbs[0]);
+    *key &= ~(1ull << orbs[1]);
+    int sign = fo_excite_sign(orbs[2], orbs[0], *key);
+    sign *= fo_excite_sign(orbs[3], orbs[1], *key);
+    *key |= 1ull << orbs[2];
+    *key |= 1ull << orbs[3];
+    return sign;
+}
+/* sing_parity fci_utils.c:54-57 */
+int fo_sing_parity(uint64_t key, const uint8_t *orbs) { return fo_excite_sign(orbs[0], orbs[1], key); }
+/* doub_parity fci_utils.c:86-94 */
+int fo_doub_parity(uint64_t key, const uint8_t *orbs) {
+    key &= ~(1ull << orbs[0]);
+    key &= ~(1ull << orbs[1]);
+    return fo_excite_sign(orbs[2], orbs[0], key) * fo_excite_sign(orbs[3], orbs[1], key);
+}
+/* find_nth_virt fci_utils.c:138-148; the reference reads occ_orbs[idx] before testing idx < n_elec */
+int fo_find_nth_virt(const uint8_t *occ, int spin, int n_elec, int n_orb, int n) {
+    uint8_t virt = (uint8_t)(n_orb * spin + n);
+    for (int i = n_elec / 2 * spin; i < n_elec && occ[i] <= virt; i++) virt++;
+    return virt;
+}
+
+/* ================================ a1: hash ========================================================= */
+
+/* HashTable::hash_fxn det_hash.hpp:160-170: the product (i+1)*scrambler is taken in 32 bits */
+uint64_t fo_hash(uint64_t key, const uint32_t *scrambler) {
+    uint8_t occ[64];
+    int n = fo_find_bits(key, occ);
+    uint64_t h = 0;
+    for (int i = 0; i < n; i++) {
+        uint32_t term = (uint32_t)(i + 1) * scrambler[occ[i]];
+        h = FO_PRIME * h + term;
+    }
+    return h;
+}
+/* DistVec::idx_to_proc vec_utils.hpp:360-379, idx_to_hash :389-400 */
+void fo_hash_keys(const uint64_t *keys, size_t n, const uint32_t *scrambler, int n_procs, uint64_t *hash_out,
+                  int32_t *owner_out) {
+    for (size_t i = 0; i < n; i++) {
+        uint64_t h = fo_hash(keys[i], scrambler);
+        if (hash_out) hash_out[i] = h;
+        if (owner_out) owner_out[i] = (int32_t)(h % (uint64_t)n_procs);
+    }
+}
+
+/* ================================ a4/a5: vector compression ======================================== */
+
+static const double *g_sort_vals;
+static int cmp_desc_abs(const void *a, const void *b) {
+    double x = fabs(g_sort_vals[*(const size_t *)a]), y = fabs(g_sort_vals[*(const size_t *)b]);
+    return (x < y) - (x > y);
+}
+
+/* find_preserve compress_utils.cpp:29-105, one rank.  The reference pops a max-heap of |v|; popping a
+ * heap visits the elements in descending |v|, which a sorted index list reproduces (ties in |v| are
+ * interchangeable: both are preserved or neither). */
+double fo_find_preserve(const double *values, size_t count, unsigned *n_samp, double *glob_norm, uint8_t *keep) {
+    double loc_one_norm = 0, glob_one_norm = 0;
+    size_t *srt = (size_t *)malloc(sizeof(size_t) * (count ? count : 1));
+    for (size_t i = 0; i < count; i++) {
+        loc_one_norm += fabs(values[i]);
+        srt[i] = i;
+        keep[i] = 0;
+    }
+    g_sort_vals = values;
+    qsort(srt, count, sizeof(size_t), cmp_desc_abs);
+    size_t next = 0; /* top of the heap = srt[next] */
+    int glob_sampled = 1, recalc_norm = 0;
+    *glob_norm = loc_one_norm;
+    while (glob_sampled > 0) {
+        glob_one_norm = loc_one_norm;
+        int loc_sampled = 0;
+        while (next < count && glob_one_norm >= 0) {
+            double el_magn = fabs(values[srt[next]]);
+            if (el_magn >= glob_one_norm / (*n_samp - loc_sampled)) {
+                keep[srt[next]] = 1;
+                loc_sampled++;
+                loc_one_norm -= el_magn;
+                glob_one_norm -= el_magn;
+                next++;
+            } else {
+                break;
+            }
+        }
+        glob_sampled = loc_sampled;
+        *n_samp -= glob_sampled;
+        if (glob_sampled == 0 && !recalc_norm) {
+            loc_one_norm = 0;
+            for (size_t i = 0; i < count; i++)
+                if (!keep[i]) loc_one_norm += fabs(values[i]);
+            glob_sampled = 1;
+            recalc_norm = 1;
+        } else {
+            recalc_norm = 0;
+        }
+    }
+    loc_one_norm = 0;
+    if (glob_one_norm < 1e-9) {
+        *n_samp = 0;
+    } else {
+        for (size_t i = 0; i < count; i++)
+            if (!keep[i]) loc_one_norm += fabs(values[i]);
+    }
+    free(srt);
+    return loc_one_norm;
+}
+
+/* seed_sys compress_utils.cpp:107-127 */
+double fo_seed_sys(const double *norms, int n_procs, int rank, double *rn, unsigned n_samp) {
+    double lbound = 0;
+    for (int p = 0; p < rank; p++) lbound += norms[p];
+    double global_norm = lbound;
+    for (int p = rank; p < n_procs; p++) global_norm += norms[p];
+    *rn *= global_norm / n_samp;
+    *rn += global_norm / n_samp * (int)(lbound * n_samp / global_norm);
+    if (*rn < lbound) *rn += global_norm / n_samp;
+    return lbound;
+}
+
+/* sys_comp compress_utils.cpp:278-327 */
+void fo_sys_comp(double *values, size_t count, double *loc_norms, int n_procs, int rank, unsigned n_samp, uint8_t *keep,
+                 double rn) {
+    double rn_sys = rn, tmp_glob_norm = 0, lbound;
+    for (int p = 0; p < n_procs; p++) tmp_glob_norm += loc_norms[p];
+    if (n_samp > 0) {
+        lbound = fo_seed_sys(loc_norms, n_procs, rank, &rn_sys, n_samp);
+    } else {
+        lbound = 0;
+        rn_sys = INFINITY;
+    }
+    loc_norms[rank] = 0;
+    for (size_t i = 0; i < count; i++) {
+        double v = values[i];
+        if (keep[i]) {
+            loc_norms[rank] += fabs(v);
+            keep[i] = 0;
+        } else if (v != 0) {
+            lbound += fabs(v);
+            if (rn_sys < lbound) {
+                values[i] = tmp_glob_norm / n_samp * ((v > 0) - (v < 0));
+                loc_norms[rank] += tmp_glob_norm / n_samp;
+                rn_sys += tmp_glob_norm / n_samp;
+            } else {
+                values[i] = 0;
+                keep[i] = 1;
+            }
+        }
+    }
+}
+
+/* adjust_shift compress_utils.cpp:684-693 */
+void fo_adjust_shift(double *shift, double one_norm, double *last_norm, double target_norm, double damp) {
+    if (*last_norm) {
+        *shift -= damp * log(one_norm / *last_norm);
+        *last_norm = one_norm;
+    }
+    if (*last_norm == 0 && one_norm > target_norm) *last_norm = one_norm;
+}
+
+/* ================================ a6: hierarchical compression ===================================== */
+
+/* find_keep_sub compress_utils.cpp:130-276.  keep is a count x n_sub byte matrix (the reference packs
+ * it into bits).  The reference works in chunks of 8 weights: the budget factor wt_factor is sampled
+ * at the start of each chunk and the tests of a chunk are made before any of its elements is
+ * processed; sub-weights are visited in groups of 8 with the guard 1e-12 for full groups and 1e-10 for
+ * the trailing partial group. */
+double fo_find_keep_sub(const double *values, const uint32_t *n_div, const double *sub_weights, size_t n_sub_cols,
+                        uint8_t *keep, const uint16_t *sub_sizes, size_t count, unsigned *n_samp, double *wt_remain) {
+    double loc_one_norm = 0, glob_one_norm = 0;
+    for (size_t i = 0; i < count; i++) {
+        loc_one_norm += values[i];
+        wt_remain[i] = values[i];
+    }
+    int glob_sampled = 1, last_pass = 0;
+    size_t n_sub = n_sub_cols;
+    const size_t coarse = 8;
+    size_t n_coarse = count / coarse;
+    double cw[8];
+    while (glob_sampled > 0) {
+        glob_one_norm = loc_one_norm;
+        if (glob_one_norm < 0) break;
+        int loc_sampled = 0;
+        for (size_t c = 0; c <= n_coarse; c++) {
+            size_t lim = c == n_coarse ? count % coarse : coarse;
+            double wt_factor = *n_samp - loc_sampled;
+            int hit[8];
+            for (size_t f = 0; f < lim; f++) {
+                size_t i = c * coarse + f;
+                hit[f] = 0;
+                if (wt_remain[i] > 0) {
+                    cw[f] = values[i] * wt_factor;
+                    if (n_div[i] > 0) cw[f] /= n_div[i];
+                    hit[f] = cw[f] >= glob_one_norm;
+                }
+            }
+            int stop = 0;
+            for (size_t f = 0; f < lim && !stop; f++) {
+                if (!hit[f]) continue;
+                size_t i = c * coarse + f;
+                double el_magn = values[i];
+                if (n_div[i] > 0) {
+                    keep[i * n_sub_cols] = 1;
+                    wt_remain[i] = 0;
+                    loc_sampled += n_div[i];
+                    loc_one_norm -= el_magn;
+                    glob_one_norm -= el_magn;
+                    if (glob_one_norm < 0) stop = 1; /* `break` leaves this chunk's element loop */
+                } else {
+                    double sub_remain = 0;
+                    const double *row = sub_weights + i * n_sub_cols;
+                    uint8_t *krow = keep + i * n_sub_cols;
+                    if (sub_sizes) n_sub = sub_sizes[i];
+                    size_t full = (n_sub / 8) * 8;
+                    for (size_t j = 0; j < n_sub; j++) {
+                        if (krow[j]) continue;
+                        double sub_magn = cw[f] * row[j];
+                        double guard = j < full ? 1e-12 : 1e-10;
+                        if (sub_magn >= glob_one_norm && fabs(sub_magn) > guard) {
+                            krow[j] = 1;
+                            loc_sampled++;
+                        } else {
+                            sub_remain += sub_magn;
+                        }
+                    }
+                    sub_remain /= wt_factor;
+                    double change = wt_remain[i] - sub_remain;
+                    wt_remain[i] = sub_remain;
+                    loc_one_norm -= change;
+                    glob_one_norm -= change;
+                }
+            }
+        }
+        glob_sampled = loc_sampled;
+        *n_samp -= glob_sampled;
+        if (last_pass && glob_sampled) last_pass = 0;
+        if (glob_sampled == 0 && !last_pass) {
+            last_pass = 1;
+            glob_sampled = 1;
+            loc_one_norm = 0;
+            for (size_t i = 0; i < count; i++) loc_one_norm += wt_remain[i];
+        }
+    }
+    loc_one_norm = 0;
+    if (glob_one_norm / *n_samp < 1e-8) {
+        *n_samp = 0;
+    } else {
+        for (size_t i = 0; i < count; i++) loc_one_norm += wt_remain[i];
+    }
+    return loc_one_norm;
+}
+
+/* sys_sub compress_utils.cpp:702-794, one rank (loc_norm = the rank's residual norm) */
+size_t fo_sys_sub(const double *values, const uint32_t *n_div, const double *sub_weights, size_t n_sub_cols,
+                  uint8_t *keep, const uint16_t *sub_sizes, size_t count, unsigned n_samp, const double *wt_remain,
+                  double loc_norm, double rn, double *new_vals, uint64_t *new_idx) {
+    double rn_sys = rn, tmp_glob_norm = loc_norm, lbound;
+    if (n_samp > 0) {
+        double norms[1] = {loc_norm};
+        lbound = fo_seed_sys(norms, 1, 0, &rn_sys, n_samp);
+    } else {
+        lbound = 0;
+        rn_sys = INFINITY;
+    }
+    size_t num_new = 0, n_sub = n_sub_cols;
+    for (size_t w = 0; w < count; w++) {
+        double v = values[w];
+        if (v == 0) continue;
+        lbound += wt_remain[w];
+        if (n_div[w] > 0) {
+            if (keep[w * n_sub_cols]) {
+                keep[w * n_sub_cols] = 0;
+                for (size_t s = 0; s < n_div[w]; s++) {
+                    new_vals[num_new] = v / n_div[w];
+                    new_idx[2 * num_new] = w;
+                    new_idx[2 * num_new + 1] = s;
+                    num_new++;
+                }
+            } else {
+                while (rn_sys < lbound) {
+                    size_t s = (size_t)((lbound - rn_sys) * n_div[w] / v);
+                    if (s < n_div[w]) {
+                        new_vals[num_new] = tmp_glob_norm / n_samp;
+                        new_idx[2 * num_new] = w;
+                        new_idx[2 * num_new + 1] = s;
+                        num_new++;
+                    }
+                    rn_sys += tmp_glob_norm / n_samp;
+                }
+            }
+        } else if (wt_remain[w] < v || rn_sys < lbound) {
+            double sub_lbound = lbound - wt_remain[w];
+            if (sub_sizes) n_sub = sub_sizes[w];
+            const double *row = sub_weights + w * n_sub_cols;
+            uint8_t *krow = keep + w * n_sub_cols;
+            for (size_t s = 0; s < n_sub; s++) {
+                if (krow[s] && row[s] != 0) {
+                    new_vals[num_new] = v * row[s];
+                    new_idx[2 * num_new] = w;
+                    new_idx[2 * num_new + 1] = s;
+                    num_new++;
+                } else {
+                    sub_lbound += v * row[s];
+                    if (rn_sys < sub_lbound && row[s] != 0) {
+                        new_vals[num_new] = tmp_glob_norm / n_samp;
+                        new_idx[2 * num_new] = w;
+                        new_idx[2 * num_new + 1] = s;
+                        num_new++;
+                        rn_sys += tmp_glob_norm / n_samp;
+                    }
+                }
+                krow[s] = 0;
+            }
+        }
+    }
+    return num_new;
+}
+
+/* comp_sub compress_utils.cpp:797-820 */
+size_t fo_comp_sub(const double *values, size_t count, const uint32_t *n_div, const double *sub_weights, size_t n_sub,
+                   const uint16_t *sub_sizes, unsigned n_samp, double rn, double *new_vals, uint64_t *new_idx,
+                   unsigned *n_samp_left, double *loc_norm) {
+    uint8_t *keep = (uint8_t *)calloc((count ? count : 1) * n_sub, 1);
+    double *wt_remain = (double *)malloc(sizeof(double) * (count + 1));
+    unsigned tmp = n_samp;
+    double ln = fo_find_keep_sub(values, n_div, sub_weights, n_sub, keep, sub_sizes, count, &tmp, wt_remain);
+    size_t n = fo_sys_sub(values, n_div, sub_weights, n_sub, keep, sub_sizes, count, tmp, wt_remain, ln, rn, new_vals,
+                          new_idx);
+    if (n_samp_left) *n_samp_left = tmp;
+    if (loc_norm) *loc_norm = ln;
+    free(keep);
+    free(wt_remain);
+    return n;
+}
+
+/* ================================ molecular Hamiltonian ============================================ */
+
+struct fo_mol {
+    unsigned n_orb, n_elec, n_frz, tot_orb; /* n_elec = unfrozen electrons */
+    unsigned n_elec_total;
+    double *eris;  /* packed, SymmERIs layout */
+    size_t n_packed;
+    double *hcore; /* tot_orb^2 */
+    uint8_t *symm; /* n_orb */
+    uint8_t lookup[8][64];
+    unsigned max_n_symm;
+    /* hb_info heat_bathPP.hpp:25-34 */
+    double *d_diff, *d_same, *s_tens, *exch_sqrt, *diag_sqrt, *exch_norms, s_norm;
+};
+
+/* SymmERIs::chemist ndarr.hpp:219-230 */
+static double chem(const fo_mol *m, size_t i1, size_t i2, size_t i3, size_t i4) {
+    size_t a = i1 < i2 ? i1 : i2, b = i1 < i2 ? i2 : i1;
+    size_t p1 = TRI_WDIAG(a, b);
+    size_t c = i3 < i4 ? i3 : i4, d = i3 < i4 ? i4 : i3;
+    size_t p2 = TRI_WDIAG(c, d);
+    size_t lo = p1 < p2 ? p1 : p2, hi = p1 < p2 ? p2 : p1;
+    return m->eris[TRI_WDIAG(lo, hi)];
+}
+/* SymmERIs::physicist ndarr.hpp:237-239 */
+static double phys(const fo_mol *m, size_t i1, size_t i2, size_t i3, size_t i4) { return chem(m, i1, i3, i2, i4); }
+
+/* set_up heat_bathPP.cpp:99-179 */
+static void fo_set_up(fo_mol *m) {
+    unsigned M = m->n_orb, T = m->tot_orb, hf = T - M;
+    m->d_diff = (double *)calloc(M * M, sizeof(double));
+    for (unsigned i = 0; i < M; i++)
+        for (unsigned j = 0; j < M; j++)
+            for (unsigned a = hf; a < T; a++)
+                for (unsigned b = hf; b < T; b++)
+                    if (i != a - hf && j != b - hf) m->d_diff[i * M + j] += fabs(phys(m, i + hf, j + hf, a, b));
+    m->d_same = (double *)calloc(M * (M - 1) / 2 + 1, sizeof(double));
+    size_t tri = 0;
+    for (unsigned j = 1; j < M; j++)
+        for (unsigned i = 0; i < j; i++) {
+            for (unsigned a = hf; a < T; a++)
+                for (unsigned b = hf; b < a; b++)
+                    if (a - hf != j && a - hf != i && b - hf != j && b - hf != i)
+                        m->d_same[tri] += 2 * fabs(phys(m, i + hf, j + hf, a, b) - phys(m, i + hf, j + hf, b, a));
+            tri++;
+        }
+    m->s_tens = (double *)calloc(M, sizeof(double));
+    m->s_norm = 0;
+    for (unsigned i = 0; i < M; i++) {
+        for (unsigned j = 0; j < i; j++) m->s_tens[i] += m->d_same[TRI_NODIAG(j, i)];
+        for (unsigned j = i + 1; j < M; j++) m->s_tens[i] += m->d_same[TRI_NODIAG(i, j)];
+        for (unsigned j = 0; j < M; j++) m->s_tens[i] += m->d_diff[i * M + j];
+        m->s_norm += m->s_tens[i];
+    }
+    m->exch_sqrt = (double *)malloc(sizeof(double) * (M * (M - 1) / 2 + 1));
+    tri = 0;
+    for (unsigned j = 0; j < M; j++)
+        for (unsigned i = 0; i < j; i++) m->exch_sqrt[tri++] = sqrt(fabs(phys(m, i + hf, j + hf, j + hf, i + hf)));
+    m->diag_sqrt = (double *)malloc(sizeof(double) * M);
+    for (unsigned j = 0; j < M; j++) m->diag_sqrt[j] = sqrt(fabs(phys(m, j + hf, j + hf, j + hf, j + hf)));
+    m->exch_norms = (double *)calloc(M, sizeof(double));
+    for (unsigned i = 0; i < M; i++) {
+        for (unsigned j = 0; j < i; j++) m->exch_norms[i] += m->exch_sqrt[TRI_NODIAG(j, i)];
+        m->exch_norms[i] += m->diag_sqrt[i];
+        for (unsigned j = i + 1; j < M; j++) m->exch_norms[i] += m->exch_sqrt[TRI_NODIAG(i, j)];
+    }
+}
+
+fo_mol *fo_mol_create(unsigned n_orb, unsigned n_elec_total, unsigned n_frz, const double *hcore, const double *eris_chem,
+                      const uint8_t *symm) {
+    fo_mol *m = (fo_mol *)calloc(1, sizeof(fo_mol));
+    unsigned T = n_orb + n_frz / 2;
+    m->n_orb = n_orb;
+    m->n_elec_total = n_elec_total;
+    m->n_elec = n_elec_total - n_frz;
+    m->n_frz = n_frz;
+    m->tot_orb = T;
+    size_t n_pair = (size_t)T * (T + 1) / 2;
+    m->n_packed = n_pair * (n_pair + 1) / 2;
+    m->eris = (double *)calloc(m->n_packed, sizeof(double));
+    /* SymmERIs::chemist_ordered ndarr.hpp:232-236: only the canonical representative is stored */
+    for (size_t i = 0; i < T; i++)
+        for (size_t j = 0; j <= i; j++)
+            for (size_t k = 0; k < T; k++)
+                for (size_t l = 0; l <= k; l++) {
+                    size_t p1 = TRI_WDIAG(j, i), p2 = TRI_WDIAG(l, k);
+                    if (p1 <= p2) m->eris[TRI_WDIAG(p1, p2)] = eris_chem[((i * T + j) * T + k) * T + l];
+                }
+    m->hcore = (double *)malloc(sizeof(double) * T * T);
+    memcpy(m->hcore, hcore, sizeof(double) * T * T);
+    m->symm = (uint8_t *)malloc(n_orb);
+    memcpy(m->symm, symm, n_orb);
+    /* gen_symm_lookup molecule.cpp:1050-1065 + SymmInfo molecule.hpp:265-280 */
+    for (unsigned i = 0; i < n_orb; i++) {
+        uint8_t s = symm[i], c = m->lookup[s][0];
+        m->lookup[s][1 + c] = (uint8_t)i;
+        m->lookup[s][0] = c + 1;
+    }
+    for (unsigned s = 0; s < 8; s++)
+        if (m->lookup[s][0] > m->max_n_symm) m->max_n_symm = m->lookup[s][0];
+    fo_set_up(m);
+    return m;
+}
+void fo_mol_destroy(fo_mol *m) {
+    if (!m) return;
+    free(m->eris); free(m->hcore); free(m->symm); free(m->d_diff); free(m->d_same); free(m->s_tens);
+    free(m->exch_sqrt); free(m->diag_sqrt); free(m->exch_norms); free(m);
+}
+size_t fo_mol_packed_len(const fo_mol *m) { return m->n_packed; }
+const double *fo_mol_packed_eris(const fo_mol *m) { return m->eris; }
+void fo_mol_hb_tables(const fo_mol *m, double *d_diff, double *d_same, double *s_tens, double *s_norm, double *exch_sqrt,
+                      double *diag_sqrt, double *exch_norms) {
+    unsigned M = m->n_orb, TT = M * (M - 1) / 2;
+    if (d_diff) memcpy(d_diff, m->d_diff, sizeof(double) * M * M);
+    if (d_same) memcpy(d_same, m->d_same, sizeof(double) * TT);
+    if (s_tens) memcpy(s_tens, m->s_tens, sizeof(double) * M);
+    if (s_norm) *s_norm = m->s_norm;
+    if (exch_sqrt) memcpy(exch_sqrt, m->exch_sqrt, sizeof(double) * TT);
+    if (diag_sqrt) memcpy(diag_sqrt, m->diag_sqrt, sizeof(double) * M);
+    if (exch_norms) memcpy(exch_norms, m->exch_norms, sizeof(double) * M);
+}
+
+static void occ_list(const fo_mol *m, uint64_t key, uint8_t *occ) {
+    int n = fo_find_bits(key, occ);
+    occ[n] = 255; /* what lies behind the row in the reference's occ_orbs_ matrix is never a match */
+    (void)m;
+}
+
+/* diag_matrel molecule.cpp:983-1029 */
+static double diag_occ(const fo_mol *m, const uint8_t *occ) {
+    unsigned hf = m->n_frz / 2, ne = m->n_elec, T = m->tot_orb, nf = m->n_frz;
+    double s = 0;
+    for (unsigned j = 0; j < hf; j++) {
+        s += m->hcore[j * T + j] * 2;
+        s += phys(m, j, j, j, j);
+        for (unsigned k = j + 1; k < hf; k++) {
+            s += phys(m, j, k, j, k) * 4;
+            s -= phys(m, j, k, k, j) * 2;
+        }
+    }
+    for (unsigned j = 0; j < ne / 2; j++) {
+        unsigned e1 = occ[j] + hf;
+        s += m->hcore[e1 * T + e1];
+        for (unsigned k = 0; k < hf; k++) {
+            s += phys(m, e1, k, e1, k) * 2;
+            s -= phys(m, e1, k, k, e1);
+        }
+        for (unsigned k = j + 1; k < ne / 2; k++) {
+            unsigned e2 = occ[k] + hf;
+            s += phys(m, e1, e2, e1, e2);
+            s -= phys(m, e1, e2, e2, e1);
+        }
+        for (unsigned k = ne / 2; k < ne; k++) {
+            unsigned e2 = occ[k] + nf - T;
+            s += phys(m, e1, e2, e1, e2);
+        }
+    }
+    for (unsigned j = ne / 2; j < ne; j++) {
+        unsigned e1 = occ[j] + nf - T;
+        s += m->hcore[e1 * T + e1];
+        for (unsigned k = 0; k < hf; k++) {
+            s += phys(m, e1, k, e1, k) * 2;
+            s -= phys(m, e1, k, k, e1);
+        }
+        for (unsigned k = j + 1; k < ne; k++) {
+            unsigned e2 = occ[k] + nf - T;
+            s += phys(m, e1, e2, e1, e2);
+            s -= phys(m, e1, e2, e2, e1);
+        }
+    }
+    return s;
+}
+double fo_mol_diag(const fo_mol *m, uint64_t key) {
+    uint8_t occ[65];
+    occ_list(m, key, occ);
+    return diag_occ(m, occ);
+}
+
+/* sing_matr_el_nosgn molecule.cpp:76-105 */
+static double sing_el_occ(const fo_mol *m, const uint8_t *orbs, const uint8_t *occ) {
+    unsigned hf = m->n_frz / 2, T = m->tot_orb, ne = m->n_elec, M = T - hf;
+    unsigned occ_spa = orbs[0] % M + hf, unocc_spa = orbs[1] % M + hf, spin = orbs[0] / M;
+    double el = m->hcore[occ_spa * T + unocc_spa];
+    for (unsigned j = 0; j < hf; j++) {
+        el += phys(m, occ_spa, j, unocc_spa, j) * 2;
+        el -= phys(m, occ_spa, j, j, unocc_spa);
+    }
+    for (unsigned j = 0; j < ne / 2; j++) {
+        unsigned q = occ[j] + hf;
+        el += phys(m, occ_spa, q, unocc_spa, q);
+        if (spin == 0) el -= phys(m, occ_spa, q, q, unocc_spa);
+    }
+    for (unsigned j = ne / 2; j < ne; j++) {
+        unsigned q = occ[j] - T + hf * 2;
+        el += phys(m, occ_spa, q, unocc_spa, q);
+        if (spin == 1) el -= phys(m, occ_spa, q, q, unocc_spa);
+    }
+    return el;
+}
+double fo_mol_sing_el(const fo_mol *m, uint64_t key, const uint8_t *orbs) {
+    uint8_t occ[65];
+    occ_list(m, key, occ);
+    return sing_el_occ(m, orbs, occ);
+}
+/* doub_matr_el_nosgn molecule.cpp:26-42 */
+double fo_mol_doub_el(const fo_mol *m, const uint8_t *orbs) {
+    unsigned hf = m->n_frz / 2, M = m->tot_orb - hf;
+    int same = orbs[0] / M == orbs[1] / M;
+    unsigned s0 = orbs[0] % M + hf, s1 = orbs[1] % M + hf, s2 = orbs[2] % M + hf, s3 = orbs[3] % M + hf;
+    double el = phys(m, s0, s1, s2, s3);
+    if (same) el -= phys(m, s0, s1, s3, s2);
+    return el;
+}
+
+#define BIT(det, b) (((det) >> (b)) & 1ull)
+
+/* sing_ex_symm molecule.cpp:178-203 */
+size_t fo_mol_sing_ex(const fo_mol *m, uint64_t det, uint8_t *out) {
+    uint8_t occ[65];
+    occ_list(m, det, occ);
+    unsigned ne = m->n_elec, M = m->n_orb;
+    size_t idx = 0;
+    for (unsigned i = 0; i < ne / 2; i++)
+        for (unsigned a = 0; a < M; a++)
+            if (!BIT(det, a) && m->symm[occ[i]] == m->symm[a]) {
+                if (out) { out[2 * idx] = occ[i]; out[2 * idx + 1] = (uint8_t)a; }
+                idx++;
+            }
+    for (unsigned i = ne / 2; i < ne; i++)
+        for (unsigned a = M; a < 2 * M; a++)
+            if (!BIT(det, a) && m->symm[occ[i] - M] == m->symm[a - M]) {
+                if (out) { out[2 * idx] = occ[i]; out[2 * idx + 1] = (uint8_t)a; }
+                idx++;
+            }
+    return idx;
+}
+/* doub_ex_symm molecule.cpp:108-175 */
+size_t fo_mol_doub_ex(const fo_mol *m, uint64_t det, uint8_t *out) {
+    uint8_t occ[65];
+    occ_list(m, det, occ);
+    unsigned ne = m->n_elec, M = m->n_orb;
+    const uint8_t *sy = m->symm;
+    size_t idx = 0;
+#define EMIT(a, b, c, d)                                                                                          \
+    do {                                                                                                          \
+        if (out) { out[4 * idx] = (uint8_t)(a); out[4 * idx + 1] = (uint8_t)(b); out[4 * idx + 2] = (uint8_t)(c); \
+                   out[4 * idx + 3] = (uint8_t)(d); }                                                             \
+        idx++;                                                                                                    \
+    } while (0)
+    for (unsigned i = 0; i < ne / 2; i++)
+        for (unsigned j = ne / 2; j < ne; j++)
+            for (unsigned k = 0; k < M; k++)
+                if (!BIT(det, k))
+                    for (unsigned l = M; l < 2 * M; l++)
+                        if (!BIT(det, l) && (sy[occ[i]] ^ sy[occ[j] - M] ^ sy[k] ^ sy[l - M]) == 0) EMIT(occ[i], occ[j], k, l);
+    for (unsigned i = 0; i < ne / 2; i++)
+        for (unsigned j = i + 1; j < ne / 2; j++)
+            for (unsigned k = 0; k < M; k++)
+                if (!BIT(det, k))
+                    for (unsigned l = k + 1; l < M; l++)
+                        if (!BIT(det, l) && (sy[occ[i]] ^ sy[occ[j]] ^ sy[k] ^ sy[l]) == 0) EMIT(occ[i], occ[j], k, l);
+    for (unsigned i = ne / 2; i < ne; i++)
+        for (unsigned j = i + 1; j < ne; j++)
+            for (unsigned k = M; k < 2 * M; k++)
+                if (!BIT(det, k))
+                    for (unsigned l = k + 1; l < 2 * M; l++)
+                        if (!BIT(det, l) && (sy[occ[i] - M] ^ sy[occ[j] - M] ^ sy[k - M] ^ sy[l - M]) == 0)
+                            EMIT(occ[i], occ[j], k, l);
+#undef EMIT
+    return idx;
+}
+/* count_singex molecule.cpp:914-933 */
+size_t fo_mol_count_singex(const fo_mol *m, uint64_t det) {
+    uint8_t occ[65];
+    occ_list(m, det, occ);
+    unsigned M = m->n_orb;
+    size_t n = 0;
+    for (unsigned e = 0; e < m->n_elec; e++) {
+        unsigned orb = occ[e], irrep = m->symm[orb % M], spin = orb / M;
+        for (unsigned s = 0; s < m->lookup[irrep][0]; s++)
+            if (!BIT(det, m->lookup[irrep][s + 1] + M * spin)) n++;
+    }
+    return n;
+}
+
+/* ---- near_uniform helpers used by apply_HBPP_sys ---- */
+/* count_symm_virt near_uniform.cpp:14-28 */
+static void count_symm_virt(const fo_mol *m, const uint8_t *occ, unsigned cnt[8][2]) {
+    unsigned M = m->n_orb, ne = m->n_elec, i;
+    for (i = 0; i < 8; i++) cnt[i][0] = cnt[i][1] = m->lookup[i][0];
+    for (i = 0; i < ne / 2; i++) cnt[m->symm[occ[i]]][0] -= 1;
+    for (; i < ne; i++) cnt[m->symm[occ[i] - M]][1] -= 1;
+}
+/* count_sing_allowed near_uniform.cpp:316-327 */
+static unsigned count_sing_allowed(const fo_mol *m, const uint8_t *occ, unsigned cnt[8][2]) {
+    unsigned n = 0;
+    for (unsigned e = 0; e < m->n_elec; e++)
+        if (cnt[m->symm[occ[e] % m->n_orb]][e / (m->n_elec / 2)] != 0) n++;
+    return n;
+}
+/* count_sing_virt near_uniform.cpp:330-347 */
+static unsigned count_sing_virt(const fo_mol *m, const uint8_t *occ, unsigned cnt[8][2], uint8_t *occ_choice) {
+    unsigned n = 0;
+    for (unsigned e = 0; e < m->n_elec; e++) {
+        unsigned va = cnt[m->symm[occ[e] % m->n_orb]][e / (m->n_elec / 2)];
+        if (va != 0) {
+            if (n == *occ_choice) {
+                *occ_choice = (uint8_t)e;
+                return va;
+            }
+            n++;
+        }
+    }
+    return 0;
+}
+/* virt_from_idx near_uniform.cpp:419-433 */
+static uint8_t virt_from_idx(uint64_t det, const uint8_t *lookup_row, uint8_t spin_shift, unsigned index) {
+    for (unsigned s = 0; s < lookup_row[0]; s++) {
+        uint8_t orb = spin_shift + lookup_row[1 + s];
+        if (!BIT(det, orb)) {
+            if (index == 0) return orb;
+            index--;
+        }
+    }
+    return 255;
+}
+
+/* ---- HB-PP rows heat_bathPP.cpp:182-412 ---- */
+static double o1_probs(const fo_mol *m, double *p, const uint8_t *occ, int exclude_first) {
+    unsigned ne = m->n_elec, M = m->n_orb, skip = exclude_first > 0;
+    double norm = 0;
+    for (unsigned i = skip; i < ne / 2; i++) { p[i - skip] = m->s_tens[occ[i]]; norm += p[i - skip]; }
+    for (unsigned i = ne / 2; i < ne; i++) { p[i - skip] = m->s_tens[occ[i] - M]; norm += p[i - skip]; }
+    double inv = 1. / norm;
+    for (unsigned i = skip; i < ne; i++) p[i - skip] *= inv;
+    return norm / m->s_norm;
+}
+static double o2_probs(const fo_mol *m, double *p, const uint8_t *occ, uint8_t o1_idx) {
+    unsigned ne = m->n_elec, M = m->n_orb;
+    unsigned o1 = occ[o1_idx], spin = o1 / M;
+    double norm = 0;
+    unsigned off = (1 - spin) * ne / 2;
+    for (unsigned i = off; i < ne / 2 + off; i++) { p[i] = m->d_diff[(o1 % M) * M + occ[i] % M]; norm += p[i]; }
+    off = spin * ne / 2;
+    for (unsigned i = off; i < o1_idx; i++) { p[i] = m->d_same[TRI_NODIAG(occ[i] % M, o1 % M)]; norm += p[i]; }
+    for (unsigned i = o1_idx + 1; i < ne / 2 + off; i++) { p[i] = m->d_same[TRI_NODIAG(o1 % M, occ[i] % M)]; norm += p[i]; }
+    p[o1_idx] = 0;
+    double inv = 1. / norm;
+    for (unsigned i = 0; i < ne; i++) p[i] *= inv;
+    return norm / m->s_tens[o1 % M];
+}
+static double o2_probs_half(const fo_mol *m, double *p, const uint8_t *occ, uint8_t o1_idx) {
+    unsigned ne = m->n_elec, M = m->n_orb;
+    unsigned o1 = occ[o1_idx], spin = o1 / M;
+    double norm = 0;
+    unsigned upper = ne / 2 > o1_idx ? o1_idx : ne / 2;
+    for (unsigned i = 0; i < upper; i++) {
+        p[i] = spin == 0 ? m->d_same[TRI_NODIAG((unsigned)occ[i], o1)] : m->d_diff[(o1 - M) * M + occ[i]];
+        norm += p[i];
+    }
+    for (unsigned i = ne / 2; i < o1_idx; i++) {
+        p[i] = spin == 0 ? m->d_diff[o1 * M + occ[i] - M] : m->d_same[TRI_NODIAG((unsigned)occ[i] - M, o1 - M)];
+        norm += p[i];
+    }
+    double inv = 1. / norm;
+    for (unsigned i = 0; i < o1_idx; i++) p[i] *= inv;
+    return norm / m->s_tens[o1 % M];
+}
+static double u1_probs(const fo_mol *m, double *p, uint8_t o1_orb, const uint8_t *occ, int exclude_first) {
+    unsigned M = m->n_orb, ne = m->n_elec;
+    unsigned spin = o1_orb / M, o1s = o1_orb % M, offset = spin * M;
+    double norm = 0;
+    size_t pi = 0;
+    unsigned oi = ne / 2 * spin;
+    unsigned curr = occ[oi];
+    for (unsigned k = 0; k < o1s; k++) {
+        if (k + offset == curr) {
+            oi++;
+            curr = occ[oi];
+        } else {
+            p[pi] = m->exch_sqrt[TRI_NODIAG(k, o1s)];
+            norm += p[pi++];
+        }
+    }
+    oi++;
+    curr = occ[oi > ne ? ne : oi];
+    for (unsigned k = o1s + 1; k < M; k++) {
+        if (k + offset == curr) {
+            if (oi < ne - 1) {
+                oi++;
+                curr = occ[oi];
+            }
+        } else {
+            p[pi] = m->exch_sqrt[TRI_NODIAG(o1s, k)];
+            norm += p[pi++];
+        }
+    }
+    if (exclude_first) {
+        norm -= p[0];
+        p[0] = 0;
+    }
+    double inv = 1. / norm;
+    for (size_t i = 0; i < pi; i++) p[i] *= inv;
+    return norm / m->exch_norms[o1s];
+}
+static double u2_weight(const fo_mol *m, unsigned o2s, unsigned u2) {
+    if (o2s == u2) return m->diag_sqrt[o2s];
+    unsigned lo = o2s < u2 ? o2s : u2, hi = o2s > u2 ? o2s : u2;
+    return m->exch_sqrt[TRI_NODIAG(lo, hi)];
+}
+static double u2_probs(const fo_mol *m, double *p, uint8_t o1, uint8_t o2, uint8_t u1, uint16_t *len) {
+    unsigned M = m->n_orb, o2s = o2 % M, u1s = u1 % M;
+    int same = o1 / M == o2 / M;
+    unsigned irrep = m->symm[o1 % M] ^ m->symm[o2s] ^ m->symm[u1s];
+    unsigned num = m->lookup[irrep][0];
+    *len = (uint16_t)num;
+    double norm = 0;
+    for (unsigned i = 0; i < num; i++) {
+        unsigned u2 = m->lookup[irrep][i + 1];
+        if ((same && u2 != u1s) || !same) {
+            p[i] = u2_weight(m, o2s, u2);
+            norm += p[i];
+        } else {
+            p[i] = 0;
+        }
+    }
+    if (norm != 0) {
+        double inv = 1 / norm;
+        for (unsigned i = 0; i < num; i++) {
+            unsigned u2 = m->lookup[irrep][i + 1];
+            if ((same && u2 != u1s) || !same) p[i] *= inv;
+        }
+    }
+    return norm / m->exch_norms[o2s];
+}
+static double u2_probs_half(const fo_mol *m, double *p, uint8_t o1, uint8_t o2, uint8_t u1, uint64_t det, uint16_t *len) {
+    unsigned M = m->n_orb, o2s = o2 % M, u1s = u1 % M, u2_spin = o2 / M;
+    int same = (o1 / M) == u2_spin;
+    unsigned irrep = m->symm[o1 % M] ^ m->symm[o2s] ^ m->symm[u1s];
+    unsigned num = m->lookup[irrep][0], i;
+    double norm = 0;
+    for (i = 0; i < num; i++) {
+        unsigned u2 = m->lookup[irrep][i + 1];
+        if (same && u2 >= u1s) break;
+        if (((same && u2 != u1s) || !same) && !BIT(det, u2 + M * u2_spin)) {
+            p[i] = u2_weight(m, o2s, u2);
+            norm += p[i];
+        } else {
+            p[i] = 0;
+        }
+    }
+    *len = (uint16_t)i;
+    if (norm != 0) {
+        double inv = 1 / norm;
+        for (unsigned k = 0; k < i; k++) p[k] *= inv;
+    }
+    return norm / m->exch_norms[o2s];
+}
+double fo_mol_hb_row(const fo_mol *m, int which, uint64_t key, int a0, int a1, int a2, double *row, int *len) {
+    uint8_t occ[65];
+    occ_list(m, key, occ);
+    uint16_t L = 0;
+    double r = 0;
+    switch (which) {
+        case 0: r = o1_probs(m, row, occ, a0); L = (uint16_t)(m->n_elec - (a0 > 0)); break;
+        case 1: r = o2_probs(m, row, occ, (uint8_t)a0); L = (uint16_t)m->n_elec; break;
+        case 2: r = o2_probs_half(m, row, occ, (uint8_t)a0); L = (uint16_t)a0; break;
+        case 3: r = u1_probs(m, row, (uint8_t)a0, occ, a1); L = (uint16_t)(m->n_orb - m->n_elec / 2); break;
+        case 4: r = u2_probs(m, row, (uint8_t)a0, (uint8_t)a1, (uint8_t)a2, &L); break;
+        case 5: r = u2_probs_half(m, row, (uint8_t)a0, (uint8_t)a1, (uint8_t)a2, key, &L); break;
+    }
+    *len = L;
+    return r;
+}
+
+/* calc_unnorm_wt heat_bathPP.cpp:414-439 */
+static double unnorm_wt(const fo_mol *m, const uint8_t *orbs) {
+    int M = (int)m->n_orb;
+    int o1 = orbs[0] % M, o2 = orbs[1] % M, u1 = orbs[2] % M, u2 = orbs[3] % M;
+    int lo1 = o1 < u1 ? o1 : u1, hi1 = o1 > u1 ? o1 : u1, lo2 = o2 < u2 ? o2 : u2, hi2 = o2 > u2 ? o2 : u2;
+    int same = orbs[0] / M == orbs[1] / M;
+    int o1u1 = TRI_NODIAG(lo1, hi1), o2u2 = TRI_NODIAG(lo2, hi2);
+    if (same) {
+        int o1o2 = TRI_NODIAG(o1, o2);
+        return m->d_same[o1o2] * (m->exch_sqrt[o1u1] * m->exch_sqrt[o2u2]) / m->s_norm / m->exch_norms[o1] /
+               m->exch_norms[o2];
+    }
+    return (m->d_diff[o2 * M + o1]) * m->exch_sqrt[o1u1] * m->exch_sqrt[o2u2] / m->s_norm / m->exch_norms[o1] /
+           m->exch_norms[o2];
+}
+/* calc_norm_wt heat_bathPP.cpp:442-598 */
+static double symm_sum(const fo_mol *m, int o, unsigned irrep, int same, int excl) {
+    double s = 0;
+    for (unsigned k = 0; k < m->lookup[irrep][0]; k++) {
+        int so = m->lookup[irrep][k + 1];
+        if ((same && so != excl) || !same) s += u2_weight(m, (unsigned)o, (unsigned)so);
+    }
+    return s;
+}
+static double norm_wt(const fo_mol *m, const uint8_t *orbs, const uint8_t *occ, uint64_t det) {
+    int M = (int)m->n_orb;
+    unsigned ne = m->n_elec;
+    int o1 = orbs[0] % M, o1_spin = orbs[0] / M, o2 = orbs[1] % M, o2_spin = orbs[1] / M, u1 = orbs[2] % M,
+        u2 = orbs[3] % M;
+    int same = o1_spin == o2_spin;
+    int os[65];
+    for (unsigned i = 0; i < ne; i++) os[i] = occ[i] % M;
+    os[ne] = 255;
+    double s_denom = 0;
+    for (unsigned i = 0; i < ne; i++) s_denom += m->s_tens[os[i]];
+    double dd[2];
+    for (int w = 0; w < 2; w++) {
+        int o = w ? o2 : o1, sp = w ? o2_spin : o1_spin;
+        double d = 0;
+        unsigned off = (1 - sp) * ne / 2, i;
+        for (i = off; i < ne / 2 + off; i++) d += m->d_diff[o * M + os[i]];
+        off = sp * ne / 2;
+        for (i = off; os[i] < o; i++) d += m->d_same[TRI_NODIAG(os[i], o)];
+        for (i++; i < ne / 2 + off; i++) d += m->d_same[TRI_NODIAG(o, os[i])];
+        dd[w] = d;
+    }
+    double ev[2];
+    for (int w = 0; w < 2; w++) {
+        int o = w ? o2 : o1, off = (w ? o2_spin : o1_spin) * M;
+        double e = 0;
+        for (int k = 0; k < o; k++)
+            if (!BIT(det, k + off)) e += m->exch_sqrt[TRI_NODIAG(k, o)];
+        for (int k = o + 1; k < M; k++)
+            if (!BIT(det, k + off)) e += m->exch_sqrt[TRI_NODIAG(o, k)];
+        ev[w] = e;
+    }
+    unsigned u1_irrep = m->symm[u1], u2_irrep = m->symm[u2];
+    double e2_no1 = symm_sum(m, o2, u2_irrep, same, u1), e1_no1 = symm_sum(m, o1, u2_irrep, same, u1);
+    double e2_no2 = symm_sum(m, o2, u1_irrep, same, u2), e1_no2 = symm_sum(m, o1, u1_irrep, same, u2);
+    int lo, hi;
+#define TRIP(a, b) (lo = (a) < (b) ? (a) : (b), hi = (a) > (b) ? (a) : (b), TRI_NODIAG(lo, hi))
+    int o1u1 = TRIP(o1, u1), o2u2 = TRIP(o2, u2);
+    double w;
+    if (same) {
+        int o1o2 = TRI_NODIAG(o1, o2), o1u2 = TRIP(o1, u2), o2u1 = TRIP(o2, u1);
+        w = m->d_same[o1o2] / s_denom *
+            (m->s_tens[o1] / dd[0] / ev[0] *
+                 (m->exch_sqrt[o1u1] * m->exch_sqrt[o2u2] / e2_no1 + m->exch_sqrt[o1u2] * m->exch_sqrt[o2u1] / e2_no2) +
+             m->s_tens[o2] / dd[1] / ev[1] *
+                 (m->exch_sqrt[o2u1] * m->exch_sqrt[o1u2] / e1_no1 + m->exch_sqrt[o2u2] * m->exch_sqrt[o1u1] / e1_no2));
+    } else {
+        w = (m->s_tens[o1] * m->d_diff[o1 * M + o2] / dd[0] / ev[0] / e2_no1 +
+             m->s_tens[o2] * m->d_diff[o2 * M + o1] / dd[1] / ev[1] / e1_no2) *
+            m->exch_sqrt[o1u1] * m->exch_sqrt[o2u2] / s_denom;
+    }
+#undef TRIP
+    return w;
+}
+double fo_mol_hb_wt(const fo_mol *m, int normalized, uint64_t key, const uint8_t *orbs) {
+    uint8_t occ[65];
+    occ_list(m, key, occ);
+    return normalized ? norm_wt(m, orbs, occ, key) : unnorm_wt(m, orbs);
+}
+
+/* apply_HBPP_sys heat_bathPP.cpp:686-992: five comp_sub stages with materialised sub-weight rows, then
+ * the finalize loop.  spawn_length bounds every intermediate list (as in the reference). */
+size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub,
+                             int new_hb, const double *uniforms5, unsigned n_samp, size_t spawn_length, double *out_val,
+                             uint64_t *out_det, uint8_t *out_orbs) {
+    unsigned ne = m->n_elec, M = m->n_orb;
+    size_t n_states = ne > M - ne / 2 ? ne : M - ne / 2;
+    if (n_states < m->max_n_symm) n_states = m->max_n_symm;
+    if (n_states < 2) n_states = 2;
+    size_t L = spawn_length;
+    double *vec1 = (double *)calloc(L, sizeof(double)), *vec2 = (double *)calloc(L, sizeof(double));
+    double *subwts = (double *)calloc(L * n_states, sizeof(double));
+    uint32_t *ndiv = (uint32_t *)calloc(L, sizeof(uint32_t));
+    uint16_t *nsub = (uint16_t *)calloc(L, sizeof(uint16_t));
+    size_t *det1 = (size_t *)calloc(L, sizeof(size_t)), *det2 = (size_t *)calloc(L, sizeof(size_t));
+    uint8_t(*orb1)[4] = (uint8_t(*)[4])calloc(L, 4), (*orb2)[4] = (uint8_t(*)[4])calloc(L, 4);
+    uint64_t *cidx = (uint64_t *)calloc(2 * L, sizeof(uint64_t));
+    uint8_t occ[65];
+    unsigned cnt[8][2];
+    size_t comp_len = n, cols;
+
+    /* singles vs doubles :713-734 */
+    cols = 2;
+    for (size_t i = 0; i < comp_len; i++) {
+        double w = fabs(vals[i]);
+        vec1[i] = w;
+        det1[i] = i;
+        if (w > 0) {
+            subwts[i * cols] = p_doub;
+            subwts[i * cols + 1] = 1 - p_doub;
+            ndiv[i] = 0;
+        } else {
+            ndiv[i] = 1;
+        }
+    }
+    comp_len = fo_comp_sub(vec1, comp_len, ndiv, subwts, cols, NULL, n_samp, uniforms5[0], vec2, cidx, NULL, NULL);
+
+    /* first occupied orbital :736-770 */
+    cols = ne - (new_hb ? 1 : 0);
+    for (size_t s = 0; s < comp_len; s++) {
+        size_t d = det1[cidx[2 * s]];
+        det2[s] = d;
+        orb1[s][0] = (uint8_t)cidx[2 * s + 1];
+        occ_list(m, keys[d], occ);
+        if (orb1[s][0] == 0) {
+            ndiv[s] = 0;
+            double tot = o1_probs(m, subwts + s * cols, occ, new_hb);
+            if (new_hb) vec2[s] *= tot;
+        } else {
+            count_symm_virt(m, occ, cnt);
+            unsigned n_occ = count_sing_allowed(m, occ, cnt);
+            if (n_occ == 0) {
+                ndiv[s] = 1;
+                vec2[s] = 0;
+            } else {
+                ndiv[s] = n_occ;
+            }
+        }
+    }
+    comp_len = fo_comp_sub(vec2, comp_len, ndiv, subwts, cols, NULL, n_samp, uniforms5[1], vec1, cidx, NULL, NULL);
+
+    /* single: virtual count; double: second occupied :772-816 (same column count as the previous stage) */
+    for (size_t s = 0; s < comp_len; s++) {
+        size_t w = cidx[2 * s], d = det2[w];
+        det1[s] = d;
+        orb2[s][0] = orb1[w][0];
+        orb2[s][1] = (uint8_t)cidx[2 * s + 1];
+        if (orb2[s][1] >= ne) {
+            vec1[s] = 0;
+            ndiv[s] = 1;
+            continue;
+        }
+        occ_list(m, keys[d], occ);
+        if (orb2[s][0] == 0) {
+            ndiv[s] = 0;
+            if (new_hb) {
+                orb2[s][1]++;
+                nsub[s] = orb2[s][1];
+                vec1[s] *= o2_probs_half(m, subwts + s * cols, occ, orb2[s][1]);
+            } else {
+                o2_probs(m, subwts + s * cols, occ, orb2[s][1]);
+            }
+        } else {
+            count_symm_virt(m, occ, cnt);
+            unsigned n_virt = count_sing_virt(m, occ, cnt, &orb2[s][1]);
+            if (n_virt == 0) {
+                ndiv[s] = 1;
+                vec1[s] = 0;
+            } else {
+                ndiv[s] = n_virt;
+                orb2[s][3] = (uint8_t)n_virt;
+            }
+        }
+    }
+    comp_len = fo_comp_sub(vec1, comp_len, ndiv, subwts, cols, new_hb ? nsub : NULL, n_samp, uniforms5[2], vec2, cidx,
+                           NULL, NULL);
+
+    /* first virtual (double) :818-864 */
+    cols = M - ne / 2;
+    for (size_t s = 0; s < comp_len; s++) {
+        size_t w = cidx[2 * s], d = det1[w];
+        det2[s] = d;
+        orb1[s][0] = orb2[w][0];
+        uint8_t o1_idx = orb2[w][1];
+        orb1[s][1] = o1_idx;
+        uint8_t o2u1 = (uint8_t)cidx[2 * s + 1];
+        orb1[s][2] = o2u1;
+        if (orb1[s][0] == 0) {
+            if (o2u1 >= ne) {
+                vec2[s] = 0;
+                ndiv[s] = 1;
+                continue;
+            }
+            ndiv[s] = 0;
+            occ_list(m, keys[d], occ);
+            int o1_spin = o1_idx / (ne / 2), o2_spin = occ[o2u1] / M;
+            double tot = u1_probs(m, subwts + s * cols, occ[o1_idx], occ, new_hb && (o1_spin == o2_spin));
+            if (new_hb) vec2[s] *= tot;
+        } else {
+            orb1[s][3] = orb2[w][3];
+            ndiv[s] = 1;
+        }
+    }
+    comp_len = fo_comp_sub(vec2, comp_len, ndiv, subwts, cols, NULL, n_samp, uniforms5[3], vec1, cidx, NULL, NULL);
+
+    /* second virtual (double) :866-915 */
+    cols = m->max_n_symm;
+    for (size_t s = 0; s < comp_len; s++) {
+        size_t w = cidx[2 * s], d = det2[w];
+        det1[s] = d;
+        orb2[s][0] = orb1[w][0];
+        uint8_t o1_idx = orb1[w][1], o2_idx = orb1[w][2];
+        orb2[s][1] = o1_idx;
+        orb2[s][2] = o2_idx;
+        if (orb2[s][0] == 0) {
+            occ_list(m, keys[d], occ);
+            uint8_t u1 = (uint8_t)fo_find_nth_virt(occ, o1_idx / (ne / 2), ne, M, (int)cidx[2 * s + 1]);
+            if (u1 >= 2 * M || BIT(keys[d], u1)) {
+                vec1[s] = 0;
+                ndiv[s] = 1;
+            } else {
+                ndiv[s] = 0;
+                orb2[s][3] = u1;
+                double tot = new_hb ? u2_probs_half(m, subwts + s * cols, occ[o1_idx], occ[o2_idx], u1, keys[d], &nsub[s])
+                                    : u2_probs(m, subwts + s * cols, occ[o1_idx], occ[o2_idx], u1, &nsub[s]);
+                if (new_hb || tot == 0) vec1[s] *= tot;
+            }
+        } else {
+            orb2[s][3] = orb1[w][3];
+            ndiv[s] = 1;
+        }
+    }
+    comp_len = fo_comp_sub(vec1, comp_len, ndiv, subwts, cols, nsub, n_samp, uniforms5[4], vec2, cidx, NULL, NULL);
+
+    /* finalize :917-991 */
+    size_t ok = 0;
+    for (size_t s = 0; s < comp_len; s++) {
+        size_t w = cidx[2 * s], d = det1[w];
+        uint64_t det = keys[d];
+        occ_list(m, det, occ);
+        uint8_t o1_idx = orb2[w][1], fin[4];
+        if (orb2[w][0] == 0) {
+            uint8_t o1 = occ[o1_idx], o2 = occ[orb2[w][2]], u1 = orb2[w][3];
+            uint8_t u2s = m->symm[o1 % M] ^ m->symm[o2 % M] ^ m->symm[u1 % M];
+            uint8_t u2 = (uint8_t)(m->lookup[u2s][cidx[2 * s + 1] + 1] + M * (o2 / M));
+            if (BIT(det, u2)) continue;
+            if (u1 == u2) continue;
+            if (u1 > u2) { uint8_t t = u1; u1 = u2; u2 = t; }
+            if (o1 > o2) { uint8_t t = o1; o1 = o2; o2 = t; }
+            fin[0] = o1; fin[1] = o2; fin[2] = u1; fin[3] = u2;
+            double tot = new_hb ? unnorm_wt(m, fin) : norm_wt(m, fin, occ, det);
+            double el = fo_mol_doub_el(m, fin) * vec2[s] / tot / p_doub;
+            if (fabs(el) > 1e-9) {
+                el *= fo_doub_parity(det, fin);
+                out_val[ok] = el;
+                out_det[ok] = d;
+                memcpy(out_orbs + 4 * ok, fin, 4);
+                ok++;
+            }
+        } else {
+            uint8_t o1 = occ[o1_idx];
+            uint8_t u1 = virt_from_idx(det, m->lookup[m->symm[o1 % M]], (uint8_t)(M * (o1 / M)), orb2[w][2]);
+            if (u1 == 255) continue;
+            fin[0] = o1; fin[1] = u1; fin[2] = fin[3] = 0;
+            count_symm_virt(m, occ, cnt);
+            unsigned n_occ = count_sing_allowed(m, occ, cnt);
+            double el = sing_el_occ(m, fin, occ);
+            el *= vec2[s] / (1 - p_doub) * n_occ * orb2[w][3];
+            if (fabs(el) > 1e-9) {
+                el *= fo_sing_parity(det, fin);
+                out_val[ok] = el;
+                out_det[ok] = d;
+                memcpy(out_orbs + 4 * ok, fin, 4);
+                ok++;
+            }
+        }
+    }
+    free(vec1); free(vec2); free(subwts); free(ndiv); free(nsub); free(det1); free(det2); free(orb1); free(orb2);
+    free(cidx);
+    return ok;
+}
+
+/* h_op_diag molecule.cpp:205-219 + h_op_offdiag :448-665 on a list; duplicates are not merged */
+size_t fo_mol_h_apply_list(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double id_fac,
+                           double h_fac, uint64_t *out_keys, double *out_vals, size_t cap) {
+    size_t k = 0;
+    unsigned ne = m->n_elec, M = m->n_orb;
+    uint8_t *sing = (uint8_t *)malloc(2 * (size_t)ne * M + 16);
+    uint8_t *doub = (uint8_t *)malloc(4 * (size_t)ne * ne * M * M + 16);
+    for (size_t i = 0; i < n; i++) {
+        if (vals[i] == 0) continue;
+        uint8_t occ[65];
+        occ_list(m, keys[i], occ);
+        if (k < cap) {
+            out_keys[k] = keys[i];
+            out_vals[k] = vals[i] * (id_fac + h_fac * diag_occ(m, occ));
+        }
+        k++;
+        size_t ns = fo_mol_sing_ex(m, keys[i], sing);
+        for (size_t e = 0; e < ns; e++) {
+            uint64_t nk = keys[i];
+            double el = sing_el_occ(m, sing + 2 * e, occ);
+            el *= fo_sing_det_parity(&nk, sing + 2 * e);
+            el *= vals[i] * h_fac;
+            if (k < cap) { out_keys[k] = nk; out_vals[k] = el; }
+            k++;
+        }
+        size_t nd = fo_mol_doub_ex(m, keys[i], doub);
+        for (size_t e = 0; e < nd; e++) {
+            uint64_t nk = keys[i];
+            double el = fo_mol_doub_el(m, doub + 4 * e);
+            el *= fo_doub_det_parity(&nk, doub + 4 * e);
+            el *= vals[i] * h_fac;
+            if (k < cap) { out_keys[k] = nk; out_vals[k] = el; }
+            k++;
+        }
+    }
+    free(sing);
+    free(doub);
+    return k;
+}

@@ -108,7 +108,7 @@ def test_find_preserve_sys_comp(ctx, n, budget, kind):
     assert g_left == r_left
     assert g_glob == pytest.approx(r_glob, rel=REL)
     assert g_loc == pytest.approx(r_loc, rel=REL, abs=1e-300)
-    for rn in (0.0, 0.37, 0.999999):
+    for rn in (1e-9, 0.37, 0.999999):
         rv, rk, rnorm = reflib.sys_comp(v, r_loc, r_left, r_keep, rn)
         gv, gk, gnorm = fries_b200.sys_comp(ctx, v, [g_loc], g_left, g_keep, rn)
         ties = int(np.sum(gk != rk))
@@ -268,7 +268,9 @@ def test_vec_add_merge_delete(ctx):
     rvec = L.ref_vec_create(100000, 50000, n_bits, 2 * half, 2, ps, vs)
     gvec = fries_b200.Vec(ctx, 100000, n_bits, 2 * half, 2, ps, vs)
     try:
-        for rnd, (origin, dest) in enumerate([(0, 0), (0, 1), (0, 1), (0, 0)]):
+        # origin != dest whenever non-initiator elements are present: with origin == dest the reference's result
+        # depends on the arrival order inside one buffer (a value may become nonzero half way through)
+        for rnd, (origin, dest) in enumerate([(0, 0), (0, 1), (0, 1), (1, 0)]):
             n = 40000
             keys = rng.choice(pool, n)
             keys[: n // 50] = pool[0]  # a hot determinant (hash-merge contention)
