@@ -463,3 +463,66 @@ extern "C" int fries_apply_hbpp_sys(fries_mol *mol, const uint64_t *h_keys, cons
     }
     return FRIES_OK;
 }
+
+// Diagnostics: run stages 0..stage and return that stage's raw output list: value, parent index, the
+// 4-byte path state of the parent item and the chosen sub-index (what the reference holds in vec1/vec2,
+// det_indices*, orb_indices* and comp_idx after the corresponding comp_sub call).
+extern "C" int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, const double *h_vals, size_t n,
+                                      double p_doub, int new_hb, const double *h_uniforms5, unsigned n_samp,
+                                      size_t spawn_cap, int stage, double *h_val, uint32_t *h_det, uint32_t *h_path,
+                                      uint32_t *h_sub, size_t *n_out) {
+    FRIES_REQUIRE(mol && h_keys && h_vals && h_uniforms5 && n_out && stage >= 0 && stage <= 4, "bad argument");
+    fries_ctx *c = mol->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    fries_hbpp *hb = nullptr;
+    FRIES_TRY(fries_hbpp_alloc(c, spawn_cap, &hb));
+    DevBuf<uint64_t> keys;
+    DevBuf<double> vals;
+    FRIES_TRY(keys.alloc(n));
+    FRIES_TRY(vals.alloc(n));
+    unsigned long long n64 = n;
+    CUDA_TRY(cudaMemcpyAsync(keys.p, h_keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(vals.p, h_vals, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(hb->n_scalar.p, &n64, 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(hb->st.p, 0, 8 * sizeof(CompState), c->stream));
+    for (int s = 0; s <= stage; s++) {
+        int o = s & 1, p = o ^ 1;
+        HbStageIO io;
+        io.keys = keys.p; io.vals = vals.p;
+        io.n_in = s == 0 ? hb->n_scalar.p : &hb->st.p[s - 1].n_out;
+        io.pv = hb->oval[p].p; io.pw = hb->owidx[p].p; io.ps = hb->osub[p].p;
+        io.pdet = hb->det[p].p; io.ppath = hb->path[p].p;
+        io.det = hb->det[o].p; io.path = hb->path[o].p;
+        io.p_doub = p_doub; io.new_hb = new_hb; io.in_cap = hb->cap;
+        CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
+                         hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
+                         hb->part_d.p, hb->part_c.p, hb->st.p + s};
+        switch (s) {
+            case 0: FRIES_TRY(launch_stage<0>(hb, mol, io, bufs, n_samp, h_uniforms5[0])); break;
+            case 1: FRIES_TRY(launch_stage<1>(hb, mol, io, bufs, n_samp, h_uniforms5[1])); break;
+            case 2: FRIES_TRY(launch_stage<2>(hb, mol, io, bufs, n_samp, h_uniforms5[2])); break;
+            case 3: FRIES_TRY(launch_stage<3>(hb, mol, io, bufs, n_samp, h_uniforms5[3])); break;
+            case 4: FRIES_TRY(launch_stage<4>(hb, mol, io, bufs, n_samp, h_uniforms5[4])); break;
+        }
+    }
+    CompState s1;
+    CUDA_TRY(cudaMemcpyAsync(&s1, hb->st.p + stage, sizeof(s1), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    size_t m = (size_t)s1.n_out;
+    *n_out = m;
+    int o = stage & 1;
+    std::vector<uint32_t> widx(m ? m : 1), det(hb->cap), path(hb->cap);
+    if (m) {
+        CUDA_TRY(cudaMemcpy(h_val, hb->oval[o].p, m * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(widx.data(), hb->owidx[o].p, m * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h_sub, hb->osub[o].p, m * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(det.data(), hb->det[o].p, hb->cap * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(path.data(), hb->path[o].p, hb->cap * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < m; i++) {
+            h_det[i] = det[widx[i]];
+            h_path[i] = path[widx[i]];
+        }
+    }
+    fries_hbpp_destroy(hb);
+    return FRIES_OK;
+}

@@ -213,6 +213,14 @@ typedef struct {
 int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frifull_params *p,
                               double uniform, fries_iter_stats *stats);
 
+/* ---- diagnostics ------------------------------------------------------------------------------------------
+ * Output list of stage `stage` (0..4) of apply_HBPP_sys: value, parent index, packed path bytes of the
+ * parent item (orb_indices state) and chosen sub-index (comp_idx[.][1]).  Used by the parity tests to
+ * localise a mismatch to one comp_sub call (heat_bathPP.cpp:731,767,813,861,912). */
+int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, const double *h_vals, size_t n, double p_doub,
+                           int new_hb, const double *h_uniforms5, unsigned n_samp, size_t spawn_cap, int stage,
+                           double *h_val, uint32_t *h_det, uint32_t *h_path, uint32_t *h_sub, size_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -218,6 +218,16 @@ void fo_adjust_shift(double *shift, double one_norm, double *last_norm, double t
 
 /* ================================ a6: hierarchical compression ===================================== */
 
+/* Chunk size of find_keep_sub.  8 = the reference (compress_utils.cpp:149).  The reference samples the budget
+ * factor (*n_samp - loc_sampled) once per chunk of 8 weights but lets the norm shrink inside the chunk, so a
+ * chunk's later elements are tested with a stale (larger) budget against a fresh (smaller) norm and a few
+ * marginal sub-weights are preserved that the self-consistent test |x| >= norm / budget would resample.
+ * With chunk size 1 both quantities are fresh for every weight and the result is the unique fixed point of
+ * that test -- which is what the device engine computes round by round.  Tests pin chunk 8 against the
+ * compiled reference and the CUDA path against chunk 1, and report how far 1 and 8 are apart. */
+static size_t g_keep_chunk = 8;
+void fo_set_keep_chunk(size_t chunk) { g_keep_chunk = chunk >= 1 && chunk <= 8 ? chunk : 8; }
+
 /* find_keep_sub compress_utils.cpp:130-276.  keep is a count x n_sub byte matrix (the reference packs
  * it into bits).  The reference works in chunks of 8 weights: the budget factor wt_factor is sampled
  * at the start of each chunk and the tests of a chunk are made before any of its elements is
@@ -232,7 +242,7 @@ double fo_find_keep_sub(const double *values, const uint32_t *n_div, const doubl
     }
     int glob_sampled = 1, last_pass = 0;
     size_t n_sub = n_sub_cols;
-    const size_t coarse = 8;
+    const size_t coarse = g_keep_chunk;
     size_t n_coarse = count / coarse;
     double cw[8];
     while (glob_sampled > 0) {
@@ -952,9 +962,40 @@ double fo_mol_hb_wt(const fo_mol *m, int normalized, uint64_t key, const uint8_t
 
 /* apply_HBPP_sys heat_bathPP.cpp:686-992: five comp_sub stages with materialised sub-weight rows, then
  * the finalize loop.  spawn_length bounds every intermediate list (as in the reference). */
+static size_t hbpp_sys(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub, int new_hb,
+                       const double *uniforms5, unsigned n_samp, size_t spawn_length, double *out_val,
+                       uint64_t *out_det, uint8_t *out_orbs, int stop_stage, uint32_t *out_sub);
+
 size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub,
                              int new_hb, const double *uniforms5, unsigned n_samp, size_t spawn_length, double *out_val,
                              uint64_t *out_det, uint8_t *out_orbs) {
+    return hbpp_sys(m, keys, vals, n, p_doub, new_hb, uniforms5, n_samp, spawn_length, out_val, out_det, out_orbs, -1,
+                    NULL);
+}
+/* diagnostics: the list that leaves the comp_sub call of stage `stage` (0..4): value, parent index, the
+ * orb_indices bytes of the parent item and the chosen sub-index */
+size_t fo_debug_hbpp_stage(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub,
+                           int new_hb, const double *uniforms5, unsigned n_samp, size_t spawn_length, int stage,
+                           double *out_val, uint64_t *out_det, uint8_t *out_orbs, uint32_t *out_sub) {
+    return hbpp_sys(m, keys, vals, n, p_doub, new_hb, uniforms5, n_samp, spawn_length, out_val, out_det, out_orbs, stage,
+                    out_sub);
+}
+
+#define FO_STAGE_DUMP(STAGE, VEC, DET, ORB)                                               \
+    if (stop_stage == (STAGE)) {                                                          \
+        for (size_t s = 0; s < comp_len; s++) {                                           \
+            size_t w = cidx[2 * s];                                                       \
+            out_val[s] = (VEC)[s];                                                        \
+            out_det[s] = (DET)[w];                                                        \
+            memcpy(out_orbs + 4 * s, (ORB)[w], 4);                                        \
+            out_sub[s] = (uint32_t)cidx[2 * s + 1];                                       \
+        }                                                                                 \
+        goto done;                                                                        \
+    }
+
+static size_t hbpp_sys(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub, int new_hb,
+                       const double *uniforms5, unsigned n_samp, size_t spawn_length, double *out_val,
+                       uint64_t *out_det, uint8_t *out_orbs, int stop_stage, uint32_t *out_sub) {
     unsigned ne = m->n_elec, M = m->n_orb;
     size_t n_states = ne > M - ne / 2 ? ne : M - ne / 2;
     if (n_states < m->max_n_symm) n_states = m->max_n_symm;
@@ -969,7 +1010,7 @@ size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double
     uint64_t *cidx = (uint64_t *)calloc(2 * L, sizeof(uint64_t));
     uint8_t occ[65];
     unsigned cnt[8][2];
-    size_t comp_len = n, cols;
+    size_t comp_len = n, cols, ok = 0;
 
     /* singles vs doubles :713-734 */
     cols = 2;
@@ -986,6 +1027,7 @@ size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double
         }
     }
     comp_len = fo_comp_sub(vec1, comp_len, ndiv, subwts, cols, NULL, n_samp, uniforms5[0], vec2, cidx, NULL, NULL);
+    FO_STAGE_DUMP(0, vec2, det1, orb1)
 
     /* first occupied orbital :736-770 */
     cols = ne - (new_hb ? 1 : 0);
@@ -1010,6 +1052,7 @@ size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double
         }
     }
     comp_len = fo_comp_sub(vec2, comp_len, ndiv, subwts, cols, NULL, n_samp, uniforms5[1], vec1, cidx, NULL, NULL);
+    FO_STAGE_DUMP(1, vec1, det2, orb1)
 
     /* single: virtual count; double: second occupied :772-816 (same column count as the previous stage) */
     for (size_t s = 0; s < comp_len; s++) {
@@ -1046,6 +1089,7 @@ size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double
     }
     comp_len = fo_comp_sub(vec1, comp_len, ndiv, subwts, cols, new_hb ? nsub : NULL, n_samp, uniforms5[2], vec2, cidx,
                            NULL, NULL);
+    FO_STAGE_DUMP(2, vec2, det1, orb2)
 
     /* first virtual (double) :818-864 */
     cols = M - ne / 2;
@@ -1074,6 +1118,7 @@ size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double
         }
     }
     comp_len = fo_comp_sub(vec2, comp_len, ndiv, subwts, cols, NULL, n_samp, uniforms5[3], vec1, cidx, NULL, NULL);
+    FO_STAGE_DUMP(3, vec1, det2, orb1)
 
     /* second virtual (double) :866-915 */
     cols = m->max_n_symm;
@@ -1103,9 +1148,10 @@ size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double
         }
     }
     comp_len = fo_comp_sub(vec1, comp_len, ndiv, subwts, cols, nsub, n_samp, uniforms5[4], vec2, cidx, NULL, NULL);
+    FO_STAGE_DUMP(4, vec2, det1, orb2)
 
     /* finalize :917-991 */
-    size_t ok = 0;
+    ok = 0;
     for (size_t s = 0; s < comp_len; s++) {
         size_t w = cidx[2 * s], d = det1[w];
         uint64_t det = keys[d];
@@ -1147,6 +1193,8 @@ size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double
             }
         }
     }
+done:
+    if (stop_stage >= 0) ok = comp_len;
     free(vec1); free(vec2); free(subwts); free(ndiv); free(nsub); free(det1); free(det2); free(orb1); free(orb2);
     free(cidx);
     return ok;

@@ -45,6 +45,7 @@ void fo_sys_comp(double *values, size_t count, double *loc_norms, int n_procs, i
                  uint8_t *keep, double rn);                        /* compress_utils.cpp:278-327 */
 
 /* ---- a6 ---- */
+void fo_set_keep_chunk(size_t chunk); /* 8 = reference behaviour (default); 1 = self-consistent fixed point */
 double fo_find_keep_sub(const double *values, const uint32_t *n_div, const double *sub_weights, size_t n_sub,
                         uint8_t *keep, const uint16_t *sub_sizes, size_t count, unsigned *n_samp,
                         double *wt_remain);                        /* compress_utils.cpp:130-276 */
@@ -80,6 +81,9 @@ double fo_mol_hb_wt(const fo_mol *m, int normalized, uint64_t key, const uint8_t
 size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub,
                              int new_hb, const double *uniforms5, unsigned n_samp, size_t spawn_length,
                              double *out_val, uint64_t *out_det, uint8_t *out_orbs); /* heat_bathPP.cpp:686-992 */
+size_t fo_debug_hbpp_stage(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub,
+                           int new_hb, const double *uniforms5, unsigned n_samp, size_t spawn_length, int stage,
+                           double *out_val, uint64_t *out_det, uint8_t *out_orbs, uint32_t *out_sub);
 /* full H.v of a list (h_op_diag molecule.cpp:205-219 + h_op_offdiag :448-665): out must hold
  * n * (1 + n_sing + n_doub) entries; duplicates are NOT merged (caller sorts + sums). */
 size_t fo_mol_h_apply_list(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double id_fac,

@@ -61,6 +61,8 @@ def lib():
             "fo_mol_apply_hbpp_sys": (sz, [vp, u64p, f64p, sz, d, i, f64p, u, sz, f64p, u64p, u8p]),
             "fo_mol_h_apply_list": (sz, [vp, u64p, f64p, sz, d, d, u64p, f64p, sz]),
         }
+        sig["fo_set_keep_chunk"] = (None, [sz])
+        sig["fo_debug_hbpp_stage"] = (sz, [vp, u64p, f64p, sz, d, i, f64p, u, sz, i, f64p, u64p, u8p, u32p])
         for name, (res, args) in sig.items():
             f = getattr(L, name)
             f.restype = res
@@ -181,3 +183,16 @@ def hash_keys(keys, scrambler, n_procs):
     o = np.zeros(k.size, np.int32)
     lib().fo_hash_keys(k, k.size, np.ascontiguousarray(scrambler, np.uint32), n_procs, h.ctypes.data, o.ctypes.data)
     return h, o
+
+
+class keep_chunk:
+    """with oraclelib.keep_chunk(1): ... -- run the oracle's find_keep_sub with the given chunk size"""
+
+    def __init__(self, chunk):
+        self.chunk = chunk
+
+    def __enter__(self):
+        lib().fo_set_keep_chunk(self.chunk)
+
+    def __exit__(self, *a):
+        lib().fo_set_keep_chunk(8)
