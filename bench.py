@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- FRI iterations/s and spawned H.v elements/s of the frisys_mol hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config ne|h2o]
+
+A "step" is one frisys_mol iteration (FRIES_bin/frisys_mol.cpp:405-552: HB-PP matrix compression ->
+spawn -> (route) -> hash-merge -> death/cloning -> find_preserve -> projected energy -> sys_comp -> delete)
+on the Ne aug-cc-pVDZ-sized configuration of examples/run_neon.sh (BASELINE.json configs[1]; synthetic
+integrals, see fries_b200/synth.py).  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # examples/run_neon.sh:12 sizes; FCIDUMP-style input (frozen core dropped), D2h
+    "ne": dict(system="ne", seed=2, point_group="D2h", eps=0.001, target=250000.0, vec_nonz=242000, mat_nonz=260000,
+               max_dets=500000, initiator=1.0, dist="HB_unnorm",
+               workload="Ne aug-cc-pVDZ-sized frisys_mol (NORB=22 NELEC=8 D2h, HB_unnorm, vec_nonz 242000, mat_nonz 260000)"),
+    # Benchmarks/Results.tex:43 sizes, H2O cc-pVDZ, C2v
+    "h2o": dict(system="h2o", seed=3, point_group="C2v", eps=0.001, target=1000000.0, vec_nonz=1000000,
+                mat_nonz=1000000, max_dets=2000000, initiator=1.0, dist="HB_unnorm",
+                workload="H2O cc-pVDZ-sized frisys_mol (NORB=24 NELEC=10 C2v, HB_unnorm, vec_nonz 1e6, mat_nonz 1e6)"),
+}
+
+# SURVEY.md section 8d algorithmic bytes
+B_PER_SAMPLE_STAGE = 40   # per matrix sample per HB-PP stage
+B_PER_SPAWN = 56          # per spawned element (write, read at merge, probe, value RMW)
+START_PARENTS = (1, 1000, 1500)
+B_PER_VEC_EL = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8}
+
+
+def mt_uniforms(seed, n):
+    """std::mt19937(seed)() / (1. + UINT32_MAX), the reference's uniform (compress_utils.cpp:24)"""
+    rs = np.random.RandomState(seed)
+    return rs.randint(0, 2**32, n, dtype=np.uint64) / (1.0 + 0xFFFFFFFF)
+
+
+def mt_u32(rs, n):
+    return rs.randint(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# workload preparation (untimed)
+# ---------------------------------------------------------------------------------------------------
+def prepare_workload(cfg, ctx, n_ranks=1, rank=0):
+    import fries_b200
+    from fries_b200.synth import SynthMol
+
+    sm = SynthMol(cfg["system"], cfg["seed"], frozen=False)
+    mol = fries_b200.Mol.from_synth(ctx, sm)
+    rs = np.random.RandomState(0)  # mt19937(0): proc scrambler then vec scrambler (frisys_mol.cpp:132-144)
+    proc_scr, vec_scr = mt_u32(rs, sm.n_bits), mt_u32(rs, sm.n_bits)
+    hf = np.array([sm.hf], np.uint64)
+    hf_en = float(mol.diag(hf)[0])
+    # trial vector = HF, H*trial with the diagonal shifted by hf_en (frisys_mol.cpp:155-214)
+    tmp = fries_b200.Vec(ctx, 1 << 16, sm.n_bits, sm.n_elec, 2, proc_scr, vec_scr)
+    tmp.set_diag_mol(mol, hf_en)
+    tmp.add(hf, np.ones(1), np.ones(1, np.uint8))
+    tmp.h_apply(mol, 0, 1, 0.0, 1.0)
+    hk, hv = tmp.download()
+    htrial_keys, htrial_vals = hk.copy(), hv[1].copy()
+    n_sing = int(mol.sing_ex(hf)[0][-1])
+    n_doub = int(mol.doub_ex(hf)[0][-1])
+    p_doub = n_doub / (n_sing + n_doub)  # frisys_mol.cpp:217-220
+    tmp.close()
+    # starting vector: (1 - 0.5 (H - E_HF))^3 HF restricted to the PARENTS[k] largest elements before each
+    # application -- a realistic population (HF, singles/doubles, up to hextuples), truncated to the vec_nonz
+    # largest elements and scaled to the target one-norm
+    big = fries_b200.Vec(ctx, 8 * cfg["max_dets"], sm.n_bits, sm.n_elec, 2, proc_scr, vec_scr)
+    big.set_diag_mol(mol, hf_en)
+    k2, cur = hf, np.ones(1)
+    for npar in START_PARENTS:
+        order = np.argsort(-np.abs(cur), kind="stable")[:npar]
+        big.upload(k2[order], np.stack([cur[order], np.zeros(order.size)]))
+        big.h_apply(mol, 0, 1, 1.0, -0.5)
+        k2, v2 = big.download()
+        cur = v2[1]
+    big.close()
+    vals = cur
+    order = np.argsort(-np.abs(vals), kind="stable")[: cfg["vec_nonz"]]
+    keys, vals = k2[order], vals[order]
+    vals = vals * (cfg["target"] / np.abs(vals).sum())
+    perm = np.random.default_rng(7).permutation(keys.size)  # storage order is not sorted by magnitude in a real run
+    keys, vals = np.ascontiguousarray(keys[perm]), np.ascontiguousarray(vals[perm])
+    return dict(sm=sm, mol=mol, proc_scr=proc_scr, vec_scr=vec_scr, hf=hf, hf_en=hf_en, htrial_keys=htrial_keys,
+                htrial_vals=htrial_vals, p_doub=p_doub, keys=keys, vals=vals)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    import fries_b200
+    from fries_b200._capi import FrisysParams, check, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = fries_b200.Context(local)
+    stream = torch.cuda.current_stream()
+    check(lib.fries_ctx_set_stream(ctx.h, stream.cuda_stream))
+
+    if world > 1:
+        from fries_b200.multi import run_multi_gpu_bench
+        return run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_workload, ClockSampler,
+                                   cpu_baseline_block)
+
+    wl = prepare_workload(cfg, ctx)
+    sm, mol = wl["sm"], wl["mol"]
+    spawn_cap = 4 * cfg["mat_nonz"]  # spawn_length = matr_samp * 4 / n_procs (frisys_mol.cpp:109)
+    vec = fries_b200.Vec(ctx, cfg["max_dets"], sm.n_bits, sm.n_elec, 2, wl["proc_scr"], wl["vec_scr"])
+    vec.set_diag_mol(mol, wl["hf_en"])
+    vec.upload(wl["keys"], np.stack([wl["vals"], np.zeros_like(wl["vals"])]))
+    vec.frisys_setup(mol, spawn_cap, wl["hf"], np.ones(1), wl["htrial_keys"], wl["htrial_vals"])
+    params = FrisysParams(eps=cfg["eps"], init_thresh=cfg["initiator"], p_doub=wl["p_doub"],
+                          new_hb=1 if cfg["dist"] == "HB_unnorm" else 0, matr_samp=cfg["mat_nonz"],
+                          target_nonz=cfg["vec_nonz"], en_shift=0.0)
+    uni = mt_uniforms(1, 6 * (args.warmup + 2 * args.steps + 64)).reshape(-1, 6)
+    ui = 0
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    last = None
+    for _ in range(args.warmup):
+        last = vec.frisys_iterate(params, uni[ui]); ui += 1
+
+    # ---- timed region: K iterations, state resident in HBM, L2 flushed between iterations ----
+    clocks = ClockSampler(local)
+    clocks.start()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    spawned = samples = 0
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record(stream)
+        last = vec.frisys_iterate(params, uni[ui]); ui += 1
+        ev[k][1].record(stream)
+        spawned += last.n_spawned
+        samples += last.n_matrix_samples
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    launches = ctx.launch_count - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    ms_per_step = ms / args.steps
+    value = 1000.0 / ms_per_step
+
+    # ---- e2e: the same iteration with the vector in HOST (pinned) memory: upload -> iterate -> download ----
+    n_now = vec.curr_size()
+    hk = torch.empty(cfg["max_dets"], dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+    hv = torch.empty(2 * cfg["max_dets"], dtype=torch.float64).pin_memory().numpy()
+    n_now = vec.download_into(hk, hv)
+    h2d = d2h = 0
+    t_e2e = 0.0
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        check(lib.fries_vec_upload(vec.h, hk.ctypes.data, hv.ctypes.data, n_now))
+        h2d += n_now * 8 * 3 + 48
+        st = vec.frisys_iterate(params, uni[ui]); ui += 1
+        n_now = vec.download_into(hk, hv)
+        d2h += n_now * 8 * 3 + 128
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
+    e2e_value = args.steps / t_e2e
+
+    # ---- per-kernel times (separate pass with event pairs around every launch) ----
+    ctx.set_profile(2)
+    prof_iters = 5
+    for _ in range(prof_iters):
+        flush.zero_()
+        stp = vec.frisys_iterate(params, uni[ui]); ui += 1
+    ctx.set_profile(0)
+    names = ["hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4", "hbpp_finalize", "merge_insert",
+             "merge_accum", "death_axpy", "find_preserve", "sys_comp", "compact"]
+    kern = {}
+    for nm in names:
+        t, n = ctx.kernel_ms(nm)
+        if n:
+            kern[nm] = t / n
+    n_vec = stp.curr_size
+    units = {nm: cfg["mat_nonz"] * B_PER_SAMPLE_STAGE for nm in names if nm.startswith("hbpp_stage")}
+    units["hbpp_finalize"] = stp.n_matrix_samples * (B_PER_SAMPLE_STAGE + 16)
+    units["merge_insert"] = stp.n_spawned * 28
+    units["merge_accum"] = stp.n_spawned * 28
+    for nm, b in B_PER_VEC_EL.items():
+        units[nm] = n_vec * b
+    top = max(kern, key=kern.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = units[top] / (kern[top] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
+                "ms_per_launch": round(kern[top], 4),
+                "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
+                "iter_algorithmic_GBps": round((96 * n_vec + 200 * cfg["mat_nonz"] + 56 * stp.n_spawned) / (ms_per_step * 1e-3) / 1e9, 2)}
+
+    out = {
+        "metric": "fri_iterations_per_sec", "value": round(value, 3), "unit": "iter/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "vec_nonz": cfg["vec_nonz"], "mat_nonz": cfg["mat_nonz"],
+                   "l2": "flushed between iterations (512 MB write)", "stored_dets": int(n_vec)},
+        "spawned_elements_per_sec": round(spawned / (ms * 1e-3), 1),
+        "matrix_samples_per_sec": round(samples / (ms * 1e-3), 1),
+        "gpu_launches": int(launches), "clocks": clk,
+        "e2e": {"value": round(e2e_value, 3), "unit": "iter/s", "h2d_bytes_per_step": int(h2d / args.steps),
+                "d2h_bytes_per_step": int(d2h / args.steps),
+                "what": "fries_vec_upload (pinned host vector) + fries_frisys_mol_iterate + fries_vec_download per step"},
+        "roofline": roofline,
+        "energy_est": last.numer / last.denom if last and last.denom else None,
+    }
+    # CPU baseline: the reference driver started from the SAME warmed-up vector (downloaded from the GPU)
+    wk, wv = vec.download()
+    wl["keys"], wl["vals"] = wk, wv[0]
+    out["cpu_baseline"] = cpu_baseline_block(cfg, wl, n_iter=int(os.environ.get("FRIES_BENCH_CPU_ITERS", "12")))
+    print(json.dumps(out), flush=True)
+    vec.close()
+    mol.close()
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own frisys_mol (oracle/_ref/frisys_mol, built from
+# /root/reference by oracle/Makefile with a single-rank MPI stand-in), same integrals, same start vector.
+# ---------------------------------------------------------------------------------------------------
+def write_fcidump(path, sm, point_group):
+    inv = {"D2h": {0: 1, 7: 2, 6: 3, 1: 4, 5: 5, 2: 6, 3: 7, 4: 8}, "C2v": {0: 1, 2: 2, 3: 3, 1: 4}}[point_group]
+    T = sm.tot_orb
+    with open(path, "w") as f:
+        f.write(f"&FCI NORB={T},NELEC={sm.n_elec_total},MS2=0,\n")
+        f.write("ORBSYM=" + ",".join(str(inv[int(s)]) for s in sm.symm_all) + ",\n")
+        f.write("ISYM=1,\n&END\n")
+        e = sm.eris_chem
+        lines = []
+        for i in range(T):
+            for j in range(i + 1):
+                for k in range(i + 1):
+                    for l in range(k + 1):
+                        if k * (k + 1) // 2 + l > i * (i + 1) // 2 + j:
+                            continue
+                        v = e[i, j, k, l]
+                        if v != 0.0:
+                            lines.append(f"{float(v)!r} {i + 1} {j + 1} {k + 1} {l + 1}\n")
+        f.writelines(lines)
+        for i in range(T):
+            for j in range(i + 1):
+                if sm.hcore[i, j] != 0.0:
+                    f.write(f"{float(sm.hcore[i, j])!r} {i + 1} {j + 1} 0 0\n")
+        f.write("0.0 0 0 0 0\n")
+
+
+def reference_iter_seconds(cfg, sm, keys, vals, it_a, it_b, workdir):
+    exe = os.path.join(ROOT, "oracle", "_ref", "frisys_mol")
+    if not os.path.exists(exe):
+        return None, "oracle/_ref/frisys_mol not built"
+    fd = os.path.join(workdir, "FCIDUMP")
+    write_fcidump(fd, sm, cfg["point_group"])
+    with open(os.path.join(workdir, "ini_dets"), "w") as f:
+        f.write("\n".join(str(int(k)) for k in keys) + "\n")
+    with open(os.path.join(workdir, "ini_vals"), "w") as f:
+        f.write("\n".join(repr(float(v)) for v in vals) + "\n")
+    times = []
+    for n_it in (it_a, it_b):
+        rd = os.path.join(workdir, f"res{n_it}") + "/"
+        os.makedirs(rd, exist_ok=True)
+        cmd = [exe, "--fcidump_path", fd, "--distribution", cfg["dist"], "--vec_nonz", str(cfg["vec_nonz"]), "--mat_nonz",
+               str(cfg["mat_nonz"]), "--max_dets", str(cfg["max_dets"]), "--epsilon", str(cfg["eps"]), "--target",
+               str(cfg["target"]), "--initiator", str(cfg["initiator"]), "--max_iter", str(n_it), "--result_dir", rd,
+               "--ini_vec", os.path.join(workdir, "ini_"), "--point_group", cfg["point_group"]]
+        env = dict(os.environ, FRIES_SEED="1")
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        times.append(time.perf_counter() - t0)
+        if r.returncode != 0 or "Exception" in r.stderr:
+            return None, "reference frisys_mol failed: " + (r.stderr.strip().splitlines() or ["?"])[-1][:200]
+    return (times[1] - times[0]) / (it_b - it_a), None
+
+
+def cpu_baseline_block(cfg, wl, n_iter):
+    wd = tempfile.mkdtemp(prefix="fries_ref_")
+    try:
+        sec, err = reference_iter_seconds(cfg, wl["sm"], wl["keys"], wl["vals"], 2, 2 + n_iter, wd)
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    if sec is None:
+        return {"value": None, "unit": "iter/s", "cores": 1, "kind": "reference", "sample": err}
+    return {"value": round(1.0 / sec, 4), "unit": "iter/s", "cores": 1, "kind": "reference",
+            "sample": f"{n_iter} iterations of the reference's frisys_mol (single rank, no MPI on this host) on the same "
+                      f"FCIDUMP and start vector; loop time = wall(max_iter={2 + n_iter}) - wall(max_iter=2)"}
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # the start vector is produced by our own preparation code when a GPU is present, else by the oracle
+    from fries_b200.synth import SynthMol
+    sm = SynthMol(cfg["system"], cfg["seed"], frozen=False)
+    keys, vals = reference_start_vector(cfg, sm)
+    wd = tempfile.mkdtemp(prefix="fries_ref_")
+    try:
+        sec, err = reference_iter_seconds(cfg, sm, keys, vals, args.warmup, args.warmup + args.steps, wd)
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    if sec is None:
+        print(json.dumps({"impl": "reference", "unavailable": err}), flush=True)
+        return
+    v = round(1.0 / sec, 4)
+    out = {"impl": "reference", "metric": "fri_iterations_per_sec", "value": v, "unit": "iter/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": cfg["workload"], "vec_nonz": cfg["vec_nonz"], "mat_nonz": cfg["mat_nonz"]},
+           "cpu_baseline": {"value": v, "unit": "iter/s", "cores": 1, "kind": "reference",
+                            "sample": f"{args.steps} iterations of oracle/_ref/frisys_mol after {args.warmup} warm-up "
+                                      "iterations, single rank (the reference is single-threaded per MPI rank; no MPI here)"},
+           "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def reference_start_vector(cfg, sm):
+    """Same start vector as the GPU arm, computed with the plain-C oracle's H.v (no GPU needed)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oraclelib
+    om = oraclelib.OracleMol(sm)
+    hf = np.array([sm.hf], np.uint64)
+    hf_en = om.diag(hf)[0]
+    # H shifted by hf_en, as the DistVec diagonal shortcut does: (1 - 0.5 (H - E_HF)) applied twice
+    k2, v2 = hf, np.ones(1)
+    for npar in START_PARENTS:
+        order = np.argsort(-np.abs(v2), kind="stable")[:npar]
+        k2, v2 = om.h_apply(k2[order], v2[order], 1.0 + 0.5 * hf_en, -0.5)
+    order = np.argsort(-np.abs(v2), kind="stable")[: cfg["vec_nonz"]]
+    keys, vals = k2[order], v2[order]
+    vals = vals * (cfg["target"] / np.abs(vals).sum())
+    perm = np.random.default_rng(7).permutation(keys.size)
+    return np.ascontiguousarray(keys[perm]), np.ascontiguousarray(vals[perm])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="ne", choices=sorted(CONFIGS))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

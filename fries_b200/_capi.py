@@ -82,6 +82,7 @@ def _load():
         "fries_vec_n_nonz": (i, [vp, P(sz)]),
         "fries_vec_nonini_occ_add": (i, [vp, P(C.c_uint64)]),
         "fries_vec_download": (i, [vp, vp, vp, sz, P(sz)]),
+        "fries_vec_upload": (i, [vp, vp, vp, sz]),
         "fries_vec_del": (i, [vp, vp, sz]),
         "fries_vec_dot": (i, [vp, vp, vp, sz, u, P(d)]),
         "fries_vec_local_norm": (i, [vp, u, P(d)]),

@@ -246,6 +246,17 @@ class Vec:
         check(lib.fries_vec_download(self.h, ptr(keys), ptr(vals), max(n, 1), C.byref(m)))
         return keys[:n], vals[:, :n]
 
+    def upload(self, keys, vals):
+        """DistVec::load from host arrays: vals is [n_vecs][n]"""
+        k, v = arr(keys, np.uint64), arr(vals, np.float64)
+        check(lib.fries_vec_upload(self.h, ptr(k), ptr(v), k.size))
+
+    def download_into(self, keys, vals) -> int:
+        """download into caller-owned (e.g. pinned) buffers; returns the element count"""
+        m = C.c_size_t(0)
+        check(lib.fries_vec_download(self.h, ptr(keys), ptr(vals), keys.size, C.byref(m)))
+        return m.value
+
     def delete(self, flags):
         f = arr(flags, np.uint8)
         check(lib.fries_vec_del(self.h, ptr(f), f.size))

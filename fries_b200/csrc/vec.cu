@@ -360,6 +360,47 @@ extern "C" int fries_vec_add(fries_vec *vec, const uint64_t *h_keys, const doubl
     return FRIES_OK;
 }
 
+// DistVec::load vec_utils.hpp:761-844 from host arrays: storage <- (keys, value rows), diag cache reset, index rebuilt
+__global__ void upload_fixup_kernel(VecView v, size_t n, unsigned n_elec, unsigned n_bits) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t k = v.keys[i];
+        if ((unsigned)__popcll(k) != n_elec || (k >> n_bits) != 0) bad++;
+        v.diag[i] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    bad = warp_sum_u64(bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(&v.cnt->bad_keys, bad);
+    if (blockIdx.x == 0 && threadIdx.x == 0) v.cnt->n = n;
+}
+
+int fries_vec_compact_flags_dev(fries_vec *vec, const uint8_t *d_flags);
+
+extern "C" int fries_vec_upload(fries_vec *vec, const uint64_t *h_keys, const double *h_vals, size_t n) {
+    FRIES_REQUIRE(vec && (n == 0 || (h_keys && h_vals)), "fries_vec_upload: NULL argument");
+    FRIES_REQUIRE(n <= vec->cap, "fries_vec_upload: %zu elements exceed the capacity %zu", n, vec->cap);
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    VecView v = vec->view();
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(v.keys, h_keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+        for (unsigned r = 0; r < vec->n_vecs; r++)
+            CUDA_TRY(cudaMemcpyAsync(v.vals + (size_t)r * v.cap, h_vals + (size_t)r * n, n * 8, cudaMemcpyHostToDevice,
+                                     c->stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(vec->cnt.p, 0, sizeof(VecCounters), c->stream));
+    upload_fixup_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(v, n, vec->n_elec, vec->n_bits);
+    c->launch_count++;
+    FRIES_TRY(fries_vec_compact_flags_dev(vec, nullptr));  // drops all-zero elements, rebuilds the index
+    VecCounters cnt;
+    FRIES_TRY(vec->read_counters(&cnt));
+    if (cnt.bad_keys) {
+        fries_set_error("fries_vec_upload: %llu determinants with an incorrect number of electrons", cnt.bad_keys);
+        return FRIES_ERR_ARG;
+    }
+    return FRIES_OK;
+}
+
 extern "C" int fries_vec_curr_size(fries_vec *vec, size_t *curr_size) {
     FRIES_REQUIRE(vec && curr_size, "NULL argument");
     VecCounters cnt;

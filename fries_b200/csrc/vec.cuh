@@ -16,6 +16,7 @@ struct VecCounters {
     unsigned long long nonini_occ_add;  // DistVec::nonini_occ_add
     unsigned long long overflow;        // insertions refused because the store is full
     unsigned long long n_spawn_valid;   // elements seen by the last merge
+    unsigned long long bad_keys;        // uploaded keys with a wrong electron count
 };
 
 struct VecView {

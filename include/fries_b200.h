@@ -163,6 +163,9 @@ int fries_vec_n_nonz(fries_vec *vec, size_t *n_nonz);               /* DistVec::
 int fries_vec_nonini_occ_add(fries_vec *vec, uint64_t *count);      /* DistVec::tot_sgn_coh :546-551 */
 /* copy out storage: keys[curr_size], vals[n_vecs][curr_size] (row-major with row stride curr_size) */
 int fries_vec_download(fries_vec *vec, uint64_t *h_keys, double *h_vals, size_t cap, size_t *n);
+/* DistVec::load :761-844 from host arrays instead of files: replace the contents by n elements (vals = n_vecs rows
+ * with row stride n), drop elements that are zero in every row, reset the diagonal cache, rebuild the index */
+int fries_vec_upload(fries_vec *vec, const uint64_t *h_keys, const double *h_vals, size_t n);
 /* DistVec::del_at_pos :458-476 for all flagged positions, followed by compaction of the storage
  * (stable) and a rebuild of the hash index */
 int fries_vec_del(fries_vec *vec, const uint8_t *h_flags, size_t n);
