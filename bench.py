@@ -230,6 +230,7 @@ def run_ours(args, cfg):
         flush.zero_()
         stp = vec.frisys_iterate(params, uni[ui]); ui += 1
     ctx.set_profile(0)
+    states = vec.states()
     names = ["hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4", "hbpp_finalize", "merge_insert",
              "merge_accum", "death_axpy", "find_preserve", "sys_comp", "compact"]
     kern = {}
@@ -257,6 +258,8 @@ def run_ours(args, cfg):
                 "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
                 "ms_per_launch": round(kern[top], 4),
                 "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
+                "rounds": {"hbpp_stages": [int(x) for x in states[:5, 4]], "find_preserve": int(states[6, 4])},
+                "stage_items_in": [int(x) for x in states[:5, 7]], "stage_items_out": [int(x) for x in states[:5, 6]],
                 "iter_algorithmic_GBps": round((96 * n_vec + 200 * cfg["mat_nonz"] + 56 * stp.n_spawned) / (ms_per_step * 1e-3) / 1e9, 2)}
 
     out = {

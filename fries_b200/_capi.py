@@ -74,6 +74,7 @@ def _load():
         "fries_mol_hb_wt": (i, [vp, i, vp, vp, sz, vp]),
         "fries_apply_hbpp_sys": (i, [vp, vp, vp, sz, d, i, vp, u, sz, vp, vp, vp, sz, P(sz)]),
         "fries_debug_hbpp_stage": (i, [vp, vp, vp, sz, d, i, vp, u, sz, i, vp, vp, vp, vp, P(sz)]),
+        "fries_hbpp_states": (i, [vp, vp]),
         "fries_vec_create": (i, [vp, sz, u, u, u, vp, vp, i, i, P(vp)]),
         "fries_vec_destroy": (i, [vp]),
         "fries_vec_add": (i, [vp, vp, vp, vp, sz, u, u]),

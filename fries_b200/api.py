@@ -298,6 +298,12 @@ class Vec:
         check(lib.fries_frisys_mol_iterate(self.h, self.mol.h, self.hb, C.byref(params), ptr(u), C.byref(st)))
         return st
 
+    def states(self):
+        """CompState records of the last iteration: dict name -> [8][...]"""
+        out = np.zeros((8, 8))
+        check(lib.fries_hbpp_states(self.hb, ptr(out)))
+        return out
+
     def frifull_iterate(self, params: FrifullParams, uniform: float) -> IterStats:
         st = IterStats()
         check(lib.fries_frifull_mol_iterate(self.h, self.mol.h, self.hb, C.byref(params), uniform, C.byref(st)))

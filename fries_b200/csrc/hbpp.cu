@@ -526,3 +526,21 @@ extern "C" int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, co
     fries_hbpp_destroy(hb);
     return FRIES_OK;
 }
+
+// Diagnostics: the CompState records of the last iteration -- per state 8 doubles:
+// loc_norm, glob_norm, new_norm, n_samp_left, rounds, n_kept, n_out, n_in.  States 0-4: HB-PP stages,
+// 5: finalize, 6: find_preserve, 7: sys_comp.
+extern "C" int fries_hbpp_states(fries_hbpp *hb, double *h_out64) {
+    FRIES_REQUIRE(hb && h_out64, "fries_hbpp_states: NULL argument");
+    fries_ctx *c = hb->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CompState st[8];
+    CUDA_TRY(cudaMemcpyAsync(st, hb->st.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < 8; s++) {
+        double *o = h_out64 + 8 * s;
+        o[0] = st[s].loc_norm; o[1] = st[s].glob_norm; o[2] = st[s].new_norm; o[3] = st[s].n_samp_left;
+        o[4] = st[s].rounds; o[5] = (double)st[s].n_kept; o[6] = (double)st[s].n_out; o[7] = (double)st[s].n_in;
+    }
+    return FRIES_OK;
+}

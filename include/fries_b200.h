@@ -224,6 +224,10 @@ int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, const double 
                            int new_hb, const double *h_uniforms5, unsigned n_samp, size_t spawn_cap, int stage,
                            double *h_val, uint32_t *h_det, uint32_t *h_path, uint32_t *h_sub, size_t *n_out);
 
+/* CompState records of the last iteration, 8 states x 8 doubles (loc_norm, glob_norm, new_norm, n_samp_left,
+ * rounds, n_kept, n_out, n_in); states 0-4 = HB-PP stages, 5 = finalize, 6 = find_preserve, 7 = sys_comp */
+int fries_hbpp_states(fries_hbpp *hb, double *h_out64);
+
 #ifdef __cplusplus
 }
 #endif

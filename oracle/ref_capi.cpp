@@ -352,8 +352,10 @@ size_t ref_mol_apply_hbpp_sys(void *h, const uint64_t *keys, const double *vals,
     RefMol *m = (RefMol *)h;
     unsigned ne = m->n_elec - m->n_frz;
     unsigned n_bytes = CEILING(2 * m->n_orb, 8);
-    Matrix<uint8_t> all_orbs(n ? n : 1, ne);
-    Matrix<uint8_t> all_dets(n ? n : 1, n_bytes);
+    /* one spare (zeroed) row: calc_u1_probs and find_nth_virt read occ_orbs[n_elec], i.e. the first entry of the
+     * next row; in the drivers the matrix is DistVec::occ_orbs_ with max_size rows, so that entry always exists */
+    Matrix<uint8_t> all_orbs(n + 1, ne);
+    Matrix<uint8_t> all_dets(n + 1, n_bytes);
     for (size_t i = 0; i < n; i++) {
         key_to_bytes(keys[i], all_dets[i], n_bytes);
         find_bits(all_dets[i], all_orbs[i], (uint8_t)n_bytes);
