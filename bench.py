@@ -156,7 +156,10 @@ def run_ours(args, cfg):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = fries_b200.Context(local)
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream for the library's kernels, the L2 flush and the timing events
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     check(lib.fries_ctx_set_stream(ctx.h, stream.cuda_stream))
 
     if world > 1:

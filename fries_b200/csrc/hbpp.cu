@@ -3,6 +3,10 @@
 
 extern __shared__ double fr_dyn_smem[];
 
+#ifndef FR_STAGE_MIN_CTAS
+#define FR_STAGE_MIN_CTAS 2  // two 512-thread CTAs per SM (<= 64 registers): the stage passes are latency bound
+#endif
+
 __device__ __forceinline__ uint32_t pk(unsigned p0, unsigned p1, unsigned p2, unsigned p3) {
     return (p0 & 0xff) | ((p1 & 0xff) << 8) | ((p2 & 0xff) << 16) | ((p3 & 0xff) << 24);
 }
@@ -160,7 +164,7 @@ struct HbProvider {
 };
 
 template <int S>
-__global__ void __launch_bounds__(FR_COMP_BLOCK)
+__global__ void __launch_bounds__(FR_COMP_BLOCK, FR_STAGE_MIN_CTAS)
 hbpp_stage_kernel(MolView gm, HbStageIO io, CompSubBufs bufs, unsigned n_samp, double rn) {
     HbProvider<S> prov;
     prov.m = mol_stage_shared(gm, fr_dyn_smem);
