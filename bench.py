@@ -39,7 +39,11 @@ CONFIGS = {
 # SURVEY.md section 8d algorithmic bytes
 B_PER_SAMPLE_STAGE = 40   # per matrix sample per HB-PP stage
 B_PER_SPAWN = 56          # per spawned element (write, read at merge, probe, value RMW)
-START_PARENTS = (1, 1000, 1500)
+START_PARENTS = (1, 1000, 1500)  # parents kept before each H application (x vec_nonz / 242000 for the last)
+
+
+def start_parents(cfg):
+    return START_PARENTS[:2] + (max(START_PARENTS[2], START_PARENTS[2] * cfg["vec_nonz"] // 242000),)
 B_PER_VEC_EL = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8}
 
 
@@ -83,7 +87,7 @@ def prepare_workload(cfg, ctx, n_ranks=1, rank=0):
     big = fries_b200.Vec(ctx, 8 * cfg["max_dets"], sm.n_bits, sm.n_elec, 2, proc_scr, vec_scr)
     big.set_diag_mol(mol, hf_en)
     k2, cur = hf, np.ones(1)
-    for npar in START_PARENTS:
+    for npar in start_parents(cfg):
         order = np.argsort(-np.abs(cur), kind="stable")[:npar]
         big.upload(k2[order], np.stack([cur[order], np.zeros(order.size)]))
         big.h_apply(mol, 0, 1, 1.0, -0.5)
@@ -397,7 +401,7 @@ def reference_start_vector(cfg, sm):
     hf_en = om.diag(hf)[0]
     # H shifted by hf_en, as the DistVec diagonal shortcut does: (1 - 0.5 (H - E_HF)) applied twice
     k2, v2 = hf, np.ones(1)
-    for npar in START_PARENTS:
+    for npar in start_parents(cfg):
         order = np.argsort(-np.abs(v2), kind="stable")[:npar]
         k2, v2 = om.h_apply(k2[order], v2[order], 1.0 + 0.5 * hf_en, -0.5)
     order = np.argsort(-np.abs(v2), kind="stable")[: cfg["vec_nonz"]]

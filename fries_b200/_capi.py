@@ -75,6 +75,14 @@ def _load():
         "fries_apply_hbpp_sys": (i, [vp, vp, vp, sz, d, i, vp, u, sz, vp, vp, vp, sz, P(sz)]),
         "fries_debug_hbpp_stage": (i, [vp, vp, vp, sz, d, i, vp, u, sz, i, vp, vp, vp, vp, P(sz)]),
         "fries_hbpp_states": (i, [vp, vp]),
+        "fries_comm_create": (i, [vp, i, i, P(vp), vp]),
+        "fries_comm_connect": (i, [vp, vp]),
+        "fries_comm_destroy": (i, [vp]),
+        "fries_comm_error": (i, [vp, P(C.c_uint64)]),
+        "fries_ctx_set_comm": (i, [vp, vp]),
+        "fries_hbpp_set_route": (i, [vp, vp, vp, vp, vp, sz]),
+        "fries_frisys_mol_spawn": (i, [vp, vp, vp, P(FrisysParams), vp]),
+        "fries_frisys_mol_finish": (i, [vp, vp, vp, P(FrisysParams), vp, vp, P(IterStats)]),
         "fries_vec_create": (i, [vp, sz, u, u, u, vp, vp, i, i, P(vp)]),
         "fries_vec_destroy": (i, [vp]),
         "fries_vec_add": (i, [vp, vp, vp, vp, sz, u, u]),

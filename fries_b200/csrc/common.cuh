@@ -63,6 +63,8 @@ struct fries_ctx {
     int ensure_scratch(size_t bytes);
     // cooperative grid size for a kernel (blocks) given block size and dynamic smem
     int coop_grid(const void *kernel, int block, size_t smem);
+    // multi-rank: peer-mapped inboxes used by the *_dev compression entry points (fries_ctx_set_comm); not owned
+    struct fries_comm *comm = nullptr;
 };
 
 // RAII-less profiling helpers: wrap a launch region

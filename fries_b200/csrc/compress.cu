@@ -10,8 +10,12 @@
 __global__ void __launch_bounds__(FR_COMP_BLOCK)
 find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned long long *__restrict__ n_ptr,
                      unsigned n_samp_in, uint8_t *__restrict__ keep, double *part_d, unsigned long long *part_c,
-                     CompState *st) {
+                     CompState *st, CommView cm) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ double sh_x0[FR_MAX_RANKS], sh_x1[FR_MAX_RANKS];
+    __shared__ unsigned long long sh_xc[FR_MAX_RANKS];
+    CommCursor cur = comm_begin(cm);
+    const bool multi = cm.n_ranks > 1;
     if (n_ptr) {  // resident pipeline: the element count lives on the device
         unsigned long long dn = *n_ptr;
         if (dn < n) n = (size_t)dn;
@@ -31,15 +35,20 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
     }
     unsigned long long dummy = 0;
     grid_reduce(grid, red, s, dummy);
-    const double glob_total = s;
-    double loc = s;
+    double loc = s, R_next = s;
+    if (multi) {  // *global_norm = sum_mpi(loc_one_norm) (:50)
+        double before;
+        comm_allgather(cm, cur, s, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+        comm_sum(cm, sh_x0, R_next, before);
+    }
+    const double glob_total = R_next;
     unsigned nrem = n_samp_in;
     unsigned long long glob_sampled = 1, kept_total = 0;
     bool recalc = false;
     double R = 0;
     unsigned rounds = 0;
     while (glob_sampled > 0) {
-        R = loc;
+        R = R_next;
         double rem = 0;
         unsigned long long cnt = 0;
         if (R >= 0) {
@@ -57,6 +66,13 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
         }
         grid_reduce(grid, red, rem, cnt);
         loc -= rem;
+        R_next = loc;
+        if (multi) {  // glob_sampled = sum_mpi(loc_sampled) (:76); next glob_one_norm = sum_mpi(loc_one_norm) (:53)
+            double before;
+            comm_allgather(cm, cur, loc, 0.0, cnt, sh_x0, sh_x1, sh_xc);
+            comm_sum(cm, sh_x0, R_next, before);
+            cnt = comm_sum_u64(cm, sh_xc);
+        }
         glob_sampled = cnt;
         nrem -= (unsigned)cnt;
         kept_total += cnt;
@@ -67,6 +83,12 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
                 if (!keep[i]) t += fabs(vals[i]);
             grid_reduce(grid, red, t, dummy);
             loc = t;
+            R_next = t;
+            if (multi) {
+                double before;
+                comm_allgather(cm, cur, t, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+                comm_sum(cm, sh_x0, R_next, before);
+            }
             glob_sampled = 1;
             recalc = true;
         } else {
@@ -91,6 +113,8 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
         st->n_kept = kept_total;
         st->n_in = n;
     }
+    grid.sync();
+    comm_end(cm, cur);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -103,8 +127,11 @@ __global__ void __launch_bounds__(FR_COMP_BLOCK)
 sys_comp_kernel(double *__restrict__ vals, size_t n, const unsigned long long *__restrict__ n_ptr,
                 uint8_t *__restrict__ keep, const double *__restrict__ in_r4, double lbound0_host, double glob_host,
                 long long n_samp_host, double rn_uniform, double *part_d, unsigned long long *part_c,
-                CompState *out_st) {
+                CompState *out_st, CommView cm) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ double sh_x0[FR_MAX_RANKS], sh_x1[FR_MAX_RANKS];
+    __shared__ unsigned long long sh_xc[FR_MAX_RANKS];
+    CommCursor cur = comm_begin(cm);
     if (n_ptr) {
         unsigned long long dn = *n_ptr;
         if (dn < n) n = (size_t)dn;
@@ -123,9 +150,15 @@ sys_comp_kernel(double *__restrict__ vals, size_t n, const unsigned long long *_
     double G = glob_host, lbound0 = lbound0_host;
     unsigned n_samp = (unsigned)n_samp_host;
     if (n_samp_host < 0) {
+        // resident pipeline: this rank's residual norm and the global budget come from find_preserve; the
+        // loc_norms are all-gathered here (frisys_mol.cpp:532) and summed in rank order (:292-295, :114-121)
         G = in_r4[0];
         n_samp = (unsigned)in_r4[2];
         lbound0 = 0;
+        if (cm.n_ranks > 1) {
+            comm_allgather(cm, cur, in_r4[0], 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+            comm_sum(cm, sh_x0, G, lbound0);
+        }
     }
     SysGrid sg;
     if (n_samp > 0) {
@@ -191,6 +224,8 @@ sys_comp_kernel(double *__restrict__ vals, size_t n, const unsigned long long *_
         out_st->new_norm = new_norm;
         out_st->n_out = n_samples;
     }
+    grid.sync();
+    comm_end(cm, cur);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -257,20 +292,23 @@ __global__ void state_to_result4(const CompState *st, double *r4) {
 
 int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, const unsigned long long *d_n,
                                unsigned n_samp, uint8_t *d_keep, CompState *d_st, double *pd, unsigned long long *pc,
-                               int grid) {
+                               int grid, const fries_comm *comm) {
+    CommView cmv = fries_comm_view(comm);
     if (grid <= 0) grid = c->coop_grid((const void *)find_preserve_kernel, FR_COMP_BLOCK, 0);
     void *args[] = {(void *)&d_values, (void *)&count, (void *)&d_n, (void *)&n_samp, (void *)&d_keep, (void *)&pd,
-                    (void *)&pc, (void *)&d_st};
+                    (void *)&pc, (void *)&d_st, (void *)&cmv};
     ProfScope ps(c, "find_preserve");
     return coop_launch(c, (const void *)find_preserve_kernel, grid, args);
 }
 
 int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, const unsigned long long *d_n, uint8_t *d_keep,
                           const double *d_in, double lbound0, double glob, long long n_samp, double rn, CompState *d_out,
-                          double *pd, unsigned long long *pc, int grid) {
+                          double *pd, unsigned long long *pc, int grid, const fries_comm *comm) {
+    CommView cmv = fries_comm_view(comm);
     if (grid <= 0) grid = c->coop_grid((const void *)sys_comp_kernel, FR_COMP_BLOCK, 0);
     void *args[] = {(void *)&d_values, (void *)&count, (void *)&d_n,  (void *)&d_keep, (void *)&d_in, (void *)&lbound0,
-                    (void *)&glob,     (void *)&n_samp, (void *)&rn,  (void *)&pd,     (void *)&pc,   (void *)&d_out};
+                    (void *)&glob,     (void *)&n_samp, (void *)&rn,  (void *)&pd,     (void *)&pc,   (void *)&d_out,
+                    (void *)&cmv};
     ProfScope ps(c, "sys_comp");
     return coop_launch(c, (const void *)sys_comp_kernel, grid, args);
 }
@@ -288,7 +326,7 @@ extern "C" int fries_find_preserve(fries_ctx *c, const double *h_values, size_t 
     RedScratch r;
     FRIES_TRY(red_scratch(c, grid, 0, r));
     CUDA_TRY(cudaMemcpyAsync(vals.p, h_values, count * 8, cudaMemcpyHostToDevice, c->stream));
-    FRIES_TRY(fries_find_preserve_launch(c, vals.p, count, nullptr, *n_samp, keep.p, r.st, r.pd, r.pc, grid));
+    FRIES_TRY(fries_find_preserve_launch(c, vals.p, count, nullptr, *n_samp, keep.p, r.st, r.pd, r.pc, grid, nullptr));
     CompState st;
     CUDA_TRY(cudaMemcpyAsync(&st, r.st, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     if (count) CUDA_TRY(cudaMemcpyAsync(h_keep, keep.p, count, cudaMemcpyDeviceToHost, c->stream));
@@ -318,7 +356,7 @@ extern "C" int fries_sys_comp(fries_ctx *c, double *h_values, size_t count, doub
     CUDA_TRY(cudaMemcpyAsync(vals.p, h_values, count * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(keep.p, h_keep, count, cudaMemcpyHostToDevice, c->stream));
     FRIES_TRY(fries_sys_comp_launch(c, vals.p, count, nullptr, keep.p, nullptr, lbound0, glob, (long long)n_samp, rand_num,
-                                    r.st + 1, r.pd, r.pc, grid));
+                                    r.st + 1, r.pd, r.pc, grid, nullptr));
     CompState st;
     CUDA_TRY(cudaMemcpyAsync(&st, r.st + 1, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     if (count) {
@@ -337,7 +375,7 @@ extern "C" int fries_find_preserve_dev(fries_ctx *c, const double *d_values, siz
     int grid = c->coop_grid((const void *)find_preserve_kernel, FR_COMP_BLOCK, 0);
     RedScratch r;
     FRIES_TRY(red_scratch(c, grid, 0, r));
-    FRIES_TRY(fries_find_preserve_launch(c, d_values, count, nullptr, n_samp, d_keep, r.st, r.pd, r.pc, grid));
+    FRIES_TRY(fries_find_preserve_launch(c, d_values, count, nullptr, n_samp, d_keep, r.st, r.pd, r.pc, grid, c->comm));
     state_to_result4<<<1, 1, 0, c->stream>>>(r.st, d_result4);
     c->launch_count++;
     CUDA_TRY(cudaGetLastError());
@@ -352,7 +390,7 @@ extern "C" int fries_sys_comp_dev(fries_ctx *c, double *d_values, size_t count, 
     RedScratch r;
     FRIES_TRY(red_scratch(c, grid, 0, r));
     FRIES_TRY(fries_sys_comp_launch(c, d_values, count, nullptr, d_keep, d_result4, 0.0, 0.0, -1LL, rand_num, r.st + 1, r.pd,
-                                    r.pc, grid));
+                                    r.pc, grid, c->comm));
     if (d_new_norm) {
         CUDA_TRY(cudaMemcpyAsync(d_new_norm, &r.st[1].new_norm, 8, cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -396,7 +434,7 @@ extern "C" int fries_comp_sub(fries_ctx *c, const double *h_values, size_t count
     CUDA_TRY(cudaMemsetAsync(r.st, 0, sizeof(CompState), c->stream));
     MatProvider prov{values.p, ndiv.p, subw.p, h_sub_sizes ? ssz.p : nullptr, count, n_sub};
     CompSubBufs bufs{veff.p, wtr.p, lb.p, ndiv.p, keep.p, kcnt.p, nsub.p, oval.p, owidx.p, osub.p,
-                     (unsigned long long)out_cap, r.pd, r.pc, r.st};
+                     (unsigned long long)out_cap, r.pd, r.pc, r.st, fries_comm_view(nullptr)};
     // ndiv is both provider input and engine state: give the engine its own copy
     DevBuf<uint32_t> ndiv_state;
     FRIES_TRY(ndiv_state.alloc(cn));

@@ -10,6 +10,7 @@
 // residual weights; an element draws the grid points rn0 + k*unit that fall in its interval.
 #pragma once
 #include "common.cuh"
+#include "comm.cuh"
 
 #define FR_COMP_BLOCK 512
 
@@ -121,6 +122,7 @@ struct CompSubBufs {
     double *part_d;               // [2][grid]
     unsigned long long *part_c;   // [2][grid]
     CompState *st;
+    CommView cm;                  // n_ranks == 1: no cross-rank exchange
 };
 
 // The hierarchical compression engine.  Provider P supplies
@@ -143,6 +145,12 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     const size_t lo = (size_t)blockIdx.x * chunk < n ? (size_t)blockIdx.x * chunk : n;
     const size_t hi = lo + chunk < n ? lo + chunk : n;
 
+    __shared__ double sh_x0[FR_MAX_RANKS], sh_x1[FR_MAX_RANKS];
+    __shared__ unsigned long long sh_xc[FR_MAX_RANKS];
+    const CommView &cm = b.cm;
+    CommCursor cur = comm_begin(cm);
+    const bool multi = cm.n_ranks > 1;
+
     // ---- phase 0: effective weights (find_keep_sub :134-137) ----
     double s = 0;
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
@@ -158,7 +166,14 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     }
     unsigned long long dummy = 0;
     grid_reduce(grid, red, s, dummy);
-    double loc = s;
+    double loc = s;          // this rank's loc_one_norm
+    double R_next = s;       // sum_mpi(loc_one_norm) for the coming round
+    if (multi) {
+        double before;
+        comm_allgather(cm, cur, s, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+        comm_sum(cm, sh_x0, R_next, before);
+        s = R_next;          // global one-norm (reported)
+    }
 
     // ---- keep rounds (find_keep_sub :153-265) ----
     unsigned nrem = n_samp_in;
@@ -168,7 +183,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     unsigned rounds = 0;
     unsigned long long kept_total = 0;
     while (glob_sampled > 0) {
-        R = loc;
+        R = R_next;
         if (R < 0) break;
         const double wt_factor = (double)nrem;
         double rem = 0;
@@ -215,6 +230,13 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         }
         grid_reduce(grid, red, rem, cnt);
         loc -= rem;
+        R_next = loc;
+        if (multi) {  // glob_sampled = sum_mpi(loc_sampled); next round's norm = sum_mpi(loc_one_norm)
+            double before;
+            comm_allgather(cm, cur, loc, 0.0, cnt, sh_x0, sh_x1, sh_xc);
+            comm_sum(cm, sh_x0, R_next, before);
+            cnt = comm_sum_u64(cm, sh_xc);
+        }
         glob_sampled = cnt;
         nrem -= (unsigned)cnt;
         kept_total += cnt;
@@ -227,6 +249,12 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
             for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) t += b.wt_remain[i];
             grid_reduce(grid, red, t, dummy);
             loc = t;
+            R_next = t;
+            if (multi) {
+                double before;
+                comm_allgather(cm, cur, t, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+                comm_sum(cm, sh_x0, R_next, before);
+            }
         }
     }
     double loc_final = 0;
@@ -240,15 +268,28 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     }
 
     // ---- resampling (sys_sub :702-794) ----
-    const double G = loc_final;
+    // loc_norms are all-gathered (comp_sub :818); this rank's grid starts at seed_sys(lbound0) (:107-127)
+    double G = loc_final, lbound0 = 0;
+    if (multi) {
+        comm_allgather(cm, cur, loc_final, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+        comm_sum(cm, sh_x0, G, lbound0);
+    }
     SysGrid sg;
-    sg.n = nrem;
     if (nrem > 0) {
-        sg.rn0 = seed_sys_dev(0.0, G, rn_uniform, nrem);
         sg.unit = G / nrem;
+        long long j0 = (long long)(int)(lbound0 * nrem / G);
+        double r = rn_uniform * sg.unit;
+        r += sg.unit * (int)(lbound0 * nrem / G);
+        if (r < lbound0) {
+            r += sg.unit;
+            j0++;
+        }
+        sg.rn0 = r;
+        sg.n = (long long)nrem - j0;
     } else {
         sg.rn0 = INFINITY;
         sg.unit = INFINITY;
+        sg.n = 0;
     }
 
     // pass 1: chunk sums of the residual weights -> canonical CTA boundaries
@@ -262,7 +303,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     grid_excl_scan(grid, red, cs, 0ull, blk_lb, e0, tot_lb, e1, sh_sd, sh_sc);
 
     // pass 2: per-input lower bound + number of outputs
-    double carry = blk_lb;
+    double carry = lbound0 + blk_lb;
     unsigned long long my_out = 0;
     unsigned long long anomalies = 0;
     for (size_t base = lo; base < hi; base += blockDim.x) {
@@ -405,4 +446,6 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         b.st->n_out = tot_out < b.out_cap ? tot_out : b.out_cap;
         b.st->n_in = n;
     }
+    grid.sync();
+    comm_end(cm, cur);
 }

@@ -183,12 +183,25 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
                      const uint32_t *__restrict__ ppath, double p_doub, int new_hb, double *__restrict__ fin_val,
                      uint32_t *__restrict__ fin_det, uint32_t *__restrict__ fin_orbs, HbSpawnArgs sp, CompState *st) {
     MolView m = mol_stage_shared(gm, fr_dyn_smem);
+    __shared__ uint32_t s_pscr[64];
+    if (sp.n_ranks > 1) {
+        if (threadIdx.x < 64) s_pscr[threadIdx.x] = sp.proc_scr[threadIdx.x];
+        __syncthreads();
+    }
     const unsigned ne = m.d.n_elec, M = m.d.n_orb;
     unsigned long long n = *n_ptr;
     if (n > in_cap) n = in_cap;
     unsigned long long ok = 0;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    // warp-uniform trip count: the routed path uses warp-wide match/shuffle
+    size_t n_round = (n + 31) & ~(size_t)31;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += stride) {
+      const bool live = i0 < n;
+      const size_t i = live ? i0 : 0;
+      double el = 0;
+      uint64_t nk = FRIES_EMPTY_KEY;
+      double add = 0;
+      if (live) {
         const uint32_t widx = pw[i], sub = ps[i];
         const uint32_t d = pdet[widx], pp = ppath[widx];
         const uint64_t key = keys[d];
@@ -196,7 +209,6 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
         mol_occ_list(key, occ);
         unsigned p0 = pp & 0xff, p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
         uint8_t orbs[4] = {0, 0, 0, 0};
-        double el = 0;
         bool is_doub = p0 == 0;
         if (is_doub) {
             unsigned o1 = occ[p1], o2 = occ[p2], u1 = p3;
@@ -242,10 +254,8 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
             }
         }
         if (el != 0) ok++;
-        if (sp.out_keys) {
+        if (sp.out_keys || sp.n_ranks > 1) {
             // spawn loop body frisys_mol.cpp:436-461
-            uint64_t nk = FRIES_EMPTY_KEY;
-            double add = 0;
             if (el != 0) {
                 double cv = sp.v0[d];
                 add = -sp.eps * el;
@@ -257,13 +267,38 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
                     nk = (nk & ~(1ull << orbs[0])) | (1ull << orbs[1]);
                 if (fabs(cv) >= sp.init_thresh) nk |= FRIES_INI_FLAG;
             }
-            sp.out_keys[i] = nk;
-            sp.out_vals[i] = add;
+            if (sp.n_ranks <= 1) {
+                sp.out_keys[i] = nk;
+                sp.out_vals[i] = add;
+            }
         } else {
             fin_val[i] = el;
             fin_det[i] = d;
             fin_orbs[i] = pk(orbs[0], orbs[1], orbs[2], orbs[3]);
         }
+      }  // live
+      if (sp.n_ranks > 1) {
+        // route: one atomicAdd per (warp, destination) instead of one per element
+        int owner = -1;
+        if (nk != FRIES_EMPTY_KEY) owner = (int)(fr_det_hash(nk & ~FRIES_INI_FLAG, s_pscr) % (unsigned)sp.n_ranks);
+        unsigned peers = __match_any_sync(0xffffffffu, owner);
+        if (owner >= 0) {
+            unsigned lane = threadIdx.x & 31;
+            int leader = __ffs(peers) - 1;
+            unsigned rank_in = __popc(peers & ((1u << lane) - 1));
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(&sp.send_counts[owner], (unsigned long long)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            unsigned long long slot = base + rank_in;
+            if (slot < sp.seg_cap) {
+                uint64_t *seg = sp.send_buf + (size_t)owner * 2 * sp.seg_cap;
+                seg[slot] = nk;
+                seg[sp.seg_cap + slot] = (uint64_t)__double_as_longlong(add);
+            } else {
+                atomicAdd(&sp.send_counts[sp.n_ranks], 1ull);
+            }
+        }
+      }
     }
     ok = warp_sum_u64(ok);
     if ((threadIdx.x & 31) == 0 && ok) atomicAdd(&st->n_out, ok);
@@ -351,7 +386,7 @@ int fries_hbpp_stages_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys
         io.in_cap = hb->cap;
         CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
                          hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
-                         hb->part_d.p, hb->part_c.p, hb->st.p + s};
+                         hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(hb->comm)};
         switch (s) {
             case 0: FRIES_TRY(launch_stage<0>(hb, mol, io, bufs, n_samp, u5[0])); break;
             case 1: FRIES_TRY(launch_stage<1>(hb, mol, io, bufs, n_samp, u5[1])); break;
@@ -366,7 +401,7 @@ int fries_hbpp_stages_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys
 int fries_hbpp_finalize_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, double p_doub, int new_hb,
                             const HbSpawnArgs *spawn) {
     fries_ctx *c = hb->ctx;
-    HbSpawnArgs sp{nullptr, 0, 0, nullptr, nullptr};
+    HbSpawnArgs sp{nullptr, 0, 0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0};
     if (spawn) sp = *spawn;
     size_t smem = (size_t)mol->view.d.blob_doubles * 8;
     int grid = c->sm_count * 4;
@@ -500,7 +535,7 @@ extern "C" int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, co
         io.p_doub = p_doub; io.new_hb = new_hb; io.in_cap = hb->cap;
         CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
                          hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
-                         hb->part_d.p, hb->part_c.p, hb->st.p + s};
+                         hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(hb->comm)};
         switch (s) {
             case 0: FRIES_TRY(launch_stage<0>(hb, mol, io, bufs, n_samp, h_uniforms5[0])); break;
             case 1: FRIES_TRY(launch_stage<1>(hb, mol, io, bufs, n_samp, h_uniforms5[1])); break;

@@ -42,6 +42,11 @@ struct fries_hbpp {
     DevBuf<uint8_t> keep_flags;
     size_t n_trial = 0, n_htrial = 0;
     int grid = 0;
+    fries_comm *comm = nullptr;  // multi-rank: peer-mapped inboxes (comm.cuh); not owned
+    // multi-rank routing: per-destination send segments (keys | vals) and counters
+    int64_t *send_buf = nullptr, *recv_buf = nullptr;  // caller-owned device buffers [n_ranks][2 * seg_cap]
+    unsigned long long *send_counts_ext = nullptr;     // caller-owned [n_ranks + 1]: per-destination counts + overflow
+    size_t seg_cap = 0;
 };
 
 // stages = false: only the reduction scratch and counters (spawn buffers are added by the caller)
@@ -58,6 +63,13 @@ struct HbSpawnArgs {
     double eps, init_thresh;
     uint64_t *out_keys;      // new determinant | FRIES_INI_FLAG, FRIES_EMPTY_KEY for failed samples
     double *out_vals;
+    // multi-rank routing (Adder::add vec_utils.hpp:957-971): pack by owner = hash(proc_scrambler) % n_ranks into
+    // per-destination segments [keys[seg_cap] | vals[seg_cap]] of the all-to-all send buffer
+    int n_ranks;
+    const uint32_t *proc_scr;              // device, 64 entries
+    uint64_t *send_buf;                    // [n_ranks][2 * seg_cap]
+    unsigned long long *send_counts;       // [n_ranks] + [n_ranks] = overflow counter
+    unsigned long long seg_cap;
 };
 int fries_hbpp_finalize_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, double p_doub, int new_hb,
                             const HbSpawnArgs *spawn);

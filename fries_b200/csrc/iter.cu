@@ -7,10 +7,10 @@ extern __shared__ double fr_dyn_smem[];
 
 int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, const unsigned long long *d_n,
                                unsigned n_samp, uint8_t *d_keep, CompState *d_st, double *pd, unsigned long long *pc,
-                               int grid);
+                               int grid, const fries_comm *comm);
 int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, const unsigned long long *d_n, uint8_t *d_keep,
                           const double *d_in, double lbound0, double glob, long long n_samp, double rn, CompState *d_out,
-                          double *pd, unsigned long long *pc, int grid);
+                          double *pd, unsigned long long *pc, int grid, const fries_comm *comm);
 int fries_vec_compact_flags_dev(fries_vec *vec, const uint8_t *d_flags);
 
 #define FR_NAN __longlong_as_double(0x7ff8000000000000ll)
@@ -446,7 +446,7 @@ static int compress_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, uns
     VecView v = vec->view();
     double *vals = v.vals + (size_t)row * v.cap;
     FRIES_TRY(fries_find_preserve_launch(c, vals, vec->cap, &vec->cnt.p->n, target_nonz, hb->keep_flags.p, hb->st.p + 6,
-                                         hb->part_d.p, hb->part_c.p, 0));
+                                         hb->part_d.p, hb->part_c.p, 0, hb->comm));
     state_to_r4_kernel<<<1, 1, 0, c->stream>>>(hb->st.p + 6, hb->scal.p + IterScalars::R4);
     c->launch_count++;
     (void)uniform;
@@ -458,7 +458,7 @@ static int resample_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, dou
     VecView v = vec->view();
     double *vals = v.vals + (size_t)row * v.cap;
     FRIES_TRY(fries_sys_comp_launch(c, vals, vec->cap, &vec->cnt.p->n, hb->keep_flags.p, hb->scal.p + IterScalars::R4,
-                                    0.0, 0.0, -1LL, uniform, hb->st.p + 7, hb->part_d.p, hb->part_c.p, 0));
+                                    0.0, 0.0, -1LL, uniform, hb->st.p + 7, hb->part_d.p, hb->part_c.p, 0, hb->comm));
     FRIES_TRY(fries_vec_compact_flags_dev(vec, hb->keep_flags.p));
     return FRIES_OK;
 }
@@ -502,7 +502,7 @@ static int read_stats(fries_vec *vec, fries_hbpp *hb, fries_iter_stats *stats, c
 extern "C" int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
                                         const double *u6, fries_iter_stats *stats) {
     FRIES_REQUIRE(vec && mol && hb && p && u6, "fries_frisys_mol_iterate: NULL argument");
-    FRIES_REQUIRE(vec->n_ranks == 1, "fries_frisys_mol_iterate: multi-rank vectors go through fries_frisys_mol_spawn/merge");
+    FRIES_REQUIRE(vec->n_ranks == 1, "fries_frisys_mol_iterate: multi-rank vectors go through fries_frisys_mol_spawn + _finish");
     fries_ctx *c = vec->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     VecView v = vec->view();
@@ -510,7 +510,7 @@ extern "C" int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hb
     // steps 2-3: hierarchical compression of H's columns
     FRIES_TRY(fries_hbpp_stages_dev(hb, mol, v.keys, v.vals, &vec->cnt.p->n, p->p_doub, p->new_hb, u6, p->matr_samp));
     // step 5: spawn (fused into finalize) and merge into row 1
-    HbSpawnArgs sp{v.vals, p->eps, p->init_thresh, hb->spawn_keys.p, hb->spawn_vals.p};
+    HbSpawnArgs sp{v.vals, p->eps, p->init_thresh, hb->spawn_keys.p, hb->spawn_vals.p, 1, nullptr, nullptr, nullptr, 0};
     FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, v.keys, p->p_doub, p->new_hb, &sp));
     FRIES_TRY(fries_vec_merge_dev(vec, hb->spawn_keys.p, hb->spawn_vals.p, hb->cap, &hb->st.p[4].n_out, 0, 1));
     // step 7: death/cloning, add_vecs(0, 1), zero row 1
@@ -527,6 +527,104 @@ extern "C" int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hb
     // step 11: systematic resampling + deletion of the zeroed elements
     FRIES_TRY(resample_vector_dev(vec, hb, 0, u6[5]));
     return read_stats(vec, hb, stats, "fries_frisys_mol_iterate");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-rank frisys_mol: the iteration is split around the all-to-all that the host issues
+// (torch.distributed / NCCL, on the same stream) -- spawn [stages + finalize + pack by owner] -> exchange
+// counts + payload -> finish [merge, death/cloning, compression].  Global reductions inside the
+// kernels go through the peer-mapped inboxes (comm.cuh).
+// ---------------------------------------------------------------------------------------------------
+struct fries_comm;
+extern "C" int fries_hbpp_set_route(fries_hbpp *hb, fries_comm *comm, void *d_send_buf, void *d_recv_buf,
+                                    void *d_send_counts, size_t seg_cap) {
+    FRIES_REQUIRE(hb && comm && d_send_buf && d_recv_buf && d_send_counts && seg_cap > 0, "fries_hbpp_set_route: bad argument");
+    hb->comm = comm;
+    hb->send_buf = (int64_t *)d_send_buf;
+    hb->recv_buf = (int64_t *)d_recv_buf;
+    hb->send_counts_ext = (unsigned long long *)d_send_counts;
+    hb->seg_cap = seg_cap;
+    return FRIES_OK;
+}
+
+// sum (numer, denom) and the per-rank counters over the ranks, in rank order; one CTA
+__global__ void xrank_stats_kernel(CommView cm, double *scal, const VecCounters *cnt, const CompState *st, double *out) {
+    __shared__ double sh_x0[FR_MAX_RANKS], sh_x1[FR_MAX_RANKS];
+    __shared__ unsigned long long sh_xc[FR_MAX_RANKS];
+    CommCursor cur = comm_begin(cm);
+    comm_allgather(cm, cur, scal[IterScalars::NUMER], scal[IterScalars::DENOM], cnt->n, sh_x0, sh_x1, sh_xc);
+    double numer, denom, b;
+    comm_sum(cm, sh_x0, numer, b);
+    comm_sum(cm, sh_x1, denom, b);
+    unsigned long long n_glob = comm_sum_u64(cm, sh_xc);
+    comm_allgather(cm, cur, (double)st[5].n_out, 0.0, cnt->overflow, sh_x0, sh_x1, sh_xc);
+    double spawned;
+    comm_sum(cm, sh_x0, spawned, b);
+    if (threadIdx.x == 0) {
+        scal[IterScalars::NUMER] = numer;
+        scal[IterScalars::DENOM] = denom;
+        out[0] = (double)n_glob;
+        out[1] = spawned;
+    }
+    __syncthreads();
+    comm_end(cm, cur);
+}
+
+extern "C" int fries_frisys_mol_spawn(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
+                                      const double *u6) {
+    FRIES_REQUIRE(vec && mol && hb && p && u6, "fries_frisys_mol_spawn: NULL argument");
+    FRIES_REQUIRE(hb->comm && hb->send_buf, "fries_frisys_mol_spawn: call fries_hbpp_set_route first");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    VecView v = vec->view();
+    CUDA_TRY(cudaMemsetAsync(hb->send_counts_ext, 0, (vec->n_ranks + 1) * 8, c->stream));
+    FRIES_TRY(fries_hbpp_stages_dev(hb, mol, v.keys, v.vals, &vec->cnt.p->n, p->p_doub, p->new_hb, u6, p->matr_samp));
+    HbSpawnArgs sp{v.vals, p->eps, p->init_thresh, nullptr, nullptr, vec->n_ranks, v.scr_proc, (uint64_t *)hb->send_buf,
+                   hb->send_counts_ext, (unsigned long long)hb->seg_cap};
+    FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, v.keys, p->p_doub, p->new_hb, &sp));
+    return FRIES_OK;
+}
+
+extern "C" int fries_frisys_mol_finish(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
+                                       const double *u6, const void *d_recv_counts, fries_iter_stats *stats) {
+    FRIES_REQUIRE(vec && mol && hb && p && u6 && d_recv_counts, "fries_frisys_mol_finish: NULL argument");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    VecView v = vec->view();
+    size_t smem = (size_t)mol->view.d.blob_doubles * 8;
+    MergeSrc src{(const uint64_t *)hb->recv_buf, nullptr, (size_t)vec->n_ranks * hb->seg_cap, nullptr,
+                 (const unsigned long long *)d_recv_counts, hb->seg_cap};
+    FRIES_TRY(fries_vec_merge_src_dev(vec, src, 0, 1));
+    {
+        ProfScope ps(c, "death_axpy");
+        death_axpy_kernel<<<c->sm_count * 8, 256, smem, c->stream>>>(mol->view, v, vec->hf_en, p->eps, p->en_shift);
+        c->launch_count++;
+    }
+    FRIES_TRY(compress_vector_dev(vec, hb, 0, p->target_nonz, u6[5]));
+    FRIES_TRY(dot_dev(vec, hb->htrial_keys.p, hb->htrial_vals.p, hb->n_htrial, 0, hb->scal.p + IterScalars::NUMER));
+    FRIES_TRY(dot_dev(vec, hb->trial_keys.p, hb->trial_vals.p, hb->n_trial, 0, hb->scal.p + IterScalars::DENOM));
+    FRIES_TRY(resample_vector_dev(vec, hb, 0, u6[5]));
+    xrank_stats_kernel<<<1, 32, 0, c->stream>>>(fries_comm_view(hb->comm), hb->scal.p, vec->cnt.p, hb->st.p,
+                                                hb->scal.p + 32);
+    c->launch_count++;
+    int rc = read_stats(vec, hb, stats, "fries_frisys_mol_finish");
+    if (stats) {
+        double g[2];
+        CUDA_TRY(cudaMemcpyAsync(g, hb->scal.p + 32, 16, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        stats->curr_size = (uint64_t)g[0];          // global number of stored determinants
+        stats->n_spawned = stats->n_matrix_samples = (uint64_t)g[1];
+    }
+    // elements that did not fit a send segment
+    unsigned long long ov = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ov, hb->send_counts_ext + vec->n_ranks, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (rc == FRIES_OK && ov) {
+        fries_set_error("fries_frisys_mol_finish: %llu spawned elements did not fit the send segments (seg_cap %zu)", ov,
+                        hb->seg_cap);
+        return FRIES_ERR_CAPACITY;
+    }
+    return rc;
 }
 
 // frifull_mol.cpp:256-320.  The vector alternates between rows: `src` is the row holding the current

@@ -17,20 +17,17 @@ __device__ __forceinline__ void load_scr(uint32_t *s_scr, const uint32_t *g_scr)
 // first insertion); streaming: 16 B in, 4 B out.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FR_VEC_BLOCK)
-merge_insert_kernel(VecView v, const uint64_t *__restrict__ in_keys, const double *__restrict__ in_vals, size_t n_max,
-                    const unsigned long long *__restrict__ d_n, uint32_t *__restrict__ slot_out) {
+merge_insert_kernel(VecView v, MergeSrc src, uint32_t *__restrict__ slot_out) {
     __shared__ uint32_t s_scr[64];
     load_scr(s_scr, v.scr_vec);
-    size_t n = n_max;
-    if (d_n) {
-        unsigned long long dn = *d_n;
-        n = dn < n_max ? (size_t)dn : n_max;
-    }
+    size_t n = src.count();
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t k = in_keys[i];
+        uint64_t k = FRIES_EMPTY_KEY;
+        double val = 0;
+        bool have = src.get(i, k, val);
         uint32_t result = FRIES_NO_POS;
-        if (k != FRIES_EMPTY_KEY && in_vals[i] != 0) {  // DistVec::add ignores zero values (:418-423)
+        if (have && k != FRIES_EMPTY_KEY && val != 0) {  // DistVec::add ignores zero values (:418-423)
             bool ini = (k >> 63) != 0;
             uint64_t key = k & ~FRIES_INI_FLAG;
             uint64_t slot = fr_det_hash(key, s_scr) & v.tmask;
@@ -72,14 +69,8 @@ merge_insert_kernel(VecView v, const uint64_t *__restrict__ in_keys, const doubl
 
 // merge phase B: accumulate with the initiator rule (vec_utils.hpp:632-637)
 __global__ void __launch_bounds__(FR_VEC_BLOCK)
-merge_accum_kernel(VecView v, const uint64_t *__restrict__ in_keys, const double *__restrict__ in_vals, size_t n_max,
-                   const unsigned long long *__restrict__ d_n, const uint32_t *__restrict__ slot_in, unsigned origin,
-                   unsigned dest) {
-    size_t n = n_max;
-    if (d_n) {
-        unsigned long long dn = *d_n;
-        n = dn < n_max ? (size_t)dn : n_max;
-    }
+merge_accum_kernel(VecView v, MergeSrc src, const uint32_t *__restrict__ slot_in, unsigned origin, unsigned dest) {
+    size_t n = src.count();
     size_t stride = (size_t)gridDim.x * blockDim.x;
     unsigned long long nonini = 0, valid = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -88,9 +79,12 @@ merge_accum_kernel(VecView v, const uint64_t *__restrict__ in_keys, const double
         uint32_t pos = v.tpos[slot];
         if (pos == FRIES_NO_POS) continue;
         valid++;
-        bool ini = (in_keys[i] >> 63) != 0;
+        uint64_t k;
+        double val;
+        src.get(i, k, val);
+        bool ini = (k >> 63) != 0;
         bool nonz = v.vals[(size_t)origin * v.cap + pos] != 0;
-        if (ini || nonz) atomicAdd(&v.vals[(size_t)dest * v.cap + pos], in_vals[i]);
+        if (ini || nonz) atomicAdd(&v.vals[(size_t)dest * v.cap + pos], val);
         if (!ini && nonz) nonini++;
     }
     nonini = warp_sum_u64(nonini);
@@ -291,8 +285,14 @@ extern "C" int fries_vec_destroy(fries_vec *v) {
 
 int fries_vec_merge_dev(fries_vec *vec, const uint64_t *d_keys, const double *d_vals, size_t n_max,
                         const unsigned long long *d_n, unsigned origin, unsigned dest) {
+    MergeSrc src{d_keys, d_vals, n_max, d_n, nullptr, 0};
+    return fries_vec_merge_src_dev(vec, src, origin, dest);
+}
+
+int fries_vec_merge_src_dev(fries_vec *vec, const MergeSrc &src, unsigned origin, unsigned dest) {
     fries_ctx *c = vec->ctx;
     FRIES_REQUIRE(origin < vec->n_vecs && dest < vec->n_vecs, "merge: row index out of range");
+    const size_t n_max = src.n_max;
     if (n_max == 0) return FRIES_OK;
     FRIES_TRY(vec->slot_scratch.ensure(n_max));
     VecView v = vec->view();
@@ -300,13 +300,12 @@ int fries_vec_merge_dev(fries_vec *vec, const uint64_t *d_keys, const double *d_
     int grid = (int)(want < (size_t)c->sm_count * 8 ? want : (size_t)c->sm_count * 8);
     {
         ProfScope ps(c, "merge_insert");
-        merge_insert_kernel<<<grid, FR_VEC_BLOCK, 0, c->stream>>>(v, d_keys, d_vals, n_max, d_n, vec->slot_scratch.p);
+        merge_insert_kernel<<<grid, FR_VEC_BLOCK, 0, c->stream>>>(v, src, vec->slot_scratch.p);
         c->launch_count++;
     }
     {
         ProfScope ps(c, "merge_accum");
-        merge_accum_kernel<<<grid, FR_VEC_BLOCK, 0, c->stream>>>(v, d_keys, d_vals, n_max, d_n, vec->slot_scratch.p,
-                                                                 origin, dest);
+        merge_accum_kernel<<<grid, FR_VEC_BLOCK, 0, c->stream>>>(v, src, vec->slot_scratch.p, origin, dest);
         c->launch_count++;
     }
     clamp_count_kernel<<<1, 1, 0, c->stream>>>(vec->cnt.p, (unsigned long long)vec->cap);

@@ -87,6 +87,35 @@ __device__ __forceinline__ uint32_t vec_lookup(const VecView &v, uint64_t key, c
     }
 }
 
+// Where a merge reads its (key | INI, value) pairs from: one flat list with an optional device-side count, or
+// the receive buffer of the all-to-all: n_seg segments [keys[seg_cap] | vals[seg_cap]] with per-segment counts.
+struct MergeSrc {
+    const uint64_t *keys;
+    const double *vals;
+    size_t n_max;                          // flat: capacity; segmented: n_seg * seg_cap
+    const unsigned long long *d_n;         // flat: optional device count
+    const unsigned long long *seg_counts;  // segmented: elements per segment (nullptr = flat)
+    size_t seg_cap;
+    __device__ __forceinline__ size_t count() const {
+        if (seg_counts || !d_n) return n_max;
+        unsigned long long dn = *d_n;
+        return dn < n_max ? (size_t)dn : n_max;
+    }
+    __device__ __forceinline__ bool get(size_t i, uint64_t &k, double &v) const {
+        if (seg_counts) {
+            size_t seg = i / seg_cap, j = i - seg * seg_cap;
+            if (j >= seg_counts[seg]) return false;
+            const uint64_t *base = keys + seg * 2 * seg_cap;
+            k = base[j];
+            v = __longlong_as_double((long long)base[seg_cap + j]);
+            return true;
+        }
+        k = keys[i];
+        v = vals[i];
+        return true;
+    }
+};
 int fries_vec_merge_dev(fries_vec *vec, const uint64_t *d_keys, const double *d_vals, size_t n_max,
                         const unsigned long long *d_n, unsigned origin, unsigned dest);
+int fries_vec_merge_src_dev(fries_vec *vec, const MergeSrc &src, unsigned origin, unsigned dest);
 int fries_vec_compact_dev(fries_vec *vec);

@@ -216,6 +216,29 @@ typedef struct {
 int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frifull_params *p,
                               double uniform, fries_iter_stats *stats);
 
+/* ---- multi-GPU (one process per GPU; owner = hash_fxn(occ; proc_scrambler) % n_ranks, vec_utils.hpp:373-379) ----
+ * Global reductions (sum_mpi compress_utils.hpp:179-231, the loc_norms Allgather) happen INSIDE the kernels through
+ * peer-mapped inboxes: fries_comm_create returns a 64-byte CUDA IPC handle, the host all-gathers the handles
+ * (torch.distributed) and passes all n_ranks x 64 bytes to fries_comm_connect.  The all-to-all of spawned elements
+ * (Adder::perform_add vec_utils.hpp:991-1019) is issued by the host between _spawn and _finish on caller-owned
+ * device buffers: send/recv_buf int64[n_ranks][2 * seg_cap] (keys | value bits per destination), send_counts
+ * int64[n_ranks + 1] (last entry = elements that did not fit). */
+typedef struct fries_comm fries_comm;
+int fries_comm_create(fries_ctx *ctx, int n_ranks, int rank, fries_comm **out, void *h_ipc_handle64);
+int fries_comm_connect(fries_comm *comm, const void *h_all_handles);
+int fries_comm_destroy(fries_comm *comm);
+int fries_comm_error(fries_comm *comm, uint64_t *epoch_of_failure);
+/* make fries_find_preserve_dev / fries_sys_comp_dev of this context collective over the ranks of comm */
+int fries_ctx_set_comm(fries_ctx *ctx, fries_comm *comm);
+int fries_hbpp_set_route(fries_hbpp *hb, fries_comm *comm, void *d_send_buf, void *d_recv_buf, void *d_send_counts,
+                         size_t seg_cap);
+/* frisys_mol.cpp:405-471 up to Adder::add; then, after the all-to-all, :465-539 from add_elements on.
+ * stats of _finish are global (summed over ranks in rank order). */
+int fries_frisys_mol_spawn(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
+                           const double *h_uniforms6);
+int fries_frisys_mol_finish(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
+                            const double *h_uniforms6, const void *d_recv_counts, fries_iter_stats *stats);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------
  * Output list of stage `stage` (0..4) of apply_HBPP_sys: value, parent index, packed path bytes of the
  * parent item (orb_indices state) and chosen sub-index (comp_idx[.][1]).  Used by the parity tests to
