@@ -28,7 +28,8 @@ class FrisysParams(C.Structure):
 
 
 class FrifullParams(C.Structure):
-    _fields_ = [("eps", C.c_double), ("target_nonz", C.c_uint), ("en_shift", C.c_double)]
+    _fields_ = [("eps", C.c_double), ("target_nonz", C.c_uint), ("en_shift", C.c_double), ("adjust_shift", C.c_int),
+                ("damp_factor", C.c_double), ("target_norm", C.c_double), ("last_one_norm", C.c_double)]
 
 
 class IterStats(C.Structure):

@@ -629,7 +629,7 @@ extern "C" int fries_frisys_mol_finish(fries_vec *vec, fries_mol *mol, fries_hbp
 
 // frifull_mol.cpp:256-320.  The vector alternates between rows: `src` is the row holding the current
 // iterate (vec_idx), the result lands in the other row.
-extern "C" int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frifull_params *p,
+extern "C" int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, fries_frifull_params *p,
                                          double uniform, fries_iter_stats *stats) {
     FRIES_REQUIRE(vec && mol && hb && p, "fries_frifull_mol_iterate: NULL argument");
     FRIES_REQUIRE(vec->n_ranks == 1, "fries_frifull_mol_iterate: single-rank entry point");
@@ -639,6 +639,17 @@ extern "C" int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_h
     CUDA_TRY(cudaMemsetAsync(hb->st.p, 0, 8 * sizeof(CompState), c->stream));
     FRIES_TRY(dot_dev(vec, hb->trial_keys.p, hb->trial_vals.p, hb->n_trial, src, hb->scal.p + IterScalars::DENOM));
     FRIES_TRY(compress_vector_dev(vec, hb, src, p->target_nonz, uniform));
+    if (p->adjust_shift) {  // needs the one-norm before compression on the host
+        double r4[4];
+        CUDA_TRY(cudaMemcpyAsync(r4, hb->scal.p + IterScalars::R4, sizeof(r4), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        double one_norm = r4[1];
+        if (p->last_one_norm) {
+            p->en_shift -= p->damp_factor * log(one_norm / p->last_one_norm);
+            p->last_one_norm = one_norm;
+        }
+        if (p->last_one_norm == 0 && one_norm > p->target_norm) p->last_one_norm = one_norm;
+    }
     FRIES_TRY(resample_vector_dev(vec, hb, src, uniform));
     uint64_t ns = 0;
     FRIES_TRY(h_apply_dev(vec, mol, hb, src, dst, 1 + p->eps * p->en_shift, -p->eps, true, &ns));

@@ -1,0 +1,469 @@
+// fries_host.hpp -- C++ host layer above the C-ABI (include/fries_b200.h).
+//
+// Mirrors the parts of the reference's host interface that the in-scope drivers use, with the reference's
+// names, argument meaning and error behaviour (std::runtime_error, caught in main):
+//   DistVec            FRIES/vec_utils.hpp:121-953      -> fries::DistVec (device-resident store)
+//   find_preserve ...  FRIES/compress_utils.hpp:28-429  -> fries::find_preserve / sys_comp / comp_sub / adjust_shift
+//   parse_fcidump ...  FRIES/io_utils.hpp:23-207        -> fries::parse_fcidump / parse_hf_input / load_vec_txt / ...
+//   argparse kwargs    FRIES/Ext_Libs/argparse.hpp      -> fries::Args (same --key value syntax and failure modes)
+// All arithmetic on vectors happens in libfries_b200.so (CUDA); this file is marshalling, file formats, control flow.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fries_b200.h"
+
+namespace fries {
+
+inline void check(int rc) {
+    if (rc != FRIES_OK) throw std::runtime_error(fries_last_error());
+}
+
+// ---- FRIES/math_utils.h macros ---------------------------------------------------------------------------------
+inline size_t ceiling(size_t x, size_t y) { return (x + y - 1) / y; }
+inline size_t tri_wdiag(size_t i, size_t j) { return j * (j + 1) / 2 + i; }
+
+// ---- determinant bit strings: the reference's uint8_t[] <-> the library's u64 key -------------------------------
+inline uint64_t key_from_bytes(const uint8_t *det, size_t n_bytes) {
+    uint64_t k = 0;
+    for (size_t b = 0; b < n_bytes && b < 8; b++) k |= (uint64_t)det[b] << (8 * b);
+    return k;
+}
+inline void key_to_bytes(uint64_t k, uint8_t *det, size_t n_bytes) {
+    for (size_t b = 0; b < n_bytes; b++) det[b] = b < 8 ? (uint8_t)(k >> (8 * b)) : 0;
+}
+// gen_hf_bitstring FRIES/fci_utils.c:10-43
+inline uint64_t gen_hf_bitstring(unsigned n_orb, unsigned n_elec) {
+    uint64_t k = 0;
+    for (unsigned i = 0; i < n_elec / 2; i++) k |= (1ull << i) | (1ull << (i + n_orb));
+    return k;
+}
+
+// ---- command line: argparse::Args semantics (Ext_Libs/argparse.hpp:347-393) ---------------------------------------
+class Args {
+    std::map<std::string, std::string> kv_;
+    std::vector<std::string> known_;
+    std::string errors_;
+
+  public:
+    Args(int argc, char **argv) {
+        for (int i = 1; i < argc; i++) {
+            std::string a = argv[i];
+            if (a.rfind("--", 0) != 0) continue;
+            a = a.substr(2);
+            size_t eq = a.find('=');
+            if (eq != std::string::npos) {
+                kv_[a.substr(0, eq)] = a.substr(eq + 1);
+            } else if (i + 1 < argc && (argv[i + 1][0] != '-' || std::isdigit((unsigned char)argv[i + 1][1]))) {
+                kv_[a] = argv[++i];
+            } else {
+                kv_[a] = "";
+                errors_ += "No value provided for: " + a + "\n";
+            }
+        }
+    }
+    bool has(const std::string &k) {
+        known_.push_back(k);
+        return kv_.count(k) != 0;
+    }
+    std::string str(const std::string &k) {  // required
+        if (!has(k)) errors_ += "Argument missing: --" + k + "\n";
+        return kv_[k];
+    }
+    std::string str(const std::string &k, const std::string &dflt) { return has(k) ? kv_[k] : dflt; }
+    double num(const std::string &k) {
+        std::string s = str(k);
+        return s.empty() ? 0 : std::stod(s);
+    }
+    double num(const std::string &k, double dflt) { return has(k) ? std::stod(kv_[k]) : dflt; }
+    void validate() {  // unknown flag -> warning and continue; missing required -> exit(-1)
+        for (auto &p : kv_) {
+            bool ok = false;
+            for (auto &k : known_) ok = ok || k == p.first;
+            if (!ok) std::cerr << "unrecognised commandline argument: " << p.first << std::endl;
+        }
+        if (!errors_.empty()) {
+            std::cerr << errors_;
+            std::exit(-1);
+        }
+    }
+};
+
+// ---- input files -----------------------------------------------------------------------------------------------------
+struct MolInput {
+    unsigned n_elec = 0;  // TOTAL electrons
+    unsigned n_frz = 0;
+    unsigned n_orb = 0;   // unfrozen spatial orbitals
+    double eps = 0, hf_en = 0, core_en = 0;
+    std::vector<uint8_t> symm;          // irreps of the unfrozen orbitals
+    std::vector<double> hcore;          // tot_orb^2
+    std::vector<double> eris_packed;    // SymmERIs layout (FRIES/ndarr.hpp:206-244) over tot_orb orbitals
+    unsigned tot_orb() const { return n_orb + n_frz / 2; }
+};
+
+// convert_symm FRIES/io_utils.cpp:189-239
+inline void convert_symm(std::vector<uint8_t> &irreps, const std::string &pg) {
+    auto apply = [&](const std::vector<uint8_t> &map, unsigned maxi) {
+        for (auto &x : irreps) {
+            if (x > maxi || x < 1) {
+                std::stringstream msg;
+                msg << "irrep index " << (unsigned)x << " read from the FCIDUMP file exceeds the maximum allowed irrep index ("
+                    << maxi << ") for point group " << pg;
+                throw std::runtime_error(msg.str());
+            }
+            x = map[x - 1];
+        }
+    };
+    if (pg == "D2h" || pg == "d2h") apply({0, 7, 6, 1, 5, 2, 3, 4}, 8);
+    else if (pg == "C2v" || pg == "c2v" || pg == "c2h" || pg == "C2h") apply({0, 2, 3, 1}, 4);
+    else if (pg == "D2" || pg == "d2") apply({0, 3, 2, 1}, 4);
+    else if (pg == "Cs" || pg == "cs" || pg == "C2" || pg == "c2" || pg == "ci" || pg == "Ci") apply({0, 1}, 2);
+    else if (pg == "C1" || pg == "c1") apply({0}, 1);
+    else throw std::runtime_error("Point group " + pg + " not recognized");
+}
+
+// parse_fcidump FRIES/io_utils.cpp:241-318
+inline MolInput parse_fcidump(const std::string &path, const std::string &point_group) {
+    std::ifstream in(path);
+    if (!in.is_open()) throw std::runtime_error("Could not open FCIDUMP file " + path);
+    std::string line;
+    std::getline(in, line);
+    auto field = [&](const std::string &key) {
+        size_t p = line.find(key);
+        if (p == std::string::npos) throw std::runtime_error("Could not find " + key + " in the first line of the FCIDUMP file");
+        size_t e = line.find(",", p);
+        return std::stoi(line.substr(p + key.size(), e - (p + key.size())));
+    };
+    MolInput m;
+    m.n_orb = field("NORB=");
+    m.n_elec = field("NELEC=");
+    if (field("MS2=") != 0) throw std::runtime_error("MS2 is not zero in FCIDUMP file.");
+    std::getline(in, line);
+    size_t p = line.find("ORBSYM=");
+    std::stringstream ss(line.substr(p == std::string::npos ? 0 : p + 7));
+    std::string tok;
+    while (std::getline(ss, tok, ',')) {
+        try {
+            if (!tok.empty()) m.symm.push_back((uint8_t)std::stoi(tok));
+        } catch (std::invalid_argument &) {
+        }
+    }
+    if (m.symm.size() != m.n_orb)
+        throw std::runtime_error("Number of irrep labels read in after ORBSYM in FCIDUMP file does not equal number of orbitals");
+    convert_symm(m.symm, point_group);
+    std::getline(in, line);  // ISYM
+    std::getline(in, line);  // &END
+    size_t T = m.n_orb, n_pair = T * (T + 1) / 2;
+    m.hcore.assign(T * T, 0.0);
+    m.eris_packed.assign(n_pair * (n_pair + 1) / 2, 0.0);
+    double v;
+    unsigned o[4];
+    while (in >> v >> o[0] >> o[1] >> o[2] >> o[3]) {
+        if (!o[0] && !o[1] && !o[2] && !o[3]) m.core_en = v;
+        else if (!o[1] && !o[2] && !o[3]) continue;
+        else if (!o[2] && !o[3]) m.hcore[(o[1] - 1) * T + o[0] - 1] = m.hcore[(o[0] - 1) * T + o[1] - 1] = v;
+        else  // chemist_ordered(o3-1, o2-1, o1-1, o0-1): stored exactly where the reference stores it
+            m.eris_packed[tri_wdiag(tri_wdiag(o[3] - 1, o[2] - 1), tri_wdiag(o[1] - 1, o[0] - 1))] = v;
+    }
+    return m;
+}
+
+inline size_t read_csv(std::vector<double> &out, const std::string &path) {
+    std::ifstream f(path);
+    if (!f.is_open()) throw std::runtime_error("Could not open file " + path);
+    std::string tok;
+    out.clear();
+    char c;
+    while (f.get(c)) {
+        if (c == ',' || c == '\n' || c == ' ' || c == '\r' || c == '\t') {
+            if (!tok.empty()) out.push_back(std::stod(tok));
+            tok.clear();
+        } else {
+            tok += c;
+        }
+    }
+    if (!tok.empty()) out.push_back(std::stod(tok));
+    return out.size();
+}
+
+// parse_hf_input FRIES/io_utils.cpp:98-187 (legacy directory: sys_params.txt, symm.txt, hcore.txt, eris.txt)
+inline MolInput parse_hf_input(const std::string &dir) {
+    std::ifstream in(dir + "sys_params.txt");
+    if (!in.is_open()) throw std::runtime_error("Could not open file sys_params.txt");
+    MolInput m;
+    std::string key;
+    auto expect = [&](const char *name, auto &dst) {
+        std::getline(in, key);
+        if (key.empty()) std::getline(in, key);
+        if (key != name) throw std::runtime_error(std::string("Could not find ") + name + " parameter in sys_params.txt");
+        in >> dst;
+        std::getline(in, key);
+    };
+    expect("n_elec", m.n_elec);
+    expect("n_frozen", m.n_frz);
+    expect("n_orb", m.n_orb);
+    expect("eps", m.eps);
+    expect("hf_energy", m.hf_en);
+    size_t T = m.tot_orb();
+    std::vector<double> tmp;
+    read_csv(tmp, dir + "symm.txt");
+    if (tmp.size() < T) throw std::runtime_error("Could not read the orbital irreps from symm.txt");
+    for (size_t i = m.n_frz / 2; i < T; i++) m.symm.push_back((uint8_t)tmp[i]);
+    if (read_csv(m.hcore, dir + "hcore.txt") < T * T) {
+        std::stringstream msg;
+        msg << "Could not read " << T * T << " elements from " << dir << "hcore.txt";
+        throw std::runtime_error(msg.str());
+    }
+    if (read_csv(tmp, dir + "eris.txt") < T * T * T * T) {
+        std::stringstream msg;
+        msg << "Could not read " << T * T * T * T << " elements from " << dir << "eris.txt";
+        throw std::runtime_error(msg.str());
+    }
+    // eris.txt is the dense FourDArr eris(i,j,a,b) = <ij|ab> = (ia|jb): pack the canonical representatives
+    size_t n_pair = T * (T + 1) / 2;
+    m.eris_packed.assign(n_pair * (n_pair + 1) / 2, 0.0);
+    for (size_t i = 0; i < T; i++)
+        for (size_t a = i; a < T; a++)
+            for (size_t j = 0; j < T; j++)
+                for (size_t b = j; b < T; b++) {
+                    size_t p1 = tri_wdiag(i, a), p2 = tri_wdiag(j, b);
+                    if (p1 <= p2) m.eris_packed[tri_wdiag(p1, p2)] = tmp[((i * T + j) * T + a) * T + b];
+                }
+    return m;
+}
+
+// read_dets + load_vec_txt FRIES/io_utils.cpp:410-482,565-586
+inline size_t load_vec_txt(const std::string &prefix, std::vector<uint64_t> &dets, std::vector<double> &vals) {
+    std::ifstream fd(prefix + "dets");
+    if (!fd.is_open()) throw std::runtime_error("Could not open file: " + prefix + "dets");
+    long long d;
+    dets.clear();
+    while (fd >> d) dets.push_back((uint64_t)d);
+    std::ifstream fv(prefix + "vals");
+    if (!fv.is_open()) throw std::runtime_error("Could not open file: " + prefix + "vals");
+    double v;
+    vals.clear();
+    while (fv >> v) vals.push_back(v);
+    if (vals.size() > dets.size()) {
+        std::cerr << "Warning: fewer determinants (" << dets.size() << ") than values (" << vals.size() << ") read in\n";
+        vals.resize(dets.size());
+    } else if (vals.size() < dets.size()) {
+        std::cerr << "Warning: fewer values (" << vals.size() << ") than determinants (" << dets.size() << ") read in\n";
+        dets.resize(vals.size());
+    }
+    return vals.size();
+}
+
+// save_proc_hash / load_proc_hash FRIES/io_utils.cpp:589-619
+inline void save_proc_hash(const std::string &dir, const std::vector<uint32_t> &scr) {
+    std::ofstream f(dir + "hash.dat", std::ios::binary);
+    if (!f.is_open()) throw std::runtime_error("Could not save file at path " + dir + "hash.dat");
+    f.write((const char *)scr.data(), sizeof(uint32_t) * scr.size());
+}
+inline void load_proc_hash(const std::string &dir, std::vector<uint32_t> &scr) {
+    std::ifstream f(dir + "hash.dat", std::ios::binary);
+    if (!f.is_open()) throw std::runtime_error("Could not open saved hash scrambler at " + dir + "hash.dat");
+    f.read((char *)scr.data(), sizeof(uint32_t) * scr.size());
+}
+// load_last_line FRIES/io_utils.cpp:636-663 (one number per line files)
+inline bool load_last_line(const std::string &path, double *val) {
+    std::ifstream f(path);
+    if (!f.is_open()) return false;
+    std::string line, last;
+    while (std::getline(f, line))
+        if (!line.empty()) last = line;
+    if (last.empty()) return false;
+    *val = std::stod(last);
+    return true;
+}
+
+// ---- RAII handles -------------------------------------------------------------------------------------------------------
+struct Context {
+    fries_ctx *h = nullptr;
+    explicit Context(int device = 0) { check(fries_ctx_create(device, &h)); }
+    ~Context() { fries_ctx_destroy(h); }
+    Context(const Context &) = delete;
+};
+
+struct Molecule {
+    fries_mol *h = nullptr;
+    unsigned n_orb, n_elec_total, n_frz;
+    Molecule(Context &c, const MolInput &m) : n_orb(m.n_orb), n_elec_total(m.n_elec), n_frz(m.n_frz) {
+        check(fries_mol_create(c.h, m.n_orb, m.n_elec, m.n_frz, m.hcore.data(), m.eris_packed.data(), m.symm.data(), &h));
+    }
+    ~Molecule() { fries_mol_destroy(h); }
+    double diag_matrel(uint64_t det) {  // molecule.cpp:983-1029
+        double out;
+        check(fries_mol_diag(h, &det, 1, &out));
+        return out;
+    }
+    size_t count_doub_ex(uint64_t det) {  // doub_ex_symm molecule.cpp:108-175 (count only)
+        uint64_t off[2];
+        check(fries_mol_doub_ex(h, &det, 1, off, nullptr, 0));
+        return off[1];
+    }
+    size_t count_singex(uint64_t det) {  // molecule.cpp:914-933
+        uint64_t off[2];
+        check(fries_mol_sing_ex(h, &det, 1, off, nullptr, 0));
+        return off[1];
+    }
+};
+
+// DistVec<double> FRIES/vec_utils.hpp:121-953, single rank, resident on the GPU.
+class DistVec {
+  public:
+    fries_vec *h = nullptr;
+    fries_hbpp *hb = nullptr;
+    unsigned n_bits, n_elec, n_vecs;
+    size_t max_size_;
+    DistVec(Context &c, size_t size, unsigned n_bits_, unsigned n_elec_, unsigned n_vecs_, const std::vector<uint32_t> &proc_scr,
+            const std::vector<uint32_t> &vec_scr)
+        : n_bits(n_bits_), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size) {
+        check(fries_vec_create(c.h, size, n_bits, n_elec, n_vecs, proc_scr.data(), vec_scr.data(), 1, 0, &h));
+    }
+    ~DistVec() {
+        if (hb) fries_hbpp_destroy(hb);
+        fries_vec_destroy(h);
+    }
+    DistVec(const DistVec &) = delete;
+    size_t max_size() const { return max_size_; }
+    size_t curr_size() {
+        size_t n;
+        check(fries_vec_curr_size(h, &n));
+        return n;
+    }
+    // add x n + perform_add(origin) with curr_vec_idx = dest (vec_utils.hpp:418-440)
+    void add(const std::vector<uint64_t> &dets, const std::vector<double> &vals, uint8_t ini_flag, unsigned origin = 0,
+             unsigned dest = 0) {
+        std::vector<uint8_t> ini(dets.size(), ini_flag);
+        check(fries_vec_add(h, dets.data(), vals.data(), ini.data(), dets.size(), origin, dest));
+    }
+    double local_norm(unsigned row = 0) {
+        double n;
+        check(fries_vec_local_norm(h, row, &n));
+        return n;
+    }
+    uint64_t tot_sgn_coh() {
+        uint64_t n;
+        check(fries_vec_nonini_occ_add(h, &n));
+        return n;
+    }
+    void download(std::vector<uint64_t> &dets, std::vector<double> &vals) {
+        size_t n = curr_size(), m;
+        dets.resize(n ? n : 1);
+        vals.resize((n ? n : 1) * n_vecs);
+        check(fries_vec_download(h, dets.data(), vals.data(), n ? n : 1, &m));
+        dets.resize(n);
+        vals.resize(n * n_vecs);
+    }
+    void upload(const std::vector<uint64_t> &dets, const std::vector<double> &vals) {
+        check(fries_vec_upload(h, dets.data(), vals.data(), dets.size()));
+    }
+    // DistVec::save vec_utils.hpp:721-745: dets<rank>.dat = curr_size x n_bytes, vals<rank>.dat = n_vecs rows, dense.txt
+    void save(const std::string &path) {
+        std::vector<uint64_t> dets;
+        std::vector<double> vals;
+        download(dets, vals);
+        size_t nb = ceiling(n_bits, 8);
+        std::vector<uint8_t> bytes(dets.size() * nb);
+        for (size_t i = 0; i < dets.size(); i++) key_to_bytes(dets[i], &bytes[i * nb], nb);
+        std::ofstream fd(path + "dets0.dat", std::ios::binary);
+        fd.write((const char *)bytes.data(), bytes.size());
+        std::ofstream fv(path + "vals0.dat", std::ios::binary);
+        fv.write((const char *)vals.data(), vals.size() * sizeof(double));
+        std::ofstream fz(path + "dense.txt");
+        fz << 0 << '\n';
+    }
+    // DistVec::load vec_utils.hpp:761-844 (single rank): re-hash, drop |v| <= 1e-9
+    void load(const std::string &path) {
+        std::ifstream fd(path + "dets0.dat", std::ios::binary);
+        if (!fd.is_open()) throw std::runtime_error("Error: could not open saved binary vector file at " + path + "dets0.dat");
+        std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(fd)), std::istreambuf_iterator<char>());
+        size_t nb = ceiling(n_bits, 8), n = bytes.size() / nb;
+        std::ifstream fv(path + "vals0.dat", std::ios::binary);
+        if (!fv.is_open()) throw std::runtime_error("Error: could not open saved binary vector file at " + path + "vals0.dat");
+        std::vector<double> all(n * n_vecs, 0.0);
+        fv.read((char *)all.data(), all.size() * sizeof(double));
+        std::vector<uint64_t> dets;
+        std::vector<double> rows[8];
+        for (size_t i = 0; i < n; i++) {
+            bool keep = false;
+            for (unsigned r = 0; r < n_vecs; r++) keep = keep || std::fabs(all[r * n + i]) > 1e-9;
+            if (!keep) continue;
+            dets.push_back(key_from_bytes(&bytes[i * nb], nb));
+            for (unsigned r = 0; r < n_vecs; r++) rows[r].push_back(all[r * n + i]);
+        }
+        std::vector<double> vals;
+        for (unsigned r = 0; r < n_vecs; r++) vals.insert(vals.end(), rows[r].begin(), rows[r].end());
+        upload(dets, vals);
+    }
+};
+
+// ---- compress_utils.hpp mirrors on host arrays -----------------------------------------------------------------------------
+// find_preserve compress_utils.cpp:29-105 (srt_idx is scratch in the reference; unused here)
+inline double find_preserve(Context &c, double *values, std::vector<size_t> &, std::vector<bool> &keep_idx, size_t count,
+                            unsigned *n_samp, double *global_norm) {
+    std::vector<uint8_t> keep(count ? count : 1);
+    double loc;
+    check(fries_find_preserve(c.h, values, count, n_samp, global_norm, keep.data(), &loc));
+    for (size_t i = 0; i < count; i++) keep_idx[i] = keep[i];
+    return loc;
+}
+// sys_comp compress_utils.cpp:278-327
+inline void sys_comp(Context &c, double *vec_vals, size_t vec_len, double *loc_norms, unsigned n_samp,
+                     std::vector<bool> &keep_exact, double rand_num) {
+    std::vector<uint8_t> keep(vec_len ? vec_len : 1);
+    for (size_t i = 0; i < vec_len; i++) keep[i] = keep_exact[i];
+    check(fries_sys_comp(c.h, vec_vals, vec_len, loc_norms, 1, 0, n_samp, keep.data(), rand_num));
+    for (size_t i = 0; i < vec_len; i++) keep_exact[i] = keep[i];
+}
+// adjust_shift compress_utils.cpp:684-693 (scalar control logic of the drivers)
+inline void adjust_shift(double *shift, double one_norm, double *last_norm, double target_norm, double damp_factor) {
+    if (*last_norm) {
+        *shift -= damp_factor * std::log(one_norm / *last_norm);
+        *last_norm = one_norm;
+    }
+    if (*last_norm == 0 && one_norm > target_norm) *last_norm = one_norm;
+}
+// round_binomially compress_utils.cpp:19-27 (used by examples/fries_test.cpp, the reference's link smoke test)
+inline int round_binomially(double p, unsigned n, std::mt19937 &mt_obj) {
+    int flr = (int)std::floor(p);
+    double prob = p - flr;
+    int ret = flr * (int)n;
+    for (unsigned i = 0; i < n; i++) ret += (mt_obj() / (1. + UINT32_MAX)) < prob;
+    return ret;
+}
+
+inline unsigned seed_from_clock_or_env() {
+    // the reference seeds mt19937 from the wall clock (frisys_mol.cpp:104-106); FRIES_SEED makes runs reproducible
+    const char *s = std::getenv("FRIES_SEED");
+    if (s) return (unsigned)std::atoll(s);
+    return (unsigned)std::random_device{}();
+}
+
+// H * trial on the device, diagonal shifted by hf_en (frisys_mol.cpp:155-214)
+inline void h_times(Context &c, Molecule &mol, double hf_en, const std::vector<uint64_t> &dets, const std::vector<double> &vals,
+                    const std::vector<uint32_t> &proc_scr, const std::vector<uint32_t> &vec_scr, unsigned n_bits,
+                    unsigned n_elec, std::vector<uint64_t> &out_dets, std::vector<double> &out_vals) {
+    size_t n_ex = (size_t)mol.n_orb * mol.n_orb * n_elec * n_elec;
+    DistVec tmp(c, std::max<size_t>(1 << 16, 2 * dets.size() * n_ex / 8), n_bits, n_elec, 2, proc_scr, vec_scr);
+    check(fries_vec_set_diag_mol(tmp.h, mol.h, hf_en));
+    tmp.add(dets, vals, 1);
+    check(fries_h_apply(tmp.h, mol.h, 0, 1, 0.0, 1.0));
+    std::vector<double> all;
+    tmp.download(out_dets, all);
+    out_vals.assign(all.begin() + out_dets.size(), all.end());
+}
+
+}  // namespace fries

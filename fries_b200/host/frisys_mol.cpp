@@ -1,0 +1,155 @@
+// frisys_mol -- FRI with systematic compression for a molecular Hamiltonian (FRIES_bin/frisys_mol.cpp), same
+// command line, stdout lines and output files; the loop body runs on the GPU (fries_frisys_mol_iterate).
+#include "fries_host.hpp"
+
+using namespace fries;
+
+int main(int argc, char *argv[]) {
+    Args args(argc, argv);
+    std::string fcidump_path = args.str("fcidump_path");
+    double target_norm = args.num("target", 0);
+    std::string dist_str = args.str("distribution");
+    uint32_t max_iter = (uint32_t)args.num("max_iter", 1000000);
+    uint32_t target_nonz = (uint32_t)args.num("vec_nonz");
+    uint32_t matr_samp = (uint32_t)args.num("mat_nonz");
+    std::string result_dir = args.str("result_dir", "./");
+    size_t max_n_dets = (size_t)args.num("max_dets");
+    double init_thresh = args.num("initiator", 0);
+    bool has_load = args.has("load_dir"), has_ini = args.has("ini_vec"), has_trial = args.has("trial_vec");
+    std::string load_dir = args.str("load_dir", ""), ini_path = args.str("ini_vec", ""), trial_path = args.str("trial_vec", "");
+    bool has_det_space = args.has("det_space");
+    double eps = args.num("epsilon");
+    std::string point_group = args.str("point_group", "C1");
+    bool has_shift = args.has("ham_shift");
+    double ham_shift = args.num("ham_shift", 0);
+    int device = (int)args.num("device", 0);
+    args.validate();
+
+    int new_hb;
+    if (dist_str == "HB") new_hb = 0;
+    else if (dist_str == "HB_unnorm") new_hb = 1;
+    else {
+        std::cerr << "\nError parsing command line: \"dist_str\" argument must be either \"NU\" or \"HB_unnorm\"\n\n";
+        return 1;
+    }
+    try {
+        if (has_det_space)
+            throw std::runtime_error("--det_space (semi-stochastic dense subspace) is not available in this build");
+        Context ctx(device);
+        double shift_damping = 0.05;
+        unsigned shift_interval = 10, save_interval = 100;
+        double en_shift = 0;
+
+        MolInput in_data = parse_fcidump(fcidump_path, point_group);
+        unsigned n_elec = in_data.n_elec, n_frz = 0, n_orb = in_data.n_orb;
+        unsigned n_elec_unf = n_elec - n_frz;
+        Molecule mol(ctx, in_data);
+        uint64_t hf_det = gen_hf_bitstring(n_orb, n_elec_unf);
+        double hf_en = has_shift ? ham_shift - in_data.core_en : mol.diag_matrel(hf_det);
+
+        unsigned seed = seed_from_clock_or_env();
+        std::cout << "seed on process 0 is " << seed << std::endl;
+        std::mt19937 mt_obj(seed);
+
+        unsigned spawn_length = matr_samp * 4;
+        std::vector<uint32_t> proc_scrambler(2 * n_orb), vec_scrambler(2 * n_orb);
+        if (has_load) {
+            load_proc_hash(load_dir, proc_scrambler);
+        } else {
+            for (auto &x : proc_scrambler) x = mt_obj();
+            save_proc_hash(result_dir, proc_scrambler);
+        }
+        for (auto &x : vec_scrambler) x = mt_obj();
+
+        DistVec sol_vec(ctx, max_n_dets, 2 * n_orb, n_elec_unf, 2, proc_scrambler, vec_scrambler);
+        check(fries_vec_set_diag_mol(sol_vec.h, mol.h, hf_en));
+
+        // trial vector and H * trial
+        std::vector<uint64_t> trial_dets{hf_det}, htrial_dets;
+        std::vector<double> trial_vals{1.0}, htrial_vals;
+        if (has_trial) load_vec_txt(trial_path, trial_dets, trial_vals);
+        h_times(ctx, mol, hf_en, trial_dets, trial_vals, proc_scrambler, vec_scrambler, 2 * n_orb, n_elec_unf, htrial_dets,
+                htrial_vals);
+
+        size_t n_hf_doub = mol.count_doub_ex(hf_det), n_hf_sing = mol.count_singex(hf_det);
+        double p_doub = (double)n_hf_doub / (n_hf_sing + n_hf_doub);
+
+        {   // sizes of the deterministic subspaces (none)
+            if (!has_load) {
+                std::ofstream dense_f(result_dir + "dense.txt");
+                if (!dense_f.is_open()) throw std::runtime_error("Error opening file containing sizes of deterministic subspaces");
+                dense_f << 0 << ", " << '\n';
+            }
+        }
+        // initial vector
+        if (has_load) {
+            sol_vec.load(load_dir);
+            load_last_line(load_dir + "S.txt", &en_shift);
+        } else if (has_ini) {
+            std::vector<uint64_t> d;
+            std::vector<double> v;
+            load_vec_txt(ini_path, d, v);
+            sol_vec.add(d, v, 1);
+        } else {
+            sol_vec.add({hf_det}, {100.0}, 1);
+        }
+        double glob_norm = sol_vec.local_norm();
+        double last_one_norm = 0;
+        (void)glob_norm;
+
+        auto open_app = [&](const char *name) {
+            std::ofstream f(result_dir + name, std::ofstream::app);
+            if (!f.is_open()) throw std::runtime_error("Could not open file for writing in directory " + result_dir);
+            return f;
+        };
+        std::ofstream num_file = open_app("projnum.txt"), den_file = open_app("projden.txt"), shift_file = open_app("S.txt"),
+                      norm_file = open_app("norm.txt"), nkept_file = open_app("nkept.txt"), ini_file = open_app("nini.txt");
+        {
+            std::ofstream param_f(result_dir + "params.txt");
+            param_f << "FRI calculation\nFCIDUMP path: " << fcidump_path << "\nepsilon (imaginary time step): " << eps
+                    << "\nTarget norm " << target_norm << "\nInitiator threshold: " << init_thresh
+                    << "\nMatrix nonzero: " << matr_samp << "\nVector nonzero: " << target_nonz << "\n";
+            if (has_load) param_f << "Restarting calculation from " << load_dir << "\n";
+            else if (has_ini) param_f << "Initializing calculation from vector files with prefix " << ini_path << '\n';
+            else param_f << "Initializing calculation from HF unit vector\n";
+        }
+        check(fries_frisys_mol_setup(sol_vec.h, mol.h, spawn_length, trial_dets.data(), trial_vals.data(), trial_dets.size(),
+                                     htrial_dets.data(), htrial_vals.data(), htrial_dets.size(), &sol_vec.hb));
+        std::cout << "Elements in dense H: " << 0 << "\n";
+
+        for (unsigned iterat = 0; iterat < max_iter; iterat++) {
+            size_t n_ini = 0;
+            // RNG consumption order of the reference: 5 uniforms inside apply_HBPP_sys, then one for sys_comp
+            double u[6];
+            for (int k = 0; k < 6; k++) u[k] = mt_obj() / (1. + UINT32_MAX);
+            fries_frisys_params p{eps, init_thresh, p_doub, new_hb, matr_samp, target_nonz, en_shift};
+            fries_iter_stats st;
+            check(fries_frisys_mol_iterate(sol_vec.h, mol.h, sol_vec.hb, &p, u, &st));
+            nkept_file << st.n_kept << '\n';
+            if ((iterat + 1) % shift_interval == 0) {
+                // NOTE the shift used inside iteration k+1 is the one adjusted after iteration k, as in the reference
+                adjust_shift(&en_shift, st.glob_norm, &last_one_norm, target_norm, shift_damping / shift_interval / eps);
+                shift_file << en_shift << "\n";
+                norm_file << st.glob_norm << "\n";
+            }
+            num_file << st.numer << '\n';
+            den_file << st.denom << '\n';
+            std::cout << iterat << ", en est: " << st.numer / st.denom << ", shift: " << en_shift << ", norm: " << st.glob_norm
+                      << '\n';
+            ini_file << n_ini << '\n';
+            if ((iterat + 1) % save_interval == 0) {
+                sol_vec.save(result_dir);
+                uint64_t tot_add = sol_vec.tot_sgn_coh();
+                num_file.flush();
+                den_file.flush();
+                shift_file.flush();
+                nkept_file.flush();
+                std::cout << "Total additions to nonzero: " << tot_add << "\n";
+            }
+        }
+        sol_vec.save(result_dir);
+    } catch (std::exception &ex) {
+        std::cerr << "\nException : " << ex.what() << "\n\n";
+    }
+    return 0;
+}

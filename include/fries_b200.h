@@ -211,9 +211,15 @@ int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, con
 typedef struct {
     double eps;
     unsigned target_nonz;
-    double en_shift;
+    double en_shift;        /* in: current shift; out: shift after this iteration's adjust_shift */
+    /* adjust_shift (compress_utils.cpp:684-693) happens between find_preserve and sys_comp of the SAME iteration
+     * (frifull_mol.cpp:270-276) and feeds h_op_diag of that iteration, so it is done inside the call */
+    int adjust_shift;       /* nonzero on iterations with (iterat + 1) % shift_interval == 0 */
+    double damp_factor;     /* shift_damping / shift_interval / eps */
+    double target_norm;     /* --target */
+    double last_one_norm;   /* in/out */
 } fries_frifull_params;
-int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frifull_params *p,
+int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, fries_frifull_params *p,
                               double uniform, fries_iter_stats *stats);
 
 /* ---- multi-GPU (one process per GPU; owner = hash_fxn(occ; proc_scrambler) % n_ranks, vec_utils.hpp:373-379) ----

@@ -1,0 +1,90 @@
+"""GPU tier: the C++ drivers (fries_b200/host/bin) against the reference's own drivers (oracle/_ref) on the same
+input files: same command line, same output files; deterministic runs agree to the printed precision, stochastic
+runs agree within combined error bars and with the exact ground state."""
+import os
+
+import numpy as np
+import pytest
+
+import oraclelib
+from driver_utils import OURS, REF, exact_ground_state, read_col, run, write_fcidump, write_hf_dir
+from fries_b200.synth import SynthMol
+
+pytestmark = pytest.mark.gpu
+TINY = ((8, 6, 0, [0, 0, 1, 2, 3, 0, 1, 2]), 4)
+have_ref = os.path.exists(os.path.join(REF, "frisys_mol"))
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    sm = SynthMol(*TINY)
+    om = oraclelib.OracleMol(sm)
+    e_corr, e_hf, n = exact_ground_state(sm, om)
+    return sm, om, e_corr, e_hf, n
+
+
+def blocked_ratio(num, den, burn, block=50):
+    num, den = num[burn:], den[burn:]
+    nb = len(num) // block
+    r = np.array([num[i * block:(i + 1) * block].sum() / den[i * block:(i + 1) * block].sum() for i in range(nb)])
+    return num.sum() / den.sum(), r.std(ddof=1) / np.sqrt(nb)
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref drivers not built")
+def test_frifull_mol_matches_reference_when_compression_is_identity(tiny, tmp_path):
+    sm, om, e_corr, e_hf, n = tiny
+    d = str(tmp_path / "hf") + "/"
+    write_hf_dir(d, sm, 0.05, float(e_hf))
+    outs = {}
+    for name, exe in (("ours", os.path.join(OURS, "frifull_mol")), ("ref", os.path.join(REF, "frifull_mol"))):
+        rd = str(tmp_path / name) + "/"
+        os.makedirs(rd)
+        r = run(exe, ["--hf_path", d, "--vec_nonz", 4 * n, "--max_dets", 8 * n, "--max_iter", 150, "--target", 110,
+                      "--result_dir", rd])
+        assert "Exception" not in r.stderr, r.stderr[-500:]
+        outs[name] = {f: read_col(rd + f) for f in ("projnum.txt", "projden.txt", "S.txt", "norm.txt")}
+        assert os.path.exists(rd + "dets0.dat") and os.path.exists(rd + "vals0.dat") and os.path.exists(rd + "hash.dat")
+    for f in ("projnum.txt", "projden.txt", "S.txt", "norm.txt"):
+        a, b = outs["ours"][f], outs["ref"][f]
+        assert a.shape == b.shape, f
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-6), (f, a[:5], b[:5])  # files carry 6 significant digits
+    # deterministic power iteration: the projected energy approaches the exact correlation energy from above
+    en = outs["ours"]["projnum.txt"][-1] / outs["ours"]["projden.txt"][-1]
+    assert e_corr - 1e-9 < en < 0
+    assert len(outs["ours"]["S.txt"]) == 15 and np.any(outs["ours"]["S.txt"] != 0)  # the shift engaged
+
+
+def test_frisys_mol_driver_energy_and_files(tiny, tmp_path):
+    sm, om, e_corr, e_hf, n = tiny
+    fd = str(tmp_path / "FCIDUMP")
+    write_fcidump(fd, sm, "D2")
+    res = {}
+    exes = [("ours", os.path.join(OURS, "frisys_mol"))]
+    if have_ref:
+        exes.append(("ref", os.path.join(REF, "frisys_mol")))
+    n_it = 6000
+    for name, exe in exes:
+        rd = str(tmp_path / name) + "/"
+        os.makedirs(rd)
+        r = run(exe, ["--fcidump_path", fd, "--distribution", "HB_unnorm", "--vec_nonz", 150, "--mat_nonz", 300, "--max_dets",
+                      20000, "--epsilon", 0.05, "--target", 500, "--max_iter", n_it, "--result_dir", rd, "--point_group",
+                      "D2"], seed=3 if name == "ours" else 4)
+        assert "Exception" not in r.stderr, r.stderr[-500:]
+        files = sorted(os.listdir(rd))
+        for f in ("S.txt", "dense.txt", "dets0.dat", "hash.dat", "nini.txt", "nkept.txt", "norm.txt", "params.txt",
+                  "projden.txt", "projnum.txt", "vals0.dat"):
+            assert f in files, (name, f, files)
+        num, den = read_col(rd + "projnum.txt"), read_col(rd + "projden.txt")
+        assert len(num) == n_it and len(read_col(rd + "S.txt")) == n_it // 10 and len(read_col(rd + "nkept.txt")) == n_it
+        assert os.path.getsize(rd + "hash.dat") == 4 * 2 * sm.n_orb
+        nd = os.path.getsize(rd + "dets0.dat") // ((2 * sm.n_orb + 7) // 8)
+        assert os.path.getsize(rd + "vals0.dat") == nd * 2 * 8
+        res[name] = blocked_ratio(num, den, burn=1000)
+        assert r.stdout.splitlines()[0].startswith("seed on process 0 is")
+        assert ", en est: " in r.stdout.splitlines()[-1] and ", shift: " in r.stdout.splitlines()[-1]
+    e, s = res["ours"]
+    print("exact", e_corr, "ours", res["ours"], "ref", res.get("ref"))
+    assert abs(e - e_corr) < 5 * s + 2e-3 * abs(e_corr) + 2e-4, (e, s, e_corr)
+    if "ref" in res:
+        er, sr = res["ref"]
+        assert abs(e - er) < 5 * (s + sr) + 2e-4, (e, s, er, sr)
