@@ -81,7 +81,9 @@ def test_frisys_mol_driver_energy_and_files(tiny, tmp_path):
         assert os.path.getsize(rd + "vals0.dat") == nd * 2 * 8
         res[name] = blocked_ratio(num, den, burn=1000)
         assert r.stdout.splitlines()[0].startswith("seed on process 0 is")
-        assert ", en est: " in r.stdout.splitlines()[-1] and ", shift: " in r.stdout.splitlines()[-1]
+        it_lines = [ln for ln in r.stdout.splitlines() if ", en est: " in ln]
+        assert len(it_lines) == n_it and ", shift: " in it_lines[-1] and ", norm: " in it_lines[-1]
+        assert r.stdout.splitlines()[-1].startswith("Total additions to nonzero:")
     e, s = res["ours"]
     print("exact", e_corr, "ours", res["ours"], "ref", res.get("ref"))
     assert abs(e - e_corr) < 5 * s + 2e-3 * abs(e_corr) + 2e-4, (e, s, e_corr)
