@@ -32,6 +32,12 @@ class FrifullParams(C.Structure):
                 ("damp_factor", C.c_double), ("target_norm", C.c_double), ("last_one_norm", C.c_double)]
 
 
+class FrisysHhParams(C.Structure):
+    _fields_ = [("eps", C.c_double), ("init_thresh", C.c_double), ("hub_u", C.c_double), ("ph_freq", C.c_double),
+                ("elec_ph", C.c_double), ("hf_en", C.c_double), ("target_nonz", C.c_uint), ("en_shift", C.c_double),
+                ("ref_key", C.c_uint64)]
+
+
 class IterStats(C.Structure):
     _fields_ = [("glob_norm", C.c_double), ("numer", C.c_double), ("denom", C.c_double), ("n_kept", C.c_uint64),
                 ("n_matrix_samples", C.c_uint64), ("n_spawned", C.c_uint64), ("curr_size", C.c_uint64)]
@@ -84,6 +90,11 @@ def _load():
         "fries_hbpp_set_route": (i, [vp, vp, vp, vp, vp, sz]),
         "fries_frisys_mol_spawn": (i, [vp, vp, vp, P(FrisysParams), vp]),
         "fries_frisys_mol_finish": (i, [vp, vp, vp, P(FrisysParams), vp, vp, P(IterStats)]),
+        "fries_vec_create_hh": (i, [vp, sz, u, u, u, u, vp, vp, i, i, P(vp)]),
+        "fries_vec_set_min_del_idx": (i, [vp, sz]),
+        "fries_hh_batch": (i, [vp, i, vp, vp, sz, u, u, u, C.c_uint64, d, vp]),
+        "fries_frisys_hh_setup": (i, [vp, sz, P(vp)]),
+        "fries_frisys_hh_iterate": (i, [vp, vp, P(FrisysHhParams), vp, P(IterStats)]),
         "fries_vec_create": (i, [vp, sz, u, u, u, vp, vp, i, i, P(vp)]),
         "fries_vec_destroy": (i, [vp]),
         "fries_vec_add": (i, [vp, vp, vp, vp, sz, u, u]),

@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._capi import (FrifullParams, FrisysParams, IterStats, MAX_SUB, arr, check, lib, ptr)
+from ._capi import (FrifullParams, FrisysHhParams, FrisysParams, IterStats, MAX_SUB, arr, check, lib, ptr)
 
 
 class Context:
@@ -201,11 +201,16 @@ class Mol:
 class Vec:
     """DistVec<double> (FRIES/vec_utils.hpp:121-953) resident on one GPU."""
 
-    def __init__(self, ctx, capacity, n_bits, n_elec, n_vecs, proc_scrambler, vec_scrambler, n_ranks=1, rank=0):
+    def __init__(self, ctx, capacity, n_bits, n_elec, n_vecs, proc_scrambler, vec_scrambler, n_ranks=1, rank=0, hh=None):
+        """hh = (n_sites, ph_bits) makes a HubHolVec (FRIES/hh_vec.hpp); n_bits is then 2 n_sites + n_sites ph_bits"""
         self.ctx, self.capacity, self.n_bits, self.n_elec, self.n_vecs = ctx, capacity, n_bits, n_elec, n_vecs
         ps, vs = arr(proc_scrambler, np.uint32), arr(vec_scrambler, np.uint32)
         h = C.c_void_p()
-        check(lib.fries_vec_create(ctx.h, capacity, n_bits, n_elec, n_vecs, ptr(ps), ptr(vs), n_ranks, rank, C.byref(h)))
+        if hh is None:
+            check(lib.fries_vec_create(ctx.h, capacity, n_bits, n_elec, n_vecs, ptr(ps), ptr(vs), n_ranks, rank, C.byref(h)))
+        else:
+            check(lib.fries_vec_create_hh(ctx.h, capacity, hh[0], hh[1], n_elec, n_vecs, ptr(ps), ptr(vs), n_ranks, rank,
+                                          C.byref(h)))
         self.h = h
         self.hb = None
 
@@ -298,6 +303,17 @@ class Vec:
         check(lib.fries_frisys_mol_iterate(self.h, self.mol.h, self.hb, C.byref(params), ptr(u), C.byref(st)))
         return st
 
+    def frisys_hh_setup(self, spawn_cap):
+        h = C.c_void_p()
+        check(lib.fries_frisys_hh_setup(self.h, spawn_cap, C.byref(h)))
+        self.hb = h
+
+    def frisys_hh_iterate(self, params: FrisysHhParams, uniforms3) -> IterStats:
+        u = arr(uniforms3, np.float64)
+        st = IterStats()
+        check(lib.fries_frisys_hh_iterate(self.h, self.hb, C.byref(params), ptr(u), C.byref(st)))
+        return st
+
     def states(self):
         """CompState records of the last iteration: dict name -> [8][...]"""
         out = np.zeros((8, 8))
@@ -308,3 +324,12 @@ class Vec:
         st = IterStats()
         check(lib.fries_frifull_mol_iterate(self.h, self.mol.h, self.hb, C.byref(params), uniform, C.byref(st)))
         return st
+
+
+def hh_batch(ctx, what, keys, vals, n_sites, n_elec, ph_bits, ref_key=0, g_over_t=0.0):
+    """what 0: hub_diag; 1: neighbour masks [n][2]; 2: calc_ref_ovlp terms (hub_holstein.cpp/.hpp, hh_vec.hpp)"""
+    k = arr(keys, np.uint64)
+    v = None if vals is None else arr(vals, np.float64)
+    out = np.zeros(k.size * (2 if what == 1 else 1))
+    check(lib.fries_hh_batch(ctx.h, what, ptr(k), ptr(v), k.size, n_sites, n_elec, ph_bits, int(ref_key), g_over_t, ptr(out)))
+    return out.reshape(-1, 2) if what == 1 else out

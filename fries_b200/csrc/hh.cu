@@ -1,0 +1,404 @@
+// a19: Hubbard-Holstein pieces and the frisys_hh loop body (FRIES_bin/frisys_hh.cpp:186-368).
+// Keys: bits [0, n) spin-up sites, [n, 2n) spin-down sites, then n phonon fields of ph_bits bits (hh_vec.hpp).
+#include "hbpp.cuh"
+#include "vec.cuh"
+
+int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, const unsigned long long *d_n,
+                               unsigned n_samp, uint8_t *d_keep, CompState *d_st, double *pd, unsigned long long *pc,
+                               int grid, const fries_comm *comm);
+int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, const unsigned long long *d_n, uint8_t *d_keep,
+                          const double *d_in, double lbound0, double glob, long long n_samp, double rn, CompState *d_out,
+                          double *pd, unsigned long long *pc, int grid, const fries_comm *comm);
+int fries_vec_compact_flags_dev(fries_vec *vec, const uint8_t *d_flags);
+
+struct HhDims {
+    unsigned n_sites, n_elec, ph_bits;
+};
+
+// hub_diag hub_holstein.cpp:101-136: number of doubly occupied sites
+__host__ __device__ __forceinline__ unsigned hh_hub_diag(uint64_t key, unsigned n) {
+    uint64_t m = (1ull << n) - 1;
+    return fr_popc((key & m) & ((key >> n) & m));
+}
+// HubHolVec::find_neighbors_1D hh_vec.hpp:139-175 as bit masks over the 2n electron bits: `right` = occupied
+// orbitals whose neighbour at +1 is empty (first list, hop to orb + 1), `left` = those whose neighbour at -1 is
+// empty (second list, hop to orb - 1); open boundary conditions, no hop between the spin blocks
+__host__ __device__ __forceinline__ void hh_neighbors(uint64_t key, unsigned n, uint64_t &plus, uint64_t &minus) {
+    uint64_t E = (1ull << (2 * n)) - 1, occ = key & E;
+    plus = occ & ~(occ >> 1) & ~(1ull << (n - 1)) & ~(1ull << (2 * n - 1));
+    minus = occ & ((~occ << 1) & E) & ~(1ull << n);
+}
+__host__ __device__ __forceinline__ unsigned hh_nth_bit(uint64_t mask, unsigned k) {
+    for (unsigned i = 0; i < k; i++) mask &= mask - 1;
+    return fr_ctz(mask);
+}
+// HubHolVec::decode_phonons hh_vec.hpp:185-197
+__host__ __device__ __forceinline__ unsigned hh_phonon(uint64_t key, const HhDims &d, unsigned site) {
+    return (unsigned)((key >> (2 * d.n_sites + site * d.ph_bits)) & ((1u << d.ph_bits) - 1));
+}
+__host__ __device__ __forceinline__ unsigned hh_total_ph(uint64_t key, const HhDims &d) {
+    unsigned s = 0;
+    for (unsigned i = 0; i < d.n_sites; i++) s += hh_phonon(key, d, i);
+    return s;
+}
+// calc_ref_ovlp hub_holstein.hpp:93-182 for ONE basis state: its contribution to the sum (the reference walks the
+// electron bytes; the byte-wise neighbour tests, including the open-boundary byte rule, are kept as written)
+__host__ __device__ inline double hh_ref_ovlp_term(uint64_t curr, double val, uint64_t ref, const HhDims &d, double g_over_t) {
+    const unsigned n = d.n_sites;
+    uint64_t E = (1ull << (2 * n)) - 1;
+    if ((curr & E) == (ref & E)) {
+        unsigned sites_found = 0, site_elecs = 0;
+        for (unsigned site = 0; site < n && sites_found < 2; site++) {
+            unsigned ph = hh_phonon(curr, d, site);
+            unsigned n_occ = fr_read_bit(ref, site) + fr_read_bit(ref, site + n);
+            if (ph > 1 || (ph == 1 && n_occ == 0)) {
+                site_elecs = 0;
+                break;
+            } else if (ph == 1) {
+                site_elecs = n_occ;
+                sites_found++;
+            }
+        }
+        if (sites_found == 2) site_elecs = 0;
+        return -(val * g_over_t * site_elecs);
+    }
+    if (hh_total_ph(curr, d) != 0) return 0.0;
+    unsigned n_hop = 0, n_common = 0;
+    const unsigned n_bytes = (2 * n + 7) / 8;
+    for (unsigned b = 0; b < n_bytes && n_hop <= 1; b++) {
+        uint8_t c = (uint8_t)(curr >> (8 * b)), r = (uint8_t)(ref >> (8 * b));
+        uint8_t c_prev = b ? (uint8_t)(curr >> (8 * (b - 1))) : 0, r_prev = b ? (uint8_t)(ref >> (8 * (b - 1))) : 0;
+        uint8_t c_next = (uint8_t)(curr >> (8 * (b + 1))), r_next = (uint8_t)(ref >> (8 * (b + 1)));
+        uint8_t not_occ = c & ~r;
+        uint8_t ref_left = c & (r >> 1);
+        uint8_t not_occ_left = (uint8_t)(~c) >> 1;
+        uint8_t ref_right = c & (uint8_t)(r << 1);
+        uint8_t not_occ_right = (uint8_t)((uint8_t)(~c) << 1);
+        if (b > 0) {
+            ref_right |= c & ((r_prev >> 7) & 1);
+            not_occ_right |= ((uint8_t)(~c_prev) >> 7) & 1;
+        }
+        if (b < n_bytes - 1) {
+            ref_left |= c & (uint8_t)(r_next << 7);
+            not_occ_left |= (uint8_t)((uint8_t)(~c_next) << 7);
+        }
+        if (b == (n + 7) / 8) ref_left &= ~(1 << ((n - 1) % 8));
+        uint8_t mask = not_occ & ((ref_left & not_occ_left) | (ref_right & not_occ_right));
+        if (b == n_bytes - 1 && (2 * n) % 8 != 0) mask &= (1 << ((2 * n) % 8)) - 1;
+        n_hop += fr_popc(mask);
+        if (n_hop > 1) break;
+        n_common += fr_popc((uint64_t)(r & c));
+    }
+    return (n_hop == 1 && n_common == d.n_elec - 1) ? val : 0.0;
+}
+
+// ---- providers for the two comp_sub stages (frisys_hh.cpp:187-226) -----------------------------------------------
+struct HhStage1 {
+    const double *vals;
+    const unsigned long long *n_in;
+    unsigned long long cap;
+    double hub_t, elec_ph;
+    __device__ size_t count() const {
+        unsigned long long n = *n_in;
+        return n < cap ? (size_t)n : (size_t)cap;
+    }
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns) const {
+        v = fabs(vals[i]);
+        nd = v > 0 ? 0u : 1u;
+        ns = 2;
+    }
+    __device__ void row(size_t, double *w) const {
+        w[0] = hub_t;  // NOT normalised in the reference (:193-194)
+        w[1] = elec_ph;
+    }
+};
+struct HhStage2 {
+    const uint64_t *keys;
+    const unsigned long long *n_in;
+    unsigned long long cap;
+    const double *pv;
+    const uint32_t *pw, *ps;
+    uint32_t *det, *ph_ex;
+    HhDims d;
+    double hub_t, elec_ph;
+    __device__ size_t count() const {
+        unsigned long long n = *n_in;
+        return n < cap ? (size_t)n : (size_t)cap;
+    }
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns) const {
+        uint32_t di = pw[i], ex = ps[i];
+        det[i] = di;
+        ph_ex[i] = ex;
+        if (ex) {
+            nd = 2 * d.n_elec;
+        } else {
+            uint64_t plus, minus;
+            hh_neighbors(keys[di], d.n_sites, plus, minus);
+            nd = fr_popc(plus) + fr_popc(minus);
+        }
+        v = pv[i] * nd;  // comp_vec2[samp_idx] *= ndiv (:217)
+        ns = 2;
+    }
+    __device__ void row(size_t, double *w) const {
+        w[0] = hub_t;  // only reached with ndiv == 0, i.e. value 0: the reference reads its stale row
+        w[1] = elec_ph;
+    }
+};
+
+__global__ void __launch_bounds__(FR_COMP_BLOCK) hh_stage1_kernel(HhStage1 prov, CompSubBufs bufs, unsigned n_samp, double rn) {
+    comp_sub_engine(prov, bufs, n_samp, rn);
+}
+__global__ void __launch_bounds__(FR_COMP_BLOCK) hh_stage2_kernel(HhStage2 prov, CompSubBufs bufs, unsigned n_samp, double rn) {
+    comp_sub_engine(prov, bufs, n_samp, rn);
+}
+
+// spawn loop body frisys_hh.cpp:246-296
+__global__ void hh_spawn_kernel(VecView v, HhDims d, const unsigned long long *n_ptr, unsigned long long cap,
+                                const double *pv, const uint32_t *pw, const uint32_t *ps, const uint32_t *det,
+                                const uint32_t *ph_ex, double eps, double init_thresh, uint64_t *out_keys, double *out_vals,
+                                CompState *st) {
+    unsigned long long n = *n_ptr;
+    if (n > cap) n = cap;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long ok = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t prev = pw[i], exc = ps[i];
+        uint32_t di = det[prev];
+        double cv = v.vals[di];
+        uint64_t key = v.keys[di], nk = key;
+        double el = pv[i] * -eps;
+        if (cv < 0) el *= -1;
+        if (ph_ex[prev]) {
+            uint8_t occ[FRIES_MAX_ELEC + 1];
+            fr_occ_list(key & ((1ull << (2 * d.n_sites)) - 1), occ);
+            unsigned site = occ[exc % d.n_elec] % d.n_sites;
+            unsigned ph = hh_phonon(key, d, site);
+            unsigned shift = 2 * d.n_sites + site * d.ph_bits;
+            if (exc < d.n_elec && ph > 0) {
+                nk = key - (1ull << shift);  // det_from_ph(..., -1)
+                el *= sqrt((double)ph);
+            } else if (exc >= d.n_elec && ph + 1 < (1u << d.ph_bits)) {
+                nk = key + (1ull << shift);  // det_from_ph(..., +1)
+                el *= sqrt((double)(ph + 1));
+            } else {
+                el = 0;
+            }
+        } else {
+            uint64_t plus, minus;
+            hh_neighbors(key, d.n_sites, plus, minus);
+            unsigned n_plus = fr_popc(plus), orig, dest;
+            if (exc < n_plus) {
+                orig = hh_nth_bit(plus, exc);
+                dest = orig + 1;
+            } else {
+                orig = hh_nth_bit(minus, exc - n_plus);
+                dest = orig - 1;
+            }
+            nk = (key & ~(1ull << orig)) | (1ull << dest);
+            el *= -1;  // hub_t
+        }
+        uint64_t outk = FRIES_EMPTY_KEY;
+        if (fabs(el) > 1e-9) {
+            outk = nk | (fabs(cv) >= init_thresh ? FRIES_INI_FLAG : 0ull);
+            ok++;
+        }
+        out_keys[i] = outk;
+        out_vals[i] = el;
+    }
+    ok = warp_sum_u64(ok);
+    if ((threadIdx.x & 31) == 0 && ok) atomicAdd(&st->n_out, ok);
+}
+
+// diagonal step + add_vecs(0, 1) + zero row 1 (frisys_hh.cpp:308-318; row 1 is zeroed at :229-230)
+__global__ void hh_diag_kernel(VecView v, HhDims d, double eps, double hub_u, double ph_freq, double hf_en, double shift) {
+    unsigned long long n64 = v.cnt->n;
+    size_t n = n64 < v.cap ? (size_t)n64 : v.cap;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    double *v0 = v.vals, *v1 = v.vals + v.cap;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a = v0[i], b = v1[i];
+        if (a != 0) {
+            uint64_t key = v.keys[i];
+            double diag_el = hh_hub_diag(key, d.n_sites);
+            double phonon_diag = hh_total_ph(key, d) * ph_freq;
+            a *= 1 - eps * (diag_el * hub_u + phonon_diag - hf_en - shift);
+        }
+        v0[i] = a + b;
+        if (b != 0) v1[i] = 0;
+    }
+}
+
+// numer/denom (frisys_hh.cpp:333-345): one CTA, fixed-order sum
+__global__ void __launch_bounds__(1024)
+hh_energy_kernel(VecView v, HhDims d, uint64_t ref, double g_over_t, double hub_t, double hub_u, double hf_en, double *out2) {
+    __shared__ double sh[34];
+    unsigned long long n64 = v.cnt->n;
+    size_t n = n64 < v.cap ? (size_t)n64 : v.cap;
+    double acc = 0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) acc += hh_ref_ovlp_term(v.keys[i], v.vals[i], ref, d, g_over_t);
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) {
+        // the reference reads position 0 (the Neel state never leaves it); here it is found by key
+        double ref_el = 0;
+        for (size_t i = 0; i < n && i < 1; i++)
+            if (v.keys[i] == ref) ref_el = v.vals[i];
+        double numer = (hh_hub_diag(ref, d.n_sites) * hub_u - hf_en) * ref_el + acc * -hub_t;
+        out2[0] = numer;
+        out2[1] = ref_el;
+    }
+}
+
+__global__ void hh_batch_kernel(int what, const uint64_t *keys, const double *vals, size_t n, HhDims d, uint64_t ref,
+                                double g_over_t, double *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (what == 0) out[i] = hh_hub_diag(keys[i], d.n_sites);
+    else if (what == 1) {
+        uint64_t p, m;
+        hh_neighbors(keys[i], d.n_sites, p, m);
+        out[2 * i] = (double)p;
+        out[2 * i + 1] = (double)m;
+    } else out[i] = hh_ref_ovlp_term(keys[i], vals[i], ref, d, g_over_t);
+}
+
+// ---- C-ABI -----------------------------------------------------------------------------------------------------------
+// what 0: hub_diag (hub_holstein.cpp:101-136); 1: neighbour masks (hh_vec.hpp:139-175) -> out[2n] (hop+1, hop-1);
+// 2: per-state terms of calc_ref_ovlp (hub_holstein.hpp:93-182)
+extern "C" int fries_hh_batch(fries_ctx *c, int what, const uint64_t *h_keys, const double *h_vals, size_t n, unsigned n_sites,
+                              unsigned n_elec, unsigned ph_bits, uint64_t ref_key, double g_over_t, double *h_out) {
+    FRIES_REQUIRE(c && h_out && (n == 0 || h_keys) && what >= 0 && what <= 2, "fries_hh_batch: bad argument");
+    FRIES_REQUIRE(what != 2 || h_vals, "fries_hh_batch: values needed");
+    if (n == 0) return FRIES_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    DevBuf<uint64_t> k;
+    DevBuf<double> v, o;
+    size_t no = what == 1 ? 2 * n : n;
+    FRIES_TRY(k.alloc(n));
+    FRIES_TRY(v.alloc(n));
+    FRIES_TRY(o.alloc(no));
+    CUDA_TRY(cudaMemcpyAsync(k.p, h_keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (h_vals) CUDA_TRY(cudaMemcpyAsync(v.p, h_vals, n * 8, cudaMemcpyHostToDevice, c->stream));
+    HhDims d{n_sites, n_elec, ph_bits};
+    hh_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(what, k.p, v.p, n, d, ref_key, g_over_t, o.p);
+    c->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_out, o.p, no * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FRIES_OK;
+}
+
+extern "C" int fries_frisys_hh_setup(fries_vec *vec, size_t spawn_cap, fries_hbpp **out) {
+    FRIES_REQUIRE(vec && out && vec->hh_sites, "fries_frisys_hh_setup: needs a vector made by fries_vec_create_hh");
+    FRIES_REQUIRE(vec->n_vecs >= 2, "fries_frisys_hh_setup: the vector needs two value rows");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    fries_hbpp *hb = nullptr;
+    FRIES_TRY(fries_hbpp_alloc(c, spawn_cap, &hb));
+    int rc = hb->spawn_keys.alloc(spawn_cap);
+    if (rc == FRIES_OK) rc = hb->spawn_vals.alloc(spawn_cap);
+    if (rc == FRIES_OK) rc = hb->keep_flags.alloc(vec->cap);
+    if (rc != FRIES_OK) {
+        fries_hbpp_destroy(hb);
+        return rc;
+    }
+    CUDA_TRY(cudaMemsetAsync(hb->keep_flags.p, 0, vec->cap, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    vec->min_del_idx = 1;  // the Neel state at position 0 is never deleted (frisys_hh.cpp:353)
+    *out = hb;
+    return FRIES_OK;
+}
+
+__global__ void hh_stats_kernel(const CompState *st, const VecCounters *cnt, const double *scal, double *out) {
+    out[0] = st[6].glob_norm;
+    out[1] = scal[4];
+    out[2] = scal[5];
+    out[3] = (double)st[6].n_kept;
+    out[4] = (double)st[5].n_out;
+    out[5] = (double)cnt->n;
+    out[6] = (double)(st[0].overflow + st[1].overflow);
+    out[7] = (double)cnt->overflow;
+}
+__global__ void hh_state_to_r4(const CompState *st, double *r4) {
+    r4[0] = st->loc_norm;
+    r4[1] = st->glob_norm;
+    r4[2] = (double)st->n_samp_left;
+    r4[3] = (double)st->n_kept;
+}
+
+extern "C" int fries_frisys_hh_iterate(fries_vec *vec, fries_hbpp *hb, const fries_frisys_hh_params *p,
+                                       const double *u3, fries_iter_stats *stats) {
+    FRIES_REQUIRE(vec && hb && p && u3 && vec->hh_sites, "fries_frisys_hh_iterate: bad argument");
+    FRIES_REQUIRE(vec->n_ranks == 1, "fries_frisys_hh_iterate: single-rank entry point");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    VecView v = vec->view();
+    HhDims d{vec->hh_sites, vec->n_elec, vec->hh_ph_bits};
+    CUDA_TRY(cudaMemsetAsync(hb->st.p, 0, 8 * sizeof(CompState), c->stream));
+    const double hub_t = 1;
+    int grid = c->coop_grid((const void *)hh_stage2_kernel, FR_COMP_BLOCK, 0);
+    int g1 = c->coop_grid((const void *)hh_stage1_kernel, FR_COMP_BLOCK, 0);
+    if (g1 < grid) grid = g1;
+    auto bufs_for = [&](int o, int s) {
+        return CompSubBufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
+                           hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
+                           hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(nullptr)};
+    };
+    unsigned n_samp = p->target_nonz;
+    {   // stage 1: hop vs phonon (:187-206)
+        HhStage1 pr{v.vals, &vec->cnt.p->n, (unsigned long long)hb->cap, hub_t, p->elec_ph};
+        CompSubBufs b = bufs_for(0, 0);
+        double rn = u3[0];
+        void *args[] = {(void *)&pr, (void *)&b, (void *)&n_samp, (void *)&rn};
+        ProfScope ps(c, "hh_stage1");
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)hh_stage1_kernel, dim3(grid), dim3(FR_COMP_BLOCK), args, 0, c->stream));
+        c->launch_count++;
+    }
+    {   // stage 2: which neighbour / which phonon move (:208-226)
+        HhStage2 pr{v.keys, &hb->st.p[0].n_out, (unsigned long long)hb->cap, hb->oval[0].p, hb->owidx[0].p, hb->osub[0].p,
+                    hb->det[0].p, hb->path[0].p, d, hub_t, p->elec_ph};
+        CompSubBufs b = bufs_for(1, 1);
+        double rn = u3[1];
+        void *args[] = {(void *)&pr, (void *)&b, (void *)&n_samp, (void *)&rn};
+        ProfScope ps(c, "hh_stage2");
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)hh_stage2_kernel, dim3(grid), dim3(FR_COMP_BLOCK), args, 0, c->stream));
+        c->launch_count++;
+    }
+    hh_spawn_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(v, d, &hb->st.p[1].n_out, (unsigned long long)hb->cap,
+                                                             hb->oval[1].p, hb->owidx[1].p, hb->osub[1].p, hb->det[0].p,
+                                                             hb->path[0].p, p->eps, p->init_thresh, hb->spawn_keys.p,
+                                                             hb->spawn_vals.p, hb->st.p + 5);
+    c->launch_count++;
+    FRIES_TRY(fries_vec_merge_dev(vec, hb->spawn_keys.p, hb->spawn_vals.p, hb->cap, &hb->st.p[1].n_out, 0, 1));
+    hh_diag_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(v, d, p->eps, p->hub_u, p->ph_freq, p->hf_en, p->en_shift);
+    c->launch_count++;
+    FRIES_TRY(fries_find_preserve_launch(c, v.vals, vec->cap, &vec->cnt.p->n, p->target_nonz, hb->keep_flags.p, hb->st.p + 6,
+                                         hb->part_d.p, hb->part_c.p, 0, nullptr));
+    hh_state_to_r4<<<1, 1, 0, c->stream>>>(hb->st.p + 6, hb->scal.p);
+    hh_energy_kernel<<<1, 1024, 0, c->stream>>>(v, d, p->ref_key, p->elec_ph / hub_t, hub_t, p->hub_u, p->hf_en, hb->scal.p + 4);
+    c->launch_count += 2;
+    FRIES_TRY(fries_sys_comp_launch(c, v.vals, vec->cap, &vec->cnt.p->n, hb->keep_flags.p, hb->scal.p, 0.0, 0.0, -1LL, u3[2],
+                                    hb->st.p + 7, hb->part_d.p, hb->part_c.p, 0, nullptr));
+    FRIES_TRY(fries_vec_compact_flags_dev(vec, hb->keep_flags.p));
+    hh_stats_kernel<<<1, 1, 0, c->stream>>>(hb->st.p, vec->cnt.p, hb->scal.p, hb->scal.p + 8);
+    c->launch_count++;
+    CUDA_TRY(cudaMemcpyAsync(c->h_pinned, hb->scal.p + 8, 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const double *h = c->h_pinned;
+    if (stats) {
+        stats->glob_norm = h[0];
+        stats->numer = h[1];
+        stats->denom = h[2];
+        stats->n_kept = (uint64_t)h[3];
+        stats->n_matrix_samples = stats->n_spawned = (uint64_t)h[4];
+        stats->curr_size = (uint64_t)h[5];
+    }
+    if (h[6] != 0) {
+        fries_set_error("fries_frisys_hh_iterate: insufficient memory allocated for matrix compression");
+        return FRIES_ERR_CAPACITY;
+    }
+    if (h[7] != 0) {
+        fries_set_error("fries_frisys_hh_iterate: determinant store is full (capacity %zu)", vec->cap);
+        return FRIES_ERR_CAPACITY;
+    }
+    return FRIES_OK;
+}

@@ -30,7 +30,7 @@ merge_insert_kernel(VecView v, MergeSrc src, uint32_t *__restrict__ slot_out) {
         if (have && k != FRIES_EMPTY_KEY && val != 0) {  // DistVec::add ignores zero values (:418-423)
             bool ini = (k >> 63) != 0;
             uint64_t key = k & ~FRIES_INI_FLAG;
-            uint64_t slot = fr_det_hash(key, s_scr) & v.tmask;
+            uint64_t slot = vec_hash(v, key, s_scr) & v.tmask;
             while (true) {
                 uint64_t cur = *((volatile uint64_t *)&v.tkeys[slot]);
                 if (cur == key) {
@@ -162,7 +162,7 @@ compact_kernel(VecView v, uint64_t *__restrict__ keys_b, double *__restrict__ va
     // phase 3: rebuild the index from the compacted keys (all distinct)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
         uint64_t key = __ldcg(&keys_b[i]);
-        uint64_t slot = fr_det_hash(key, s_scr) & v.tmask;
+        uint64_t slot = vec_hash(v, key, s_scr) & v.tmask;
         while (true) {
             unsigned long long old = atomicCAS((unsigned long long *)&v.tkeys[slot], FRIES_EMPTY_KEY, key);
             if (old == FRIES_EMPTY_KEY) {
@@ -273,6 +273,29 @@ extern "C" int fries_vec_create(fries_ctx *c, size_t capacity, unsigned n_bits, 
     return FRIES_OK;
 }
 
+// HubHolVec ctor hh_vec.hpp:27-29: n_bits = 2 n_sites + n_sites * ph_bits; hashes include the phonon numbers
+extern "C" int fries_vec_create_hh(fries_ctx *c, size_t capacity, unsigned n_sites, unsigned ph_bits, unsigned n_elec,
+                                   unsigned n_vecs, const uint32_t *h_proc_scr, const uint32_t *h_vec_scr, int n_ranks,
+                                   int rank, fries_vec **out) {
+    FRIES_REQUIRE(n_sites >= 2 && ph_bits >= 1 && n_sites * (2 + ph_bits) <= 63 && (1u << ph_bits) <= 2 * n_sites,
+                  "fries_vec_create_hh: %u sites x (2 + %u) bits do not fit one 63-bit key (or phonon numbers exceed the scrambler)",
+                  n_sites, ph_bits);
+    // the scramblers have 2 n_sites entries (frisys_hh.cpp:72,100); pad to the key width for the generic ctor
+    std::vector<uint32_t> ps(n_sites * (2 + ph_bits), 0), vs(n_sites * (2 + ph_bits), 0);
+    memcpy(ps.data(), h_proc_scr, 2 * n_sites * 4);
+    memcpy(vs.data(), h_vec_scr, 2 * n_sites * 4);
+    FRIES_TRY(fries_vec_create(c, capacity, n_sites * (2 + ph_bits), n_elec, n_vecs, ps.data(), vs.data(), n_ranks, rank, out));
+    (*out)->hh_sites = n_sites;
+    (*out)->hh_ph_bits = ph_bits;
+    return FRIES_OK;
+}
+// DistVec::set_min_del_idx vec_utils.hpp: positions below idx are never deleted
+extern "C" int fries_vec_set_min_del_idx(fries_vec *vec, size_t idx) {
+    FRIES_REQUIRE(vec, "NULL argument");
+    vec->min_del_idx = idx;
+    return FRIES_OK;
+}
+
 extern "C" int fries_hbpp_destroy(struct fries_hbpp *hb);
 extern "C" int fries_vec_destroy(fries_vec *v) {
     if (v) {
@@ -335,7 +358,8 @@ extern "C" int fries_vec_add(fries_vec *vec, const uint64_t *h_keys, const doubl
             fries_set_error("fries_vec_add: key %zu has bits above n_bits=%u", i, vec->n_bits);
             return FRIES_ERR_ARG;
         }
-        if ((unsigned)__builtin_popcountll(h_keys[i]) != vec->n_elec) {
+        uint64_t ek = vec->hh_sites ? (h_keys[i] & ((1ull << (2 * vec->hh_sites)) - 1)) : h_keys[i];
+        if ((unsigned)__builtin_popcountll(ek) != vec->n_elec) {
             // DistVec::idx_to_hash throws for a wrong electron count (vec_utils.hpp:389-399)
             fries_set_error("Determinant %016llx created with an incorrect number of electrons",
                             (unsigned long long)h_keys[i]);
@@ -365,7 +389,8 @@ __global__ void upload_fixup_kernel(VecView v, size_t n, unsigned n_elec, unsign
     unsigned long long bad = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint64_t k = v.keys[i];
-        if ((unsigned)__popcll(k) != n_elec || (k >> n_bits) != 0) bad++;
+        uint64_t ek = v.hh_sites ? (k & ((1ull << (2 * v.hh_sites)) - 1)) : k;
+        if ((unsigned)__popcll(ek) != n_elec || (k >> n_bits) != 0) bad++;
         v.diag[i] = __longlong_as_double(0x7ff8000000000000ll);
     }
     bad = warp_sum_u64(bad);

@@ -31,12 +31,14 @@ struct VecView {
     const uint32_t *scr_vec;   // device, 64 entries
     const uint32_t *scr_proc;  // device, 64 entries
     VecCounters *cnt;
+    unsigned hh_sites, hh_ph_bits;  // Hubbard-Holstein keys (hh_vec.hpp): 2 n_sites electron bits + n_sites phonon fields; 0 = molecular
 };
 
 struct fries_vec {
     fries_ctx *ctx = nullptr;
     size_t cap = 0, tsize = 0;
     unsigned n_bits = 0, n_elec = 0, n_vecs = 0;
+    unsigned hh_sites = 0, hh_ph_bits = 0;
     int n_ranks = 1, rank = 0;
     DevBuf<uint64_t> keys[2];
     DevBuf<double> vals[2];
@@ -70,15 +72,35 @@ struct fries_vec {
         v.scr_vec = scr.p;
         v.scr_proc = scr.p + 64;
         v.cnt = cnt.p;
+        v.hh_sites = hh_sites;
+        v.hh_ph_bits = hh_ph_bits;
         return v;
     }
     int read_counters(VecCounters *out);
 };
 
+// HashTable::hash_fxn with phonon numbers (det_hash.hpp:160-170; HubHolVec::idx_to_hash hh_vec.hpp:72-88):
+// occupied electron orbitals first, then the phonon number of every site, both through the same scrambler
+__host__ __device__ __forceinline__ uint64_t fr_det_hash_hh(uint64_t key, const uint32_t *scr, unsigned n_sites,
+                                                            unsigned ph_bits) {
+    uint64_t elec = key & ((1ull << (2 * n_sites)) - 1);
+    uint64_t h = fr_det_hash(elec, scr);
+    uint64_t ph = key >> (2 * n_sites);
+    for (uint32_t i = 0; i < n_sites; i++) {
+        uint32_t num = (uint32_t)(ph & ((1u << ph_bits) - 1));
+        ph >>= ph_bits;
+        h = FRIES_HASH_PRIME * h + (uint32_t)((i + 1) * scr[num]);
+    }
+    return h;
+}
+__host__ __device__ __forceinline__ uint64_t vec_hash(const VecView &v, uint64_t key, const uint32_t *s_scr) {
+    return v.hh_sites ? fr_det_hash_hh(key, s_scr, v.hh_sites, v.hh_ph_bits) : fr_det_hash(key, s_scr);
+}
+
 // find the storage position of `key` (flag bit already stripped); FRIES_NO_POS if absent.
 // HashTable::read(create = false) det_hash.hpp:60-94
 __device__ __forceinline__ uint32_t vec_lookup(const VecView &v, uint64_t key, const uint32_t *s_scr) {
-    uint64_t slot = fr_det_hash(key, s_scr) & v.tmask;
+    uint64_t slot = vec_hash(v, key, s_scr) & v.tmask;
     while (true) {
         uint64_t cur = v.tkeys[slot];
         if (cur == key) return v.tpos[slot];

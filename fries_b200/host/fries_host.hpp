@@ -243,6 +243,41 @@ inline MolInput parse_hf_input(const std::string &dir) {
     return m;
 }
 
+// parse_hh_input FRIES/io_utils.cpp:320-408: key / value lines in a fixed order
+struct HhInput {
+    unsigned n_elec = 0, lat_len = 0, n_dim = 0;
+    double eps = 0, elec_int = 0, ph_freq = 0, elec_ph = 0, hf_en = 0;
+};
+inline HhInput parse_hh_input(const std::string &path) {
+    std::ifstream in(path);
+    if (!in.is_open()) throw std::runtime_error("Could not open file containing Hubbard-Holstein parameters");
+    HhInput h;
+    std::string key;
+    auto expect = [&](const char *name, const char *what, auto &dst) {
+        std::getline(in, key);
+        if (key.empty()) std::getline(in, key);
+        if (key != name)
+            throw std::runtime_error(std::string("Could not find ") + what + " in file containing Hubbard-Holstein parameters");
+        in >> dst;
+        std::getline(in, key);
+    };
+    expect("n_elec", "n_elec parameter", h.n_elec);
+    expect("lat_len", "lat_len parameter", h.lat_len);
+    expect("n_dim", "n_dim parameter", h.n_dim);
+    expect("eps", "eps parameter", h.eps);
+    expect("U", "electron interaction parameter (U)", h.elec_int);
+    expect("omega", "phonon frequency parameter (omega)", h.ph_freq);
+    expect("g", "electron-phonon interaction parameter (g)", h.elec_ph);
+    expect("gs_energy", "gs_energy parameter", h.hf_en);
+    return h;
+}
+// gen_neel_det_1D FRIES/Hamiltonians/hub_holstein.cpp:139-171: up spins on even sites, down spins on odd sites
+inline uint64_t gen_neel_det_1D(unsigned n_sites, unsigned n_elec) {
+    uint64_t k = 0;
+    for (unsigned e = 0; e < n_elec / 2; e++) k |= (1ull << (2 * e)) | (1ull << (n_sites + 2 * e + 1));
+    return k;
+}
+
 // read_dets + load_vec_txt FRIES/io_utils.cpp:410-482,565-586
 inline size_t load_vec_txt(const std::string &prefix, std::vector<uint64_t> &dets, std::vector<double> &vals) {
     std::ifstream fd(prefix + "dets");
@@ -331,6 +366,12 @@ class DistVec {
             const std::vector<uint32_t> &vec_scr)
         : n_bits(n_bits_), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size) {
         check(fries_vec_create(c.h, size, n_bits, n_elec, n_vecs, proc_scr.data(), vec_scr.data(), 1, 0, &h));
+    }
+    // HubHolVec FRIES/hh_vec.hpp:27-29
+    DistVec(Context &c, size_t size, unsigned n_sites, unsigned ph_bits, unsigned n_elec_, unsigned n_vecs_,
+            const std::vector<uint32_t> &proc_scr, const std::vector<uint32_t> &vec_scr)
+        : n_bits(n_sites * (2 + ph_bits)), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size) {
+        check(fries_vec_create_hh(c.h, size, n_sites, ph_bits, n_elec, n_vecs, proc_scr.data(), vec_scr.data(), 1, 0, &h));
     }
     ~DistVec() {
         if (hb) fries_hbpp_destroy(hb);

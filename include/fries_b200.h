@@ -222,6 +222,31 @@ typedef struct {
 int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, fries_frifull_params *p,
                               double uniform, fries_iter_stats *stats);
 
+/* ---- a19: Hubbard-Holstein (frisys_hh) ----------------------------------------------------------------------
+ * Keys: bits [0, n) spin-up sites, [n, 2n) spin-down sites, then n phonon fields of ph_bits bits
+ * (HubHolVec FRIES/hh_vec.hpp:27-29); hashes include the phonon numbers (hh_vec.hpp:56-88). */
+int fries_vec_create_hh(fries_ctx *ctx, size_t capacity, unsigned n_sites, unsigned ph_bits, unsigned n_elec,
+                        unsigned n_vecs, const uint32_t *h_proc_scrambler, const uint32_t *h_vec_scrambler, int n_ranks,
+                        int rank, fries_vec **out);
+int fries_vec_set_min_del_idx(fries_vec *vec, size_t idx); /* DistVec::set_min_del_idx */
+/* what 0: hub_diag hub_holstein.cpp:101-136 -> out[n]; 1: find_neighbors_1D hh_vec.hpp:139-175 as two bit masks per
+ * state (hop to orb+1, hop to orb-1) -> out[2n]; 2: per-state terms of calc_ref_ovlp hub_holstein.hpp:93-182 -> out[n] */
+int fries_hh_batch(fries_ctx *ctx, int what, const uint64_t *h_keys, const double *h_vals, size_t n, unsigned n_sites,
+                   unsigned n_elec, unsigned ph_bits, uint64_t ref_key, double g_over_t, double *h_out);
+typedef struct {
+    double eps;            /* imaginary time step */
+    double init_thresh;    /* --initiator */
+    double hub_u, ph_freq, elec_ph, hf_en; /* U, omega, g, gs_energy of the parameter file (io_utils.cpp:320-408) */
+    unsigned target_nonz;  /* --vec_nonz (also the matrix-compression budget, frisys_hh.cpp:202,222) */
+    double en_shift;
+    uint64_t ref_key;      /* Neel state gen_neel_det_1D hub_holstein.cpp:139-171 */
+} fries_frisys_hh_params;
+int fries_frisys_hh_setup(fries_vec *vec, size_t spawn_cap, fries_hbpp **out);
+/* frisys_hh loop body FRIES_bin/frisys_hh.cpp:186-368; uniforms3 = stage 1, stage 2, vector compression;
+ * stats: numer/denom as written to projnum.txt/projden.txt (denom = weight of the Neel state) */
+int fries_frisys_hh_iterate(fries_vec *vec, fries_hbpp *hb, const fries_frisys_hh_params *p, const double *h_uniforms3,
+                            fries_iter_stats *stats);
+
 /* ---- multi-GPU (one process per GPU; owner = hash_fxn(occ; proc_scrambler) % n_ranks, vec_utils.hpp:373-379) ----
  * Global reductions (sum_mpi compress_utils.hpp:179-231, the loc_norms Allgather) happen INSIDE the kernels through
  * peer-mapped inboxes: fries_comm_create returns a 64-byte CUDA IPC handle, the host all-gathers the handles

@@ -1239,3 +1239,108 @@ size_t fo_mol_h_apply_list(const fo_mol *m, const uint64_t *keys, const double *
     free(doub);
     return k;
 }
+
+/* ================================ a19: Hubbard-Holstein ============================================ */
+
+/* hub_diag hub_holstein.cpp:101-136: sites occupied by both spins */
+unsigned fo_hub_diag(uint64_t key, unsigned n_sites) {
+    unsigned n = 0;
+    for (unsigned s = 0; s < n_sites; s++) n += (unsigned)(BIT(key, s) & BIT(key, s + n_sites));
+    return n;
+}
+/* gen_neel_det_1D hub_holstein.cpp:139-171: spin-up electrons on even sites, spin-down on odd sites */
+uint64_t fo_gen_neel_det_1D(unsigned n_sites, unsigned n_elec) {
+    uint64_t k = 0;
+    for (unsigned e = 0; e < n_elec / 2; e++) {
+        k |= 1ull << (2 * e);
+        k |= 1ull << (n_sites + 2 * e + 1);
+    }
+    return k;
+}
+/* HubHolVec::find_neighbors_1D hh_vec.hpp:139-175.  out = [n_plus, orbs..., (pad to n_elec + 1), n_minus, orbs...]:
+ * first list = occupied orbitals whose neighbour at +1 is empty, second list = neighbour at -1 empty; open boundary */
+void fo_hh_neighbors(uint64_t key, unsigned n_sites, unsigned n_elec, uint8_t *out) {
+    unsigned np = 0, nm = 0;
+    for (unsigned o = 0; o < 2 * n_sites; o++) {
+        if (!BIT(key, o)) continue;
+        if (o != n_sites - 1 && o != 2 * n_sites - 1 && !BIT(key, o + 1)) out[1 + np++] = (uint8_t)o;
+    }
+    for (unsigned o = 1; o < 2 * n_sites; o++) {
+        if (!BIT(key, o)) continue;
+        if (o != n_sites && !BIT(key, o - 1)) out[n_elec + 2 + nm++] = (uint8_t)o;
+    }
+    out[0] = (uint8_t)np;
+    out[n_elec + 1] = (uint8_t)nm;
+}
+/* hash_fxn with phonon numbers det_hash.hpp:160-170 as used by HubHolVec::idx_to_hash hh_vec.hpp:72-88 */
+uint64_t fo_hash_hh(uint64_t key, const uint32_t *scr, unsigned n_sites, unsigned ph_bits) {
+    uint64_t h = 0;
+    unsigned i = 0;
+    for (unsigned o = 0; o < 2 * n_sites; o++)
+        if (BIT(key, o)) {
+            h = FO_PRIME * h + (uint32_t)((i + 1) * scr[o]);
+            i++;
+        }
+    for (unsigned s = 0; s < n_sites; s++) {
+        unsigned ph = (unsigned)((key >> (2 * n_sites + s * ph_bits)) & ((1u << ph_bits) - 1));
+        h = FO_PRIME * h + (uint32_t)((s + 1) * scr[ph]);
+    }
+    return h;
+}
+/* calc_ref_ovlp hub_holstein.hpp:93-182 (byte-wise walk over the electron bits, as the reference) */
+double fo_hh_ref_ovlp(const uint64_t *keys, const double *vals, size_t n, uint64_t ref, unsigned n_elec, unsigned n_sites,
+                      unsigned ph_bits, double g_over_t) {
+    double result = 0;
+    unsigned n_bytes = (2 * n_sites + 7) / 8;
+    uint64_t emask = (1ull << (2 * n_sites)) - 1;
+    for (size_t d = 0; d < n; d++) {
+        uint64_t cur = keys[d];
+        unsigned ph[64], tot_ph = 0;
+        for (unsigned s = 0; s < n_sites; s++) {
+            ph[s] = (unsigned)((cur >> (2 * n_sites + s * ph_bits)) & ((1u << ph_bits) - 1));
+            tot_ph += ph[s];
+        }
+        if ((cur & emask) == (ref & emask)) {
+            unsigned found = 0, site_elecs = 0;
+            for (unsigned s = 0; s < n_sites && found < 2; s++) {
+                unsigned n_occ = (unsigned)(BIT(ref, s) + BIT(ref, s + n_sites));
+                if (ph[s] > 1 || (ph[s] == 1 && n_occ == 0)) {
+                    site_elecs = 0;
+                    break;
+                } else if (ph[s] == 1) {
+                    site_elecs = n_occ;
+                    found++;
+                }
+            }
+            if (found == 2) site_elecs = 0;
+            result -= vals[d] * g_over_t * site_elecs;
+            continue;
+        }
+        if (tot_ph != 0) continue;
+        unsigned n_hop = 0, n_common = 0;
+        for (unsigned b = 0; b < n_bytes && n_hop <= 1; b++) {
+            uint8_t c = (uint8_t)(cur >> (8 * b)), r = (uint8_t)(ref >> (8 * b));
+            uint8_t cp = b ? (uint8_t)(cur >> (8 * (b - 1))) : 0, rp = b ? (uint8_t)(ref >> (8 * (b - 1))) : 0;
+            uint8_t cn = (uint8_t)(cur >> (8 * (b + 1))), rn = (uint8_t)(ref >> (8 * (b + 1)));
+            uint8_t not_occ = c & (uint8_t)~r;
+            uint8_t ref_left = c & (r >> 1), not_occ_left = (uint8_t)~c >> 1;
+            uint8_t ref_right = c & (uint8_t)(r << 1), not_occ_right = (uint8_t)((uint8_t)~c << 1);
+            if (b > 0) {
+                ref_right |= c & ((rp >> 7) & 1);
+                not_occ_right |= ((uint8_t)~cp >> 7) & 1;
+            }
+            if (b < n_bytes - 1) {
+                ref_left |= c & (uint8_t)(rn << 7);
+                not_occ_left |= (uint8_t)((uint8_t)~cn << 7);
+            }
+            if (b == (n_sites + 7) / 8) ref_left &= (uint8_t)~(1 << ((n_sites - 1) % 8));
+            uint8_t mask = not_occ & ((ref_left & not_occ_left) | (ref_right & not_occ_right));
+            if (b == n_bytes - 1 && (2 * n_sites) % 8 != 0) mask &= (uint8_t)((1 << ((2 * n_sites) % 8)) - 1);
+            n_hop += (unsigned)__builtin_popcount(mask);
+            if (n_hop > 1) break;
+            n_common += (unsigned)__builtin_popcount(r & c);
+        }
+        if (n_hop == 1 && n_common == n_elec - 1) result += vals[d];
+    }
+    return result;
+}

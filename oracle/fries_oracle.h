@@ -89,6 +89,14 @@ size_t fo_debug_hbpp_stage(const fo_mol *m, const uint64_t *keys, const double *
 size_t fo_mol_h_apply_list(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double id_fac,
                            double h_fac, uint64_t *out_keys, double *out_vals, size_t cap);
 
+/* ---- a19: Hubbard-Holstein ---- */
+unsigned fo_hub_diag(uint64_t key, unsigned n_sites);                         /* hub_holstein.cpp:101-136 */
+uint64_t fo_gen_neel_det_1D(unsigned n_sites, unsigned n_elec);               /* hub_holstein.cpp:139-171 */
+void fo_hh_neighbors(uint64_t key, unsigned n_sites, unsigned n_elec, uint8_t *out); /* hh_vec.hpp:139-175 */
+uint64_t fo_hash_hh(uint64_t key, const uint32_t *scr, unsigned n_sites, unsigned ph_bits); /* hh_vec.hpp:72-88 */
+double fo_hh_ref_ovlp(const uint64_t *keys, const double *vals, size_t n, uint64_t ref, unsigned n_elec, unsigned n_sites,
+                      unsigned ph_bits, double g_over_t);                     /* hub_holstein.hpp:93-182 */
+
 #ifdef __cplusplus
 }
 #endif

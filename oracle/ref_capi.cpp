@@ -501,4 +501,47 @@ uint64_t ref_gen_neel_det_1D(unsigned n_sites, unsigned n_elec, unsigned ph_bits
     return bytes_to_key(bytes, 8);
 }
 
+
+/* HubHolVec helpers, FRIES/hh_vec.hpp: find_neighbors_1D :139-175 (out: 2 x (n_elec + 1) bytes), idx_to_hash :72-88 */
+static HubHolVec<double> *make_hh(unsigned n_sites, unsigned ph_bits, unsigned n_elec, const uint32_t *scr) {
+    std::vector<uint32_t> s(scr, scr + 2 * n_sites);
+    std::function<double(const uint8_t *)> diag = [n_sites](const uint8_t *det) { return (double)hub_diag((uint8_t *)det, n_sites); };
+    return new HubHolVec<double>(16, 16, (uint8_t)n_sites, (uint8_t)ph_bits, n_elec, 1, diag, 1, s, s);
+}
+void ref_hh_neighbors(uint64_t key, unsigned n_sites, unsigned ph_bits, unsigned n_elec, uint8_t *out) {
+    uint32_t scr[64] = {0};
+    HubHolVec<double> *v = make_hh(n_sites, ph_bits, n_elec, scr);
+    uint8_t bytes[16] = {0};
+    key_to_bytes(key, bytes, 8);
+    v->find_neighbors_1D(bytes, out);
+    delete v;
+}
+uint64_t ref_hh_hash(uint64_t key, unsigned n_sites, unsigned ph_bits, unsigned n_elec, const uint32_t *scr) {
+    HubHolVec<double> *v = make_hh(n_sites, ph_bits, n_elec, scr);
+    uint8_t bytes[16] = {0}, orbs[64];
+    key_to_bytes(key, bytes, 8);
+    uint64_t h = (uint64_t)v->idx_to_hash(bytes, orbs);
+    delete v;
+    return h;
+}
+/* calc_ref_ovlp hub_holstein.hpp:93-182 over a list */
+double ref_hh_ref_ovlp(const uint64_t *keys, const double *vals, size_t n, uint64_t ref, unsigned n_elec, unsigned n_sites,
+                       unsigned ph_bits, double g_over_t) {
+    uint32_t scr[64] = {0};
+    HubHolVec<double> *v = make_hh(n_sites, ph_bits, n_elec, scr);
+    size_t nb = CEILING(n_sites * (2 + ph_bits), 8);
+    Matrix<uint8_t> dets(n + 1, nb), ph(n + 1, n_sites);
+    std::vector<double> vv(vals, vals + n);
+    for (size_t i = 0; i < n; i++) {
+        key_to_bytes(keys[i], dets[i], nb);
+        v->decode_phonons(dets[i], ph[i]);
+    }
+    uint8_t ref_b[16] = {0}, occ[64];
+    key_to_bytes(ref, ref_b, 8);
+    v->gen_orb_list(ref_b, occ);
+    double r = calc_ref_ovlp(dets, vv.data(), ph, n, ref_b, occ, (uint8_t)n_elec, n_sites, g_over_t);
+    delete v;
+    return r;
+}
+
 }  // extern "C"

@@ -90,3 +90,41 @@ def test_frisys_mol_driver_energy_and_files(tiny, tmp_path):
     if "ref" in res:
         er, sr = res["ref"]
         assert abs(e - er) < 5 * (s + sr) + 2e-4, (e, s, er, sr)
+
+
+# ---- config[0]: Hubbard model, frisys_hh (examples/run_hubbard.sh sizes; parameter file with the keys HEAD's parser wants) ----
+HUBBARD_PARAMS = "n_elec\n6\nlat_len\n6\nn_dim\n1\neps\n0.01\nU\n2\nomega\n0\ng\n0\ngs_energy\n-3.98791841486987\n"
+HUBBARD_EXACT = -4.546313794436 + 3.98791841486987  # exact E0 (400 determinants) minus gs_energy, SURVEY.md section 6
+
+
+def test_frisys_hh_driver_energy_and_files(tmp_path):
+    pf = str(tmp_path / "hubbard_params.txt")
+    open(pf, "w").write(HUBBARD_PARAMS)
+    res = {}
+    exes = [("ours", os.path.join(OURS, "frisys_hh"))]
+    if os.path.exists(os.path.join(REF, "frisys_hh")):
+        exes.append(("ref", os.path.join(REF, "frisys_hh")))
+    n_it = 6000
+    for name, exe in exes:
+        rd = str(tmp_path / name) + "/"
+        os.makedirs(rd)
+        r = run(exe, ["--params_path", pf, "--target", 1000, "--max_dets", 1000, "--vec_nonz", 200, "--max_iter", n_it,
+                      "--result_dir", rd], seed=5 if name == "ours" else 6)
+        assert "Exception" not in r.stderr, r.stderr[-500:]
+        files = sorted(os.listdir(rd))
+        for f in ("S.txt", "dets0.dat", "hash.dat", "norm.txt", "params.txt", "projden.txt", "projnum.txt", "vals0.dat"):
+            assert f in files, (name, f, files)
+        num, den = read_col(rd + "projnum.txt"), read_col(rd + "projden.txt")
+        assert len(num) == n_it and len(read_col(rd + "S.txt")) == n_it // 10
+        assert os.path.getsize(rd + "hash.dat") == 4 * 12
+        nd = os.path.getsize(rd + "dets0.dat") // 4  # 30 bits -> 4 bytes per state
+        assert os.path.getsize(rd + "vals0.dat") == nd * 2 * 8 and 0 < nd <= 400
+        it_lines = [ln for ln in r.stdout.splitlines() if ", en est: " in ln]
+        assert len(it_lines) == n_it and it_lines[-1].split(",")[1].startswith(" norm: ") and ", n_neel: " in it_lines[-1]
+        res[name] = blocked_ratio(num, den, burn=2000)
+    e, s = res["ours"]
+    print("hubbard exact", HUBBARD_EXACT, "ours", res["ours"], "ref", res.get("ref"))
+    assert abs(e - HUBBARD_EXACT) < 5 * s + 3e-3, (e, s, HUBBARD_EXACT)
+    if "ref" in res:
+        er, sr = res["ref"]
+        assert abs(e - er) < 5 * (s + sr) + 1e-3, (e, s, er, sr)

@@ -379,3 +379,40 @@ def test_h_apply(mols, ctx, n_par):
         assert n_sp == want
     finally:
         vec.close()
+
+
+# ---- a19: Hubbard-Holstein pieces ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_sites,n_elec", [(6, 6), (8, 6), (10, 10)])
+def test_hh_pieces(ctx, n_sites, n_elec):
+    import fries_b200
+    from test_oracle_hh import libs, random_states
+    L, R = libs()
+    ph_bits = 3
+    rng = np.random.default_rng(n_sites)
+    neel = L.fo_gen_neel_det_1D(n_sites, n_elec)
+    scr = rng.integers(0, 2**32, 2 * n_sites, dtype=np.uint64).astype(np.uint32)
+    keys = np.unique(np.concatenate([[neel], random_states(rng, 400, n_sites, n_elec, ph_bits, True),
+                                     random_states(rng, 400, n_sites, n_elec, ph_bits, False)]).astype(np.uint64))
+    vals = rng.normal(size=keys.size)
+    assert np.array_equal(fries_b200.hh_batch(ctx, 0, keys, None, n_sites, n_elec, ph_bits),
+                          [R.ref_hub_diag(int(k), n_sites) for k in keys])
+    masks = fries_b200.hh_batch(ctx, 1, keys, None, n_sites, n_elec, ph_bits)
+    for k, (p, m) in zip(keys, masks):
+        b = np.zeros(2 * (n_elec + 1), np.uint8)
+        R.ref_hh_neighbors(int(k), n_sites, ph_bits, n_elec, b)
+        assert [i for i in range(64) if (int(p) >> i) & 1] == list(b[1:1 + b[0]])
+        assert [i for i in range(64) if (int(m) >> i) & 1] == list(b[n_elec + 2:n_elec + 2 + b[n_elec + 1]])
+    for g in (0.0, 0.7):
+        terms = fries_b200.hh_batch(ctx, 2, keys, vals, n_sites, n_elec, ph_bits, neel, g)
+        assert terms.sum() == pytest.approx(R.ref_hh_ref_ovlp(keys, vals, keys.size, neel, n_elec, n_sites, ph_bits, g), rel=1e-12, abs=1e-12)
+    # the store's index uses the hash with phonon numbers: every state (with phonons) is found again
+    vec = fries_b200.Vec(ctx, 4096, n_sites * (2 + ph_bits), n_elec, 2, scr, scr, hh=(n_sites, ph_bits))
+    vec.add(keys, vals, np.ones(keys.size, np.uint8))
+    assert vec.curr_size() == keys.size
+    assert vec.dot(keys, np.ones(keys.size), 0) == pytest.approx(vals.sum(), rel=1e-12)
+    vec.add(keys[::2], vals[::2], np.zeros(keys[::2].size, np.uint8))  # non-initiator adds onto occupied states
+    gk, gv = vec.download()
+    lut = dict(zip(gk.tolist(), gv[0].tolist()))
+    for i, k in enumerate(keys):
+        assert lut[int(k)] == pytest.approx(vals[i] * (2 if i % 2 == 0 else 1), rel=1e-14)
+    vec.close()
