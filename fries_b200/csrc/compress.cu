@@ -238,13 +238,15 @@ struct MatProvider {
     const uint16_t *sub_sizes;
     size_t n, n_sub;
     __device__ size_t count() const { return n; }
-    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns) const {
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv) const {
         v = values[i];
         nd = ndiv[i];
         ns = sub_sizes ? sub_sizes[i] : (uint32_t)n_sub;
+        rinv = 1.0;
     }
-    __device__ void row(size_t i, double *w) const {
-        for (size_t j = 0; j < n_sub; j++) w[j] = subw[i * n_sub + j];
+    template <class F>
+    __device__ void visit(size_t i, double, F &&f) const {
+        for (uint32_t j = 0; j < n_sub; j++) f(j, subw[i * n_sub + j]);
     }
 };
 
@@ -406,7 +408,7 @@ extern "C" int fries_comp_sub(fries_ctx *c, const double *h_values, size_t count
     CUDA_TRY(cudaSetDevice(c->device));
     int grid = c->coop_grid((const void *)comp_sub_mat_kernel, FR_COMP_BLOCK, 0);
     size_t cn = count ? count : 1;
-    DevBuf<double> values, subw, veff, wtr, lb, oval;
+    DevBuf<double> values, subw, veff, wtr, lb, oval, rinv;
     DevBuf<uint32_t> ndiv, keep, kcnt, owidx, osub;
     DevBuf<uint16_t> ssz;
     DevBuf<uint8_t> nsub;
@@ -415,6 +417,7 @@ extern "C" int fries_comp_sub(fries_ctx *c, const double *h_values, size_t count
     FRIES_TRY(veff.alloc(cn));
     FRIES_TRY(wtr.alloc(cn));
     FRIES_TRY(lb.alloc(cn));
+    FRIES_TRY(rinv.alloc(cn));
     FRIES_TRY(ndiv.alloc(cn));
     FRIES_TRY(keep.alloc(cn));
     FRIES_TRY(kcnt.alloc(cn));
@@ -433,7 +436,7 @@ extern "C" int fries_comp_sub(fries_ctx *c, const double *h_values, size_t count
     }
     CUDA_TRY(cudaMemsetAsync(r.st, 0, sizeof(CompState), c->stream));
     MatProvider prov{values.p, ndiv.p, subw.p, h_sub_sizes ? ssz.p : nullptr, count, n_sub};
-    CompSubBufs bufs{veff.p, wtr.p, lb.p, ndiv.p, keep.p, kcnt.p, nsub.p, oval.p, owidx.p, osub.p,
+    CompSubBufs bufs{veff.p, wtr.p, lb.p, rinv.p, ndiv.p, keep.p, kcnt.p, nsub.p, oval.p, owidx.p, osub.p,
                      (unsigned long long)out_cap, r.pd, r.pc, r.st, fries_comm_view(nullptr)};
     // ndiv is both provider input and engine state: give the engine its own copy
     DevBuf<uint32_t> ndiv_state;

@@ -109,6 +109,7 @@ struct CompSubBufs {
     double *veff;
     double *wt_remain;
     double *lb;          // exclusive prefix of wt_remain (resampling lower bound)
+    double *rinv;        // 1 / (row norm): the row generator's normalisation, computed once in prep
     uint32_t *ndiv;
     uint32_t *keep;      // bit j = sub-element j preserved exactly (bit 0 for uniform rows)
     uint32_t *kcnt;      // outputs this input emits
@@ -127,8 +128,10 @@ struct CompSubBufs {
 
 // The hierarchical compression engine.  Provider P supplies
 //   size_t count();                                            number of inputs
-//   void prep(size_t i, double &v, uint32_t &ndiv, uint32_t &nsub);   effective weight + row shape
-//   void row(size_t i, double *w);                             the nsub sub-weights of input i
+//   void prep(size_t i, double &v, uint32_t &ndiv, uint32_t &nsub, double &rinv);  effective weight, row shape,
+//                                                              normalisation factor of the row (stored per input)
+//   void visit(size_t i, double rinv, F f);                    calls f(j, w_j) for the nsub sub-weights in order --
+//                                                              rows are streamed, never materialised
 // Restates comp_sub (compress_utils.cpp:797-820): find_keep_sub :130-276 then sys_sub :702-794.
 template <class P>
 __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_in, double rn_uniform) {
@@ -154,9 +157,10 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     // ---- phase 0: effective weights (find_keep_sub :134-137) ----
     double s = 0;
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        double v;
+        double v, rinv = 1.0;
         uint32_t nd, ns;
-        prov.prep(i, v, nd, ns);
+        prov.prep(i, v, nd, ns, rinv);
+        b.rinv[i] = rinv;
         b.veff[i] = v;
         b.wt_remain[i] = v;
         b.ndiv[i] = nd;
@@ -202,14 +206,12 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                         cnt += nd;
                         rem += v;
                     } else {
-                        double w[FRIES_MAX_SUB];
-                        prov.row(i, w);
                         uint32_t ns = b.nsub[i], kb = b.keep[i];
                         uint32_t full = (ns / 8) * 8;
                         double sub_remain = 0;
-                        for (uint32_t j = 0; j < ns; j++) {
-                            if (!((kb >> j) & 1u)) {
-                                double sm = cw * w[j];
+                        prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) {
+                            if (j < ns && !((kb >> j) & 1u)) {
+                                double sm = cw * wj;
                                 double eps = j < full ? 1e-12 : 1e-10;
                                 if (sm >= R && fabs(sm) > eps) {
                                     kb |= 1u << j;
@@ -218,7 +220,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                                     sub_remain += sm;
                                 }
                             }
-                        }
+                        });
                         b.keep[i] = kb;
                         sub_remain /= wt_factor;
                         double change = wr - sub_remain;
@@ -332,23 +334,22 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                     long long k0 = sg.count_below(start);
                     double g = sg.point(k0);
                     if (wr < v || g < lbound) {
-                        double w[FRIES_MAX_SUB];
-                        prov.row(i, w);
                         uint32_t ns = b.nsub[i], kb = b.keep[i];
                         double sub_lb = lbound - wr;
-                        for (uint32_t j = 0; j < ns; j++) {
-                            if (((kb >> j) & 1u) && w[j] != 0) {
+                        prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) {
+                            if (j >= ns) return;
+                            if (((kb >> j) & 1u) && wj != 0) {
                                 k++;
                             } else {
-                                sub_lb += v * w[j];
-                                if (g < sub_lb && w[j] != 0) {
+                                sub_lb += v * wj;
+                                if (g < sub_lb && wj != 0) {
                                     k++;
                                     k0++;
                                     g = sg.point(k0);
                                     if (g < sub_lb) anomalies++;
                                 }
                             }
-                        }
+                        });
                     }
                 }
             }
@@ -408,24 +409,23 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                     }
                 }
             } else {
-                double w[FRIES_MAX_SUB];
-                prov.row(i, w);
                 uint32_t ns = b.nsub[i], kb = b.keep[i];
                 long long k0 = sg.count_below(start);
                 double g = sg.point(k0);
                 double sub_lb = lbound - wr;
-                for (uint32_t j = 0; j < ns; j++) {
-                    if (((kb >> j) & 1u) && w[j] != 0) {
-                        FR_EMIT(v * w[j], j);
+                prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) {
+                    if (j >= ns) return;
+                    if (((kb >> j) & 1u) && wj != 0) {
+                        FR_EMIT(v * wj, j);
                     } else {
-                        sub_lb += v * w[j];
-                        if (g < sub_lb && w[j] != 0) {
+                        sub_lb += v * wj;
+                        if (g < sub_lb && wj != 0) {
                             FR_EMIT(samp_val, j);
                             k0++;
                             g = sg.point(k0);
                         }
                     }
-                }
+                });
             }
 #undef FR_EMIT
         }

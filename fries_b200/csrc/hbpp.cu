@@ -12,7 +12,8 @@ __device__ __forceinline__ uint32_t pk(unsigned p0, unsigned p1, unsigned p2, un
 }
 
 // Provider of stage S of the hierarchy.  prep() restates the per-sample set-up loop that precedes each
-// comp_sub call in apply_HBPP_sys; row() regenerates the sub-weight row the reference stores in subwts.
+// comp_sub call in apply_HBPP_sys; visit() streams the sub-weight row the reference stores in subwts
+// (mol.cuh hbs_* generators: masks + popcount, no row array, no occupied list).
 template <int S>
 struct HbProvider {
     MolView m;  // tables in shared memory
@@ -23,8 +24,26 @@ struct HbProvider {
         return n < io.in_cap ? (size_t)n : (size_t)io.in_cap;
     }
 
-    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns) const {
+    // singles bookkeeping (count_symm_virt + count_sing_allowed / count_sing_virt, near_uniform.cpp:14-28,316-347)
+    __device__ unsigned sing_allowed(uint64_t key) const {
+        uint8_t occ[FRIES_MAX_ELEC + 1], cnt[FR_N_IRREPS][2];
+        mol_occ_list(key, occ);
+        mol_count_symm_virt(m, occ, cnt);
+        return mol_count_sing_allowed(m, occ, cnt);
+    }
+    __device__ unsigned sing_virt(uint64_t key, unsigned &choice) const {
+        uint8_t occ[FRIES_MAX_ELEC + 1], cnt[FR_N_IRREPS][2];
+        mol_occ_list(key, occ);
+        mol_count_symm_virt(m, occ, cnt);
+        uint8_t ch = (uint8_t)choice;
+        unsigned n = mol_count_sing_virt(m, occ, cnt, &ch);
+        choice = ch;
+        return n;
+    }
+
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv) const {
         const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+        rinv = 1.0;
         if (S == 0) {  // singles vs doubles :713-727
             double w = fabs(io.vals[i]);
             v = w;
@@ -38,22 +57,19 @@ struct HbProvider {
         const uint32_t d = io.pdet[widx], pp = io.ppath[widx];
         v = io.pv[i];
         io.det[i] = d;
-        uint8_t occ[FRIES_MAX_ELEC + 1];
         const uint64_t key = io.keys[d];
-        mol_occ_list(key, occ);
         unsigned p0 = pp & 0xff, p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
-        double w[FRIES_MAX_SUB];
         if (S == 1) {  // first occupied orbital :738-763
             p0 = sub;
             ns = ne - (io.new_hb ? 1 : 0);
             if (p0 == 0) {
                 nd = 0;
-                double tot = hb_o1_probs(m, w, occ, io.new_hb);
-                if (io.new_hb) v *= tot;
+                double norm = 0;
+                hbs_o1(m, key, io.new_hb, [&](unsigned, double raw) { norm += raw; });
+                rinv = 1. / norm;
+                if (io.new_hb) v *= norm / m.d.s_norm;
             } else {
-                uint8_t cnt[FR_N_IRREPS][2];
-                mol_count_symm_virt(m, occ, cnt);
-                unsigned n_occ = mol_count_sing_allowed(m, occ, cnt);
+                unsigned n_occ = sing_allowed(key);
                 if (n_occ == 0) {
                     nd = 1;
                     v = 0;
@@ -70,17 +86,19 @@ struct HbProvider {
                 nd = 1;
             } else if (p0 == 0) {
                 nd = 0;
+                OccMask o = mol_occ_mask(m, key);
                 if (io.new_hb) {
                     p1++;
                     ns = p1;
-                    v *= hb_o2_probs_half(m, w, occ, p1);
+                    double norm = 0;
+                    hbs_o2_half(m, key, p1, [&](unsigned, double raw) { norm += raw; });
+                    rinv = 1. / norm;
+                    v *= norm / m.s_tens[mol_elec_orb(m, o, p1) % M];
+                } else {
+                    rinv = 1. / hbs_o2_norm(m, key, p1);
                 }
             } else {
-                uint8_t cnt[FR_N_IRREPS][2];
-                mol_count_symm_virt(m, occ, cnt);
-                uint8_t ch = (uint8_t)p1;
-                unsigned n_virt = mol_count_sing_virt(m, occ, cnt, &ch);
-                p1 = ch;
+                unsigned n_virt = sing_virt(key, p1);
                 if (n_virt == 0) {
                     nd = 1;
                     v = 0;
@@ -99,9 +117,17 @@ struct HbProvider {
                     nd = 1;
                 } else {
                     nd = 0;
-                    int o1_spin = p1 / (ne / 2), o2_spin = occ[p2] / M;
-                    double tot = hb_u1_probs(m, w, occ[p1], occ, io.new_hb && (o1_spin == o2_spin));
-                    if (io.new_hb) v *= tot;
+                    OccMask o = mol_occ_mask(m, key);
+                    unsigned o1_orb = mol_elec_orb(m, o, p1);
+                    bool excl = io.new_hb && (p1 / (ne / 2) == mol_elec_orb(m, o, p2) / M);
+                    double norm = 0, first = 0;
+                    hbs_u1(m, key, o1_orb, [&](unsigned j, double raw) {
+                        if (j == 0) first = raw;
+                        norm += raw;
+                    });
+                    if (excl) norm -= first;
+                    rinv = 1. / norm;
+                    if (io.new_hb) v *= norm / m.exch_norms[o1_orb % M];
                 }
                 p3 = 0;
             } else {
@@ -111,17 +137,27 @@ struct HbProvider {
         } else {  // S == 4: 2nd virtual (double) :866-908
             ns = m.d.max_n_symm;
             if (p0 == 0) {
-                unsigned u1 = mol_find_nth_virt(occ, p1 / (ne / 2), ne, M, sub);
-                if (u1 >= 2 * M || fr_read_bit(key, u1)) {
+                OccMask o = mol_occ_mask(m, key);
+                unsigned spin = p1 / (ne / 2);
+                uint32_t vm = ~(spin ? o.b : o.a) & (uint32_t)((1ull << M) - 1);
+                if (sub >= (unsigned)__popc(vm)) {  // find_nth_virt (fci_utils.c:138-148) would leave the orbital range
                     v = 0;
                     nd = 1;
                 } else {
+                    unsigned u1 = fr_nth_bit32(vm, sub) + M * spin;
                     nd = 0;
                     p3 = u1;
-                    unsigned len;
-                    double tot = io.new_hb ? hb_u2_probs_half(m, w, occ[p1], occ[p2], u1, key, &len)
-                                           : hb_u2_probs(m, w, occ[p1], occ[p2], u1, &len);
+                    unsigned o1_orb = mol_elec_orb(m, o, p1), o2_orb = mol_elec_orb(m, o, p2);
+                    double norm = 0;
+                    unsigned len = 0;
+                    if (io.new_hb) {
+                        hbs_u2_half(m, o1_orb, o2_orb, u1, key, [&](unsigned j, double raw) { norm += raw; len = j + 1; });
+                    } else {
+                        hbs_u2(m, o1_orb, o2_orb, u1, [&](unsigned j, double raw) { norm += raw; len = j + 1; });
+                    }
                     ns = len;
+                    rinv = norm != 0 ? 1 / norm : 1.0;
+                    double tot = norm / m.exch_norms[o2_orb % M];
                     if (io.new_hb || tot == 0) v *= tot;
                 }
             } else {
@@ -131,34 +167,35 @@ struct HbProvider {
         }
     }
 
-    __device__ void row(size_t i, double *w) const {
+    template <class F>
+    __device__ void visit(size_t i, double rinv, F &&f) const {
         if (S == 0) {
-            w[0] = io.p_doub;
-            w[1] = 1 - io.p_doub;
+            f(0u, io.p_doub);
+            f(1u, 1 - io.p_doub);
             return;
         }
         const unsigned ne = m.d.n_elec, M = m.d.n_orb;
         const uint32_t pp = io.path[i];
         const uint64_t key = io.keys[io.det[i]];
-        uint8_t occ[FRIES_MAX_ELEC + 1];
-        mol_occ_list(key, occ);
         unsigned p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
         if (S == 1) {
-            hb_o1_probs(m, w, occ, io.new_hb);
+            hbs_o1(m, key, io.new_hb, [&](unsigned j, double raw) { f(j, raw * rinv); });
         } else if (S == 2) {
             if (io.new_hb)
-                hb_o2_probs_half(m, w, occ, p1);
+                hbs_o2_half(m, key, p1, [&](unsigned j, double raw) { f(j, raw * rinv); });
             else
-                hb_o2_probs(m, w, occ, p1);
+                hbs_o2(m, key, p1, [&](unsigned j, double raw) { f(j, raw * rinv); });
         } else if (S == 3) {
-            int o1_spin = p1 / (ne / 2), o2_spin = occ[p2] / M;
-            hb_u1_probs(m, w, occ[p1], occ, io.new_hb && (o1_spin == o2_spin));
+            OccMask o = mol_occ_mask(m, key);
+            bool excl = io.new_hb && (p1 / (ne / 2) == mol_elec_orb(m, o, p2) / M);
+            hbs_u1(m, key, mol_elec_orb(m, o, p1), [&](unsigned j, double raw) { f(j, (excl && j == 0) ? 0.0 : raw * rinv); });
         } else {
-            unsigned len;
+            OccMask o = mol_occ_mask(m, key);
+            unsigned o1_orb = mol_elec_orb(m, o, p1), o2_orb = mol_elec_orb(m, o, p2);
             if (io.new_hb)
-                hb_u2_probs_half(m, w, occ[p1], occ[p2], p3, key, &len);
+                hbs_u2_half(m, o1_orb, o2_orb, p3, key, [&](unsigned j, double raw) { f(j, raw * rinv); });
             else
-                hb_u2_probs(m, w, occ[p1], occ[p2], p3, &len);
+                hbs_u2(m, o1_orb, o2_orb, p3, [&](unsigned j, double raw) { f(j, raw * rinv); });
         }
     }
 };
@@ -316,7 +353,7 @@ int fries_hbpp_alloc(fries_ctx *c, size_t cap, fries_hbpp **out, bool stages) {
     int rc = FRIES_OK;
 #define A(buf, n) if (rc == FRIES_OK) rc = hb->buf.alloc(n)
     if (stages) {
-        A(veff, cap); A(wtr, cap); A(lb, cap); A(ndiv, cap); A(keep, cap); A(kcnt, cap); A(nsub, cap);
+        A(veff, cap); A(wtr, cap); A(lb, cap); A(rinv, cap); A(ndiv, cap); A(keep, cap); A(kcnt, cap); A(nsub, cap);
         for (int b = 0; b < 2; b++) {
             A(oval[b], cap); A(owidx[b], cap); A(osub[b], cap); A(det[b], cap); A(path[b], cap);
         }
@@ -384,7 +421,7 @@ int fries_hbpp_stages_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys
         io.p_doub = p_doub;
         io.new_hb = new_hb;
         io.in_cap = hb->cap;
-        CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
+        CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->rinv.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
                          hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
                          hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(hb->comm)};
         switch (s) {
@@ -533,7 +570,7 @@ extern "C" int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, co
         io.pdet = hb->det[p].p; io.ppath = hb->path[p].p;
         io.det = hb->det[o].p; io.path = hb->path[o].p;
         io.p_doub = p_doub; io.new_hb = new_hb; io.in_cap = hb->cap;
-        CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
+        CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->rinv.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
                          hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
                          hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(hb->comm)};
         switch (s) {

@@ -29,7 +29,7 @@ struct HbStageIO {
 struct fries_hbpp {
     fries_ctx *ctx = nullptr;
     size_t cap = 0;
-    DevBuf<double> veff, wtr, lb, oval[2], fin_val;
+    DevBuf<double> veff, wtr, lb, rinv, oval[2], fin_val;
     DevBuf<uint32_t> ndiv, keep, kcnt, owidx[2], osub[2], det[2], path[2], fin_det, fin_orbs;
     DevBuf<uint8_t> nsub;
     DevBuf<double> part_d;

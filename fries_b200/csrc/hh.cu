@@ -102,14 +102,16 @@ struct HhStage1 {
         unsigned long long n = *n_in;
         return n < cap ? (size_t)n : (size_t)cap;
     }
-    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns) const {
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv) const {
         v = fabs(vals[i]);
         nd = v > 0 ? 0u : 1u;
         ns = 2;
+        rinv = 1.0;
     }
-    __device__ void row(size_t, double *w) const {
-        w[0] = hub_t;  // NOT normalised in the reference (:193-194)
-        w[1] = elec_ph;
+    template <class F>
+    __device__ void visit(size_t, double, F &&f) const {
+        f(0u, hub_t);  // NOT normalised in the reference (:193-194)
+        f(1u, elec_ph);
     }
 };
 struct HhStage2 {
@@ -125,7 +127,8 @@ struct HhStage2 {
         unsigned long long n = *n_in;
         return n < cap ? (size_t)n : (size_t)cap;
     }
-    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns) const {
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv) const {
+        rinv = 1.0;
         uint32_t di = pw[i], ex = ps[i];
         det[i] = di;
         ph_ex[i] = ex;
@@ -139,9 +142,10 @@ struct HhStage2 {
         v = pv[i] * nd;  // comp_vec2[samp_idx] *= ndiv (:217)
         ns = 2;
     }
-    __device__ void row(size_t, double *w) const {
-        w[0] = hub_t;  // only reached with ndiv == 0, i.e. value 0: the reference reads its stale row
-        w[1] = elec_ph;
+    template <class F>
+    __device__ void visit(size_t, double, F &&f) const {
+        f(0u, hub_t);  // only reached with ndiv == 0, i.e. value 0: the reference reads its stale row
+        f(1u, elec_ph);
     }
 };
 
@@ -339,7 +343,7 @@ extern "C" int fries_frisys_hh_iterate(fries_vec *vec, fries_hbpp *hb, const fri
     int g1 = c->coop_grid((const void *)hh_stage1_kernel, FR_COMP_BLOCK, 0);
     if (g1 < grid) grid = g1;
     auto bufs_for = [&](int o, int s) {
-        return CompSubBufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
+        return CompSubBufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->rinv.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
                            hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
                            hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(nullptr)};
     };

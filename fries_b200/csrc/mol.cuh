@@ -300,176 +300,216 @@ __host__ __device__ inline unsigned mol_for_each_doub(const MolView &m, uint64_t
     return n;
 }
 
-// ---- a8: HB-PP weight rows heat_bathPP.cpp:182-412.  Each returns the reference's return value -----------------
-// calc_o1_probs :182-200; row length n_elec - (exclude_first > 0)
-__host__ __device__ inline double hb_o1_probs(const MolView &m, double *p, const uint8_t *occ, int exclude_first) {
-    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
-    unsigned skip = exclude_first > 0;
-    double norm = 0;
-    for (unsigned i = skip; i < ne / 2; i++) {
-        p[i - skip] = m.s_tens[occ[i]];
-        norm += p[i - skip];
-    }
-    for (unsigned i = ne / 2; i < ne; i++) {
-        p[i - skip] = m.s_tens[occ[i] - M];
-        norm += p[i - skip];
-    }
-    double inv = 1. / norm;
-    for (unsigned i = skip; i < ne; i++) p[i - skip] *= inv;
-    return norm / m.d.s_norm;
+// ---- a8: HB-PP weight rows heat_bathPP.cpp:182-412 -------------------------------------------------------------
+// Streaming generators: hbs_*(..., f) call f(j, raw_j) for the entries j = 0, 1, ... of one row in index order with
+// the UN-normalised weight; the reference stores raw_j * (1 / norm).  Everything is derived from the u64 key with
+// popcount / find-nth-set-bit, so a kernel never materialises the row or the occupied list (no local memory).
+__host__ __device__ __forceinline__ unsigned fr_nth_bit32(uint32_t mask, unsigned n) {
+#ifdef __CUDA_ARCH__
+    return __fns(mask, 0, n + 1);
+#else
+    for (unsigned i = 0; i < n; i++) mask &= mask - 1;
+    return (unsigned)__builtin_ctz(mask);
+#endif
 }
-// calc_o2_probs :203-233; row length n_elec
-__host__ __device__ inline double hb_o2_probs(const MolView &m, double *p, const uint8_t *occ, unsigned o1_idx) {
-    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
-    unsigned o1 = occ[o1_idx], o1_spin = o1 / M, o1s = o1 % M;
-    double norm = 0;
-    unsigned off = (1 - o1_spin) * ne / 2;
-    for (unsigned i = off; i < ne / 2 + off; i++) {
-        p[i] = m.d_diff[o1s * M + occ[i] % M];
-        norm += p[i];
-    }
-    off = o1_spin * ne / 2;
-    for (unsigned i = off; i < o1_idx; i++) {
-        p[i] = m.d_same[FR_TRI_NODIAG(occ[i] % M, o1s)];
-        norm += p[i];
-    }
-    for (unsigned i = o1_idx + 1; i < ne / 2 + off; i++) {
-        p[i] = m.d_same[FR_TRI_NODIAG(o1s, occ[i] % M)];
-        norm += p[i];
-    }
-    p[o1_idx] = 0;
-    double inv = 1. / norm;
-    for (unsigned i = 0; i < ne; i++) p[i] *= inv;
-    return norm / m.s_tens[o1s];
+struct OccMask {
+    uint32_t a, b;  // spatial-orbital occupation of the two spin blocks
+};
+__host__ __device__ __forceinline__ OccMask mol_occ_mask(const MolView &m, uint64_t key) {
+    uint32_t all = (uint32_t)((1ull << m.d.n_orb) - 1);
+    OccMask o;
+    o.a = (uint32_t)(key & all);
+    o.b = (uint32_t)((key >> m.d.n_orb) & all);
+    return o;
 }
-// calc_o2_probs_half :236-270; row length o1_idx
-__host__ __device__ inline double hb_o2_probs_half(const MolView &m, double *p, const uint8_t *occ, unsigned o1_idx) {
-    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
-    unsigned o1 = occ[o1_idx], o1_spin = o1 / M;
-    double norm = 0;
-    unsigned upper = ne / 2 > o1_idx ? o1_idx : ne / 2;
-    for (unsigned i = 0; i < upper; i++) {
-        if (o1_spin == 0)
-            p[i] = m.d_same[FR_TRI_NODIAG((unsigned)occ[i], o1)];
-        else
-            p[i] = m.d_diff[(o1 - M) * M + occ[i]];
-        norm += p[i];
-    }
-    for (unsigned i = ne / 2; i < o1_idx; i++) {
-        if (o1_spin == 0)
-            p[i] = m.d_diff[o1 * M + occ[i] - M];
-        else
-            p[i] = m.d_same[FR_TRI_NODIAG((unsigned)occ[i] - M, o1 - M)];
-        norm += p[i];
-    }
-    double inv = 1. / norm;
-    for (unsigned i = 0; i < o1_idx; i++) p[i] *= inv;
-    return norm / m.s_tens[o1 % M];
+// spin orbital of the idx-th electron (alpha block first, ascending)
+__host__ __device__ __forceinline__ unsigned mol_elec_orb(const MolView &m, const OccMask &o, unsigned idx) {
+    const unsigned h = m.d.n_elec / 2;
+    return idx < h ? fr_nth_bit32(o.a, idx) : m.d.n_orb + fr_nth_bit32(o.b, idx - h);
 }
-// calc_u1_probs :273-319; row length M - n_elec / 2.  occ must be readable at index n_elec.
-__host__ __device__ inline double hb_u1_probs(const MolView &m, double *p, unsigned o1_orb, const uint8_t *occ,
-                                              int exclude_first) {
-    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
-    unsigned o1_spin = o1_orb / M, o1s = o1_orb % M, offset = o1_spin * M;
-    double norm = 0;
-    unsigned pi = 0, oi = ne / 2 * o1_spin;
-    unsigned curr = occ[oi];
-    for (unsigned k = 0; k < o1s; k++) {
-        if (k + offset == curr) {
-            oi++;
-            curr = occ[oi];
-        } else {
-            p[pi] = m.exch_sqrt[FR_TRI_NODIAG(k, o1s)];
-            norm += p[pi];
-            pi++;
-        }
+
+// calc_o1_probs :182-200: one entry per electron (the first is skipped when exclude_first); norm = sum in index order
+template <class F>
+__host__ __device__ __forceinline__ void hbs_o1(const MolView &m, uint64_t key, int exclude_first, F &&f) {
+    OccMask o = mol_occ_mask(m, key);
+    unsigned j = 0;
+    uint32_t am = o.a;
+    if (exclude_first > 0) am &= am - 1;
+    while (am) {
+        f(j++, m.s_tens[fr_ctz(am)]);
+        am &= am - 1;
     }
-    oi++;
-    curr = oi <= ne ? occ[oi] : 255;
-    for (unsigned k = o1s + 1; k < M; k++) {
-        if (k + offset == curr) {
-            if (oi < ne - 1) {
-                oi++;
-                curr = occ[oi];
-            }
-        } else {
-            p[pi] = m.exch_sqrt[FR_TRI_NODIAG(o1s, k)];
-            norm += p[pi];
-            pi++;
-        }
+    uint32_t bm = o.b;
+    while (bm) {
+        f(j++, m.s_tens[fr_ctz(bm)]);
+        bm &= bm - 1;
     }
-    if (exclude_first) {
-        norm -= p[0];
-        p[0] = 0;
-    }
-    double inv = 1. / norm;
-    for (unsigned i = 0; i < pi; i++) p[i] *= inv;
-    return norm / m.exch_norms[o1s];
 }
-// calc_u2_probs :322-365
-__host__ __device__ inline double hb_u2_probs(const MolView &m, double *p, unsigned o1_orb, unsigned o2_orb,
-                                              unsigned u1_orb, unsigned *len) {
+// calc_o2_probs_half :236-270: entries for the electrons before o1_idx
+template <class F>
+__host__ __device__ __forceinline__ void hbs_o2_half(const MolView &m, uint64_t key, unsigned o1_idx, F &&f) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb, h = ne / 2;
+    OccMask o = mol_occ_mask(m, key);
+    unsigned o1 = mol_elec_orb(m, o, o1_idx);
+    unsigned upper = h > o1_idx ? o1_idx : h, j = 0;
+    uint32_t am = o.a;
+    for (; j < upper; j++) {
+        unsigned q = fr_ctz(am);
+        am &= am - 1;
+        f(j, o1 < M ? m.d_same[FR_TRI_NODIAG(q, o1)] : m.d_diff[(o1 - M) * M + q]);
+    }
+    uint32_t bm = o.b;
+    for (j = h; j < o1_idx; j++) {
+        unsigned q = fr_ctz(bm);
+        bm &= bm - 1;
+        f(j, o1 < M ? m.d_diff[o1 * M + q] : m.d_same[FR_TRI_NODIAG(q, o1 - M)]);
+    }
+}
+// calc_o2_probs :203-233: ne entries in index order (entry o1_idx is 0)
+template <class F>
+__host__ __device__ __forceinline__ void hbs_o2(const MolView &m, uint64_t key, unsigned o1_idx, F &&f) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb, h = ne / 2;
+    OccMask o = mol_occ_mask(m, key);
+    unsigned o1 = mol_elec_orb(m, o, o1_idx), o1_spin = o1 / M, o1s = o1 % M;
+    for (unsigned j = 0; j < ne; j++) {
+        unsigned q = mol_elec_orb(m, o, j) % M;
+        double raw;
+        if (j / h != o1_spin) raw = m.d_diff[o1s * M + q];
+        else if (j < o1_idx) raw = m.d_same[FR_TRI_NODIAG(q, o1s)];
+        else if (j > o1_idx) raw = m.d_same[FR_TRI_NODIAG(o1s, q)];
+        else raw = 0;
+        f(j, raw);
+    }
+}
+// its norm is accumulated opposite-spin block first, then the same-spin entries (:211-224)
+__host__ __device__ __forceinline__ double hbs_o2_norm(const MolView &m, uint64_t key, unsigned o1_idx) {
+    const unsigned ne = m.d.n_elec, M = m.d.n_orb, h = ne / 2;
+    OccMask o = mol_occ_mask(m, key);
+    unsigned o1 = mol_elec_orb(m, o, o1_idx), o1_spin = o1 / M, o1s = o1 % M;
+    double norm = 0;
+    unsigned off = (1 - o1_spin) * h;
+    for (unsigned j = off; j < h + off; j++) norm += m.d_diff[o1s * M + mol_elec_orb(m, o, j) % M];
+    off = o1_spin * h;
+    for (unsigned j = off; j < o1_idx; j++) norm += m.d_same[FR_TRI_NODIAG(mol_elec_orb(m, o, j) % M, o1s)];
+    for (unsigned j = o1_idx + 1; j < h + off; j++) norm += m.d_same[FR_TRI_NODIAG(o1s, mol_elec_orb(m, o, j) % M)];
+    return norm;
+}
+// calc_u1_probs :273-319: one entry per virtual orbital of o1's spin, ascending (raw values; the caller applies
+// exclude_first: norm -= raw_0, entry 0 = 0)
+template <class F>
+__host__ __device__ __forceinline__ void hbs_u1(const MolView &m, uint64_t key, unsigned o1_orb, F &&f) {
+    const unsigned M = m.d.n_orb;
+    OccMask o = mol_occ_mask(m, key);
+    unsigned o1s = o1_orb % M;
+    uint32_t vm = ~(o1_orb / M ? o.b : o.a) & (uint32_t)((1ull << M) - 1);
+    unsigned j = 0;
+    while (vm) {
+        unsigned k = fr_ctz(vm);
+        vm &= vm - 1;
+        f(j++, m.exch_sqrt[k < o1s ? FR_TRI_NODIAG(k, o1s) : FR_TRI_NODIAG(o1s, k)]);
+    }
+}
+__host__ __device__ __forceinline__ double hbs_u2_weight(const MolView &m, unsigned o2s, unsigned u2) {
+    if (o2s == u2) return m.diag_sqrt[o2s];
+    unsigned mn = o2s < u2 ? o2s : u2, mx = o2s > u2 ? o2s : u2;
+    return m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
+}
+// calc_u2_probs :322-365: one entry per orbital of the irrep that completes the double (0 for u2 == u1, same spin)
+template <class F>
+__host__ __device__ __forceinline__ void hbs_u2(const MolView &m, unsigned o1_orb, unsigned o2_orb, unsigned u1_orb, F &&f) {
     const unsigned M = m.d.n_orb;
     unsigned o2s = o2_orb % M, u1s = u1_orb % M;
     bool same = (o1_orb / M) == (o2_orb / M);
     unsigned irrep = m.symm[o1_orb % M] ^ m.symm[o2s] ^ m.symm[u1s];
     unsigned num = mol_lookup(m, irrep, 0);
-    *len = num;
-    double norm = 0;
     for (unsigned i = 0; i < num; i++) {
         unsigned u2 = mol_lookup(m, irrep, i + 1);
-        if ((same && u2 != u1s) || !same) {
-            if (o2s == u2) {
-                p[i] = m.diag_sqrt[o2s];
-            } else {
-                unsigned mn = o2s < u2 ? o2s : u2, mx = o2s > u2 ? o2s : u2;
-                p[i] = m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
-            }
-            norm += p[i];
-        } else {
-            p[i] = 0;
-        }
+        f(i, ((same && u2 != u1s) || !same) ? hbs_u2_weight(m, o2s, u2) : 0.0);
     }
-    if (norm != 0) {
-        double inv = 1 / norm;
-        for (unsigned i = 0; i < num; i++) {
-            unsigned u2 = mol_lookup(m, irrep, i + 1);
-            if ((same && u2 != u1s) || !same) p[i] *= inv;
-        }
-    }
-    return norm / m.exch_norms[o2s];
 }
-// calc_u2_probs_half :368-412
-__host__ __device__ inline double hb_u2_probs_half(const MolView &m, double *p, unsigned o1_orb, unsigned o2_orb,
-                                                   unsigned u1_orb, uint64_t det, unsigned *len) {
+// calc_u2_probs_half :368-412: stops at u2 >= u1 for same-spin pairs; occupied u2 get 0
+template <class F>
+__host__ __device__ __forceinline__ void hbs_u2_half(const MolView &m, unsigned o1_orb, unsigned o2_orb, unsigned u1_orb,
+                                                     uint64_t det, F &&f) {
     const unsigned M = m.d.n_orb;
     unsigned o2s = o2_orb % M, u1s = u1_orb % M, u2_spin = o2_orb / M;
     bool same = (o1_orb / M) == u2_spin;
     unsigned irrep = m.symm[o1_orb % M] ^ m.symm[o2s] ^ m.symm[u1s];
     unsigned num = mol_lookup(m, irrep, 0);
-    double norm = 0;
-    unsigned i;
-    for (i = 0; i < num; i++) {
+    for (unsigned i = 0; i < num; i++) {
         unsigned u2 = mol_lookup(m, irrep, i + 1);
         if (same && u2 >= u1s) break;
-        if (((same && u2 != u1s) || !same) && !fr_read_bit(det, u2 + M * u2_spin)) {
-            if (o2s == u2) {
-                p[i] = m.diag_sqrt[o2s];
-            } else {
-                unsigned mn = o2s < u2 ? o2s : u2, mx = o2s > u2 ? o2s : u2;
-                p[i] = m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
-            }
-            norm += p[i];
-        } else {
-            p[i] = 0;
-        }
+        bool ok = ((same && u2 != u1s) || !same) && !fr_read_bit(det, u2 + M * u2_spin);
+        f(i, ok ? hbs_u2_weight(m, o2s, u2) : 0.0);
     }
-    *len = i;
+}
+
+// Array forms with the reference's signatures and return values (parity entry points, finalize-free code).
+__host__ __device__ __forceinline__ uint64_t mol_key_of_occ(const MolView &m, const uint8_t *occ) {
+    uint64_t k = 0;
+    for (unsigned i = 0; i < m.d.n_elec; i++) k |= 1ull << occ[i];
+    return k;
+}
+__host__ __device__ inline double hb_o1_probs(const MolView &m, double *p, const uint8_t *occ, int exclude_first) {
+    uint64_t key = mol_key_of_occ(m, occ);
+    double norm = 0;
+    unsigned n = 0;
+    hbs_o1(m, key, exclude_first, [&](unsigned j, double raw) { p[j] = raw; norm += raw; n = j + 1; });
+    double inv = 1. / norm;
+    for (unsigned j = 0; j < n; j++) p[j] *= inv;
+    return norm / m.d.s_norm;
+}
+__host__ __device__ inline double hb_o2_probs(const MolView &m, double *p, const uint8_t *occ, unsigned o1_idx) {
+    uint64_t key = mol_key_of_occ(m, occ);
+    double norm = hbs_o2_norm(m, key, o1_idx), inv = 1. / norm;
+    hbs_o2(m, key, o1_idx, [&](unsigned j, double raw) { p[j] = raw * inv; });
+    return norm / m.s_tens[occ[o1_idx] % m.d.n_orb];
+}
+__host__ __device__ inline double hb_o2_probs_half(const MolView &m, double *p, const uint8_t *occ, unsigned o1_idx) {
+    uint64_t key = mol_key_of_occ(m, occ);
+    double norm = 0;
+    hbs_o2_half(m, key, o1_idx, [&](unsigned j, double raw) { p[j] = raw; norm += raw; });
+    double inv = 1. / norm;
+    for (unsigned j = 0; j < o1_idx; j++) p[j] *= inv;
+    return norm / m.s_tens[occ[o1_idx] % m.d.n_orb];
+}
+__host__ __device__ inline double hb_u1_probs(const MolView &m, double *p, unsigned o1_orb, const uint8_t *occ,
+                                              int exclude_first) {
+    uint64_t key = mol_key_of_occ(m, occ);
+    double norm = 0;
+    unsigned n = 0;
+    hbs_u1(m, key, o1_orb, [&](unsigned j, double raw) { p[j] = raw; norm += raw; n = j + 1; });
+    if (exclude_first) {
+        norm -= p[0];
+        p[0] = 0;
+    }
+    double inv = 1. / norm;
+    for (unsigned j = 0; j < n; j++) p[j] *= inv;
+    return norm / m.exch_norms[o1_orb % m.d.n_orb];
+}
+__host__ __device__ inline double hb_u2_probs(const MolView &m, double *p, unsigned o1_orb, unsigned o2_orb,
+                                              unsigned u1_orb, unsigned *len) {
+    double norm = 0;
+    unsigned n = 0;
+    hbs_u2(m, o1_orb, o2_orb, u1_orb, [&](unsigned j, double raw) { p[j] = raw; norm += raw; n = j + 1; });
+    *len = mol_lookup(m, m.symm[o1_orb % m.d.n_orb] ^ m.symm[o2_orb % m.d.n_orb] ^ m.symm[u1_orb % m.d.n_orb], 0);
     if (norm != 0) {
         double inv = 1 / norm;
-        for (unsigned k = 0; k < i; k++) p[k] *= inv;
+        for (unsigned j = 0; j < n; j++) p[j] *= inv;
     }
-    return norm / m.exch_norms[o2s];
+    return norm / m.exch_norms[o2_orb % m.d.n_orb];
+}
+__host__ __device__ inline double hb_u2_probs_half(const MolView &m, double *p, unsigned o1_orb, unsigned o2_orb,
+                                                   unsigned u1_orb, uint64_t det, unsigned *len) {
+    double norm = 0;
+    unsigned n = 0;
+    hbs_u2_half(m, o1_orb, o2_orb, u1_orb, det, [&](unsigned j, double raw) { p[j] = raw; norm += raw; n = j + 1; });
+    *len = n;
+    if (norm != 0) {
+        double inv = 1 / norm;
+        for (unsigned j = 0; j < n; j++) p[j] *= inv;
+    }
+    return norm / m.exch_norms[o2_orb % m.d.n_orb];
 }
 
 // ---- a9: total weights -----------------------------------------------------------------------------------------
