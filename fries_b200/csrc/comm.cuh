@@ -15,7 +15,7 @@
 #include "common.cuh"
 
 #define FR_MAX_RANKS 8
-#define FR_COMM_PAYLOAD 4  // doubles per slot
+#define FR_COMM_PAYLOAD 12  // doubles per slot
 
 struct CommView {
     int n_ranks, rank;
@@ -79,6 +79,42 @@ __device__ __forceinline__ void comm_allgather(const CommView &cm, CommCursor &c
         out_d0[q] = slot[0];
         out_d1[q] = slot[1];
         out_c[q] = (unsigned long long)__double_as_longlong(slot[2]);
+    }
+    __syncthreads();
+    cur.e = e;
+}
+
+// All-gather of n <= FR_COMM_PAYLOAD doubles per rank.  out is shared memory [n][FR_MAX_RANKS].
+__device__ __forceinline__ void comm_allgather_v(const CommView &cm, CommCursor &cur, const double *vals, int n,
+                                                 double (*out)[FR_MAX_RANKS]) {
+    if (cm.n_ranks <= 1) {
+        if (threadIdx.x == 0)
+            for (int k = 0; k < n; k++) out[k][0] = vals[k];
+        __syncthreads();
+        return;
+    }
+    const unsigned long long e = cur.e + 1;
+    const int par = (int)(e & 1);
+    if (blockIdx.x == 0 && threadIdx.x < cm.n_ranks) {
+        int p = threadIdx.x;
+        double *slot = cm.inbox[p] + ((size_t)par * cm.n_ranks + cm.rank) * FR_COMM_PAYLOAD;
+        for (int k = 0; k < n; k++) slot[k] = vals[k];
+        __threadfence_system();
+        *((volatile unsigned long long *)(cm.flags[p] + (size_t)par * cm.n_ranks + cm.rank)) = e;
+    }
+    if (threadIdx.x < cm.n_ranks) {
+        int q = threadIdx.x;
+        volatile unsigned long long *f = cm.flags[cm.rank] + (size_t)par * cm.n_ranks + q;
+        long long t0 = clock64();
+        while (*f < e) {
+            if (clock64() - t0 > 20000000000ll) {
+                *cm.error = e;
+                break;
+            }
+        }
+        __threadfence_system();
+        const volatile double *slot = cm.inbox[cm.rank] + ((size_t)par * cm.n_ranks + q) * FR_COMM_PAYLOAD;
+        for (int k = 0; k < n; k++) out[k][q] = slot[k];
     }
     __syncthreads();
     cur.e = e;

@@ -232,6 +232,49 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
     return sh[32];
 }
 
+// fused (double, u64) block sum: 3 barriers instead of 6.  shd / shc hold 33 entries each.
+__device__ __forceinline__ void block_sum_pair(double &d, unsigned long long &c, double *shd, unsigned long long *shc) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        d += __shfl_down_sync(0xffffffffu, d, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+        shd[w] = d;
+        shc[w] = c;
+    }
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < nw ? shd[lane] : 0.0;
+        unsigned long long u = lane < nw ? shc[lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t += __shfl_down_sync(0xffffffffu, t, o);
+            u += __shfl_down_sync(0xffffffffu, u, o);
+        }
+        if (lane == 0) {
+            shd[32] = t;
+            shc[32] = u;
+        }
+    }
+    __syncthreads();
+    d = shd[32];
+    c = shc[32];
+}
+// every lane of the warp obtains the same sum (fixed butterfly: identical in every warp of every CTA)
+__device__ __forceinline__ double warp_allsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_allsum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // fixed-order sum of `n` per-block partials, executed redundantly by every block after a grid sync;
 // every block obtains the bit-identical result.
 __device__ __forceinline__ double grid_partial_sum(const double *part, int n, double *sh) {

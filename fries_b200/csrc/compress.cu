@@ -2,26 +2,31 @@
 #include "compress.cuh"
 
 // ---------------------------------------------------------------------------------------------------
-// find_preserve (compress_utils.cpp:29-105) as threshold rounds: an element is preserved once
-// |v| >= R / n_left where R is the one-norm of what is not yet preserved.  The reference pops a heap
-// per rank and re-syncs R across ranks every round; one CTA-chunk here = one "rank".
-// Traffic per round: 8 B/element (values; keep flags are 1 B and stay in L2).
+// find_preserve (compress_utils.cpp:29-105).  The reference pops a max-heap per rank: an element is preserved
+// when |v| >= R / n_left (R = one-norm of what is not yet preserved), and R, n_left are re-synchronised across
+// ranks every round.  That is Newton's iteration on the concave function g(t) = R(t) - t n(t) from above; its
+// state is a single threshold (preserved = {|v| >= thr}), so the rounds here are read-only passes.  Each pass
+// probes FP_PROBES thresholds t_k = (R / n_left) 2^-k at once; the lowest probe that is still at or above its
+// own Newton image (t_k >= R_k / n_k, i.e. not below the fixed point) becomes the new threshold, which skips
+// several Newton steps per grid barrier.  Keep flags are written by the exact recomputation pass that the
+// reference also performs when a round preserves nothing (:78-90).
+// Traffic per round: 8 B/element (values only).
 // ---------------------------------------------------------------------------------------------------
+#define FP_PROBES 4
 __global__ void __launch_bounds__(FR_COMP_BLOCK)
 find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned long long *__restrict__ n_ptr,
                      unsigned n_samp_in, uint8_t *__restrict__ keep, double *part_d, unsigned long long *part_c,
                      CompState *st, CommView cm) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sh_x0[FR_MAX_RANKS], sh_x1[FR_MAX_RANKS];
-    __shared__ unsigned long long sh_xc[FR_MAX_RANKS];
+    __shared__ double sh_x[2 * FP_PROBES + 1][FR_MAX_RANKS];
+    __shared__ double sh_d[FP_PROBES * 33 + 1];
+    __shared__ unsigned long long sh_c[FP_PROBES * 33 + 1];
     CommCursor cur = comm_begin(cm);
     const bool multi = cm.n_ranks > 1;
     if (n_ptr) {  // resident pipeline: the element count lives on the device
         unsigned long long dn = *n_ptr;
         if (dn < n) n = (size_t)dn;
     }
-    __shared__ double sh_d[34];
-    __shared__ unsigned long long sh_c[34];
     GridRed red{part_d, part_c, 0, (int)gridDim.x, sh_d, sh_c};
     size_t chunk = (n + gridDim.x - 1) / gridDim.x;
     chunk = (chunk + 31) & ~(size_t)31;
@@ -29,65 +34,122 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
     const size_t hi = lo + chunk < n ? lo + chunk : n;
 
     double s = 0;
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        s += fabs(vals[i]);
-        keep[i] = 0;
-    }
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += fabs(vals[i]);
     unsigned long long dummy = 0;
     grid_reduce(grid, red, s, dummy);
     double loc = s, R_next = s;
     if (multi) {  // *global_norm = sum_mpi(loc_one_norm) (:50)
+        comm_allgather_v(cm, cur, &s, 1, sh_x);
         double before;
-        comm_allgather(cm, cur, s, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
-        comm_sum(cm, sh_x0, R_next, before);
+        comm_sum(cm, sh_x[0], R_next, before);
     }
     const double glob_total = R_next;
     unsigned nrem = n_samp_in;
     unsigned long long glob_sampled = 1, kept_total = 0;
     bool recalc = false;
-    double R = 0;
+    double R = 0, thr = INFINITY, fresh_loc = 0;
     unsigned rounds = 0;
-    while (glob_sampled > 0) {
+    while (glob_sampled > 0 && rounds < 100000) {  // the bound only guards against a corrupted reduction
         R = R_next;
-        double rem = 0;
-        unsigned long long cnt = 0;
+        double sk[FP_PROBES];
+        unsigned long long ck[FP_PROBES];
+        double tk[FP_PROBES];
+#pragma unroll
+        for (int k = 0; k < FP_PROBES; k++) {
+            sk[k] = 0;
+            ck[k] = 0;
+        }
+        tk[0] = R / nrem;  // glob_one_norm / (*n_samp - loc_sampled), loc_sampled stale (:59)
+#pragma unroll
+        for (int k = 1; k < FP_PROBES; k++) tk[k] = tk[k - 1] * 0.5;
         if (R >= 0) {
-            const double thr = R / nrem;  // glob_one_norm / (*n_samp - loc_sampled), loc_sampled stale
             for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-                if (!keep[i]) {
-                    double m = fabs(vals[i]);
-                    if (m >= thr) {
-                        keep[i] = 1;
-                        cnt++;
-                        rem += m;
-                    }
+                double m = fabs(vals[i]);
+                if (m < thr && m >= tk[FP_PROBES - 1]) {
+                    int kk = FP_PROBES - 1;
+#pragma unroll
+                    for (int k = FP_PROBES - 2; k >= 0; k--)
+                        if (m >= tk[k]) kk = k;
+                    // bucket kk = the highest probe the element reaches
+#pragma unroll
+                    for (int k = 0; k < FP_PROBES; k++)
+                        if (k == kk) {
+                            sk[k] += m;
+                            ck[k]++;
+                        }
                 }
             }
         }
-        grid_reduce(grid, red, rem, cnt);
-        loc -= rem;
-        R_next = loc;
-        if (multi) {  // glob_sampled = sum_mpi(loc_sampled) (:76); next glob_one_norm = sum_mpi(loc_one_norm) (:53)
-            double before;
-            comm_allgather(cm, cur, loc, 0.0, cnt, sh_x0, sh_x1, sh_xc);
-            comm_sum(cm, sh_x0, R_next, before);
-            cnt = comm_sum_u64(cm, sh_xc);
+        grid_reduce_vec<FP_PROBES>(grid, red, sk, ck, sh_d, sh_c);
+        // cumulative over the probes: everything at or above t_k
+#pragma unroll
+        for (int k = 1; k < FP_PROBES; k++) {
+            sk[k] += sk[k - 1];
+            ck[k] += ck[k - 1];
         }
-        glob_sampled = cnt;
-        nrem -= (unsigned)cnt;
-        kept_total += cnt;
+        double gS[FP_PROBES], locs_after[FP_PROBES];
+        unsigned long long gC[FP_PROBES];
+        if (multi) {
+            double pay[2 * FP_PROBES + 1];
+#pragma unroll
+            for (int k = 0; k < FP_PROBES; k++) {
+                pay[k] = sk[k];
+                pay[FP_PROBES + k] = (double)ck[k];
+            }
+            pay[2 * FP_PROBES] = loc;
+            comm_allgather_v(cm, cur, pay, 2 * FP_PROBES + 1, sh_x);
+#pragma unroll
+            for (int k = 0; k < FP_PROBES; k++) {
+                double a = 0, c = 0, l = 0;
+                for (int p = 0; p < cm.n_ranks; p++) {
+                    a += sh_x[k][p];
+                    c += sh_x[FP_PROBES + k][p];
+                    l += sh_x[2 * FP_PROBES][p] - sh_x[k][p];  // sum_mpi(loc_one_norm) after this probe's subtraction
+                }
+                gS[k] = a;
+                gC[k] = (unsigned long long)c;
+                locs_after[k] = l;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < FP_PROBES; k++) {
+                gS[k] = sk[k];
+                gC[k] = ck[k];
+                locs_after[k] = loc - sk[k];
+            }
+        }
+        int ks = 0;  // probe 0 is the reference's own test
+#pragma unroll
+        for (int k = 1; k < FP_PROBES; k++) {
+            if (gC[k] < nrem) {
+                double Rk = R - gS[k], nk = (double)(nrem - (unsigned)gC[k]);
+                if (tk[k] >= Rk / nk) ks = k;
+            }
+        }
+        if (gC[ks] > 0) thr = tk[ks];
+        loc -= sk[ks];
+        R_next = locs_after[ks];
+        glob_sampled = gC[ks];
+        nrem -= (unsigned)gC[ks];
+        kept_total += gC[ks];
         rounds++;
         if (glob_sampled == 0 && !recalc) {
+            // exact recomputation of the residual norm (:78-90) + keep flags of the current threshold
             double t = 0;
-            for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
-                if (!keep[i]) t += fabs(vals[i]);
+            for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+                double m = fabs(vals[i]);
+                bool kp = m >= thr;
+                keep[i] = kp ? 1 : 0;
+                if (!kp) t += m;
+            }
             grid_reduce(grid, red, t, dummy);
             loc = t;
             R_next = t;
+            fresh_loc = t;
             if (multi) {
+                comm_allgather_v(cm, cur, &t, 1, sh_x);
                 double before;
-                comm_allgather(cm, cur, t, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
-                comm_sum(cm, sh_x0, R_next, before);
+                comm_sum(cm, sh_x[0], R_next, before);
             }
             glob_sampled = 1;
             recalc = true;
@@ -95,15 +157,13 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
             recalc = false;
         }
     }
+    // the loop ends with a round that preserved nothing right after an exact recomputation, so the flags and
+    // the residual norm of that recomputation are final (the reference sums once more, :98-102: same quantity)
     double loc_final = 0;
     if (R < 1e-9) {
         nrem = 0;
     } else {
-        double t = 0;
-        for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
-            if (!keep[i]) t += fabs(vals[i]);
-        grid_reduce(grid, red, t, dummy);
-        loc_final = t;
+        loc_final = fresh_loc;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->loc_norm = loc_final;
@@ -138,8 +198,8 @@ sys_comp_kernel(double *__restrict__ vals, size_t n, const unsigned long long *_
     }
     __shared__ double sh_d[34];
     __shared__ unsigned long long sh_c[34];
-    __shared__ double sh_sd[34];
-    __shared__ unsigned long long sh_sc[34];
+    __shared__ double sh_sd[68];
+    __shared__ unsigned long long sh_sc[68];
     GridRed red{part_d, part_c, 0, (int)gridDim.x, sh_d, sh_c};
     size_t chunk = (n + gridDim.x - 1) / gridDim.x;
     chunk = (chunk + 31) & ~(size_t)31;
@@ -269,14 +329,15 @@ struct RedScratch {
     unsigned long long *pc;
     CompState *st;
 };
-// carve [2][grid] doubles + [2][grid] u64 + 2 CompState out of the context scratch, after `skip` bytes
+// carve [2][grid][FP_PROBES] doubles + the same in u64 + 2 CompState out of the context scratch, after `skip` bytes
 static int red_scratch(fries_ctx *c, int grid, size_t skip, RedScratch &r) {
-    size_t need = skip + (size_t)grid * 4 * 8 + 2 * sizeof(CompState) + 256;
+    size_t per = (size_t)grid * 2 * FP_PROBES * 8;
+    size_t need = skip + 2 * per + 2 * sizeof(CompState) + 512;
     FRIES_TRY(c->ensure_scratch(need));
     char *p = (char *)c->d_scratch + ((skip + 255) & ~(size_t)255);
     r.pd = (double *)p;
-    r.pc = (unsigned long long *)(p + (size_t)grid * 2 * 8);
-    r.st = (CompState *)(p + (size_t)grid * 4 * 8);
+    r.pc = (unsigned long long *)(p + per);
+    r.st = (CompState *)(p + 2 * per);
     return FRIES_OK;
 }
 

@@ -36,28 +36,100 @@ struct GridRed {
     unsigned long long *shc;  // 33 u64
 };
 
-// all-CTA reduction of (d, c); result in every thread of every CTA, bit-identical.
-__device__ __forceinline__ void grid_reduce(cg::grid_group &grid, GridRed &r, double &d, unsigned long long &c) {
-    d = block_sum(d, r.shd);
-    c = block_sum_u64(c, r.shc);
-    if (threadIdx.x == 0) {
-        __stcg(&r.pd[r.parity * r.nb + blockIdx.x], d);
-        __stcg(&r.pc[r.parity * r.nb + blockIdx.x], c);
+// K fused (double, u64) block sums with 3 barriers; results in every thread.  shd / shc: K x 33 entries.
+template <int K>
+__device__ __forceinline__ void block_sum_vec(double (&d)[K], unsigned long long (&c)[K], double *shd,
+                                              unsigned long long *shc) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d[k] += __shfl_down_sync(0xffffffffu, d[k], o);
+            c[k] += __shfl_down_sync(0xffffffffu, c[k], o);
+        }
     }
-    grid.sync();
-    double v = 0;
-    unsigned long long w = 0;
-    for (int i = threadIdx.x; i < r.nb; i += blockDim.x) {
-        v += __ldcg(&r.pd[r.parity * r.nb + i]);
-        w += __ldcg(&r.pc[r.parity * r.nb + i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            shd[k * 33 + w] = d[k];
+            shc[k * 33 + w] = c[k];
+        }
     }
-    d = block_sum(v, r.shd);
-    c = block_sum_u64(w, r.shc);
-    r.parity ^= 1;
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double t = lane < nw ? shd[k * 33 + lane] : 0.0;
+            unsigned long long u = lane < nw ? shc[k * 33 + lane] : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                t += __shfl_down_sync(0xffffffffu, t, o);
+                u += __shfl_down_sync(0xffffffffu, u, o);
+            }
+            if (lane == 0) {
+                shd[k * 33 + 32] = t;
+                shc[k * 33 + 32] = u;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        d[k] = shd[k * 33 + 32];
+        c[k] = shc[k * 33 + 32];
+    }
 }
 
-// Exclusive prefix over CTAs of per-CTA values (d, c): every CTA evaluates the same fixed scan
-// network over the nb partials, so all CTAs agree bitwise on every boundary.
+// all-CTA reduction of K (double, u64) pairs with ONE grid barrier; result in every thread of every CTA,
+// bit-identical (every CTA re-reduces the per-CTA partials in the same fixed order: one partial per thread, all
+// loads in flight at once, then the block tree).  The partial arrays hold 2 x nb x K entries.
+template <int K>
+__device__ __forceinline__ void grid_reduce_vec(cg::grid_group &grid, GridRed &r, double (&d)[K], unsigned long long (&c)[K],
+                                                double *shd, unsigned long long *shc, bool block_reduced = false) {
+    if (!block_reduced) block_sum_vec<K>(d, c, shd, shc);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            __stcg(&r.pd[((size_t)r.parity * r.nb + blockIdx.x) * K + k], d[k]);
+            __stcg(&r.pc[((size_t)r.parity * r.nb + blockIdx.x) * K + k], c[k]);
+        }
+    }
+    grid.sync();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        d[k] = 0;
+        c[k] = 0;
+    }
+    for (int i = threadIdx.x; i < r.nb; i += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            d[k] += __ldcg(&r.pd[((size_t)r.parity * r.nb + i) * K + k]);
+            c[k] += __ldcg(&r.pc[((size_t)r.parity * r.nb + i) * K + k]);
+        }
+    }
+    block_sum_vec<K>(d, c, shd, shc);
+    r.parity ^= 1;
+}
+__device__ __forceinline__ void grid_reduce(cg::grid_group &grid, GridRed &r, double &d, unsigned long long &c) {
+    double dd[1] = {d};
+    unsigned long long cc[1] = {c};
+    grid_reduce_vec<1>(grid, r, dd, cc, r.shd, r.shc);
+    d = dd[0];
+    c = cc[0];
+}
+// same, for values that are already reduced over the CTA (uniform in the CTA)
+__device__ __forceinline__ void grid_reduce_blk(cg::grid_group &grid, GridRed &r, double &d, unsigned long long &c) {
+    double dd[1] = {d};
+    unsigned long long cc[1] = {c};
+    grid_reduce_vec<1>(grid, r, dd, cc, r.shd, r.shc, true);
+    d = dd[0];
+    c = cc[0];
+}
+
+// Exclusive prefix over CTAs of per-CTA values (d, c) and their totals, identical arithmetic in every CTA.
+// sh_scan_d / sh_scan_c: 2 x 33 entries.
 __device__ __forceinline__ void grid_excl_scan(cg::grid_group &grid, GridRed &r, double d, unsigned long long c,
                                                double &ex_d, unsigned long long &ex_c, double &tot_d,
                                                unsigned long long &tot_c, double *sh_scan_d,
@@ -67,33 +139,25 @@ __device__ __forceinline__ void grid_excl_scan(cg::grid_group &grid, GridRed &r,
         __stcg(&r.pc[r.parity * r.nb + blockIdx.x], c);
     }
     grid.sync();
-    double run_d = 0;
-    unsigned long long run_c = 0;
-    double my_d = 0;
-    unsigned long long my_c = 0;
-    for (int base = 0; base < r.nb; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        double a = i < r.nb ? __ldcg(&r.pd[r.parity * r.nb + i]) : 0.0;
-        unsigned long long b = i < r.nb ? __ldcg(&r.pc[r.parity * r.nb + i]) : 0ull;
-        double ea, ta;
-        unsigned long long ec, tc;
-        block_excl_scan(a, b, ea, ec, ta, tc, sh_scan_d, sh_scan_c);
-        if (i == (int)blockIdx.x) {
-            sh_scan_d[33] = run_d + ea;
-            sh_scan_c[33] = run_c + ec;
+    double dv[2] = {0, 0};
+    unsigned long long cv[2] = {0, 0};
+    for (int i = threadIdx.x; i < r.nb; i += blockDim.x) {
+        double a = __ldcg(&r.pd[r.parity * r.nb + i]);
+        unsigned long long b = __ldcg(&r.pc[r.parity * r.nb + i]);
+        dv[1] += a;
+        cv[1] += b;
+        if (i < (int)blockIdx.x) {
+            dv[0] += a;
+            cv[0] += b;
         }
-        run_d += ta;
-        run_c += tc;
     }
+    block_sum_vec<2>(dv, cv, sh_scan_d, sh_scan_c);
+    ex_d = dv[0];
+    tot_d = dv[1];
+    ex_c = cv[0];
+    tot_c = cv[1];
     __syncthreads();
-    my_d = sh_scan_d[33];
-    my_c = sh_scan_c[33];
-    ex_d = my_d;
-    ex_c = my_c;
-    tot_d = run_d;
-    tot_c = run_c;
     r.parity ^= 1;
-    __syncthreads();
 }
 
 // seed_sys compress_utils.cpp:107-127 for a rank whose lower ranks hold `lbound` of the `glob` norm
@@ -138,8 +202,8 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh_d[34];
     __shared__ unsigned long long sh_c[34];
-    __shared__ double sh_sd[34];
-    __shared__ unsigned long long sh_sc[34];
+    __shared__ double sh_sd[68];
+    __shared__ unsigned long long sh_sc[68];
     GridRed red{b.part_d, b.part_c, 0, (int)gridDim.x, sh_d, sh_c};
 
     const size_t n = prov.count();
@@ -186,7 +250,10 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     double R = 0;
     unsigned rounds = 0;
     unsigned long long kept_total = 0;
-    while (glob_sampled > 0) {
+    // the residual norm of the last exact recomputation stays valid while no round preserves anything
+    bool fresh = false;
+    double fresh_cs = 0, fresh_loc = 0, fresh_G = 0, fresh_lb0 = 0;
+    while (glob_sampled > 0 && rounds < 100000) {  // the bound only guards against a corrupted reduction
         R = R_next;
         if (R < 0) break;
         const double wt_factor = (double)nrem;
@@ -243,38 +310,51 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         nrem -= (unsigned)cnt;
         kept_total += cnt;
         rounds++;
+        if (cnt) fresh = false;
         if (last_pass && glob_sampled) last_pass = 0;
         if (glob_sampled == 0 && !last_pass) {
             last_pass = 1;
             glob_sampled = 1;
             double t = 0;
             for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) t += b.wt_remain[i];
-            grid_reduce(grid, red, t, dummy);
+            block_sum_pair(t, dummy, sh_d, sh_c);
+            fresh_cs = t;  // this CTA's chunk of the residual weights = its share of the resampling line
+            grid_reduce_blk(grid, red, t, dummy);
             loc = t;
             R_next = t;
+            fresh_G = t;
+            fresh_lb0 = 0;
             if (multi) {
-                double before;
                 comm_allgather(cm, cur, t, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
-                comm_sum(cm, sh_x0, R_next, before);
+                comm_sum(cm, sh_x0, R_next, fresh_lb0);
+                fresh_G = R_next;
             }
+            fresh = true;
+            fresh_loc = t;
         }
     }
-    double loc_final = 0;
+    // ---- residual norm (find_keep_sub :267-275) and this rank's place on the resampling line (comp_sub :818,
+    // seed_sys :107-127): reuse the last exact recomputation when nothing was preserved after it ----
+    double loc_final = 0, cs = 0, G = 0, lbound0 = 0;
     if (R / nrem < 1e-8) {
         nrem = 0;
+    } else if (fresh) {
+        loc_final = fresh_loc;
+        cs = fresh_cs;
+        G = fresh_G;
+        lbound0 = fresh_lb0;
     } else {
         double t = 0;
         for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) t += b.wt_remain[i];
-        grid_reduce(grid, red, t, dummy);
+        block_sum_pair(t, dummy, sh_d, sh_c);
+        cs = t;
+        grid_reduce_blk(grid, red, t, dummy);
         loc_final = t;
-    }
-
-    // ---- resampling (sys_sub :702-794) ----
-    // loc_norms are all-gathered (comp_sub :818); this rank's grid starts at seed_sys(lbound0) (:107-127)
-    double G = loc_final, lbound0 = 0;
-    if (multi) {
-        comm_allgather(cm, cur, loc_final, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
-        comm_sum(cm, sh_x0, G, lbound0);
+        G = t;
+        if (multi) {
+            comm_allgather(cm, cur, loc_final, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+            comm_sum(cm, sh_x0, G, lbound0);
+        }
     }
     SysGrid sg;
     if (nrem > 0) {
@@ -294,12 +374,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         sg.n = 0;
     }
 
-    // pass 1: chunk sums of the residual weights -> canonical CTA boundaries
-    double cs = 0;
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        if (b.veff[i] != 0) cs += b.wt_remain[i];
-    }
-    cs = block_sum(cs, sh_d);
+    // CTA boundaries on the resampling line from the chunk sums of the residual weights
     double blk_lb, tot_lb;
     unsigned long long e0, e1;
     grid_excl_scan(grid, red, cs, 0ull, blk_lb, e0, tot_lb, e1, sh_sd, sh_sc);

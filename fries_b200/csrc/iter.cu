@@ -193,8 +193,8 @@ scan_counts_kernel(const uint32_t *__restrict__ counts, size_t n, unsigned long 
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh_d[34];
     __shared__ unsigned long long sh_c[34];
-    __shared__ double sh_sd[34];
-    __shared__ unsigned long long sh_sc[34];
+    __shared__ double sh_sd[68];
+    __shared__ unsigned long long sh_sc[68];
     GridRed red{part_d, part_c, 0, (int)gridDim.x, sh_d, sh_c};
     size_t chunk = (n + gridDim.x - 1) / gridDim.x;
     chunk = (chunk + 31) & ~(size_t)31;

@@ -113,8 +113,8 @@ compact_kernel(VecView v, uint64_t *__restrict__ keys_b, double *__restrict__ va
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh_d[34];
     __shared__ unsigned long long sh_c[34];
-    __shared__ double sh_sd[34];
-    __shared__ unsigned long long sh_sc[34];
+    __shared__ double sh_sd[68];
+    __shared__ unsigned long long sh_sc[68];
     __shared__ uint32_t s_scr[64];
     load_scr(s_scr, v.scr_vec);
     GridRed red{part_d, part_c, 0, (int)gridDim.x, sh_d, sh_c};
