@@ -267,6 +267,12 @@ def run_ours(args, cfg):
                 "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
                 "rounds": {"hbpp_stages": [int(x) for x in states[:5, 4]], "find_preserve": int(states[6, 4])},
                 "stage_items_in": [int(x) for x in states[:5, 7]], "stage_items_out": [int(x) for x in states[:5, 6]],
+                "stage_bracket": {"fast": [int(x) for x in states[:5, 10]], "candidates": [int(x) for x in states[:5, 9]]},
+                "stage_phase_us": {"what": "in-kernel %globaltimer of CTA 0: prep, preserved set, line scan, count, emit",
+                                   "us": [[round((states[s, 13 + k] - states[s, 12 + k]) / 1e3, 1) for k in range(5)]
+                                          for s in range(5)],
+                                   "candidate_rounds_us": [round((states[s, 18] - states[s, 13]) / 1e3, 1) for s in range(5)],
+                                   "apply_cut_us": [round((states[s, 19] - states[s, 18]) / 1e3, 1) for s in range(5)]},
                 "iter_algorithmic_GBps": round((96 * n_vec + 200 * cfg["mat_nonz"] + 56 * stp.n_spawned) / (ms_per_step * 1e-3) / 1e9, 2)}
 
     out = {

@@ -315,8 +315,9 @@ class Vec:
         return st
 
     def states(self):
-        """CompState records of the last iteration: dict name -> [8][...]"""
-        out = np.zeros((8, 8))
+        """CompState records of the last iteration [8 states][20]: loc_norm, glob_norm, new_norm, n_samp_left,
+        rounds, n_kept, n_out, n_in, anomalies, n_cand, fast, overflow, 8 phase time stamps (ns)"""
+        out = np.zeros((8, 20))
         check(lib.fries_hbpp_states(self.hb, ptr(out)))
         return out
 

@@ -132,6 +132,14 @@ __host__ __device__ __forceinline__ int fr_ctz(uint64_t x) {
     return __builtin_ctzll(x);
 #endif
 }
+// 32-bit overload: one FLO/BREV pair instead of the 64-bit emulation
+__host__ __device__ __forceinline__ int fr_ctz(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
 __host__ __device__ __forceinline__ bool fr_read_bit(uint64_t key, int b) { return (key >> b) & 1ull; }
 
 // find_bits (math_utils.c:62-98): ascending list of set bits

@@ -25,11 +25,29 @@ struct CompState {
     unsigned long long n_in;     // inputs seen
     unsigned long long overflow; // outputs that did not fit out_cap (dropped)
     unsigned long long anomalies;// FP-tie events (two grid points in one sub-element, clamped sub index)
+    unsigned long long n_cand;   // candidates collected inside the threshold bracket (bracket_solve)
+    unsigned long long fast;     // 1: the bracketed solve decided the preserved set, 0: plain rounds
+    unsigned long long ts[8];    // %globaltimer (ns) of CTA 0 at the phase boundaries of comp_sub_engine
 };
 
+__device__ __forceinline__ unsigned long long fr_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FR_STAMP(st, k)                                                  \
+    do {                                                                 \
+        if (blockIdx.x == 0 && threadIdx.x == 0) (st)->ts[k] = fr_globaltimer(); \
+    } while (0)
+
+// Layout of the partial arrays: [2 parities][nb CTAs][FR_RED_STRIDE]; the stride does not depend on how many values a
+// reduction carries, so that consecutive reductions of different widths never overlap (a CTA may already write the
+// partials of the next reduction while another one still reads those of the current one).
+#define FR_RED_STRIDE 8
+#define FR_RED_PART_LEN (2 * 1024 * FR_RED_STRIDE)  // entries per partial array: cooperative grids of <= 1024 CTAs
 struct GridRed {
-    double *pd;               // [2][nb]
-    unsigned long long *pc;   // [2][nb]
+    double *pd;               // [2][nb][FR_RED_STRIDE]
+    unsigned long long *pc;   // [2][nb][FR_RED_STRIDE]
     int parity;
     int nb;
     double *shd;              // 33 doubles of shared memory
@@ -92,8 +110,8 @@ __device__ __forceinline__ void grid_reduce_vec(cg::grid_group &grid, GridRed &r
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            __stcg(&r.pd[((size_t)r.parity * r.nb + blockIdx.x) * K + k], d[k]);
-            __stcg(&r.pc[((size_t)r.parity * r.nb + blockIdx.x) * K + k], c[k]);
+            __stcg(&r.pd[((size_t)r.parity * r.nb + blockIdx.x) * FR_RED_STRIDE + k], d[k]);
+            __stcg(&r.pc[((size_t)r.parity * r.nb + blockIdx.x) * FR_RED_STRIDE + k], c[k]);
         }
     }
     grid.sync();
@@ -105,8 +123,8 @@ __device__ __forceinline__ void grid_reduce_vec(cg::grid_group &grid, GridRed &r
     for (int i = threadIdx.x; i < r.nb; i += blockDim.x) {
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            d[k] += __ldcg(&r.pd[((size_t)r.parity * r.nb + i) * K + k]);
-            c[k] += __ldcg(&r.pc[((size_t)r.parity * r.nb + i) * K + k]);
+            d[k] += __ldcg(&r.pd[((size_t)r.parity * r.nb + i) * FR_RED_STRIDE + k]);
+            c[k] += __ldcg(&r.pc[((size_t)r.parity * r.nb + i) * FR_RED_STRIDE + k]);
         }
     }
     block_sum_vec<K>(d, c, shd, shc);
@@ -135,15 +153,15 @@ __device__ __forceinline__ void grid_excl_scan(cg::grid_group &grid, GridRed &r,
                                                unsigned long long &tot_c, double *sh_scan_d,
                                                unsigned long long *sh_scan_c) {
     if (threadIdx.x == 0) {
-        __stcg(&r.pd[r.parity * r.nb + blockIdx.x], d);
-        __stcg(&r.pc[r.parity * r.nb + blockIdx.x], c);
+        __stcg(&r.pd[((size_t)r.parity * r.nb + blockIdx.x) * FR_RED_STRIDE], d);
+        __stcg(&r.pc[((size_t)r.parity * r.nb + blockIdx.x) * FR_RED_STRIDE], c);
     }
     grid.sync();
     double dv[2] = {0, 0};
     unsigned long long cv[2] = {0, 0};
     for (int i = threadIdx.x; i < r.nb; i += blockDim.x) {
-        double a = __ldcg(&r.pd[r.parity * r.nb + i]);
-        unsigned long long b = __ldcg(&r.pc[r.parity * r.nb + i]);
+        double a = __ldcg(&r.pd[((size_t)r.parity * r.nb + i) * FR_RED_STRIDE]);
+        unsigned long long b = __ldcg(&r.pc[((size_t)r.parity * r.nb + i) * FR_RED_STRIDE]);
         dv[1] += a;
         cv[1] += b;
         if (i < (int)blockIdx.x) {
@@ -158,6 +176,196 @@ __device__ __forceinline__ void grid_excl_scan(cg::grid_group &grid, GridRed &r,
     tot_c = cv[1];
     __syncthreads();
     r.parity ^= 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Bracketed solve of the preservation threshold.
+//
+// The keep rounds of find_preserve / find_keep_sub are Newton's iteration from above on the threshold
+// t -> R(t) / n(t) (R = one-norm of what is not preserved, n = budget left); thresholds only decrease, the
+// preserved set is always "every element >= t", and the rounds may start from ANY such set that is inside the
+// final one.  Lemma used below: the set H = {x >= t_hi} is inside the final set whenever
+// t_hi >= R(H) / n(H) (downward induction over H in sorted order).  Given a bracket [t_lo, t_hi) around the
+// expected fixed point (the fixed point of the previous iteration of the same compression, widened by a
+// relative half-width h), ONE pass over the data yields the exact (count, sum) of H and the short list of
+// candidates inside the bracket; the Newton rounds then run on that list alone, redundantly in every CTA
+// (registers + block reductions, no grid barrier), with candidate sums accumulated as exact integers
+// (every x >= t_lo is a multiple of ulp(t_lo)), so the result does not depend on the order in which the
+// candidates were appended.  The bracket is valid iff H passes the lemma's test and t_lo is below the
+// final threshold; otherwise the caller falls back to the plain rounds over the full data.
+// ---------------------------------------------------------------------------------------------------
+#define FR_CAND_PER_THREAD 8
+#define FR_CAND_CAP (FR_COMP_BLOCK * FR_CAND_PER_THREAD)
+
+struct KeepPred {
+    double t;   // fixed-point threshold of the previous run (0: none)
+    double h;   // relative half-width of the bracket
+};
+
+struct CandList {
+    double *x;                  // [FR_CAND_CAP] candidate magnitudes
+    uint32_t *mult;             // [FR_CAND_CAP] multiplicities (uniform division: n_div pieces of equal size)
+    unsigned long long *count;  // appended so far (may exceed the capacity: then the bracket is invalid)
+};
+
+__device__ __forceinline__ void cand_append(const CandList &cl, double x, uint32_t mult) {
+    // once the list has overflowed the bracket is invalid anyway: stop hammering the counter
+    if (*(volatile unsigned long long *)cl.count > FR_CAND_CAP) return;
+    unsigned long long k = atomicAdd(cl.count, 1ull);
+    if (k < FR_CAND_CAP) {
+        cl.x[k] = x;
+        cl.mult[k] = mult;
+    }
+}
+
+struct BracketResult {
+    bool valid;
+    double x_cut;                   // preserved <=> x >= x_cut
+    double R;                       // one-norm of what is not preserved (by subtraction, as the reference's rounds)
+    unsigned nrem;                  // budget left
+    unsigned long long kept_cand;   // pieces preserved from the candidate list
+    unsigned rounds;
+};
+
+#ifdef FR_BRACKET_TIMING
+__device__ long long fr_bt[16];
+#define FR_BT(k)                                                    \
+    do {                                                            \
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (k) < 16) fr_bt[k] = clock64(); \
+    } while (0)
+#else
+#define FR_BT(k)
+#endif
+// shc: >= 17 u64 of shared memory (shd unused, kept for symmetry).  Uniform result in every thread of every CTA.
+// All sums are integers (counts; candidate magnitudes in units of ulp(t_lo), as eight 16-bit limbs so that a warp's
+// total fits the 32-bit redux instruction), reduced with redux.sync + shared-memory atomics: order-independent,
+// and far cheaper than 64-bit shuffle trees (SHFL issues once per cycle per SM).
+__device__ __forceinline__ BracketResult bracket_solve(const CandList &cl, double R0, long long nrem0, double t_lo,
+                                                       double t_hi, double *shd, unsigned long long *shc) {
+    (void)shd;
+    BracketResult res;
+    res.valid = false;
+    res.x_cut = t_hi;
+    res.R = R0;
+    res.nrem = 0;
+    res.kept_cand = 0;
+    res.rounds = 0;
+    FR_BT(0);
+    const unsigned long long ncand = __ldcg(cl.count);
+    if (ncand > FR_CAND_CAP || nrem0 <= 0 || nrem0 > 0xffffffffll) return res;
+    if (!(t_hi * (double)nrem0 >= R0)) return res;  // H is not certainly preserved
+    // ulp(t_lo) = 2^(E_lo - 1075) with E_lo the biased exponent; every candidate is an integer multiple of it
+    const int E_lo = (int)((__double_as_longlong(t_lo) >> 52) & 0x7ff);
+    if (E_lo < 64 || E_lo > 1900) return res;  // (sub)normal extremes: leave to the plain rounds
+    const double ulp_lo = __longlong_as_double((long long)(E_lo - 52) << 52);
+    double x[FR_CAND_PER_THREAD];
+    uint32_t mu[FR_CAND_PER_THREAD];
+    unsigned state = 0;  // bit k: candidate k of this thread not yet preserved
+#pragma unroll
+    for (int k = 0; k < FR_CAND_PER_THREAD; k++) {
+        unsigned idx = threadIdx.x + k * FR_COMP_BLOCK;
+        x[k] = 0;
+        mu[k] = 0;
+        if (idx < ncand) {
+            x[k] = __ldcg(cl.x + idx);
+            mu[k] = __ldcg(cl.mult + idx);
+            state |= 1u << k;
+        }
+    }
+    // shared accumulators (32-bit: native shared-memory atomics): [buf][0..2] count limbs, [buf][3..10] sum limbs,
+    // 16 bits each (a warp's total < 2^21, a CTA's < 2^25).  Two buffers alternate so that one barrier per round suffices.
+    unsigned *acc = reinterpret_cast<unsigned *>(shc);
+    unsigned long long *acc_min = shc + 16;
+    if (threadIdx.x < 24) acc[threadIdx.x] = 0;
+    if (threadIdx.x == 24) *acc_min = 0x7ff0000000000000ull;  // +inf
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    unsigned long long cnt_tot = 0;
+    unsigned __int128 sum_tot = 0;
+    double R = R0;
+    unsigned long long nrem = (unsigned long long)nrem0;
+    double xmin = INFINITY;
+    FR_BT(1);
+    for (unsigned round = 0; round < 4096; round++) {
+        unsigned *a = acc + 12 * (round & 1);
+        unsigned long long c = 0;
+        unsigned __int128 s = 0;
+        const double fac = (double)nrem;
+#pragma unroll
+        for (int k = 0; k < FR_CAND_PER_THREAD; k++) {
+            if (((state >> k) & 1u) && x[k] * fac >= R) {
+                state &= ~(1u << k);
+                c += mu[k];
+                // x / ulp(t_lo), exact: mantissa shifted by the exponent difference (0 or 1: x < t_hi < 2 t_lo)
+                const long long xb = __double_as_longlong(x[k]);
+                const unsigned long long ix = ((unsigned long long)(xb & 0xfffffffffffffll) | (1ull << 52))
+                                              << ((int)((xb >> 52) & 0x7ff) - E_lo);
+                s += (unsigned __int128)ix * mu[k];
+                xmin = fmin(xmin, x[k]);
+            }
+        }
+        if (__any_sync(0xffffffffu, c != 0)) {
+            const unsigned long long slo = (unsigned long long)s, shi = (unsigned long long)(s >> 64);
+#pragma unroll
+            for (int q = 0; q < 11; q++) {
+                unsigned v = q < 3 ? (unsigned)((c >> (16 * q)) & 0xffffu)
+                                   : q < 7 ? (unsigned)((slo >> (16 * (q - 3))) & 0xffffu)
+                                           : (unsigned)((shi >> (16 * (q - 7))) & 0xffffu);
+                if (__any_sync(0xffffffffu, v != 0)) {
+                    unsigned w = __reduce_add_sync(0xffffffffu, v);
+                    if (lane == 0) atomicAdd(&a[q], w);
+                }
+            }
+        }
+        // clear the other buffer for the next round (its readers passed the previous barrier)
+        if (threadIdx.x < 12) acc[12 * ((round & 1) ^ 1) + threadIdx.x] = 0;
+        __syncthreads();
+        res.rounds = round + 1;
+        const unsigned long long c_round = (unsigned long long)a[0] + ((unsigned long long)a[1] << 16) +
+                                           ((unsigned long long)a[2] << 32);
+        if (c_round == 0) break;
+        cnt_tot += c_round;
+        unsigned __int128 s_round = 0;
+#pragma unroll
+        for (int q = 7; q >= 0; q--) s_round = (s_round << 16) + a[3 + q];
+        sum_tot += s_round;
+        if (cnt_tot >= (unsigned long long)nrem0) return res;  // budget exhausted inside the bracket
+        nrem = (unsigned long long)nrem0 - cnt_tot;
+        double kept_sum = (double)(unsigned long long)(sum_tot >> 64) * 18446744073709551616.0 +
+                          (double)(unsigned long long)sum_tot;
+        R = R0 - kept_sum * ulp_lo;
+        FR_BT(2 + round);
+    }
+    FR_BT(6);
+    // smallest preserved candidate: positive doubles order like their bit patterns
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    if (lane == 0 && xmin < INFINITY) atomicMin(acc_min, (unsigned long long)__double_as_longlong(xmin));
+    __syncthreads();
+    xmin = __longlong_as_double((long long)*acc_min);
+    __syncthreads();
+    FR_BT(7);
+    res.x_cut = xmin < t_hi ? xmin : t_hi;
+    res.R = R;
+    res.nrem = (unsigned)nrem;
+    res.kept_cand = cnt_tot;
+    res.valid = t_lo * (double)nrem < R;  // nothing below the bracket can be preserved
+    return res;
+}
+
+// next bracket from this run's fixed point
+__device__ __forceinline__ void keep_pred_update(KeepPred *p, double t_prev, double h_prev, double t_fin,
+                                                 unsigned long long ncand) {
+    const double h_min = 5e-4, h_max = 0.05;
+    double h = 0.01;
+    if (t_prev > 0 && t_fin > 0) {
+        double drift = fabs(t_fin / t_prev - 1.0);
+        h = fmax(6.0 * drift, 0.6 * h_prev);
+        if (ncand > FR_CAND_CAP / 2) h = fmin(h, 0.5 * h_prev);
+    }
+    h = fmin(fmax(h, h_min), h_max);
+    p->t = (t_fin > 0 && isfinite(t_fin)) ? t_fin : 0.0;
+    p->h = h;
 }
 
 // seed_sys compress_utils.cpp:107-127 for a rank whose lower ranks hold `lbound` of the `glob` norm
@@ -188,6 +396,9 @@ struct CompSubBufs {
     unsigned long long *part_c;   // [2][grid]
     CompState *st;
     CommView cm;                  // n_ranks == 1: no cross-rank exchange
+    // bracketed threshold solve (optional): prediction carried between runs + candidate list
+    KeepPred *pred;
+    CandList cand;
 };
 
 // The hierarchical compression engine.  Provider P supplies
@@ -202,8 +413,8 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh_d[34];
     __shared__ unsigned long long sh_c[34];
-    __shared__ double sh_sd[68];
-    __shared__ unsigned long long sh_sc[68];
+    __shared__ double sh_sd[6 * 33];
+    __shared__ unsigned long long sh_sc[6 * 33];
     GridRed red{b.part_d, b.part_c, 0, (int)gridDim.x, sh_d, sh_c};
 
     const size_t n = prov.count();
@@ -218,8 +429,20 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     CommCursor cur = comm_begin(cm);
     const bool multi = cm.n_ranks > 1;
 
-    // ---- phase 0: effective weights (find_keep_sub :134-137) ----
-    double s = 0;
+    FR_STAMP(b.st, 0);
+    // bracket around the expected fixed point (see bracket_solve); uniform over the grid
+    double t_pred = 0, h_pred = 0;
+    if (b.pred) {
+        t_pred = __ldcg(&b.pred->t);
+        h_pred = __ldcg(&b.pred->h);
+    }
+    const bool try_fast = !multi && t_pred > 0 && h_pred > 0 && h_pred < 0.25;
+    const double t_lo = t_pred * (1.0 - h_pred), t_hi = t_pred * (1.0 + h_pred);
+
+    // ---- phase 0: effective weights (find_keep_sub :134-137); with a bracket also the exact (count, sum) of
+    // everything at or above it and the list of candidates inside it ----
+    double s = 0, s_hi = 0;
+    unsigned long long c_hi = 0;
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         double v, rinv = 1.0;
         uint32_t nd, ns;
@@ -231,9 +454,39 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         b.nsub[i] = (uint8_t)ns;
         b.keep[i] = 0;
         s += v;
+        if (try_fast && v >= t_lo) {
+            if (nd > 0) {
+                double x = v / nd;
+                if (x >= t_hi) {
+                    c_hi += nd;
+                    s_hi += v;
+                } else if (x >= t_lo) {
+                    cand_append(b.cand, x, nd);
+                }
+            } else {
+                prov.visit(i, rinv, [&](uint32_t j, double wj) {
+                    if (j < ns) {
+                        double x = v * wj;
+                        if (x >= t_hi) {
+                            c_hi++;
+                            s_hi += x;
+                        } else if (x >= t_lo) {
+                            cand_append(b.cand, x, 1u);
+                        }
+                    }
+                });
+            }
+        }
     }
     unsigned long long dummy = 0;
-    grid_reduce(grid, red, s, dummy);
+    {
+        double dd[2] = {s, s_hi};
+        unsigned long long cc[2] = {c_hi, 0ull};
+        grid_reduce_vec<2>(grid, red, dd, cc, sh_sd, sh_sc);
+        s = dd[0];
+        s_hi = dd[1];
+        c_hi = cc[0];
+    }
     double loc = s;          // this rank's loc_one_norm
     double R_next = s;       // sum_mpi(loc_one_norm) for the coming round
     if (multi) {
@@ -243,6 +496,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         s = R_next;          // global one-norm (reported)
     }
 
+    FR_STAMP(b.st, 1);  // phase 0 done
     // ---- keep rounds (find_keep_sub :153-265) ----
     unsigned nrem = n_samp_in;
     unsigned long long glob_sampled = 1;
@@ -253,6 +507,67 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     // the residual norm of the last exact recomputation stays valid while no round preserves anything
     bool fresh = false;
     double fresh_cs = 0, fresh_loc = 0, fresh_G = 0, fresh_lb0 = 0;
+    unsigned long long n_cand = 0;
+    bool fast_done = false;
+    if (try_fast) {
+        // Newton rounds on the candidate list only (every CTA, redundantly), then ONE pass that applies the cut
+        n_cand = __ldcg(b.cand.count);
+        BracketResult br = bracket_solve(b.cand, s - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi, sh_sd, sh_sc);
+        FR_STAMP(b.st, 6);  // candidate rounds done
+        if (br.valid) {
+            const double x_cut = br.x_cut, fac = (double)br.nrem;
+            double t = 0;
+            unsigned long long kc = 0;
+            for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+                double v = b.veff[i];
+                double wr = v;
+                if (v >= x_cut || v * fac >= br.R) {  // the reference recomputes the residual of such an input (:206-262)
+                    uint32_t nd = b.ndiv[i];
+                    if (nd > 0) {
+                        if (v / nd >= x_cut) {
+                            b.keep[i] = 1;
+                            wr = 0;
+                            kc += nd;
+                        }
+                    } else {
+                        uint32_t ns = b.nsub[i], kb = 0;
+                        double sub_remain = 0;
+                        prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) {
+                            if (j < ns) {
+                                double x = v * wj;
+                                if (x >= x_cut) {
+                                    kb |= 1u << j;
+                                    kc++;
+                                } else {
+                                    sub_remain += x;
+                                }
+                            }
+                        });
+                        b.keep[i] = kb;
+                        wr = sub_remain;
+                    }
+                    b.wt_remain[i] = wr;
+                }
+                t += wr;
+            }
+            block_sum_pair(t, kc, sh_d, sh_c);
+            fresh_cs = t;
+            FR_STAMP(b.st, 7);  // cut applied (CTA 0)
+            grid_reduce_blk(grid, red, t, kc);
+            kept_total = c_hi + br.kept_cand;
+            if (kc != kept_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&b.st->anomalies, 1ull << 32);
+            nrem = br.nrem;
+            R = br.R;
+            rounds = br.rounds;
+            fresh = true;
+            fresh_loc = t;
+            fresh_G = t;
+            fresh_lb0 = 0;
+            fast_done = true;
+            glob_sampled = 0;  // skip the plain rounds
+            if (blockIdx.x == 0 && threadIdx.x == 0) b.st->fast = 1;
+        }
+    }
     while (glob_sampled > 0 && rounds < 100000) {  // the bound only guards against a corrupted reduction
         R = R_next;
         if (R < 0) break;
@@ -336,6 +651,8 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     // ---- residual norm (find_keep_sub :267-275) and this rank's place on the resampling line (comp_sub :818,
     // seed_sys :107-127): reuse the last exact recomputation when nothing was preserved after it ----
     double loc_final = 0, cs = 0, G = 0, lbound0 = 0;
+    if (b.pred && blockIdx.x == 0 && threadIdx.x == 0)
+        keep_pred_update(b.pred, try_fast ? t_pred : 0.0, h_pred, nrem > 0 ? R / nrem : 0.0, n_cand);
     if (R / nrem < 1e-8) {
         nrem = 0;
     } else if (fresh) {
@@ -374,11 +691,13 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         sg.n = 0;
     }
 
+    FR_STAMP(b.st, 2);  // preserved set decided
     // CTA boundaries on the resampling line from the chunk sums of the residual weights
     double blk_lb, tot_lb;
     unsigned long long e0, e1;
     grid_excl_scan(grid, red, cs, 0ull, blk_lb, e0, tot_lb, e1, sh_sd, sh_sc);
 
+    FR_STAMP(b.st, 3);
     // pass 2: per-input lower bound + number of outputs
     double carry = lbound0 + blk_lb;
     unsigned long long my_out = 0;
@@ -394,7 +713,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         if (act) {
             double start = carry + ex;
             b.lb[i] = start;
-            uint32_t k = 0;
+            uint32_t k = 0, code = 0;
             if (v != 0) {
                 uint32_t nd = b.ndiv[i];
                 double lbound = start + wr;
@@ -411,13 +730,17 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                     if (wr < v || g < lbound) {
                         uint32_t ns = b.nsub[i], kb = b.keep[i];
                         double sub_lb = lbound - wr;
+                        uint32_t n_kept_out = 0, s1 = 0, s2 = 0;
                         prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) {
                             if (j >= ns) return;
                             if (((kb >> j) & 1u) && wj != 0) {
                                 k++;
+                                n_kept_out++;
                             } else {
                                 sub_lb += v * wj;
                                 if (g < sub_lb && wj != 0) {
+                                    if (k == 0) s1 = j;
+                                    if (k == 1) s2 = j;
                                     k++;
                                     k0++;
                                     g = sg.point(k0);
@@ -425,10 +748,13 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                                 }
                             }
                         });
+                        // one or two resampled outputs and nothing preserved: remember the sub-indices so that the
+                        // emit pass does not have to regenerate the row (kcnt bits 30-31 = count, 16-20 / 21-25 = subs)
+                        if (n_kept_out == 0 && k >= 1 && k <= 2) code = (k << 30) | (s1 << 16) | (s2 << 21);
                     }
                 }
             }
-            b.kcnt[i] = k;
+            b.kcnt[i] = code ? code : k;
             my_out += k;
         }
         carry += tot;
@@ -438,6 +764,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     unsigned long long blk_off, tot_out;
     grid_excl_scan(grid, red, 0.0, my_out, d0, blk_off, d1, tot_out, sh_sd, sh_sc);
 
+    FR_STAMP(b.st, 4);  // count pass + offset scan done
     // pass 3: emit
     unsigned long long ocarry = blk_off;
     unsigned long long overflow = 0;
@@ -445,17 +772,12 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     for (size_t base = lo; base < hi; base += blockDim.x) {
         size_t i = base + threadIdx.x;
         bool act = i < hi;
-        uint32_t k = act ? b.kcnt[i] : 0;
+        const uint32_t code = act ? b.kcnt[i] : 0;
+        const uint32_t mode = code >> 30;
+        uint32_t k = mode ? mode : code;
         double ex, tot;
         unsigned long long ec, tc;
         block_excl_scan(0.0, (unsigned long long)k, ex, ec, tot, tc, sh_sd, sh_sc);
-        if (act && k > 0) {
-            unsigned long long o = ocarry + ec;
-            double v = b.veff[i];
-            uint32_t nd = b.ndiv[i];
-            double start = b.lb[i];
-            double wr = b.wt_remain[i];
-            double lbound = start + wr;
 #define FR_EMIT(VAL, SUB)                              \
     do {                                               \
         if (o < b.out_cap) {                           \
@@ -467,6 +789,17 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         }                                              \
         o++;                                           \
     } while (0)
+        if (act && mode) {  // one or two resampled outputs recorded by the count pass
+            unsigned long long o = ocarry + ec;
+            FR_EMIT(samp_val, (code >> 16) & 31u);
+            if (mode == 2) FR_EMIT(samp_val, (code >> 21) & 31u);
+        } else if (act && k > 0) {
+            unsigned long long o = ocarry + ec;
+            double v = b.veff[i];
+            uint32_t nd = b.ndiv[i];
+            double start = b.lb[i];
+            double wr = b.wt_remain[i];
+            double lbound = start + wr;
             if (nd > 0) {
                 if (b.keep[i]) {
                     double each = v / nd;
@@ -522,5 +855,15 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         b.st->n_in = n;
     }
     grid.sync();
+    FR_STAMP(b.st, 5);  // emit done
     comm_end(cm, cur);
 }
+
+// host launchers (compress.cu).  d_st must be zeroed by the caller; pred / cand_x / cand_m == nullptr: plain rounds.
+int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, const unsigned long long *d_n,
+                               unsigned n_samp, uint8_t *d_keep, CompState *d_st, double *pd, unsigned long long *pc,
+                               int grid, const fries_comm *comm, KeepPred *pred = nullptr, double *cand_x = nullptr,
+                               uint32_t *cand_m = nullptr);
+int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, const unsigned long long *d_n, uint8_t *d_keep,
+                          const double *d_in, double lbound0, double glob, long long n_samp, double rn, CompState *d_out,
+                          double *pd, unsigned long long *pc, int grid, const fries_comm *comm);

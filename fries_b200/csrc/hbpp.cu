@@ -359,13 +359,54 @@ int fries_hbpp_alloc(fries_ctx *c, size_t cap, fries_hbpp **out, bool stages) {
         }
         A(fin_val, cap); A(fin_det, cap); A(fin_orbs, cap);
     }
-    A(part_d, 4 * 1024); A(part_c, 4 * 1024); A(st, 8); A(n_scalar, 4); A(scal, 64);
+    A(part_d, FR_RED_PART_LEN); A(part_c, FR_RED_PART_LEN); A(st, 8); A(n_scalar, 4); A(scal, 64);
+    A(cand_x, FR_CAND_CAP); A(cand_m, FR_CAND_CAP); A(pred, 8);
 #undef A
+    if (rc == FRIES_OK && cudaMemset(hb->pred.p, 0, 8 * sizeof(KeepPred)) != cudaSuccess) {
+        fries_set_error("fries_hbpp_alloc: cudaMemset failed");
+        rc = FRIES_ERR_CUDA;
+    }
     if (rc != FRIES_OK) {
         delete hb;
         return rc;
     }
     *out = hb;
+    return FRIES_OK;
+}
+
+// Diagnostics: run every standalone compression `n` times on the same inputs and return the last run, so that the
+// parity tests can exercise the bracketed threshold solve (which needs the fixed point of a previous run).
+int fr_debug_repeat = 1;
+int fr_bracket_on = 1;
+extern "C" int fries_debug_set_repeat(int n) {
+    fr_debug_repeat = n < 1 ? 1 : n;
+    return FRIES_OK;
+}
+double fr_debug_perturb = 0;  // warm-up runs of a repeated standalone call see the values scaled by (1 + perturb)
+extern "C" int fries_debug_set_perturb(double rel) {
+    fr_debug_perturb = rel;
+    return FRIES_OK;
+}
+// scale a device array (warm-up runs of the repeated standalone calls)
+__global__ void fr_scale_kernel(double *v, size_t n, double f) {
+    // per-element factor 1 + (f - 1) u_i with u_i in [0, 2): the fixed point moves by about f - 1, not exactly
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double u = (double)(((unsigned)i * 2654435761u) >> 16) / 32768.0;
+        v[i] *= 1.0 + (f - 1.0) * u;
+    }
+}
+int fr_debug_upload_vals(fries_ctx *c, double *d_vals, const double *h_vals, size_t n, bool warmup) {
+    CUDA_TRY(cudaMemcpyAsync(d_vals, h_vals, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (warmup && fr_debug_perturb != 0 && n) fr_scale_kernel<<<256, 256, 0, c->stream>>>(d_vals, n, 1.0 + fr_debug_perturb);
+    return FRIES_OK;
+}
+int fr_last_fast = 0;  // number of compressions of the last standalone call decided by the bracketed solve
+extern "C" int fries_debug_last_fast(int *n_fast) {
+    if (n_fast) *n_fast = fr_last_fast;
+    return FRIES_OK;
+}
+extern "C" int fries_debug_set_bracket(int on) {
+    fr_bracket_on = on ? 1 : 0;
     return FRIES_OK;
 }
 
@@ -423,7 +464,8 @@ int fries_hbpp_stages_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys
         io.in_cap = hb->cap;
         CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->rinv.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
                          hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
-                         hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(hb->comm)};
+                         hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(hb->comm),
+                         fr_bracket_on ? hb->pred.p + s : nullptr, CandList{hb->cand_x.p, hb->cand_m.p, &hb->st.p[s].n_cand}};
         switch (s) {
             case 0: FRIES_TRY(launch_stage<0>(hb, mol, io, bufs, n_samp, u5[0])); break;
             case 1: FRIES_TRY(launch_stage<1>(hb, mol, io, bufs, n_samp, u5[1])); break;
@@ -497,12 +539,18 @@ extern "C" int fries_apply_hbpp_sys(fries_mol *mol, const uint64_t *h_keys, cons
     CU(cudaMemcpyAsync(keys.p, h_keys, n * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(vals.p, h_vals, n * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(hb->n_scalar.p, &n64, 8, cudaMemcpyHostToDevice, c->stream));
-    rc = fries_hbpp_stages_dev(hb, mol, keys.p, vals.p, hb->n_scalar.p, p_doub, new_hb, h_uniforms5, n_samp);
+    for (int rep = 0; rep < fr_debug_repeat && rc == FRIES_OK; rep++) {
+        rc = fr_debug_upload_vals(c, vals.p, h_vals, n, rep + 1 < fr_debug_repeat);
+        if (rc == FRIES_OK)
+            rc = fries_hbpp_stages_dev(hb, mol, keys.p, vals.p, hb->n_scalar.p, p_doub, new_hb, h_uniforms5, n_samp);
+    }
     if (rc == FRIES_OK) rc = fries_hbpp_finalize_dev(hb, mol, keys.p, p_doub, new_hb, nullptr);
     if (rc != FRIES_OK) return fail(rc);
     CompState st[6];
     CU(cudaMemcpyAsync(st, hb->st.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    fr_last_fast = 0;
+    for (int s = 0; s < 5; s++) fr_last_fast += (int)st[s].fast;
     for (int s = 0; s < 5; s++)
         if (st[s].overflow) {
             // the reference prints "insufficient memory allocated for matrix compression" (:732,768,814,862,913)
@@ -560,6 +608,8 @@ extern "C" int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, co
     CUDA_TRY(cudaMemcpyAsync(keys.p, h_keys, n * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(vals.p, h_vals, n * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(hb->n_scalar.p, &n64, 8, cudaMemcpyHostToDevice, c->stream));
+    for (int rep = 0; rep < fr_debug_repeat; rep++) {
+    FRIES_TRY(fr_debug_upload_vals(c, vals.p, h_vals, n, rep + 1 < fr_debug_repeat));
     CUDA_TRY(cudaMemsetAsync(hb->st.p, 0, 8 * sizeof(CompState), c->stream));
     for (int s = 0; s <= stage; s++) {
         int o = s & 1, p = o ^ 1;
@@ -572,7 +622,8 @@ extern "C" int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, co
         io.p_doub = p_doub; io.new_hb = new_hb; io.in_cap = hb->cap;
         CompSubBufs bufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->rinv.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
                          hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
-                         hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(hb->comm)};
+                         hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(hb->comm),
+                         fr_bracket_on ? hb->pred.p + s : nullptr, CandList{hb->cand_x.p, hb->cand_m.p, &hb->st.p[s].n_cand}};
         switch (s) {
             case 0: FRIES_TRY(launch_stage<0>(hb, mol, io, bufs, n_samp, h_uniforms5[0])); break;
             case 1: FRIES_TRY(launch_stage<1>(hb, mol, io, bufs, n_samp, h_uniforms5[1])); break;
@@ -580,6 +631,7 @@ extern "C" int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, co
             case 3: FRIES_TRY(launch_stage<3>(hb, mol, io, bufs, n_samp, h_uniforms5[3])); break;
             case 4: FRIES_TRY(launch_stage<4>(hb, mol, io, bufs, n_samp, h_uniforms5[4])); break;
         }
+    }
     }
     CompState s1;
     CUDA_TRY(cudaMemcpyAsync(&s1, hb->st.p + stage, sizeof(s1), cudaMemcpyDeviceToHost, c->stream));
@@ -603,8 +655,10 @@ extern "C" int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, co
     return FRIES_OK;
 }
 
-// Diagnostics: the CompState records of the last iteration -- per state 8 doubles:
-// loc_norm, glob_norm, new_norm, n_samp_left, rounds, n_kept, n_out, n_in.  States 0-4: HB-PP stages,
+// Diagnostics: the CompState records of the last iteration -- per state 20 doubles:
+// loc_norm, glob_norm, new_norm, n_samp_left, rounds, n_kept, n_out, n_in, anomalies, n_cand, fast, overflow,
+// then 8 phase time stamps in ns relative to ts[0] (comp_sub_engine: 1 prep, 2 preserved set, 3 line scan,
+// 4 count + offsets, 5 emit).  States 0-4: HB-PP stages,
 // 5: finalize, 6: find_preserve, 7: sys_comp.
 extern "C" int fries_hbpp_states(fries_hbpp *hb, double *h_out64) {
     FRIES_REQUIRE(hb && h_out64, "fries_hbpp_states: NULL argument");
@@ -614,9 +668,12 @@ extern "C" int fries_hbpp_states(fries_hbpp *hb, double *h_out64) {
     CUDA_TRY(cudaMemcpyAsync(st, hb->st.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (int s = 0; s < 8; s++) {
-        double *o = h_out64 + 8 * s;
+        double *o = h_out64 + 20 * s;
         o[0] = st[s].loc_norm; o[1] = st[s].glob_norm; o[2] = st[s].new_norm; o[3] = st[s].n_samp_left;
         o[4] = st[s].rounds; o[5] = (double)st[s].n_kept; o[6] = (double)st[s].n_out; o[7] = (double)st[s].n_in;
+        o[8] = (double)st[s].anomalies; o[9] = (double)st[s].n_cand; o[10] = (double)st[s].fast;
+        o[11] = (double)st[s].overflow;
+        for (int k = 0; k < 8; k++) o[12 + k] = st[s].ts[k] >= st[s].ts[0] ? (double)(st[s].ts[k] - st[s].ts[0]) : 0.0;
     }
     return FRIES_OK;
 }

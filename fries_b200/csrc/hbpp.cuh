@@ -36,6 +36,11 @@ struct fries_hbpp {
     DevBuf<unsigned long long> part_c;
     DevBuf<CompState> st;  // [0..4] stages, [5] finalize counters, [6] vector compression
     DevBuf<unsigned long long> n_scalar;
+    // bracketed threshold solve (compress.cuh): candidate list (shared by all compressions of an iteration, which
+    // run one after the other) and one prediction per compression site: [0..4] HB-PP stages, [5] find_preserve
+    DevBuf<double> cand_x;
+    DevBuf<uint32_t> cand_m;
+    DevBuf<KeepPred> pred;
     // frisys/frifull driver state (iter.cu)
     DevBuf<uint64_t> trial_keys, htrial_keys, spawn_keys;
     DevBuf<double> trial_vals, htrial_vals, spawn_vals, scal;

@@ -1,14 +1,9 @@
 // a19: Hubbard-Holstein pieces and the frisys_hh loop body (FRIES_bin/frisys_hh.cpp:186-368).
 // Keys: bits [0, n) spin-up sites, [n, 2n) spin-down sites, then n phonon fields of ph_bits bits (hh_vec.hpp).
 #include "hbpp.cuh"
+extern int fr_bracket_on;  // hbpp.cu
 #include "vec.cuh"
 
-int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, const unsigned long long *d_n,
-                               unsigned n_samp, uint8_t *d_keep, CompState *d_st, double *pd, unsigned long long *pc,
-                               int grid, const fries_comm *comm);
-int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, const unsigned long long *d_n, uint8_t *d_keep,
-                          const double *d_in, double lbound0, double glob, long long n_samp, double rn, CompState *d_out,
-                          double *pd, unsigned long long *pc, int grid, const fries_comm *comm);
 int fries_vec_compact_flags_dev(fries_vec *vec, const uint8_t *d_flags);
 
 struct HhDims {
@@ -345,7 +340,8 @@ extern "C" int fries_frisys_hh_iterate(fries_vec *vec, fries_hbpp *hb, const fri
     auto bufs_for = [&](int o, int s) {
         return CompSubBufs{hb->veff.p, hb->wtr.p, hb->lb.p, hb->rinv.p, hb->ndiv.p, hb->keep.p, hb->kcnt.p, hb->nsub.p,
                            hb->oval[o].p, hb->owidx[o].p, hb->osub[o].p, (unsigned long long)hb->cap,
-                           hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(nullptr)};
+                           hb->part_d.p, hb->part_c.p, hb->st.p + s, fries_comm_view(nullptr),
+                           fr_bracket_on ? hb->pred.p + s : nullptr, CandList{hb->cand_x.p, hb->cand_m.p, &hb->st.p[s].n_cand}};
     };
     unsigned n_samp = p->target_nonz;
     {   // stage 1: hop vs phonon (:187-206)
@@ -376,7 +372,8 @@ extern "C" int fries_frisys_hh_iterate(fries_vec *vec, fries_hbpp *hb, const fri
     hh_diag_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(v, d, p->eps, p->hub_u, p->ph_freq, p->hf_en, p->en_shift);
     c->launch_count++;
     FRIES_TRY(fries_find_preserve_launch(c, v.vals, vec->cap, &vec->cnt.p->n, p->target_nonz, hb->keep_flags.p, hb->st.p + 6,
-                                         hb->part_d.p, hb->part_c.p, 0, nullptr));
+                                         hb->part_d.p, hb->part_c.p, 0, nullptr, hb->pred.p + 5, hb->cand_x.p,
+                                         hb->cand_m.p));
     hh_state_to_r4<<<1, 1, 0, c->stream>>>(hb->st.p + 6, hb->scal.p);
     hh_energy_kernel<<<1, 1024, 0, c->stream>>>(v, d, p->ref_key, p->elec_ph / hub_t, hub_t, p->hub_u, p->hf_en, hb->scal.p + 4);
     c->launch_count += 2;

@@ -5,12 +5,6 @@
 
 extern __shared__ double fr_dyn_smem[];
 
-int fries_find_preserve_launch(fries_ctx *c, const double *d_values, size_t count, const unsigned long long *d_n,
-                               unsigned n_samp, uint8_t *d_keep, CompState *d_st, double *pd, unsigned long long *pc,
-                               int grid, const fries_comm *comm);
-int fries_sys_comp_launch(fries_ctx *c, double *d_values, size_t count, const unsigned long long *d_n, uint8_t *d_keep,
-                          const double *d_in, double lbound0, double glob, long long n_samp, double rn, CompState *d_out,
-                          double *pd, unsigned long long *pc, int grid, const fries_comm *comm);
 int fries_vec_compact_flags_dev(fries_vec *vec, const uint8_t *d_flags);
 
 #define FR_NAN __longlong_as_double(0x7ff8000000000000ll)
@@ -446,7 +440,8 @@ static int compress_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, uns
     VecView v = vec->view();
     double *vals = v.vals + (size_t)row * v.cap;
     FRIES_TRY(fries_find_preserve_launch(c, vals, vec->cap, &vec->cnt.p->n, target_nonz, hb->keep_flags.p, hb->st.p + 6,
-                                         hb->part_d.p, hb->part_c.p, 0, hb->comm));
+                                         hb->part_d.p, hb->part_c.p, 0, hb->comm, hb->pred.p + 5, hb->cand_x.p,
+                                         hb->cand_m.p));
     state_to_r4_kernel<<<1, 1, 0, c->stream>>>(hb->st.p + 6, hb->scal.p + IterScalars::R4);
     c->launch_count++;
     (void)uniform;

@@ -306,7 +306,19 @@ __host__ __device__ inline unsigned mol_for_each_doub(const MolView &m, uint64_t
 // popcount / find-nth-set-bit, so a kernel never materialises the row or the occupied list (no local memory).
 __host__ __device__ __forceinline__ unsigned fr_nth_bit32(uint32_t mask, unsigned n) {
 #ifdef __CUDA_ARCH__
-    return __fns(mask, 0, n + 1);
+    // position of the n-th (0-based) set bit by a popcount binary search: 5 branch-free steps (__fns is a
+    // software loop of ~100 instructions)
+    unsigned pos = 0, t;
+    t = __popc(mask & 0xffffu);
+    if (n >= t) { n -= t; pos = 16; mask >>= 16; }
+    t = __popc(mask & 0xffu);
+    if (n >= t) { n -= t; pos += 8; mask >>= 8; }
+    t = __popc(mask & 0xfu);
+    if (n >= t) { n -= t; pos += 4; mask >>= 4; }
+    t = __popc(mask & 0x3u);
+    if (n >= t) { n -= t; pos += 2; mask >>= 2; }
+    if (n >= (mask & 1u)) pos += 1;
+    return pos;
 #else
     for (unsigned i = 0; i < n; i++) mask &= mask - 1;
     return (unsigned)__builtin_ctz(mask);

@@ -252,8 +252,8 @@ extern "C" int fries_vec_create(fries_ctx *c, size_t capacity, unsigned n_bits, 
     if (rc == FRIES_OK) rc = v->tpos.alloc(t);
     if (rc == FRIES_OK) rc = v->scr.alloc(128);
     if (rc == FRIES_OK) rc = v->cnt.alloc(1);
-    if (rc == FRIES_OK) rc = v->red_d.alloc(4 * 1024);
-    if (rc == FRIES_OK) rc = v->red_c.alloc(4 * 1024);
+    if (rc == FRIES_OK) rc = v->red_d.alloc(FR_RED_PART_LEN);
+    if (rc == FRIES_OK) rc = v->red_c.alloc(FR_RED_PART_LEN);
     if (rc != FRIES_OK) {
         delete v;
         return rc;

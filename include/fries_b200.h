@@ -278,9 +278,25 @@ int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, const double 
                            int new_hb, const double *h_uniforms5, unsigned n_samp, size_t spawn_cap, int stage,
                            double *h_val, uint32_t *h_det, uint32_t *h_path, uint32_t *h_sub, size_t *n_out);
 
-/* CompState records of the last iteration, 8 states x 8 doubles (loc_norm, glob_norm, new_norm, n_samp_left,
- * rounds, n_kept, n_out, n_in); states 0-4 = HB-PP stages, 5 = finalize, 6 = find_preserve, 7 = sys_comp */
-int fries_hbpp_states(fries_hbpp *hb, double *h_out64);
+/* CompState records of the last iteration, 8 states x 20 doubles (loc_norm, glob_norm, new_norm, n_samp_left,
+ * rounds, n_kept, n_out, n_in, anomalies, n_cand, fast, overflow, then 8 in-kernel phase time stamps in ns relative
+ * to the first: 1 prep, 2 preserved set decided, 3 line scan, 4 count + offsets, 5 emit); states 0-4 = HB-PP stages, 5 = finalize,
+ * 6 = find_preserve, 7 = sys_comp.  fast = 1: the preserved set came from the bracketed threshold solve (one data
+ * pass + rounds on n_cand candidates), 0: from the plain rounds over the data. */
+int fries_hbpp_states(fries_hbpp *hb, double *h_out160);
+
+/* Run every standalone (host-buffer) compression n times on the same inputs and return the last run: the bracketed
+ * threshold solve starts from the fixed point of a previous run, which a one-shot call does not have. */
+int fries_debug_set_repeat(int n);
+/* the warm-up runs (all but the last) of a repeated call see their input values scaled by (1 + rel): the last run
+ * then starts from a bracket that is off by about that much, as in consecutive FRI iterations */
+int fries_debug_set_perturb(double rel);
+/* on = 0: every compression uses the plain rounds (the reference's own iteration); on = 1 (default): bracketed solve
+ * whenever a previous fixed point is available.  Both give the same preserved sets up to FP ties. */
+int fries_debug_set_bracket(int on);
+/* how many compressions of the last fries_comp_sub / fries_apply_hbpp_sys / fries_find_preserve call were decided by
+ * the bracketed solve */
+int fries_debug_last_fast(int *n_fast);
 
 #ifdef __cplusplus
 }
