@@ -20,7 +20,7 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
                      unsigned n_samp_in, uint8_t *__restrict__ keep, double *part_d, unsigned long long *part_c,
                      CompState *st, CommView cm, KeepPred *pred, CandList cand) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sh_x[2 * FP_PROBES + 1][FR_MAX_RANKS];
+    __shared__ double sh_x[12][FR_MAX_RANKS];
     __shared__ double sh_d[6 * 33];
     __shared__ unsigned long long sh_c[6 * 33];
     CommCursor cur = comm_begin(cm);
@@ -36,12 +36,14 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
     const size_t hi = lo + chunk < n ? lo + chunk : n;
 
     // bracket around the expected fixed point (compress.cuh, bracket_solve)
-    double t_pred = 0, h_pred = 0;
-    if (pred) {
-        t_pred = __ldcg(&pred->t);
-        h_pred = __ldcg(&pred->h);
+    __shared__ unsigned long long sh_bc[2];  // one load per CTA, then broadcast
+    if (threadIdx.x == 0) {
+        sh_bc[0] = pred ? (unsigned long long)__double_as_longlong(__ldcg(&pred->t)) : 0ull;
+        sh_bc[1] = pred ? (unsigned long long)__double_as_longlong(__ldcg(&pred->h)) : 0ull;
     }
-    const bool try_fast = !multi && t_pred > 0 && h_pred > 0 && h_pred < 0.25;
+    __syncthreads();
+    const double t_pred = __longlong_as_double((long long)sh_bc[0]), h_pred = __longlong_as_double((long long)sh_bc[1]);
+    const bool try_fast = t_pred > 0 && h_pred > 0 && h_pred < 0.25;
     const double t_lo = t_pred * (1.0 - h_pred), t_hi = t_pred * (1.0 + h_pred);
     double s = 0, s_hi = 0;
     unsigned long long c_hi = 0;
@@ -67,10 +69,21 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
         c_hi = cc[0];
     }
     double loc = s, R_next = s;
-    if (multi) {  // *global_norm = sum_mpi(loc_one_norm) (:50)
-        comm_allgather_v(cm, cur, &s, 1, sh_x);
+    bool peers_ok = try_fast ? bracket_list_fits(cand, sh_c) : false;
+    if (multi) {  // *global_norm = sum_mpi(loc_one_norm) (:50); the bracket statistics ride along
+        double pay[4] = {s, s_hi, (double)c_hi, peers_ok ? 1.0 : 0.0};
+        comm_allgather_v(cm, cur, pay, 4, sh_x);
         double before;
         comm_sum(cm, sh_x[0], R_next, before);
+        double gs = 0, gc = 0;
+        for (int p = 0; p < cm.n_ranks; p++) {
+            gs += sh_x[1][p];
+            gc += sh_x[2][p];
+            if (sh_x[3][p] == 0.0) peers_ok = false;
+        }
+        s_hi = gs;
+        c_hi = (unsigned long long)gc;
+        __syncthreads();
     }
     const double glob_total = R_next;
     unsigned nrem = n_samp_in;
@@ -80,8 +93,9 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
     unsigned rounds = 0;
     unsigned long long n_cand = 0;
     if (try_fast) {
-        n_cand = __ldcg(cand.count);
-        BracketResult br = bracket_solve(cand, s - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi, sh_d, sh_c);
+        BracketResult br = bracket_solve(grid, cand, st->gacc, glob_total - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo,
+                                         t_hi, sh_d, sh_c, cm, cur, sh_x, peers_ok);
+        n_cand = br.n_cand;
         if (br.valid) {
             // one pass: keep flags of the cut + exact residual norm (:78-90)
             double t = 0;
@@ -97,7 +111,7 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
             }
             grid_reduce(grid, red, t, kc);
             kept_total = c_hi + br.kept_cand;
-            if (kc != kept_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->anomalies, 1ull << 32);
+            if (!multi && kc != kept_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->anomalies, 1ull << 32);
             fresh_loc = t;
             thr = br.x_cut;
             nrem = br.nrem;
@@ -456,8 +470,8 @@ extern "C" int fries_find_preserve(fries_ctx *c, const double *h_values, size_t 
     DevBuf<uint32_t> cand_m;
     DevBuf<KeepPred> pred;
     if (fr_debug_repeat > 1) {
-        FRIES_TRY(cand_x.alloc(FR_CAND_CAP));
-        FRIES_TRY(cand_m.alloc(FR_CAND_CAP));
+        FRIES_TRY(cand_x.alloc(FR_CAND_GCAP));
+        FRIES_TRY(cand_m.alloc(FR_CAND_GCAP));
         FRIES_TRY(pred.alloc(1));
         CUDA_TRY(cudaMemsetAsync(pred.p, 0, sizeof(KeepPred), c->stream));
     }
@@ -581,8 +595,8 @@ extern "C" int fries_comp_sub(fries_ctx *c, const double *h_values, size_t count
     DevBuf<uint32_t> cand_m;
     DevBuf<KeepPred> pred;
     if (fr_debug_repeat > 1) {
-        FRIES_TRY(cand_x.alloc(FR_CAND_CAP));
-        FRIES_TRY(cand_m.alloc(FR_CAND_CAP));
+        FRIES_TRY(cand_x.alloc(FR_CAND_GCAP));
+        FRIES_TRY(cand_m.alloc(FR_CAND_GCAP));
         FRIES_TRY(pred.alloc(1));
         CUDA_TRY(cudaMemsetAsync(pred.p, 0, sizeof(KeepPred), c->stream));
     }

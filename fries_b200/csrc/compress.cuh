@@ -28,6 +28,7 @@ struct CompState {
     unsigned long long n_cand;   // candidates collected inside the threshold bracket (bracket_solve)
     unsigned long long fast;     // 1: the bracketed solve decided the preserved set, 0: plain rounds
     unsigned long long ts[8];    // %globaltimer (ns) of CTA 0 at the phase boundaries of comp_sub_engine
+    unsigned long long gacc[40]; // grid-wide integer accumulators of the distributed candidate rounds (zeroed by the host)
 };
 
 __device__ __forceinline__ unsigned long long fr_globaltimer() {
@@ -195,7 +196,8 @@ __device__ __forceinline__ void grid_excl_scan(cg::grid_group &grid, GridRed &r,
 // final threshold; otherwise the caller falls back to the plain rounds over the full data.
 // ---------------------------------------------------------------------------------------------------
 #define FR_CAND_PER_THREAD 8
-#define FR_CAND_CAP (FR_COMP_BLOCK * FR_CAND_PER_THREAD)
+#define FR_CAND_CAP (FR_COMP_BLOCK * FR_CAND_PER_THREAD)  // candidates one CTA can hold in registers
+#define FR_CAND_GCAP (1u << 20)                            // capacity of the list (grid-distributed rounds beyond one CTA)
 
 struct KeepPred {
     double t;   // fixed-point threshold of the previous run (0: none)
@@ -203,16 +205,16 @@ struct KeepPred {
 };
 
 struct CandList {
-    double *x;                  // [FR_CAND_CAP] candidate magnitudes
-    uint32_t *mult;             // [FR_CAND_CAP] multiplicities (uniform division: n_div pieces of equal size)
+    double *x;                  // [FR_CAND_GCAP] candidate magnitudes
+    uint32_t *mult;             // [FR_CAND_GCAP] multiplicities (uniform division: n_div pieces of equal size)
     unsigned long long *count;  // appended so far (may exceed the capacity: then the bracket is invalid)
 };
 
 __device__ __forceinline__ void cand_append(const CandList &cl, double x, uint32_t mult) {
     // once the list has overflowed the bracket is invalid anyway: stop hammering the counter
-    if (*(volatile unsigned long long *)cl.count > FR_CAND_CAP) return;
+    if (*(volatile unsigned long long *)cl.count > FR_CAND_GCAP) return;
     unsigned long long k = atomicAdd(cl.count, 1ull);
-    if (k < FR_CAND_CAP) {
+    if (k < FR_CAND_GCAP) {
         cl.x[k] = x;
         cl.mult[k] = mult;
     }
@@ -220,6 +222,7 @@ __device__ __forceinline__ void cand_append(const CandList &cl, double x, uint32
 
 struct BracketResult {
     bool valid;
+    unsigned long long n_cand;      // length of the candidate list
     double x_cut;                   // preserved <=> x >= x_cut
     double R;                       // one-norm of what is not preserved (by subtraction, as the reference's rounds)
     unsigned nrem;                  // budget left
@@ -236,13 +239,35 @@ __device__ long long fr_bt[16];
 #else
 #define FR_BT(k)
 #endif
-// shc: >= 17 u64 of shared memory (shd unused, kept for symmetry).  Uniform result in every thread of every CTA.
+// shc: >= 32 u64 of shared memory (shd unused, kept for symmetry).  Uniform result in every thread of every CTA.
 // All sums are integers (counts; candidate magnitudes in units of ulp(t_lo), as eight 16-bit limbs so that a warp's
 // total fits the 32-bit redux instruction), reduced with redux.sync + shared-memory atomics: order-independent,
 // and far cheaper than 64-bit shuffle trees (SHFL issues once per cycle per SM).
-__device__ __forceinline__ BracketResult bracket_solve(const CandList &cl, double R0, long long nrem0, double t_lo,
-                                                       double t_hi, double *shd, unsigned long long *shc) {
+//
+// Lists of up to FR_CAND_CAP candidates are solved redundantly by every CTA (no grid barrier).  Longer lists (large
+// vectors: the list grows like the square root of the vector length) are split across the CTAs, FR_CAND_CAP each;
+// the per-round totals then go through integer atomics on gacc (CompState) and one grid barrier per round.
+//
+// Several ranks (cm.n_ranks > 1): R0 / nrem0 are the global values, every rank runs the rounds on its own candidates
+// in the grid-distributed form (the cross-rank protocol of comm.cuh needs a grid barrier between two exchanges) and
+// the per-round integer totals are all-gathered and summed; all ranks take identical decisions.  `peers_ok` must be
+// the AND over the ranks of local_list_fits() (the caller exchanges it with its own first all-gather).
+__device__ __forceinline__ bool bracket_list_fits(const CandList &cl, unsigned long long *shc) {
+    if (threadIdx.x == 0) shc[20] = __ldcg(cl.count);
+    __syncthreads();
+    unsigned long long ncand = shc[20];
+    __syncthreads();
+    unsigned long long gcap = (unsigned long long)gridDim.x * FR_CAND_CAP;
+    if (gcap > FR_CAND_GCAP) gcap = FR_CAND_GCAP;
+    return ncand <= gcap;
+}
+__device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, const CandList &cl,
+                                                       unsigned long long *gacc, double R0, long long nrem0,
+                                                       double t_lo, double t_hi, double *shd, unsigned long long *shc,
+                                                       const CommView &cm, CommCursor &cur,
+                                                       double (*sh_x)[FR_MAX_RANKS], bool peers_ok) {
     (void)shd;
+    const bool multi = cm.n_ranks > 1;
     BracketResult res;
     res.valid = false;
     res.x_cut = t_hi;
@@ -250,9 +275,18 @@ __device__ __forceinline__ BracketResult bracket_solve(const CandList &cl, doubl
     res.nrem = 0;
     res.kept_cand = 0;
     res.rounds = 0;
+    res.n_cand = 0;
     FR_BT(0);
-    const unsigned long long ncand = __ldcg(cl.count);
-    if (ncand > FR_CAND_CAP || nrem0 <= 0 || nrem0 > 0xffffffffll) return res;
+    if (threadIdx.x == 0) shc[20] = __ldcg(cl.count);
+    __syncthreads();
+    const unsigned long long ncand = shc[20];
+    res.n_cand = ncand;
+    __syncthreads();
+    unsigned long long gcap = (unsigned long long)gridDim.x * FR_CAND_CAP;
+    if (gcap > FR_CAND_GCAP) gcap = FR_CAND_GCAP;
+    if (ncand > gcap || !peers_ok || nrem0 <= 0 || nrem0 > 0xffffffffll) return res;
+    const bool dist = multi || ncand > FR_CAND_CAP;
+    const unsigned long long slice0 = dist ? (unsigned long long)blockIdx.x * FR_CAND_CAP : 0ull;
     if (!(t_hi * (double)nrem0 >= R0)) return res;  // H is not certainly preserved
     // ulp(t_lo) = 2^(E_lo - 1075) with E_lo the biased exponent; every candidate is an integer multiple of it
     const int E_lo = (int)((__double_as_longlong(t_lo) >> 52) & 0x7ff);
@@ -263,7 +297,7 @@ __device__ __forceinline__ BracketResult bracket_solve(const CandList &cl, doubl
     unsigned state = 0;  // bit k: candidate k of this thread not yet preserved
 #pragma unroll
     for (int k = 0; k < FR_CAND_PER_THREAD; k++) {
-        unsigned idx = threadIdx.x + k * FR_COMP_BLOCK;
+        unsigned long long idx = slice0 + threadIdx.x + k * FR_COMP_BLOCK;
         x[k] = 0;
         mu[k] = 0;
         if (idx < ncand) {
@@ -321,13 +355,49 @@ __device__ __forceinline__ BracketResult bracket_solve(const CandList &cl, doubl
         if (threadIdx.x < 12) acc[12 * ((round & 1) ^ 1) + threadIdx.x] = 0;
         __syncthreads();
         res.rounds = round + 1;
-        const unsigned long long c_round = (unsigned long long)a[0] + ((unsigned long long)a[1] << 16) +
-                                           ((unsigned long long)a[2] << 32);
+        unsigned long long lim[11];
+        if (!dist) {
+#pragma unroll
+            for (int q = 0; q < 11; q++) lim[q] = a[q];
+        } else {
+            // CTA totals -> grid totals.  Three global buffers rotate: buffer (round + 1) % 3 was last read two rounds
+            // ago (every CTA has passed the barrier after those reads), so CTA 0 may clear it before this barrier.
+            unsigned long long *g = gacc + 12 * (round % 3);
+            if (round == 0) FR_BT(8);
+            if (threadIdx.x < 11 && a[threadIdx.x]) atomicAdd(&g[threadIdx.x], (unsigned long long)a[threadIdx.x]);
+            if (blockIdx.x == 0 && threadIdx.x < 12) gacc[12 * ((round + 1) % 3) + threadIdx.x] = 0;
+            if (round == 0) FR_BT(9);
+            grid.sync();
+            if (round == 0) FR_BT(10);
+            // one load per CTA and value, then a shared-memory broadcast: 150 000 threads reading the same eleven
+            // words serialise in L2 (measured: 11 us)
+            unsigned long long *bc = shc + 20;
+            if (threadIdx.x < 11) bc[threadIdx.x] = __ldcg(&g[threadIdx.x]);
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 11; q++) lim[q] = bc[q];
+            __syncthreads();
+            if (round == 0) FR_BT(11);
+            if (multi) {  // rank totals -> global totals (limbs < 2^36: exact in a double)
+                double pay[11];
+#pragma unroll
+                for (int q = 0; q < 11; q++) pay[q] = (double)lim[q];
+                comm_allgather_v(cm, cur, pay, 11, sh_x);
+#pragma unroll
+                for (int q = 0; q < 11; q++) {
+                    unsigned long long t = 0;
+                    for (int p = 0; p < cm.n_ranks; p++) t += (unsigned long long)sh_x[q][p];
+                    lim[q] = t;
+                }
+                __syncthreads();
+            }
+        }
+        const unsigned long long c_round = lim[0] + (lim[1] << 16) + (lim[2] << 32);
         if (c_round == 0) break;
         cnt_tot += c_round;
         unsigned __int128 s_round = 0;
 #pragma unroll
-        for (int q = 7; q >= 0; q--) s_round = (s_round << 16) + a[3 + q];
+        for (int q = 7; q >= 0; q--) s_round = (s_round << 16) + lim[3 + q];
         sum_tot += s_round;
         if (cnt_tot >= (unsigned long long)nrem0) return res;  // budget exhausted inside the bracket
         nrem = (unsigned long long)nrem0 - cnt_tot;
@@ -344,6 +414,22 @@ __device__ __forceinline__ BracketResult bracket_solve(const CandList &cl, doubl
     __syncthreads();
     xmin = __longlong_as_double((long long)*acc_min);
     __syncthreads();
+    if (dist) {  // gacc[36] (zeroed by the host) collects max(inf_bits - bits) = the smallest preserved magnitude
+        if (threadIdx.x == 0 && xmin < INFINITY)
+            atomicMax(&gacc[36], 0x7ff0000000000000ull - (unsigned long long)__double_as_longlong(xmin));
+        grid.sync();
+        if (threadIdx.x == 0) shc[20] = __ldcg(&gacc[36]);
+        __syncthreads();
+        xmin = __longlong_as_double((long long)(0x7ff0000000000000ull - shc[20]));
+        __syncthreads();
+        if (multi) {
+            comm_allgather_v(cm, cur, &xmin, 1, sh_x);
+            double t = INFINITY;
+            for (int p = 0; p < cm.n_ranks; p++) t = fmin(t, sh_x[0][p]);
+            xmin = t;
+            __syncthreads();
+        }
+    }
     FR_BT(7);
     res.x_cut = xmin < t_hi ? xmin : t_hi;
     res.R = R;
@@ -353,15 +439,17 @@ __device__ __forceinline__ BracketResult bracket_solve(const CandList &cl, doubl
     return res;
 }
 
-// next bracket from this run's fixed point
+// next bracket from this run's fixed point: wide enough for the observed drift of the fixed point between runs (x 6),
+// otherwise steered towards a list of ~2500 candidates (one CTA's registers hold 4096: no grid barrier in the rounds)
 __device__ __forceinline__ void keep_pred_update(KeepPred *p, double t_prev, double h_prev, double t_fin,
                                                  unsigned long long ncand) {
-    const double h_min = 5e-4, h_max = 0.05;
+    const double h_min = 1e-4, h_max = 0.05;
     double h = 0.01;
     if (t_prev > 0 && t_fin > 0) {
         double drift = fabs(t_fin / t_prev - 1.0);
-        h = fmax(6.0 * drift, 0.6 * h_prev);
-        if (ncand > FR_CAND_CAP / 2) h = fmin(h, 0.5 * h_prev);
+        double steer = h_prev * 2500.0 / (double)(ncand > 0 ? ncand : 1);
+        steer = fmin(fmax(steer, 0.5 * h_prev), 1.5 * h_prev);
+        h = fmax(6.0 * drift, steer);
     }
     h = fmin(fmax(h, h_min), h_max);
     p->t = (t_fin > 0 && isfinite(t_fin)) ? t_fin : 0.0;
@@ -417,13 +505,22 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     __shared__ unsigned long long sh_sc[6 * 33];
     GridRed red{b.part_d, b.part_c, 0, (int)gridDim.x, sh_d, sh_c};
 
-    const size_t n = prov.count();
+    // scalars every thread needs: loaded once per CTA and broadcast (all-thread loads of one address serialise in L2)
+    __shared__ unsigned long long sh_bc[4];
+    if (threadIdx.x == 0) {
+        sh_bc[0] = (unsigned long long)prov.count();
+        sh_bc[1] = b.pred ? (unsigned long long)__double_as_longlong(__ldcg(&b.pred->t)) : 0ull;
+        sh_bc[2] = b.pred ? (unsigned long long)__double_as_longlong(__ldcg(&b.pred->h)) : 0ull;
+    }
+    __syncthreads();
+    const size_t n = (size_t)sh_bc[0];
     size_t chunk = (n + gridDim.x - 1) / gridDim.x;
     chunk = (chunk + 31) & ~(size_t)31;
     const size_t lo = (size_t)blockIdx.x * chunk < n ? (size_t)blockIdx.x * chunk : n;
     const size_t hi = lo + chunk < n ? lo + chunk : n;
 
     __shared__ double sh_x0[FR_MAX_RANKS], sh_x1[FR_MAX_RANKS];
+    __shared__ double sh_xv[12][FR_MAX_RANKS];
     __shared__ unsigned long long sh_xc[FR_MAX_RANKS];
     const CommView &cm = b.cm;
     CommCursor cur = comm_begin(cm);
@@ -431,12 +528,8 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
 
     FR_STAMP(b.st, 0);
     // bracket around the expected fixed point (see bracket_solve); uniform over the grid
-    double t_pred = 0, h_pred = 0;
-    if (b.pred) {
-        t_pred = __ldcg(&b.pred->t);
-        h_pred = __ldcg(&b.pred->h);
-    }
-    const bool try_fast = !multi && t_pred > 0 && h_pred > 0 && h_pred < 0.25;
+    const double t_pred = __longlong_as_double((long long)sh_bc[1]), h_pred = __longlong_as_double((long long)sh_bc[2]);
+    const bool try_fast = t_pred > 0 && h_pred > 0 && h_pred < 0.25;
     const double t_lo = t_pred * (1.0 - h_pred), t_hi = t_pred * (1.0 + h_pred);
 
     // ---- phase 0: effective weights (find_keep_sub :134-137); with a bracket also the exact (count, sum) of
@@ -489,11 +582,22 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     }
     double loc = s;          // this rank's loc_one_norm
     double R_next = s;       // sum_mpi(loc_one_norm) for the coming round
+    bool peers_ok = try_fast ? bracket_list_fits(b.cand, sh_sc) : false;
     if (multi) {
         double before;
-        comm_allgather(cm, cur, s, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+        comm_allgather(cm, cur, s, s_hi, c_hi | (peers_ok ? 0ull : 1ull << 63), sh_x0, sh_x1, sh_xc);
         comm_sum(cm, sh_x0, R_next, before);
         s = R_next;          // global one-norm (reported)
+        double gs = 0;
+        unsigned long long gc = 0;
+        for (int p = 0; p < cm.n_ranks; p++) {
+            gs += sh_x1[p];
+            gc += sh_xc[p] & ~(1ull << 63);
+            if (sh_xc[p] >> 63) peers_ok = false;
+        }
+        s_hi = gs;           // global (count, sum) of everything at or above the bracket
+        c_hi = gc;
+        __syncthreads();
     }
 
     FR_STAMP(b.st, 1);  // phase 0 done
@@ -511,8 +615,9 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     bool fast_done = false;
     if (try_fast) {
         // Newton rounds on the candidate list only (every CTA, redundantly), then ONE pass that applies the cut
-        n_cand = __ldcg(b.cand.count);
-        BracketResult br = bracket_solve(b.cand, s - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi, sh_sd, sh_sc);
+        BracketResult br = bracket_solve(grid, b.cand, b.st->gacc, s - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi,
+                                         sh_sd, sh_sc, cm, cur, sh_xv, peers_ok);
+        n_cand = br.n_cand;
         FR_STAMP(b.st, 6);  // candidate rounds done
         if (br.valid) {
             const double x_cut = br.x_cut, fac = (double)br.nrem;
@@ -555,7 +660,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
             FR_STAMP(b.st, 7);  // cut applied (CTA 0)
             grid_reduce_blk(grid, red, t, kc);
             kept_total = c_hi + br.kept_cand;
-            if (kc != kept_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&b.st->anomalies, 1ull << 32);
+            if (!multi && kc != kept_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&b.st->anomalies, 1ull << 32);
             nrem = br.nrem;
             R = br.R;
             rounds = br.rounds;
@@ -563,6 +668,12 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
             fresh_loc = t;
             fresh_G = t;
             fresh_lb0 = 0;
+            if (multi) {  // this rank's place on the global resampling line (seed_sys :107-127)
+                double tot;
+                comm_allgather(cm, cur, t, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+                comm_sum(cm, sh_x0, tot, fresh_lb0);
+                fresh_G = tot;
+            }
             fast_done = true;
             glob_sampled = 0;  // skip the plain rounds
             if (blockIdx.x == 0 && threadIdx.x == 0) b.st->fast = 1;

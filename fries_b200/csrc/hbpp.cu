@@ -360,7 +360,7 @@ int fries_hbpp_alloc(fries_ctx *c, size_t cap, fries_hbpp **out, bool stages) {
         A(fin_val, cap); A(fin_det, cap); A(fin_orbs, cap);
     }
     A(part_d, FR_RED_PART_LEN); A(part_c, FR_RED_PART_LEN); A(st, 8); A(n_scalar, 4); A(scal, 64);
-    A(cand_x, FR_CAND_CAP); A(cand_m, FR_CAND_CAP); A(pred, 8);
+    A(cand_x, FR_CAND_GCAP); A(cand_m, FR_CAND_GCAP); A(pred, 8);
 #undef A
     if (rc == FRIES_OK && cudaMemset(hb->pred.p, 0, 8 * sizeof(KeepPred)) != cudaSuccess) {
         fries_set_error("fries_hbpp_alloc: cudaMemset failed");

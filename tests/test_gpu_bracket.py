@@ -50,7 +50,10 @@ def last_fast():
 
 
 @pytest.mark.parametrize("n,budget,kind", [(1000, 100, "lognormal"), (50000, 5000, "fri"), (300000, 30000, "fri"),
-                                            (300000, 250000, "lognormal"), (2000000, 700000, "lognormal")])
+                                            (300000, 250000, "lognormal"), (2000000, 700000, "lognormal"),
+                                            # dense near the threshold: tens of thousands of candidates, i.e. the
+                                            # grid-distributed candidate rounds
+                                            (2000000, 500000, "uniform"), (3000000, 2500000, "uniform")])
 @pytest.mark.parametrize("perturb", [0.0, 0.003, -0.004])
 def test_find_preserve_bracket(ctx, n, budget, kind, perturb):
     import fries_b200

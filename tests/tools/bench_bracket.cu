@@ -4,12 +4,18 @@
 #include <cstdio>
 #include <vector>
 void fries_set_error(const char *, ...) {}
-__global__ void __launch_bounds__(512, 2) k_solve(CandList cl, double R0, long long nrem0, double t_lo, double t_hi,
+__global__ void __launch_bounds__(512, 2) k_solve(CandList cl, unsigned long long *gacc, double R0, long long nrem0, double t_lo, double t_hi,
                                                    long long *cyc, double *out) {
     __shared__ double shd[6 * 33];
     __shared__ unsigned long long shc[6 * 33];
+    cg::grid_group grid = cg::this_grid();
+    grid.sync();
     long long t0 = clock64();
-    BracketResult br = bracket_solve(cl, R0, nrem0, t_lo, t_hi, shd, shc);
+    __shared__ double sh_x[12][FR_MAX_RANKS];
+    CommView cm{};
+    cm.n_ranks = 1;
+    CommCursor cur{0};
+    BracketResult br = bracket_solve(grid, cl, gacc, R0, nrem0, t_lo, t_hi, shd, shc, cm, cur, sh_x, true);
     long long t1 = clock64();
     if (threadIdx.x == 0) {
         cyc[blockIdx.x] = t1 - t0;
@@ -18,25 +24,28 @@ __global__ void __launch_bounds__(512, 2) k_solve(CandList cl, double R0, long l
         }
     }
 }
-int main() {
-    const int nc = 2000;
-    std::vector<double> x(FR_CAND_CAP);
-    std::vector<uint32_t> m(FR_CAND_CAP, 1);
+int run(int nc) {
+    std::vector<double> x(FR_CAND_GCAP);
+    std::vector<uint32_t> m(FR_CAND_GCAP, 1);
     double T = 1.0, h = 0.01;
     for (int i = 0; i < nc; i++) x[i] = T * (1 - h) + 2 * h * T * ((i * 7919) % nc) / nc;
     // state: 100000 budget left, R0 chosen so that the fixed point is ~T
-    long long nrem0 = 100000;
+    long long nrem0 = 100000 + 50ll * nc;
     double R0 = T * nrem0 * 1.002;
     CandList cl;
     unsigned long long cnt = nc;
-    cudaMalloc(&cl.x, FR_CAND_CAP * 8); cudaMalloc(&cl.mult, FR_CAND_CAP * 4); cudaMalloc(&cl.count, 8);
-    cudaMemcpy(cl.x, x.data(), FR_CAND_CAP * 8, cudaMemcpyHostToDevice);
-    cudaMemcpy(cl.mult, m.data(), FR_CAND_CAP * 4, cudaMemcpyHostToDevice);
+    cudaMalloc(&cl.x, FR_CAND_GCAP * 8); cudaMalloc(&cl.mult, FR_CAND_GCAP * 4); cudaMalloc(&cl.count, 8);
+    unsigned long long *gacc; cudaMalloc(&gacc, 40 * 8);
+    cudaMemcpy(cl.x, x.data(), FR_CAND_GCAP * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(cl.mult, m.data(), FR_CAND_GCAP * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(cl.count, &cnt, 8, cudaMemcpyHostToDevice);
     long long *cyc; double *out;
     cudaMalloc(&cyc, 296 * 8); cudaMalloc(&out, 64);
     for (int rep = 0; rep < 3; rep++) {
-        k_solve<<<296, 512>>>(cl, R0, nrem0, T * (1 - h), T * (1 + h), cyc, out);
+        cudaMemset(gacc, 0, 40 * 8);
+        double tl = T * (1 - h), th = T * (1 + h);
+        void *args[] = {&cl, &gacc, &R0, &nrem0, &tl, &th, &cyc, &out};
+        cudaLaunchCooperativeKernel((void *)k_solve, dim3(296), dim3(512), args, 0, 0);
         cudaDeviceSynchronize();
         long long hc[296]; double ho[6];
         cudaMemcpy(hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost);
@@ -49,7 +58,12 @@ int main() {
         cudaMemcpyFromSymbol(bt, fr_bt, sizeof(bt));
         printf("  phases (cycles):");
         for (int k = 1; k < 8; k++) printf(" %lld", bt[k] - bt[k - 1]);
+        printf("  | round 0: work %lld atomics %lld sync %lld loads %lld", bt[8] - bt[1], bt[9] - bt[8], bt[10] - bt[9], bt[11] - bt[10]);
         printf("\n");
     }
+    return 0;
+}
+int main() {
+    for (int nc : {2000, 20000, 200000}) { printf("== %d candidates\n", nc); run(nc); }
     return 0;
 }
