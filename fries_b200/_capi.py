@@ -92,6 +92,9 @@ def _load():
         "fries_comm_error": (i, [vp, P(C.c_uint64)]),
         "fries_ctx_set_comm": (i, [vp, vp]),
         "fries_hbpp_set_route": (i, [vp, vp, vp, vp, vp, sz]),
+        "fries_comm_route_create": (i, [vp, sz, vp]),
+        "fries_comm_route_connect": (i, [vp, vp]),
+        "fries_hbpp_set_route_p2p": (i, [vp, vp]),
         "fries_frisys_mol_spawn": (i, [vp, vp, vp, P(FrisysParams), vp]),
         "fries_frisys_mol_finish": (i, [vp, vp, vp, P(FrisysParams), vp, vp, P(IterStats)]),
         "fries_vec_create_hh": (i, [vp, sz, u, u, u, u, vp, vp, i, i, P(vp)]),

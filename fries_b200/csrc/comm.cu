@@ -64,9 +64,100 @@ extern "C" int fries_comm_connect(fries_comm *cm, const void *h_all_handles) {
     return FRIES_OK;
 }
 
+// ---- spawn route window --------------------------------------------------------------------------------------------
+static size_t route_bytes(int n_ranks, size_t seg_cap) { return (size_t)n_ranks * 2 * seg_cap * 8 + 2 * FR_MAX_RANKS * 8; }
+static void bind_route(fries_comm *cm) {
+    RouteView &r = cm->route;
+    r.n_ranks = cm->n_ranks;
+    r.rank = cm->rank;
+    r.seg_cap = cm->seg_cap;
+    size_t data = (size_t)cm->n_ranks * 2 * cm->seg_cap * 8;
+    for (int p = 0; p < FR_MAX_RANKS; p++) {
+        char *base = (char *)(p < cm->n_ranks ? cm->win_peer[p] : nullptr);
+        r.win[p] = (uint64_t *)base;
+        r.counts[p] = (unsigned long long *)(base ? base + data : nullptr);
+        r.flags[p] = (unsigned long long *)(base ? base + data + FR_MAX_RANKS * 8 : nullptr);
+    }
+}
+
+extern "C" int fries_comm_route_create(fries_comm *cm, size_t seg_cap, void *h_ipc_handle64) {
+    FRIES_REQUIRE(cm && h_ipc_handle64 && seg_cap > 0, "fries_comm_route_create: bad argument");
+    FRIES_REQUIRE(cm->win_local == nullptr, "fries_comm_route_create: the window exists already");
+    CUDA_TRY(cudaSetDevice(cm->ctx->device));
+    cm->seg_cap = seg_cap;
+    size_t bytes = route_bytes(cm->n_ranks, seg_cap);
+    CUDA_TRY(cudaMalloc(&cm->win_local, bytes));
+    CUDA_TRY(cudaMemset(cm->win_local, 0, bytes));
+    cm->win_peer[cm->rank] = cm->win_local;
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, cm->win_local));
+    memcpy(h_ipc_handle64, &h, 64);
+    bind_route(cm);
+    return FRIES_OK;
+}
+
+extern "C" int fries_comm_route_connect(fries_comm *cm, const void *h_all_handles) {
+    FRIES_REQUIRE(cm && h_all_handles && cm->win_local, "fries_comm_route_connect: create the window first");
+    CUDA_TRY(cudaSetDevice(cm->ctx->device));
+    for (int p = 0; p < cm->n_ranks; p++) {
+        if (p == cm->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)h_all_handles + 64 * p, 64);
+        CUDA_TRY(cudaIpcOpenMemHandle(&cm->win_peer[p], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    bind_route(cm);
+    return FRIES_OK;
+}
+
+// after the spawn kernel: publish this source's per-destination counts, then the epoch flag, to every destination
+__global__ void route_publish_kernel(RouteView r, const unsigned long long *send_counts, unsigned long long epoch) {
+    int p = threadIdx.x;
+    if (p < r.n_ranks) {
+        unsigned long long c = send_counts[p];
+        if (c > r.seg_cap) c = r.seg_cap;
+        __threadfence_system();  // the spawn kernel's stores (previous kernel on this stream) before the flag
+        *((volatile unsigned long long *)(r.counts[p] + r.rank)) = c;
+        __threadfence_system();
+        *((volatile unsigned long long *)(r.flags[p] + r.rank)) = epoch;
+    }
+}
+// before the merge: wait until every source has published `epoch`; copy the counts next to the merge's other inputs
+__global__ void route_wait_kernel(RouteView r, unsigned long long epoch, unsigned long long *recv_counts,
+                                  unsigned long long *error) {
+    int q = threadIdx.x;
+    if (q < r.n_ranks) {
+        volatile unsigned long long *f = r.flags[r.rank] + q;
+        long long t0 = clock64();
+        while (*f < epoch) {
+            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; do not hang the GPU
+                *error = epoch;
+                break;
+            }
+        }
+        __threadfence_system();
+        recv_counts[q] = *((volatile unsigned long long *)(r.counts[r.rank] + q));
+    }
+}
+int fries_comm_route_publish(fries_comm *cm, const unsigned long long *d_send_counts) {
+    cm->route_epoch++;
+    route_publish_kernel<<<1, 32, 0, cm->ctx->stream>>>(cm->route, d_send_counts, cm->route_epoch);
+    cm->ctx->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return FRIES_OK;
+}
+int fries_comm_route_wait(fries_comm *cm, unsigned long long *d_recv_counts) {
+    route_wait_kernel<<<1, 32, 0, cm->ctx->stream>>>(cm->route, cm->route_epoch, d_recv_counts, cm->view.error);
+    cm->ctx->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return FRIES_OK;
+}
+
 extern "C" int fries_comm_destroy(fries_comm *cm) {
     if (!cm) return FRIES_OK;
     cudaSetDevice(cm->ctx->device);
+    for (int p = 0; p < cm->n_ranks; p++)
+        if (p != cm->rank && cm->win_peer[p]) cudaIpcCloseMemHandle(cm->win_peer[p]);
+    if (cm->win_local) cudaFree(cm->win_local);
     for (int p = 0; p < cm->n_ranks; p++)
         if (p != cm->rank && cm->peer[p]) cudaIpcCloseMemHandle(cm->peer[p]);
     if (cm->local) cudaFree(cm->local);

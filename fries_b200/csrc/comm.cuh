@@ -136,11 +136,31 @@ __device__ __forceinline__ unsigned long long comm_sum_u64(const CommView &cm, c
     return t;
 }
 
+// Receive window of the spawn route (Adder::perform_add vec_utils.hpp:991-1019 without a collective call): every
+// rank owns [n_ranks sources][keys[seg_cap] | value bits[seg_cap]] + counts[n_ranks] + flags[n_ranks] in its HBM,
+// mapped into every peer.  The spawn kernel of source r stores an element owned by rank p straight into
+// win[p] segment r over NVLink (slots from a LOCAL per-destination counter: a (source, destination) pair has its own
+// segment, so no remote atomics); a one-warp kernel then publishes the counts and an epoch flag to the peers, and the
+// receiving side waits on its own flags before it merges.
+struct RouteView {
+    uint64_t *win[FR_MAX_RANKS];               // win[p]: rank p's window
+    unsigned long long *counts[FR_MAX_RANKS];  // counts[p]: [n_ranks] on rank p (entry r written by source r)
+    unsigned long long *flags[FR_MAX_RANKS];   // flags[p]:  [n_ranks] epochs on rank p
+    unsigned long long seg_cap;
+    int n_ranks, rank;
+};
+
 struct fries_comm {
     fries_ctx *ctx = nullptr;
     int n_ranks = 1, rank = 0;
     void *local = nullptr;                 // this rank's inbox + flags + epoch + error (one allocation)
     void *peer[FR_MAX_RANKS] = {nullptr};  // mapped peers (peer[rank] == local)
     CommView view;
+    // spawn route window (fries_comm_route_create / _connect); win_local == nullptr: no window
+    void *win_local = nullptr;
+    void *win_peer[FR_MAX_RANKS] = {nullptr};
+    size_t seg_cap = 0;
+    unsigned long long route_epoch = 0;    // host-side: one per exchange, identical on all ranks
+    RouteView route;
 };
 CommView fries_comm_view(const fries_comm *cm);  // n_ranks = 1 view when cm == nullptr

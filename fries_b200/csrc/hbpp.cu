@@ -328,7 +328,8 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
             base = __shfl_sync(peers, base, leader);
             unsigned long long slot = base + rank_in;
             if (slot < sp.seg_cap) {
-                uint64_t *seg = sp.send_buf + (size_t)owner * 2 * sp.seg_cap;
+                uint64_t *seg = sp.peer_win[owner] ? sp.peer_win[owner] + (size_t)sp.rank * 2 * sp.seg_cap
+                                                   : sp.send_buf + (size_t)owner * 2 * sp.seg_cap;
                 seg[slot] = nk;
                 seg[sp.seg_cap + slot] = (uint64_t)__double_as_longlong(add);
             } else {
@@ -480,7 +481,7 @@ int fries_hbpp_stages_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys
 int fries_hbpp_finalize_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, double p_doub, int new_hb,
                             const HbSpawnArgs *spawn) {
     fries_ctx *c = hb->ctx;
-    HbSpawnArgs sp{nullptr, 0, 0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0};
+    HbSpawnArgs sp{nullptr, 0, 0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0, {nullptr}, 0};
     if (spawn) sp = *spawn;
     size_t smem = (size_t)mol->view.d.blob_doubles * 8;
     int grid = c->sm_count * 4;

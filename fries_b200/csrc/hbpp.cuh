@@ -52,6 +52,9 @@ struct fries_hbpp {
     int64_t *send_buf = nullptr, *recv_buf = nullptr;  // caller-owned device buffers [n_ranks][2 * seg_cap]
     unsigned long long *send_counts_ext = nullptr;     // caller-owned [n_ranks + 1]: per-destination counts + overflow
     size_t seg_cap = 0;
+    // direct route: the windows live in `comm` (fries_comm_route_create); counters are owned here
+    bool p2p = false;
+    DevBuf<unsigned long long> p2p_send_counts, p2p_recv_counts;
 };
 
 // stages = false: only the reduction scratch and counters (spawn buffers are added by the caller)
@@ -75,6 +78,10 @@ struct HbSpawnArgs {
     uint64_t *send_buf;                    // [n_ranks][2 * seg_cap]
     unsigned long long *send_counts;       // [n_ranks] + [n_ranks] = overflow counter
     unsigned long long seg_cap;
+    // direct route (comm.cuh RouteView): peer_win[p] != nullptr -> elements owned by rank p are stored straight into
+    // segment `rank` of p's receive window over NVLink instead of the local send buffer
+    uint64_t *peer_win[FR_MAX_RANKS];
+    int rank;
 };
 int fries_hbpp_finalize_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, double p_doub, int new_hb,
                             const HbSpawnArgs *spawn);

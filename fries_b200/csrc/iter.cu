@@ -505,7 +505,8 @@ extern "C" int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hb
     // steps 2-3: hierarchical compression of H's columns
     FRIES_TRY(fries_hbpp_stages_dev(hb, mol, v.keys, v.vals, &vec->cnt.p->n, p->p_doub, p->new_hb, u6, p->matr_samp));
     // step 5: spawn (fused into finalize) and merge into row 1
-    HbSpawnArgs sp{v.vals, p->eps, p->init_thresh, hb->spawn_keys.p, hb->spawn_vals.p, 1, nullptr, nullptr, nullptr, 0};
+    HbSpawnArgs sp{v.vals, p->eps, p->init_thresh, hb->spawn_keys.p, hb->spawn_vals.p, 1, nullptr, nullptr, nullptr, 0,
+                   {nullptr}, 0};
     FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, v.keys, p->p_doub, p->new_hb, &sp));
     FRIES_TRY(fries_vec_merge_dev(vec, hb->spawn_keys.p, hb->spawn_vals.p, hb->cap, &hb->st.p[4].n_out, 0, 1));
     // step 7: death/cloning, add_vecs(0, 1), zero row 1
@@ -530,7 +531,8 @@ extern "C" int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hb
 // counts + payload -> finish [merge, death/cloning, compression].  Global reductions inside the
 // kernels go through the peer-mapped inboxes (comm.cuh).
 // ---------------------------------------------------------------------------------------------------
-struct fries_comm;
+int fries_comm_route_publish(fries_comm *cm, const unsigned long long *d_send_counts);
+int fries_comm_route_wait(fries_comm *cm, unsigned long long *d_recv_counts);
 extern "C" int fries_hbpp_set_route(fries_hbpp *hb, fries_comm *comm, void *d_send_buf, void *d_recv_buf,
                                     void *d_send_counts, size_t seg_cap) {
     FRIES_REQUIRE(hb && comm && d_send_buf && d_recv_buf && d_send_counts && seg_cap > 0, "fries_hbpp_set_route: bad argument");
@@ -568,25 +570,50 @@ __global__ void xrank_stats_kernel(CommView cm, double *scal, const VecCounters 
 extern "C" int fries_frisys_mol_spawn(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
                                       const double *u6) {
     FRIES_REQUIRE(vec && mol && hb && p && u6, "fries_frisys_mol_spawn: NULL argument");
-    FRIES_REQUIRE(hb->comm && hb->send_buf, "fries_frisys_mol_spawn: call fries_hbpp_set_route first");
+    FRIES_REQUIRE(hb->comm && (hb->send_buf || hb->p2p),
+                  "fries_frisys_mol_spawn: call fries_hbpp_set_route or fries_hbpp_set_route_p2p first");
     fries_ctx *c = vec->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     VecView v = vec->view();
     CUDA_TRY(cudaMemsetAsync(hb->send_counts_ext, 0, (vec->n_ranks + 1) * 8, c->stream));
     FRIES_TRY(fries_hbpp_stages_dev(hb, mol, v.keys, v.vals, &vec->cnt.p->n, p->p_doub, p->new_hb, u6, p->matr_samp));
     HbSpawnArgs sp{v.vals, p->eps, p->init_thresh, nullptr, nullptr, vec->n_ranks, v.scr_proc, (uint64_t *)hb->send_buf,
-                   hb->send_counts_ext, (unsigned long long)hb->seg_cap};
+                   hb->send_counts_ext, (unsigned long long)hb->seg_cap, {nullptr}, vec->rank};
+    if (hb->p2p)
+        for (int q = 0; q < vec->n_ranks; q++) sp.peer_win[q] = hb->comm->route.win[q];
     FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, v.keys, p->p_doub, p->new_hb, &sp));
+    // direct route: the elements are already in their owners' windows; publish counts + epoch flag to the peers
+    if (hb->p2p) FRIES_TRY(fries_comm_route_publish(hb->comm, hb->send_counts_ext));
+    return FRIES_OK;
+}
+
+// Direct spawn route over peer-mapped windows (comm.cuh RouteView): no collective call, no host round trip between
+// _spawn and _finish.  The window (fries_comm_route_create / _connect) fixes the segment capacity.
+extern "C" int fries_hbpp_set_route_p2p(fries_hbpp *hb, fries_comm *comm) {
+    FRIES_REQUIRE(hb && comm && comm->win_local, "fries_hbpp_set_route_p2p: create and connect the route window first");
+    CUDA_TRY(cudaSetDevice(hb->ctx->device));
+    hb->comm = comm;
+    hb->p2p = true;
+    hb->seg_cap = comm->seg_cap;
+    FRIES_TRY(hb->p2p_send_counts.alloc(FR_MAX_RANKS + 1));
+    FRIES_TRY(hb->p2p_recv_counts.alloc(FR_MAX_RANKS));
+    hb->send_counts_ext = hb->p2p_send_counts.p;
+    hb->send_buf = nullptr;
+    hb->recv_buf = (int64_t *)comm->win_local;
     return FRIES_OK;
 }
 
 extern "C" int fries_frisys_mol_finish(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
                                        const double *u6, const void *d_recv_counts, fries_iter_stats *stats) {
-    FRIES_REQUIRE(vec && mol && hb && p && u6 && d_recv_counts, "fries_frisys_mol_finish: NULL argument");
+    FRIES_REQUIRE(vec && mol && hb && p && u6 && (d_recv_counts || hb->p2p), "fries_frisys_mol_finish: NULL argument");
     fries_ctx *c = vec->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     VecView v = vec->view();
     size_t smem = (size_t)mol->view.d.blob_doubles * 8;
+    if (hb->p2p) {  // wait for every source's epoch flag; the counts arrive with it
+        FRIES_TRY(fries_comm_route_wait(hb->comm, hb->p2p_recv_counts.p));
+        d_recv_counts = hb->p2p_recv_counts.p;
+    }
     MergeSrc src{(const uint64_t *)hb->recv_buf, nullptr, (size_t)vec->n_ranks * hb->seg_cap, nullptr,
                  (const unsigned long long *)d_recv_counts, hb->seg_cap};
     FRIES_TRY(fries_vec_merge_src_dev(vec, src, 0, 1));

@@ -10,6 +10,7 @@ This module is plumbing only: buffers are torch tensors, all arithmetic is in li
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -37,6 +38,14 @@ class Comm:
         handles = gather_bytes(dist, bytes(handle), world, device)
         blob = b"".join(handles)
         check(lib.fries_comm_connect(self.h, blob))
+        dist.barrier()
+
+    def open_route(self, dist, seg_cap: int, device):
+        """receive window of the direct spawn route (fries_comm_route_create / _connect)"""
+        handle = (C.c_uint8 * 64)()
+        check(lib.fries_comm_route_create(self.h, seg_cap, handle))
+        blob = b"".join(gather_bytes(dist, bytes(handle), self.world, device))
+        check(lib.fries_comm_route_connect(self.h, blob))
         dist.barrier()
 
     def error_epoch(self) -> int:
@@ -75,22 +84,29 @@ def owned_slice(owner: np.ndarray, rank: int):
 
 
 class MultiGpuFrisys:
-    """frisys_mol loop body over n_ranks GPUs: spawn -> all-to-all -> finish"""
+    """frisys_mol loop body over n_ranks GPUs.  route = "p2p" (default): the spawn kernel stores every element straight
+    into its owner's receive window over NVLink and _finish waits on epoch flags -- no collective, no host round trip;
+    route = "nccl": spawn -> all_to_all_single (counts, then fixed-capacity segments) -> finish."""
 
     def __init__(self, ctx, dist, rank, world, mol, sm, max_dets_local, spawn_cap_local, seg_cap, proc_scr, vec_scr,
-                 hf_en, trial, htrial):
+                 hf_en, trial, htrial, route="p2p"):
         from .api import Vec
-        self.ctx, self.dist, self.rank, self.world = ctx, dist, rank, world
+        self.ctx, self.dist, self.rank, self.world, self.route = ctx, dist, rank, world, route
         device = torch.device("cuda", torch.cuda.current_device())
         self.comm = Comm(ctx, dist, rank, world, device)
-        self.router = Router(dist, world, seg_cap, device)
+        self.seg_cap = seg_cap
         self.vec = Vec(ctx, max_dets_local, sm.n_bits, sm.n_elec, 2, proc_scr, vec_scr, world, rank)
         self.vec.set_diag_mol(mol, hf_en)
         self.vec.frisys_setup(mol, spawn_cap_local, trial[0], trial[1], htrial[0], htrial[1])
         self.mol = mol
-        r = self.router
-        check(lib.fries_hbpp_set_route(self.vec.hb, self.comm.h, r.send_buf.data_ptr(), r.recv_buf.data_ptr(),
-                                       r.send_counts.data_ptr(), seg_cap))
+        if route == "p2p":
+            self.router = None
+            self.comm.open_route(dist, seg_cap, device)
+            check(lib.fries_hbpp_set_route_p2p(self.vec.hb, self.comm.h))
+        else:
+            self.router = r = Router(dist, world, seg_cap, device)
+            check(lib.fries_hbpp_set_route(self.vec.hb, self.comm.h, r.send_buf.data_ptr(), r.recv_buf.data_ptr(),
+                                           r.send_counts.data_ptr(), seg_cap))
 
     def load(self, keys, vals, owner):
         idx = owned_slice(owner, self.rank)
@@ -102,11 +118,24 @@ class MultiGpuFrisys:
     def iterate(self, params: FrisysParams, uniforms6) -> IterStats:
         u = arr(uniforms6, np.float64)
         check(lib.fries_frisys_mol_spawn(self.vec.h, self.mol.h, self.vec.hb, C.byref(params), ptr(u)))
-        self.router.exchange()
         st = IterStats()
-        check(lib.fries_frisys_mol_finish(self.vec.h, self.mol.h, self.vec.hb, C.byref(params), ptr(u),
-                                          self.router.recv_counts.data_ptr(), C.byref(st)))
+        if self.router is None:
+            check(lib.fries_frisys_mol_finish(self.vec.h, self.mol.h, self.vec.hb, C.byref(params), ptr(u), None,
+                                              C.byref(st)))
+        else:
+            self.router.exchange()
+            check(lib.fries_frisys_mol_finish(self.vec.h, self.mol.h, self.vec.hb, C.byref(params), ptr(u),
+                                              self.router.recv_counts.data_ptr(), C.byref(st)))
         return st
+
+    @property
+    def route_description(self):
+        if self.router is None:
+            return {"collective": "none: the spawn kernel stores into the owners' peer-mapped receive windows over "
+                                  "NVLink (csrc/comm.cuh RouteView), epoch flags instead of a barrier",
+                    "bytes_per_rank_per_step": "16 B per spawned element (only what was spawned)"}
+        return {"collective": "nccl all_to_all_single (counts + fixed-capacity segments)",
+                "bytes_per_rank_per_step": self.router.bytes_sent_per_exchange}
 
     def close(self):
         self.vec.close()
@@ -131,7 +160,8 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
     spawn_cap_local = 4 * gcfg["mat_nonz"] // world          # spawn_length = matr_samp * 4 / n_procs
     seg_cap = 2 * gcfg["mat_nonz"] // (world * world) + 8192
     eng = MultiGpuFrisys(ctx, dist, rank, world, mol, sm, cfg["max_dets"], spawn_cap_local, seg_cap, wl["proc_scr"],
-                         wl["vec_scr"], wl["hf_en"], (wl["hf"], np.ones(1)), (wl["htrial_keys"], wl["htrial_vals"]))
+                         wl["vec_scr"], wl["hf_en"], (wl["hf"], np.ones(1)), (wl["htrial_keys"], wl["htrial_vals"]),
+                         route=os.environ.get("FRIES_ROUTE", "p2p"))
     eng.load(wl["keys"], wl["vals"], owner)
     params = FrisysParams(eps=cfg["eps"], init_thresh=cfg["initiator"], p_doub=wl["p_doub"],
                           new_hb=1 if cfg["dist"] == "HB_unnorm" else 0, matr_samp=gcfg["mat_nonz"],
@@ -175,9 +205,8 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
             "spawned_elements_per_sec": round(spawned / (ms * 1e-3), 1),
             "determinant_updates_per_sec": round(gcfg["vec_nonz"] * args.steps / (ms * 1e-3), 1),
             "gpu_launches": int(ctx.launch_count - launches0), "clocks": clk,
-            "route": {"collective": "nccl all_to_all_single (counts + fixed-capacity segments)",
-                      "bytes_per_rank_per_step": eng.router.bytes_sent_per_exchange,
-                      "scalar_reductions": "in-kernel, peer-mapped inboxes over NVLink (csrc/comm.cuh)"},
+            "route": dict(eng.route_description,
+                          scalar_reductions="in-kernel, peer-mapped inboxes over NVLink (csrc/comm.cuh)"),
             "e2e": {"value": round(1000.0 / ms_per_step, 3), "unit": "iter/s", "h2d_bytes_per_step": 48,
                     "d2h_bytes_per_step": 128,
                     "what": "fries_frisys_mol_spawn + all_to_all + fries_frisys_mol_finish per step; the vector is "

@@ -263,6 +263,14 @@ int fries_comm_error(fries_comm *comm, uint64_t *epoch_of_failure);
 int fries_ctx_set_comm(fries_ctx *ctx, fries_comm *comm);
 int fries_hbpp_set_route(fries_hbpp *hb, fries_comm *comm, void *d_send_buf, void *d_recv_buf, void *d_send_counts,
                          size_t seg_cap);
+/* Direct route (preferred): every rank owns a receive window [n_ranks sources][keys[seg_cap] | value bits[seg_cap]]
+ * mapped into its peers (same IPC handshake as the inboxes).  The spawn kernel stores each element straight into its
+ * owner's window over NVLink / NVSwitch -- routing is fused into the kernel that produces the elements -- and
+ * _finish waits on per-source epoch flags; there is no collective call and no host round trip between _spawn and
+ * _finish, and fries_frisys_mol_finish takes d_recv_counts = NULL. */
+int fries_comm_route_create(fries_comm *comm, size_t seg_cap, void *h_ipc_handle64);
+int fries_comm_route_connect(fries_comm *comm, const void *h_all_handles);
+int fries_hbpp_set_route_p2p(fries_hbpp *hb, fries_comm *comm);
 /* frisys_mol.cpp:405-471 up to Adder::add; then, after the all-to-all, :465-539 from add_elements on.
  * stats of _finish are global (summed over ranks in rank order). */
 int fries_frisys_mol_spawn(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, const fries_frisys_params *p,
