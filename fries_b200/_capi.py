@@ -82,6 +82,7 @@ def _load():
         "fries_apply_hbpp_sys": (i, [vp, vp, vp, sz, d, i, vp, u, sz, vp, vp, vp, sz, P(sz)]),
         "fries_debug_hbpp_stage": (i, [vp, vp, vp, sz, d, i, vp, u, sz, i, vp, vp, vp, vp, P(sz)]),
         "fries_hbpp_states": (i, [vp, vp]),
+        "fries_hbpp_round_stamps": (i, [vp, i, vp]),
         "fries_debug_set_repeat": (i, [i]),
         "fries_debug_set_bracket": (i, [i]),
         "fries_debug_set_perturb": (i, [d]),
@@ -90,6 +91,7 @@ def _load():
         "fries_comm_connect": (i, [vp, vp]),
         "fries_comm_destroy": (i, [vp]),
         "fries_comm_error": (i, [vp, P(C.c_uint64)]),
+        "fries_comm_pingpong": (i, [vp, i, i, i, P(d)]),
         "fries_ctx_set_comm": (i, [vp, vp]),
         "fries_hbpp_set_route": (i, [vp, vp, vp, vp, vp, sz]),
         "fries_comm_route_create": (i, [vp, sz, vp]),

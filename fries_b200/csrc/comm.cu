@@ -1,8 +1,10 @@
 // fries_comm: peer-mapped inboxes for the in-kernel cross-rank reductions (comm.cuh).
 #include "comm.cuh"
 
-#define FR_COMM_BYTES 8192
-// layout of one rank's allocation: [0, 4096) inbox doubles, [4096, 6144) flags, [6144] epoch, [6152] error
+#define FR_COMM_HEAD 8192
+// layout of one rank's allocation: [0, 4096) inbox words, [4096, 6144) unused, [6144] epoch, [6152] error,
+// [8192, ...) candidate windows: x[n_ranks][FR_COMM_XCAP] doubles, then mult[n_ranks][FR_COMM_XCAP] u32
+#define FR_COMM_BYTES(n_ranks) (FR_COMM_HEAD + (size_t)(n_ranks) * FR_COMM_XCAP * 12)
 #define FR_COMM_OFF_FLAGS 4096
 #define FR_COMM_OFF_EPOCH 6144
 #define FR_COMM_OFF_ERROR 6152
@@ -15,6 +17,8 @@ static void bind_view(fries_comm *cm) {
         char *base = (char *)(p < cm->n_ranks ? cm->peer[p] : nullptr);
         v.inbox[p] = (double *)base;
         v.flags[p] = (unsigned long long *)(base ? base + FR_COMM_OFF_FLAGS : nullptr);
+        v.cand_x[p] = (double *)(base ? base + FR_COMM_HEAD : nullptr);
+        v.cand_m[p] = (uint32_t *)(base ? base + FR_COMM_HEAD + (size_t)cm->n_ranks * FR_COMM_XCAP * 8 : nullptr);
     }
     v.epoch = (unsigned long long *)((char *)cm->local + FR_COMM_OFF_EPOCH);
     v.error = (unsigned long long *)((char *)cm->local + FR_COMM_OFF_ERROR);
@@ -38,8 +42,8 @@ extern "C" int fries_comm_create(fries_ctx *c, int n_ranks, int rank, fries_comm
     cm->ctx = c;
     cm->n_ranks = n_ranks;
     cm->rank = rank;
-    CUDA_TRY(cudaMalloc(&cm->local, FR_COMM_BYTES));
-    CUDA_TRY(cudaMemset(cm->local, 0, FR_COMM_BYTES));
+    CUDA_TRY(cudaMalloc(&cm->local, FR_COMM_BYTES(n_ranks)));
+    CUDA_TRY(cudaMemset(cm->local, 0, FR_COMM_BYTES(n_ranks)));
     cm->peer[rank] = cm->local;
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, cm->local));
@@ -162,6 +166,51 @@ extern "C" int fries_comm_destroy(fries_comm *cm) {
         if (p != cm->rank && cm->peer[p]) cudaIpcCloseMemHandle(cm->peer[p]);
     if (cm->local) cudaFree(cm->local);
     delete cm;
+    return FRIES_OK;
+}
+
+// Diagnostics: cost of one in-kernel exchange.  `iters` all-gathers of n doubles, a grid barrier between two of them,
+// in a cooperative grid of `ctas` CTAs of 512 threads (0: the compression kernels' launch shape).
+__global__ void __launch_bounds__(512) comm_pingpong_kernel(CommView cm, int iters, int n, double *out) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh_x[FR_COMM_PAYLOAD][FR_MAX_RANKS];
+    CommCursor cur = comm_begin(cm);
+    double acc = 0;
+    for (int it = 0; it < iters; it++) {
+        double vals[FR_COMM_PAYLOAD];
+        for (int k = 0; k < FR_COMM_PAYLOAD; k++) vals[k] = it + k + cm.rank;
+        comm_allgather_v(cm, cur, vals, n, sh_x);
+        acc += sh_x[0][0];
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out = acc;
+    grid.sync();
+    comm_end(cm, cur);
+}
+extern "C" int fries_comm_pingpong(fries_comm *cm, int ctas, int iters, int n, double *us_per_exchange) {
+    FRIES_REQUIRE(cm && us_per_exchange && iters > 0 && n >= 1 && n <= FR_COMM_PAYLOAD, "fries_comm_pingpong: bad argument");
+    fries_ctx *c = cm->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (ctas <= 0) ctas = c->coop_grid((const void *)comm_pingpong_kernel, 512, 0);
+    DevBuf<double> out;
+    FRIES_TRY(out.alloc(1));
+    CommView v = cm->view;
+    double *po = out.p;
+    void *args[] = {(void *)&v, (void *)&iters, (void *)&n, (void *)&po};
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {  // the first launch absorbs the skew between the ranks
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)comm_pingpong_kernel, dim3(ctas), dim3(512), args, 0, c->stream));
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+    }
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *us_per_exchange = 1e3 * ms / iters;
     return FRIES_OK;
 }
 

@@ -10,12 +10,14 @@
 //
 // Slots are double buffered by epoch parity.  A rank can only publish epoch e+2 after all ranks published
 // e+1, and a rank publishes e+1 only after all its CTAs passed the grid.sync that follows their reads of
-// epoch e, so a slot is never overwritten while it is being read.
+// epoch e, so a slot is never overwritten while it is being read: TWO EXCHANGES OF ONE RANK MUST BE SEPARATED BY A
+// GRID BARRIER (every caller's rounds have one: the reduction that produces the next payload).
 #pragma once
 #include "common.cuh"
 
 #define FR_MAX_RANKS 8
 #define FR_COMM_PAYLOAD 12  // doubles per slot
+#define FR_COMM_XCAP 16384  // candidates one rank may contribute to a bracketed threshold solve (compress.cuh)
 
 struct CommView {
     int n_ranks, rank;
@@ -23,6 +25,11 @@ struct CommView {
     unsigned long long *flags[FR_MAX_RANKS];  // flags[p]: [2][n_ranks] epochs on rank p
     unsigned long long *epoch;                // local: next epoch to use (persists across kernels)
     unsigned long long *error;                // local: set when a poll times out
+    // candidate windows of the bracketed threshold solve: cand_x[p] / cand_m[p] = rank p's window,
+    // [n_ranks sources][FR_COMM_XCAP]; every rank stores its candidates into ALL windows, so that after one exchange
+    // every rank holds the complete list and solves it without further communication
+    double *cand_x[FR_MAX_RANKS];
+    uint32_t *cand_m[FR_MAX_RANKS];
 };
 
 struct CommCursor {
@@ -39,8 +46,66 @@ __device__ __forceinline__ void comm_end(const CommView &cm, const CommCursor &c
     if (cm.n_ranks > 1 && blockIdx.x == 0 && threadIdx.x == 0) *cm.epoch = c.e;
 }
 
-// All-gather of (d0, d1, c) across ranks.  Must be called by every thread of every CTA with grid-uniform
-// arguments.  out_* (shared memory, >= FR_MAX_RANKS entries) receive the per-rank values in rank order.
+// Exchange protocol ("LL": data and flag travel in the same 8-byte store, as in NCCL's low-latency protocol).  A
+// double is sent as two words (32 data bits | 32-bit epoch tag); a word is valid when its tag equals the epoch, so an
+// exchange costs ONE NVLink traversal: no __threadfence_system between payload and flag on the writer, none between
+// flag and payload on the reader.  Layout of rank p's inbox: [2 parities][n_ranks sources][2 * FR_COMM_PAYLOAD] words.
+__device__ __forceinline__ void comm_exchange_ll(const CommView &cm, CommCursor &cur, const double *vals, int n,
+                                                 double (*out)[FR_MAX_RANKS]) {
+    __shared__ unsigned sh_stage[FR_MAX_RANKS][2 * FR_COMM_PAYLOAD];
+    const unsigned long long e = cur.e + 1;  // epochs start at 1; the inbox starts zeroed
+    const unsigned tag = (unsigned)e;
+    const int par = (int)(e & 1), nw = 2 * n, total = cm.n_ranks * nw;
+    if (blockIdx.x == 0) {
+        for (int t = threadIdx.x; t < total; t += blockDim.x) {
+            int p = t / nw, w = t - p * nw;
+            unsigned long long bits = (unsigned long long)__double_as_longlong(vals[w >> 1]);
+            unsigned data = (w & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+            volatile unsigned long long *slot = (volatile unsigned long long *)cm.inbox[p] +
+                                                ((size_t)par * cm.n_ranks + cm.rank) * (2 * FR_COMM_PAYLOAD) + w;
+            *slot = (unsigned long long)data | ((unsigned long long)tag << 32);
+        }
+    }
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        int q = t / nw, w = t - q * nw;
+        volatile unsigned long long *slot = (volatile unsigned long long *)cm.inbox[cm.rank] +
+                                            ((size_t)par * cm.n_ranks + q) * (2 * FR_COMM_PAYLOAD) + w;
+        unsigned long long v = *slot;
+        long long t0 = clock64();
+        while ((unsigned)(v >> 32) != tag) {
+            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; do not hang the GPU
+                *cm.error = e;
+                break;
+            }
+            v = *slot;
+        }
+        sh_stage[q][w] = (unsigned)v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < cm.n_ranks * n; t += blockDim.x) {
+        int q = t / n, k = t - q * n;
+        unsigned long long bits = (unsigned long long)sh_stage[q][2 * k] | ((unsigned long long)sh_stage[q][2 * k + 1] << 32);
+        out[k][q] = __longlong_as_double((long long)bits);
+    }
+    __syncthreads();
+    cur.e = e;
+}
+
+// All-gather of n <= FR_COMM_PAYLOAD doubles per rank.  Must be called by every thread of every CTA with grid-uniform
+// arguments, and two exchanges of one rank must be separated by a grid barrier (see the header comment).
+// out is shared memory [n][FR_MAX_RANKS].
+__device__ __forceinline__ void comm_allgather_v(const CommView &cm, CommCursor &cur, const double *vals, int n,
+                                                 double (*out)[FR_MAX_RANKS]) {
+    if (cm.n_ranks <= 1) {
+        if (threadIdx.x == 0)
+            for (int k = 0; k < n; k++) out[k][0] = vals[k];
+        __syncthreads();
+        return;
+    }
+    comm_exchange_ll(cm, cur, vals, n, out);
+}
+
+// All-gather of (d0, d1, c) across ranks; out_* (shared memory, >= FR_MAX_RANKS entries) in rank order.
 __device__ __forceinline__ void comm_allgather(const CommView &cm, CommCursor &cur, double d0, double d1,
                                                unsigned long long c, double *out_d0, double *out_d1,
                                                unsigned long long *out_c) {
@@ -53,71 +118,15 @@ __device__ __forceinline__ void comm_allgather(const CommView &cm, CommCursor &c
         __syncthreads();
         return;
     }
-    const unsigned long long e = cur.e + 1;  // epochs start at 1; flags start at 0
-    const int par = (int)(e & 1);
-    if (blockIdx.x == 0 && threadIdx.x < cm.n_ranks) {
-        int p = threadIdx.x;
-        double *slot = cm.inbox[p] + ((size_t)par * cm.n_ranks + cm.rank) * FR_COMM_PAYLOAD;
-        slot[0] = d0;
-        slot[1] = d1;
-        slot[2] = __longlong_as_double((long long)c);
-        __threadfence_system();
-        *((volatile unsigned long long *)(cm.flags[p] + (size_t)par * cm.n_ranks + cm.rank)) = e;
-    }
+    __shared__ double sh_o[3][FR_MAX_RANKS];
+    double vals[3] = {d0, d1, __longlong_as_double((long long)c)};
+    comm_exchange_ll(cm, cur, vals, 3, sh_o);
     if (threadIdx.x < cm.n_ranks) {
-        int q = threadIdx.x;
-        volatile unsigned long long *f = cm.flags[cm.rank] + (size_t)par * cm.n_ranks + q;
-        long long t0 = clock64();
-        while (*f < e) {
-            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; do not hang the GPU
-                *cm.error = e;
-                break;
-            }
-        }
-        __threadfence_system();
-        const volatile double *slot = cm.inbox[cm.rank] + ((size_t)par * cm.n_ranks + q) * FR_COMM_PAYLOAD;
-        out_d0[q] = slot[0];
-        out_d1[q] = slot[1];
-        out_c[q] = (unsigned long long)__double_as_longlong(slot[2]);
+        out_d0[threadIdx.x] = sh_o[0][threadIdx.x];
+        out_d1[threadIdx.x] = sh_o[1][threadIdx.x];
+        out_c[threadIdx.x] = (unsigned long long)__double_as_longlong(sh_o[2][threadIdx.x]);
     }
     __syncthreads();
-    cur.e = e;
-}
-
-// All-gather of n <= FR_COMM_PAYLOAD doubles per rank.  out is shared memory [n][FR_MAX_RANKS].
-__device__ __forceinline__ void comm_allgather_v(const CommView &cm, CommCursor &cur, const double *vals, int n,
-                                                 double (*out)[FR_MAX_RANKS]) {
-    if (cm.n_ranks <= 1) {
-        if (threadIdx.x == 0)
-            for (int k = 0; k < n; k++) out[k][0] = vals[k];
-        __syncthreads();
-        return;
-    }
-    const unsigned long long e = cur.e + 1;
-    const int par = (int)(e & 1);
-    if (blockIdx.x == 0 && threadIdx.x < cm.n_ranks) {
-        int p = threadIdx.x;
-        double *slot = cm.inbox[p] + ((size_t)par * cm.n_ranks + cm.rank) * FR_COMM_PAYLOAD;
-        for (int k = 0; k < n; k++) slot[k] = vals[k];
-        __threadfence_system();
-        *((volatile unsigned long long *)(cm.flags[p] + (size_t)par * cm.n_ranks + cm.rank)) = e;
-    }
-    if (threadIdx.x < cm.n_ranks) {
-        int q = threadIdx.x;
-        volatile unsigned long long *f = cm.flags[cm.rank] + (size_t)par * cm.n_ranks + q;
-        long long t0 = clock64();
-        while (*f < e) {
-            if (clock64() - t0 > 20000000000ll) {
-                *cm.error = e;
-                break;
-            }
-        }
-        __threadfence_system();
-        const volatile double *slot = cm.inbox[cm.rank] + ((size_t)par * cm.n_ranks + q) * FR_COMM_PAYLOAD;
-        for (int k = 0; k < n; k++) out[k][q] = slot[k];
-    }
-    __syncthreads();
-    cur.e = e;
 }
 
 // rank-ordered sums (sum_mpi): total over all ranks and the prefix over the ranks before this one

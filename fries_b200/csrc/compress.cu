@@ -47,6 +47,7 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
     const double t_lo = t_pred * (1.0 - h_pred), t_hi = t_pred * (1.0 + h_pred);
     double s = 0, s_hi = 0;
     unsigned long long c_hi = 0;
+    bool appended = false;
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         double m = fabs(vals[i]);
         s += m;
@@ -55,10 +56,12 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
                 c_hi++;
                 s_hi += m;
             } else {
-                cand_append(cand, m, 1u);
+                cand_append(cand, cm, m, 1u);
+                appended = true;
             }
         }
     }
+    cand_flush(cm, appended);
     unsigned long long dummy = 0;
     {
         double dd[2] = {s, s_hi};
@@ -69,10 +72,12 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
         c_hi = cc[0];
     }
     double loc = s, R_next = s;
-    bool peers_ok = try_fast ? bracket_list_fits(cand, sh_c) : false;
-    if (multi) {  // *global_norm = sum_mpi(loc_one_norm) (:50); the bracket statistics ride along
-        double pay[4] = {s, s_hi, (double)c_hi, peers_ok ? 1.0 : 0.0};
-        comm_allgather_v(cm, cur, pay, 4, sh_x);
+    __shared__ unsigned long long sh_seg[FR_MAX_RANKS];
+    const unsigned long long my_cand = try_fast ? bracket_list_len(cand, sh_c) : 0ull;
+    bool peers_ok = try_fast && my_cand <= (multi ? (unsigned long long)FR_COMM_XCAP : (unsigned long long)FR_CAND_GCAP);
+    if (multi) {  // *global_norm = sum_mpi(loc_one_norm) (:50); the bracket statistics and list lengths ride along
+        double pay[5] = {s, s_hi, (double)c_hi, peers_ok ? 1.0 : 0.0, (double)my_cand};
+        comm_allgather_v(cm, cur, pay, 5, sh_x);
         double before;
         comm_sum(cm, sh_x[0], R_next, before);
         double gs = 0, gc = 0;
@@ -81,8 +86,10 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
             gc += sh_x[2][p];
             if (sh_x[3][p] == 0.0) peers_ok = false;
         }
+        if (threadIdx.x < cm.n_ranks) sh_seg[threadIdx.x] = (unsigned long long)sh_x[4][threadIdx.x];
         s_hi = gs;
         c_hi = (unsigned long long)gc;
+        if (try_fast) __threadfence_system();  // acquire side: the peers' candidates in this rank's window
         __syncthreads();
     }
     const double glob_total = R_next;
@@ -94,7 +101,7 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
     unsigned long long n_cand = 0;
     if (try_fast) {
         BracketResult br = bracket_solve(grid, cand, st->gacc, glob_total - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo,
-                                         t_hi, sh_d, sh_c, cm, cur, sh_x, peers_ok);
+                                         t_hi, sh_d, sh_c, cm, sh_seg, peers_ok);
         n_cand = br.n_cand;
         if (br.valid) {
             // one pass: keep flags of the cut + exact residual norm (:78-90)

@@ -29,6 +29,8 @@ struct CompState {
     unsigned long long fast;     // 1: the bracketed solve decided the preserved set, 0: plain rounds
     unsigned long long ts[8];    // %globaltimer (ns) of CTA 0 at the phase boundaries of comp_sub_engine
     unsigned long long gacc[40]; // grid-wide integer accumulators of the distributed candidate rounds (zeroed by the host)
+    unsigned long long rts[16];  // %globaltimer of CTA 0 inside distributed rounds 0-3: start, before / after the grid
+                                 // barrier, after the cross-rank exchange
 };
 
 __device__ __forceinline__ unsigned long long fr_globaltimer() {
@@ -210,14 +212,29 @@ struct CandList {
     unsigned long long *count;  // appended so far (may exceed the capacity: then the bracket is invalid)
 };
 
-__device__ __forceinline__ void cand_append(const CandList &cl, double x, uint32_t mult) {
+// Single rank: the list lives in cl.x / cl.mult.  Several ranks: the slot comes from the same local counter, and the
+// candidate is stored into segment `rank` of EVERY rank's window (comm.cuh).  The caller issues ONE system-scope fence
+// per thread after its collection loop (cand_flush), then a grid barrier; its first cross-rank exchange after that
+// publishes the counts, and every rank solves the merged list on its own.
+__device__ __forceinline__ void cand_append(const CandList &cl, const CommView &cm, double x, uint32_t mult) {
     // once the list has overflowed the bracket is invalid anyway: stop hammering the counter
-    if (*(volatile unsigned long long *)cl.count > FR_CAND_GCAP) return;
+    const unsigned long long cap = cm.n_ranks > 1 ? FR_COMM_XCAP : FR_CAND_GCAP;
+    if (*(volatile unsigned long long *)cl.count > cap) return;
     unsigned long long k = atomicAdd(cl.count, 1ull);
-    if (k < FR_CAND_GCAP) {
+    if (k >= cap) return;
+    if (cm.n_ranks > 1) {
+        for (int p = 0; p < cm.n_ranks; p++) {
+            cm.cand_x[p][(size_t)cm.rank * FR_COMM_XCAP + k] = x;
+            cm.cand_m[p][(size_t)cm.rank * FR_COMM_XCAP + k] = mult;
+        }
+    } else {
         cl.x[k] = x;
         cl.mult[k] = mult;
     }
+}
+
+__device__ __forceinline__ void cand_flush(const CommView &cm, bool appended) {
+    if (cm.n_ranks > 1 && appended) __threadfence_system();
 }
 
 struct BracketResult {
@@ -248,24 +265,22 @@ __device__ long long fr_bt[16];
 // vectors: the list grows like the square root of the vector length) are split across the CTAs, FR_CAND_CAP each;
 // the per-round totals then go through integer atomics on gacc (CompState) and one grid barrier per round.
 //
-// Several ranks (cm.n_ranks > 1): R0 / nrem0 are the global values, every rank runs the rounds on its own candidates
-// in the grid-distributed form (the cross-rank protocol of comm.cuh needs a grid barrier between two exchanges) and
-// the per-round integer totals are all-gathered and summed; all ranks take identical decisions.  `peers_ok` must be
-// the AND over the ranks of local_list_fits() (the caller exchanges it with its own first all-gather).
-__device__ __forceinline__ bool bracket_list_fits(const CandList &cl, unsigned long long *shc) {
+// Several ranks (cm.n_ranks > 1): R0 / nrem0 are the global values and the list is the concatenation, in rank order, of
+// the ranks' segments in this rank's candidate window (cand_append stored them there; `seg_len` = their lengths from the
+// caller's first all-gather, which also orders the remote stores).  Every rank solves the identical list with identical
+// arithmetic: no communication inside the solve.  `peers_ok`: every rank's list fitted its segment.
+__device__ __forceinline__ unsigned long long bracket_list_len(const CandList &cl, unsigned long long *shc) {
     if (threadIdx.x == 0) shc[20] = __ldcg(cl.count);
     __syncthreads();
     unsigned long long ncand = shc[20];
     __syncthreads();
-    unsigned long long gcap = (unsigned long long)gridDim.x * FR_CAND_CAP;
-    if (gcap > FR_CAND_GCAP) gcap = FR_CAND_GCAP;
-    return ncand <= gcap;
+    return ncand;
 }
 __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, const CandList &cl,
                                                        unsigned long long *gacc, double R0, long long nrem0,
                                                        double t_lo, double t_hi, double *shd, unsigned long long *shc,
-                                                       const CommView &cm, CommCursor &cur,
-                                                       double (*sh_x)[FR_MAX_RANKS], bool peers_ok) {
+                                                       const CommView &cm, const unsigned long long *seg_len,
+                                                       bool peers_ok) {
     (void)shd;
     const bool multi = cm.n_ranks > 1;
     BracketResult res;
@@ -277,15 +292,23 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
     res.rounds = 0;
     res.n_cand = 0;
     FR_BT(0);
-    if (threadIdx.x == 0) shc[20] = __ldcg(cl.count);
-    __syncthreads();
-    const unsigned long long ncand = shc[20];
+    unsigned long long ncand;
+    unsigned long long seg_end[FR_MAX_RANKS];  // multi: exclusive end of each rank's segment in the concatenation
+    if (multi) {
+        unsigned long long t = 0;
+        for (int p = 0; p < FR_MAX_RANKS; p++) {
+            if (p < cm.n_ranks) t += seg_len[p];
+            seg_end[p] = t;
+        }
+        ncand = t;
+    } else {
+        ncand = bracket_list_len(cl, shc);
+    }
     res.n_cand = ncand;
-    __syncthreads();
     unsigned long long gcap = (unsigned long long)gridDim.x * FR_CAND_CAP;
     if (gcap > FR_CAND_GCAP) gcap = FR_CAND_GCAP;
     if (ncand > gcap || !peers_ok || nrem0 <= 0 || nrem0 > 0xffffffffll) return res;
-    const bool dist = multi || ncand > FR_CAND_CAP;
+    const bool dist = ncand > FR_CAND_CAP;
     const unsigned long long slice0 = dist ? (unsigned long long)blockIdx.x * FR_CAND_CAP : 0ull;
     if (!(t_hi * (double)nrem0 >= R0)) return res;  // H is not certainly preserved
     // ulp(t_lo) = 2^(E_lo - 1075) with E_lo the biased exponent; every candidate is an integer multiple of it
@@ -301,8 +324,16 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
         x[k] = 0;
         mu[k] = 0;
         if (idx < ncand) {
-            x[k] = __ldcg(cl.x + idx);
-            mu[k] = __ldcg(cl.mult + idx);
+            if (multi) {
+                int q = 0;
+                while (idx >= seg_end[q]) q++;
+                size_t off = (size_t)q * FR_COMM_XCAP + (size_t)(idx - (q ? seg_end[q - 1] : 0ull));
+                x[k] = __ldcg(cm.cand_x[cm.rank] + off);
+                mu[k] = __ldcg(cm.cand_m[cm.rank] + off);
+            } else {
+                x[k] = __ldcg(cl.x + idx);
+                mu[k] = __ldcg(cl.mult + idx);
+            }
             state |= 1u << k;
         }
     }
@@ -318,9 +349,10 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
     unsigned __int128 sum_tot = 0;
     double R = R0;
     unsigned long long nrem = (unsigned long long)nrem0;
-    double xmin = INFINITY;
+    double xmin = INFINITY, dist_xmin = INFINITY;
     FR_BT(1);
     for (unsigned round = 0; round < 4096; round++) {
+        if (dist && round < 4 && blockIdx.x == 0 && threadIdx.x == 0) gacc[40 + 4 * round] = fr_globaltimer();
         unsigned *a = acc + 12 * (round & 1);
         unsigned long long c = 0;
         unsigned __int128 s = 0;
@@ -350,6 +382,12 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
                     if (lane == 0) atomicAdd(&a[q], w);
                 }
             }
+            if (dist) {  // running minimum of the preserved candidates (positive doubles order like their bit patterns)
+                double wm = xmin;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) wm = fmin(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+                if (lane == 0 && wm < INFINITY) atomicMin(acc_min, (unsigned long long)__double_as_longlong(wm));
+            }
         }
         // clear the other buffer for the next round (its readers passed the previous barrier)
         if (threadIdx.x < 12) acc[12 * ((round & 1) ^ 1) + threadIdx.x] = 0;
@@ -363,34 +401,29 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
             // CTA totals -> grid totals.  Three global buffers rotate: buffer (round + 1) % 3 was last read two rounds
             // ago (every CTA has passed the barrier after those reads), so CTA 0 may clear it before this barrier.
             unsigned long long *g = gacc + 12 * (round % 3);
+            unsigned long long *rts = gacc + 40;  // CompState::rts follows gacc
+            if (round < 4 && blockIdx.x == 0 && threadIdx.x == 0) rts[4 * round + 1] = fr_globaltimer();
             if (round == 0) FR_BT(8);
             if (threadIdx.x < 11 && a[threadIdx.x]) atomicAdd(&g[threadIdx.x], (unsigned long long)a[threadIdx.x]);
+            // gacc[36] (zeroed by the host) collects max(inf_bits - bits) = the smallest preserved magnitude so far
+            if (threadIdx.x == 11 && *acc_min < 0x7ff0000000000000ull) atomicMax(&gacc[36], 0x7ff0000000000000ull - *acc_min);
             if (blockIdx.x == 0 && threadIdx.x < 12) gacc[12 * ((round + 1) % 3) + threadIdx.x] = 0;
             if (round == 0) FR_BT(9);
             grid.sync();
             if (round == 0) FR_BT(10);
+            if (round < 4 && blockIdx.x == 0 && threadIdx.x == 0) rts[4 * round + 2] = fr_globaltimer();
             // one load per CTA and value, then a shared-memory broadcast: 150 000 threads reading the same eleven
             // words serialise in L2 (measured: 11 us)
             unsigned long long *bc = shc + 20;
             if (threadIdx.x < 11) bc[threadIdx.x] = __ldcg(&g[threadIdx.x]);
+            if (threadIdx.x == 11) bc[11] = __ldcg(&gacc[36]);
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < 11; q++) lim[q] = bc[q];
+            dist_xmin = __longlong_as_double((long long)(0x7ff0000000000000ull - bc[11]));
             __syncthreads();
             if (round == 0) FR_BT(11);
-            if (multi) {  // rank totals -> global totals (limbs < 2^36: exact in a double)
-                double pay[11];
-#pragma unroll
-                for (int q = 0; q < 11; q++) pay[q] = (double)lim[q];
-                comm_allgather_v(cm, cur, pay, 11, sh_x);
-#pragma unroll
-                for (int q = 0; q < 11; q++) {
-                    unsigned long long t = 0;
-                    for (int p = 0; p < cm.n_ranks; p++) t += (unsigned long long)sh_x[q][p];
-                    lim[q] = t;
-                }
-                __syncthreads();
-            }
+            if (round < 4 && blockIdx.x == 0 && threadIdx.x == 0) rts[4 * round + 3] = fr_globaltimer();
         }
         const unsigned long long c_round = lim[0] + (lim[1] << 16) + (lim[2] << 32);
         if (c_round == 0) break;
@@ -408,27 +441,15 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
     }
     FR_BT(6);
     // smallest preserved candidate: positive doubles order like their bit patterns
+    if (!dist) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-    if (lane == 0 && xmin < INFINITY) atomicMin(acc_min, (unsigned long long)__double_as_longlong(xmin));
-    __syncthreads();
-    xmin = __longlong_as_double((long long)*acc_min);
-    __syncthreads();
-    if (dist) {  // gacc[36] (zeroed by the host) collects max(inf_bits - bits) = the smallest preserved magnitude
-        if (threadIdx.x == 0 && xmin < INFINITY)
-            atomicMax(&gacc[36], 0x7ff0000000000000ull - (unsigned long long)__double_as_longlong(xmin));
-        grid.sync();
-        if (threadIdx.x == 0) shc[20] = __ldcg(&gacc[36]);
+        for (int o = 16; o > 0; o >>= 1) xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        if (lane == 0 && xmin < INFINITY) atomicMin(acc_min, (unsigned long long)__double_as_longlong(xmin));
         __syncthreads();
-        xmin = __longlong_as_double((long long)(0x7ff0000000000000ull - shc[20]));
+        xmin = __longlong_as_double((long long)*acc_min);
         __syncthreads();
-        if (multi) {
-            comm_allgather_v(cm, cur, &xmin, 1, sh_x);
-            double t = INFINITY;
-            for (int p = 0; p < cm.n_ranks; p++) t = fmin(t, sh_x[0][p]);
-            xmin = t;
-            __syncthreads();
-        }
+    } else {
+        xmin = dist_xmin;  // grid (and rank) minimum, read with the totals of the last round
     }
     FR_BT(7);
     res.x_cut = xmin < t_hi ? xmin : t_hi;
@@ -536,6 +557,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     // everything at or above it and the list of candidates inside it ----
     double s = 0, s_hi = 0;
     unsigned long long c_hi = 0;
+    bool appended = false;
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         double v, rinv = 1.0;
         uint32_t nd, ns;
@@ -554,7 +576,8 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                     c_hi += nd;
                     s_hi += v;
                 } else if (x >= t_lo) {
-                    cand_append(b.cand, x, nd);
+                    cand_append(b.cand, cm, x, nd);
+                    appended = true;
                 }
             } else {
                 prov.visit(i, rinv, [&](uint32_t j, double wj) {
@@ -564,13 +587,15 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                             c_hi++;
                             s_hi += x;
                         } else if (x >= t_lo) {
-                            cand_append(b.cand, x, 1u);
+                            cand_append(b.cand, cm, x, 1u);
+                            appended = true;
                         }
                     }
                 });
             }
         }
     }
+    cand_flush(cm, appended);
     unsigned long long dummy = 0;
     {
         double dd[2] = {s, s_hi};
@@ -582,21 +607,27 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     }
     double loc = s;          // this rank's loc_one_norm
     double R_next = s;       // sum_mpi(loc_one_norm) for the coming round
-    bool peers_ok = try_fast ? bracket_list_fits(b.cand, sh_sc) : false;
+    __shared__ unsigned long long sh_seg[FR_MAX_RANKS];  // multi: length of every rank's candidate segment
+    const unsigned long long my_cand = try_fast ? bracket_list_len(b.cand, sh_sc) : 0ull;
+    bool peers_ok = try_fast && my_cand <= (multi ? (unsigned long long)FR_COMM_XCAP : (unsigned long long)FR_CAND_GCAP);
     if (multi) {
+        // one exchange: norm, bracket statistics, list length (the remote candidate stores were fenced by their
+        // writers before the grid barrier of the reduction above, so they are ordered before this exchange)
+        double pay[5] = {s, s_hi, (double)c_hi, peers_ok ? 1.0 : 0.0, (double)my_cand};
+        comm_allgather_v(cm, cur, pay, 5, sh_xv);
         double before;
-        comm_allgather(cm, cur, s, s_hi, c_hi | (peers_ok ? 0ull : 1ull << 63), sh_x0, sh_x1, sh_xc);
-        comm_sum(cm, sh_x0, R_next, before);
+        comm_sum(cm, sh_xv[0], R_next, before);
         s = R_next;          // global one-norm (reported)
-        double gs = 0;
-        unsigned long long gc = 0;
+        double gs = 0, gc = 0;
         for (int p = 0; p < cm.n_ranks; p++) {
-            gs += sh_x1[p];
-            gc += sh_xc[p] & ~(1ull << 63);
-            if (sh_xc[p] >> 63) peers_ok = false;
+            gs += sh_xv[1][p];
+            gc += sh_xv[2][p];
+            if (sh_xv[3][p] == 0.0) peers_ok = false;
         }
+        if (threadIdx.x < cm.n_ranks) sh_seg[threadIdx.x] = (unsigned long long)sh_xv[4][threadIdx.x];
         s_hi = gs;           // global (count, sum) of everything at or above the bracket
-        c_hi = gc;
+        c_hi = (unsigned long long)gc;
+        if (try_fast) __threadfence_system();  // acquire side: the peers' candidates in this rank's window
         __syncthreads();
     }
 
@@ -616,7 +647,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     if (try_fast) {
         // Newton rounds on the candidate list only (every CTA, redundantly), then ONE pass that applies the cut
         BracketResult br = bracket_solve(grid, b.cand, b.st->gacc, s - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi,
-                                         sh_sd, sh_sc, cm, cur, sh_xv, peers_ok);
+                                         sh_sd, sh_sc, cm, sh_seg, peers_ok);
         n_cand = br.n_cand;
         FR_STAMP(b.st, 6);  // candidate rounds done
         if (br.valid) {

@@ -661,6 +661,18 @@ extern "C" int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, co
 // then 8 phase time stamps in ns relative to ts[0] (comp_sub_engine: 1 prep, 2 preserved set, 3 line scan,
 // 4 count + offsets, 5 emit).  States 0-4: HB-PP stages,
 // 5: finalize, 6: find_preserve, 7: sys_comp.
+// Diagnostics: time stamps inside the distributed candidate rounds of state s (CompState::rts), ns relative to the first
+extern "C" int fries_hbpp_round_stamps(fries_hbpp *hb, int s, double *h_out16) {
+    FRIES_REQUIRE(hb && h_out16 && s >= 0 && s < 8, "fries_hbpp_round_stamps: bad argument");
+    fries_ctx *c = hb->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CompState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, hb->st.p + s, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 16; k++) h_out16[k] = st.rts[k] >= st.rts[0] ? (double)(st.rts[k] - st.rts[0]) : -1.0;
+    return FRIES_OK;
+}
+
 extern "C" int fries_hbpp_states(fries_hbpp *hb, double *h_out64) {
     FRIES_REQUIRE(hb && h_out64, "fries_hbpp_states: NULL argument");
     fries_ctx *c = hb->ctx;

@@ -193,6 +193,21 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
     ms = float(ms.item())
     ms_per_step = ms / args.steps
+    # per-kernel times (event pairs around every launch; kernels with in-kernel exchanges include the wait for peers)
+    ctx.set_profile(2)
+    for _ in range(5):
+        flush.zero_()
+        last = eng.iterate(params, uni[ui]); ui += 1
+    ctx.set_profile(0)
+    kern = {}
+    for nm in ["hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4", "hbpp_finalize", "merge_insert",
+               "merge_accum", "death_axpy", "find_preserve", "sys_comp", "compact"]:
+        t, n = ctx.kernel_ms(nm)
+        if n:
+            kern[nm] = round(t / n, 4)
+    states = eng.vec.states()
+    rts = np.zeros(16)
+    check(lib.fries_hbpp_round_stamps(eng.vec.hb, 3, ptr(rts)))
     err = eng.comm.error_epoch()
     if rank == 0:
         out = {
@@ -212,6 +227,15 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
                     "what": "fries_frisys_mol_spawn + all_to_all + fries_frisys_mol_finish per step; the vector is "
                             "resident (uniforms in, iteration statistics out)"},
             "comm_error_epoch": err,
+            "stage3_round_stamps_us": [round(x / 1e3, 1) for x in rts],
+            "kernels_ms_rank0": kern,
+            "rounds": {"hbpp_stages": [int(x) for x in states[:5, 4]], "find_preserve": int(states[6, 4]),
+                       "fast": [int(x) for x in states[:7, 10]]},
+            "stage_phase_us": {"what": "in-kernel %globaltimer of CTA 0 on rank 0: prep, preserved set, line scan, count, emit",
+                               "us": [[round((states[s, 13 + k] - states[s, 12 + k]) / 1e3, 1) for k in range(5)]
+                                      for s in range(5)],
+                               "candidate_rounds_us": [round((states[s, 18] - states[s, 13]) / 1e3, 1) for s in range(5)],
+                               "apply_cut_us": [round((states[s, 19] - states[s, 18]) / 1e3, 1) for s in range(5)]},
             "energy_est": last.numer / last.denom if last.denom else None,
         }
         print(json.dumps(out), flush=True)

@@ -259,6 +259,9 @@ int fries_comm_create(fries_ctx *ctx, int n_ranks, int rank, fries_comm **out, v
 int fries_comm_connect(fries_comm *comm, const void *h_all_handles);
 int fries_comm_destroy(fries_comm *comm);
 int fries_comm_error(fries_comm *comm, uint64_t *epoch_of_failure);
+/* diagnostics: average cost (us) of one in-kernel all-gather of n doubles + grid barrier, `iters` in a row, in a
+ * cooperative grid of `ctas` CTAs (0 = the compression kernels' shape); collective over the ranks */
+int fries_comm_pingpong(fries_comm *comm, int ctas, int iters, int n, double *us_per_exchange);
 /* make fries_find_preserve_dev / fries_sys_comp_dev of this context collective over the ranks of comm */
 int fries_ctx_set_comm(fries_ctx *ctx, fries_comm *comm);
 int fries_hbpp_set_route(fries_hbpp *hb, fries_comm *comm, void *d_send_buf, void *d_recv_buf, void *d_send_counts,
@@ -292,6 +295,9 @@ int fries_debug_hbpp_stage(fries_mol *mol, const uint64_t *h_keys, const double 
  * 6 = find_preserve, 7 = sys_comp.  fast = 1: the preserved set came from the bracketed threshold solve (one data
  * pass + rounds on n_cand candidates), 0: from the plain rounds over the data. */
 int fries_hbpp_states(fries_hbpp *hb, double *h_out160);
+/* %globaltimer stamps (ns, relative to the first) inside the distributed candidate rounds 0-3 of state `state`:
+ * per round start, before the grid barrier, after it, after the cross-rank exchange */
+int fries_hbpp_round_stamps(fries_hbpp *hb, int state, double *h_out16);
 
 /* Run every standalone (host-buffer) compression n times on the same inputs and return the last run: the bracketed
  * threshold solve starts from the fixed point of a previous run, which a one-shot call does not have. */

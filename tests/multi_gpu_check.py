@@ -35,6 +35,13 @@ def main():
     comm = Comm(ctx, dist, rank, world, dev)
     check(lib.fries_ctx_set_comm(ctx.h, comm.h))
 
+    # ---- (0) cost of one in-kernel exchange ----
+    for ctas, n in ((1, 1), (1, 12), (0, 1), (0, 12)):
+        us = C.c_double(0)
+        check(lib.fries_comm_pingpong(comm.h, ctas, 200, n, C.byref(us)))
+        if rank == 0:
+            print(f"[multi] exchange of {n} doubles + grid barrier, {'1 CTA' if ctas else 'full grid'}: {us.value:.2f} us", flush=True)
+
     # ---- (1) distributed vector compression ----
     rng = np.random.default_rng(5)
     n, budget = 400000, 60000

@@ -11,11 +11,9 @@ __global__ void __launch_bounds__(512, 2) k_solve(CandList cl, unsigned long lon
     cg::grid_group grid = cg::this_grid();
     grid.sync();
     long long t0 = clock64();
-    __shared__ double sh_x[12][FR_MAX_RANKS];
     CommView cm{};
     cm.n_ranks = 1;
-    CommCursor cur{0};
-    BracketResult br = bracket_solve(grid, cl, gacc, R0, nrem0, t_lo, t_hi, shd, shc, cm, cur, sh_x, true);
+    BracketResult br = bracket_solve(grid, cl, gacc, R0, nrem0, t_lo, t_hi, shd, shc, cm, nullptr, true);
     long long t1 = clock64();
     if (threadIdx.x == 0) {
         cyc[blockIdx.x] = t1 - t0;
