@@ -45,6 +45,10 @@ START_PARENTS = (1, 1000, 1500)  # parents kept before each H application (x vec
 def start_parents(cfg):
     return START_PARENTS[:2] + (max(START_PARENTS[2], START_PARENTS[2] * cfg["vec_nonz"] // 242000),)
 B_PER_VEC_EL = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the Ne-sized bench, from ONE `ncu --set full` capture
+# (profiles/r01c_ncu_full_hbpp_stage_raw.csv); not measured live
+NCU_TRAFFIC_NE = {"hbpp_stage0": 4.18e6, "hbpp_stage1": 11.92e6, "hbpp_stage2": 12.93e6, "hbpp_stage3": 10.24e6,
+                  "hbpp_stage4": 9.89e6}
 
 
 def mt_uniforms(seed, n):
@@ -261,7 +265,10 @@ def run_ours(args, cfg):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = units[top] / (kern[top] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": None,
+                "frac": round(achieved / peak, 5),
+                "traffic": NCU_TRAFFIC_NE.get(top) if cfg["system"] == "ne" else None,
+                "traffic_source": "profiles/r01c_ncu_full_hbpp_stage_raw.csv (bytes per launch)",
+                "algorithmic_bytes_per_launch": units[top],
                 "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
                 "ms_per_launch": round(kern[top], 4),
                 "kernels_ms": {k: round(v, 4) for k, v in kern.items()},

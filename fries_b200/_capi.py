@@ -119,6 +119,7 @@ def _load():
         "fries_vec_set_diag_mol": (i, [vp, vp, d]),
         "fries_h_apply": (i, [vp, vp, u, u, d, d]),
         "fries_h_apply_last_spawned": (i, [vp, P(C.c_uint64)]),
+        "fries_h_apply_routed": (i, [vp, vp, vp, u, u, d, d, P(C.c_uint64)]),
         "fries_frisys_mol_setup": (i, [vp, vp, sz, vp, vp, sz, vp, vp, sz, P(vp)]),
         "fries_hbpp_destroy": (i, [vp]),
         "fries_frisys_mol_iterate": (i, [vp, vp, vp, P(FrisysParams), vp, P(IterStats)]),

@@ -105,7 +105,7 @@ __device__ __forceinline__ void parent_ctx(const MolView &m, uint64_t key, Paren
 }
 
 // n-th set bit (0-based) of a 32-bit mask
-__device__ __forceinline__ unsigned nth_bit(uint32_t mask, unsigned n) { return __fns(mask, 0, n + 1); }
+__device__ __forceinline__ unsigned nth_bit(uint32_t mask, unsigned n) { return fr_nth_bit32(mask, n); }
 
 // Visit this lane's share of the off-diagonal connections of the parent.  F(is_double, o0, o1, v0, v1).
 template <class F>
@@ -217,8 +217,13 @@ scan_counts_kernel(const uint32_t *__restrict__ counts, size_t n, unsigned long 
 __global__ void __launch_bounds__(256)
 hv_fill_kernel(MolView gm, VecView v, unsigned src, size_t n_parents, const uint32_t *__restrict__ counts,
                const unsigned long long *__restrict__ offs, unsigned long long win_lo, unsigned long long win_len,
-               double h_fac, uint64_t *__restrict__ out_keys, double *__restrict__ out_vals) {
+               double h_fac, uint64_t *__restrict__ out_keys, double *__restrict__ out_vals, HbSpawnArgs sp) {
     MolView m = mol_stage_shared(gm, fr_dyn_smem);
+    __shared__ uint32_t s_pscr[64];
+    if (sp.n_ranks > 1) {
+        if (threadIdx.x < 64) s_pscr[threadIdx.x] = sp.proc_scr[threadIdx.x];
+        __syncthreads();
+    }
     const unsigned lane = threadIdx.x & 31;
     size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t p = warp; p < n_parents; p += nwarps) {
@@ -252,12 +257,68 @@ hv_fill_kernel(MolView gm, VecView v, unsigned src, size_t n_parents, const uint
                     el *= fr_sing_det_parity(nk, o0, o1);
                 }
                 el *= val * h_fac;  // matr_el *= curr_el * h_fac (molecule.cpp:601,655)
-                out_keys[pos - win_lo] = nk | FRIES_INI_FLAG;
-                out_vals[pos - win_lo] = el;
+                if (sp.n_ranks <= 1) {
+                    out_keys[pos - win_lo] = nk | FRIES_INI_FLAG;
+                    out_vals[pos - win_lo] = el;
+                } else {
+                    // Adder::add (vec_utils.hpp:957-971): straight into segment `rank` of the owner's receive window;
+                    // the lanes that are active here and share a destination take their slots with one atomic
+                    int owner = (int)(fr_det_hash(nk, s_pscr) % (unsigned)sp.n_ranks);
+                    unsigned am = __activemask();
+                    unsigned peers = __match_any_sync(am, owner);
+                    int leader = __ffs(peers) - 1;
+                    unsigned rank_in = __popc(peers & ((1u << lane) - 1));
+                    unsigned long long base = 0;
+                    if ((int)lane == leader) base = atomicAdd(&sp.send_counts[owner], (unsigned long long)__popc(peers));
+                    base = __shfl_sync(peers, base, leader);
+                    unsigned long long slot = base + rank_in;
+                    if (slot < sp.seg_cap) {
+                        uint64_t *seg = sp.peer_win[owner] + (size_t)sp.rank * 2 * sp.seg_cap;
+                        seg[slot] = nk | FRIES_INI_FLAG;
+                        seg[sp.seg_cap + slot] = (uint64_t)__double_as_longlong(el);
+                    } else {
+                        atomicAdd(&sp.send_counts[sp.n_ranks], 1ull);
+                    }
+                }
             }
             pos++;
         });
     }
+}
+
+__global__ void xrank_stats_kernel(CommView cm, double *scal, const VecCounters *cnt, const CompState *st, double *out);
+// tiny collective helpers over the inboxes: one CTA per rank
+int fries_comm_route_publish(fries_comm *cm, const unsigned long long *d_send_counts);
+int fries_comm_route_wait(fries_comm *cm, unsigned long long *d_recv_counts);
+int fries_vec_merge_src_dev(fries_vec *vec, const MergeSrc &src, unsigned origin, unsigned dest);
+__global__ void xrank_max_kernel(CommView cm, double mine, double *out) {
+    __shared__ double sh_x[1][FR_MAX_RANKS];
+    CommCursor cur = comm_begin(cm);
+    comm_allgather_v(cm, cur, &mine, 1, sh_x);
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int p = 0; p < cm.n_ranks; p++) t = fmax(t, sh_x[0][p]);
+        *out = t;
+    }
+    __syncthreads();
+    comm_end(cm, cur);
+}
+static int xrank_max_u64(fries_hbpp *hb, unsigned long long mine, unsigned long long *out) {
+    fries_ctx *c = hb->ctx;
+    xrank_max_kernel<<<1, 64, 0, c->stream>>>(fries_comm_view(hb->comm), (double)mine, hb->scal.p + 40);
+    c->launch_count++;
+    double r = 0;
+    CUDA_TRY(cudaMemcpyAsync(&r, hb->scal.p + 40, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = (unsigned long long)r;
+    return FRIES_OK;
+}
+static int xrank_barrier(fries_hbpp *hb) {
+    fries_ctx *c = hb->ctx;
+    xrank_max_kernel<<<1, 64, 0, c->stream>>>(fries_comm_view(hb->comm), 0.0, hb->scal.p + 41);
+    c->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return FRIES_OK;
 }
 
 struct HvScratch {
@@ -308,12 +369,47 @@ static int h_apply_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned 
     CUDA_TRY(cudaMemcpyAsync(&total, sc.total.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (n_spawned) *n_spawned = total;
+    HbSpawnArgs sp{nullptr, 0, 0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0, {nullptr}, 0};
+    if (vec->n_ranks > 1) {
+        // Several ranks: every window of <= seg_cap connections is routed into the owners' receive windows
+        // (direct route, comm.cuh) and merged there; all ranks run the same number of windows (the maximum).
+        FRIES_REQUIRE(hb->p2p && hb->comm, "h_apply on a partitioned vector needs fries_hbpp_set_route_p2p");
+        const unsigned long long win = hb->seg_cap;
+        unsigned long long rounds = (total + win - 1) / win, g_rounds = 0;
+        FRIES_TRY(xrank_max_u64(hb, rounds, &g_rounds));
+        sp = HbSpawnArgs{nullptr, 0, 0, nullptr, nullptr, vec->n_ranks, v.scr_proc, nullptr, hb->send_counts_ext,
+                         (unsigned long long)hb->seg_cap, {nullptr}, vec->rank};
+        for (int q = 0; q < vec->n_ranks; q++) sp.peer_win[q] = hb->comm->route.win[q];
+        for (unsigned long long r = 0; r < g_rounds; r++) {
+            unsigned long long lo = r * win, len = lo < total ? (total - lo < win ? total - lo : win) : 0;
+            CUDA_TRY(cudaMemsetAsync(hb->send_counts_ext, 0, (vec->n_ranks + 1) * 8, c->stream));
+            if (len) {
+                ProfScope ps(c, "hv_fill");
+                hv_fill_kernel<<<grid, 256, smem, c->stream>>>(mol->view, v, src, n_parents, sc.counts.p, sc.offs.p, lo, len,
+                                                               h_fac, nullptr, nullptr, sp);
+                c->launch_count++;
+                CUDA_TRY(cudaGetLastError());
+            }
+            FRIES_TRY(fries_comm_route_publish(hb->comm, hb->send_counts_ext));
+            FRIES_TRY(fries_comm_route_wait(hb->comm, hb->p2p_recv_counts.p));
+            MergeSrc msrc{(const uint64_t *)hb->recv_buf, nullptr, (size_t)vec->n_ranks * hb->seg_cap, nullptr,
+                          hb->p2p_recv_counts.p, hb->seg_cap};
+            FRIES_TRY(fries_vec_merge_src_dev(vec, msrc, 0, dest));
+            // the windows are single-buffered: nobody may store round r + 1 before every rank has merged round r
+            FRIES_TRY(xrank_barrier(hb));
+            v = vec->view();
+        }
+        unsigned long long ov = 0;
+        CUDA_TRY(cudaMemcpyAsync(&ov, hb->send_counts_ext + vec->n_ranks, 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        FRIES_REQUIRE(ov == 0, "h_apply: %llu connections did not fit a route segment", ov);
+    } else
     for (unsigned long long lo = 0; lo < total; lo += hb->cap) {
         unsigned long long len = total - lo < hb->cap ? total - lo : hb->cap;
         {
             ProfScope ps(c, "hv_fill");
             hv_fill_kernel<<<grid, 256, smem, c->stream>>>(mol->view, v, src, n_parents, sc.counts.p, sc.offs.p, lo, len,
-                                                           h_fac, hb->spawn_keys.p, hb->spawn_vals.p);
+                                                           h_fac, hb->spawn_keys.p, hb->spawn_vals.p, sp);
             c->launch_count++;
         }
         CUDA_TRY(cudaGetLastError());
@@ -351,6 +447,19 @@ extern "C" int fries_h_apply(fries_vec *vec, fries_mol *mol, unsigned src, unsig
     uint64_t ns = 0;
     FRIES_TRY(h_apply_dev(vec, mol, vec->hv_scratch, src, dest, id_fac, h_fac, true, &ns));
     vec->last_spawned = ns;
+    return FRIES_OK;
+}
+// H.v on a partitioned vector: `hb` carries the direct route (fries_hbpp_set_route_p2p); collective over the ranks
+extern "C" int fries_h_apply_routed(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned src, unsigned dest,
+                                    double id_fac, double h_fac, uint64_t *n_spawned) {
+    FRIES_REQUIRE(vec && mol && hb, "fries_h_apply_routed: NULL argument");
+    FRIES_REQUIRE(vec->n_bits == 2 * mol->view.d.n_orb && vec->n_elec == mol->view.d.n_elec,
+                  "fries_h_apply_routed: vector does not match the molecule");
+    CUDA_TRY(cudaSetDevice(vec->ctx->device));
+    FRIES_TRY(ensure_spawn(hb));
+    uint64_t ns = 0;
+    FRIES_TRY(h_apply_dev(vec, mol, hb, src, dest, id_fac, h_fac, true, &ns));
+    if (n_spawned) *n_spawned = ns;
     return FRIES_OK;
 }
 extern "C" int fries_h_apply_last_spawned(fries_vec *vec, uint64_t *n) {
@@ -654,14 +763,15 @@ extern "C" int fries_frisys_mol_finish(fries_vec *vec, fries_mol *mol, fries_hbp
 extern "C" int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, fries_frifull_params *p,
                                          double uniform, fries_iter_stats *stats) {
     FRIES_REQUIRE(vec && mol && hb && p, "fries_frifull_mol_iterate: NULL argument");
-    FRIES_REQUIRE(vec->n_ranks == 1, "fries_frifull_mol_iterate: single-rank entry point");
+    FRIES_REQUIRE(vec->n_ranks == 1 || (hb->p2p && hb->comm),
+                  "fries_frifull_mol_iterate: a partitioned vector needs fries_hbpp_set_route_p2p");
     fries_ctx *c = vec->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     unsigned src = vec->cur_row, dst = src ^ 1;
     CUDA_TRY(cudaMemsetAsync(hb->st.p, 0, 8 * sizeof(CompState), c->stream));
     FRIES_TRY(dot_dev(vec, hb->trial_keys.p, hb->trial_vals.p, hb->n_trial, src, hb->scal.p + IterScalars::DENOM));
     FRIES_TRY(compress_vector_dev(vec, hb, src, p->target_nonz, uniform));
-    if (p->adjust_shift) {  // needs the one-norm before compression on the host
+    if (p->adjust_shift) {  // needs the (global) one-norm before compression on the host
         double r4[4];
         CUDA_TRY(cudaMemcpyAsync(r4, hb->scal.p + IterScalars::R4, sizeof(r4), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -677,12 +787,26 @@ extern "C" int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_h
     FRIES_TRY(h_apply_dev(vec, mol, hb, src, dst, 1 + p->eps * p->en_shift, -p->eps, true, &ns));
     vec->cur_row = dst;
     FRIES_TRY(dot_dev(vec, hb->trial_keys.p, hb->trial_vals.p, hb->n_trial, dst, hb->scal.p + IterScalars::NUMER));
+    if (vec->n_ranks > 1) {  // <trial|v>, <trial|v'>, sizes and spawn counts summed over the ranks, in rank order
+        unsigned long long ns64 = ns;
+        CUDA_TRY(cudaMemcpyAsync(&hb->st.p[5].n_out, &ns64, 8, cudaMemcpyHostToDevice, c->stream));
+        xrank_stats_kernel<<<1, 32, 0, c->stream>>>(fries_comm_view(hb->comm), hb->scal.p, vec->cnt.p, hb->st.p,
+                                                    hb->scal.p + 32);
+        c->launch_count++;
+    }
     int rc = read_stats(vec, hb, stats, "fries_frifull_mol_iterate");
     if (stats) {
         // numer = ((1 + eps S) denom - <trial|v'>) / eps  (frifull_mol.cpp:294-296)
         stats->numer = ((1 + p->eps * p->en_shift) * stats->denom - stats->numer) / p->eps;
         stats->n_spawned = ns;
         stats->n_matrix_samples = ns;
+        if (vec->n_ranks > 1) {
+            double g[2];
+            CUDA_TRY(cudaMemcpyAsync(g, hb->scal.p + 32, 16, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            stats->curr_size = (uint64_t)g[0];
+            stats->n_spawned = stats->n_matrix_samples = (uint64_t)g[1];
+        }
     }
     return rc;
 }

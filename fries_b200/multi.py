@@ -115,6 +115,18 @@ class MultiGpuFrisys:
         self.vec.upload(k, np.stack([v, np.zeros_like(v)]))
         return idx.size
 
+    def h_apply(self, src, dest, id_fac, h_fac) -> int:
+        """deterministic H.v on the partitioned vector (direct route only); returns this rank's spawn count"""
+        n = C.c_uint64(0)
+        check(lib.fries_h_apply_routed(self.vec.h, self.mol.h, self.vec.hb, src, dest, id_fac, h_fac, C.byref(n)))
+        return n.value
+
+    def frifull_iterate(self, params, uniform: float) -> IterStats:
+        """frifull_mol.cpp:256-320 over the ranks (direct route only)"""
+        st = IterStats()
+        check(lib.fries_frifull_mol_iterate(self.vec.h, self.mol.h, self.vec.hb, C.byref(params), uniform, C.byref(st)))
+        return st
+
     def iterate(self, params: FrisysParams, uniforms6) -> IterStats:
         u = arr(uniforms6, np.float64)
         check(lib.fries_frisys_mol_spawn(self.vec.h, self.mol.h, self.vec.hb, C.byref(params), ptr(u)))

@@ -180,6 +180,10 @@ int fries_vec_set_diag_mol(fries_vec *vec, fries_mol *mol, double hf_en); /* dia
 int fries_h_apply(fries_vec *vec, fries_mol *mol, unsigned src, unsigned dest, double id_fac, double h_fac);
 /* number of off-diagonal elements generated by the last fries_h_apply (the spawned H.v elements) */
 int fries_h_apply_last_spawned(fries_vec *vec, uint64_t *n_spawned);
+/* The same on a vector partitioned over ranks (collective): windows of <= seg_cap connections are stored straight into
+ * their owners' receive windows (hb carries the direct route, fries_hbpp_set_route_p2p) and merged there. */
+int fries_h_apply_routed(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned src, unsigned dest, double id_fac,
+                         double h_fac, uint64_t *n_spawned);
 
 /* ---- a17/a18 + drivers: one FRI iteration ---------------------------------------------------------------
  * frisys_mol loop body FRIES_bin/frisys_mol.cpp:405-552 (steps 1-11 of SURVEY.md 3.1) on resident
@@ -219,6 +223,7 @@ typedef struct {
     double target_norm;     /* --target */
     double last_one_norm;   /* in/out */
 } fries_frifull_params;
+/* single rank, or -- with the direct route set on hb -- collective over the ranks of a partitioned vector */
 int fries_frifull_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, fries_frifull_params *p,
                               double uniform, fries_iter_stats *stats);
 
