@@ -34,6 +34,12 @@ CONFIGS = {
     "h2o": dict(system="h2o", seed=3, point_group="C2v", eps=0.001, target=1000000.0, vec_nonz=1000000,
                 mat_nonz=1000000, max_dets=2000000, initiator=1.0, dist="HB_unnorm",
                 workload="H2O cc-pVDZ-sized frisys_mol (NORB=24 NELEC=10 C2v, HB_unnorm, vec_nonz 1e6, mat_nonz 1e6)"),
+    # BASELINE.json configs[4] / SURVEY.md 8d C5, the share of ONE GPU: 1.25e7 distinct random determinants (5 alpha +
+    # 5 beta in 26 orbitals, default_rng(12345)), values sign * 10^(-4u), N2 cc-pVDZ-sized integrals (frozen core)
+    "c5": dict(system="n2", seed=7, point_group="D2h", eps=0.001, target=1.25e7, vec_nonz=12500000, mat_nonz=12500000,
+               max_dets=25000000, initiator=1.0, dist="HB_unnorm", synthetic_vector=True, frozen=True,
+               workload="synthetic 1.25e7-determinant vector per GPU, N2 cc-pVDZ-sized integrals (NORB=26 NELEC=10, "
+                        "HB_unnorm, vec_nonz = mat_nonz = 1.25e7 per GPU): spawn -> merge -> compress"),
 }
 
 # SURVEY.md section 8d algorithmic bytes
@@ -68,7 +74,7 @@ def prepare_workload(cfg, ctx, n_ranks=1, rank=0):
     import fries_b200
     from fries_b200.synth import SynthMol
 
-    sm = SynthMol(cfg["system"], cfg["seed"], frozen=False)
+    sm = SynthMol(cfg["system"], cfg["seed"], frozen=bool(cfg.get("frozen", False)))
     mol = fries_b200.Mol.from_synth(ctx, sm)
     rs = np.random.RandomState(0)  # mt19937(0): proc scrambler then vec scrambler (frisys_mol.cpp:132-144)
     proc_scr, vec_scr = mt_u32(rs, sm.n_bits), mt_u32(rs, sm.n_bits)
@@ -85,6 +91,10 @@ def prepare_workload(cfg, ctx, n_ranks=1, rank=0):
     n_doub = int(mol.doub_ex(hf)[0][-1])
     p_doub = n_doub / (n_sing + n_doub)  # frisys_mol.cpp:217-220
     tmp.close()
+    if cfg.get("synthetic_vector"):
+        keys, vals = synthetic_vector(sm, cfg["vec_nonz"], cfg["target"])
+        return dict(sm=sm, mol=mol, proc_scr=proc_scr, vec_scr=vec_scr, hf=hf, hf_en=hf_en, htrial_keys=htrial_keys,
+                    htrial_vals=htrial_vals, p_doub=p_doub, keys=keys, vals=vals)
     # starting vector: (1 - 0.5 (H - E_HF))^3 HF restricted to the PARENTS[k] largest elements before each
     # application -- a realistic population (HF, singles/doubles, up to hextuples), truncated to the vec_nonz
     # largest elements and scaled to the target one-norm
@@ -106,6 +116,28 @@ def prepare_workload(cfg, ctx, n_ranks=1, rank=0):
     keys, vals = np.ascontiguousarray(keys[perm]), np.ascontiguousarray(vals[perm])
     return dict(sm=sm, mol=mol, proc_scr=proc_scr, vec_scr=vec_scr, hf=hf, hf_en=hf_en, htrial_keys=htrial_keys,
                 htrial_vals=htrial_vals, p_doub=p_doub, keys=keys, vals=vals)
+
+
+def synthetic_vector(sm, n, one_norm):
+    """n distinct random determinants (HF first) with values sign * 10^(-4u), u ~ U(0,1), scaled to the one-norm"""
+    rng = np.random.default_rng(12345)
+    M, h = sm.n_orb, sm.n_elec // 2
+    parts, have = [np.array([sm.hf], np.uint64)], 1
+    while have < n:
+        m = min(2_000_000, int(1.1 * (n - have)) + 1024)
+        a = np.argpartition(rng.random((m, M), dtype=np.float32), h, axis=1)[:, :h].astype(np.uint64)
+        b = np.argpartition(rng.random((m, M), dtype=np.float32), h, axis=1)[:, :h].astype(np.uint64)
+        k = (np.uint64(1) << a).sum(axis=1, dtype=np.uint64) | ((np.uint64(1) << b).sum(axis=1, dtype=np.uint64) << np.uint64(M))
+        parts.append(k)
+        keys = np.unique(np.concatenate(parts))
+        parts, have = [keys], keys.size
+    keys = parts[0]
+    keys = keys[keys != np.uint64(sm.hf)]
+    keys = np.concatenate([np.array([sm.hf], np.uint64), keys[rng.permutation(keys.size)[: n - 1]]])
+    vals = rng.choice([-1.0, 1.0], n) * 10.0 ** (-4.0 * rng.random(n))
+    vals[0] = 1.0
+    vals *= one_norm / np.abs(vals).sum()
+    return np.ascontiguousarray(keys), np.ascontiguousarray(vals)
 
 
 class ClockSampler:
@@ -300,7 +332,11 @@ def run_ours(args, cfg):
     # CPU baseline: the reference driver started from the SAME warmed-up vector (downloaded from the GPU)
     wk, wv = vec.download()
     wl["keys"], wl["vals"] = wk, wv[0]
-    out["cpu_baseline"] = cpu_baseline_block(cfg, wl, n_iter=int(os.environ.get("FRIES_BENCH_CPU_ITERS", "12")))
+    if cfg.get("synthetic_vector"):
+        out["cpu_baseline"] = {"value": None, "unit": "iter/s", "cores": 1, "kind": "reference",
+                               "sample": "not run at this size (one reference iteration takes > 10 s); see the default config"}
+    else:
+        out["cpu_baseline"] = cpu_baseline_block(cfg, wl, n_iter=int(os.environ.get("FRIES_BENCH_CPU_ITERS", "12")))
     print(json.dumps(out), flush=True)
     vec.close()
     mol.close()
