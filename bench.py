@@ -92,7 +92,10 @@ def prepare_workload(cfg, ctx, n_ranks=1, rank=0):
     p_doub = n_doub / (n_sing + n_doub)  # frisys_mol.cpp:217-220
     tmp.close()
     if cfg.get("synthetic_vector"):
-        keys, vals = synthetic_vector(sm, cfg["vec_nonz"], cfg["target"])
+        if cfg.get("skip_vector"):  # multi-GPU: every rank draws and routes its own share (fries_b200/multi.py)
+            keys, vals = hf, np.ones(1)
+        else:
+            keys, vals = synthetic_vector(sm, cfg["vec_nonz"], cfg["target"])
         return dict(sm=sm, mol=mol, proc_scr=proc_scr, vec_scr=vec_scr, hf=hf, hf_en=hf_en, htrial_keys=htrial_keys,
                     htrial_vals=htrial_vals, p_doub=p_doub, keys=keys, vals=vals)
     # starting vector: (1 - 0.5 (H - E_HF))^3 HF restricted to the PARENTS[k] largest elements before each
@@ -118,9 +121,9 @@ def prepare_workload(cfg, ctx, n_ranks=1, rank=0):
                 htrial_vals=htrial_vals, p_doub=p_doub, keys=keys, vals=vals)
 
 
-def synthetic_vector(sm, n, one_norm):
+def synthetic_vector(sm, n, one_norm, seed=12345):
     """n distinct random determinants (HF first) with values sign * 10^(-4u), u ~ U(0,1), scaled to the one-norm"""
-    rng = np.random.default_rng(12345)
+    rng = np.random.default_rng(seed)
     M, h = sm.n_orb, sm.n_elec // 2
     parts, have = [np.array([sm.hf], np.uint64)], 1
     while have < n:

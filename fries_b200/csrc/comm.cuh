@@ -17,7 +17,7 @@
 
 #define FR_MAX_RANKS 8
 #define FR_COMM_PAYLOAD 12  // doubles per slot
-#define FR_COMM_XCAP 16384  // candidates one rank may contribute to a bracketed threshold solve (compress.cuh)
+#define FR_COMM_XCAP 262144 // candidates one rank may contribute to a bracketed threshold solve (compress.cuh)
 
 struct CommView {
     int n_ranks, rank;

@@ -202,8 +202,9 @@ __device__ __forceinline__ void grid_excl_scan(cg::grid_group &grid, GridRed &r,
 #define FR_CAND_GCAP (1u << 20)                            // capacity of the list (grid-distributed rounds beyond one CTA)
 
 struct KeepPred {
-    double t;   // fixed-point threshold of the previous run (0: none)
-    double h;   // relative half-width of the bracket
+    double t;       // centre of the next bracket: the last fixed point extrapolated by the last ratio (0: none)
+    double h;       // relative half-width of the bracket
+    double t_last;  // fixed point of the previous run
 };
 
 struct CandList {
@@ -460,20 +461,26 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
     return res;
 }
 
-// next bracket from this run's fixed point: wide enough for the observed drift of the fixed point between runs (x 6),
-// otherwise steered towards a list of ~2500 candidates (one CTA's registers hold 4096: no grid barrier in the rounds)
-__device__ __forceinline__ void keep_pred_update(KeepPred *p, double t_prev, double h_prev, double t_fin,
+// Next bracket from this run's fixed point.  Centre: geometric extrapolation t_fin * (t_fin / t_last) -- the one-norm of
+// an FRI iterate drifts smoothly (death/cloning, shift updates), and so do the thresholds.  Half-width: 6 x the error of
+// the centre that was used for this run, otherwise steered towards a list of ~2500 candidates (one CTA's registers hold
+// 4096: no grid barrier in the rounds).
+__device__ __forceinline__ void keep_pred_update(KeepPred *p, double t_used, double h_prev, double t_fin,
                                                  unsigned long long ncand) {
     const double h_min = 1e-4, h_max = 0.05;
-    double h = 0.01;
-    if (t_prev > 0 && t_fin > 0) {
-        double drift = fabs(t_fin / t_prev - 1.0);
+    const double t_last = p->t_last;
+    double h = 0.01, ratio = 1.0;
+    if (t_used > 0 && t_fin > 0) {
+        double err = fabs(t_fin / t_used - 1.0);
         double steer = h_prev * 2500.0 / (double)(ncand > 0 ? ncand : 1);
         steer = fmin(fmax(steer, 0.5 * h_prev), 1.5 * h_prev);
-        h = fmax(6.0 * drift, steer);
+        h = fmax(6.0 * err, steer);
     }
+    if (t_last > 0 && t_fin > 0) ratio = fmin(fmax(t_fin / t_last, 0.8), 1.25);
     h = fmin(fmax(h, h_min), h_max);
-    p->t = (t_fin > 0 && isfinite(t_fin)) ? t_fin : 0.0;
+    const bool ok = t_fin > 0 && isfinite(t_fin);
+    p->t = ok ? t_fin * ratio : 0.0;
+    p->t_last = ok ? t_fin : 0.0;
     p->h = h;
 }
 

@@ -166,15 +166,50 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
     gcfg["mat_nonz"] = cfg["mat_nonz"] * world
     gcfg["target"] = cfg["target"] * world
     gcfg["max_dets"] = cfg["max_dets"] * world
+    synthetic = bool(cfg.get("synthetic_vector"))
+    if synthetic:
+        gcfg["skip_vector"] = True
     wl = prepare_workload(gcfg, ctx)  # every rank prepares the same global start vector (deterministic)
     sm, mol = wl["sm"], wl["mol"]
-    _, owner = hash_owner(ctx, wl["keys"], wl["proc_scr"], world)
+    if not synthetic:
+        _, owner = hash_owner(ctx, wl["keys"], wl["proc_scr"], world)
     spawn_cap_local = 4 * gcfg["mat_nonz"] // world          # spawn_length = matr_samp * 4 / n_procs
     seg_cap = 2 * gcfg["mat_nonz"] // (world * world) + 8192
     eng = MultiGpuFrisys(ctx, dist, rank, world, mol, sm, cfg["max_dets"], spawn_cap_local, seg_cap, wl["proc_scr"],
                          wl["vec_scr"], wl["hf_en"], (wl["hf"], np.ones(1)), (wl["htrial_keys"], wl["htrial_vals"]),
                          route=os.environ.get("FRIES_ROUTE", "p2p"))
-    eng.load(wl["keys"], wl["vals"], owner)
+    if synthetic:
+        # every rank draws its own share of random determinants, the shares are routed to their hash owners with one
+        # all-to-all (untimed set-up), duplicates across ranks merge at the owner
+        from bench import synthetic_vector
+        k_r, v_r = synthetic_vector(sm, cfg["vec_nonz"], 1.0, seed=12345 + rank)
+        if rank:
+            k_r, v_r = k_r[1:], v_r[1:]  # the Hartree-Fock determinant comes from rank 0 only
+        _, own_r = hash_owner(ctx, k_r, wl["proc_scr"], world)
+        order = np.argsort(own_r, kind="stable")
+        counts = np.bincount(own_r, minlength=world).astype(np.int64)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        send_c = torch.from_numpy(counts).to(dev)
+        recv_c = torch.empty_like(send_c)
+        dist.all_to_all_single(recv_c, send_c)
+        n_recv = int(recv_c.sum().item())
+        send_k = torch.from_numpy(k_r[order].view(np.int64)).to(dev)
+        send_v = torch.from_numpy(v_r[order]).to(dev)
+        recv_k = torch.empty(n_recv, dtype=torch.int64, device=dev)
+        recv_v = torch.empty(n_recv, dtype=torch.float64, device=dev)
+        dist.all_to_all_single(recv_k, send_k, recv_c.tolist(), counts.tolist())
+        dist.all_to_all_single(recv_v, send_v, recv_c.tolist(), counts.tolist())
+        lk, first = np.unique(recv_k.cpu().numpy().view(np.uint64), return_index=True)
+        lv = recv_v.cpu().numpy()[first]
+        perm = np.random.default_rng(7 + rank).permutation(lk.size)
+        lk, lv = np.ascontiguousarray(lk[perm]), np.ascontiguousarray(lv[perm])
+        nrm = torch.tensor([np.abs(lv).sum()], dtype=torch.float64, device=dev)
+        dist.all_reduce(nrm)
+        lv *= gcfg["target"] / float(nrm.item())
+        del send_k, send_v, recv_k, recv_v
+        eng.vec.upload(lk, np.stack([lv, np.zeros_like(lv)]))
+    else:
+        eng.load(wl["keys"], wl["vals"], owner)
     params = FrisysParams(eps=cfg["eps"], init_thresh=cfg["initiator"], p_doub=wl["p_doub"],
                           new_hb=1 if cfg["dist"] == "HB_unnorm" else 0, matr_samp=gcfg["mat_nonz"],
                           target_nonz=gcfg["vec_nonz"], en_shift=0.0)
