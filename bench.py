@@ -204,6 +204,8 @@ def run_ours(args, cfg):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     check(lib.fries_ctx_set_stream(ctx.h, stream.cuda_stream))
+    if os.environ.get("FRIES_NO_BRACKET"):  # diagnostics: the reference's plain rounds in every compression
+        check(lib.fries_debug_set_bracket(0))
 
     if world > 1:
         from fries_b200.multi import run_multi_gpu_bench

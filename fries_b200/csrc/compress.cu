@@ -379,11 +379,14 @@ struct MatProvider {
     const uint16_t *sub_sizes;
     size_t n, n_sub;
     __device__ size_t count() const { return n; }
-    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv) const {
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv, double &wmax) const {
         v = values[i];
         nd = ndiv[i];
         ns = sub_sizes ? sub_sizes[i] : (uint32_t)n_sub;
         rinv = 1.0;
+        wmax = 0;
+        if (nd == 0)
+            for (uint32_t j = 0; j < ns && j < n_sub; j++) wmax = fmax(wmax, subw[i * n_sub + j]);
     }
     template <class F>
     __device__ void visit(size_t i, double, F &&f) const {

@@ -519,7 +519,7 @@ struct CompSubBufs {
 
 // The hierarchical compression engine.  Provider P supplies
 //   size_t count();                                            number of inputs
-//   void prep(size_t i, double &v, uint32_t &ndiv, uint32_t &nsub, double &rinv);  effective weight, row shape,
+//   void prep(size_t i, double &v, uint32_t &ndiv, uint32_t &nsub, double &rinv, double &wmax);  effective weight, row shape,
 //                                                              normalisation factor of the row (stored per input)
 //   void visit(size_t i, double rinv, F f);                    calls f(j, w_j) for the nsub sub-weights in order --
 //                                                              rows are streamed, never materialised
@@ -566,9 +566,9 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     unsigned long long c_hi = 0;
     bool appended = false;
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        double v, rinv = 1.0;
+        double v, rinv = 1.0, wmax = 1.0;
         uint32_t nd, ns;
-        prov.prep(i, v, nd, ns, rinv);
+        prov.prep(i, v, nd, ns, rinv, wmax);
         b.rinv[i] = rinv;
         b.veff[i] = v;
         b.wt_remain[i] = v;
@@ -576,7 +576,11 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         b.nsub[i] = (uint8_t)ns;
         b.keep[i] = 0;
         s += v;
-        if (try_fast && v >= t_lo) {
+        // largest piece of this input (an upper bound for rows): parked in lb[], which is free until the count pass;
+        // an input whose largest piece is below the bracket needs no row here and none in the cut pass
+        const double xmax = nd > 0 ? v / nd : v * wmax;
+        b.lb[i] = xmax;
+        if (try_fast && xmax >= t_lo) {
             if (nd > 0) {
                 double x = v / nd;
                 if (x >= t_hi) {
@@ -664,7 +668,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
             for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
                 double v = b.veff[i];
                 double wr = v;
-                if (v >= x_cut || v * fac >= br.R) {  // the reference recomputes the residual of such an input (:206-262)
+                if (b.lb[i] >= x_cut) {  // largest piece (phase 0); below the cut nothing of this input is preserved
                     uint32_t nd = b.ndiv[i];
                     if (nd > 0) {
                         if (v / nd >= x_cut) {

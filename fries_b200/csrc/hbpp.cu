@@ -41,11 +41,15 @@ struct HbProvider {
         return n;
     }
 
-    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv) const {
+    // wmax: an upper bound of the sub-weights visit() will stream for this input (exactly the largest one where the
+    // row is traversed here anyway); the engine skips the row of an input whose v * wmax is below the threshold bracket
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv, double &wmax) const {
         const unsigned ne = m.d.n_elec, M = m.d.n_orb;
         rinv = 1.0;
+        wmax = 1.0;
         if (S == 0) {  // singles vs doubles :713-727
             double w = fabs(io.vals[i]);
+            wmax = fmax(io.p_doub, 1 - io.p_doub);
             v = w;
             nd = w > 0 ? 0u : 1u;
             ns = 2;
@@ -64,9 +68,13 @@ struct HbProvider {
             ns = ne - (io.new_hb ? 1 : 0);
             if (p0 == 0) {
                 nd = 0;
-                double norm = 0;
-                hbs_o1(m, key, io.new_hb, [&](unsigned, double raw) { norm += raw; });
+                double norm = 0, mx = 0;
+                hbs_o1(m, key, io.new_hb, [&](unsigned, double raw) {
+                    norm += raw;
+                    mx = fmax(mx, raw);
+                });
                 rinv = 1. / norm;
+                wmax = mx * rinv;
                 if (io.new_hb) v *= norm / m.d.s_norm;
             } else {
                 unsigned n_occ = sing_allowed(key);
@@ -90,9 +98,13 @@ struct HbProvider {
                 if (io.new_hb) {
                     p1++;
                     ns = p1;
-                    double norm = 0;
-                    hbs_o2_half(m, key, p1, [&](unsigned, double raw) { norm += raw; });
+                    double norm = 0, mx = 0;
+                    hbs_o2_half(m, key, p1, [&](unsigned, double raw) {
+                        norm += raw;
+                        mx = fmax(mx, raw);
+                    });
                     rinv = 1. / norm;
+                    wmax = mx * rinv;
                     v *= norm / m.s_tens[mol_elec_orb(m, o, p1) % M];
                 } else {
                     rinv = 1. / hbs_o2_norm(m, key, p1);
@@ -120,13 +132,15 @@ struct HbProvider {
                     OccMask o = mol_occ_mask(m, key);
                     unsigned o1_orb = mol_elec_orb(m, o, p1);
                     bool excl = io.new_hb && (p1 / (ne / 2) == mol_elec_orb(m, o, p2) / M);
-                    double norm = 0, first = 0;
+                    double norm = 0, first = 0, mx = 0;
                     hbs_u1(m, key, o1_orb, [&](unsigned j, double raw) {
                         if (j == 0) first = raw;
                         norm += raw;
+                        mx = fmax(mx, raw);
                     });
                     if (excl) norm -= first;
                     rinv = 1. / norm;
+                    wmax = mx * rinv;
                     if (io.new_hb) v *= norm / m.exch_norms[o1_orb % M];
                 }
                 p3 = 0;
@@ -148,15 +162,24 @@ struct HbProvider {
                     nd = 0;
                     p3 = u1;
                     unsigned o1_orb = mol_elec_orb(m, o, p1), o2_orb = mol_elec_orb(m, o, p2);
-                    double norm = 0;
+                    double norm = 0, mx = 0;
                     unsigned len = 0;
                     if (io.new_hb) {
-                        hbs_u2_half(m, o1_orb, o2_orb, u1, key, [&](unsigned j, double raw) { norm += raw; len = j + 1; });
+                        hbs_u2_half(m, o1_orb, o2_orb, u1, key, [&](unsigned j, double raw) {
+                            norm += raw;
+                            mx = fmax(mx, raw);
+                            len = j + 1;
+                        });
                     } else {
-                        hbs_u2(m, o1_orb, o2_orb, u1, [&](unsigned j, double raw) { norm += raw; len = j + 1; });
+                        hbs_u2(m, o1_orb, o2_orb, u1, [&](unsigned j, double raw) {
+                            norm += raw;
+                            mx = fmax(mx, raw);
+                            len = j + 1;
+                        });
                     }
                     ns = len;
                     rinv = norm != 0 ? 1 / norm : 1.0;
+                    wmax = mx * rinv;
                     double tot = norm / m.exch_norms[o2_orb % M];
                     if (io.new_hb || tot == 0) v *= tot;
                 }

@@ -97,11 +97,12 @@ struct HhStage1 {
         unsigned long long n = *n_in;
         return n < cap ? (size_t)n : (size_t)cap;
     }
-    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv) const {
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv, double &wmax) const {
         v = fabs(vals[i]);
         nd = v > 0 ? 0u : 1u;
         ns = 2;
         rinv = 1.0;
+        wmax = fmax(hub_t, elec_ph);  // the row is not normalised
     }
     template <class F>
     __device__ void visit(size_t, double, F &&f) const {
@@ -122,8 +123,9 @@ struct HhStage2 {
         unsigned long long n = *n_in;
         return n < cap ? (size_t)n : (size_t)cap;
     }
-    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv) const {
+    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv, double &wmax) const {
         rinv = 1.0;
+        wmax = fmax(hub_t, elec_ph);
         uint32_t di = pw[i], ex = ps[i];
         det[i] = di;
         ph_ex[i] = ex;
