@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
+#include <type_traits>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -351,6 +352,18 @@ __device__ __forceinline__ void block_excl_scan(double a, unsigned long long c, 
     __syncthreads();
 }
 
+// Row generators call fr_emit(f, j, w) for every entry; a visitor may return void (visit everything) or bool
+// (false = the visitor has all it needs: stop generating the row).
+template <class F>
+__host__ __device__ __forceinline__ bool fr_emit(F &&f, unsigned j, double w) {
+    if constexpr (std::is_void<decltype(f(j, w))>::value) {
+        f(j, w);
+        return true;
+    } else {
+        return f(j, w);
+    }
+}
+
 // The systematic-sampling grid g_k = rn0 + k * unit, k = 0 .. n - 1 (n = sampling budget).  The reference
 // walks it with a running `rn_sys += unit` and the test `rn_sys < lbound` (compress_utils.cpp:313-318,
 // 745-755); here an element asks how many grid points lie strictly below a bound.  Indices >= n do not
@@ -358,13 +371,14 @@ __device__ __forceinline__ void block_excl_scan(double a, unsigned long long c, 
 // total from drawing an (n+1)-th sample.
 struct SysGrid {
     double rn0, unit;
+    double inv;  // 1 / unit: first guess of an index (the guess is then made consistent with the FP grid, see below)
     long long n;
     __device__ __forceinline__ double point(long long k) const {
         return k < n ? fma((double)k, unit, rn0) : INFINITY;
     }
     __device__ __forceinline__ long long count_below(double x) const {
         if (n <= 0 || !(x > rn0)) return 0;
-        double q = (x - rn0) / unit;
+        double q = (x - rn0) * inv;
         long long k = q >= (double)n ? n : (long long)ceil(q);
         if (k < 0) k = 0;
         if (k > n) k = n;

@@ -313,10 +313,12 @@ sys_comp_kernel(double *__restrict__ vals, size_t n, const unsigned long long *_
             j0++;
         }
         sg.rn0 = r;
+        sg.inv = 1.0 / sg.unit;
         sg.n = (long long)n_samp - j0;
     } else {
         sg.rn0 = INFINITY;
         sg.unit = INFINITY;
+        sg.inv = 0;
         sg.n = 0;
     }
     double cs = 0;
@@ -390,7 +392,8 @@ struct MatProvider {
     }
     template <class F>
     __device__ void visit(size_t i, double, F &&f) const {
-        for (uint32_t j = 0; j < n_sub; j++) f(j, subw[i * n_sub + j]);
+        for (uint32_t j = 0; j < n_sub; j++)
+            if (!fr_emit(f, j, subw[i * n_sub + j])) return;
     }
 };
 

@@ -339,11 +339,14 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
         }
     }
     // shared accumulators (32-bit: native shared-memory atomics): [buf][0..2] count limbs, [buf][3..10] sum limbs,
-    // 16 bits each (a warp's total < 2^21, a CTA's < 2^25).  Two buffers alternate so that one barrier per round suffices.
+    // 16 bits each (a warp's total < 2^21, a CTA's < 2^25).  THREE buffers rotate so that one barrier per round
+    // suffices: round r accumulates into buffer r % 3 and clears buffer (r + 1) % 3, which was last read in round
+    // r - 2 -- every thread has passed the barrier of round r - 1 after those reads.  (With two buffers a warp that
+    // runs ahead could clear the totals of round r - 1 while a slower warp is still reading them.)
     unsigned *acc = reinterpret_cast<unsigned *>(shc);
-    unsigned long long *acc_min = shc + 16;
-    if (threadIdx.x < 24) acc[threadIdx.x] = 0;
-    if (threadIdx.x == 24) *acc_min = 0x7ff0000000000000ull;  // +inf
+    unsigned long long *acc_min = shc + 18;
+    if (threadIdx.x < 36) acc[threadIdx.x] = 0;
+    if (threadIdx.x == 36) *acc_min = 0x7ff0000000000000ull;  // +inf
     __syncthreads();
     const int lane = threadIdx.x & 31;
     unsigned long long cnt_tot = 0;
@@ -354,7 +357,7 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
     FR_BT(1);
     for (unsigned round = 0; round < 4096; round++) {
         if (dist && round < 4 && blockIdx.x == 0 && threadIdx.x == 0) gacc[40 + 4 * round] = fr_globaltimer();
-        unsigned *a = acc + 12 * (round & 1);
+        unsigned *a = acc + 12 * (round % 3);
         unsigned long long c = 0;
         unsigned __int128 s = 0;
         const double fac = (double)nrem;
@@ -390,8 +393,8 @@ __device__ __forceinline__ BracketResult bracket_solve(cg::grid_group &grid, con
                 if (lane == 0 && wm < INFINITY) atomicMin(acc_min, (unsigned long long)__double_as_longlong(wm));
             }
         }
-        // clear the other buffer for the next round (its readers passed the previous barrier)
-        if (threadIdx.x < 12) acc[12 * ((round & 1) ^ 1) + threadIdx.x] = 0;
+        // clear the next round's buffer (its last readers passed the previous barrier)
+        if (threadIdx.x < 12) acc[12 * ((round + 1) % 3) + threadIdx.x] = 0;
         __syncthreads();
         res.rounds = round + 1;
         unsigned long long lim[11];
@@ -837,10 +840,12 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
             j0++;
         }
         sg.rn0 = r;
+        sg.inv = 1.0 / sg.unit;
         sg.n = (long long)nrem - j0;
     } else {
         sg.rn0 = INFINITY;
         sg.unit = INFINITY;
+        sg.inv = 0;
         sg.n = 0;
     }
 
@@ -884,8 +889,8 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                         uint32_t ns = b.nsub[i], kb = b.keep[i];
                         double sub_lb = lbound - wr;
                         uint32_t n_kept_out = 0, s1 = 0, s2 = 0;
-                        prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) {
-                            if (j >= ns) return;
+                        prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) -> bool {
+                            if (j >= ns) return false;
                             if (((kb >> j) & 1u) && wj != 0) {
                                 k++;
                                 n_kept_out++;
@@ -900,6 +905,8 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                                     if (g < sub_lb) anomalies++;
                                 }
                             }
+                            // the rest of the row matters only while a grid point or a preserved piece is left in it
+                            return g < lbound || ((unsigned long long)kb >> (j + 1)) != 0;
                         });
                         // one or two resampled outputs and nothing preserved: remember the sub-indices so that the
                         // emit pass does not have to regenerate the row (kcnt bits 30-31 = count, 16-20 / 21-25 = subs)
@@ -974,8 +981,9 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                 long long k0 = sg.count_below(start);
                 double g = sg.point(k0);
                 double sub_lb = lbound - wr;
-                prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) {
-                    if (j >= ns) return;
+                const unsigned long long o_end = o + k;
+                prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) -> bool {
+                    if (j >= ns) return false;
                     if (((kb >> j) & 1u) && wj != 0) {
                         FR_EMIT(v * wj, j);
                     } else {
@@ -986,6 +994,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                             g = sg.point(k0);
                         }
                     }
+                    return o < o_end;  // all outputs of this input are written
                 });
             }
 #undef FR_EMIT

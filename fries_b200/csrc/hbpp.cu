@@ -193,8 +193,7 @@ struct HbProvider {
     template <class F>
     __device__ void visit(size_t i, double rinv, F &&f) const {
         if (S == 0) {
-            f(0u, io.p_doub);
-            f(1u, 1 - io.p_doub);
+            if (fr_emit(f, 0u, io.p_doub)) fr_emit(f, 1u, 1 - io.p_doub);
             return;
         }
         const unsigned ne = m.d.n_elec, M = m.d.n_orb;
@@ -202,23 +201,24 @@ struct HbProvider {
         const uint64_t key = io.keys[io.det[i]];
         unsigned p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
         if (S == 1) {
-            hbs_o1(m, key, io.new_hb, [&](unsigned j, double raw) { f(j, raw * rinv); });
+            hbs_o1(m, key, io.new_hb, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
         } else if (S == 2) {
             if (io.new_hb)
-                hbs_o2_half(m, key, p1, [&](unsigned j, double raw) { f(j, raw * rinv); });
+                hbs_o2_half(m, key, p1, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
             else
-                hbs_o2(m, key, p1, [&](unsigned j, double raw) { f(j, raw * rinv); });
+                hbs_o2(m, key, p1, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
         } else if (S == 3) {
             OccMask o = mol_occ_mask(m, key);
             bool excl = io.new_hb && (p1 / (ne / 2) == mol_elec_orb(m, o, p2) / M);
-            hbs_u1(m, key, mol_elec_orb(m, o, p1), [&](unsigned j, double raw) { f(j, (excl && j == 0) ? 0.0 : raw * rinv); });
+            hbs_u1(m, key, mol_elec_orb(m, o, p1),
+                   [&](unsigned j, double raw) { return fr_emit(f, j, (excl && j == 0) ? 0.0 : raw * rinv); });
         } else {
             OccMask o = mol_occ_mask(m, key);
             unsigned o1_orb = mol_elec_orb(m, o, p1), o2_orb = mol_elec_orb(m, o, p2);
             if (io.new_hb)
-                hbs_u2_half(m, o1_orb, o2_orb, p3, key, [&](unsigned j, double raw) { f(j, raw * rinv); });
+                hbs_u2_half(m, o1_orb, o2_orb, p3, key, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
             else
-                hbs_u2(m, o1_orb, o2_orb, p3, [&](unsigned j, double raw) { f(j, raw * rinv); });
+                hbs_u2(m, o1_orb, o2_orb, p3, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
         }
     }
 };

@@ -106,8 +106,7 @@ struct HhStage1 {
     }
     template <class F>
     __device__ void visit(size_t, double, F &&f) const {
-        f(0u, hub_t);  // NOT normalised in the reference (:193-194)
-        f(1u, elec_ph);
+        if (fr_emit(f, 0u, hub_t)) fr_emit(f, 1u, elec_ph);  // NOT normalised in the reference (:193-194)
     }
 };
 struct HhStage2 {
@@ -141,8 +140,7 @@ struct HhStage2 {
     }
     template <class F>
     __device__ void visit(size_t, double, F &&f) const {
-        f(0u, hub_t);  // only reached with ndiv == 0, i.e. value 0: the reference reads its stale row
-        f(1u, elec_ph);
+        if (fr_emit(f, 0u, hub_t)) fr_emit(f, 1u, elec_ph);  // only reached with ndiv == 0 (value 0)
     }
 };
 

@@ -348,12 +348,12 @@ __host__ __device__ __forceinline__ void hbs_o1(const MolView &m, uint64_t key, 
     uint32_t am = o.a;
     if (exclude_first > 0) am &= am - 1;
     while (am) {
-        f(j++, m.s_tens[fr_ctz(am)]);
+        if (!fr_emit(f, j++, m.s_tens[fr_ctz(am)])) return;
         am &= am - 1;
     }
     uint32_t bm = o.b;
     while (bm) {
-        f(j++, m.s_tens[fr_ctz(bm)]);
+        if (!fr_emit(f, j++, m.s_tens[fr_ctz(bm)])) return;
         bm &= bm - 1;
     }
 }
@@ -368,13 +368,13 @@ __host__ __device__ __forceinline__ void hbs_o2_half(const MolView &m, uint64_t 
     for (; j < upper; j++) {
         unsigned q = fr_ctz(am);
         am &= am - 1;
-        f(j, o1 < M ? m.d_same[FR_TRI_NODIAG(q, o1)] : m.d_diff[(o1 - M) * M + q]);
+        if (!fr_emit(f, j, o1 < M ? m.d_same[FR_TRI_NODIAG(q, o1)] : m.d_diff[(o1 - M) * M + q])) return;
     }
     uint32_t bm = o.b;
     for (j = h; j < o1_idx; j++) {
         unsigned q = fr_ctz(bm);
         bm &= bm - 1;
-        f(j, o1 < M ? m.d_diff[o1 * M + q] : m.d_same[FR_TRI_NODIAG(q, o1 - M)]);
+        if (!fr_emit(f, j, o1 < M ? m.d_diff[o1 * M + q] : m.d_same[FR_TRI_NODIAG(q, o1 - M)])) return;
     }
 }
 // calc_o2_probs :203-233: ne entries in index order (entry o1_idx is 0)
@@ -390,7 +390,7 @@ __host__ __device__ __forceinline__ void hbs_o2(const MolView &m, uint64_t key, 
         else if (j < o1_idx) raw = m.d_same[FR_TRI_NODIAG(q, o1s)];
         else if (j > o1_idx) raw = m.d_same[FR_TRI_NODIAG(o1s, q)];
         else raw = 0;
-        f(j, raw);
+        if (!fr_emit(f, j, raw)) return;
     }
 }
 // its norm is accumulated opposite-spin block first, then the same-spin entries (:211-224)
@@ -418,7 +418,7 @@ __host__ __device__ __forceinline__ void hbs_u1(const MolView &m, uint64_t key, 
     while (vm) {
         unsigned k = fr_ctz(vm);
         vm &= vm - 1;
-        f(j++, m.exch_sqrt[k < o1s ? FR_TRI_NODIAG(k, o1s) : FR_TRI_NODIAG(o1s, k)]);
+        if (!fr_emit(f, j++, m.exch_sqrt[k < o1s ? FR_TRI_NODIAG(k, o1s) : FR_TRI_NODIAG(o1s, k)])) return;
     }
 }
 __host__ __device__ __forceinline__ double hbs_u2_weight(const MolView &m, unsigned o2s, unsigned u2) {
@@ -436,7 +436,7 @@ __host__ __device__ __forceinline__ void hbs_u2(const MolView &m, unsigned o1_or
     unsigned num = mol_lookup(m, irrep, 0);
     for (unsigned i = 0; i < num; i++) {
         unsigned u2 = mol_lookup(m, irrep, i + 1);
-        f(i, ((same && u2 != u1s) || !same) ? hbs_u2_weight(m, o2s, u2) : 0.0);
+        if (!fr_emit(f, i, ((same && u2 != u1s) || !same) ? hbs_u2_weight(m, o2s, u2) : 0.0)) return;
     }
 }
 // calc_u2_probs_half :368-412: stops at u2 >= u1 for same-spin pairs; occupied u2 get 0
@@ -452,7 +452,7 @@ __host__ __device__ __forceinline__ void hbs_u2_half(const MolView &m, unsigned 
         unsigned u2 = mol_lookup(m, irrep, i + 1);
         if (same && u2 >= u1s) break;
         bool ok = ((same && u2 != u1s) || !same) && !fr_read_bit(det, u2 + M * u2_spin);
-        f(i, ok ? hbs_u2_weight(m, o2s, u2) : 0.0);
+        if (!fr_emit(f, i, ok ? hbs_u2_weight(m, o2s, u2) : 0.0)) return;
     }
 }
 
