@@ -328,12 +328,13 @@ struct HvScratch {
 
 // dest <- id_fac * src + h_fac * H * src.  Spawn buffers: hb->spawn_keys / spawn_vals (cap entries).
 static int h_apply_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned src, unsigned dest, double id_fac,
-                       double h_fac, bool do_diag, uint64_t *n_spawned) {
+                       double h_fac, bool do_diag, uint64_t *n_spawned, size_t only_first = 0) {
     fries_ctx *c = vec->ctx;
     FRIES_REQUIRE(src < vec->n_vecs && dest < vec->n_vecs && src != dest, "h_apply: need two different rows");
     VecCounters cnt;
     FRIES_TRY(vec->read_counters(&cnt));
     size_t n_parents = (size_t)cnt.n;
+    if (only_first && only_first < n_parents) n_parents = only_first;  // the dense subspace of a semi-stochastic run
     if (n_spawned) *n_spawned = 0;
     if (n_parents == 0) return FRIES_OK;
     size_t smem = (size_t)mol->view.d.blob_doubles * 8;
@@ -513,12 +514,12 @@ __global__ void trial_dot_kernel(VecView v, const uint64_t *__restrict__ t_keys,
                                  size_t n_trial, unsigned row, double *out);
 
 struct IterScalars {  // hb->scal layout (doubles)
-    enum { R4 = 0, NUMER = 4, DENOM = 5, NEW_NORM = 6, STATS = 8 };
+    enum { R4 = 0, NUMER = 4, DENOM = 5, NEW_NORM = 6, STATS = 8, DENSE_NORM = 43 };
 };
 
 __global__ void iter_stats_kernel(const CompState *st, const VecCounters *cnt, const double *scal, double *out) {
     // out[0..]: glob_norm, numer, denom, n_kept, n_matrix_samples, curr_size, overflow flags, anomalies
-    out[0] = st[6].glob_norm;
+    out[0] = st[6].glob_norm + scal[IterScalars::DENSE_NORM];  // frisys_mol.cpp:504: glob_norm += dense_norm()
     out[1] = scal[IterScalars::NUMER];
     out[2] = scal[IterScalars::DENOM];
     out[3] = (double)st[6].n_kept;
@@ -543,15 +544,40 @@ __global__ void state_to_r4_kernel(const CompState *st, double *r4) {
     r4[3] = (double)st->n_kept;
 }
 
+// number of compressible elements: stored minus the dense subspace (frisys_mol.cpp:419,503)
+__global__ void dense_count_kernel(const VecCounters *cnt, unsigned long long n_dense, unsigned long long *out) {
+    unsigned long long n = cnt->n;
+    *out = n > n_dense ? n - n_dense : 0ull;
+}
+// sum |v| over the dense subspace (DistVec::dense_norm vec_utils.hpp:903-917); one CTA, fixed order
+__global__ void dense_norm_kernel(const double *vals, size_t n_dense, double *out) {
+    __shared__ double sh[33];
+    double t = 0;
+    for (size_t i = threadIdx.x; i < n_dense; i += blockDim.x) t += fabs(vals[i]);
+    t = block_sum(t, sh);
+    if (threadIdx.x == 0) *out = t;
+}
+static const unsigned long long *stochastic_count(fries_vec *vec, fries_hbpp *hb) {
+    if (vec->n_dense == 0) return &vec->cnt.p->n;
+    dense_count_kernel<<<1, 1, 0, vec->ctx->stream>>>(vec->cnt.p, (unsigned long long)vec->n_dense, hb->n_scalar.p + 1);
+    vec->ctx->launch_count++;
+    return hb->n_scalar.p + 1;
+}
+
 static int compress_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, unsigned target_nonz, double uniform) {
-    // find_preserve -> sys_comp -> del_at_pos for the zeroed elements (frisys_mol.cpp:501-539)
+    // find_preserve -> sys_comp -> del_at_pos for the zeroed elements (frisys_mol.cpp:501-539); the dense subspace of
+    // a semi-stochastic run (the first n_dense positions) is left alone
     fries_ctx *c = vec->ctx;
     VecView v = vec->view();
-    double *vals = v.vals + (size_t)row * v.cap;
-    FRIES_TRY(fries_find_preserve_launch(c, vals, vec->cap, &vec->cnt.p->n, target_nonz, hb->keep_flags.p, hb->st.p + 6,
+    const size_t nd = vec->n_dense;
+    double *vals = v.vals + (size_t)row * v.cap + nd;
+    FRIES_TRY(fries_find_preserve_launch(c, vals, vec->cap - nd, stochastic_count(vec, hb), target_nonz,
+                                         hb->keep_flags.p + nd, hb->st.p + 6,
                                          hb->part_d.p, hb->part_c.p, 0, hb->comm, hb->pred.p + 5, hb->cand_x.p,
                                          hb->cand_m.p));
     state_to_r4_kernel<<<1, 1, 0, c->stream>>>(hb->st.p + 6, hb->scal.p + IterScalars::R4);
+    c->launch_count++;
+    dense_norm_kernel<<<1, 256, 0, c->stream>>>(v.vals + (size_t)row * v.cap, nd, hb->scal.p + IterScalars::DENSE_NORM);
     c->launch_count++;
     (void)uniform;
     return FRIES_OK;
@@ -560,9 +586,11 @@ static int compress_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, uns
 static int resample_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, double uniform) {
     fries_ctx *c = vec->ctx;
     VecView v = vec->view();
-    double *vals = v.vals + (size_t)row * v.cap;
-    FRIES_TRY(fries_sys_comp_launch(c, vals, vec->cap, &vec->cnt.p->n, hb->keep_flags.p, hb->scal.p + IterScalars::R4,
-                                    0.0, 0.0, -1LL, uniform, hb->st.p + 7, hb->part_d.p, hb->part_c.p, 0, hb->comm));
+    const size_t nd = vec->n_dense;
+    double *vals = v.vals + (size_t)row * v.cap + nd;
+    FRIES_TRY(fries_sys_comp_launch(c, vals, vec->cap - nd, stochastic_count(vec, hb), hb->keep_flags.p + nd,
+                                    hb->scal.p + IterScalars::R4, 0.0, 0.0, -1LL, uniform, hb->st.p + 7, hb->part_d.p,
+                                    hb->part_c.p, 0, hb->comm));
     FRIES_TRY(fries_vec_compact_flags_dev(vec, hb->keep_flags.p));
     return FRIES_OK;
 }
@@ -611,13 +639,22 @@ extern "C" int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hb
     CUDA_TRY(cudaSetDevice(c->device));
     VecView v = vec->view();
     size_t smem = (size_t)mol->view.d.blob_doubles * 8;
-    // steps 2-3: hierarchical compression of H's columns
-    FRIES_TRY(fries_hbpp_stages_dev(hb, mol, v.keys, v.vals, &vec->cnt.p->n, p->p_doub, p->new_hb, u6, p->matr_samp));
+    // steps 2-3: hierarchical compression of H's columns (semi-stochastic: only of the columns outside the dense
+    // subspace, frisys_mol.cpp:414-419)
+    const size_t nd = vec->n_dense;
+    FRIES_TRY(fries_hbpp_stages_dev(hb, mol, v.keys + nd, v.vals + nd, stochastic_count(vec, hb), p->p_doub, p->new_hb, u6,
+                                    p->matr_samp));
     // step 5: spawn (fused into finalize) and merge into row 1
-    HbSpawnArgs sp{v.vals, p->eps, p->init_thresh, hb->spawn_keys.p, hb->spawn_vals.p, 1, nullptr, nullptr, nullptr, 0,
+    HbSpawnArgs sp{v.vals + nd, p->eps, p->init_thresh, hb->spawn_keys.p, hb->spawn_vals.p, 1, nullptr, nullptr, nullptr, 0,
                    {nullptr}, 0};
-    FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, v.keys, p->p_doub, p->new_hb, &sp));
+    FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, v.keys + nd, p->p_doub, p->new_hb, &sp));
     FRIES_TRY(fries_vec_merge_dev(vec, hb->spawn_keys.p, hb->spawn_vals.p, hb->cap, &hb->st.p[4].n_out, 0, 1));
+    if (nd) {
+        // deterministic subspace multiplication (frisys_mol.cpp:479-485): every connection of the dense determinants,
+        // -eps * <D'|H|D> * v_D with the values from before the spawn (row 0 is untouched so far), into row 1
+        FRIES_TRY(h_apply_dev(vec, mol, hb, 0, 1, 0.0, -p->eps, false, nullptr, nd));
+        v = vec->view();
+    }
     // step 7: death/cloning, add_vecs(0, 1), zero row 1
     {
         ProfScope ps(c, "death_axpy");

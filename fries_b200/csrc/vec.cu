@@ -289,6 +289,19 @@ extern "C" int fries_vec_create_hh(fries_ctx *c, size_t capacity, unsigned n_sit
     (*out)->hh_ph_bits = ph_bits;
     return FRIES_OK;
 }
+// Semi-stochastic calculations (DistVec::init_dense vec_utils.hpp:858-897): the first n_dense stored determinants are
+// the deterministic subspace -- never deleted, never compressed; their columns of H are applied exactly
+extern "C" int fries_vec_set_dense(fries_vec *vec, size_t n_dense) {
+    FRIES_REQUIRE(vec, "fries_vec_set_dense: NULL vector");
+    FRIES_REQUIRE(vec->n_ranks == 1 || n_dense == 0, "fries_vec_set_dense: the dense subspace is single-rank in this build");
+    VecCounters cnt;
+    FRIES_TRY(vec->read_counters(&cnt));
+    FRIES_REQUIRE(n_dense <= cnt.n, "fries_vec_set_dense: %zu exceeds the number of stored determinants", n_dense);
+    vec->n_dense = n_dense;
+    vec->min_del_idx = n_dense;
+    return FRIES_OK;
+}
+
 // DistVec::set_min_del_idx vec_utils.hpp: positions below idx are never deleted
 extern "C" int fries_vec_set_min_del_idx(fries_vec *vec, size_t idx) {
     FRIES_REQUIRE(vec, "NULL argument");

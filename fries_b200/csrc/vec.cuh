@@ -52,6 +52,7 @@ struct fries_vec {
     DevBuf<double> red_d;               // reduction partials
     DevBuf<unsigned long long> red_c;
     size_t min_del_idx = 0;
+    size_t n_dense = 0;                  // semi-stochastic: the first n_dense stored determinants form the dense subspace
     fries_mol *diag_mol = nullptr;
     double hf_en = 0;
     uint64_t last_spawned = 0;

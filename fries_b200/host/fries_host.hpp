@@ -424,7 +424,27 @@ class DistVec {
         std::ofstream fv(path + "vals0.dat", std::ios::binary);
         fv.write((const char *)vals.data(), vals.size() * sizeof(double));
         std::ofstream fz(path + "dense.txt");
-        fz << 0 << '\n';
+        fz << n_dense << "," << '\n';
+    }
+    // DistVec::init_dense vec_utils.hpp:858-897 (single rank): the determinants of the file (read_dets io_utils.cpp:565-586,
+    // one integer per determinant) become the first stored elements, with value 0, and are never deleted
+    size_t n_dense = 0;
+    size_t init_dense(const std::string &read_path, const std::string &save_dir) {
+        std::ifstream fdets(read_path);
+        if (!fdets.is_open()) throw std::runtime_error("Could not open file: " + read_path);
+        std::vector<uint64_t> dets;
+        long long in_det;
+        while (fdets >> in_det) dets.push_back((uint64_t)in_det);
+        std::vector<double> zeros(dets.size() * n_vecs, 0.0);
+        check(fries_vec_set_min_del_idx(h, dets.size()));  // an upload drops all-zero elements beyond this index
+        upload(dets, zeros);
+        n_dense = dets.size();
+        check(fries_vec_set_dense(h, n_dense));
+        std::ofstream dense_f(save_dir + "dense.txt");
+        if (!dense_f.is_open())
+            throw std::runtime_error("Could not load deterministic subspace from file at path " + save_dir + "dense.txt");
+        dense_f << n_dense << "," << '\n';
+        return n_dense;
     }
     // DistVec::load vec_utils.hpp:761-844 (single rank): re-hash, drop |v| <= 1e-9
     void load(const std::string &path) {
@@ -436,10 +456,16 @@ class DistVec {
         if (!fv.is_open()) throw std::runtime_error("Error: could not open saved binary vector file at " + path + "vals0.dat");
         std::vector<double> all(n * n_vecs, 0.0);
         fv.read((char *)all.data(), all.size() * sizeof(double));
+        {   // sizes of the dense subspaces (one per rank; single rank here): the first n_dense entries are kept as they are
+            std::ifstream fz(path + "dense.txt");
+            n_dense = 0;
+            if (fz.is_open()) fz >> n_dense;
+            if (n_dense > n) n_dense = n;
+        }
         std::vector<uint64_t> dets;
         std::vector<double> rows[8];
         for (size_t i = 0; i < n; i++) {
-            bool keep = false;
+            bool keep = i < n_dense;
             for (unsigned r = 0; r < n_vecs; r++) keep = keep || std::fabs(all[r * n + i]) > 1e-9;
             if (!keep) continue;
             dets.push_back(key_from_bytes(&bytes[i * nb], nb));
@@ -447,7 +473,9 @@ class DistVec {
         }
         std::vector<double> vals;
         for (unsigned r = 0; r < n_vecs; r++) vals.insert(vals.end(), rows[r].begin(), rows[r].end());
+        check(fries_vec_set_min_del_idx(h, n_dense));
         upload(dets, vals);
+        if (n_dense) check(fries_vec_set_dense(h, n_dense));
     }
 };
 

@@ -18,6 +18,7 @@ int main(int argc, char *argv[]) {
     bool has_load = args.has("load_dir"), has_ini = args.has("ini_vec"), has_trial = args.has("trial_vec");
     std::string load_dir = args.str("load_dir", ""), ini_path = args.str("ini_vec", ""), trial_path = args.str("trial_vec", "");
     bool has_det_space = args.has("det_space");
+    std::string det_space_path = args.str("det_space", "");
     double eps = args.num("epsilon");
     std::string point_group = args.str("point_group", "C1");
     bool has_shift = args.has("ham_shift");
@@ -33,8 +34,6 @@ int main(int argc, char *argv[]) {
         return 1;
     }
     try {
-        if (has_det_space)
-            throw std::runtime_error("--det_space (semi-stochastic dense subspace) is not available in this build");
         Context ctx(device);
         double shift_damping = 0.05;
         unsigned shift_interval = 10, save_interval = 100;
@@ -74,8 +73,12 @@ int main(int argc, char *argv[]) {
         size_t n_hf_doub = mol.count_doub_ex(hf_det), n_hf_sing = mol.count_singex(hf_det);
         double p_doub = (double)n_hf_doub / (n_hf_sing + n_hf_doub);
 
-        {   // sizes of the deterministic subspaces (none)
-            if (!has_load) {
+        // deterministic subspace of a semi-stochastic calculation (frisys_mol.cpp:233-252): its determinants come first
+        size_t n_determ = 0;
+        if (!has_load) {
+            if (has_det_space) {
+                n_determ = sol_vec.init_dense(det_space_path, result_dir);
+            } else {
                 std::ofstream dense_f(result_dir + "dense.txt");
                 if (!dense_f.is_open()) throw std::runtime_error("Error opening file containing sizes of deterministic subspaces");
                 dense_f << 0 << ", " << '\n';
@@ -84,6 +87,7 @@ int main(int argc, char *argv[]) {
         // initial vector
         if (has_load) {
             sol_vec.load(load_dir);
+            n_determ = sol_vec.n_dense;
             load_last_line(load_dir + "S.txt", &en_shift);
         } else if (has_ini) {
             std::vector<uint64_t> d;
@@ -115,7 +119,20 @@ int main(int argc, char *argv[]) {
         }
         check(fries_frisys_mol_setup(sol_vec.h, mol.h, spawn_length, trial_dets.data(), trial_vals.data(), trial_dets.size(),
                                      htrial_dets.data(), htrial_vals.data(), htrial_dets.size(), &sol_vec.hb));
-        std::cout << "Elements in dense H: " << 0 << "\n";
+        {   // frisys_mol.cpp:398-401: size of the pre-computed dense part of H = all connections of the dense determinants
+            size_t tot_dense_h = 0;
+            if (n_determ) {
+                std::vector<uint64_t> d;
+                std::vector<double> vv;
+                sol_vec.download(d, vv);
+                std::vector<uint64_t> off(n_determ + 1);
+                check(fries_mol_sing_ex(mol.h, d.data(), n_determ, off.data(), nullptr, 0));
+                tot_dense_h += off[n_determ];
+                check(fries_mol_doub_ex(mol.h, d.data(), n_determ, off.data(), nullptr, 0));
+                tot_dense_h += off[n_determ];
+            }
+            std::cout << "Elements in dense H: " << tot_dense_h << "\n";
+        }
 
         for (unsigned iterat = 0; iterat < max_iter; iterat++) {
             size_t n_ini = 0;

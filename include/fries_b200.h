@@ -234,6 +234,11 @@ int fries_vec_create_hh(fries_ctx *ctx, size_t capacity, unsigned n_sites, unsig
                         unsigned n_vecs, const uint32_t *h_proc_scrambler, const uint32_t *h_vec_scrambler, int n_ranks,
                         int rank, fries_vec **out);
 int fries_vec_set_min_del_idx(fries_vec *vec, size_t idx); /* DistVec::set_min_del_idx */
+/* Semi-stochastic calculations (DistVec::init_dense vec_utils.hpp:858-897, frisys_mol.cpp:347-401,414-419,479-485,
+ * 503-504,533-536): the first n_dense stored determinants are the deterministic subspace.  fries_frisys_mol_iterate
+ * then compresses and resamples only the rest, applies the dense determinants' columns of H exactly, and reports the
+ * one-norm including the dense part.  Single rank. */
+int fries_vec_set_dense(fries_vec *vec, size_t n_dense);
 /* what 0: hub_diag hub_holstein.cpp:101-136 -> out[n]; 1: find_neighbors_1D hh_vec.hpp:139-175 as two bit masks per
  * state (hop to orb+1, hop to orb-1) -> out[2n]; 2: per-state terms of calc_ref_ovlp hub_holstein.hpp:93-182 -> out[n] */
 int fries_hh_batch(fries_ctx *ctx, int what, const uint64_t *h_keys, const double *h_vals, size_t n, unsigned n_sites,

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oraclelib
-from driver_utils import OURS, REF, exact_ground_state, read_col, run, write_fcidump, write_hf_dir
+from driver_utils import OURS, REF, exact_ground_state, read_col, run, write_fcidump, write_hf_dir, write_vec
 from fries_b200.synth import SynthMol
 
 pytestmark = pytest.mark.gpu
@@ -90,6 +90,58 @@ def test_frisys_mol_driver_energy_and_files(tiny, tmp_path):
     if "ref" in res:
         er, sr = res["ref"]
         assert abs(e - er) < 5 * (s + sr) + 2e-4, (e, s, er, sr)
+
+
+def test_frisys_mol_semistochastic_det_space(tiny, tmp_path):
+    """--det_space (frisys_mol.cpp:233-252,347-401,479-485): the determinants of the file form a
+    dense subspace whose columns of H are applied exactly.  Same files and statistics as the reference's driver."""
+    sm, om, e_corr, e_hf, n = tiny
+    fd = str(tmp_path / "FCIDUMP")
+    write_fcidump(fd, sm, "D2")
+    # dense subspace: the Hartree-Fock determinant and its 24 most strongly coupled connections
+    hf = np.array([sm.hf], np.uint64)
+    k, v = om.h_apply(hf, np.ones(1), 0.0, 1.0)
+    order = np.argsort(-np.abs(v), kind="stable")
+    dense = [int(sm.hf)] + [int(x) for x in k[order] if int(x) != int(sm.hf)][:24]
+    dp = str(tmp_path / "dense_dets.txt")
+    open(dp, "w").write("\n".join(str(d) for d in dense) + "\n")
+    # start from HF plus all of its connections, so that the stochastic part is not empty in the first iteration (the
+    # reference's driver does not survive an empty one)
+    ip = str(tmp_path / "ini_")
+    others = [(int(a), float(b)) for a, b in zip(k, v) if int(a) != int(sm.hf)]
+    write_vec(ip, [int(sm.hf)] + [a for a, _ in others], [100.0] + [-20.0 * b for _, b in others])
+    res = {}
+    exes = [("ours", os.path.join(OURS, "frisys_mol"))]
+    if have_ref:
+        exes.append(("ref", os.path.join(REF, "frisys_mol")))
+    n_it = 5000
+    for name, exe in exes:
+        rd = str(tmp_path / name) + "/"
+        os.makedirs(rd)
+        # mat_nonz = 3000: the reference sizes the scratch of its dense-H set-up by spawn_length = 4 mat_nonz
+        r = run(exe, ["--fcidump_path", fd, "--distribution", "HB_unnorm", "--vec_nonz", 150, "--mat_nonz", 3000, "--max_dets",
+                      20000, "--epsilon", 0.05, "--target", 500, "--max_iter", n_it, "--result_dir", rd, "--point_group",
+                      "D2", "--det_space", dp, "--ini_vec", ip], seed=7 if name == "ours" else 8)
+        assert "Exception" not in r.stderr, (name, r.stderr[-500:])
+        assert open(rd + "dense.txt").read().split(",")[0].strip() == str(len(dense)), open(rd + "dense.txt").read()
+        dense_h = [ln for ln in r.stdout.splitlines() if ln.startswith("Elements in dense H:")]
+        assert dense_h and int(dense_h[0].split(":")[1]) > 0
+        res[name + "_dense_h"] = int(dense_h[0].split(":")[1])
+        num, den = read_col(rd + "projnum.txt"), read_col(rd + "projden.txt")
+        assert len(num) == n_it, (name, r.stderr[-600:], r.stdout[-600:])
+        res[name] = blocked_ratio(num, den, burn=1000)
+        # the dense determinants are the first stored ones and survive every compression
+        nb = (2 * sm.n_orb + 7) // 8
+        raw = np.fromfile(rd + "dets0.dat", dtype=np.uint8).reshape(-1, nb)
+        first = [int.from_bytes(bytes(row), "little") for row in raw[:len(dense)]]
+        assert sorted(first) == sorted(dense), name
+    e, s = res["ours"]
+    print("semi-stochastic: exact", e_corr, "ours", res["ours"], "ref", res.get("ref"))
+    assert abs(e - e_corr) < 5 * s + 2e-3 * abs(e_corr) + 2e-4, (e, s, e_corr)
+    if "ref" in res:
+        er, sr = res["ref"]
+        assert abs(e - er) < 5 * (s + sr) + 2e-4, (e, s, er, sr)
+        assert res["ours_dense_h"] == res["ref_dense_h"]
 
 
 # ---- config[0]: Hubbard model, frisys_hh (examples/run_hubbard.sh sizes; parameter file with the keys HEAD's parser wants) ----
