@@ -252,6 +252,23 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
         t, n = ctx.kernel_ms(nm)
         if n:
             kern[nm] = round(t / n, 4)
+    # roofline of the slowest kernel on rank 0 (an HB-PP stage: 40 B per matrix sample; one GPU's share)
+    roofline = None
+    if kern:
+        top = max(kern, key=kern.get)
+        try:
+            peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                     "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+            src = "MEASURED_PEAKS.json (burst copy)"
+        except OSError:
+            peak, src = 6650.0, "fallback B200_PROFILING.md"
+        bytes_alg = {"hbpp_finalize": 56, "merge_insert": 28, "merge_accum": 28}.get(top, 40) * cfg["mat_nonz"]
+        if top in ("death_axpy", "find_preserve", "sys_comp", "compact"):
+            bytes_alg = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8}[top] * cfg["vec_nonz"]
+        ach = bytes_alg / (kern[top] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 5), "traffic": None, "peak_source": src, "ms_per_launch": kern[top],
+                    "algorithmic_bytes_per_launch": bytes_alg, "what": "rank 0, one GPU's share of the samples"}
     states = eng.vec.states()
     rts = np.zeros(16)
     check(lib.fries_hbpp_round_stamps(eng.vec.hb, 3, ptr(rts)))
@@ -273,6 +290,7 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
                     "d2h_bytes_per_step": 128,
                     "what": "fries_frisys_mol_spawn + all_to_all + fries_frisys_mol_finish per step; the vector is "
                             "resident (uniforms in, iteration statistics out)"},
+            "roofline": roofline,
             "comm_error_epoch": err,
             "stage3_round_stamps_us": [round(x / 1e3, 1) for x in rts],
             "kernels_ms_rank0": kern,
