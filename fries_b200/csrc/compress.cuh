@@ -656,7 +656,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     // the residual norm of the last exact recomputation stays valid while no round preserves anything
     bool fresh = false;
     double fresh_cs = 0, fresh_loc = 0, fresh_G = 0, fresh_lb0 = 0;
-    unsigned long long n_cand = 0;
+    unsigned long long n_cand = 0, fast_kc = 0;
     bool fast_done = false;
     if (try_fast) {
         // Newton rounds on the candidate list only (every CTA, redundantly), then ONE pass that applies the cut
@@ -701,24 +701,14 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
                 t += wr;
             }
             block_sum_pair(t, kc, sh_d, sh_c);
-            fresh_cs = t;
+            fresh_cs = t;      // this CTA's share of the resampling line
+            fast_kc = kc;      // pieces this CTA preserved
             FR_STAMP(b.st, 7);  // cut applied (CTA 0)
-            grid_reduce_blk(grid, red, t, kc);
+            // the grid totals (residual norm, preserved pieces) come out of the line scan below: no reduction here
             kept_total = c_hi + br.kept_cand;
-            if (!multi && kc != kept_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&b.st->anomalies, 1ull << 32);
             nrem = br.nrem;
             R = br.R;
             rounds = br.rounds;
-            fresh = true;
-            fresh_loc = t;
-            fresh_G = t;
-            fresh_lb0 = 0;
-            if (multi) {  // this rank's place on the global resampling line (seed_sys :107-127)
-                double tot;
-                comm_allgather(cm, cur, t, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
-                comm_sum(cm, sh_x0, tot, fresh_lb0);
-                fresh_G = tot;
-            }
             fast_done = true;
             glob_sampled = 0;  // skip the plain rounds
             if (blockIdx.x == 0 && threadIdx.x == 0) b.st->fast = 1;
@@ -809,8 +799,12 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
     double loc_final = 0, cs = 0, G = 0, lbound0 = 0;
     if (b.pred && blockIdx.x == 0 && threadIdx.x == 0)
         keep_pred_update(b.pred, try_fast ? t_pred : 0.0, h_pred, nrem > 0 ? R / nrem : 0.0, n_cand);
+    bool defer = false;  // bracketed solve: residual norm and line position come out of the line scan
     if (R / nrem < 1e-8) {
         nrem = 0;
+    } else if (fast_done) {
+        cs = fresh_cs;
+        defer = true;
     } else if (fresh) {
         loc_final = fresh_loc;
         cs = fresh_cs;
@@ -827,6 +821,22 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         if (multi) {
             comm_allgather(cm, cur, loc_final, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
             comm_sum(cm, sh_x0, G, lbound0);
+        }
+    }
+    FR_STAMP(b.st, 2);  // preserved set decided
+    // CTA boundaries on the resampling line from the chunk sums of the residual weights
+    double blk_lb, tot_lb;
+    unsigned long long e0, e1;
+    grid_excl_scan(grid, red, cs, defer ? fast_kc : 0ull, blk_lb, e0, tot_lb, e1, sh_sd, sh_sc);
+    if (defer) {
+        loc_final = tot_lb;
+        G = tot_lb;
+        lbound0 = 0;
+        if (multi) {  // this rank's place on the global resampling line (seed_sys :107-127)
+            comm_allgather(cm, cur, loc_final, 0.0, 0ull, sh_x0, sh_x1, sh_xc);
+            comm_sum(cm, sh_x0, G, lbound0);
+        } else if (e1 != kept_total && blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicAdd(&b.st->anomalies, 1ull << 32);  // the cut pass and the candidate rounds disagree: cannot happen
         }
     }
     SysGrid sg;
@@ -848,12 +858,6 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         sg.inv = 0;
         sg.n = 0;
     }
-
-    FR_STAMP(b.st, 2);  // preserved set decided
-    // CTA boundaries on the resampling line from the chunk sums of the residual weights
-    double blk_lb, tot_lb;
-    unsigned long long e0, e1;
-    grid_excl_scan(grid, red, cs, 0ull, blk_lb, e0, tot_lb, e1, sh_sd, sh_sc);
 
     FR_STAMP(b.st, 3);
     // pass 2: per-input lower bound + number of outputs

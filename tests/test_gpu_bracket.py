@@ -139,8 +139,9 @@ def test_apply_hbpp_sys_bracket(mols, new_hb, n_det, n_samp, perturb):
 def test_iterate_bracket_on_off(ctx):
     """frisys_mol iterations with and without the bracketed solve, same uniforms.  New determinants are appended in
     the order the merge kernel's atomics resolve, so two runs of the SAME configuration already differ by a few
-    resampled elements per iteration; the comparison is therefore statistical (one-norm to 2e-4), and the point of
-    the test is that the bracketed solve engages and leaves budgets and sizes intact."""
+    resampled elements per iteration (a random walk of about one sample unit = 5e-5 of the one-norm per iteration); the
+    comparison is therefore statistical (one-norm to 1e-3 after 8 iterations), and the point of the test is that the
+    bracketed solve engages and leaves budgets and sizes intact."""
     import fries_b200
     from fries_b200._capi import FrisysParams, check, lib
     from fries_b200.synth import SynthMol
@@ -180,7 +181,7 @@ def test_iterate_bracket_on_off(ctx):
     for it in range(8):
         a, b = out[0][it], out[1][it]
         assert not a[4].any()
-        assert abs(a[0] - b[0]) <= 3 and b[1] == pytest.approx(a[1], rel=2e-4)
+        assert abs(a[0] - b[0]) <= 3 and b[1] == pytest.approx(a[1], rel=1e-3)
         assert b[2] == pytest.approx(a[2], rel=1e-2, abs=1e-6) and b[3] == pytest.approx(a[3], rel=2e-3)
     fast = np.array([r[4] for r in out[1]])
     print("fast flags per iteration (stages 0-4, finalize, find_preserve):\n", fast)
