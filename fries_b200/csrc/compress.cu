@@ -254,7 +254,7 @@ find_preserve_kernel(const double *__restrict__ vals, size_t n, const unsigned l
         st->n_kept = kept_total;
         st->n_in = n;
     }
-    grid.sync();
+    if (cm.n_ranks > 1) grid.sync();  // the epoch is stored once every CTA is past its last exchange; a single rank needs no barrier at the end
     comm_end(cm, cur);
 }
 
@@ -367,7 +367,7 @@ sys_comp_kernel(double *__restrict__ vals, size_t n, const unsigned long long *_
         out_st->new_norm = new_norm;
         out_st->n_out = n_samples;
     }
-    grid.sync();
+    if (cm.n_ranks > 1) grid.sync();  // the epoch is stored once every CTA is past its last exchange; a single rank needs no barrier at the end
     comm_end(cm, cur);
 }
 

@@ -24,21 +24,31 @@ struct HbProvider {
         return n < io.in_cap ? (size_t)n : (size_t)io.in_cap;
     }
 
-    // singles bookkeeping (count_symm_virt + count_sing_allowed / count_sing_virt, near_uniform.cpp:14-28,316-347)
+    // singles bookkeeping (count_symm_virt + count_sing_allowed / count_sing_virt, near_uniform.cpp:14-28,316-347) on bit
+    // masks: no occupied list and no per-irrep counter array (local memory) in the hot loop
     __device__ unsigned sing_allowed(uint64_t key) const {
-        uint8_t occ[FRIES_MAX_ELEC + 1], cnt[FR_N_IRREPS][2];
-        mol_occ_list(key, occ);
-        mol_count_symm_virt(m, occ, cnt);
-        return mol_count_sing_allowed(m, occ, cnt);
+        OccMask o = mol_occ_mask(m, key);
+        return mol_count_sing_allowed_bits(m, o.a, o.b);
     }
+    // choice in: index among the allowed electrons (alpha block first); out: electron index; returns its virtual count
     __device__ unsigned sing_virt(uint64_t key, unsigned &choice) const {
-        uint8_t occ[FRIES_MAX_ELEC + 1], cnt[FR_N_IRREPS][2];
-        mol_occ_list(key, occ);
-        mol_count_symm_virt(m, occ, cnt);
-        uint8_t ch = (uint8_t)choice;
-        unsigned n = mol_count_sing_virt(m, occ, cnt, &ch);
-        choice = ch;
-        return n;
+        const unsigned M = m.d.n_orb, h = m.d.n_elec / 2;
+        OccMask o = mol_occ_mask(m, key);
+        uint32_t al_a, al_b;
+        mol_sing_allowed_masks(m, o.a, o.b, al_a, al_b);
+        const unsigned na = (unsigned)__popc(al_a), nb = (unsigned)__popc(al_b);
+        const uint32_t all = (uint32_t)((1ull << M) - 1);
+        if (choice < na) {
+            unsigned orb = fr_nth_bit32(al_a, choice);
+            choice = (unsigned)__popc(o.a & ((1u << orb) - 1u));
+            return (unsigned)__popc(~o.a & all & m.irr_mask[m.symm[orb]]);
+        }
+        if (choice < na + nb) {
+            unsigned orb = fr_nth_bit32(al_b, choice - na);
+            choice = h + (unsigned)__popc(o.b & ((1u << orb) - 1u));
+            return (unsigned)__popc(~o.b & all & m.irr_mask[m.symm[orb]]);
+        }
+        return 0;  // count_sing_virt leaves occ_choice untouched and returns 0 when the index is out of range
     }
 
     // wmax: an upper bound of the sub-weights visit() will stream for this input (exactly the largest one where the

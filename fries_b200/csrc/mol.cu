@@ -96,6 +96,7 @@ extern "C" int fries_mol_create(fries_ctx *c, unsigned n_orb, unsigned n_elec_to
     d.off_exch_norms = off; off += M;
     d.off_symm = off; off += (M + 7) / 8;
     d.off_lookup = off; off += (FR_N_IRREPS * (M + 1) + 7) / 8;
+    d.off_irr = off; off += (FR_N_IRREPS * 4 + 7) / 8;
     d.blob_doubles = off;
     // symmetry tables (integer bookkeeping; gen_symm_lookup molecule.cpp:1050-1065, SymmInfo molecule.hpp:265-280)
     std::vector<double> h_blob(off, 0.0);
@@ -108,6 +109,8 @@ extern "C" int fries_mol_create(fries_ctx *c, unsigned n_orb, unsigned n_elec_to
         lookup[s * (M + 1) + 1 + cnt] = (uint8_t)i;
         lookup[s * (M + 1)] = cnt + 1;
     }
+    uint32_t *irr_mask = (uint32_t *)(h_blob.data() + d.off_irr);
+    for (unsigned i = 0; i < M; i++) irr_mask[h_symm[i] % FR_N_IRREPS] |= 1u << i;
     d.max_n_symm = 0;
     for (unsigned s = 0; s < FR_N_IRREPS; s++)
         if (lookup[s * (M + 1)] > d.max_n_symm) d.max_n_symm = lookup[s * (M + 1)];

@@ -25,6 +25,7 @@ struct MolDims {
     uint32_t max_n_symm;
     uint32_t blob_doubles;  // size of the small-table blob in doubles (incl. the byte tables)
     uint32_t off_d_diff, off_d_same, off_s_tens, off_exch_sqrt, off_diag_sqrt, off_exch_norms, off_symm, off_lookup;
+    uint32_t off_irr;   // [8] u32: spatial orbitals of each irrep as a bit mask
     double s_norm;
 };
 
@@ -35,6 +36,7 @@ struct MolView {
     const double *d_diff, *d_same, *s_tens, *exch_sqrt, *diag_sqrt, *exch_norms;  // hb_info heat_bathPP.hpp:25-34
     const uint8_t *symm;    // [M] irreps
     const uint8_t *lookup;  // [8][M + 1] gen_symm_lookup molecule.cpp:1050-1065
+    const uint32_t *irr_mask;  // [8] spatial orbitals of each irrep as a bit mask
 };
 
 __host__ __device__ __forceinline__ void mol_bind_blob(MolView &m, const double *blob) {
@@ -46,6 +48,7 @@ __host__ __device__ __forceinline__ void mol_bind_blob(MolView &m, const double 
     m.exch_norms = blob + m.d.off_exch_norms;
     m.symm = (const uint8_t *)(blob + m.d.off_symm);
     m.lookup = (const uint8_t *)(blob + m.d.off_lookup);
+    m.irr_mask = (const uint32_t *)(blob + m.d.off_irr);
 }
 
 __host__ __device__ __forceinline__ uint8_t mol_lookup(const MolView &m, unsigned irrep, unsigned col) {
@@ -188,6 +191,30 @@ __host__ __device__ inline unsigned mol_count_sing_virt(const MolView &m, const 
     }
     return 0;
 }
+// The same three on bit masks (no occupied list, no per-irrep counter array in local memory): the virtual orbitals of
+// irrep r and spin s are popc(virt_s & irr_mask[r]); an electron is "allowed" when its irrep has a virtual orbital of
+// its spin.  mol_sing_allowed_masks returns the allowed occupied orbitals of both spins.
+__host__ __device__ __forceinline__ void mol_sing_allowed_masks(const MolView &m, uint32_t occ_a, uint32_t occ_b,
+                                                                uint32_t &al_a, uint32_t &al_b) {
+    const uint32_t all = (uint32_t)((1ull << m.d.n_orb) - 1);
+    const uint32_t va = ~occ_a & all, vb = ~occ_b & all;
+    uint32_t oa = 0, ob = 0;
+#pragma unroll
+    for (unsigned r = 0; r < FR_N_IRREPS; r++) {
+        const uint32_t im = m.irr_mask[r];
+        if (va & im) oa |= im;
+        if (vb & im) ob |= im;
+    }
+    al_a = occ_a & oa;
+    al_b = occ_b & ob;
+}
+// count_sing_allowed
+__host__ __device__ __forceinline__ unsigned mol_count_sing_allowed_bits(const MolView &m, uint32_t occ_a, uint32_t occ_b) {
+    uint32_t al_a, al_b;
+    mol_sing_allowed_masks(m, occ_a, occ_b, al_a, al_b);
+    return (unsigned)(fr_popc((uint64_t)al_a) + fr_popc((uint64_t)al_b));
+}
+
 // virt_from_idx near_uniform.cpp:419-433
 __host__ __device__ inline unsigned mol_virt_from_idx(const MolView &m, uint64_t det, unsigned irrep, unsigned spin_shift,
                                                       unsigned index) {
