@@ -275,13 +275,12 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
         const uint32_t widx = pw[i], sub = ps[i];
         const uint32_t d = pdet[widx], pp = ppath[widx];
         const uint64_t key = keys[d];
-        uint8_t occ[FRIES_MAX_ELEC + 1];
-        mol_occ_list(key, occ);
+        const OccMask om = mol_occ_mask(m, key);  // occupied orbitals by spin: no occupied list in the common paths
         unsigned p0 = pp & 0xff, p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
         uint8_t orbs[4] = {0, 0, 0, 0};
         bool is_doub = p0 == 0;
         if (is_doub) {
-            unsigned o1 = occ[p1], o2 = occ[p2], u1 = p3;
+            unsigned o1 = mol_elec_orb(m, om, p1), o2 = mol_elec_orb(m, om, p2), u1 = p3;
             unsigned u2_symm = m.symm[o1 % M] ^ m.symm[o2 % M] ^ m.symm[u1 % M];
             unsigned u2 = mol_lookup(m, u2_symm, sub + 1) + M * (o2 / M);
             if (!fr_read_bit(key, u2) && u1 != u2) {
@@ -299,7 +298,14 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
                 orbs[1] = (uint8_t)o2;
                 orbs[2] = (uint8_t)u1;
                 orbs[3] = (uint8_t)u2;
-                double tot = new_hb ? hb_unnorm_wt(m, orbs) : hb_norm_wt(m, orbs, occ, key);
+                double tot;
+                if (new_hb) {
+                    tot = hb_unnorm_wt(m, orbs);
+                } else {
+                    uint8_t occ[FRIES_MAX_ELEC + 1];
+                    mol_occ_list(key, occ);
+                    tot = hb_norm_wt(m, orbs, occ, key);
+                }
                 el = mol_doub_el(m, orbs) * pv[i] / tot / p_doub;
                 if (fabs(el) > 1e-9)
                     el *= fr_doub_parity(key, o1, o2, u1, u2);
@@ -307,15 +313,13 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
                     el = 0;
             }
         } else {
-            unsigned o1 = occ[p1];
+            unsigned o1 = mol_elec_orb(m, om, p1);
             unsigned u1 = mol_virt_from_idx(m, key, m.symm[o1 % M], M * (o1 / M), p2);
             if (u1 != 255) {
                 orbs[0] = (uint8_t)o1;
                 orbs[1] = (uint8_t)u1;
-                uint8_t cnt[FR_N_IRREPS][2];
-                mol_count_symm_virt(m, occ, cnt);
-                unsigned n_occ = mol_count_sing_allowed(m, occ, cnt);
-                el = mol_sing_el(m, o1, u1, occ);
+                unsigned n_occ = mol_count_sing_allowed_bits(m, om.a, om.b);
+                el = mol_sing_el_bits(m, o1, u1, om.a, om.b);
                 el *= pv[i] / (1 - p_doub) * n_occ * p3;
                 if (fabs(el) > 1e-9)
                     el *= fr_sing_parity(key, o1, u1);

@@ -147,6 +147,27 @@ __host__ __device__ inline double mol_sing_el(const MolView &m, unsigned o, unsi
     }
     return el;
 }
+// the same sum, same order, with the occupied orbitals taken from the two spin masks (ascending) instead of a list
+__host__ __device__ inline double mol_sing_el_bits(const MolView &m, unsigned o, unsigned v, uint32_t occ_a, uint32_t occ_b) {
+    const unsigned hf = m.d.n_frz / 2, M = m.d.n_orb;
+    unsigned occ_spa = (o % M) + hf, unocc_spa = (v % M) + hf, occ_spin = o / M;
+    double el = mol_hcore(m, occ_spa, unocc_spa);
+    for (unsigned j = 0; j < hf; j++) {
+        el += eri_phys(m, occ_spa, j, unocc_spa, j) * 2;
+        el -= eri_phys(m, occ_spa, j, j, unocc_spa);
+    }
+    for (uint32_t am = occ_a; am; am &= am - 1) {
+        unsigned q = (unsigned)fr_ctz(am) + hf;
+        el += eri_phys(m, occ_spa, q, unocc_spa, q);
+        if (occ_spin == 0) el -= eri_phys(m, occ_spa, q, q, unocc_spa);
+    }
+    for (uint32_t bm = occ_b; bm; bm &= bm - 1) {
+        unsigned q = (unsigned)fr_ctz(bm) + hf;
+        el += eri_phys(m, occ_spa, q, unocc_spa, q);
+        if (occ_spin == 1) el -= eri_phys(m, occ_spa, q, q, unocc_spa);
+    }
+    return el;
+}
 __host__ __device__ inline double mol_doub_el(const MolView &m, const uint8_t *orbs) {
     const unsigned hf = m.d.n_frz / 2, M = m.d.n_orb;
     bool same_sp = (orbs[0] / M) == (orbs[1] / M);
