@@ -312,6 +312,8 @@ def run_ours(args, cfg):
                 "rounds": {"hbpp_stages": [int(x) for x in states[:5, 4]], "find_preserve": int(states[6, 4])},
                 "stage_items_in": [int(x) for x in states[:5, 7]], "stage_items_out": [int(x) for x in states[:5, 6]],
                 "stage_bracket": {"fast": [int(x) for x in states[:5, 10]], "candidates": [int(x) for x in states[:5, 9]]},
+                "find_preserve_bracket": {"fast": int(states[6, 10]), "candidates": int(states[6, 9]),
+                                          "rounds": int(states[6, 4])},
                 "stage_phase_us": {"what": "in-kernel %globaltimer of CTA 0: prep, preserved set, line scan, count, emit",
                                    "us": [[round((states[s, 13 + k] - states[s, 12 + k]) / 1e3, 1) for k in range(5)]
                                           for s in range(5)],
