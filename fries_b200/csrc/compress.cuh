@@ -665,7 +665,7 @@ __device__ void comp_sub_engine(P &prov, const CompSubBufs &b, unsigned n_samp_i
         n_cand = br.n_cand;
         FR_STAMP(b.st, 6);  // candidate rounds done
         if (br.valid) {
-            const double x_cut = br.x_cut, fac = (double)br.nrem;
+            const double x_cut = br.x_cut;
             double t = 0;
             unsigned long long kc = 0;
             for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {

@@ -258,7 +258,7 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
         if (threadIdx.x < 64) s_pscr[threadIdx.x] = sp.proc_scr[threadIdx.x];
         __syncthreads();
     }
-    const unsigned ne = m.d.n_elec, M = m.d.n_orb;
+    const unsigned M = m.d.n_orb;
     unsigned long long n = *n_ptr;
     if (n > in_cap) n = in_cap;
     unsigned long long ok = 0;

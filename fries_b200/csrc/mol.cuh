@@ -220,7 +220,6 @@ __host__ __device__ __forceinline__ void mol_sing_allowed_masks(const MolView &m
     const uint32_t all = (uint32_t)((1ull << m.d.n_orb) - 1);
     const uint32_t va = ~occ_a & all, vb = ~occ_b & all;
     uint32_t oa = 0, ob = 0;
-#pragma unroll
     for (unsigned r = 0; r < FR_N_IRREPS; r++) {
         const uint32_t im = m.irr_mask[r];
         if (va & im) oa |= im;
