@@ -400,6 +400,10 @@ int fries_hbpp_alloc(fries_ctx *c, size_t cap, fries_hbpp **out, bool stages) {
     A(part_d, FR_RED_PART_LEN); A(part_c, FR_RED_PART_LEN); A(st, 8); A(n_scalar, 4); A(scal, 64);
     A(cand_x, FR_CAND_GCAP); A(cand_m, FR_CAND_GCAP); A(pred, 8);
 #undef A
+    if (rc == FRIES_OK && cudaMemset(hb->scal.p, 0, 64 * sizeof(double)) != cudaSuccess) {
+        fries_set_error("fries_hbpp_alloc: cudaMemset failed");
+        rc = FRIES_ERR_CUDA;
+    }
     if (rc == FRIES_OK && cudaMemset(hb->pred.p, 0, 8 * sizeof(KeepPred)) != cudaSuccess) {
         fries_set_error("fries_hbpp_alloc: cudaMemset failed");
         rc = FRIES_ERR_CUDA;

@@ -53,6 +53,7 @@ struct fries_hbpp {
     unsigned long long *send_counts_ext = nullptr;     // caller-owned [n_ranks + 1]: per-destination counts + overflow
     size_t seg_cap = 0;
     // direct route: the windows live in `comm` (fries_comm_route_create); counters are owned here
+    bool dense_norm_set = false;  // scal[DENSE_NORM] holds a nonzero contribution of a dense subspace
     bool p2p = false;
     DevBuf<unsigned long long> p2p_send_counts, p2p_recv_counts;
 };

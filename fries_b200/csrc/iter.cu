@@ -577,8 +577,14 @@ static int compress_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, uns
                                          hb->cand_m.p));
     state_to_r4_kernel<<<1, 1, 0, c->stream>>>(hb->st.p + 6, hb->scal.p + IterScalars::R4);
     c->launch_count++;
-    dense_norm_kernel<<<1, 256, 0, c->stream>>>(v.vals + (size_t)row * v.cap, nd, hb->scal.p + IterScalars::DENSE_NORM);
-    c->launch_count++;
+    if (nd) {  // the slot is zero otherwise (fries_hbpp_alloc)
+        dense_norm_kernel<<<1, 256, 0, c->stream>>>(v.vals + (size_t)row * v.cap, nd, hb->scal.p + IterScalars::DENSE_NORM);
+        c->launch_count++;
+        hb->dense_norm_set = true;
+    } else if (hb->dense_norm_set) {
+        CUDA_TRY(cudaMemsetAsync(hb->scal.p + IterScalars::DENSE_NORM, 0, sizeof(double), c->stream));
+        hb->dense_norm_set = false;
+    }
     (void)uniform;
     return FRIES_OK;
 }
