@@ -208,6 +208,240 @@ void fo_sys_comp(double *values, size_t count, double *loc_norms, int n_procs, i
 }
 
 /* adjust_shift compress_utils.cpp:684-693 */
+/* ---- pivotal family ------------------------------------------------------------------- */
+
+/* std::mt19937 (the 32-bit Mersenne twister of the C++ standard; the reference draws uniforms as
+ * mt() / (1. + UINT32_MAX), compress_utils.cpp:24,436,468): the first n outputs for a seed. */
+void fo_mt19937_fill(uint32_t seed, size_t n, uint32_t *out) {
+    uint32_t st[624];
+    st[0] = seed;
+    for (int i = 1; i < 624; i++) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+    int pos = 624;
+    for (size_t k = 0; k < n; k++) {
+        if (pos == 624) {
+            for (int i = 0; i < 624; i++) {
+                uint32_t y = (st[i] & 0x80000000u) | (st[(i + 1) % 624] & 0x7fffffffu);
+                st[i] = st[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            pos = 0;
+        }
+        uint32_t y = st[pos++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        out[k] = y;
+    }
+}
+
+static double piv_uniform(const uint32_t *draws, size_t *used) { return draws[(*used)++] / 4294967296.0; }
+
+/* piv_samp_serial, compress_utils.cpp:389-520.  Ordered pivotal sampling of n_samp of the elements with keep == 0:
+ * the cumulative line of their magnitudes is cut into n_samp units of seg_norm / n_samp; in every unit one
+ * candidate is drawn among the carried element and the elements that end inside the unit, and a second draw
+ * decides whether the candidate or the element straddling the unit's upper border is the sample (the other one is
+ * carried into the next unit).  keep out: 1 = zeroed element.  Two draws per unit, taken from draws[*used...]. */
+void fo_piv_samp_serial(double *v, size_t n, double seg_norm, uint32_t n_samp, uint8_t *keep, const uint32_t *draws,
+                        size_t *used) {
+    if (n_samp == 0) {
+        for (size_t i = 0; i < n; i++) {
+            if (keep[i]) keep[i] = 0;
+            else v[i] = 0;
+            if (v[i] == 0) keep[i] = 1;
+        }
+        return;
+    }
+    const double unit = seg_norm / n_samp;
+    size_t cap = 2 * n / n_samp + 4;
+    double *lst = (double *)malloc(sizeof(double) * cap); /* lst[0] = the carried element's share of this unit */
+    lst[0] = 0;
+    size_t pos = 0, carried = 0;
+    uint32_t done = 0;
+    while (pos < n && done < n_samp) {
+        size_t off = 0, cnt = 1;
+        double acc = lst[0];
+        while (acc < unit && pos + off < n) {
+            if (!keep[pos + off]) {
+                if (cnt == cap) {
+                    cap *= 2;
+                    lst = (double *)realloc(lst, sizeof(double) * cap);
+                }
+                lst[cnt] = fabs(v[pos + off]);
+                acc += lst[cnt];
+                cnt++;
+            }
+            off++;
+        }
+        const int at_end = pos + off == n;
+        size_t border = off > 0 ? off - 1 : 0; /* offset of the straddling element */
+        if (at_end) border++;                  /* no straddling element: everything is interior */
+        const double over = acc - unit;        /* b_n */
+        if (!at_end) {
+            cnt--;
+            acc -= lst[cnt];
+        }
+        const double under = unit - acc;       /* a_n */
+        double r = piv_uniform(draws, used) * acc;
+        double run = 0;
+        size_t pick = 0;
+        while (run < r && pick < cnt) {
+            run += lst[pick];
+            pick++;
+        }
+        if (r > 0) pick--;
+        if (pick != 0 && pos != 0) { /* the carried element lost */
+            v[carried] = 0;
+            keep[carried] = 1;
+        }
+        double p_pass = at_end ? 0.0 : under / (unit - over);
+        r = piv_uniform(draws, used);
+        const int take_border = r < p_pass;
+        if (!take_border && pick == 0) {
+            double t = v[carried];
+            v[carried] = unit * ((t > 0) - (t < 0));
+        }
+        size_t k = 1, next_carried = take_border ? carried : pos + border; /* pick == 0: carried once more */
+        for (size_t o = 0; o < border; o++) {
+            size_t i = pos + o;
+            if (keep[i]) {
+                keep[i] = 0;
+                continue;
+            }
+            if (k == pick) {
+                if (take_border) next_carried = i;
+                else {
+                    double t = v[i];
+                    v[i] = unit * ((t > 0) - (t < 0));
+                }
+            } else {
+                v[i] = 0;
+                keep[i] = 1;
+            }
+            k++;
+        }
+        if (take_border) {
+            double t = v[pos + border];
+            v[pos + border] = unit * ((t > 0) - (t < 0));
+        }
+        carried = next_carried;
+        pos += border + 1;
+        lst[0] = over;
+        done++;
+    }
+    for (; pos < n; pos++) {
+        if (!keep[pos]) {
+            v[pos] = 0;
+            keep[pos] = 1;
+        } else {
+            keep[pos] = 0;
+        }
+    }
+    if (carried < n) {
+        v[carried] = 0;
+        keep[carried] = 1;
+    }
+    free(lst);
+}
+
+/* piv_budget, compress_utils.cpp:556-608: integer budgets of the ranks with expectation n_samp * norm_p / total;
+ * the fractional parts are settled by pivotal sampling on rank 0 and scattered (here: all budgets are returned). */
+void fo_piv_budget(const double *loc_norms, int n_procs, uint32_t n_samp, const uint32_t *draws, size_t *used,
+                   uint32_t *budgets) {
+    double glob = 0;
+    for (int p = 0; p < n_procs; p++) glob += loc_norms[p];
+    double *wt = (double *)malloc(sizeof(double) * (size_t)n_procs);
+    uint8_t *kp = (uint8_t *)calloc((size_t)n_procs, 1);
+    uint32_t tot = 0, n_frac = 0;
+    for (int p = 0; p < n_procs; p++) {
+        budgets[p] = (uint32_t)(loc_norms[p] / glob * n_samp);
+        tot += budgets[p];
+        wt[p] = loc_norms[p] - budgets[p] * glob / n_samp;
+        if (wt[p] < 1e-12) wt[p] = 0;
+        if (wt[p] > 0) n_frac++;
+    }
+    if (n_frac == n_samp - tot) {
+        for (int p = 0; p < n_procs; p++)
+            if (wt[p] > 0) budgets[p]++;
+        tot = n_samp;
+    }
+    if (tot < n_samp) {
+        fo_piv_samp_serial(wt, (size_t)n_procs, glob * (n_samp - tot) / n_samp, n_samp - tot, kp, draws, used);
+        for (int p = 0; p < n_procs; p++)
+            if (wt[p] > 0) budgets[p]++;
+    }
+    free(wt);
+    free(kp);
+}
+
+/* adjust_probs, compress_utils.cpp:610-681: after a rank's expected sample count exp_loc was rounded to the integer
+ * *n_loc, rescale its leading elements so that the inclusion probabilities add up to *n_loc again.  Returns the
+ * norm to hand to piv_samp_serial. */
+double fo_adjust_probs(double *v, size_t n, uint32_t *n_loc, double exp_loc, uint32_t n_tot, double tot_norm,
+                       uint8_t *keep) {
+    const double top = (double)ceill(exp_loc);
+    const double frac = exp_loc - (unsigned int)exp_loc;
+    const double unit = tot_norm / n_tot;
+    const double loc_norm = exp_loc * unit;
+    int too_big = 0;
+    for (size_t i = 0; i < n && !too_big; i++)
+        if (!keep[i] && fabs(v[i]) >= loc_norm / top) too_big = 1;
+    if (!too_big) return loc_norm;
+    double counter = exp_loc;
+    const int up = *n_loc > exp_loc;
+    for (size_t i = 0; i < n; i++) {
+        if (keep[i]) continue;
+        int8_t sgn = 2 * (v[i] > 0) - 1;
+        double pi = fabs(v[i]) / unit;
+        if (up) {
+            if (pi < frac) {
+                counter += pi / frac - pi;
+                v[i] /= frac;
+            } else {
+                counter -= pi;
+                v[i] = sgn * unit;
+                keep[i] = 1;
+                (*n_loc)--;
+            }
+            if (counter >= *n_loc) {
+                v[i] = fma(sgn * unit, *n_loc - counter, v[i]); /* contracted by the reference's -O3 -march build */
+                break;
+            }
+        } else {
+            if (pi > frac) {
+                double q = (pi - frac) / (1 - frac);
+                counter += q - pi;
+                v[i] = sgn * q * unit;
+            } else {
+                counter -= pi;
+                v[i] = 0;
+            }
+            if (counter <= *n_loc) {
+                v[i] = fma(sgn * unit, *n_loc - counter, v[i]); /* contracted by the reference's -O3 -march build */
+                break;
+            }
+        }
+    }
+    return *n_loc * loc_norm / exp_loc;
+}
+
+/* piv_comp_parallel, compress_utils.cpp:354-386, for one rank of n_procs (loc_norms of the OTHER ranks are inputs:
+ * the reference all-gathers them; rank's own entry is overwritten by find_preserve's residual norm when n_procs == 1).
+ * Single-rank use: n_procs = 1, loc_norms = NULL. */
+void fo_piv_comp(double *v, size_t n, uint32_t compress_size, uint8_t *keep, const uint32_t *draws, size_t *used) {
+    unsigned n_samp = compress_size;
+    double glob;
+    double loc = fo_find_preserve(v, n, &n_samp, &glob, keep);
+    glob = 0;
+    glob += loc;
+    uint32_t loc_samp = 0;
+    double new_norm = 0;
+    if (n_samp != 0) {
+        fo_piv_budget(&loc, 1, n_samp, draws, used, &loc_samp);
+        new_norm = fo_adjust_probs(v, n, &loc_samp, n_samp * loc / glob, n_samp, glob, keep);
+    }
+    fo_piv_samp_serial(v, n, new_norm, loc_samp, keep, draws, used);
+}
+
 void fo_adjust_shift(double *shift, double one_norm, double *last_norm, double target_norm, double damp) {
     if (*last_norm) {
         *shift -= damp * log(one_norm / *last_norm);

@@ -56,6 +56,16 @@ size_t fo_sys_sub(const double *values, const uint32_t *n_div, const double *sub
 size_t fo_comp_sub(const double *values, size_t count, const uint32_t *n_div, const double *sub_weights,
                    size_t n_sub, const uint16_t *sub_sizes, unsigned n_samp, double rn, double *new_vals,
                    uint64_t *new_idx, unsigned *n_samp_left, double *loc_norm); /* compress_utils.cpp:797-820 */
+/* ---- pivotal family: piv_samp_serial / piv_budget / adjust_probs / piv_comp_parallel ---- */
+void fo_mt19937_fill(uint32_t seed, size_t n, uint32_t *out);     /* std::mt19937(seed): first n outputs */
+void fo_piv_samp_serial(double *v, size_t n, double seg_norm, uint32_t n_samp, uint8_t *keep, const uint32_t *draws,
+                        size_t *used);                             /* compress_utils.cpp:389-520 */
+void fo_piv_budget(const double *loc_norms, int n_procs, uint32_t n_samp, const uint32_t *draws, size_t *used,
+                   uint32_t *budgets);                             /* compress_utils.cpp:552-608 */
+double fo_adjust_probs(double *v, size_t n, uint32_t *n_loc, double exp_loc, uint32_t n_tot, double tot_norm,
+                       uint8_t *keep);                             /* compress_utils.cpp:610-681 */
+void fo_piv_comp(double *v, size_t n, uint32_t compress_size, uint8_t *keep, const uint32_t *draws,
+                 size_t *used);                                    /* compress_utils.cpp:354-386, single rank */
 void fo_adjust_shift(double *shift, double one_norm, double *last_norm, double target_norm,
                      double damp);                                 /* compress_utils.cpp:684-693 */
 

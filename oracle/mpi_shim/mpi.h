@@ -38,7 +38,12 @@ typedef int MPI_Datatype; /* value = size of the type in bytes */
 static inline int MPI_Init(int *argc, char ***argv) { (void)argc; (void)argv; return MPI_SUCCESS; }
 static inline int MPI_Finalize(void) { return MPI_SUCCESS; }
 static inline int MPI_Comm_rank(MPI_Comm c, int *rank) { (void)c; *rank = 0; return MPI_SUCCESS; }
-static inline int MPI_Comm_size(MPI_Comm c, int *size) { (void)c; *size = 1; return MPI_SUCCESS; }
+/* The communicator has one rank.  For ONE purpose a test may pretend otherwise: piv_budget (compress_utils.cpp:564-608)
+ * does all of its arithmetic on rank 0 and only scatters the result, so with fries_shim_world_size = n rank 0 computes
+ * the budgets of n ranks from caller-supplied norms and MPI_Scatter logs what it would have sent. */
+__attribute__((weak)) int fries_shim_world_size = 1;
+__attribute__((weak)) unsigned char fries_shim_scatter_log[1024];
+static inline int MPI_Comm_size(MPI_Comm c, int *size) { (void)c; *size = fries_shim_world_size; return MPI_SUCCESS; }
 
 static inline int MPI_Bcast(void *buf, int count, MPI_Datatype t, int root, MPI_Comm c) {
     (void)buf; (void)count; (void)t; (void)root; (void)c;
@@ -76,7 +81,10 @@ static inline int MPI_Gather(const void *sbuf, int scount, MPI_Datatype st, void
 
 static inline int MPI_Scatter(const void *sbuf, int scount, MPI_Datatype st, void *rbuf, int rcount,
                               MPI_Datatype rt, int root, MPI_Comm c) {
-    (void)scount; (void)st; (void)root; (void)c;
+    (void)root; (void)c;
+    if (fries_shim_world_size > 1 && (size_t)fries_shim_world_size * (size_t)scount * (size_t)st <= sizeof(fries_shim_scatter_log)) {
+        memcpy(fries_shim_scatter_log, sbuf, (size_t)fries_shim_world_size * (size_t)scount * (size_t)st);
+    }
     if (rbuf != MPI_IN_PLACE) {
         fries_shim_copy_(sbuf, rbuf, (size_t)rcount * (size_t)rt);
     }

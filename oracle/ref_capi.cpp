@@ -138,6 +138,73 @@ void ref_sys_comp(double *values, size_t count, double *loc_norm, unsigned n_sam
     for (size_t i = 0; i < count; i++) keep[i] = k[i];
 }
 
+/* ---- pivotal family ---------------------------------------------------------------------------
+ * The reference draws from a std::mt19937&; the bindings seed one, discard `skip` outputs and report how many
+ * outputs the call consumed (by stepping a copy of the generator until the states agree). */
+namespace {
+size_t draws_between(std::mt19937 before, const std::mt19937 &after, size_t limit) {
+    size_t k = 0;
+    while (!(before == after) && k < limit) {
+        before();
+        k++;
+    }
+    return k;
+}
+}  // namespace
+
+/* first n outputs of std::mt19937(seed) */
+void ref_mt19937_fill(uint32_t seed, size_t n, uint32_t *out) {
+    std::mt19937 mt(seed);
+    for (size_t i = 0; i < n; i++) out[i] = (uint32_t)mt();
+}
+
+/* piv_samp_serial, FRIES/compress_utils.cpp:390-530 */
+size_t ref_piv_samp_serial(double *values, size_t count, double seg_norm, uint32_t n_samp, uint8_t *keep,
+                           uint32_t seed, uint64_t skip) {
+    std::vector<bool> k(count);
+    for (size_t i = 0; i < count; i++) k[i] = keep[i] != 0;
+    std::mt19937 mt(seed);
+    mt.discard(skip);
+    std::mt19937 before = mt;
+    piv_samp_serial(values, count, seg_norm, n_samp, k, mt);
+    for (size_t i = 0; i < count; i++) keep[i] = k[i];
+    return draws_between(before, mt, 2 * (size_t)n_samp + 8);
+}
+
+/* piv_budget, FRIES/compress_utils.cpp:560-608, as rank 0 of n_procs ranks (see oracle/mpi_shim/mpi.h): all budgets */
+size_t ref_piv_budget(const double *loc_norms, int n_procs, uint32_t n_samp, uint32_t seed, uint32_t *budgets) {
+    std::vector<double> ln(loc_norms, loc_norms + n_procs);
+    std::mt19937 mt(seed);
+    std::mt19937 before = mt;
+    fries_shim_world_size = n_procs;
+    uint32_t mine = piv_budget(ln.data(), n_samp, mt);
+    if (n_procs > 1) std::memcpy(budgets, fries_shim_scatter_log, sizeof(uint32_t) * n_procs);
+    else budgets[0] = mine;
+    fries_shim_world_size = 1;
+    return draws_between(before, mt, 2 * (size_t)n_procs + 8);
+}
+
+/* adjust_probs, FRIES/compress_utils.cpp:617-681 */
+double ref_adjust_probs(double *values, size_t count, uint32_t *n_samp_loc, double exp_nsamp_loc, uint32_t n_samp_tot,
+                        double tot_norm, uint8_t *keep) {
+    std::vector<bool> k(count);
+    for (size_t i = 0; i < count; i++) k[i] = keep[i] != 0;
+    double r = adjust_probs(values, count, n_samp_loc, exp_nsamp_loc, n_samp_tot, tot_norm, k);
+    for (size_t i = 0; i < count; i++) keep[i] = k[i];
+    return r;
+}
+
+/* piv_comp_parallel, FRIES/compress_utils.cpp:354-387, single rank.  keep out: 1 = zeroed element */
+size_t ref_piv_comp_parallel(double *values, size_t count, uint32_t compress_size, uint8_t *keep, uint32_t seed) {
+    std::vector<size_t> srt(count);
+    std::vector<bool> k(count, false);
+    std::mt19937 mt(seed);
+    std::mt19937 before = mt;
+    piv_comp_parallel(values, count, compress_size, srt, k, mt);
+    for (size_t i = 0; i < count; i++) keep[i] = k[i];
+    return draws_between(before, mt, 2 * (size_t)compress_size + 8);
+}
+
 /* seed_sys, FRIES/compress_utils.cpp:107-127, single rank */
 double ref_seed_sys(double *norms, double *rn, unsigned n_samp) { return seed_sys(norms, rn, n_samp); }
 

@@ -45,6 +45,11 @@ def lib():
             "fo_sys_comp": (None, [f64p, sz, f64p, i, i, u, u8p, d]),
             "fo_comp_sub": (sz, [f64p, sz, u32p, f64p, sz, vp, u, d, f64p, u64p, P(u), P(d)]),
             "fo_adjust_shift": (None, [P(d), d, P(d), d, d]),
+            "fo_mt19937_fill": (None, [C.c_uint32, sz, u32p]),
+            "fo_piv_samp_serial": (None, [f64p, sz, d, C.c_uint32, u8p, u32p, P(sz)]),
+            "fo_piv_budget": (None, [f64p, i, C.c_uint32, u32p, P(sz), u32p]),
+            "fo_adjust_probs": (d, [f64p, sz, P(C.c_uint32), d, C.c_uint32, d, u8p]),
+            "fo_piv_comp": (None, [f64p, sz, C.c_uint32, u8p, u32p, P(sz)]),
             "fo_mol_create": (vp, [u, u, u, f64p, f64p, u8p]),
             "fo_mol_destroy": (None, [vp]),
             "fo_mol_packed_len": (sz, [vp]),
@@ -196,3 +201,43 @@ class keep_chunk:
 
     def __exit__(self, *a):
         lib().fo_set_keep_chunk(8)
+
+
+def mt19937(seed, n):
+    """first n outputs of std::mt19937(seed)"""
+    out = np.zeros(n, np.uint32)
+    lib().fo_mt19937_fill(seed, n, out)
+    return out
+
+
+def piv_samp_serial(values, seg_norm, n_samp, keep, draws):
+    """-> values, keep (1 = zeroed), draws consumed"""
+    v = np.array(values, np.float64)
+    k = np.array(keep, np.uint8)
+    used = C.c_size_t(0)
+    lib().fo_piv_samp_serial(v, len(v), seg_norm, n_samp, k, np.ascontiguousarray(draws, np.uint32), C.byref(used))
+    return v, k, used.value
+
+
+def piv_budget(loc_norms, n_samp, draws):
+    ln = np.ascontiguousarray(loc_norms, np.float64)
+    b = np.zeros(len(ln), np.uint32)
+    used = C.c_size_t(0)
+    lib().fo_piv_budget(ln, len(ln), n_samp, np.ascontiguousarray(draws, np.uint32), C.byref(used), b)
+    return b, used.value
+
+
+def adjust_probs(values, n_loc, exp_loc, n_tot, tot_norm, keep):
+    v = np.array(values, np.float64)
+    k = np.array(keep, np.uint8)
+    nl = C.c_uint32(n_loc)
+    r = lib().fo_adjust_probs(v, len(v), C.byref(nl), exp_loc, n_tot, tot_norm, k)
+    return v, k, nl.value, r
+
+
+def piv_comp(values, compress_size, draws):
+    v = np.array(values, np.float64)
+    k = np.zeros(len(v), np.uint8)
+    used = C.c_size_t(0)
+    lib().fo_piv_comp(v, len(v), compress_size, k, np.ascontiguousarray(draws, np.uint32), C.byref(used))
+    return v, k, used.value

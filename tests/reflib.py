@@ -52,6 +52,16 @@ def lib():
         L.ref_find_keep_sub.restype = C.c_double
         L.ref_find_keep_sub.argtypes = [f64p, C.c_size_t, u32p, f64p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint), f64p,
                                         u8p]
+        L.ref_mt19937_fill.restype = None
+        L.ref_mt19937_fill.argtypes = [C.c_uint32, C.c_size_t, u32p]
+        L.ref_piv_samp_serial.restype = C.c_size_t
+        L.ref_piv_samp_serial.argtypes = [f64p, C.c_size_t, C.c_double, C.c_uint32, u8p, C.c_uint32, C.c_uint64]
+        L.ref_piv_budget.restype = C.c_size_t
+        L.ref_piv_budget.argtypes = [f64p, C.c_int, C.c_uint32, C.c_uint32, u32p]
+        L.ref_adjust_probs.restype = C.c_double
+        L.ref_adjust_probs.argtypes = [f64p, C.c_size_t, C.POINTER(C.c_uint32), C.c_double, C.c_uint32, C.c_double, u8p]
+        L.ref_piv_comp_parallel.restype = C.c_size_t
+        L.ref_piv_comp_parallel.argtypes = [f64p, C.c_size_t, C.c_uint32, u8p, C.c_uint32]
         L.ref_adjust_shift.restype = None
         L.ref_adjust_shift.argtypes = [C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double]
         L.ref_mol_create.restype = C.c_void_p
@@ -195,3 +205,40 @@ def comp_sub(values, n_div, sub_weights, sub_sizes, n_samp, rn, cap):
     n = lib().ref_comp_sub(v, len(v), nd, sw.reshape(-1), sw.shape[1], None if ss is None else ss.ctypes.data, n_samp,
                            rn, nv, ni.reshape(-1), cap)
     return nv[:n].copy(), ni[:n].copy()
+
+
+def mt19937(seed, n):
+    """first n outputs of std::mt19937(seed)"""
+    out = np.zeros(n, np.uint32)
+    lib().ref_mt19937_fill(seed, n, out)
+    return out
+
+
+def piv_samp_serial(values, seg_norm, n_samp, keep, seed, skip=0):
+    """-> values, keep (1 = zeroed), draws consumed"""
+    v = np.array(values, np.float64)
+    k = np.array(keep, np.uint8)
+    used = lib().ref_piv_samp_serial(v, len(v), seg_norm, n_samp, k, seed, skip)
+    return v, k, used
+
+
+def piv_budget(loc_norms, n_samp, seed):
+    ln = np.ascontiguousarray(loc_norms, np.float64)
+    b = np.zeros(len(ln), np.uint32)
+    used = lib().ref_piv_budget(ln, len(ln), n_samp, seed, b)
+    return b, used
+
+
+def adjust_probs(values, n_loc, exp_loc, n_tot, tot_norm, keep):
+    v = np.array(values, np.float64)
+    k = np.array(keep, np.uint8)
+    nl = C.c_uint32(n_loc)
+    r = lib().ref_adjust_probs(v, len(v), C.byref(nl), exp_loc, n_tot, tot_norm, k)
+    return v, k, nl.value, r
+
+
+def piv_comp_parallel(values, compress_size, seed):
+    v = np.array(values, np.float64)
+    k = np.zeros(len(v), np.uint8)
+    used = lib().ref_piv_comp_parallel(v, len(v), compress_size, k, seed)
+    return v, k, used
