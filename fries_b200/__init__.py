@@ -3,3 +3,4 @@ the tests and bench.py; the product is libfries_b200.so (C-ABI in include/fries_
 layer in fries_b200/host/."""
 from . import _capi  # noqa: F401  (raises ImportError when the CUDA library has not been built)
 from .api import Context, Mol, Vec, find_preserve, sys_comp, comp_sub, hash_owner, bit_op, hh_batch  # noqa: F401
+from .api import piv_samp_serial, adjust_probs, piv_budget, piv_comp  # noqa: F401

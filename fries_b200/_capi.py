@@ -68,6 +68,11 @@ def _load():
         "fries_sys_comp": (i, [vp, vp, sz, vp, i, i, u, vp, d]),
         "fries_find_preserve_dev": (i, [vp, vp, sz, u, vp, vp]),
         "fries_sys_comp_dev": (i, [vp, vp, sz, vp, vp, d, vp]),
+        "fries_piv_samp_serial": (i, [vp, vp, sz, d, C.c_uint32, vp, vp, P(sz)]),
+        "fries_piv_samp_dev": (i, [vp, vp, sz, d, C.c_uint32, vp, vp, vp, sz, vp]),
+        "fries_adjust_probs": (i, [vp, vp, sz, P(C.c_uint32), d, C.c_uint32, d, vp, P(d)]),
+        "fries_piv_budget": (i, [vp, i, C.c_uint32, vp, P(sz), vp]),
+        "fries_piv_comp": (i, [vp, vp, sz, C.c_uint32, vp, vp, P(sz), vp, i, i, i, C.c_uint32]),
         "fries_comp_sub": (i, [vp, vp, sz, vp, vp, sz, vp, u, d, vp, vp, sz, P(sz), P(u), P(d)]),
         "fries_mol_create": (i, [vp, u, u, u, vp, vp, vp, P(vp)]),
         "fries_mol_destroy": (i, [vp]),

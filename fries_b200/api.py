@@ -101,6 +101,58 @@ def comp_sub(ctx, values, n_div, sub_weights, sub_sizes, n_samp, rand_num, out_c
     return nv[:n_out.value].copy(), ni[:n_out.value].copy(), left.value, ln.value
 
 
+# ---- pivotal family (compress_utils.cpp:354-681); draws = raw outputs of the caller's mt19937 ----------------------
+def piv_samp_serial(ctx, values, seg_norm, n_samp, keep, draws):
+    """compress_utils.cpp:390-530 -> (values, delete flags, draws consumed)"""
+    v = np.array(values, np.float64)
+    k = np.array(keep, np.uint8)
+    dr = arr(draws, np.uint32)
+    if dr.size < 2 * n_samp:
+        raise ValueError("piv_samp_serial needs 2 draws per sample")
+    used = C.c_size_t(0)
+    check(lib.fries_piv_samp_serial(ctx.h, ptr(v), v.size, seg_norm, n_samp, ptr(k), ptr(dr), C.byref(used)))
+    return v, k, used.value
+
+
+def adjust_probs(ctx, values, n_samp_loc, exp_nsamp_loc, n_samp_tot, tot_norm, keep):
+    """compress_utils.cpp:617-681 -> (values, keep, n_samp_loc, norm for the sampler)"""
+    v = np.array(values, np.float64)
+    k = np.array(keep, np.uint8)
+    nl, nn = C.c_uint32(n_samp_loc), C.c_double(0)
+    check(lib.fries_adjust_probs(ctx.h, ptr(v), v.size, C.byref(nl), exp_nsamp_loc, n_samp_tot, tot_norm, ptr(k),
+                                 C.byref(nn)))
+    return v, k, nl.value, nn.value
+
+
+def piv_budget(loc_norms, n_samp, draws):
+    """compress_utils.cpp:560-608 (host arithmetic, as on the reference's rank 0) -> (budgets of all ranks, draws used)"""
+    ln = arr(loc_norms, np.float64)
+    dr = arr(draws, np.uint32)
+    if dr.size < 2 * ln.size:
+        raise ValueError("piv_budget needs up to 2 draws per rank")
+    b = np.zeros(ln.size, np.uint32)
+    used = C.c_size_t(0)
+    check(lib.fries_piv_budget(ptr(ln), ln.size, n_samp, ptr(dr), C.byref(used), ptr(b)))
+    return b, used.value
+
+
+def piv_comp(ctx, values, compress_size, draws, loc_norms=None, rank=0, keep=None, n_samp_left=0):
+    """piv_comp_parallel compress_utils.cpp:354-387 -> (values, delete flags, draws consumed[, loc_norms]).
+    Single rank: only values / compress_size / draws.  As one rank of several: loc_norms (all-gathered residual norms),
+    keep and n_samp_left from the collective find_preserve."""
+    v = np.array(values, np.float64)
+    dr = arr(draws, np.uint32)
+    n_ranks = 1 if loc_norms is None else len(loc_norms)
+    if dr.size < 2 * (compress_size + n_ranks):
+        raise ValueError("piv_comp needs 2 * (compress_size + n_ranks) draws")
+    k = np.zeros(v.size, np.uint8) if keep is None else np.array(keep, np.uint8)
+    ln = None if loc_norms is None else np.array(loc_norms, np.float64)
+    used = C.c_size_t(0)
+    check(lib.fries_piv_comp(ctx.h, ptr(v), v.size, compress_size, ptr(k), ptr(dr), C.byref(used), ptr(ln), n_ranks, rank,
+                             0 if keep is None else 1, n_samp_left))
+    return (v, k, used.value) if ln is None else (v, k, used.value, ln)
+
+
 # ---- molecular Hamiltonian ----------------------------------------------------------------------------------
 class Mol:
     """Integrals + SymmInfo + hb_info resident on the GPU (molecule.hpp, heat_bathPP.hpp)."""

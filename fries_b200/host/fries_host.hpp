@@ -3,7 +3,8 @@
 // Mirrors the parts of the reference's host interface that the in-scope drivers use, with the reference's
 // names, argument meaning and error behaviour (std::runtime_error, caught in main):
 //   DistVec            FRIES/vec_utils.hpp:121-953      -> fries::DistVec (device-resident store)
-//   find_preserve ...  FRIES/compress_utils.hpp:28-429  -> fries::find_preserve / sys_comp / comp_sub / adjust_shift
+//   find_preserve ...  FRIES/compress_utils.hpp:28-429  -> fries::find_preserve / sys_comp / comp_sub / adjust_shift /
+//                      piv_samp_serial / piv_budget / adjust_probs / piv_comp_parallel
 //   parse_fcidump ...  FRIES/io_utils.hpp:23-207        -> fries::parse_fcidump / parse_hf_input / load_vec_txt / ...
 //   argparse kwargs    FRIES/Ext_Libs/argparse.hpp      -> fries::Args (same --key value syntax and failure modes)
 // All arithmetic on vectors happens in libfries_b200.so (CUDA); this file is marshalling, file formats, control flow.
@@ -496,6 +497,55 @@ inline void sys_comp(Context &c, double *vec_vals, size_t vec_len, double *loc_n
     for (size_t i = 0; i < vec_len; i++) keep[i] = keep_exact[i];
     check(fries_sys_comp(c.h, vec_vals, vec_len, loc_norms, 1, 0, n_samp, keep.data(), rand_num));
     for (size_t i = 0; i < vec_len; i++) keep_exact[i] = keep[i];
+}
+// ---- pivotal family compress_utils.cpp:354-681.  The reference's functions draw from the caller's std::mt19937; the C-ABI
+// takes the generator's next raw outputs and reports how many it used, and the generator is advanced by exactly that.
+namespace detail {
+inline std::vector<uint32_t> peek(const std::mt19937 &mt, size_t n) {
+    std::mt19937 copy = mt;
+    std::vector<uint32_t> d(n ? n : 1);
+    for (size_t i = 0; i < n; i++) d[i] = (uint32_t)copy();
+    return d;
+}
+}  // namespace detail
+// piv_samp_serial compress_utils.cpp:390-530
+inline void piv_samp_serial(Context &c, double *vec_vals, size_t vec_len, double seg_norm, uint32_t n_samp,
+                            std::vector<bool> &keep_exact, std::mt19937 &mt_obj) {
+    std::vector<uint8_t> keep(vec_len ? vec_len : 1);
+    for (size_t i = 0; i < vec_len; i++) keep[i] = keep_exact[i];
+    std::vector<uint32_t> draws = detail::peek(mt_obj, 2 * (size_t)n_samp);
+    size_t used = 0;
+    check(fries_piv_samp_serial(c.h, vec_vals, vec_len, seg_norm, n_samp, keep.data(), draws.data(), &used));
+    mt_obj.discard(used);
+    for (size_t i = 0; i < vec_len; i++) keep_exact[i] = keep[i];
+}
+// piv_budget compress_utils.cpp:560-608: budgets of all ranks (the reference returns the caller's after an MPI_Scatter)
+inline std::vector<uint32_t> piv_budget(const double *loc_norms, int n_ranks, uint32_t n_samp, std::mt19937 &mt_obj) {
+    std::vector<uint32_t> budgets(n_ranks), draws = detail::peek(mt_obj, 2 * (size_t)n_ranks);
+    size_t used = 0;
+    check(fries_piv_budget(loc_norms, n_ranks, n_samp, draws.data(), &used, budgets.data()));
+    mt_obj.discard(used);
+    return budgets;
+}
+// adjust_probs compress_utils.cpp:617-681
+inline double adjust_probs(Context &c, double *vec_vals, size_t vec_len, uint32_t *n_samp_loc, double exp_nsamp_loc,
+                           uint32_t n_samp_tot, double tot_norm, std::vector<bool> &keep_exact) {
+    std::vector<uint8_t> keep(vec_len ? vec_len : 1);
+    for (size_t i = 0; i < vec_len; i++) keep[i] = keep_exact[i];
+    double norm = 0;
+    check(fries_adjust_probs(c.h, vec_vals, vec_len, n_samp_loc, exp_nsamp_loc, n_samp_tot, tot_norm, keep.data(), &norm));
+    for (size_t i = 0; i < vec_len; i++) keep_exact[i] = keep[i];
+    return norm;
+}
+// piv_comp_parallel compress_utils.cpp:354-387 (single rank; srt_scratch is unused here)
+inline void piv_comp_parallel(Context &c, double *vec_vals, size_t vec_len, uint32_t compress_size, std::vector<size_t> &,
+                              std::vector<bool> &keep_scratch, std::mt19937 &rn_gen) {
+    std::vector<uint8_t> keep(vec_len ? vec_len : 1);
+    std::vector<uint32_t> draws = detail::peek(rn_gen, 2 * ((size_t)compress_size + 1));
+    size_t used = 0;
+    check(fries_piv_comp(c.h, vec_vals, vec_len, compress_size, keep.data(), draws.data(), &used, nullptr, 1, 0, 0, 0));
+    rn_gen.discard(used);
+    for (size_t i = 0; i < vec_len; i++) keep_scratch[i] = keep[i];
 }
 // adjust_shift compress_utils.cpp:684-693 (scalar control logic of the drivers)
 inline void adjust_shift(double *shift, double one_norm, double *last_norm, double target_norm, double damp_factor) {

@@ -94,6 +94,38 @@ int fries_find_preserve_dev(fries_ctx *ctx, const double *d_values, size_t count
 int fries_sys_comp_dev(fries_ctx *ctx, double *d_values, size_t count, const double *d_result4, uint8_t *d_keep,
                        double rand_num, double *d_new_norm);
 
+/* ---- pivotal compression family ------------------------------------------------------
+ * Randomness: the reference hands these functions a std::mt19937& and draws uniforms as mt() / 2^32
+ * (compress_utils.cpp:436,468).  Here the caller passes the generator's next raw 32-bit outputs in h_draws and
+ * advances its generator by *n_draws_used afterwards (std::mt19937::discard); unit k of the sampler uses draws
+ * 2k and 2k + 1, exactly as the sequential sweep does.
+ *
+ * piv_samp_serial FRIES/compress_utils.cpp:390-530: ordered pivotal sampling of n_samp of the elements with
+ * keep == 0, each becoming +-seg_norm / n_samp; every one of them must be smaller than that unit.  keep in:
+ * preserved flags, out: 1 = zeroed element.  h_draws: 2 * n_samp entries. */
+int fries_piv_samp_serial(fries_ctx *ctx, double *h_values, size_t count, double seg_norm, uint32_t n_samp,
+                          uint8_t *h_keep, const uint32_t *h_draws, size_t *n_draws_used);
+/* resident form; d_work: 8 bytes per element + 12 per sample (+ 1 kB of alignment slack);
+ * d_result4 (may be NULL) receives {one-norm after, elements drawn, units processed, anomalies} */
+int fries_piv_samp_dev(fries_ctx *ctx, double *d_values, size_t count, double seg_norm, uint32_t n_samp, uint8_t *d_keep,
+                       const uint32_t *d_draws, void *d_work, size_t work_bytes, double *d_result4);
+/* adjust_probs FRIES/compress_utils.cpp:617-681: returns the norm for the sampler in *new_norm, updates
+ * *n_samp_loc, values and keep flags */
+int fries_adjust_probs(fries_ctx *ctx, double *h_values, size_t count, uint32_t *n_samp_loc, double exp_nsamp_loc,
+                       uint32_t n_samp_tot, double tot_norm, uint8_t *h_keep, double *new_norm);
+/* piv_budget FRIES/compress_utils.cpp:560-608: rank 0's host arithmetic on n_ranks norms; budgets of ALL ranks
+ * (the reference scatters them).  h_draws: up to 2 * n_ranks entries.  No device work. */
+int fries_piv_budget(const double *loc_norms, int n_ranks, uint32_t n_samp, const uint32_t *h_draws,
+                     size_t *n_draws_used, uint32_t *budgets);
+/* piv_comp_parallel FRIES/compress_utils.cpp:354-387 = find_preserve + piv_budget + adjust_probs +
+ * piv_samp_serial.  Single rank: n_ranks = 1, preserved = 0, h_loc_norms may be NULL.  As one rank of several
+ * (preserved = 1): h_keep, n_samp_left and h_loc_norms[n_ranks] come from the collective find_preserve and the
+ * all-gather of its residual norms (:364-365).  h_draws: 2 * (compress_size + n_ranks) entries.  On return
+ * h_loc_norms[rank] (if given) is this rank's one-norm after compression. */
+int fries_piv_comp(fries_ctx *ctx, double *h_values, size_t count, uint32_t compress_size, uint8_t *h_keep,
+                   const uint32_t *h_draws, size_t *n_draws_used, double *h_loc_norms, int n_ranks, int rank,
+                   int preserved, uint32_t n_samp_left);
+
 /* ---- a6: hierarchical compression with explicit sub-weights -----------------------------------------
  * comp_sub FRIES/compress_utils.cpp:797-820 = find_keep_sub :130-276 + sys_sub :702-794.
  * sub_weights row-major count x n_sub (n_sub <= FRIES_MAX_SUB); sub_sizes may be NULL.

@@ -15,7 +15,7 @@ _lib = None
 
 def build():
     src = os.path.join(HERE, "hostcheck.cu")
-    deps = [src] + [os.path.join(HERE, "..", "..", "fries_b200", "csrc", f) for f in ("mol.cuh", "common.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "..", "fries_b200", "csrc", f) for f in ("mol.cuh", "common.cuh", "piv.cuh")]
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(SO), exist_ok=True)
@@ -55,5 +55,9 @@ def lib():
         L.hc_hb_wt.argtypes = [C.c_void_p, C.c_int, C.c_uint64, u8p]
         L.hc_sing_counts.restype = C.c_uint
         L.hc_sing_counts.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        L.hc_piv_samp.restype = C.c_size_t
+        L.hc_piv_samp.argtypes = [f64p, C.c_size_t, u8p, C.c_double, C.c_uint32, u32p, C.POINTER(C.c_uint64)]
+        L.hc_adjust_probs.restype = C.c_double
+        L.hc_adjust_probs.argtypes = [f64p, C.c_size_t, u8p, C.POINTER(C.c_uint32), C.c_double, C.c_uint32, C.c_double]
         _lib = L
     return _lib

@@ -5,6 +5,7 @@
 // CPU-only test tier can check them against the compiled reference before GPU time is spent.  The
 // kernels themselves (launch geometry, scans, atomics, staging) are only checked by the -m gpu tests.
 #include "../../fries_b200/csrc/mol.cuh"
+#include "../../fries_b200/csrc/piv.cuh"
 #include <vector>
 
 struct HcMol {
@@ -137,5 +138,72 @@ unsigned hc_sing_counts(void *p, uint64_t key, unsigned occ_choice, unsigned *el
     *n_virt = mol_count_sing_virt(m, occ, cnt, &ch);
     *elec_idx = ch;
     return mol_count_sing_allowed(m, occ, cnt);
+}
+
+// ---- pivotal family (piv.cuh): the kernels' phases of piv.cu, run one after the other on the host with a sequential
+// prefix sum (the device sums in chunks: same values up to the last bit) --------------------------------------------------
+size_t hc_piv_samp(double *vals, size_t n, uint8_t *keep, double seg_norm, uint32_t n_samp, const uint32_t *draws,
+                   uint64_t *anomalies) {
+    const PivGrid g = piv_grid(seg_norm, n_samp);
+    uint32_t n_units = 0;
+    *anomalies = 0;
+    if (n_samp > 0 && n > 0) {
+        std::vector<double> E(n);
+        double run = 0;
+        for (size_t i = 0; i < n; i++) E[i] = run += keep[i] ? 0.0 : fabs(vals[i]);
+        std::vector<uint32_t> cross(n_samp, PIV_NONE), sample(n_samp, PIV_NONE), carry(n_samp, PIV_NONE);
+        for (size_t i = 0; i < n; i++)
+            piv_mark_cross(g, i ? E[i - 1] : 0.0, E[i], (uint32_t)i, [&](uint32_t k, uint32_t el) { cross[k] = el; });
+        uint32_t n_crossed = g.borders_le(E[n - 1]);
+        auto loadE = [&](uint32_t j) { return E[j]; };
+        auto loadC = [&](uint32_t k) {
+            uint32_t c = cross[k];
+            if (c == PIV_NONE) c = piv_search(loadE, 0u, (uint32_t)(n - 1), g.border((uint64_t)k + 1));
+            return c;
+        };
+        n_units = piv_n_units(g, n_crossed, n_crossed ? loadC(n_crossed - 1) : 0, n);
+        for (uint32_t k = 0; k < n_units; k++)
+            piv_unit(g, k, n_crossed, n, loadE, loadC, draws[2 * k] / 4294967296.0, draws[2 * k + 1] / 4294967296.0,
+                     sample[k], carry[k]);
+        for (uint32_t k = 0; k < n_units; k++) {
+            uint32_t s = sample[k];
+            if (s == PIV_CARRIED) s = piv_resolve(k, [&](uint32_t j) { return carry[j]; });
+            if (s < n && keep[s] != 1) keep[s] = 2;
+            else (*anomalies)++;
+        }
+    }
+    for (size_t i = 0; i < n; i++) piv_finish(g.unit, n_samp, vals[i], keep[i]);
+    return 2 * (size_t)n_units;
+}
+
+double hc_adjust_probs(double *vals, size_t n, uint8_t *keep, uint32_t *n_loc, double exp_loc, uint32_t n_tot,
+                       double tot_norm) {
+    const PivAdjust a = piv_adjust_setup(*n_loc, exp_loc, n_tot, tot_norm);
+    const double thresh = a.loc_norm / ceil(exp_loc);
+    bool big = false;
+    for (size_t i = 0; i < n; i++)
+        if (!keep[i] && fabs(vals[i]) >= thresh) big = true;
+    if (!big) return a.loc_norm;
+    double g = a.g0();
+    uint32_t exact_cnt = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (keep[i]) continue;
+        double dg;
+        unsigned long long dk;
+        a.delta(fabs(vals[i]), dg, dk);
+        double g_before = g, g_after = g + dg;
+        g = g_after;
+        if (!a.reached(g_before)) continue;
+        bool exact;
+        double v = vals[i], nv = a.apply(v, exact);
+        if (a.last(g_after)) nv = fma((v > 0 ? 1.0 : -1.0) * a.unit, -g_after, nv);
+        vals[i] = nv;
+        if (exact) {
+            keep[i] = 1;
+            exact_cnt++;
+        }
+    }
+    *n_loc -= exact_cnt;
+    return *n_loc * a.loc_norm / exp_loc;
 }
 }
