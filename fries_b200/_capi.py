@@ -73,6 +73,7 @@ def _load():
         "fries_adjust_probs": (i, [vp, vp, sz, P(C.c_uint32), d, C.c_uint32, d, vp, P(d)]),
         "fries_piv_budget": (i, [vp, i, C.c_uint32, vp, P(sz), vp]),
         "fries_piv_comp": (i, [vp, vp, sz, C.c_uint32, vp, vp, P(sz), vp, i, i, i, C.c_uint32]),
+        "fries_vec_compress": (i, [vp, u, u, C.c_uint32, i, vp, sz, P(sz)]),
         "fries_comp_sub": (i, [vp, vp, sz, vp, vp, sz, vp, u, d, vp, vp, sz, P(sz), P(u), P(d)]),
         "fries_mol_create": (i, [vp, u, u, u, vp, vp, vp, P(vp)]),
         "fries_mol_destroy": (i, [vp]),

@@ -318,6 +318,14 @@ class Vec:
         f = arr(flags, np.uint8)
         check(lib.fries_vec_del(self.h, ptr(f), f.size))
 
+    def compress(self, start_row, end_row, compress_size, draws, method="piv") -> int:
+        """compress_vecs / compress_vecs_sys vec_utils.cpp:10-70 -> draws consumed"""
+        dr = arr(draws, np.uint32)
+        used = C.c_size_t(0)
+        check(lib.fries_vec_compress(self.h, start_row, end_row, compress_size, 0 if method == "piv" else 1, ptr(dr),
+                                     dr.size, C.byref(used)))
+        return used.value
+
     def dot(self, keys, vals, row=0) -> float:
         k, v = arr(keys, np.uint64), arr(vals, np.float64)
         out = C.c_double(0)

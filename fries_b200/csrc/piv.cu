@@ -4,6 +4,7 @@
 // between the phases.
 #include "piv.cuh"
 #include "compress.cuh"
+#include "vec.cuh"
 
 struct PivResult {
     double new_norm;               // one-norm after sampling (preserved + drawn)
@@ -506,5 +507,78 @@ extern "C" int fries_piv_comp(fries_ctx *c, double *h_values, size_t count, uint
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (n_draws_used) *n_draws_used = used + 2 * (size_t)r.n_units;
     if (h_loc_norms) h_loc_norms[rank] = r.new_norm;
+    return FRIES_OK;
+}
+
+// compress_vecs / compress_vecs_sys (FRIES/vec_utils.cpp:10-70) on the resident store: rows [start_row, end_row) are
+// compressed one after the other to compress_size elements (method 0: piv_comp_parallel, draws consumed as there;
+// method 1: find_preserve + sys_comp with one draw per row), then every element that is zero in ALL rows is deleted
+// (del_at_pos only removes such elements, vec_utils.hpp:458-476, so the reference's del_arr bookkeeping reduces to
+// this).  Single rank.
+extern "C" int fries_vec_compress(fries_vec *vec, unsigned start_row, unsigned end_row, uint32_t compress_size, int method,
+                                  const uint32_t *h_draws, size_t n_draws, size_t *n_draws_used) {
+    FRIES_REQUIRE(vec && (h_draws || n_draws == 0), "fries_vec_compress: NULL argument");
+    FRIES_REQUIRE(start_row <= end_row && end_row <= vec->n_vecs, "fries_vec_compress: rows [%u, %u) of %u", start_row,
+                  end_row, vec->n_vecs);
+    FRIES_REQUIRE(method == 0 || method == 1, "fries_vec_compress: method 0 (pivotal) or 1 (systematic)");
+    FRIES_REQUIRE(vec->n_ranks == 1, "fries_vec_compress: single rank");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    VecCounters cnt;
+    FRIES_TRY(vec->read_counters(&cnt));
+    const size_t n = (size_t)cnt.n;
+    int grid = piv_grid_size(c);
+    DevBuf<uint8_t> keep;
+    DevBuf<uint32_t> draws;
+    PivWork w;
+    FRIES_TRY(keep.alloc(n));
+    if (method == 0) {
+        FRIES_TRY(draws.alloc(2 * (size_t)compress_size + 2));
+        FRIES_TRY(w.alloc(n, compress_size));
+    }
+    PivScratch s;
+    FRIES_TRY(piv_scratch(c, grid, s));
+    size_t used = 0;
+    for (unsigned row = start_row; row < end_row; row++) {
+        double *d_vals = vec->vals[vec->cur].p + (size_t)row * vec->cap;
+        CUDA_TRY(cudaMemsetAsync(s.st, 0, sizeof(CompState), c->stream));
+        FRIES_TRY(fries_find_preserve_launch(c, d_vals, n, nullptr, compress_size, keep.p, s.st, s.pd, s.pc, 0, nullptr));
+        CompState st;
+        CUDA_TRY(cudaMemcpyAsync(&st, s.st, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const unsigned n_samp = st.n_samp_left;
+        const double loc = st.loc_norm;
+        if (method == 1) {
+            FRIES_REQUIRE(used < n_draws, "fries_vec_compress: out of draws (one per row)");
+            double rn = h_draws[used++] / 4294967296.0;
+            FRIES_TRY(fries_sys_comp_launch(c, d_vals, n, nullptr, keep.p, nullptr, 0.0, loc, (long long)n_samp, rn, s.st,
+                                            s.pd, s.pc, 0, nullptr));
+            continue;
+        }
+        uint32_t loc_samp = 0;
+        const double *d_par = nullptr;
+        if (n_samp != 0) {
+            size_t bu = 0;
+            FRIES_REQUIRE(used + 2 <= n_draws, "fries_vec_compress: out of draws");
+            FRIES_TRY(fries_piv_budget(&loc, 1, n_samp, h_draws + used, &bu, &loc_samp));
+            used += bu;
+            double exp_loc = n_samp * loc / loc;
+            if (exp_loc > 0) {
+                FRIES_TRY(piv_adjust_launch(c, d_vals, n, keep.p, loc_samp, exp_loc, n_samp, loc, s, grid, s.par));
+                d_par = s.par;
+            }
+        }
+        FRIES_REQUIRE(used + 2 * (size_t)loc_samp <= n_draws, "fries_vec_compress: out of draws (2 per sample)");
+        if (loc_samp)
+            CUDA_TRY(cudaMemcpyAsync(draws.p, h_draws + used, 8 * (size_t)loc_samp, cudaMemcpyHostToDevice, c->stream));
+        FRIES_TRY(piv_samp_launch(c, d_vals, n, keep.p, 0.0, loc_samp, d_par, draws.p, w.view(), s, grid));
+        PivResult r;
+        CUDA_TRY(cudaMemcpyAsync(&r, s.res, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // also keeps h_draws' staging buffer safe for the next row
+        used += 2 * (size_t)r.n_units;
+    }
+    FRIES_TRY(fries_vec_compact_dev(vec));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (n_draws_used) *n_draws_used = used;
     return FRIES_OK;
 }

@@ -126,6 +126,12 @@ int fries_piv_comp(fries_ctx *ctx, double *h_values, size_t count, uint32_t comp
                    const uint32_t *h_draws, size_t *n_draws_used, double *h_loc_norms, int n_ranks, int rank,
                    int preserved, uint32_t n_samp_left);
 
+/* compress_vecs (method 0, pivotal) / compress_vecs_sys (method 1, systematic) FRIES/vec_utils.cpp:10-70 on the resident
+ * store: rows [start_row, end_row) are each compressed to compress_size elements, then the elements that are zero in
+ * every row are deleted.  Draws as above (method 1: one per row).  Single rank. */
+int fries_vec_compress(fries_vec *vec, unsigned start_row, unsigned end_row, uint32_t compress_size, int method,
+                       const uint32_t *h_draws, size_t n_draws, size_t *n_draws_used);
+
 /* ---- a6: hierarchical compression with explicit sub-weights -----------------------------------------
  * comp_sub FRIES/compress_utils.cpp:797-820 = find_keep_sub :130-276 + sys_sub :702-794.
  * sub_weights row-major count x n_sub (n_sub <= FRIES_MAX_SUB); sub_sizes may be NULL.

@@ -5,11 +5,13 @@ import os
 import numpy as np
 import pytest
 
-from golden_cases import (COMP_SUB_CASES, HBPP_CASES, MOL_CASES, VEC_COMP_CASES, comp_sub_inputs, hbpp_inputs, mol_keys,
-                          vec_values)
+from golden_cases import (COMP_SUB_CASES, HBPP_CASES, MOL_CASES, PIV_ADJUST_CASES, PIV_COMP_CASES, PIV_SAMP_CASES,
+                          VEC_COMP_CASES, comp_sub_inputs, hbpp_inputs, mol_keys, piv_adjust_inputs, piv_comp_inputs,
+                          piv_samp_inputs, vec_values)
 
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fries_golden.npz"))
+GP = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "piv_golden.npz"))
 REL = 1e-12
 
 
@@ -97,3 +99,56 @@ def test_apply_hbpp_sys_golden(ctx, i):
     # same number of samples up to the marginal preservation decisions; both are draws of the same estimator
     assert abs(len(gset) - len(rset)) <= max(3, len(rset) // 4)
     gm.close()
+
+
+# ---- pivotal family against the reference's outputs (tests/golden/piv_golden.npz) -----------------------------------
+def std_mt19937(seed, n):
+    """std::mt19937(seed) outputs: numpy's legacy seeding of MT19937 is the same init_genrand"""
+    return np.random.RandomState(seed).randint(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+
+
+def test_mt19937_draws_are_the_standard_ones():
+    assert np.array_equal(std_mt19937(5489, 10000)[-4:], GP["mt5489_10000"])
+
+
+@pytest.mark.parametrize("i", range(len(PIV_SAMP_CASES)))
+def test_piv_samp_serial_golden(ctx, i):
+    import fries_b200
+    from test_hostcheck_piv import same_up_to_closing_unit
+    case = PIV_SAMP_CASES[i]
+    v, keep, norm = piv_samp_inputs(case)
+    gv, gk, used = fries_b200.piv_samp_serial(ctx, v, norm, case[2], keep, std_mt19937(case[0], 2 * case[2] + 8))
+    assert used == GP[f"ps{i}_used"]
+    if case[2] == 0:
+        assert np.array_equal(gv, GP[f"ps{i}_v"]) and np.array_equal(gk, GP[f"ps{i}_k"])
+    else:
+        same_up_to_closing_unit(v, keep, norm, case[2], gv, gk, GP[f"ps{i}_v"], GP[f"ps{i}_k"])
+        assert ((keep == 0) & (gv != 0)).sum() == case[2]
+
+
+@pytest.mark.parametrize("i", range(len(PIV_ADJUST_CASES)))
+def test_adjust_probs_golden(ctx, i):
+    import fries_b200
+    case = PIV_ADJUST_CASES[i]
+    v, keep, n_loc, tot_norm = piv_adjust_inputs(case)
+    gv, gk, gn, gnorm = fries_b200.adjust_probs(ctx, v, n_loc, case[3], case[2], tot_norm, keep)
+    assert gn == GP[f"pa{i}_n"] and gnorm == GP[f"pa{i}_norm"] and np.array_equal(gk, GP[f"pa{i}_k"])
+    assert np.allclose(gv, GP[f"pa{i}_v"], rtol=0, atol=1e-10 * tot_norm / case[2])
+    assert (gv != GP[f"pa{i}_v"]).sum() <= 1
+
+
+@pytest.mark.parametrize("i", range(len(PIV_COMP_CASES)))
+def test_piv_comp_parallel_golden(ctx, i):
+    import fries_b200
+    case = PIV_COMP_CASES[i]
+    v = piv_comp_inputs(case)
+    gv, gk, used = fries_b200.piv_comp(ctx, v, case[2], std_mt19937(case[0], 2 * case[2] + 8))
+    assert used == GP[f"pc{i}_used"]
+    ref = np.zeros(len(v))
+    ref[GP[f"pc{i}_idx"]] = GP[f"pc{i}_val"]
+    diff = np.flatnonzero((gv != 0) != (ref != 0))
+    assert len(diff) <= 2  # the closing unit may pick another of its candidates (see tests/test_gpu_piv.py)
+    same = np.ones(len(v), bool)
+    same[diff] = False
+    assert np.allclose(gv[same], ref[same], rtol=1e-12, atol=0)
+    assert np.array_equal(gk == 1, gv == 0)

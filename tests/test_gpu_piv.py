@@ -162,3 +162,63 @@ def test_piv_comp_is_unbiased(ctx):
     p = np.where(keep == 1, 0.0, np.abs(v) / unit)
     sd = unit * np.sqrt(p * (1 - p) / reps)
     assert np.all(np.abs(mean - v) <= 5 * sd + 1e-9 * np.abs(v))
+
+
+@pytest.mark.parametrize("method", ["piv", "sys"])
+def test_vec_compress_rows(ctx, method):
+    """compress_vecs / compress_vecs_sys (vec_utils.cpp:10-70) on the resident store: rows 1 and 2 of a 3-row vector are
+    compressed, row 0 is left alone, and elements that end up zero in all three rows disappear"""
+    import fries_b200
+    from fries_b200.synth import SynthMol
+    from test_hostcheck_piv import same_up_to_closing_unit
+    sm = SynthMol("ne", 2, False)
+    rng = np.random.default_rng(17)
+    n, m = 6000, 700
+    keys = sm.random_dets(n, rng, None).astype(np.uint64)
+    vals = rng.standard_normal((3, n)) * np.exp(2 * rng.standard_normal((3, n)))
+    vals[0, rng.random(n) < 0.6] = 0       # row 0: many zeros, so that some elements die
+    vals[2, rng.random(n) < 0.2] = 0
+    scr = rng.integers(0, 2**32, sm.n_bits, dtype=np.uint64).astype(np.uint32)
+    vec = fries_b200.Vec(ctx, 2 * n, sm.n_bits, sm.n_elec, 3, scr, scr)
+    vec.upload(keys, vals)
+    k0, v0 = vec.download()
+    assert np.array_equal(k0, keys) and np.array_equal(v0, vals)
+    draws = ol.mt19937(99, 4 * m + 16)
+    used = vec.compress(1, 3, m, draws, method)
+    # expected: the oracle row by row on consecutive draws
+    exp = vals.copy()
+    o_used = 0
+    swaps = []
+    for r in (1, 2):
+        if method == "piv":
+            ov, ok, u = ol.piv_comp(vals[r], m, draws[o_used:])
+            o_used += u
+        else:
+            loc, glob, left, keep = ol.find_preserve(vals[r], m)
+            ov, ok, _ = ol.sys_comp(vals[r], [loc], left, keep, draws[o_used] / 4294967296.0)
+            o_used += 1
+        exp[r] = ov
+    assert used == o_used
+    gk, gv = vec.download()
+    # map the surviving elements back to their original positions (compaction is stable)
+    pos = np.flatnonzero(np.isin(keys, gk))
+    assert np.array_equal(keys[pos], gk)
+    full = np.zeros_like(vals)
+    full[:, pos] = gv
+    assert np.array_equal(full[0], vals[0])
+    for r in (1, 2):
+        assert (full[r] != 0).sum() == m
+        if method == "piv":
+            loc, glob, left, keep = ol.find_preserve(vals[r], m)
+            kz = np.zeros(n, np.uint8)
+            swaps.append(same_up_to_closing_unit(vals[r], keep, loc, left, full[r], kz, exp[r], kz, rtol=1e-12))
+        else:
+            ties = int(((full[r] != 0) != (exp[r] != 0)).sum())
+            assert ties <= 2  # FP-boundary ties of the systematic grid, as in test_gpu_parity.py
+            same = (full[r] != 0) == (exp[r] != 0)
+            assert np.allclose(full[r][same], exp[r][same], rtol=1e-12, atol=0)
+    # exactly the elements that are zero in every row are gone
+    dead = ~np.any(full != 0, axis=0)
+    assert dead.sum() > 0 and len(gk) == n - dead.sum()
+    assert not np.isin(keys[dead], gk).any()
+    vec.close()

@@ -7,10 +7,12 @@ import pytest
 
 import oraclelib
 from fries_b200.synth import SynthMol
-from golden_cases import (COMP_SUB_CASES, HBPP_CASES, MOL_CASES, VEC_COMP_CASES, comp_sub_inputs, hbpp_inputs, mol_keys,
-                          vec_values)
+from golden_cases import (COMP_SUB_CASES, HBPP_CASES, MOL_CASES, PIV_ADJUST_CASES, PIV_BUDGET_CASES, PIV_COMP_CASES,
+                          PIV_SAMP_CASES, VEC_COMP_CASES, comp_sub_inputs, hbpp_inputs, mol_keys, piv_adjust_inputs,
+                          piv_budget_inputs, piv_comp_inputs, piv_samp_inputs, vec_values)
 
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fries_golden.npz"))
+GP = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "piv_golden.npz"))
 
 
 def test_hash_golden():
@@ -72,3 +74,41 @@ def test_apply_hbpp_sys_golden(i):
     ov, od, oo = om.apply_hbpp_sys(keys, vals, 0.97, case[3], G[f"hb{i}_uni"], case[2], 4 * case[2] + 4 * case[1])
     assert np.array_equal(od, G[f"hb{i}_d"]) and np.array_equal(oo, G[f"hb{i}_o"])
     assert np.allclose(ov, G[f"hb{i}_v"], rtol=1e-13, atol=0)
+
+
+# ---- pivotal family (tests/golden/piv_golden.npz, generator tests/golden/make_piv_golden.py) -----------------------
+def test_mt19937_golden():
+    assert np.array_equal(oraclelib.mt19937(5489, 10000)[-4:], GP["mt5489_10000"])
+
+
+@pytest.mark.parametrize("i", range(len(PIV_SAMP_CASES)))
+def test_piv_samp_serial_golden(i):
+    case = PIV_SAMP_CASES[i]
+    v, keep, norm = piv_samp_inputs(case)
+    ov, ok, used = oraclelib.piv_samp_serial(v, norm, case[2], keep, oraclelib.mt19937(case[0], 2 * case[2] + 8))
+    assert used == GP[f"ps{i}_used"] and np.array_equal(ov, GP[f"ps{i}_v"]) and np.array_equal(ok, GP[f"ps{i}_k"])
+
+
+@pytest.mark.parametrize("i", range(len(PIV_BUDGET_CASES)))
+def test_piv_budget_golden(i):
+    case = PIV_BUDGET_CASES[i]
+    b, used = oraclelib.piv_budget(piv_budget_inputs(case), case[2], oraclelib.mt19937(case[0], 2 * case[1] + 8))
+    assert used == GP[f"pb{i}_used"] and np.array_equal(b, GP[f"pb{i}_b"])
+
+
+@pytest.mark.parametrize("i", range(len(PIV_ADJUST_CASES)))
+def test_adjust_probs_golden(i):
+    case = PIV_ADJUST_CASES[i]
+    v, keep, n_loc, tot_norm = piv_adjust_inputs(case)
+    ov, ok, on, onorm = oraclelib.adjust_probs(v, n_loc, case[3], case[2], tot_norm, keep)
+    assert on == GP[f"pa{i}_n"] and onorm == GP[f"pa{i}_norm"]
+    assert np.array_equal(ov, GP[f"pa{i}_v"]) and np.array_equal(ok, GP[f"pa{i}_k"])
+
+
+@pytest.mark.parametrize("i", range(len(PIV_COMP_CASES)))
+def test_piv_comp_parallel_golden(i):
+    case = PIV_COMP_CASES[i]
+    ov, ok, used = oraclelib.piv_comp(piv_comp_inputs(case), case[2], oraclelib.mt19937(case[0], 2 * case[2] + 8))
+    nz = np.flatnonzero(ov)
+    assert used == GP[f"pc{i}_used"] and np.array_equal(nz, GP[f"pc{i}_idx"]) and np.array_equal(ov[nz], GP[f"pc{i}_val"])
+    assert np.array_equal(ok == 1, ov == 0)

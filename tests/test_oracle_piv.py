@@ -7,24 +7,13 @@ import pytest
 
 import oraclelib as ol
 import reflib
+from golden_cases import piv_samp_inputs
 
 needs_ref = pytest.mark.skipif(not reflib.available(), reason="oracle/_ref not built")
 
 
 def piv_case(seed, n, n_samp, frac_keep=0.0, zeros=0.0):
-    """values whose non-preserved magnitudes are all below seg_norm / n_samp (piv_samp_serial's contract)"""
-    rng = np.random.default_rng(seed)
-    v = rng.random(n) ** 3 * np.where(rng.random(n) < 0.5, -1.0, 1.0)
-    v[rng.random(n) < zeros] = 0
-    keep = (rng.random(n) < frac_keep).astype(np.uint8)
-    keep[v == 0] = 0
-    for _ in range(100):
-        norm = np.abs(v[keep == 0]).sum()
-        big = (keep == 0) & (np.abs(v) >= norm / n_samp)
-        if not big.any():
-            break
-        v[big] *= 0.5
-    return v, keep, float(np.abs(v[keep == 0]).sum())
+    return piv_samp_inputs((seed, n, n_samp, frac_keep, zeros))
 
 
 @needs_ref
