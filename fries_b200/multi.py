@@ -59,6 +59,44 @@ class Comm:
             self.h = None
 
 
+def piv_comp_parallel(ctx, dist, rank: int, world: int, values_local, compress_size: int, shared_draws, local_draws,
+                      device):
+    """piv_comp_parallel (compress_utils.cpp:354-387) of a vector partitioned over the ranks.
+
+    ctx must carry the ranks' inboxes (fries_ctx_set_comm): find_preserve is collective with its reductions inside the
+    kernel.  The residual norms are all-gathered (the reference's MPI_Allgather, :365), every rank evaluates rank 0's
+    budget arithmetic on the SAME shared_draws (the reference draws on rank 0 and scatters, :560-608), then adjusts and
+    samples its own shard with local_draws.  Returns (values, delete flags, budget of this rank, norms before, one-norm
+    after); plumbing only, the arithmetic is in libfries_b200.so."""
+    from .api import piv_budget
+    v = np.ascontiguousarray(values_local, np.float64)
+    d_vals = torch.tensor(v, device=device)
+    d_keep = torch.zeros(max(v.size, 1), dtype=torch.uint8, device=device)
+    d_r4 = torch.zeros(4, dtype=torch.float64, device=device)
+    check(lib.fries_find_preserve_dev(ctx.h, d_vals.data_ptr(), v.size, compress_size, d_keep.data_ptr(), d_r4.data_ptr()))
+    ctx.sync()
+    r4 = d_r4.cpu().numpy()
+    n_left = int(r4[2])
+    norms = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
+    dist.all_gather(norms, d_r4[0:1].clone())
+    norms = np.array([float(t.item()) for t in norms])
+    keep = d_keep.cpu().numpy()[:v.size]
+    shared = arr(shared_draws, np.uint32)
+    used_b = 0
+    if n_left:
+        _, used_b = piv_budget(norms, n_left, shared)
+    draws = np.concatenate([shared[:used_b], arr(local_draws, np.uint32)])
+    if draws.size < 2 * (compress_size + world):
+        raise ValueError("piv_comp_parallel needs 2 * compress_size local draws")
+    ln = norms.copy()
+    k = keep.copy()
+    used = C.c_size_t(0)
+    check(lib.fries_piv_comp(ctx.h, ptr(v), v.size, compress_size, ptr(k), ptr(draws), C.byref(used), ptr(ln), world, rank,
+                             1, n_left))
+    n_drawn = (used.value - used_b) // 2
+    return v, k, n_drawn, (keep, norms, n_left, used_b), float(ln[rank])
+
+
 class Router:
     """the Adder's exchange (vec_utils.hpp:991-1019): counts, then fixed-capacity segments"""
 

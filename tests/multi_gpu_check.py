@@ -75,6 +75,38 @@ def main():
         assert np.allclose(d_vals.cpu().numpy()[same], ov[lo:hi][same], rtol=1e-12, atol=0)
     if rank == 0:
         print(f"[multi] distributed find_preserve/sys_comp over {world} ranks == single-rank oracle", flush=True)
+    # ---- (1b) distributed pivotal compression: every rank's shard against the oracle's chain piv_budget ->
+    #      adjust_probs -> piv_samp_serial (each pinned against the reference) on the same norms and draws ----
+    from fries_b200.multi import piv_comp_parallel
+    from test_hostcheck_piv import same_up_to_closing_unit
+    shared = oraclelib.mt19937(1234, 2 * world + 8)
+    local = oraclelib.mt19937(77 + rank, 2 * budget + 8)
+    gv, gk, n_drawn, (keep, norms, n_left, used_b), new_norm = piv_comp_parallel(ctx, dist, rank, world, v[lo:hi], budget,
+                                                                                shared, local, dev)
+    assert np.array_equal(keep, o_keep[lo:hi]) and n_left == o_left
+    mine = np.abs(v[lo:hi][keep == 0]).sum()
+    assert abs(norms[rank] - mine) <= 1e-12 * mine
+    budgets, ub = oraclelib.piv_budget(norms, n_left, shared)
+    assert ub == used_b and int(budgets.sum()) == n_left
+    glob = float(np.sum(norms))
+    exp_loc = n_left * norms[rank] / glob
+    av, ak, a_n, a_norm = oraclelib.adjust_probs(v[lo:hi], int(budgets[rank]), exp_loc, n_left, glob, keep)
+    ov2, ok2, o_used = oraclelib.piv_samp_serial(av, a_norm, a_n, ak, local)
+    assert n_drawn == a_n == o_used // 2, (n_drawn, a_n, o_used)
+    # elements that adjust_probs made exact are preserved for the sampler: they are not candidates of a sampling unit
+    same_up_to_closing_unit(av, ak, a_norm, a_n, gv, gk, ov2, ok2, rtol=1e-10)
+    tot = torch.tensor([float((gv != 0).sum())], device=dev, dtype=torch.float64)
+    dist.all_reduce(tot)
+    assert int(tot.item()) == budget, (int(tot.item()), budget)
+    if rank == 0:
+        print(f"[multi] distributed piv_comp_parallel over {world} ranks: budgets {budgets.tolist()} == oracle chain, "
+              f"{budget} elements in total", flush=True)
+    if os.environ.get("FRIES_MULTI_ONLY") == "compress":
+        check(lib.fries_ctx_set_comm(ctx.h, None))
+        comm.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     check(lib.fries_ctx_set_comm(ctx.h, None))
     comm.close()
 

@@ -1,5 +1,5 @@
 """GPU tier, >= 2 GPUs: tests/multi_gpu_check.py under torchrun (one rank per GPU): in-kernel exchange ping-pong,
-distributed find_preserve / sys_comp against the single-rank oracle, 30 frisys_mol iterations on both spawn routes with
+distributed find_preserve / sys_comp against the single-rank oracle, distributed piv_comp_parallel against the oracle's chain, 30 frisys_mol iterations on both spawn routes with
 the ownership invariant, routed H.v against the single-GPU H.v, multi-rank frifull_mol.  Skipped on a one-GPU box (the
 driver's GPU tier); run by hand with gpurun --gpus 2 / 8 during the round."""
 import os
@@ -24,5 +24,6 @@ def test_multi_gpu_check_under_torchrun():
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("[multi]")]
     assert r.returncode == 0, r.stdout[-3000:]
     assert any("== single-rank oracle" in ln for ln in lines), lines
+    assert any("distributed piv_comp_parallel" in ln for ln in lines), lines
     assert any("route p2p" in ln for ln in lines) and any("route nccl" in ln for ln in lines), lines
     assert any("routed H.v == single-GPU H.v" in ln for ln in lines), lines
