@@ -69,7 +69,7 @@ def piv_comp_parallel(ctx, dist, rank: int, world: int, values_local, compress_s
     samples its own shard with local_draws.  Returns (values, delete flags, budget of this rank, norms before, one-norm
     after); plumbing only, the arithmetic is in libfries_b200.so."""
     from .api import piv_budget
-    v = np.ascontiguousarray(values_local, np.float64)
+    v = np.array(values_local, np.float64)  # a copy: the compression works in place
     d_vals = torch.tensor(v, device=device)
     d_keep = torch.zeros(max(v.size, 1), dtype=torch.uint8, device=device)
     d_r4 = torch.zeros(4, dtype=torch.float64, device=device)
