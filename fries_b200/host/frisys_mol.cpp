@@ -6,9 +6,15 @@ using namespace fries;
 
 int main(int argc, char *argv[]) {
     Args args(argc, argv);
-    std::string fcidump_path = args.str("fcidump_path");
+    // --hf_path <dir>/ (legacy input directory, io_utils.cpp:98-187) is accepted in place of --fcidump_path, as in the
+    // reference's examples/run_neon.sh and Benchmarks/Results.tex command lines: epsilon then defaults to the eps of
+    // sys_params.txt, the distribution to HB_unnorm, frozen core electrons are honoured and energies are relative to
+    // hf_energy.  Everything else is the HEAD command line (FRIES_bin/frisys_mol.cpp:17-32).
+    bool legacy = args.has("hf_path");
+    std::string hf_path = args.str("hf_path", "");
+    std::string fcidump_path = legacy ? args.str("fcidump_path", "") : args.str("fcidump_path");
     double target_norm = args.num("target", 0);
-    std::string dist_str = args.str("distribution");
+    std::string dist_str = legacy ? args.str("distribution", "HB_unnorm") : args.str("distribution");
     uint32_t max_iter = (uint32_t)args.num("max_iter", 1000000);
     uint32_t target_nonz = (uint32_t)args.num("vec_nonz");
     uint32_t matr_samp = (uint32_t)args.num("mat_nonz");
@@ -19,7 +25,7 @@ int main(int argc, char *argv[]) {
     std::string load_dir = args.str("load_dir", ""), ini_path = args.str("ini_vec", ""), trial_path = args.str("trial_vec", "");
     bool has_det_space = args.has("det_space");
     std::string det_space_path = args.str("det_space", "");
-    double eps = args.num("epsilon");
+    double eps = legacy ? args.num("epsilon", -1) : args.num("epsilon");
     std::string point_group = args.str("point_group", "C1");
     bool has_shift = args.has("ham_shift");
     double ham_shift = args.num("ham_shift", 0);
@@ -39,12 +45,13 @@ int main(int argc, char *argv[]) {
         unsigned shift_interval = 10, save_interval = 100;
         double en_shift = 0;
 
-        MolInput in_data = parse_fcidump(fcidump_path, point_group);
-        unsigned n_elec = in_data.n_elec, n_frz = 0, n_orb = in_data.n_orb;
+        MolInput in_data = legacy ? parse_hf_input(hf_path) : parse_fcidump(fcidump_path, point_group);
+        unsigned n_elec = in_data.n_elec, n_frz = legacy ? in_data.n_frz : 0, n_orb = in_data.n_orb;
         unsigned n_elec_unf = n_elec - n_frz;
+        if (legacy && eps < 0) eps = in_data.eps;
         Molecule mol(ctx, in_data);
         uint64_t hf_det = gen_hf_bitstring(n_orb, n_elec_unf);
-        double hf_en = has_shift ? ham_shift - in_data.core_en : mol.diag_matrel(hf_det);
+        double hf_en = has_shift ? ham_shift - in_data.core_en : (legacy ? in_data.hf_en : mol.diag_matrel(hf_det));
 
         unsigned seed = seed_from_clock_or_env();
         std::cout << "seed on process 0 is " << seed << std::endl;
@@ -110,7 +117,7 @@ int main(int argc, char *argv[]) {
                       norm_file = open_app("norm.txt"), nkept_file = open_app("nkept.txt"), ini_file = open_app("nini.txt");
         {
             std::ofstream param_f(result_dir + "params.txt");
-            param_f << "FRI calculation\nFCIDUMP path: " << fcidump_path << "\nepsilon (imaginary time step): " << eps
+            param_f << "FRI calculation\n" << (legacy ? "HF path: " : "FCIDUMP path: ") << (legacy ? hf_path : fcidump_path) << "\nepsilon (imaginary time step): " << eps
                     << "\nTarget norm " << target_norm << "\nInitiator threshold: " << init_thresh
                     << "\nMatrix nonzero: " << matr_samp << "\nVector nonzero: " << target_nonz << "\n";
             if (has_load) param_f << "Restarting calculation from " << load_dir << "\n";

@@ -92,6 +92,28 @@ def test_frisys_mol_driver_energy_and_files(tiny, tmp_path):
         assert abs(e - er) < 5 * (s + sr) + 2e-4, (e, s, er, sr)
 
 
+def test_frisys_mol_legacy_hf_path(tiny, tmp_path):
+    """the command line of the reference's examples/run_neon.sh (legacy --hf_path directory, no --distribution, no
+    --epsilon): same trajectory as the FCIDUMP form of the same molecule with the same seed"""
+    sm, om, e_corr, e_hf, n = tiny
+    fd = str(tmp_path / "FCIDUMP")
+    write_fcidump(fd, sm, "D2")
+    d = str(tmp_path / "hf") + "/"
+    write_hf_dir(d, sm, 0.05, float(e_hf))
+    common = ["--vec_nonz", 150, "--mat_nonz", 300, "--max_dets", 20000, "--target", 500, "--max_iter", 300]
+    out = {}
+    for name, extra in (("fcidump", ["--fcidump_path", fd, "--distribution", "HB_unnorm", "--epsilon", 0.05, "--point_group",
+                                     "D2"]), ("legacy", ["--hf_path", d])):
+        rd = str(tmp_path / name) + "/"
+        os.makedirs(rd)
+        r = run(os.path.join(OURS, "frisys_mol"), extra + common + ["--result_dir", rd], seed=11)
+        assert "Exception" not in r.stderr and r.returncode == 0, r.stderr[-500:]
+        out[name] = (read_col(rd + "projnum.txt"), read_col(rd + "projden.txt"))
+        assert ("HF path: " if name == "legacy" else "FCIDUMP path: ") in open(rd + "params.txt").read()
+    for a, b in zip(out["fcidump"], out["legacy"]):
+        assert len(a) == 300 and np.allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
 def test_frisys_mol_semistochastic_det_space(tiny, tmp_path):
     """--det_space (frisys_mol.cpp:233-252,347-401,479-485): the determinants of the file form a
     dense subspace whose columns of H are applied exactly.  Same files and statistics as the reference's driver."""
