@@ -123,6 +123,8 @@ def _load():
         "fries_vec_del": (i, [vp, vp, sz]),
         "fries_vec_dot": (i, [vp, vp, vp, sz, u, P(d)]),
         "fries_vec_local_norm": (i, [vp, u, P(d)]),
+        "fries_vec_two_norm": (i, [vp, u, P(d)]),
+        "fries_vec_row_op": (i, [vp, i, u, u, d]),
         "fries_vec_set_diag_mol": (i, [vp, vp, d]),
         "fries_h_apply": (i, [vp, vp, u, u, d, d]),
         "fries_h_apply_last_spawned": (i, [vp, P(C.c_uint64)]),

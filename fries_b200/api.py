@@ -337,6 +337,23 @@ class Vec:
         check(lib.fries_vec_local_norm(self.h, row, C.byref(out)))
         return out.value
 
+    def two_norm(self, row=0) -> float:
+        out = C.c_double(0)
+        check(lib.fries_vec_two_norm(self.h, row, C.byref(out)))
+        return out.value
+
+    def add_vecs(self, dst, src, c=1.0):
+        check(lib.fries_vec_row_op(self.h, 0, dst, src, c))
+
+    def copy_vec(self, src, dst):
+        check(lib.fries_vec_row_op(self.h, 1, dst, src, 0.0))
+
+    def weight_vec(self, dst, src, expo):
+        check(lib.fries_vec_row_op(self.h, 2, dst, src, expo))
+
+    def zero_vec(self, row):
+        check(lib.fries_vec_row_op(self.h, 3, row, row, 0.0))
+
     def set_diag_mol(self, mol, hf_en):
         check(lib.fries_vec_set_diag_mol(self.h, mol.h, hf_en))
 

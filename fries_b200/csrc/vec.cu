@@ -195,7 +195,7 @@ trial_dot_kernel(VecView v, const uint64_t *__restrict__ t_keys, const double *_
 
 // DistVec::local_norm vec_utils.hpp:683-689
 __global__ void __launch_bounds__(FR_COMP_BLOCK)
-local_norm_kernel(VecView v, unsigned row, double *part_d, unsigned long long *part_c, double *out) {
+local_norm_kernel(VecView v, unsigned row, int squares, double *part_d, unsigned long long *part_c, double *out) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh_d[34];
     __shared__ unsigned long long sh_c[34];
@@ -204,11 +204,18 @@ local_norm_kernel(VecView v, unsigned row, double *part_d, unsigned long long *p
     size_t n = n64 < v.cap ? (size_t)n64 : v.cap;
     double s = 0;
     size_t gstride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride)
-        s += fabs(v.vals[(size_t)row * v.cap + i]);
+    const double *x = v.vals + (size_t)row * v.cap;
+    // four independent loads in flight per thread
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * gstride) {
+        double a[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) a[k] = i + k * gstride < n ? x[i + k * gstride] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) s += squares ? a[k] * a[k] : fabs(a[k]);
+    }
     unsigned long long dummy = 0;
     grid_reduce(grid, red, s, dummy);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *out = s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out = squares ? sqrt(s) : s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -536,9 +543,62 @@ extern "C" int fries_vec_dot(fries_vec *vec, const uint64_t *h_keys, const doubl
     return FRIES_OK;
 }
 
+// DistVec::add_vecs / copy_vec / weight_vec / zero_vec (vec_utils.hpp:547-579) on the stored elements of two rows
+__global__ void __launch_bounds__(256)
+row_op_kernel(VecView v, int op, unsigned dst, unsigned src, double c) {
+    unsigned long long n64 = v.cnt->n;
+    const size_t n = n64 < v.cap ? (size_t)n64 : v.cap;
+    double *d = v.vals + (size_t)dst * v.cap;
+    const double *s = v.vals + (size_t)src * v.cap;
+    const size_t gstride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * gstride) {
+        double a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            size_t j = i + k * gstride;
+            a[k] = (j < n && op != 1 && op != 3) ? d[j] : 0.0;
+            b[k] = (j < n && op != 3) ? s[j] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            size_t j = i + k * gstride;
+            if (j >= n) continue;
+            double r;
+            switch (op) {
+                case 0: r = a[k] + b[k] * c; break;                   // add_vecs(dst, src, c)
+                case 1: r = b[k]; break;                              // copy_vec(src, dst)
+                case 2: r = a[k] * pow(1 + fabs(b[k]), c); break;     // weight_vec(dst, src, expo)
+                default: r = 0.0; break;                              // zero_vec
+            }
+            d[j] = r;
+        }
+    }
+}
+
+extern "C" int fries_vec_row_op(fries_vec *vec, int op, unsigned dst, unsigned src, double c) {
+    FRIES_REQUIRE(vec, "fries_vec_row_op: NULL vector");
+    FRIES_REQUIRE(op >= 0 && op <= 3, "fries_vec_row_op: op %d not in 0..3", op);
+    FRIES_REQUIRE(dst < vec->n_vecs && src < vec->n_vecs, "fries_vec_row_op: row out of range");
+    fries_ctx *ctx = vec->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    row_op_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(vec->view(), op, dst, src, c);
+    ctx->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    return FRIES_OK;
+}
+
+static int vec_norm(fries_vec *vec, unsigned row, int squares, double *out);
+extern "C" int fries_vec_two_norm(fries_vec *vec, unsigned row, double *out) {
+    FRIES_REQUIRE(vec && out, "NULL argument");
+    FRIES_REQUIRE(row < vec->n_vecs, "fries_vec_two_norm: row out of range");
+    return vec_norm(vec, row, 1, out);
+}
 extern "C" int fries_vec_local_norm(fries_vec *vec, unsigned row, double *out) {
     FRIES_REQUIRE(vec && out, "NULL argument");
     FRIES_REQUIRE(row < vec->n_vecs, "fries_vec_local_norm: row out of range");
+    return vec_norm(vec, row, 0, out);
+}
+static int vec_norm(fries_vec *vec, unsigned row, int squares, double *out) {
     fries_ctx *c = vec->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     int grid = c->coop_grid((const void *)local_norm_kernel, FR_COMP_BLOCK, 0);
@@ -548,7 +608,7 @@ extern "C" int fries_vec_local_norm(fries_vec *vec, unsigned row, double *out) {
     double *pd = vec->red_d.p;
     unsigned long long *pc = vec->red_c.p;
     double *po = dout.p;
-    void *args[] = {(void *)&v, (void *)&row, (void *)&pd, (void *)&pc, (void *)&po};
+    void *args[] = {(void *)&v, (void *)&row, (void *)&squares, (void *)&pd, (void *)&pc, (void *)&po};
     CUDA_TRY(cudaLaunchCooperativeKernel((const void *)local_norm_kernel, dim3(grid), dim3(FR_COMP_BLOCK), args, 0,
                                          c->stream));
     c->launch_count++;

@@ -363,6 +363,10 @@ class DistVec {
     fries_hbpp *hb = nullptr;
     unsigned n_bits, n_elec, n_vecs;
     size_t max_size_;
+    uint8_t curr_vec_idx_ = 0;
+    std::vector<uint64_t> buf_dets_;
+    std::vector<double> buf_vals_;
+    std::vector<uint8_t> buf_ini_;
     DistVec(Context &c, size_t size, unsigned n_bits_, unsigned n_elec_, unsigned n_vecs_, const std::vector<uint32_t> &proc_scr,
             const std::vector<uint32_t> &vec_scr)
         : n_bits(n_bits_), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size) {
@@ -391,10 +395,61 @@ class DistVec {
         std::vector<uint8_t> ini(dets.size(), ini_flag);
         check(fries_vec_add(h, dets.data(), vals.data(), ini.data(), dets.size(), origin, dest));
     }
-    double local_norm(unsigned row = 0) {
+    double local_norm(unsigned row) {
         double n;
         check(fries_vec_local_norm(h, row, &n));
         return n;
+    }
+    double local_norm() { return local_norm(curr_vec_idx_); }  // vec_utils.hpp:683-689
+    double two_norm() {                                         // :695-701
+        double n;
+        check(fries_vec_two_norm(h, curr_vec_idx_, &n));
+        return n;
+    }
+    // the row that add / perform_add / local_norm / dot / zero_vec work on (vec_utils.hpp:585-599)
+    void set_curr_vec_idx(uint8_t new_idx) {
+        if (new_idx >= n_vecs) {
+            std::stringstream error;
+            error << "Argument to set_curr_vec_idx (" << (unsigned)new_idx << ") is out of bounds";
+            throw std::runtime_error(error.str());
+        }
+        curr_vec_idx_ = new_idx;
+    }
+    uint8_t curr_vec_idx() const { return curr_vec_idx_; }
+    size_t n_nonz() { return curr_size(); }
+    // add(idx, val, ini_flag) buffers one element, perform_add(origin) sends the buffer to the store (:418-440, 957-1019)
+    void add(uint64_t det, double val, uint8_t ini_flag) {
+        if (val == 0) return;
+        buf_dets_.push_back(det);
+        buf_vals_.push_back(val);
+        buf_ini_.push_back(ini_flag);
+    }
+    void perform_add(size_t origin = 0) {
+        if (!buf_dets_.empty())
+            check(fries_vec_add(h, buf_dets_.data(), buf_vals_.data(), buf_ini_.data(), buf_dets_.size(), (unsigned)origin,
+                                curr_vec_idx_));
+        buf_dets_.clear();
+        buf_vals_.clear();
+        buf_ini_.clear();
+    }
+    void add_vecs(uint8_t idx1, uint8_t idx2, double c = 1.0) { check(fries_vec_row_op(h, 0, idx1, idx2, c)); }   // :547-557
+    void copy_vec(uint8_t src, uint8_t dst) { check(fries_vec_row_op(h, 1, dst, src, 0.0)); }                   // :561-565
+    void weight_vec(uint8_t idx1, uint8_t idx2, double expo) { check(fries_vec_row_op(h, 2, idx1, idx2, expo)); }  // :569-573
+    void zero_vec() { check(fries_vec_row_op(h, 3, curr_vec_idx_, curr_vec_idx_, 0.0)); }                       // :577-579
+    // dot with a (replicated) list of determinants (:228-253)
+    double dot(const std::vector<uint64_t> &dets, const std::vector<double> &vals) {
+        double out;
+        check(fries_vec_dot(h, dets.data(), vals.data(), dets.size(), curr_vec_idx_, &out));
+        return out;
+    }
+    // del_at_pos for every flagged position + cleanup (:458-497): elements that are zero in every row disappear
+    void del_at_pos(const std::vector<bool> &flags) {
+        std::vector<uint8_t> f(flags.begin(), flags.end());
+        check(fries_vec_del(h, f.data(), f.size()));
+    }
+    void cleanup() {
+        std::vector<uint8_t> f(curr_size(), 1);
+        check(fries_vec_del(h, f.data(), f.size()));
     }
     uint64_t tot_sgn_coh() {
         uint64_t n;

@@ -211,6 +211,10 @@ int fries_vec_del(fries_vec *vec, const uint8_t *h_flags, size_t n);
 int fries_vec_dot(fries_vec *vec, const uint64_t *h_keys, const double *h_vals, size_t n, unsigned row, double *out);
 /* DistVec::local_norm :683-689 of a row */
 int fries_vec_local_norm(fries_vec *vec, unsigned row, double *out);
+int fries_vec_two_norm(fries_vec *vec, unsigned row, double *out);   /* DistVec::two_norm :695-701 */
+/* row arithmetic on the stored elements (vec_utils.hpp:547-579).  op 0: add_vecs(dst, src, c)  dst += c * src;
+ * 1: copy_vec(src, dst); 2: weight_vec(dst, src, expo = c)  dst *= (1 + |src|)^c; 3: zero_vec of row dst */
+int fries_vec_row_op(fries_vec *vec, int op, unsigned dst, unsigned src, double c);
 int fries_vec_set_diag_mol(fries_vec *vec, fries_mol *mol, double hf_en); /* diag_calc_ = diag_matrel - hf_en */
 
 /* ---- a16: deterministic H.v (h_op_diag molecule.cpp:205-219 + h_op_offdiag :448-665) ---------------------

@@ -416,3 +416,34 @@ def test_hh_pieces(ctx, n_sites, n_elec):
     for i, k in enumerate(keys):
         assert lut[int(k)] == pytest.approx(vals[i] * (2 if i % 2 == 0 else 1), rel=1e-14)
     vec.close()
+
+
+def test_vec_row_ops(ctx):
+    """DistVec::add_vecs / copy_vec / weight_vec / zero_vec / two_norm / local_norm (vec_utils.hpp:547-579,683-701)
+    against the same loops in numpy"""
+    import fries_b200
+    rng = np.random.default_rng(23)
+    n_orb, half, n = 20, 4, 70001
+    n_bits = 2 * n_orb
+    scr = rng.integers(0, 2**32, n_bits, dtype=np.uint64).astype(np.uint32)
+    keys = np.unique(rand_dets(rng, 2 * n, n_orb, half))[:n]
+    vals = rng.standard_normal((3, keys.size))
+    vec = fries_b200.Vec(ctx, 2 * n, n_bits, 2 * half, 3, scr, scr)
+    vec.upload(keys, vals)
+    exp = vals.copy()
+    vec.add_vecs(0, 1, -0.75)
+    exp[0] += exp[1] * -0.75
+    vec.weight_vec(2, 0, -0.5)
+    exp[2] *= (1 + np.abs(exp[0])) ** -0.5
+    vec.copy_vec(2, 1)
+    exp[1] = exp[2]
+    assert vec.two_norm(0) == pytest.approx(np.sqrt((exp[0] ** 2).sum()), rel=1e-13)
+    assert vec.local_norm(2) == pytest.approx(np.abs(exp[2]).sum(), rel=1e-13)
+    k, v = vec.download()
+    assert np.array_equal(k, keys)
+    assert np.array_equal(v[0], exp[0]) and np.array_equal(v[1], exp[1])
+    assert np.allclose(v[2], exp[2], rtol=1e-14, atol=0)  # pow on the device vs libm
+    vec.zero_vec(0)
+    k, v = vec.download()
+    assert not v[0].any() and np.array_equal(v[1], exp[1]) and k.size == keys.size  # zeroed, not deleted
+    vec.close()
