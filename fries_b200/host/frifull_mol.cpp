@@ -56,7 +56,8 @@ int main(int argc, char *argv[]) {
             load_vec_txt(ini_path, d, v);
             sol_vec.add(d, v, 1);
         } else {
-            sol_vec.add({hf_det}, {100.0}, 1);
+            sol_vec.add(hf_det, 100.0, 1);  // DistVec::add + perform_add, as the reference does
+            sol_vec.perform_add(0);
         }
         double last_one_norm = 0;
         auto open_app = [&](const char *name) {

@@ -51,7 +51,8 @@ int main(int argc, char *argv[]) {
             sol_vec.load(load_dir);
             last_one_norm = sol_vec.local_norm();
         } else {
-            sol_vec.add({neel_det}, {100.0}, 1);
+            sol_vec.add(neel_det, 100.0, 1);  // DistVec::add + perform_add, as the reference does
+            sol_vec.perform_add(0);
         }
         auto open_app = [&](const char *name) {
             std::ofstream f(result_dir + name, std::ofstream::app);

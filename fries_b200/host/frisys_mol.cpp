@@ -102,7 +102,8 @@ int main(int argc, char *argv[]) {
             load_vec_txt(ini_path, d, v);
             sol_vec.add(d, v, 1);
         } else {
-            sol_vec.add({hf_det}, {100.0}, 1);
+            sol_vec.add(hf_det, 100.0, 1);  // DistVec::add + perform_add, as the reference does
+            sol_vec.perform_add(0);
         }
         double glob_norm = sol_vec.local_norm();
         double last_one_norm = 0;
