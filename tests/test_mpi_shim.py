@@ -1,0 +1,86 @@
+"""CPU tier: the multi-process mode of the MPI stand-in (oracle/mpi_shim: mpi.h + shimrun.py) that lets the reference's
+own MPI code use the host cores for the CPU baseline.  (1) every collective the reference calls, with rank-dependent
+patterns, on 3 and 8 ranks (and more ranks than cores); (2) the reference's frisys_mol on 1 / 2 / 4 ranks: per-rank
+checkpoint files, and the same energy as the exact ground state within error bars."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "mpi_shim"))
+import shimrun  # noqa: E402
+from driver_utils import REF, exact_ground_state, read_col, write_fcidump  # noqa: E402
+
+have_ref = os.path.exists(os.path.join(REF, "frisys_mol"))
+
+
+@pytest.fixture(scope="module")
+def selftest(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("shim") / "selftest")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-I" + os.path.join(ROOT, "oracle", "mpi_shim"),
+                           os.path.join(ROOT, "oracle", "mpi_shim", "selftest.c"), "-o", exe])
+    return exe
+
+
+@pytest.mark.parametrize("n", [1, 3, 8, 19])
+def test_collectives(selftest, n, tmp_path):
+    out = open(tmp_path / "out.txt", "w+")
+    rc, sec = shimrun.run(n, [selftest], 1 << 20, timeout=120, stdout=out, stderr=subprocess.STDOUT)
+    out.seek(0)
+    assert rc == 0 and out.read().strip() == f"shim ok {n}"
+
+
+def test_a_dead_rank_ends_the_run(tmp_path):
+    # rank 1 exits at once, the others would wait in their first barrier for ever: the launcher kills them
+    prog = tmp_path / "p.c"
+    prog.write_text('#include <mpi.h>\n#include <stdlib.h>\nint main(int c, char **v) { MPI_Init(&c, &v); int r; '
+                    'MPI_Comm_rank(MPI_COMM_WORLD, &r); if (r == 1) exit(7); double x = 0; '
+                    'MPI_Bcast(&x, 1, MPI_DOUBLE, 0, MPI_COMM_WORLD); return 0; }\n')
+    exe = str(tmp_path / "p")
+    subprocess.check_call(["gcc", "-O1", "-I" + os.path.join(ROOT, "oracle", "mpi_shim"), str(prog), "-o", exe])
+    rc, sec = shimrun.run(3, [exe], 1 << 20, timeout=60)
+    assert rc == 7 and sec < 30
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref drivers not built")
+def test_reference_frisys_mol_on_several_ranks(tmp_path):
+    import re
+
+    import oraclelib
+    from fries_b200.synth import SynthMol
+    sm = SynthMol((8, 6, 0, [0, 0, 1, 2, 3, 0, 1, 2]), 4)
+    e_corr, e_hf, n_dets = exact_ground_state(sm, oraclelib.OracleMol(sm))
+    fd = str(tmp_path / "FCIDUMP")
+    write_fcidump(fd, sm, "D2")
+    n_it = 4000
+    for n in (1, 2, 4):
+        rd = str(tmp_path / f"r{n}") + "/"
+        os.makedirs(rd)
+        cmd = [os.path.join(REF, "frisys_mol"), "--fcidump_path", fd, "--distribution", "HB_unnorm", "--vec_nonz", "150",
+               "--mat_nonz", "300", "--max_dets", "20000", "--epsilon", "0.05", "--target", "500", "--max_iter", str(n_it),
+               "--result_dir", rd, "--point_group", "D2"]
+        err = open(tmp_path / f"err{n}.txt", "w+")
+        rc, sec = shimrun.run(n, cmd, 8 << 20, timeout=300, env=dict(os.environ, FRIES_SEED=str(10 + n)), stderr=err,
+                              stamp=re.compile(r"^(\d+), en est: "))
+        err.seek(0)
+        assert rc == 0 and "Exception" not in err.read()
+        assert len(shimrun.run.stamps) == n_it and [int(k) for k, _ in shimrun.run.stamps[:3]] == [0, 1, 2]
+        for r in range(n):
+            assert os.path.exists(rd + f"dets{r}.dat") and os.path.exists(rd + f"vals{r}.dat")
+        num, den = read_col(rd + "projnum.txt")[1000:], read_col(rd + "projden.txt")[1000:]
+        blocks = np.array([num[i:i + 100].sum() / den[i:i + 100].sum() for i in range(0, len(num), 100)])
+        e, s = num.sum() / den.sum(), blocks.std(ddof=1) / np.sqrt(len(blocks))
+        print(n, "ranks:", e, "+-", s, "exact", e_corr, f"{sec:.2f} s")
+        assert abs(e - e_corr) < 5 * s + 2e-3 * abs(e_corr) + 2e-4, (n, e, s, e_corr)
+
+
+def test_rank_count_respects_an_override(monkeypatch):
+    sys.path.insert(0, ROOT)
+    import bench
+    n = bench.reference_rank_count()
+    assert n >= 1 and n & (n - 1) == 0 and n <= 64
+    monkeypatch.setenv("FRIES_REF_RANKS", "3")
+    assert bench.reference_rank_count() == 3
