@@ -1,4 +1,4 @@
-/* Single-rank stand-in for <mpi.h>.
+/* Stand-in for <mpi.h>: one rank, or N processes over a shared-memory file (see "multi-process mode" below).
  *
  * TEST INFRASTRUCTURE ONLY.  The reference (sgreene8/FRIES) is an MPI code and this image has no
  * MPI.  This header lets the reference's own sources compile and run as ONE rank so that they can
