@@ -114,6 +114,25 @@ void ref_hash_keys(const uint64_t *keys, size_t n, int n_bits, const uint32_t *s
     }
 }
 
+/* Attach this process to the multi-process communicator of oracle/mpi_shim (FRIES_SHIM_* in the environment, set by
+ * shimrun.py): afterwards the reference's collectives inside find_preserve / sys_comp / piv_comp_parallel are real. */
+int ref_mpi_init(void) {
+    MPI_Init(nullptr, nullptr);
+    int n = 1;
+    MPI_Comm_size(MPI_COMM_WORLD, &n);
+    return n;
+}
+int ref_mpi_rank(void) {
+    int r = 0;
+    MPI_Comm_rank(MPI_COMM_WORLD, &r);
+    return r;
+}
+
+/* MPI_Allgather(MPI_IN_PLACE) of `count` doubles per rank, as the drivers do for loc_norms (frisys_mol.cpp:532) */
+void ref_allgather_doubles(double *buf, int count) {
+    MPI_Allgather(MPI_IN_PLACE, 0, MPI_DOUBLE, buf, count, MPI_DOUBLE, MPI_COMM_WORLD);
+}
+
 /* ---- a4/a5: vector compression -------------------------------------------------------------- */
 
 /* find_preserve, FRIES/compress_utils.cpp:29-105.  keep_out[i] in {0,1}. Returns the local

@@ -52,6 +52,10 @@ def lib():
         L.ref_find_keep_sub.restype = C.c_double
         L.ref_find_keep_sub.argtypes = [f64p, C.c_size_t, u32p, f64p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint), f64p,
                                         u8p]
+        L.ref_mpi_init.restype = C.c_int
+        L.ref_mpi_rank.restype = C.c_int
+        L.ref_allgather_doubles.restype = None
+        L.ref_allgather_doubles.argtypes = [f64p, C.c_int]
         L.ref_mt19937_fill.restype = None
         L.ref_mt19937_fill.argtypes = [C.c_uint32, C.c_size_t, u32p]
         L.ref_piv_samp_serial.restype = C.c_size_t

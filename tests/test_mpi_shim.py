@@ -84,3 +84,57 @@ def test_rank_count_respects_an_override(monkeypatch):
     assert n >= 1 and n & (n - 1) == 0 and n <= 64
     monkeypatch.setenv("FRIES_REF_RANKS", "3")
     assert bench.reference_rank_count() == 3
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+@pytest.mark.parametrize("world", [2, 3])
+def test_reference_compression_on_several_ranks(tmp_path, world):
+    """What the multi-GPU checks assume, established with the reference's own multi-rank code (tests/mpi_rank_script.py
+    under shimrun): (a) find_preserve over the ranks keeps exactly the set of the single-rank oracle on the whole vector;
+    (b) sys_comp over the ranks draws the single-rank oracle's samples (up to FP-boundary ties); (c) the reference's
+    multi-rank piv_comp_parallel equals the chain piv_budget (rank 0's draws) -> adjust_probs -> piv_samp_serial (each
+    rank's own draws) that tests/multi_gpu_check.py uses as the expectation for the GPUs."""
+    import oraclelib as ol
+    from mpi_rank_script import make_vector, shard_bounds
+    from test_hostcheck_piv import same_up_to_closing_unit
+    n, budget, rn = 60000, 9000, 0.31
+    err = open(tmp_path / "err.txt", "w+")
+    rc, sec = shimrun.run(world, [sys.executable, os.path.join(ROOT, "tests", "mpi_rank_script.py"), str(tmp_path), str(n),
+                                  str(budget), str(rn)], 8 << 20, timeout=300, stderr=err, all_output=True)
+    err.seek(0)
+    assert rc == 0, err.read()[-2000:]
+    v = make_vector(n)
+    b = shard_bounds(n, world)
+    res = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    # (a)
+    o_loc, o_glob, o_left, o_keep = ol.find_preserve(v, budget)
+    assert np.array_equal(np.concatenate([r["keep"] for r in res]), o_keep)
+    assert all(int(r["left"]) == o_left for r in res)
+    assert sum(float(r["loc"]) for r in res) == pytest.approx(o_loc, rel=1e-12)
+    # (b)
+    ov, ok, _ = ol.sys_comp(v, [o_loc], o_left, o_keep, rn)
+    sk = np.concatenate([r["sk"] for r in res])
+    sv = np.concatenate([r["sv"] for r in res])
+    ties = int((sk != ok).sum())
+    assert ties <= 2, ties
+    same = sk == ok
+    assert np.allclose(sv[same], ov[same], rtol=1e-12, atol=0)
+    # (c)
+    norms = res[0]["norms"]
+    glob = 0.0
+    for x in norms:
+        glob += x
+    draws0 = ol.mt19937(100, 2 * budget + 2 * world + 8)
+    budgets, used_b = ol.piv_budget(norms, o_left, draws0)
+    assert int(budgets.sum()) == o_left
+    total = 0
+    for r in range(world):
+        shard, keep = v[b[r]:b[r + 1]], o_keep[b[r]:b[r + 1]]
+        draws = draws0[used_b:] if r == 0 else ol.mt19937(100 + r, 2 * budget + 8)
+        av, ak, a_n, a_norm = ol.adjust_probs(shard, int(budgets[r]), o_left * norms[r] / glob, o_left, glob, keep)
+        ev, ek, used = ol.piv_samp_serial(av, a_norm, a_n, ak, draws)
+        assert int(res[r]["used"]) == used + (used_b if r == 0 else 0)
+        # bit for bit: the chain is the reference's own sequence of calls
+        assert np.array_equal(res[r]["pv"], ev) and np.array_equal(res[r]["pk"], ek)
+        total += int((ev != 0).sum())
+    assert total == budget
