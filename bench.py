@@ -303,6 +303,7 @@ def run_ours(args, cfg):
     achieved = units[top] / (kern[top] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5),
+                "peak_nominal": 8000.0, "frac_nominal": round(achieved / 8000.0, 5),  # report against both
                 "traffic": NCU_TRAFFIC_NE.get(top) if cfg["system"] == "ne" else None,
                 "traffic_source": "profiles/r01c_ncu_full_hbpp_stage_raw.csv (bytes per launch)",
                 "algorithmic_bytes_per_launch": units[top],
@@ -320,6 +321,8 @@ def run_ours(args, cfg):
                                    "candidate_rounds_us": [round((states[s, 18] - states[s, 13]) / 1e3, 1) for s in range(5)],
                                    "apply_cut_us": [round((states[s, 19] - states[s, 18]) / 1e3, 1) for s in range(5)]},
                 "iter_algorithmic_GBps": round((96 * n_vec + 200 * cfg["mat_nonz"] + 56 * stp.n_spawned) / (ms_per_step * 1e-3) / 1e9, 2)}
+    # the whole iteration against the roofline, by SURVEY 8d's byte contract B_iter = 96 N_v + 200 N_m + 56 N_s
+    roofline["iter_frac"] = round(roofline["iter_algorithmic_GBps"] / peak, 5)
 
     out = {
         "metric": "fri_iterations_per_sec", "value": round(value, 3), "unit": "iter/s", "n_gpus": 1, "steps": args.steps,
