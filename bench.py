@@ -399,6 +399,13 @@ def reference_rank_count():
             cores = max(1, min(cores, int(int(quota) / int(period))))
     except (OSError, ValueError):
         pass
+    try:  # cgroup v1
+        quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if quota > 0 and period > 0:
+            cores = max(1, min(cores, quota // period))
+    except (OSError, ValueError):
+        pass
     n = 1
     while 2 * n <= min(cores, 64):
         n *= 2
@@ -437,7 +444,7 @@ def reference_iter_seconds(cfg, sm, keys, vals, it_a, it_b, workdir, n_ranks=1):
 
     try:
         with open(err_path, "w") as ef:
-            rc, _ = shimrun.run(n_ranks, cmd, 256 << 20, timeout=900, env=env, stderr=ef,
+            rc, _ = shimrun.run(n_ranks, cmd, 256 << 20, timeout=300, env=env, stderr=ef,
                                 stamp=re.compile(r"^(\d+), en est: "))
     except OSError:
         # no pseudo-terminal on this host: wall-clock difference of two runs with different --max_iter (noisier)
@@ -445,7 +452,7 @@ def reference_iter_seconds(cfg, sm, keys, vals, it_a, it_b, workdir, n_ranks=1):
         for n_it in (it_a, it_b):
             cmd[cmd.index("--max_iter") + 1] = str(n_it)
             with open(err_path, "w") as ef:
-                rc, sec = shimrun.run(n_ranks, cmd, 256 << 20, timeout=900, env=env, stdout=subprocess.DEVNULL, stderr=ef)
+                rc, sec = shimrun.run(n_ranks, cmd, 256 << 20, timeout=300, env=env, stdout=subprocess.DEVNULL, stderr=ef)
             if failure(rc):
                 return None, failure(rc)
             walls.append(sec)
