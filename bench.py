@@ -346,7 +346,11 @@ def run_ours(args, cfg):
         out["cpu_baseline"] = {"value": None, "unit": "iter/s", "cores": 1, "kind": "reference",
                                "sample": "not run at this size (one reference iteration takes > 10 s); see the default config"}
     else:
-        out["cpu_baseline"] = cpu_baseline_block(cfg, wl, n_iter=int(os.environ.get("FRIES_BENCH_CPU_ITERS", "12")))
+        try:
+            out["cpu_baseline"] = cpu_baseline_block(cfg, wl, n_iter=int(os.environ.get("FRIES_BENCH_CPU_ITERS", "12")))
+        except Exception as exc:  # the GPU numbers above stand on their own: never lose the line to the CPU leg
+            out["cpu_baseline"] = {"value": None, "unit": "iter/s", "cores": 1, "kind": "reference",
+                                   "sample": f"reference run failed: {type(exc).__name__}: {exc}"[:300]}
     print(json.dumps(out), flush=True)
     vec.close()
     mol.close()
@@ -466,6 +470,13 @@ def reference_iter_seconds(cfg, sm, keys, vals, it_a, it_b, workdir, n_ranks=1):
 
 
 def reference_iter_seconds_best(cfg, sm, keys, vals, it_a, it_b):
+    try:
+        return _reference_iter_seconds_best(cfg, sm, keys, vals, it_a, it_b)
+    except Exception as exc:
+        return None, 0, f"reference run failed: {type(exc).__name__}: {exc}"[:300]
+
+
+def _reference_iter_seconds_best(cfg, sm, keys, vals, it_a, it_b):
     """the reference on all the host cores it can use (reference_rank_count ranks), falling back to one rank if the
     multi-process run fails; returns (seconds per iteration, ranks used, error)"""
     tried, best = [], None
