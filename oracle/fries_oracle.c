@@ -1434,6 +1434,256 @@ done:
     return ok;
 }
 
+/* apply_HBPP_piv heat_bathPP.cpp:1014-1419 (spin_parity = 0): the same five factors as apply_HBPP_sys, but every factor is
+ * multiplied out into a "long" vector (value x row of weights, one group per input), compressed by piv_comp_parallel
+ * (compress_utils.cpp:354-387) and collapsed again (collapse_long_ :994-1012).  The last collapse computes the sample's
+ * orbitals, total sampling weight and SIGNED matrix element (:1250-1415; cutoff 1e-12).  Draws: the mt19937 outputs the
+ * five piv_comp_parallel calls consume, in order. */
+typedef struct {
+    double *val;           /* short vector */
+    size_t *det1, *det2;
+    uint8_t (*orb1)[4], (*orb2)[4];
+    uint16_t *group;
+} piv_state;
+
+/* collapse_long_ :994-1012 with the transfer rule of stage `stage` (0..3) */
+static size_t piv_collapse(piv_state *p, const double *lng, size_t n_short, uint8_t *zeroed, int stage) {
+    size_t out = 0, li = 0;
+    /* the transfer may overwrite entries at positions <= the one being read (out <= short index), as in the reference */
+    for (size_t si = 0; si < n_short; si++) {
+        for (unsigned g = 0; g < p->group[si]; g++, li++) {
+            if (!zeroed[li]) {
+                p->val[out] = lng[li];
+                switch (stage) {
+                    case 0:
+                        p->det2[out] = p->det1[si];
+                        p->orb1[out][0] = (uint8_t)g;
+                        break;
+                    case 1:
+                        p->det1[out] = p->det2[si];
+                        p->orb2[out][0] = p->orb1[si][0];
+                        p->orb2[out][1] = (uint8_t)g;
+                        break;
+                    case 2: {
+                        int single = p->orb2[si][0] == 1;
+                        p->det2[out] = p->det1[si];
+                        p->orb1[out][0] = p->orb2[si][0];
+                        p->orb1[out][1] = p->orb2[si][1];
+                        p->orb1[out][2] = (uint8_t)g;
+                        if (single) p->orb1[out][3] = p->orb2[si][3];
+                        break;
+                    }
+                    default: {
+                        int single = p->orb1[si][0] == 1;
+                        p->det1[out] = p->det2[si];
+                        p->orb2[out][0] = p->orb1[si][0];
+                        p->orb2[out][1] = p->orb1[si][1];
+                        p->orb2[out][2] = p->orb1[si][2];
+                        p->orb2[out][3] = single ? p->orb1[si][3] : (uint8_t)g;
+                        break;
+                    }
+                }
+                out++;
+            }
+            zeroed[li] = 0;
+        }
+    }
+    return out;
+}
+
+size_t fo_mol_apply_hbpp_piv(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub,
+                             int new_hb, const uint32_t *draws, size_t *used, unsigned n_samp, size_t spawn_length,
+                             double *out_val, uint64_t *out_det, uint8_t *out_orbs) {
+    const unsigned ne = m->n_elec, M = m->n_orb;
+    size_t n_states = ne > M - ne / 2 ? ne : M - ne / 2;
+    if (n_states < m->max_n_symm) n_states = m->max_n_symm;
+    if (n_states < 2) n_states = 2;
+    const size_t L = spawn_length;
+    piv_state p;
+    p.val = (double *)calloc(L, sizeof(double));
+    p.det1 = (size_t *)calloc(L, sizeof(size_t));
+    p.det2 = (size_t *)calloc(L, sizeof(size_t));
+    p.orb1 = (uint8_t(*)[4])calloc(L, 4);
+    p.orb2 = (uint8_t(*)[4])calloc(L, 4);
+    p.group = (uint16_t *)calloc(L, sizeof(uint16_t));
+    double *lng = (double *)calloc(L * n_states, sizeof(double));
+    uint8_t *zeroed = (uint8_t *)calloc(L * n_states, 1);
+    uint8_t occ[65];
+    unsigned cnt[8][2];
+    size_t n_short = n, n_long;
+    for (size_t i = 0; i < n; i++) {
+        p.val[i] = vals[i];
+        p.det1[i] = i;
+    }
+    /* singles vs doubles :1046-1066 */
+    n_long = 0;
+    for (size_t i = 0; i < n_short; i++) {
+        double w = fabs(p.val[i]);
+        if (w > 0) {
+            lng[n_long++] = w * p_doub;
+            lng[n_long++] = w * (1 - p_doub);
+            p.group[i] = 2;
+        } else {
+            p.group[i] = 0;
+        }
+    }
+    fo_piv_comp(lng, n_long, n_samp, zeroed, draws, used);
+    n_short = piv_collapse(&p, lng, n_short, zeroed, 0);
+    /* first occupied orbital :1068-1100 */
+    n_long = 0;
+    for (size_t i = 0; i < n_short; i++) {
+        occ_list(m, keys[p.det2[i]], occ);
+        if (p.orb1[i][0] == 0) {
+            unsigned len = ne - (new_hb ? 1 : 0);
+            p.group[i] = (uint16_t)len;
+            double tot = o1_probs(m, lng + n_long, occ, new_hb);
+            for (unsigned j = 0; j < len; j++) lng[n_long + j] *= p.val[i] * (new_hb ? tot : 1);
+            n_long += len;
+        } else {
+            count_symm_virt(m, occ, cnt);
+            unsigned n_occ = count_sing_allowed(m, occ, cnt);
+            p.group[i] = (uint16_t)n_occ;
+            for (unsigned j = 0; j < n_occ; j++) lng[n_long + j] = p.val[i] / n_occ;
+            n_long += n_occ;
+        }
+    }
+    fo_piv_comp(lng, n_long, n_samp, zeroed, draws, used);
+    n_short = piv_collapse(&p, lng, n_short, zeroed, 1);
+    /* virtual of a single; second occupied orbital of a double :1102-1160 */
+    n_long = 0;
+    for (size_t i = 0; i < n_short; i++) {
+        if (p.orb2[i][1] >= ne) {
+            p.group[i] = 0;
+            continue;
+        }
+        occ_list(m, keys[p.det1[i]], occ);
+        if (p.orb2[i][0] == 0) {
+            double tot = 1;
+            unsigned n_o2;
+            if (new_hb) {
+                p.orb2[i][1]++;
+                n_o2 = p.orb2[i][1];
+                tot = o2_probs_half(m, lng + n_long, occ, p.orb2[i][1]);
+            } else {
+                n_o2 = ne;
+                o2_probs(m, lng + n_long, occ, p.orb2[i][1]);
+            }
+            for (unsigned j = 0; j < n_o2; j++) lng[n_long + j] *= tot * p.val[i];
+            p.group[i] = (uint16_t)n_o2;
+            n_long += n_o2;
+        } else {
+            count_symm_virt(m, occ, cnt);
+            unsigned n_virt = count_sing_virt(m, occ, cnt, &p.orb2[i][1]);
+            if (n_virt == 0) {
+                p.group[i] = 0;
+            } else {
+                p.group[i] = (uint16_t)n_virt;
+                p.orb2[i][3] = (uint8_t)n_virt;
+                for (unsigned j = 0; j < n_virt; j++) lng[n_long + j] = p.val[i] / n_virt;
+                n_long += n_virt;
+            }
+        }
+    }
+    fo_piv_comp(lng, n_long, n_samp, zeroed, draws, used);
+    n_short = piv_collapse(&p, lng, n_short, zeroed, 2);
+    /* first virtual orbital of a double :1162-1216 */
+    n_long = 0;
+    for (size_t i = 0; i < n_short; i++) {
+        uint8_t o2u1 = p.orb1[i][2];
+        if (p.orb1[i][0] == 0) {
+            if (o2u1 >= ne) {
+                p.group[i] = 0;
+                continue;
+            }
+            occ_list(m, keys[p.det2[i]], occ);
+            uint8_t o1_idx = p.orb1[i][1];
+            int o1_spin = o1_idx / (ne / 2), o2_spin = occ[o2u1] / M;
+            double tot = u1_probs(m, lng + n_long, occ[o1_idx], occ, new_hb && (o1_spin == o2_spin));
+            unsigned n_virt = M - ne / 2;
+            p.group[i] = (uint16_t)n_virt;
+            for (unsigned j = 0; j < n_virt; j++) lng[n_long + j] *= p.val[i] * (new_hb ? tot : 1);
+            n_long += n_virt;
+        } else {
+            p.group[i] = 1; /* :1190-1195 set 0 on an out-of-range index and then 1 unconditionally */
+            lng[n_long++] = p.val[i];
+        }
+    }
+    fo_piv_comp(lng, n_long, n_samp, zeroed, draws, used);
+    n_short = piv_collapse(&p, lng, n_short, zeroed, 3);
+    /* second virtual orbital of a double :1218-1246 */
+    n_long = 0;
+    for (size_t i = 0; i < n_short; i++) {
+        uint64_t det = keys[p.det1[i]];
+        uint8_t o1_idx = p.orb2[i][1];
+        if (p.orb2[i][0] == 0) {
+            occ_list(m, det, occ);
+            uint8_t u1 = (uint8_t)fo_find_nth_virt(occ, o1_idx / (ne / 2), ne, M, p.orb2[i][3]);
+            if (BIT(det, u1)) {
+                p.group[i] = 0;
+            } else {
+                p.orb2[i][3] = u1;
+                uint16_t n_probs;
+                double tot = new_hb ? u2_probs_half(m, lng + n_long, occ[o1_idx], occ[p.orb2[i][2]], u1, det, &n_probs)
+                                    : u2_probs(m, lng + n_long, occ[o1_idx], occ[p.orb2[i][2]], u1, &n_probs);
+                for (unsigned j = 0; j < n_probs; j++) lng[n_long + j] *= p.val[i] * (new_hb ? tot : 1);
+                p.group[i] = n_probs;
+                n_long += n_probs;
+            }
+        } else {
+            p.group[i] = 1;
+            lng[n_long++] = p.val[i];
+        }
+    }
+    fo_piv_comp(lng, n_long, n_samp, zeroed, draws, used);
+    /* last collapse with the samples' orbitals, weights and signed matrix elements :1248-1417 */
+    size_t ok = 0, li = 0;
+    for (size_t si = 0; si < n_short; si++) {
+        for (unsigned g = 0; g < p.group[si]; g++, li++) {
+            if (zeroed[li]) {
+                zeroed[li] = 0;
+                continue;
+            }
+            size_t d = p.det1[si];
+            uint64_t det = keys[d], new_det = det;
+            occ_list(m, det, occ);
+            uint8_t o1_idx = p.orb2[si][1], fin[4];
+            double tot, el;
+            if (p.orb2[si][0] == 0) {
+                uint8_t o1 = occ[o1_idx], o2 = occ[p.orb2[si][2]], u1 = p.orb2[si][3];
+                uint8_t u2s = m->symm[o1 % M] ^ m->symm[o2 % M] ^ m->symm[u1 % M];
+                uint8_t u2 = (uint8_t)(m->lookup[u2s][g + 1] + M * (o2 / M));
+                if (BIT(det, u2) || u1 == u2) continue;
+                if (u1 > u2) { uint8_t t = u1; u1 = u2; u2 = t; }
+                if (o1 > o2) { uint8_t t = o1; o1 = o2; o2 = t; }
+                fin[0] = o1; fin[1] = o2; fin[2] = u1; fin[3] = u2;
+                tot = new_hb ? unnorm_wt(m, fin) : norm_wt(m, fin, occ, det);
+                tot *= p_doub;
+                el = fo_mol_doub_el(m, fin);
+                el *= fo_doub_det_parity(&new_det, fin);
+            } else {
+                uint8_t o1 = occ[o1_idx];
+                uint8_t u1 = virt_from_idx(det, m->lookup[m->symm[o1 % M]], (uint8_t)(M * (o1 / M)), p.orb2[si][2]);
+                if (u1 == 255) continue;
+                fin[0] = o1; fin[1] = u1; fin[2] = fin[3] = 0;
+                count_symm_virt(m, occ, cnt);
+                unsigned n_occ = count_sing_allowed(m, occ, cnt);
+                tot = (1 - p_doub) / n_occ / p.orb2[si][3];
+                el = sing_el_occ(m, fin, occ);
+                el *= fo_sing_det_parity(&new_det, fin);
+            }
+            double v = lng[li] * el / tot;
+            if (fabs(v) > 1e-12) {
+                out_val[ok] = v;
+                out_det[ok] = d;
+                memcpy(out_orbs + 4 * ok, fin, 4);
+                ok++;
+            }
+        }
+    }
+    free(p.val); free(p.det1); free(p.det2); free(p.orb1); free(p.orb2); free(p.group); free(lng); free(zeroed);
+    return ok;
+}
+
 /* h_op_diag molecule.cpp:205-219 + h_op_offdiag :448-665 on a list; duplicates are not merged */
 size_t fo_mol_h_apply_list(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double id_fac,
                            double h_fac, uint64_t *out_keys, double *out_vals, size_t cap) {

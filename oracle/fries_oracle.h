@@ -91,6 +91,9 @@ double fo_mol_hb_wt(const fo_mol *m, int normalized, uint64_t key, const uint8_t
 size_t fo_mol_apply_hbpp_sys(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub,
                              int new_hb, const double *uniforms5, unsigned n_samp, size_t spawn_length,
                              double *out_val, uint64_t *out_det, uint8_t *out_orbs); /* heat_bathPP.cpp:686-992 */
+size_t fo_mol_apply_hbpp_piv(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub,
+                             int new_hb, const uint32_t *draws, size_t *used, unsigned n_samp, size_t spawn_length,
+                             double *out_val, uint64_t *out_det, uint8_t *out_orbs); /* heat_bathPP.cpp:1014-1419 */
 size_t fo_debug_hbpp_stage(const fo_mol *m, const uint64_t *keys, const double *vals, size_t n, double p_doub,
                            int new_hb, const double *uniforms5, unsigned n_samp, size_t spawn_length, int stage,
                            double *out_val, uint64_t *out_det, uint8_t *out_orbs, uint32_t *out_sub);

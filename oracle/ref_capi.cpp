@@ -476,6 +476,49 @@ size_t ref_mol_apply_hbpp_sys(void *h, const uint64_t *keys, const double *vals,
     return ns;
 }
 
+/* apply_HBPP_piv, FRIES/Hamiltonians/heat_bathPP.cpp:1014-1419, spin_parity = 0, with the real matrix-element
+ * functions.  mt19937(seed); *n_draws receives the number of generator outputs consumed. */
+size_t ref_mol_apply_hbpp_piv(void *h, const uint64_t *keys, const double *vals, size_t n, double p_doub, int new_hb,
+                              unsigned seed, unsigned n_samp, size_t spawn_length, double *out_val, uint64_t *out_det,
+                              uint8_t *out_orbs, size_t cap, size_t *n_draws) {
+    RefMol *m = (RefMol *)h;
+    unsigned ne = m->n_elec - m->n_frz;
+    unsigned n_bytes = CEILING(2 * m->n_orb, 8);
+    Matrix<uint8_t> all_orbs(n + 1, ne);
+    Matrix<uint8_t> all_dets(n + 1, n_bytes);
+    for (size_t i = 0; i < n; i++) {
+        key_to_bytes(keys[i], all_dets[i], n_bytes);
+        find_bits(all_dets[i], all_orbs[i], (uint8_t)n_bytes);
+    }
+    size_t n_states = ne > (m->n_orb - ne / 2) ? ne : m->n_orb - ne / 2;
+    if (n_states < m->symm_info->max_n_symm) n_states = m->symm_info->max_n_symm;
+    if (n_states < 2) n_states = 2;
+    HBCompressPiv comp(spawn_length, n_states);
+    for (size_t i = 0; i < n; i++) {
+        comp.vec1[i] = vals[i];
+        comp.det_indices1[i] = i;
+    }
+    comp.vec_len = n;
+    std::mt19937 mt(seed);
+    std::mt19937 before = mt;
+    unsigned tot_orb = m->tot_orb, n_frz = m->n_frz;
+    SymmERIs *eris = &m->eris;
+    Matrix<double> *hc = &m->hcore;
+    std::function<double(uint8_t *, uint8_t *)> sing_fn = [=](uint8_t *ex, uint8_t *occ) {
+        return sing_matr_el_nosgn(ex, occ, tot_orb, *eris, *hc, n_frz, ne);
+    };
+    std::function<double(uint8_t *)> doub_fn = [=](uint8_t *ex) { return doub_matr_el_nosgn(ex, tot_orb, *eris, n_frz); };
+    apply_HBPP_piv(all_orbs, all_dets, &comp, m->hb, m->symm_info, p_doub, new_hb != 0, mt, n_samp, sing_fn, doub_fn, 0);
+    if (n_draws) *n_draws = draws_between(before, mt, 12 * (size_t)n_samp + 64);
+    size_t ns = comp.vec_len;
+    for (size_t i = 0; i < ns && i < cap; i++) {
+        out_val[i] = comp.vec1[i];
+        out_det[i] = comp.det_indices2[i];
+        std::memcpy(out_orbs + 4 * i, comp.orb_indices1[i], 4);
+    }
+    return ns;
+}
+
 /* ---- a2/a3: DistVec add / perform_add / add_elements ------------------------------------------ */
 
 struct RefVec {

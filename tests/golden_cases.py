@@ -116,3 +116,7 @@ def piv_comp_inputs(case):
     seed, n, m = case
     rng = np.random.default_rng(300 + seed)
     return rng.standard_normal(n) * np.exp(3 * rng.standard_normal(n))
+
+
+# apply_HBPP_piv: (mol case, n_det, n_samp, new_hb, mt19937 seed), inputs as hbpp_inputs
+PIV_HBPP_CASES = [(("ne", 2, False), 1, 50, 1, 1), (("ne", 2, True), 300, 1000, 1, 2), (("h2o", 3, True), 1000, 1500, 0, 2)]

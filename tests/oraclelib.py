@@ -50,6 +50,7 @@ def lib():
             "fo_piv_budget": (None, [f64p, i, C.c_uint32, u32p, P(sz), u32p]),
             "fo_adjust_probs": (d, [f64p, sz, P(C.c_uint32), d, C.c_uint32, d, u8p]),
             "fo_piv_comp": (None, [f64p, sz, C.c_uint32, u8p, u32p, P(sz)]),
+            "fo_mol_apply_hbpp_piv": (sz, [vp, u64p, f64p, sz, d, i, u32p, P(sz), u, sz, f64p, u64p, u8p]),
             "fo_mol_create": (vp, [u, u, u, f64p, f64p, u8p]),
             "fo_mol_destroy": (None, [vp]),
             "fo_mol_packed_len": (sz, [vp]),
@@ -137,6 +138,18 @@ class OracleMol:
                                         np.ascontiguousarray(uniforms5, np.float64), n_samp, spawn_length, ov, od,
                                         oo.reshape(-1))
         return ov[:n].copy(), od[:n].copy(), oo[:n].copy()
+
+    def apply_hbpp_piv(self, keys, vals, p_doub, new_hb, draws, n_samp, spawn_length):
+        """heat_bathPP.cpp:1014-1419 -> (values, det indices, orbitals, draws consumed)"""
+        ov = np.zeros(spawn_length)
+        od = np.zeros(spawn_length, np.uint64)
+        oo = np.zeros((spawn_length, 4), np.uint8)
+        used = C.c_size_t(0)
+        n = lib().fo_mol_apply_hbpp_piv(self.h, np.ascontiguousarray(keys, np.uint64),
+                                        np.ascontiguousarray(vals, np.float64), len(keys), p_doub, int(new_hb),
+                                        np.ascontiguousarray(draws, np.uint32), C.byref(used), n_samp, spawn_length, ov, od,
+                                        oo.reshape(-1))
+        return ov[:n].copy(), od[:n].copy(), oo[:n].copy(), used.value
 
     def h_apply(self, keys, vals, id_fac, h_fac):
         """merged result of id_fac*v + h_fac*H*v as sorted (keys, vals)"""

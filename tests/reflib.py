@@ -86,6 +86,9 @@ def lib():
                                      C.POINTER(C.c_int)]
         L.ref_mol_hb_wt.restype = C.c_double
         L.ref_mol_hb_wt.argtypes = [C.c_void_p, C.c_int, C.c_uint64, u8p]
+        L.ref_mol_apply_hbpp_piv.restype = C.c_size_t
+        L.ref_mol_apply_hbpp_piv.argtypes = [C.c_void_p, u64p, f64p, C.c_size_t, C.c_double, C.c_int, C.c_uint, C.c_uint,
+                                             C.c_size_t, f64p, u64p, u8p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ref_mol_apply_hbpp_sys.restype = C.c_size_t
         L.ref_mol_apply_hbpp_sys.argtypes = [C.c_void_p, u64p, f64p, C.c_size_t, C.c_double, C.c_int, C.c_uint, C.c_uint,
                                              C.c_size_t, f64p, f64p, u64p, u8p, C.c_size_t]
@@ -173,6 +176,18 @@ class RefMol:
                                          np.ascontiguousarray(vals, np.float64), len(keys), p_doub, int(new_hb), seed,
                                          n_samp, spawn_length, uni, ov, od, oo.reshape(-1), cap)
         return uni, ov[:n].copy(), od[:n].copy(), oo[:n].copy()
+
+    def apply_hbpp_piv(self, keys, vals, p_doub, new_hb, seed, n_samp, spawn_length):
+        """apply_HBPP_piv with mt19937(seed) -> (values, det indices, orbitals, draws consumed)"""
+        cap = spawn_length
+        ov = np.zeros(cap)
+        od = np.zeros(cap, np.uint64)
+        oo = np.zeros((cap, 4), np.uint8)
+        used = C.c_size_t(0)
+        n = lib().ref_mol_apply_hbpp_piv(self.h, np.ascontiguousarray(keys, np.uint64),
+                                         np.ascontiguousarray(vals, np.float64), len(keys), p_doub, int(new_hb), seed,
+                                         n_samp, spawn_length, ov, od, oo.reshape(-1), cap, C.byref(used))
+        return ov[:n].copy(), od[:n].copy(), oo[:n].copy(), used.value
 
     def h_apply(self, keys, vals, id_fac, h_fac, max_dets, proc_scr, vec_scr):
         ok = np.zeros(max_dets, np.uint64)

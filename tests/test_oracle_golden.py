@@ -8,7 +8,7 @@ import pytest
 import oraclelib
 from fries_b200.synth import SynthMol
 from golden_cases import (COMP_SUB_CASES, HBPP_CASES, MOL_CASES, PIV_ADJUST_CASES, PIV_BUDGET_CASES, PIV_COMP_CASES,
-                          PIV_SAMP_CASES, VEC_COMP_CASES, comp_sub_inputs, hbpp_inputs, mol_keys, piv_adjust_inputs,
+                          PIV_HBPP_CASES, PIV_SAMP_CASES, VEC_COMP_CASES, comp_sub_inputs, hbpp_inputs, mol_keys, piv_adjust_inputs,
                           piv_budget_inputs, piv_comp_inputs, piv_samp_inputs, vec_values)
 
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fries_golden.npz"))
@@ -112,3 +112,15 @@ def test_piv_comp_parallel_golden(i):
     nz = np.flatnonzero(ov)
     assert used == GP[f"pc{i}_used"] and np.array_equal(nz, GP[f"pc{i}_idx"]) and np.array_equal(ov[nz], GP[f"pc{i}_val"])
     assert np.array_equal(ok == 1, ov == 0)
+
+
+@pytest.mark.parametrize("i", range(len(PIV_HBPP_CASES)))
+def test_apply_hbpp_piv_golden(i):
+    case = PIV_HBPP_CASES[i]
+    sm = SynthMol(*case[0])
+    keys, vals = hbpp_inputs(sm, case)
+    ov, od, oo, used = oraclelib.OracleMol(sm).apply_hbpp_piv(keys, vals, 0.97, case[3],
+                                                             oraclelib.mt19937(case[4], 12 * case[2] + 64), case[2],
+                                                             4 * case[2] + 4 * case[1])
+    assert used == GP[f"ph{i}_used"] and np.array_equal(od, GP[f"ph{i}_d"]) and np.array_equal(oo, GP[f"ph{i}_o"])
+    assert np.allclose(ov, GP[f"ph{i}_v"], rtol=1e-12, atol=0)

@@ -110,3 +110,45 @@ def test_piv_comp_parallel_matches_reference(seed, n, m):
     assert oused == rused
     assert np.array_equal(ok, rk) and np.array_equal(ov, rv)
     assert (ov != 0).sum() <= m and np.array_equal(ok == 1, ov == 0)
+
+
+# ---- apply_HBPP_piv (heat_bathPP.cpp:1014-1419): the pivotal twin of apply_HBPP_sys --------------------------------
+@needs_ref
+@pytest.mark.parametrize("case,new_hb,n_det,n_samp", [(("ne", 2, False), 1, 1, 50), (("ne", 2, False), 0, 300, 1000),
+                                                       (("ne", 2, True), 1, 300, 1000), (("n2", 7, True), 1, 2000, 4000),
+                                                       (("h2o", 3, True), 0, 2000, 3000),
+                                                       (((8, 6, 0, [0, 0, 1, 2, 3, 0, 1, 2]), 4, True), 1, 40, 3000)])
+def test_apply_hbpp_piv_matches_reference(case, new_hb, n_det, n_samp):
+    from fries_b200.synth import SynthMol
+    from golden_cases import make_values
+    sm = SynthMol(*case)
+    om, rm = ol.OracleMol(sm), reflib.RefMol(sm)
+    rng = np.random.default_rng(n_det + new_hb)
+    keys = np.concatenate([[sm.hf], sm.random_dets(n_det - 1, rng, 0)]).astype(np.uint64) if n_det > 1 else \
+        np.array([sm.hf], np.uint64)
+    vals = make_values(rng, n_det, "fri")
+    vals[0] = 100.0
+    cap = 4 * n_samp + 4 * n_det
+    for seed in (1, 2):
+        rv, rd, ro, rused = rm.apply_hbpp_piv(keys, vals, 0.97, new_hb, seed, n_samp, cap)
+        ov, od, oo, oused = om.apply_hbpp_piv(keys, vals, 0.97, new_hb, ol.mt19937(seed, 12 * n_samp + 64), n_samp, cap)
+        assert oused == rused and len(ov) == len(rv) > 0
+        assert np.array_equal(od, rd) and np.array_equal(oo, ro)
+        assert np.allclose(ov, rv, rtol=1e-12, atol=0)
+        print(f"apply_hbpp_piv {case[0]} new_hb={new_hb}: {len(rv)} samples, {rused} draws")
+
+
+@needs_ref
+def test_apply_hbpp_piv_exact_limit_equals_sys():
+    """tests/test_hamiltonian.cpp:507-519: with a budget above the number of excitations the pivotal and the systematic
+    pipeline return the same tuples (here also the same values up to the sign the pivotal variant includes)"""
+    from fries_b200.synth import SynthMol
+    sm = SynthMol("ne", 2, True)
+    om = ol.OracleMol(sm)
+    hf = np.array([sm.hf], np.uint64)
+    n_ex = len(om.sing_ex(int(sm.hf))) + len(om.doub_ex(int(sm.hf)))
+    sv, sd, so = om.apply_hbpp_sys(hf, np.ones(1), 0.95, 1, np.full(5, 0.5), 8 * n_ex, 16 * n_ex)
+    pv, pd, po, used = om.apply_hbpp_piv(hf, np.ones(1), 0.95, 1, ol.mt19937(0, 64), 8 * n_ex, 16 * n_ex)
+    assert used == 0 or used % 2 == 0
+    assert np.array_equal(po, so) and len(pv) == n_ex
+    assert np.allclose(np.abs(pv), np.abs(sv), rtol=1e-12, atol=0)
