@@ -19,7 +19,8 @@ import time
 HDR = 4096
 
 
-def run(n, cmd, slot_bytes=64 << 20, timeout=None, env=None, all_output=False, stdout=None, stderr=None, stamp=None):
+def run(n, cmd, slot_bytes=64 << 20, timeout=None, env=None, all_output=False, stdout=None, stderr=None, stamp=None,
+        grace=3.0):
     """returns (exit code of rank 0 or the first failing rank, wall seconds).  stamp: a compiled regex with one group;
     the ranks' stdout then goes through one pseudo-terminal (so that it is line buffered) and the arrival time of every
     matching line is appended to the list stamp_out as (group(1), perf_counter) -- pass it as run.stamps afterwards."""
@@ -72,6 +73,7 @@ def run(n, cmd, slot_bytes=64 << 20, timeout=None, env=None, all_output=False, s
                 wait = 0
 
         rc = None
+        failed_at = None
         while rc is None:
             if master is not None:
                 drain(0.005)
@@ -79,7 +81,14 @@ def run(n, cmd, slot_bytes=64 << 20, timeout=None, env=None, all_output=False, s
             if all(c is not None for c in codes):
                 rc = next((c for c in codes if c), 0)
             elif any(c not in (None, 0) for c in codes):
-                rc = next(c for c in codes if c not in (None, 0))
+                # a rank failed: the others may be about to finish too (e.g. a test binary that fails on every rank);
+                # give them a moment before they are killed -- if they wait in a barrier they will never finish
+                if failed_at is None:
+                    failed_at = time.perf_counter()
+                if time.perf_counter() - failed_at > grace:
+                    rc = next(c for c in codes if c not in (None, 0))
+                elif master is None:
+                    time.sleep(0.01)
             elif timeout is not None and time.perf_counter() - t0 > timeout:
                 rc = 124
             elif master is None:
