@@ -86,6 +86,7 @@ def _load():
         "fries_mol_hb_rows": (i, [vp, i, vp, vp, sz, vp, vp, vp]),
         "fries_mol_hb_wt": (i, [vp, i, vp, vp, sz, vp]),
         "fries_apply_hbpp_sys": (i, [vp, vp, vp, sz, d, i, vp, u, sz, vp, vp, vp, sz, P(sz)]),
+        "fries_apply_hbpp_piv": (i, [vp, vp, vp, sz, d, i, vp, sz, P(sz), u, sz, vp, vp, vp, sz, P(sz)]),
         "fries_debug_hbpp_stage": (i, [vp, vp, vp, sz, d, i, vp, u, sz, i, vp, vp, vp, vp, P(sz)]),
         "fries_hbpp_states": (i, [vp, vp]),
         "fries_hbpp_round_stamps": (i, [vp, i, vp]),

@@ -237,6 +237,18 @@ class Mol:
         check(lib.fries_mol_hb_wt(self.h, int(normalized), ptr(k), ptr(o), k.size, ptr(out)))
         return out
 
+    def apply_hbpp_piv(self, keys, vals, p_doub, new_hb, draws, n_samp, spawn_cap):
+        """heat_bathPP.cpp:1014-1419 -> (values, det indices, orbitals[n][4], draws consumed)"""
+        k, v, dr = arr(keys, np.uint64), arr(vals, np.float64), arr(draws, np.uint32)
+        ov = np.zeros(spawn_cap)
+        od = np.zeros(spawn_cap, np.uint64)
+        oo = np.zeros((spawn_cap, 4), np.uint8)
+        n_out, used = C.c_size_t(0), C.c_size_t(0)
+        check(lib.fries_apply_hbpp_piv(self.h, ptr(k), ptr(v), k.size, p_doub, int(new_hb), ptr(dr), dr.size, C.byref(used),
+                                       n_samp, spawn_cap, ptr(ov), ptr(od), ptr(oo), spawn_cap, C.byref(n_out)))
+        n = n_out.value
+        return ov[:n].copy(), od[:n].copy(), oo[:n].copy(), used.value
+
     def apply_hbpp_sys(self, keys, vals, p_doub, new_hb, uniforms5, n_samp, spawn_cap):
         """apply_HBPP_sys heat_bathPP.cpp:686-992 -> (vals, parent index, orbs[n][4])"""
         k, v, u = arr(keys, np.uint64), arr(vals, np.float64), arr(uniforms5, np.float64)

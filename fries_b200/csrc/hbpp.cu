@@ -251,7 +251,8 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
                      unsigned long long in_cap, const double *__restrict__ pv, const uint32_t *__restrict__ pw,
                      const uint32_t *__restrict__ ps, const uint32_t *__restrict__ pdet,
                      const uint32_t *__restrict__ ppath, double p_doub, int new_hb, double *__restrict__ fin_val,
-                     uint32_t *__restrict__ fin_det, uint32_t *__restrict__ fin_orbs, HbSpawnArgs sp, CompState *st) {
+                     uint32_t *__restrict__ fin_det, uint32_t *__restrict__ fin_orbs, HbSpawnArgs sp, CompState *st,
+                     double cutoff) {
     MolView m = mol_stage_shared(gm, fr_dyn_smem);
     __shared__ uint32_t s_pscr[64];
     if (sp.n_ranks > 1) {
@@ -307,7 +308,7 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
                     tot = hb_norm_wt(m, orbs, occ, key);
                 }
                 el = mol_doub_el(m, orbs) * pv[i] / tot / p_doub;
-                if (fabs(el) > 1e-9)
+                if (fabs(el) > cutoff)
                     el *= fr_doub_parity(key, o1, o2, u1, u2);
                 else
                     el = 0;
@@ -321,7 +322,7 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
                 unsigned n_occ = mol_count_sing_allowed_bits(m, om.a, om.b);
                 el = mol_sing_el_bits(m, o1, u1, om.a, om.b);
                 el *= pv[i] / (1 - p_doub) * n_occ * p3;
-                if (fabs(el) > 1e-9)
+                if (fabs(el) > cutoff)
                     el *= fr_sing_parity(key, o1, u1);
                 else
                     el = 0;
@@ -520,7 +521,7 @@ int fries_hbpp_stages_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys
 }
 
 int fries_hbpp_finalize_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, double p_doub, int new_hb,
-                            const HbSpawnArgs *spawn) {
+                            const HbSpawnArgs *spawn, double cutoff) {
     fries_ctx *c = hb->ctx;
     HbSpawnArgs sp{nullptr, 0, 0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0, {nullptr}, 0};
     if (spawn) sp = *spawn;
@@ -531,7 +532,7 @@ int fries_hbpp_finalize_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_ke
     hbpp_finalize_kernel<<<grid, 256, smem, c->stream>>>(mol->view, d_keys, &hb->st.p[4].n_out,
                                                          (unsigned long long)hb->cap, hb->oval[0].p, hb->owidx[0].p,
                                                          hb->osub[0].p, hb->det[0].p, hb->path[0].p, p_doub, new_hb,
-                                                         hb->fin_val.p, hb->fin_det.p, hb->fin_orbs.p, sp, hb->st.p + 5);
+                                                         hb->fin_val.p, hb->fin_det.p, hb->fin_orbs.p, sp, hb->st.p + 5, cutoff);
     c->launch_count++;
     CUDA_TRY(cudaGetLastError());
     return FRIES_OK;
@@ -625,6 +626,275 @@ extern "C" int fries_apply_hbpp_sys(fries_mol *mol, const uint64_t *h_keys, cons
     fries_hbpp_destroy(hb);
     if (k > out_cap) {
         fries_set_error("fries_apply_hbpp_sys: %zu samples, output buffers hold %zu", k, out_cap);
+        return FRIES_ERR_CAPACITY;
+    }
+    return FRIES_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// apply_HBPP_piv (heat_bathPP.cpp:1014-1419, spin_parity = 0): the pivotal twin of apply_HBPP_sys.  Every factor is
+// multiplied out into a "long" vector -- one group of entries per input: value / n_div for the uniform rows, value x
+// weight_j for the explicit ones, streamed by the same providers as the systematic stages --, compressed in place by
+// piv_comp_parallel (piv.cu) and collapsed into the next stage's input list (collapse_long_ :994-1012).  The outputs of
+// a stage have the systematic pipeline's format (value, input index, sub index), so the stage providers and the
+// finalize kernel are shared.  Plain launches and a one-CTA scan: this is the API-completeness path, not the hot one.
+// ---------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256)
+hbpp_piv_prep_kernel(MolView gm, HbStageIO io, double *veff, uint32_t *ndiv, uint8_t *nsub, double *rinv, uint32_t *gsize) {
+    HbProvider<S> prov;
+    prov.m = mol_stage_shared(gm, fr_dyn_smem);
+    prov.io = io;
+    const size_t n = prov.count(), stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v, ri, wmax;
+        uint32_t nd, ns;
+        prov.prep(i, v, nd, ns, ri, wmax);
+        if (ns > FRIES_MAX_SUB) ns = FRIES_MAX_SUB;
+        veff[i] = v;
+        ndiv[i] = nd;
+        nsub[i] = (uint8_t)ns;
+        rinv[i] = ri;
+        gsize[i] = nd > 0 ? nd : ns;
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256)
+hbpp_piv_fill_kernel(MolView gm, HbStageIO io, const double *veff, const uint32_t *ndiv, const uint8_t *nsub,
+                     const double *rinv, const unsigned long long *goff, double *lng) {
+    HbProvider<S> prov;
+    prov.m = mol_stage_shared(gm, fr_dyn_smem);
+    prov.io = io;
+    const size_t n = prov.count(), stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = veff[i];
+        const uint32_t nd = ndiv[i], ns = nsub[i];
+        double *dst = lng + goff[i];
+        if (nd > 0) {
+            const double piece = v / nd;
+            for (uint32_t j = 0; j < nd; j++) dst[j] = piece;
+        } else {
+            for (uint32_t j = 0; j < ns; j++) dst[j] = 0.0;
+            prov.visit(i, rinv[i], [&](unsigned j, double w) {
+                if (j < ns) dst[j] = v * w;
+            });
+        }
+    }
+}
+
+// exclusive prefix of `in[0 .. n)` (n on the device) into out, total to *tot; one CTA of 1024 threads
+__global__ void __launch_bounds__(1024)
+hbpp_piv_scan_kernel(const uint32_t *in, const unsigned long long *n_ptr, unsigned long long n_cap,
+                     unsigned long long *out, unsigned long long *tot) {
+    __shared__ double sh_d[34];
+    __shared__ unsigned long long sh_c[34];
+    unsigned long long n = *n_ptr;
+    if (n > n_cap) n = n_cap;
+    unsigned long long carry = 0;
+    for (unsigned long long base = 0; base < n; base += blockDim.x) {
+        unsigned long long i = base + threadIdx.x;
+        unsigned long long c = i < n ? in[i] : 0ull, ec, tc;
+        double ex, t;
+        block_excl_scan(0.0, c, ex, ec, t, tc, sh_d, sh_c);
+        if (i < n) out[i] = carry + ec;
+        carry += tc;
+    }
+    if (threadIdx.x == 0) *tot = carry;
+}
+
+// survivors per group (zeroed flag 0), then -- after the scan -- the next stage's input list
+__global__ void __launch_bounds__(256)
+hbpp_piv_count_kernel(const unsigned long long *n_ptr, unsigned long long n_cap, const uint32_t *gsize,
+                      const unsigned long long *goff, const uint8_t *zeroed, uint32_t *cnt) {
+    unsigned long long n = *n_ptr;
+    if (n > n_cap) n = n_cap;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t *z = zeroed + goff[i];
+        uint32_t c = 0;
+        for (uint32_t j = 0; j < gsize[i]; j++) c += z[j] ? 0u : 1u;
+        cnt[i] = c;
+    }
+}
+__global__ void __launch_bounds__(256)
+hbpp_piv_collapse_kernel(const unsigned long long *n_ptr, unsigned long long n_cap, const uint32_t *gsize,
+                         const unsigned long long *goff, const uint8_t *zeroed, const double *lng,
+                         const unsigned long long *ooff, unsigned long long out_cap, double *out_val, uint32_t *out_widx,
+                         uint32_t *out_sub) {
+    unsigned long long n = *n_ptr;
+    if (n > n_cap) n = n_cap;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long b = goff[i];
+        unsigned long long o = ooff[i];
+        for (uint32_t j = 0; j < gsize[i]; j++) {
+            if (zeroed[b + j]) continue;
+            if (o < out_cap) {
+                out_val[o] = lng[b + j];
+                out_widx[o] = (uint32_t)i;
+                out_sub[o] = j;
+            }
+            o++;
+        }
+    }
+}
+__global__ void hbpp_piv_set_nout_kernel(CompState *st, const unsigned long long *tot, unsigned long long cap) {
+    unsigned long long t = *tot;
+    st->n_out = t < cap ? t : cap;
+    st->overflow = t > cap ? t - cap : 0;
+}
+
+template <int S>
+static int piv_stage(fries_hbpp *hb, fries_mol *mol, HbStageIO &io, int o, double *lng, uint8_t *zeroed, size_t long_cap,
+                     uint32_t *gsize, unsigned long long *goff, uint32_t *cnt, unsigned long long *ooff,
+                     unsigned long long *tot2, unsigned n_samp, const uint32_t *h_draws, size_t n_draws, size_t *used) {
+    fries_ctx *c = hb->ctx;
+    const size_t smem = (size_t)mol->view.d.blob_doubles * 8;
+    const int grid = c->sm_count * 4;
+    const unsigned long long cap = hb->cap;
+    hbpp_piv_prep_kernel<S><<<grid, 256, smem, c->stream>>>(mol->view, io, hb->veff.p, hb->ndiv.p, hb->nsub.p, hb->rinv.p, gsize);
+    hbpp_piv_scan_kernel<<<1, 1024, 0, c->stream>>>(gsize, io.n_in, cap, goff, tot2);
+    c->launch_count += 2;
+    unsigned long long n_long = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_long, tot2, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaGetLastError());
+    FRIES_REQUIRE(n_long <= long_cap, "fries_apply_hbpp_piv: stage %d expands to %llu entries, the scratch holds %zu", S,
+                  n_long, long_cap);
+    if (n_long == 0) {  // no input left (every earlier sample was dropped): an empty stage
+        CUDA_TRY(cudaMemsetAsync(tot2 + 1, 0, 8, c->stream));
+        hbpp_piv_set_nout_kernel<<<1, 1, 0, c->stream>>>(hb->st.p + S, tot2 + 1, cap);
+        c->launch_count++;
+        CUDA_TRY(cudaGetLastError());
+        return FRIES_OK;
+    }
+    hbpp_piv_fill_kernel<S><<<grid, 256, smem, c->stream>>>(mol->view, io, hb->veff.p, hb->ndiv.p, hb->nsub.p, hb->rinv.p, goff, lng);
+    c->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    FRIES_TRY(fries_piv_comp_resident(c, lng, (size_t)n_long, n_samp, zeroed, h_draws, n_draws, used));
+    hbpp_piv_count_kernel<<<grid, 256, 0, c->stream>>>(io.n_in, cap, gsize, goff, zeroed, cnt);
+    hbpp_piv_scan_kernel<<<1, 1024, 0, c->stream>>>(cnt, io.n_in, cap, ooff, tot2 + 1);
+    hbpp_piv_collapse_kernel<<<grid, 256, 0, c->stream>>>(io.n_in, cap, gsize, goff, zeroed, lng, ooff, cap, hb->oval[o].p,
+                                                          hb->owidx[o].p, hb->osub[o].p);
+    hbpp_piv_set_nout_kernel<<<1, 1, 0, c->stream>>>(hb->st.p + S, tot2 + 1, cap);
+    c->launch_count += 4;
+    CUDA_TRY(cudaGetLastError());
+    return FRIES_OK;
+}
+
+extern "C" int fries_apply_hbpp_piv(fries_mol *mol, const uint64_t *h_keys, const double *h_vals, size_t n, double p_doub,
+                                    int new_hb, const uint32_t *h_draws, size_t n_draws, size_t *n_draws_used,
+                                    unsigned n_samp, size_t spawn_cap, double *h_out_val, uint64_t *h_out_det,
+                                    uint8_t *h_out_orbs, size_t out_cap, size_t *n_out) {
+    FRIES_REQUIRE(mol && h_draws && n_out && (n == 0 || (h_keys && h_vals)), "fries_apply_hbpp_piv: NULL argument");
+    FRIES_REQUIRE(n <= spawn_cap, "fries_apply_hbpp_piv: %zu inputs exceed the scratch capacity %zu", n, spawn_cap);
+    fries_ctx *c = mol->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    *n_out = 0;
+    if (n_draws_used) *n_draws_used = 0;
+    if (n == 0) return FRIES_OK;
+    const MolDims &d = mol->view.d;
+    uint64_t half = (1ull << d.n_orb) - 1;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t k = h_keys[i];
+        FRIES_REQUIRE((k >> (2 * d.n_orb)) == 0 && (unsigned)__builtin_popcountll(k & half) == d.n_elec / 2 &&
+                          (unsigned)__builtin_popcountll(k >> d.n_orb) == d.n_elec / 2,
+                      "fries_apply_hbpp_piv: determinant %zu has the wrong electron count", i);
+    }
+    size_t n_states = d.n_elec > d.n_orb - d.n_elec / 2 ? d.n_elec : d.n_orb - d.n_elec / 2;
+    if (n_states < d.max_n_symm) n_states = d.max_n_symm;
+    if (n_states < 2) n_states = 2;
+    const size_t long_cap = spawn_cap * n_states;  // HBCompressPiv::long_vec (heat_bathPP.hpp:303-310)
+    struct Guard {
+        fries_hbpp *hb = nullptr;
+        ~Guard() {
+            if (hb) fries_hbpp_destroy(hb);
+        }
+    } g;
+    FRIES_TRY(fries_hbpp_alloc(c, spawn_cap, &g.hb));
+    fries_hbpp *hb = g.hb;
+    DevBuf<uint64_t> keys;
+    DevBuf<double> vals, lng;
+    DevBuf<uint8_t> zeroed;
+    DevBuf<uint32_t> gsize, cnt;
+    DevBuf<unsigned long long> goff, ooff, tot2;
+    FRIES_TRY(keys.alloc(n));
+    FRIES_TRY(vals.alloc(n));
+    FRIES_TRY(lng.alloc(long_cap));
+    FRIES_TRY(zeroed.alloc(long_cap));
+    FRIES_TRY(gsize.alloc(spawn_cap));
+    FRIES_TRY(cnt.alloc(spawn_cap));
+    FRIES_TRY(goff.alloc(spawn_cap));
+    FRIES_TRY(ooff.alloc(spawn_cap));
+    FRIES_TRY(tot2.alloc(2));
+    unsigned long long n64 = n;
+    CUDA_TRY(cudaMemcpyAsync(keys.p, h_keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(vals.p, h_vals, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(hb->n_scalar.p, &n64, 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(hb->st.p, 0, 8 * sizeof(CompState), c->stream));
+    size_t used = 0;
+    for (int s = 0; s < 5; s++) {
+        int o = s & 1, p = o ^ 1;
+        HbStageIO io;
+        io.keys = keys.p;
+        io.vals = vals.p;
+        io.n_in = s == 0 ? hb->n_scalar.p : &hb->st.p[s - 1].n_out;
+        io.pv = hb->oval[p].p;
+        io.pw = hb->owidx[p].p;
+        io.ps = hb->osub[p].p;
+        io.pdet = hb->det[p].p;
+        io.ppath = hb->path[p].p;
+        io.det = hb->det[o].p;
+        io.path = hb->path[o].p;
+        io.p_doub = p_doub;
+        io.new_hb = new_hb;
+        io.in_cap = hb->cap;
+#define PIV_STAGE(S)                                                                                                       \
+    FRIES_TRY(piv_stage<S>(hb, mol, io, o, lng.p, zeroed.p, long_cap, gsize.p, goff.p, cnt.p, ooff.p, tot2.p, n_samp, h_draws, \
+                           n_draws, &used))
+        switch (s) {
+            case 0: PIV_STAGE(0); break;
+            case 1: PIV_STAGE(1); break;
+            case 2: PIV_STAGE(2); break;
+            case 3: PIV_STAGE(3); break;
+            default: PIV_STAGE(4); break;
+        }
+#undef PIV_STAGE
+    }
+    FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, keys.p, p_doub, new_hb, nullptr, 1e-12));  // cutoff of :1409
+    CompState st[6];
+    CUDA_TRY(cudaMemcpyAsync(st, hb->st.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < 5; s++)
+        if (st[s].overflow) {
+            fries_set_error("fries_apply_hbpp_piv: stage %d produced %llu samples beyond spawn_cap %zu", s, st[s].overflow,
+                            spawn_cap);
+            return FRIES_ERR_CAPACITY;
+        }
+    size_t m = (size_t)st[5].n_in;
+    std::vector<double> v(m ? m : 1);
+    std::vector<uint32_t> dd(m ? m : 1), oo(m ? m : 1);
+    if (m) {
+        CUDA_TRY(cudaMemcpyAsync(v.data(), hb->fin_val.p, m * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(dd.data(), hb->fin_det.p, m * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(oo.data(), hb->fin_orbs.p, m * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    size_t k = 0;
+    for (size_t i = 0; i < m; i++) {
+        if (v[i] == 0) continue;
+        if (k < out_cap) {
+            h_out_val[k] = v[i];
+            h_out_det[k] = dd[i];
+            memcpy(h_out_orbs + 4 * k, &oo[i], 4);
+        }
+        k++;
+    }
+    *n_out = k;
+    if (n_draws_used) *n_draws_used = used;
+    if (k > out_cap) {
+        fries_set_error("fries_apply_hbpp_piv: %zu samples, output buffers hold %zu", k, out_cap);
         return FRIES_ERR_CAPACITY;
     }
     return FRIES_OK;

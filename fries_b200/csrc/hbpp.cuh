@@ -84,5 +84,10 @@ struct HbSpawnArgs {
     uint64_t *peer_win[FR_MAX_RANKS];
     int rank;
 };
+// cutoff: samples with |value| at or below it are dropped (1e-9 in apply_HBPP_sys :960,986; 1e-12 in apply_HBPP_piv)
 int fries_hbpp_finalize_dev(fries_hbpp *hb, fries_mol *mol, const uint64_t *d_keys, double p_doub, int new_hb,
-                            const HbSpawnArgs *spawn);
+                            const HbSpawnArgs *spawn, double cutoff = 1e-9);
+
+// piv.cu: piv_comp_parallel (single rank) in place on a resident vector; see there
+int fries_piv_comp_resident(fries_ctx *c, double *d_vals, size_t n, uint32_t compress_size, uint8_t *d_keep,
+                            const uint32_t *h_draws, size_t n_draws, size_t *used);

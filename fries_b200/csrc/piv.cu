@@ -429,11 +429,60 @@ extern "C" int fries_piv_budget(const double *loc_norms, int n_ranks, uint32_t n
     }
     if (tot < n_samp) {
         FRIES_REQUIRE(h_draws, "fries_piv_budget: draws needed");
-        piv_samp_host(wt, glob * (n_samp - tot) / n_samp, n_samp - tot, h_draws, used);
+        if (!(glob > 0)) {
+            // nothing left to sample on any rank: the reference's sweep (unit = 0) still steps over one rank per unit and
+            // draws twice each time (compress_utils.cpp:420-505); no budget changes
+            used = 2 * (size_t)((uint32_t)n_ranks < n_samp - tot ? (uint32_t)n_ranks : n_samp - tot);
+        } else
+            piv_samp_host(wt, glob * (n_samp - tot) / n_samp, n_samp - tot, h_draws, used);
         for (int p = 0; p < n_ranks; p++)
             if (wt[p] > 0) budgets[p]++;
     }
     if (n_draws_used) *n_draws_used = used;
+    return FRIES_OK;
+}
+
+// piv_comp_parallel (single rank) on a RESIDENT vector: find_preserve, budget, adjust_probs, pivotal sampling in place;
+// d_keep out: 1 = zeroed element.  h_draws[n_draws]: the caller's generator outputs, *used is advanced.  Host round
+// trips: the budget left by find_preserve and the number of sampling units.  Used by fries_apply_hbpp_piv (hbpp.cu).
+int fries_piv_comp_resident(fries_ctx *c, double *d_vals, size_t n, uint32_t compress_size, uint8_t *d_keep,
+                            const uint32_t *h_draws, size_t n_draws, size_t *used) {
+    FRIES_REQUIRE(n < 0xfffffff0ull, "pivotal compression: at most 2^32 - 16 elements");
+    int grid = piv_grid_size(c);
+    DevBuf<uint32_t> draws;
+    PivWork w;
+    FRIES_TRY(draws.alloc(2 * (size_t)compress_size + 2));
+    FRIES_TRY(w.alloc(n, compress_size));
+    PivScratch s;
+    FRIES_TRY(piv_scratch(c, grid, s));
+    CUDA_TRY(cudaMemsetAsync(s.st, 0, sizeof(CompState), c->stream));
+    FRIES_TRY(fries_find_preserve_launch(c, d_vals, n, nullptr, compress_size, d_keep, s.st, s.pd, s.pc, 0, nullptr));
+    CompState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, s.st, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const unsigned n_samp = st.n_samp_left;
+    const double loc = st.loc_norm;
+    uint32_t loc_samp = 0;
+    const double *d_par = nullptr;
+    if (n_samp != 0) {
+        size_t bu = 0;
+        FRIES_REQUIRE(*used + 2 <= n_draws, "pivotal compression: out of draws");
+        FRIES_TRY(fries_piv_budget(&loc, 1, n_samp, h_draws + *used, &bu, &loc_samp));
+        *used += bu;
+        double exp_loc = n_samp * loc / loc;
+        if (exp_loc > 0) {
+            FRIES_TRY(piv_adjust_launch(c, d_vals, n, d_keep, loc_samp, exp_loc, n_samp, loc, s, grid, s.par));
+            d_par = s.par;
+        }
+    }
+    FRIES_REQUIRE(*used + 2 * (size_t)loc_samp <= n_draws, "pivotal compression: out of draws (2 per sample)");
+    if (loc_samp)
+        CUDA_TRY(cudaMemcpyAsync(draws.p, h_draws + *used, 8 * (size_t)loc_samp, cudaMemcpyHostToDevice, c->stream));
+    FRIES_TRY(piv_samp_launch(c, d_vals, n, d_keep, 0.0, loc_samp, d_par, draws.p, w.view(), s, grid));
+    PivResult r;
+    CUDA_TRY(cudaMemcpyAsync(&r, s.res, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *used += 2 * (size_t)r.n_units;
     return FRIES_OK;
 }
 

@@ -182,6 +182,14 @@ int fries_apply_hbpp_sys(fries_mol *mol, const uint64_t *h_keys, const double *h
                          int new_hb, const double *h_uniforms5, unsigned n_samp, size_t spawn_cap, double *h_out_val,
                          uint64_t *h_out_det, uint8_t *h_out_orbs, size_t out_cap, size_t *n_out);
 
+/* apply_HBPP_piv FRIES/Hamiltonians/heat_bathPP.cpp:1014-1419 (spin_parity = 0): the pivotal twin of
+ * fries_apply_hbpp_sys.  h_draws: the caller's next mt19937 outputs, consumed by the five piv_comp_parallel calls
+ * (at most about 2 * (n_samp + 1) each); outputs as fries_apply_hbpp_sys, values carry the excitation's sign. */
+int fries_apply_hbpp_piv(fries_mol *mol, const uint64_t *h_keys, const double *h_vals, size_t n, double p_doub,
+                         int new_hb, const uint32_t *h_draws, size_t n_draws, size_t *n_draws_used, unsigned n_samp,
+                         size_t spawn_cap, double *h_out_val, uint64_t *h_out_det, uint8_t *h_out_orbs, size_t out_cap,
+                         size_t *n_out);
+
 /* ---- a2/a3: the determinant store ---------------------------------------------------------------------
  * DistVec<double> ctor FRIES/vec_utils.hpp:154-198: capacity, n_bits (= 2 n_orb), n_elec, n_vecs rows,
  * proc_scrambler / vec_scrambler (n_bits uint32 each). */

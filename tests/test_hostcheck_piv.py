@@ -134,3 +134,19 @@ def test_product_piv_budget(seed, n_procs, n_samp):
     if reflib.available():
         rb, rused = reflib.piv_budget(ln, n_samp, seed)
         assert np.array_equal(ob, rb) and rused == oused
+
+
+@pytest.mark.parametrize("n_procs,n_samp", [(1, 5), (2, 4), (3, 2), (8, 1), (4, 100)])
+def test_product_piv_budget_nothing_left(n_procs, n_samp):
+    """Every rank's residual norm is zero (all elements preserved) while samples are left over -- the exact limit of the
+    HB-PP pipeline (tests/test_hbpp_exact_limit.py).  The reference's sweep then runs on a zero unit, steps over one rank
+    per unit and still draws twice each time: budgets stay zero, and the generator must advance by the same count."""
+    import fries_b200
+    ln = np.zeros(n_procs)
+    draws = ol.mt19937(11, 2 * n_procs + 8)
+    ob, oused = ol.piv_budget(ln, n_samp, draws)
+    pb, pused = fries_b200.piv_budget(ln, n_samp, draws)
+    assert np.array_equal(pb, ob) and not pb.any()
+    assert pused == oused == 2 * min(n_procs, n_samp)
+    # the compiled reference is not consulted here: 0 / 0 -> (uint32_t)NaN is undefined behaviour in piv_budget
+    # (compress_utils.cpp:570) and this build of it faults; the oracle restates the x86 outcome (budget 0)

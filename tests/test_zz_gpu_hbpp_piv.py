@@ -1,0 +1,77 @@
+"""GPU tier, LAST file on purpose: fries_apply_hbpp_piv (apply_HBPP_piv, heat_bathPP.cpp:1014-1419) against the oracle's
+restatement, which is pinned to the compiled reference (tests/test_oracle_piv.py, golden tests/golden/piv_golden.npz).
+
+The device pipeline was written after this round's GPU budget was spent: it compiles for sm_100a and is a composition of
+pieces that are verified on the GPU (stage providers, pivotal compression, finalize kernel), but its first GPU run is
+this test.  Until a green run is on record
+  * every case runs in a CHILD process under a hard wall-clock limit (a fault or a hang of an unverified kernel ends the
+    child, never the pytest process that carries the verified tier), and
+  * the cases are non-strict xfail, so that they report XPASS / XFAIL without deciding the tier;
+the file sorts last so that nothing runs after it.  `python tests/test_zz_gpu_hbpp_piv.py <case>` is the child."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = [(("ne", 2, False), 1, 1, 50), (("ne", 2, True), 1, 300, 1000), (("h2o", 3, True), 0, 1000, 1500),
+         (((8, 6, 0, [0, 0, 1, 2, 3, 0, 1, 2]), 4, True), 1, 40, 3000)]
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+              pytest.mark.xfail(strict=False, reason="first GPU run of fries_apply_hbpp_piv is pending (written without GPU access)")]
+
+
+def run_case(idx):
+    """child: one case, CUDA path against the oracle; prints one JSON line"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fries_b200
+    import oraclelib as ol
+    from fries_b200.synth import SynthMol
+    from golden_cases import make_values
+    case, new_hb, n_det, n_samp = CASES[idx]
+    sm = SynthMol(*case)
+    ctx = fries_b200.Context(0)
+    gm = fries_b200.Mol.from_synth(ctx, sm)
+    om = ol.OracleMol(sm)
+    rng = np.random.default_rng(n_det + new_hb)
+    keys = np.concatenate([[sm.hf], sm.random_dets(n_det - 1, rng, 0)]).astype(np.uint64) if n_det > 1 else \
+        np.array([sm.hf], np.uint64)
+    vals = make_values(rng, n_det, "fri")
+    vals[0] = 100.0
+    cap = 4 * n_samp + 4 * n_det
+    draws = ol.mt19937(3, 12 * n_samp + 64)
+    ov, od, oo, oused = ol.OracleMol.apply_hbpp_piv(om, keys, vals, 0.97, new_hb, draws, n_samp, cap)
+    gv, gd, go, gused = gm.apply_hbpp_piv(keys, vals, 0.97, new_hb, draws, n_samp, cap)
+    oset = {(int(d), tuple(o)): v for d, o, v in zip(od, oo.tolist(), ov)}
+    gset = {(int(d), tuple(o)): v for d, o, v in zip(gd, go.tolist(), gv)}
+    diff = set(oset) ^ set(gset)
+    worst = max((abs(gset[k] - oset[k]) / abs(oset[k]) for k in set(oset) & set(gset)), default=0.0)
+    print(json.dumps({"case": str(case[0]), "new_hb": new_hb, "n_oracle": len(oset), "n_gpu": len(gset), "n_differ": len(diff),
+                      "worst_rel": worst, "draws_gpu": int(gused), "draws_oracle": int(oused)}), flush=True)
+    gm.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_apply_hbpp_piv(idx):
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), str(idx)], cwd=ROOT, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=150)
+    except subprocess.TimeoutExpired as e:  # the child is killed by subprocess.run
+        pytest.fail(f"apply_hbpp_piv case {idx}: no result within 150 s (child killed): {str(e.stdout)[-1500:]}")
+    assert r.returncode == 0, r.stdout[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    print("apply_hbpp_piv", res)
+    # five chained pivotal compressions: each may close its last sampling unit differently (tests/test_gpu_piv.py), and a
+    # different sample early on changes a handful of downstream ones
+    assert res["n_differ"] <= max(12, res["n_oracle"] // 200)
+    assert res["worst_rel"] <= 1e-6
+    assert abs(res["draws_gpu"] - res["draws_oracle"]) <= 8
+
+
+if __name__ == "__main__":
+    run_case(int(sys.argv[1]))
