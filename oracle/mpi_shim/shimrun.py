@@ -20,7 +20,7 @@ HDR = 4096
 
 
 def run(n, cmd, slot_bytes=64 << 20, timeout=None, env=None, all_output=False, stdout=None, stderr=None, stamp=None,
-        grace=3.0):
+        grace=3.0, cwd=None):
     """returns (exit code of rank 0 or the first failing rank, wall seconds).  stamp: a compiled regex with one group;
     the ranks' stdout then goes through one pseudo-terminal (so that it is line buffered) and the arrival time of every
     matching line is appended to the list stamp_out as (group(1), perf_counter) -- pass it as run.stamps afterwards."""
@@ -45,7 +45,7 @@ def run(n, cmd, slot_bytes=64 << 20, timeout=None, env=None, all_output=False, s
             # the drivers print their per-iteration line on the rank that owns the Hartree-Fock determinant, not on rank 0
             out = slave if slave is not None else (subprocess.DEVNULL if quiet else stdout)
             procs.append(subprocess.Popen(cmd, env=e, stdout=out, stderr=subprocess.DEVNULL if quiet else stderr,
-                                          start_new_session=True))
+                                          start_new_session=True, cwd=cwd))
         if slave is not None:
             os.close(slave)
             slave = None

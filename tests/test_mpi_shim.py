@@ -147,7 +147,7 @@ def test_reference_unit_tests_on_two_ranks(tmp_path):
     input directory given on the command line (not given here; its eris.txt is stripped from the repository anyway)"""
     out = open(tmp_path / "out.txt", "w+")
     rc, sec = shimrun.run(2, [os.path.join(REF, "unit_tests")], 8 << 20, timeout=600, stdout=out, stderr=subprocess.STDOUT,
-                          all_output=False)
+                          all_output=False, cwd=str(tmp_path))  # the suite writes alias.txt into its working directory
     out.seek(0)
     txt = out.read()
     import re
