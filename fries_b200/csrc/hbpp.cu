@@ -7,232 +7,6 @@ extern __shared__ double fr_dyn_smem[];
 #define FR_STAGE_MIN_CTAS 2  // two 512-thread CTAs per SM (<= 64 registers): the stage passes are latency bound
 #endif
 
-__device__ __forceinline__ uint32_t pk(unsigned p0, unsigned p1, unsigned p2, unsigned p3) {
-    return (p0 & 0xff) | ((p1 & 0xff) << 8) | ((p2 & 0xff) << 16) | ((p3 & 0xff) << 24);
-}
-
-// Provider of stage S of the hierarchy.  prep() restates the per-sample set-up loop that precedes each
-// comp_sub call in apply_HBPP_sys; visit() streams the sub-weight row the reference stores in subwts
-// (mol.cuh hbs_* generators: masks + popcount, no row array, no occupied list).
-template <int S>
-struct HbProvider {
-    MolView m;  // tables in shared memory
-    HbStageIO io;
-
-    __device__ size_t count() const {
-        unsigned long long n = *io.n_in;
-        return n < io.in_cap ? (size_t)n : (size_t)io.in_cap;
-    }
-
-    // singles bookkeeping (count_symm_virt + count_sing_allowed / count_sing_virt, near_uniform.cpp:14-28,316-347) on bit
-    // masks: no occupied list and no per-irrep counter array (local memory) in the hot loop
-    __device__ unsigned sing_allowed(uint64_t key) const {
-        OccMask o = mol_occ_mask(m, key);
-        return mol_count_sing_allowed_bits(m, o.a, o.b);
-    }
-    // choice in: index among the allowed electrons (alpha block first); out: electron index; returns its virtual count
-    __device__ unsigned sing_virt(uint64_t key, unsigned &choice) const {
-        const unsigned M = m.d.n_orb, h = m.d.n_elec / 2;
-        OccMask o = mol_occ_mask(m, key);
-        uint32_t al_a, al_b;
-        mol_sing_allowed_masks(m, o.a, o.b, al_a, al_b);
-        const unsigned na = (unsigned)__popc(al_a), nb = (unsigned)__popc(al_b);
-        const uint32_t all = (uint32_t)((1ull << M) - 1);
-        if (choice < na) {
-            unsigned orb = fr_nth_bit32(al_a, choice);
-            choice = (unsigned)__popc(o.a & ((1u << orb) - 1u));
-            return (unsigned)__popc(~o.a & all & m.irr_mask[m.symm[orb]]);
-        }
-        if (choice < na + nb) {
-            unsigned orb = fr_nth_bit32(al_b, choice - na);
-            choice = h + (unsigned)__popc(o.b & ((1u << orb) - 1u));
-            return (unsigned)__popc(~o.b & all & m.irr_mask[m.symm[orb]]);
-        }
-        return 0;  // count_sing_virt leaves occ_choice untouched and returns 0 when the index is out of range
-    }
-
-    // wmax: an upper bound of the sub-weights visit() will stream for this input (exactly the largest one where the
-    // row is traversed here anyway); the engine skips the row of an input whose v * wmax is below the threshold bracket
-    __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv, double &wmax) const {
-        const unsigned ne = m.d.n_elec, M = m.d.n_orb;
-        rinv = 1.0;
-        wmax = 1.0;
-        if (S == 0) {  // singles vs doubles :713-727
-            double w = fabs(io.vals[i]);
-            wmax = fmax(io.p_doub, 1 - io.p_doub);
-            v = w;
-            nd = w > 0 ? 0u : 1u;
-            ns = 2;
-            io.det[i] = (uint32_t)i;
-            io.path[i] = 0;
-            return;
-        }
-        const uint32_t widx = io.pw[i], sub = io.ps[i];
-        const uint32_t d = io.pdet[widx], pp = io.ppath[widx];
-        v = io.pv[i];
-        io.det[i] = d;
-        const uint64_t key = io.keys[d];
-        unsigned p0 = pp & 0xff, p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
-        if (S == 1) {  // first occupied orbital :738-763
-            p0 = sub;
-            ns = ne - (io.new_hb ? 1 : 0);
-            if (p0 == 0) {
-                nd = 0;
-                double norm = 0, mx = 0;
-                hbs_o1(m, key, io.new_hb, [&](unsigned, double raw) {
-                    norm += raw;
-                    mx = fmax(mx, raw);
-                });
-                rinv = 1. / norm;
-                wmax = mx * rinv;
-                if (io.new_hb) v *= norm / m.d.s_norm;
-            } else {
-                unsigned n_occ = sing_allowed(key);
-                if (n_occ == 0) {
-                    nd = 1;
-                    v = 0;
-                } else {
-                    nd = n_occ;
-                }
-            }
-            io.path[i] = pk(p0, 0, 0, 0);
-        } else if (S == 2) {  // 2nd occupied (double) / virtual count (single) :772-809
-            p1 = sub;
-            ns = ne - (io.new_hb ? 1 : 0);
-            if (p1 >= ne) {
-                v = 0;
-                nd = 1;
-            } else if (p0 == 0) {
-                nd = 0;
-                OccMask o = mol_occ_mask(m, key);
-                if (io.new_hb) {
-                    p1++;
-                    ns = p1;
-                    double norm = 0, mx = 0;
-                    hbs_o2_half(m, key, p1, [&](unsigned, double raw) {
-                        norm += raw;
-                        mx = fmax(mx, raw);
-                    });
-                    rinv = 1. / norm;
-                    wmax = mx * rinv;
-                    v *= norm / m.s_tens[mol_elec_orb(m, o, p1) % M];
-                } else {
-                    rinv = 1. / hbs_o2_norm(m, key, p1);
-                }
-            } else {
-                unsigned n_virt = sing_virt(key, p1);
-                if (n_virt == 0) {
-                    nd = 1;
-                    v = 0;
-                } else {
-                    nd = n_virt;
-                    p3 = n_virt;
-                }
-            }
-            io.path[i] = pk(p0, p1, 0, p3);
-        } else if (S == 3) {  // 1st virtual (double) :818-857
-            p2 = sub;
-            ns = M - ne / 2;
-            if (p0 == 0) {
-                if (p2 >= ne) {
-                    v = 0;
-                    nd = 1;
-                } else {
-                    nd = 0;
-                    OccMask o = mol_occ_mask(m, key);
-                    unsigned o1_orb = mol_elec_orb(m, o, p1);
-                    bool excl = io.new_hb && (p1 / (ne / 2) == mol_elec_orb(m, o, p2) / M);
-                    double norm = 0, first = 0, mx = 0;
-                    hbs_u1(m, key, o1_orb, [&](unsigned j, double raw) {
-                        if (j == 0) first = raw;
-                        norm += raw;
-                        mx = fmax(mx, raw);
-                    });
-                    if (excl) norm -= first;
-                    rinv = 1. / norm;
-                    wmax = mx * rinv;
-                    if (io.new_hb) v *= norm / m.exch_norms[o1_orb % M];
-                }
-                p3 = 0;
-            } else {
-                nd = 1;
-            }
-            io.path[i] = pk(p0, p1, p2, p3);
-        } else {  // S == 4: 2nd virtual (double) :866-908
-            ns = m.d.max_n_symm;
-            if (p0 == 0) {
-                OccMask o = mol_occ_mask(m, key);
-                unsigned spin = p1 / (ne / 2);
-                uint32_t vm = ~(spin ? o.b : o.a) & (uint32_t)((1ull << M) - 1);
-                if (sub >= (unsigned)__popc(vm)) {  // find_nth_virt (fci_utils.c:138-148) would leave the orbital range
-                    v = 0;
-                    nd = 1;
-                } else {
-                    unsigned u1 = fr_nth_bit32(vm, sub) + M * spin;
-                    nd = 0;
-                    p3 = u1;
-                    unsigned o1_orb = mol_elec_orb(m, o, p1), o2_orb = mol_elec_orb(m, o, p2);
-                    double norm = 0, mx = 0;
-                    unsigned len = 0;
-                    if (io.new_hb) {
-                        hbs_u2_half(m, o1_orb, o2_orb, u1, key, [&](unsigned j, double raw) {
-                            norm += raw;
-                            mx = fmax(mx, raw);
-                            len = j + 1;
-                        });
-                    } else {
-                        hbs_u2(m, o1_orb, o2_orb, u1, [&](unsigned j, double raw) {
-                            norm += raw;
-                            mx = fmax(mx, raw);
-                            len = j + 1;
-                        });
-                    }
-                    ns = len;
-                    rinv = norm != 0 ? 1 / norm : 1.0;
-                    wmax = mx * rinv;
-                    double tot = norm / m.exch_norms[o2_orb % M];
-                    if (io.new_hb || tot == 0) v *= tot;
-                }
-            } else {
-                nd = 1;
-            }
-            io.path[i] = pk(p0, p1, p2, p3);
-        }
-    }
-
-    template <class F>
-    __device__ void visit(size_t i, double rinv, F &&f) const {
-        if (S == 0) {
-            if (fr_emit(f, 0u, io.p_doub)) fr_emit(f, 1u, 1 - io.p_doub);
-            return;
-        }
-        const unsigned ne = m.d.n_elec, M = m.d.n_orb;
-        const uint32_t pp = io.path[i];
-        const uint64_t key = io.keys[io.det[i]];
-        unsigned p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
-        if (S == 1) {
-            hbs_o1(m, key, io.new_hb, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
-        } else if (S == 2) {
-            if (io.new_hb)
-                hbs_o2_half(m, key, p1, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
-            else
-                hbs_o2(m, key, p1, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
-        } else if (S == 3) {
-            OccMask o = mol_occ_mask(m, key);
-            bool excl = io.new_hb && (p1 / (ne / 2) == mol_elec_orb(m, o, p2) / M);
-            hbs_u1(m, key, mol_elec_orb(m, o, p1),
-                   [&](unsigned j, double raw) { return fr_emit(f, j, (excl && j == 0) ? 0.0 : raw * rinv); });
-        } else {
-            OccMask o = mol_occ_mask(m, key);
-            unsigned o1_orb = mol_elec_orb(m, o, p1), o2_orb = mol_elec_orb(m, o, p2);
-            if (io.new_hb)
-                hbs_u2_half(m, o1_orb, o2_orb, p3, key, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
-            else
-                hbs_u2(m, o1_orb, o2_orb, p3, [&](unsigned j, double raw) { return fr_emit(f, j, raw * rinv); });
-        }
-    }
-};
-
 template <int S>
 __global__ void __launch_bounds__(FR_COMP_BLOCK, FR_STAGE_MIN_CTAS)
 hbpp_stage_kernel(MolView gm, HbStageIO io, CompSubBufs bufs, unsigned n_samp, double rn) {
@@ -259,7 +33,6 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
         if (threadIdx.x < 64) s_pscr[threadIdx.x] = sp.proc_scr[threadIdx.x];
         __syncthreads();
     }
-    const unsigned M = m.d.n_orb;
     unsigned long long n = *n_ptr;
     if (n > in_cap) n = in_cap;
     unsigned long long ok = 0;
@@ -276,58 +49,9 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
         const uint32_t widx = pw[i], sub = ps[i];
         const uint32_t d = pdet[widx], pp = ppath[widx];
         const uint64_t key = keys[d];
-        const OccMask om = mol_occ_mask(m, key);  // occupied orbitals by spin: no occupied list in the common paths
-        unsigned p0 = pp & 0xff, p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
-        uint8_t orbs[4] = {0, 0, 0, 0};
-        bool is_doub = p0 == 0;
-        if (is_doub) {
-            unsigned o1 = mol_elec_orb(m, om, p1), o2 = mol_elec_orb(m, om, p2), u1 = p3;
-            unsigned u2_symm = m.symm[o1 % M] ^ m.symm[o2 % M] ^ m.symm[u1 % M];
-            unsigned u2 = mol_lookup(m, u2_symm, sub + 1) + M * (o2 / M);
-            if (!fr_read_bit(key, u2) && u1 != u2) {
-                if (u1 > u2) {
-                    unsigned t = u1;
-                    u1 = u2;
-                    u2 = t;
-                }
-                if (o1 > o2) {
-                    unsigned t = o1;
-                    o1 = o2;
-                    o2 = t;
-                }
-                orbs[0] = (uint8_t)o1;
-                orbs[1] = (uint8_t)o2;
-                orbs[2] = (uint8_t)u1;
-                orbs[3] = (uint8_t)u2;
-                double tot;
-                if (new_hb) {
-                    tot = hb_unnorm_wt(m, orbs);
-                } else {
-                    uint8_t occ[FRIES_MAX_ELEC + 1];
-                    mol_occ_list(key, occ);
-                    tot = hb_norm_wt(m, orbs, occ, key);
-                }
-                el = mol_doub_el(m, orbs) * pv[i] / tot / p_doub;
-                if (fabs(el) > cutoff)
-                    el *= fr_doub_parity(key, o1, o2, u1, u2);
-                else
-                    el = 0;
-            }
-        } else {
-            unsigned o1 = mol_elec_orb(m, om, p1);
-            unsigned u1 = mol_virt_from_idx(m, key, m.symm[o1 % M], M * (o1 / M), p2);
-            if (u1 != 255) {
-                orbs[0] = (uint8_t)o1;
-                orbs[1] = (uint8_t)u1;
-                unsigned n_occ = mol_count_sing_allowed_bits(m, om.a, om.b);
-                el = mol_sing_el_bits(m, o1, u1, om.a, om.b);
-                el *= pv[i] / (1 - p_doub) * n_occ * p3;
-                if (fabs(el) > cutoff)
-                    el *= fr_sing_parity(key, o1, u1);
-                else
-                    el = 0;
-            }
-        }
+        uint8_t orbs[4];
+        bool is_doub;
+        el = hbpp_finalize_sample(m, key, pp, sub, pv[i], p_doub, new_hb, cutoff, orbs, is_doub);
         if (el != 0) ok++;
         if (sp.out_keys || sp.n_ranks > 1) {
             // spawn loop body frisys_mol.cpp:436-461
@@ -646,17 +370,8 @@ hbpp_piv_prep_kernel(MolView gm, HbStageIO io, double *veff, uint32_t *ndiv, uin
     prov.m = mol_stage_shared(gm, fr_dyn_smem);
     prov.io = io;
     const size_t n = prov.count(), stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        double v, ri, wmax;
-        uint32_t nd, ns;
-        prov.prep(i, v, nd, ns, ri, wmax);
-        if (ns > FRIES_MAX_SUB) ns = FRIES_MAX_SUB;
-        veff[i] = v;
-        ndiv[i] = nd;
-        nsub[i] = (uint8_t)ns;
-        rinv[i] = ri;
-        gsize[i] = nd > 0 ? nd : ns;
-    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        gsize[i] = hbpp_piv_group_prep(prov, i, veff[i], ndiv[i], nsub[i], rinv[i]);
 }
 
 template <int S>
@@ -667,20 +382,8 @@ hbpp_piv_fill_kernel(MolView gm, HbStageIO io, const double *veff, const uint32_
     prov.m = mol_stage_shared(gm, fr_dyn_smem);
     prov.io = io;
     const size_t n = prov.count(), stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double v = veff[i];
-        const uint32_t nd = ndiv[i], ns = nsub[i];
-        double *dst = lng + goff[i];
-        if (nd > 0) {
-            const double piece = v / nd;
-            for (uint32_t j = 0; j < nd; j++) dst[j] = piece;
-        } else {
-            for (uint32_t j = 0; j < ns; j++) dst[j] = 0.0;
-            prov.visit(i, rinv[i], [&](unsigned j, double w) {
-                if (j < ns) dst[j] = v * w;
-            });
-        }
-    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        hbpp_piv_group_fill(prov, i, veff[i], ndiv[i], nsub[i], rinv[i], lng + goff[i]);
 }
 
 // exclusive prefix of `in[0 .. n)` (n on the device) into out, total to *tot; one CTA of 1024 threads

@@ -10,21 +10,8 @@
 #pragma once
 #include "compress.cuh"
 #include "molhost.cuh"
+#include "hbpp_prov.cuh"
 
-struct HbStageIO {
-    const uint64_t *keys;            // parent determinants (storage order)
-    const double *vals;              // stage 0 input: vector values
-    const unsigned long long *n_in;  // number of inputs of this stage (device)
-    // outputs of the previous stage (inputs of this one)
-    const double *pv;
-    const uint32_t *pw, *ps;
-    const uint32_t *pdet, *ppath;
-    // per-item path state written by this stage
-    uint32_t *det, *path;
-    double p_doub;
-    int new_hb;
-    unsigned long long in_cap;       // inputs beyond this index were dropped by the previous stage
-};
 
 struct fries_hbpp {
     fries_ctx *ctx = nullptr;

@@ -15,7 +15,7 @@ _lib = None
 
 def build():
     src = os.path.join(HERE, "hostcheck.cu")
-    deps = [src] + [os.path.join(HERE, "..", "..", "fries_b200", "csrc", f) for f in ("mol.cuh", "common.cuh", "piv.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "..", "fries_b200", "csrc", f) for f in ("mol.cuh", "common.cuh", "piv.cuh", "hbpp_prov.cuh")]
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(SO), exist_ok=True)
@@ -59,5 +59,15 @@ def lib():
         L.hc_piv_samp.argtypes = [f64p, C.c_size_t, u8p, C.c_double, C.c_uint32, u32p, C.POINTER(C.c_uint64)]
         L.hc_adjust_probs.restype = C.c_double
         L.hc_adjust_probs.argtypes = [f64p, C.c_size_t, u8p, C.POINTER(C.c_uint32), C.c_double, C.c_uint32, C.c_double]
+        u64p = np.ctypeslib.ndpointer(np.uint64, flags="C")
+        L.hc_hbpiv_begin.restype = C.c_void_p
+        L.hc_hbpiv_begin.argtypes = [C.c_void_p, u64p, f64p, C.c_size_t, C.c_double, C.c_int, C.c_size_t]
+        L.hc_hbpiv_end.argtypes = [C.c_void_p]
+        L.hc_hbpiv_expand.restype = C.c_size_t
+        L.hc_hbpiv_expand.argtypes = [C.c_void_p, C.c_int, f64p, C.c_size_t]
+        L.hc_hbpiv_collapse.restype = C.c_size_t
+        L.hc_hbpiv_collapse.argtypes = [C.c_void_p, C.c_int, f64p, u8p]
+        L.hc_hbpiv_finalize.restype = C.c_size_t
+        L.hc_hbpiv_finalize.argtypes = [C.c_void_p, C.c_double, f64p, u64p, u8p]
         _lib = L
     return _lib

@@ -6,6 +6,7 @@
 // kernels themselves (launch geometry, scans, atomics, staging) are only checked by the -m gpu tests.
 #include "../../fries_b200/csrc/mol.cuh"
 #include "../../fries_b200/csrc/piv.cuh"
+#include "../../fries_b200/csrc/hbpp_prov.cuh"
 #include <vector>
 
 struct HcMol {
@@ -33,8 +34,13 @@ void *hc_mol_create(unsigned n_orb, unsigned n_elec_total, unsigned n_frz, const
     d.off_exch_norms = off; off += M;
     d.off_symm = off; off += (M + 7) / 8;
     d.off_lookup = off; off += (FR_N_IRREPS * (M + 1) + 7) / 8;
+    d.off_irr = off; off += (FR_N_IRREPS * 4 + 7) / 8;
     d.blob_doubles = off;
     h->blob.assign(off, 0.0);
+    {
+        uint32_t *irr = (uint32_t *)&h->blob[d.off_irr];  // as fries_mol_create (mol.cu)
+        for (unsigned i = 0; i < M; i++) irr[symm[i] % FR_N_IRREPS] |= 1u << i;
+    }
     memcpy(&h->blob[d.off_d_diff], d_diff, M * M * 8);
     memcpy(&h->blob[d.off_d_same], d_same, TT * 8);
     memcpy(&h->blob[d.off_s_tens], s_tens, M * 8);
@@ -205,5 +211,135 @@ double hc_adjust_probs(double *vals, size_t n, uint8_t *keep, uint32_t *n_loc, d
     }
     *n_loc -= exact_cnt;
     return *n_loc * a.loc_norm / exp_loc;
+}
+
+// ---- apply_HBPP_piv: the device pipeline of fries_apply_hbpp_piv (hbpp.cu) step by step on the host.  The per-input
+// arithmetic is the product's (hbpp_prov.cuh: providers, group prep / fill, finalize of a sample); scans, collapse and
+// buffer ping-pong are restated here as the kernels do them; the pivotal compression between expand and collapse is
+// done by the caller (the oracle's piv_comp_parallel in tests/test_hostcheck_hbpp_piv.py). ----
+struct HcPiv {
+    HcMol *mol;
+    std::vector<uint64_t> keys;
+    std::vector<double> vals;
+    size_t cap;
+    std::vector<double> oval[2], veff, rinv;
+    std::vector<uint32_t> owidx[2], osub[2], det[2], path[2], ndiv, gsize;
+    std::vector<uint8_t> nsub;
+    std::vector<unsigned long long> goff;
+    unsigned long long n_in;
+    double p_doub;
+    int new_hb;
+};
+void *hc_hbpiv_begin(void *mol, const uint64_t *keys, const double *vals, size_t n, double p_doub, int new_hb, size_t cap) {
+    HcPiv *h = new HcPiv();
+    h->mol = (HcMol *)mol;
+    h->keys.assign(keys, keys + n);
+    h->vals.assign(vals, vals + n);
+    h->cap = cap;
+    for (int k = 0; k < 2; k++) {
+        h->oval[k].assign(cap, 0.0);
+        h->owidx[k].assign(cap, 0);
+        h->osub[k].assign(cap, 0);
+        h->det[k].assign(cap, 0);
+        h->path[k].assign(cap, 0);
+    }
+    h->veff.assign(cap, 0.0);
+    h->rinv.assign(cap, 0.0);
+    h->ndiv.assign(cap, 0);
+    h->gsize.assign(cap, 0);
+    h->nsub.assign(cap, 0);
+    h->goff.assign(cap, 0);
+    h->n_in = n;
+    h->p_doub = p_doub;
+    h->new_hb = new_hb;
+    return h;
+}
+void hc_hbpiv_end(void *p) { delete (HcPiv *)p; }
+
+static HbStageIO hbpiv_io(HcPiv *h, int s) {
+    int o = s & 1, p = o ^ 1;  // fries_apply_hbpp_piv's ping-pong
+    HbStageIO io;
+    io.keys = h->keys.data();
+    io.vals = h->vals.data();
+    io.n_in = &h->n_in;
+    io.pv = h->oval[p].data();
+    io.pw = h->owidx[p].data();
+    io.ps = h->osub[p].data();
+    io.pdet = h->det[p].data();
+    io.ppath = h->path[p].data();
+    io.det = h->det[o].data();
+    io.path = h->path[o].data();
+    io.p_doub = h->p_doub;
+    io.new_hb = h->new_hb;
+    io.in_cap = h->cap;
+    return io;
+}
+}  // extern "C"
+template <int S>
+static size_t hbpiv_expand(HcPiv *h, double *lng, size_t long_cap) {
+    HbProvider<S> prov;
+    prov.m = h->mol->v;
+    prov.io = hbpiv_io(h, S);
+    const size_t n = prov.count();
+    unsigned long long tot = 0;
+    for (size_t i = 0; i < n; i++) {  // prep kernel + scan kernel
+        h->gsize[i] = hbpp_piv_group_prep(prov, i, h->veff[i], h->ndiv[i], h->nsub[i], h->rinv[i]);
+        h->goff[i] = tot;
+        tot += h->gsize[i];
+    }
+    if (tot > long_cap) return (size_t)-1;
+    for (size_t i = 0; i < n; i++)  // fill kernel
+        hbpp_piv_group_fill(prov, i, h->veff[i], h->ndiv[i], h->nsub[i], h->rinv[i], lng + h->goff[i]);
+    return (size_t)tot;
+}
+extern "C" {
+size_t hc_hbpiv_expand(void *p, int stage, double *lng, size_t long_cap) {
+    HcPiv *h = (HcPiv *)p;
+    switch (stage) {
+        case 0: return hbpiv_expand<0>(h, lng, long_cap);
+        case 1: return hbpiv_expand<1>(h, lng, long_cap);
+        case 2: return hbpiv_expand<2>(h, lng, long_cap);
+        case 3: return hbpiv_expand<3>(h, lng, long_cap);
+        default: return hbpiv_expand<4>(h, lng, long_cap);
+    }
+}
+// count / scan / collapse kernels + set_nout; returns the uncapped number of survivors
+size_t hc_hbpiv_collapse(void *p, int stage, const double *lng, const uint8_t *zeroed) {
+    HcPiv *h = (HcPiv *)p;
+    const int o = stage & 1;
+    unsigned long long n = h->n_in < h->cap ? h->n_in : h->cap, out = 0;
+    for (unsigned long long i = 0; i < n; i++) {
+        const unsigned long long b = h->goff[i];
+        for (uint32_t j = 0; j < h->gsize[i]; j++) {
+            if (zeroed[b + j]) continue;
+            if (out < h->cap) {
+                h->oval[o][out] = lng[b + j];
+                h->owidx[o][out] = (uint32_t)i;
+                h->osub[o][out] = j;
+            }
+            out++;
+        }
+    }
+    h->n_in = out < h->cap ? out : h->cap;
+    return (size_t)out;
+}
+// hbpp_finalize_kernel without spawn arguments + the host marshalling of fries_apply_hbpp_piv
+size_t hc_hbpiv_finalize(void *p, double cutoff, double *out_val, uint64_t *out_det, uint8_t *out_orbs) {
+    HcPiv *h = (HcPiv *)p;
+    size_t k = 0;
+    for (unsigned long long i = 0; i < h->n_in; i++) {
+        const uint32_t widx = h->owidx[0][i], sub = h->osub[0][i];
+        const uint32_t d = h->det[0][widx], pp = h->path[0][widx];
+        uint8_t orbs[4];
+        bool is_doub;
+        double el = hbpp_finalize_sample(h->mol->v, h->keys[d], pp, sub, h->oval[0][i], h->p_doub, h->new_hb, cutoff, orbs,
+                                         is_doub);
+        if (el == 0) continue;
+        out_val[k] = el;
+        out_det[k] = d;
+        memcpy(out_orbs + 4 * k, orbs, 4);
+        k++;
+    }
+    return k;
 }
 }

@@ -2,8 +2,8 @@
 restatement, which is pinned to the compiled reference (tests/test_oracle_piv.py, golden tests/golden/piv_golden.npz).
 
 The device pipeline was written after this round's GPU budget was spent: it compiles for sm_100a and is a composition of
-pieces that are verified on the GPU (stage providers, pivotal compression, finalize kernel), but its first GPU run is
-this test.  Until a green run is on record
+pieces that are verified on the GPU (stage providers, pivotal compression, finalize kernel) whose composition reproduces the
+oracle sample for sample when run on the host (tests/test_hostcheck_hbpp_piv.py), but its first GPU run is this test.  Until a green run is on record
   * every case runs in a CHILD process under a hard wall-clock limit (a fault or a hang of an unverified kernel ends the
     child, never the pytest process that carries the verified tier), and
   * the cases are non-strict xfail, so that they report XPASS / XFAIL without deciding the tier;
@@ -46,11 +46,16 @@ def run_case(idx):
     draws = ol.mt19937(3, 12 * n_samp + 64)
     ov, od, oo, oused = ol.OracleMol.apply_hbpp_piv(om, keys, vals, 0.97, new_hb, draws, n_samp, cap)
     gv, gd, go, gused = gm.apply_hbpp_piv(keys, vals, 0.97, new_hb, draws, n_samp, cap)
-    oset = {(int(d), tuple(o)): v for d, o, v in zip(od, oo.tolist(), ov)}
-    gset = {(int(d), tuple(o)): v for d, o, v in zip(gd, go.tolist(), gv)}
-    diff = set(oset) ^ set(gset)
-    worst = max((abs(gset[k] - oset[k]) / abs(oset[k]) for k in set(oset) & set(gset)), default=0.0)
-    print(json.dumps({"case": str(case[0]), "new_hb": new_hb, "n_oracle": len(oset), "n_gpu": len(gset), "n_differ": len(diff),
+    def bag(dd, orbs, vv):  # multisets: with new_hb = 0 an excitation is reached along several paths
+        out = {}
+        for d, o, v in zip(dd, orbs.tolist(), vv):
+            out.setdefault((int(d), tuple(o)), []).append(float(v))
+        return {k: sorted(v) for k, v in out.items()}
+    ob, gb = bag(od, oo, ov), bag(gd, go, gv)
+    n_diff = sum(abs(len(ob.get(k, [])) - len(gb.get(k, []))) for k in set(ob) | set(gb))
+    worst = max((abs(x - y) / abs(y) for k in set(ob) & set(gb) if len(ob[k]) == len(gb[k]) for x, y in zip(gb[k], ob[k])),
+                default=0.0)
+    print(json.dumps({"case": str(case[0]), "new_hb": new_hb, "n_oracle": len(ov), "n_gpu": len(gv), "n_differ": n_diff,
                       "worst_rel": worst, "draws_gpu": int(gused), "draws_oracle": int(oused)}), flush=True)
     gm.close()
     ctx.close()
