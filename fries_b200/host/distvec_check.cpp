@@ -1,0 +1,151 @@
+// Self-check of the raw-pointer view of fries::DistVec (values / indices / occ_orbs / operator[] / operator() /
+// orbs_at_pos / matr_el_at_pos / internal_dot / dense_norm / idx_to_hash / idx_to_proc / add_elements / push_host;
+// FRIES/vec_utils.hpp:200-953) on the GPU: a small store is filled through add + perform_add, read back through the
+// pointers and compared with the values that went in.  Exit code 0 = all checks passed; every failure prints a line.
+#include "fries_host.hpp"
+using namespace fries;
+
+static int n_fail = 0;
+#define CHECK(cond)                                                                    \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            std::cout << "FAILED line " << __LINE__ << ": " #cond << std::endl;        \
+            n_fail++;                                                                  \
+        }                                                                              \
+    } while (0)
+
+int main() {
+    try {
+        Context ctx(0);
+        const unsigned n_orb = 10, n_elec = 6, n_bits = 2 * n_orb;
+        std::mt19937 mt(7);
+        std::vector<uint32_t> pscr(n_bits), vscr(n_bits);
+        for (auto &x : pscr) x = mt();
+        for (auto &x : vscr) x = mt();
+        DistVec vec(ctx, 4096, n_bits, n_elec, 2, pscr, vscr);
+        // 200 distinct determinants with 3 alpha + 3 beta electrons
+        std::map<uint64_t, double> truth;
+        while (truth.size() < 200) {
+            uint64_t k = 0;
+            for (int spin = 0; spin < 2; spin++) {
+                unsigned got = 0;
+                while (got < n_elec / 2) {
+                    unsigned o = mt() % n_orb + spin * n_orb;
+                    if (!(k >> o & 1)) {
+                        k |= 1ull << o;
+                        got++;
+                    }
+                }
+            }
+            if (truth.count(k)) continue;
+            double v = (double)(mt() % 2000) / 100.0 - 10.0;
+            if (v == 0) v = 0.5;
+            truth[k] = v;
+        }
+        uint8_t det[8];
+        for (auto &kv : truth) {
+            key_to_bytes(kv.first, det, 3);
+            CHECK(vec.add(det, kv.second, 1));  // pointer form
+        }
+        vec.perform_add(0);
+        CHECK(vec.curr_size() == truth.size());
+        CHECK(vec.num_vecs() == 2 && vec.max_size() == 4096 && vec.adder_size() == 4096);
+        // raw view
+        Matrix<uint8_t> &idx = vec.indices();
+        Matrix<uint8_t> &occ = vec.occ_orbs();
+        CHECK(idx.cols() == 3 && occ.cols() == n_elec);
+        double *vals = vec.values();
+        double norm = 0;
+        for (size_t i = 0; i < vec.curr_size(); i++) {
+            uint64_t k = key_from_bytes(idx[i], 3);
+            CHECK(truth.count(k) == 1);
+            CHECK(vals[i] == truth[k] && *vec[i] == truth[k] && *vec(0, i) == truth[k] && *vec(1, i) == 0);
+            uint8_t o2[64];
+            CHECK(vec.gen_orb_list(idx[i], o2) == n_elec && memcmp(o2, occ[i], n_elec) == 0 && vec.orbs_at_pos(i) == occ[i]);
+            uint8_t o3[64];
+            CHECK(vec.idx_to_hash(idx[i], o3) == hash_fxn(vscr.data(), occ[i], n_elec));
+            CHECK(vec.idx_to_proc(idx[i], 8) == (int)(hash_fxn(pscr.data(), occ[i], n_elec) % 8));
+            norm += std::fabs(vals[i]);
+        }
+        CHECK(std::fabs(norm - vec.local_norm()) <= 1e-12 * norm);
+        // diagonal elements through the user's function, cached
+        int calls = 0;
+        vec.set_diag_calc([&](const uint8_t *o) {
+            calls++;
+            double s = 0;
+            for (unsigned i = 0; i < n_elec; i++) s += o[i];
+            return s;
+        });
+        double d5 = vec.matr_el_at_pos(5);
+        CHECK(d5 == vec.matr_el_at_pos(5) && calls == 1);
+        // internal_dot / two_norm
+        double tn = vec.two_norm();
+        CHECK(std::fabs(vec.internal_dot(0, 0) - tn) <= 1e-12 * tn && vec.internal_dot(0, 1) == 0);
+        bool threw = false;
+        try {
+            vec.internal_dot(0, 2);
+        } catch (std::runtime_error &) {
+            threw = true;
+        }
+        CHECK(threw);
+        // write through the pointers, push back: element 3 doubled, element 4 deleted (zero in every row)
+        uint64_t k3 = key_from_bytes(idx[3], 3), k4 = key_from_bytes(idx[4], 3);
+        *vec[3] *= 2;
+        *vec[4] = 0;
+        vec.push_host();
+        CHECK(vec.curr_size() == truth.size() - 1);
+        std::vector<uint64_t> one{k3}, gone{k4};
+        std::vector<double> w{1.0};
+        CHECK(vec.dot(one, w) == 2 * truth[k3] && vec.dot(gone, w) == 0);
+        // Matrix form of dot
+        Matrix<uint8_t> tm(2, 3);
+        key_to_bytes(k3, tm[0], 3);
+        key_to_bytes(k4, tm[1], 3);
+        double tv[2] = {1.0, 1.0};
+        CHECK(vec.dot(tm, tv, 2) == 2 * truth[k3]);
+        // add_elements: a received buffer, bit n_bits = initiator flag; a flagged new determinant is created, an unflagged
+        // one is dropped, an unflagged existing one accumulates (vec_utils.hpp:606-641)
+        uint64_t k_new1 = 0x7ull | (0x7ull << n_orb), k_new2 = 0x38ull | (0x38ull << n_orb);
+        std::vector<uint8_t> buf(3 * 3);
+        std::vector<double> bv{1.25, 2.5, 0.75};
+        bool new1 = !truth.count(k_new1), new2 = !truth.count(k_new2);
+        key_to_bytes(k_new1 | (1ull << n_bits), &buf[0], 3);
+        key_to_bytes(k_new2, &buf[3], 3);
+        key_to_bytes(k3, &buf[6], 3);
+        size_t before = vec.curr_size();
+        vec.add_elements(buf.data(), bv.data(), 3, 0);
+        CHECK(vec.curr_size() == before + (new1 ? 1 : 0));
+        std::vector<uint64_t> q{k_new1, k_new2, k3};
+        std::vector<double> q1{1, 0, 0}, q2{0, 1, 0}, q3{0, 0, 1};
+        if (new1) CHECK(vec.dot(q, q1) == 1.25);
+        if (new2) CHECK(vec.dot(q, q2) == 0);
+        CHECK(vec.dot(q, q3) == 2 * truth[k3] + 0.75);
+        // fix_min_del_idx + dense_norm without a dense subspace, print_ht, collect_procs, expand
+        vec.fix_min_del_idx();
+        vec.set_min_del_idx(0);
+        CHECK(vec.dense_norm() == 0);
+        vec.collect_procs();
+        vec.print_ht();
+        threw = false;
+        try {
+            vec.expand();
+        } catch (std::runtime_error &) {
+            threw = true;
+        }
+        CHECK(threw);
+        // wrong electron count
+        threw = false;
+        uint8_t bad[3] = {1, 0, 0}, o4[64];
+        try {
+            vec.idx_to_hash(bad, o4);
+        } catch (std::runtime_error &e) {
+            threw = std::string(e.what()).find("incorrect number of electrons") != std::string::npos;
+        }
+        CHECK(threw);
+    } catch (std::exception &e) {
+        std::cout << "Exception : " << e.what() << std::endl;
+        return 2;
+    }
+    std::cout << (n_fail ? "distvec_check: FAILED" : "distvec_check: all checks passed") << std::endl;
+    return n_fail ? 1 : 0;
+}

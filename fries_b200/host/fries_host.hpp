@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -49,6 +50,48 @@ inline uint64_t gen_hf_bitstring(unsigned n_orb, unsigned n_elec) {
     uint64_t k = 0;
     for (unsigned i = 0; i < n_elec / 2; i++) k |= (1ull << i) | (1ull << (i + n_orb));
     return k;
+}
+
+// ---- Matrix<T> FRIES/ndarr.hpp:20-140: row-major 2-D array with the reference's accessors ---------------------------
+template <class T>
+class Matrix {
+    size_t rows_ = 0, cols_ = 0;
+    std::vector<T> data_;
+
+  public:
+    Matrix() = default;
+    Matrix(size_t rows, size_t cols) : rows_(rows), cols_(cols), data_(rows * cols) {}
+    T &operator()(size_t row, size_t col) { return data_[row * cols_ + col]; }
+    const T &operator()(size_t row, size_t col) const { return data_[row * cols_ + col]; }
+    T *operator[](size_t row) { return data_.data() + row * cols_; }
+    const T *operator[](size_t row) const { return data_.data() + row * cols_; }
+    void reshape(size_t new_rows, size_t new_cols) {
+        rows_ = new_rows;
+        cols_ = new_cols;
+        data_.resize(new_rows * new_cols);
+    }
+    size_t rows() const { return rows_; }
+    size_t cols() const { return cols_; }
+    T *data() { return data_.data(); }
+    const T *data() const { return data_.data(); }
+};
+
+// find_bits FRIES/math_utils.c:62-98: positions of the 1 bits of a byte string, ascending; returns their number
+inline uint8_t find_bits(const uint8_t *bit_str, uint8_t *bits, uint8_t n_bytes) {
+    uint8_t n = 0;
+    for (unsigned b = 0; b < n_bytes; b++)
+        for (unsigned i = 0; i < 8; i++)
+            if (bit_str[b] >> i & 1) bits[n++] = (uint8_t)(8 * b + i);
+    return n;
+}
+// HashTable::hash_fxn FRIES/det_hash.hpp:160-170 (the device twin is fr_det_hash): the product (i + 1) * scrambler is
+// taken in 32 bits, the recurrence in 64
+inline uintmax_t hash_fxn(const uint32_t *scrambler, const uint8_t *occ_orbs, unsigned n_elec, const uint8_t *phonon_nums = nullptr,
+                          unsigned n_phonon = 0) {
+    uintmax_t hash = 0;
+    for (unsigned i = 0; i < n_elec; i++) hash = 1099511628211ULL * hash + (uint32_t)((i + 1) * scrambler[occ_orbs[i]]);
+    for (unsigned i = 0; i < n_phonon; i++) hash = 1099511628211ULL * hash + (uint32_t)((i + 1) * scrambler[phonon_nums[i]]);
+    return hash;
 }
 
 // ---- command line: argparse::Args semantics (Ext_Libs/argparse.hpp:347-393) ---------------------------------------
@@ -367,15 +410,18 @@ class DistVec {
     std::vector<uint64_t> buf_dets_;
     std::vector<double> buf_vals_;
     std::vector<uint8_t> buf_ini_;
+    std::vector<uint32_t> proc_scr_, vec_scr_;  // hash.dat contents (HashTable scramblers, det_hash.hpp:41-58)
+    unsigned hh_sites_ = 0, hh_ph_bits_ = 0;    // HubHolVec only
     DistVec(Context &c, size_t size, unsigned n_bits_, unsigned n_elec_, unsigned n_vecs_, const std::vector<uint32_t> &proc_scr,
             const std::vector<uint32_t> &vec_scr)
-        : n_bits(n_bits_), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size) {
+        : n_bits(n_bits_), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size), proc_scr_(proc_scr), vec_scr_(vec_scr) {
         check(fries_vec_create(c.h, size, n_bits, n_elec, n_vecs, proc_scr.data(), vec_scr.data(), 1, 0, &h));
     }
     // HubHolVec FRIES/hh_vec.hpp:27-29
     DistVec(Context &c, size_t size, unsigned n_sites, unsigned ph_bits, unsigned n_elec_, unsigned n_vecs_,
             const std::vector<uint32_t> &proc_scr, const std::vector<uint32_t> &vec_scr)
-        : n_bits(n_sites * (2 + ph_bits)), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size) {
+        : n_bits(n_sites * (2 + ph_bits)), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size), proc_scr_(proc_scr),
+          vec_scr_(vec_scr), hh_sites_(n_sites), hh_ph_bits_(ph_bits) {
         check(fries_vec_create_hh(c.h, size, n_sites, ph_bits, n_elec, n_vecs, proc_scr.data(), vec_scr.data(), 1, 0, &h));
     }
     ~DistVec() {
@@ -394,6 +440,7 @@ class DistVec {
              unsigned dest = 0) {
         std::vector<uint8_t> ini(dets.size(), ini_flag);
         check(fries_vec_add(h, dets.data(), vals.data(), ini.data(), dets.size(), origin, dest));
+        host_valid_ = false;
     }
     double local_norm(unsigned row) {
         double n;
@@ -431,11 +478,12 @@ class DistVec {
         buf_dets_.clear();
         buf_vals_.clear();
         buf_ini_.clear();
+        host_valid_ = false;
     }
-    void add_vecs(uint8_t idx1, uint8_t idx2, double c = 1.0) { check(fries_vec_row_op(h, 0, idx1, idx2, c)); }   // :547-557
-    void copy_vec(uint8_t src, uint8_t dst) { check(fries_vec_row_op(h, 1, dst, src, 0.0)); }                   // :561-565
-    void weight_vec(uint8_t idx1, uint8_t idx2, double expo) { check(fries_vec_row_op(h, 2, idx1, idx2, expo)); }  // :569-573
-    void zero_vec() { check(fries_vec_row_op(h, 3, curr_vec_idx_, curr_vec_idx_, 0.0)); }                       // :577-579
+    void add_vecs(uint8_t idx1, uint8_t idx2, double c = 1.0) { host_valid_ = false; check(fries_vec_row_op(h, 0, idx1, idx2, c)); }   // :547-557
+    void copy_vec(uint8_t src, uint8_t dst) { host_valid_ = false; check(fries_vec_row_op(h, 1, dst, src, 0.0)); }                   // :561-565
+    void weight_vec(uint8_t idx1, uint8_t idx2, double expo) { host_valid_ = false; check(fries_vec_row_op(h, 2, idx1, idx2, expo)); }  // :569-573
+    void zero_vec() { host_valid_ = false; check(fries_vec_row_op(h, 3, curr_vec_idx_, curr_vec_idx_, 0.0)); }                       // :577-579
     // dot with a (replicated) list of determinants (:228-253)
     double dot(const std::vector<uint64_t> &dets, const std::vector<double> &vals) {
         double out;
@@ -446,10 +494,164 @@ class DistVec {
     void del_at_pos(const std::vector<bool> &flags) {
         std::vector<uint8_t> f(flags.begin(), flags.end());
         check(fries_vec_del(h, f.data(), f.size()));
+        host_valid_ = false;
     }
     void cleanup() {
         std::vector<uint8_t> f(curr_size(), 1);
         check(fries_vec_del(h, f.data(), f.size()));
+        host_valid_ = false;
+    }
+    // ---- the reference's raw-pointer view of the storage ------------------------------------------------------------------
+    // values() / indices() / occ_orbs() / operator[] / operator() / orbs_at_pos hand out pointers into the reference's own
+    // arrays (vec_utils.hpp:505-516,643-663).  Here the storage is resident in HBM, so the pointers go into a host
+    // snapshot: sync_host() takes it (one device -> host copy of keys and values), push_host() writes the snapshot's
+    // values back for callers that modified them through the pointers (elements that became zero in every row are dropped,
+    // as by del_at_pos).  Any call that changes the store on the device (perform_add, the iterate calls, del_at_pos,
+    // row operations) invalidates the snapshot; the accessors then take a new one.  Callers that drive the store through
+    // the C-ABI directly (the iterate calls on `h`) call invalidate_host() themselves.
+  private:
+    std::vector<uint64_t> host_keys_;
+    std::vector<double> host_vals_;  // n_vecs rows, row stride host_keys_.size()
+    Matrix<uint8_t> host_idx_, host_occ_;
+    std::vector<double> host_matr_el_;
+    bool host_valid_ = false;
+    std::function<double(const uint8_t *)> diag_calc_;
+
+  public:
+    void invalidate_host() { host_valid_ = false; }
+    void sync_host() {
+        download(host_keys_, host_vals_);
+        const size_t n = host_keys_.size(), nb = ceiling(n_bits, 8);
+        host_idx_.reshape(n ? n : 1, nb);
+        host_occ_.reshape(n ? n : 1, n_elec);
+        for (size_t i = 0; i < n; i++) {
+            key_to_bytes(host_keys_[i], host_idx_[i], nb);
+            gen_orb_list(host_idx_[i], host_occ_[i]);
+        }
+        host_matr_el_.assign(n, std::nan(""));
+        host_valid_ = true;
+    }
+    void push_host() {
+        if (!host_valid_) throw std::runtime_error("DistVec::push_host without a host snapshot (call sync_host first)");
+        upload(host_keys_, host_vals_);
+        host_valid_ = false;
+    }
+    double *values() {  // :505-507: the current row
+        if (!host_valid_) sync_host();
+        return host_vals_.data() + (size_t)curr_vec_idx_ * host_keys_.size();
+    }
+    uint8_t num_vecs() const { return (uint8_t)n_vecs; }
+    Matrix<uint8_t> &indices() {  // :513-515: curr_size x n_bytes bit strings
+        if (!host_valid_) sync_host();
+        return host_idx_;
+    }
+    Matrix<uint8_t> &occ_orbs() {  // :661-663
+        if (!host_valid_) sync_host();
+        return host_occ_;
+    }
+    uint8_t *orbs_at_pos(size_t pos) { return occ_orbs()[pos]; }  // :657-659
+    double *operator[](size_t pos) { return values() + pos; }     // :643-645
+    double *operator()(size_t vec_idx, size_t pos) {               // :647-649
+        if (!host_valid_) sync_host();
+        return host_vals_.data() + vec_idx * host_keys_.size() + pos;
+    }
+    // the diagonal matrix element function the reference's constructor takes (vec_utils.hpp:154-198)
+    void set_diag_calc(std::function<double(const uint8_t *)> f) { diag_calc_ = std::move(f); }
+    double matr_el_at_pos(size_t pos) {  // :672-677, cached per snapshot
+        if (!host_valid_) sync_host();
+        if (!diag_calc_) throw std::runtime_error("DistVec::matr_el_at_pos: no diagonal matrix element function (set_diag_calc)");
+        if (std::isnan(host_matr_el_[pos])) host_matr_el_[pos] = diag_calc_(host_occ_[pos]);
+        return host_matr_el_[pos];
+    }
+    double internal_dot(uint8_t idx1, uint8_t idx2) {  // :324-340
+        if (idx1 >= n_vecs || idx2 >= n_vecs) {
+            std::stringstream error;
+            error << "Error: idx" << (idx1 >= n_vecs ? 1 : 2) << " argument to internal_dot ("
+                  << (unsigned)(idx1 >= n_vecs ? idx1 : idx2) << ") exceeds bounds of value matrix (" << n_vecs << ")";
+            throw std::runtime_error(error.str());
+        }
+        if (!host_valid_) sync_host();
+        const size_t n = host_keys_.size();
+        double dprod = 0;
+        for (size_t i = 0; i < n; i++) dprod += host_vals_[idx1 * n + i] * host_vals_[idx2 * n + i];
+        return dprod;
+    }
+    double dense_norm() {  // :903-917 (single rank)
+        if (n_dense == 0) return 0;
+        const double *v = values();
+        double result = 0;
+        for (size_t i = 0; i < n_dense && i < host_keys_.size(); i++) result += std::fabs(v[i]);
+        return result;
+    }
+    uint8_t gen_orb_list(const uint8_t *det, uint8_t *occ) {  // :212-214 (HubHolVec: electrons only, hh_vec.hpp:43-45)
+        if (hh_sites_) {
+            uint8_t tmp[64];
+            uint8_t n = find_bits(det, tmp, (uint8_t)ceiling(n_bits, 8)), k = 0;
+            for (uint8_t i = 0; i < n; i++)
+                if (tmp[i] < 2 * hh_sites_) occ[k++] = tmp[i];
+            return k;
+        }
+        return find_bits(det, occ, (uint8_t)ceiling(n_bits, 8));
+    }
+    uintmax_t idx_to_hash(const uint8_t *idx, uint8_t *orbs) {  // :389-400
+        if (hh_sites_) throw std::runtime_error("DistVec::idx_to_hash: HubHolVec hashes live on the device (fries_hash_owner)");
+        if (gen_orb_list(idx, orbs) != n_elec) {
+            std::stringstream error;
+            error << "Determinant ";
+            for (size_t b = 0; b < ceiling(n_bits, 8); b++) {
+                char hex[3];
+                snprintf(hex, sizeof(hex), "%02x", idx[b]);
+                error << hex;
+            }
+            error << " created with an incorrect number of electrons";
+            throw std::runtime_error(error.str());
+        }
+        return hash_fxn(vec_scr_.data(), orbs, n_elec);
+    }
+    int idx_to_proc(const uint8_t *idx, const uint8_t *orbs, int n_procs = 1) {  // :373-379
+        (void)idx;
+        return (int)(hash_fxn(proc_scr_.data(), orbs, n_elec) % (uintmax_t)n_procs);
+    }
+    int idx_to_proc(const uint8_t *idx, int n_procs = 1) {  // :360-365
+        uint8_t orbs[64];
+        gen_orb_list(idx, orbs);
+        return idx_to_proc(idx, orbs, n_procs);
+    }
+    // pointer forms of add (:418-436) and dot (:242-253)
+    bool add(const uint8_t *idx, double val, uint8_t ini_flag) {
+        add(key_from_bytes(idx, ceiling(n_bits, 8)), val, ini_flag);
+        return true;  // the buffer grows on demand: never full
+    }
+    bool add(const uint8_t *idx, const uint8_t *, double val, uint8_t ini_flag) { return add(idx, val, ini_flag); }
+    double dot(Matrix<uint8_t> &idx2, const double *vals2, size_t num2) {
+        std::vector<uint64_t> keys(num2);
+        for (size_t i = 0; i < num2; i++) keys[i] = key_from_bytes(idx2[i], idx2.cols());
+        double out;
+        check(fries_vec_dot(h, keys.data(), vals2, num2, curr_vec_idx_, &out));
+        return out;
+    }
+    double dot(Matrix<uint8_t> &idx2, const double *vals2, size_t num2, const uintmax_t *) { return dot(idx2, vals2, num2); }
+    // add_elements :606-641: `count` received elements, bit n_bits of an index = initiator flag (Adder::add :965)
+    void add_elements(const uint8_t *indices, const double *vals, size_t count, size_t origin) {
+        const size_t nb = ceiling(n_bits + 1, 8);
+        std::vector<uint64_t> keys(count);
+        std::vector<uint8_t> ini(count);
+        for (size_t i = 0; i < count; i++) {
+            uint64_t k = key_from_bytes(indices + i * nb, nb);
+            ini[i] = (uint8_t)(k >> n_bits & 1);
+            keys[i] = k & ~(1ull << n_bits);
+        }
+        check(fries_vec_add(h, keys.data(), vals, ini.data(), count, (unsigned)origin, curr_vec_idx_));
+        host_valid_ = false;
+    }
+    size_t adder_size() const { return max_size_; }  // :523-525: add() never reports a full buffer here
+    void set_min_del_idx(size_t idx) { check(fries_vec_set_min_del_idx(h, idx)); }  // :501-503
+    void fix_min_del_idx() { set_min_del_idx(curr_size()); }                         // :497-499
+    // :343-353 doubles the arrays; the device store is allocated once (size it with --max_dets)
+    void expand() { throw std::runtime_error("DistVec::expand: the device store has a fixed capacity (max_size)"); }
+    void collect_procs() {}  // :920-952: single rank, nothing to gather
+    void print_ht() {         // :405-407: the device index is one open-addressing table, not per-bucket chains
+        std::cout << "hash index: " << curr_size() << " of " << max_size_ << " elements stored\n";
     }
     uint64_t tot_sgn_coh() {
         uint64_t n;
@@ -466,6 +668,7 @@ class DistVec {
     }
     void upload(const std::vector<uint64_t> &dets, const std::vector<double> &vals) {
         check(fries_vec_upload(h, dets.data(), vals.data(), dets.size()));
+        host_valid_ = false;
     }
     // DistVec::save vec_utils.hpp:721-745: dets<rank>.dat = curr_size x n_bytes, vals<rank>.dat = n_vecs rows, dense.txt
     void save(const std::string &path) {

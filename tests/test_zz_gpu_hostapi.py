@@ -1,0 +1,24 @@
+"""GPU tier, after the verified files on purpose: the raw-pointer view of the C++ mirror fries::DistVec (values / indices /
+occ_orbs / operator[] / operator() / orbs_at_pos / matr_el_at_pos / internal_dot / dense_norm / idx_to_hash / idx_to_proc /
+add_elements / push_host; FRIES/vec_utils.hpp:200-953) checked by the self-checking program
+fries_b200/host/distvec_check.cpp.  The accessors are host code over C-ABI calls that the verified tier covers
+(fries_vec_download / upload / add / dot), written after this round's GPU budget was spent: the program is a child process
+and the case a non-strict xfail until a green run is on record.  Pure-host pieces: tests/test_hostapi_cpu.py (CPU tier)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "fries_b200", "host", "bin", "distvec_check")
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(200),
+              pytest.mark.xfail(strict=False, reason="first GPU run of distvec_check is pending (written without GPU access)")]
+
+
+def test_distvec_raw_pointer_view():
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "fries_b200", "host")])
+    r = subprocess.run([EXE], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout[-2000:]
