@@ -9,6 +9,7 @@
 //   argparse kwargs    FRIES/Ext_Libs/argparse.hpp      -> fries::Args (same --key value syntax and failure modes)
 // All arithmetic on vectors happens in libfries_b200.so (CUDA); this file is marshalling, file formats, control flow.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -92,6 +93,93 @@ inline uintmax_t hash_fxn(const uint32_t *scrambler, const uint8_t *occ_orbs, un
     for (unsigned i = 0; i < n_elec; i++) hash = 1099511628211ULL * hash + (uint32_t)((i + 1) * scrambler[occ_orbs[i]]);
     for (unsigned i = 0; i < n_phonon; i++) hash = 1099511628211ULL * hash + (uint32_t)((i + 1) * scrambler[phonon_nums[i]]);
     return hash;
+}
+
+// ---- FRIES/det_store.h, math_utils.h, fci_utils.h on the reference's byte strings (host twins of the device functions
+// fr_* in csrc/common.cuh; determinants of up to 64 bits) --------------------------------------------------------------
+inline int read_bit(const uint8_t *bit_str, uint8_t bit_idx) { return bit_str[bit_idx / 8] >> (bit_idx % 8) & 1; }   // det_store.h:23-26
+inline void zero_bit(uint8_t *bit_str, uint8_t bit_idx) { bit_str[bit_idx / 8] &= (uint8_t)~(1u << (bit_idx % 8)); }  // det_store.c:11-15
+inline void set_bit(uint8_t *bit_str, uint8_t bit_idx) { bit_str[bit_idx / 8] |= (uint8_t)(1u << (bit_idx % 8)); }    // det_store.c:17-21
+// print_str det_store.c:23-29: hexadecimal, most significant byte first
+inline void print_str(const uint8_t *bit_str, uint8_t n_bytes, char *out_str) {
+    for (unsigned b = 0; b < n_bytes; b++) snprintf(out_str + 2 * b, 3, "%02x", bit_str[n_bytes - 1 - b]);
+    out_str[2 * n_bytes] = 0;
+}
+// bits_between math_utils.c:9-58: 1 bits strictly between positions a and b
+inline unsigned bits_between(const uint8_t *bit_str, uint8_t a, uint8_t b) {
+    const unsigned lo = a < b ? a : b, hi = a < b ? b : a;
+    const uint64_t key = key_from_bytes(bit_str, hi / 8 + 1);
+    const uint64_t below_hi = hi ? (~0ull >> (64 - hi)) : 0ull, upto_lo = ~0ull >> (63 - lo);
+    return (unsigned)__builtin_popcountll(key & below_hi & ~upto_lo);
+}
+// find_diff_bits math_utils.c:100-131: positions of the first 4 differing bits; UINT8_MAX when more than 4 differ
+inline uint8_t find_diff_bits(const uint8_t *str1, const uint8_t *str2, uint8_t *bits, uint8_t n_bytes) {
+    uint8_t n = 0;
+    for (unsigned b = 0; b < n_bytes; b++) {
+        uint8_t x = str1[b] ^ str2[b];
+        for (unsigned i = 0; i < 8; i++)
+            if (x >> i & 1) {
+                if (n == 4) return UINT8_MAX;
+                bits[n++] = (uint8_t)(8 * b + i);
+            }
+    }
+    return n;
+}
+// excite_sign fci_utils.c:128-135: (-1)^(electrons strictly between the two operators)
+inline int excite_sign(uint8_t cre_op, uint8_t des_op, const uint8_t *det) {
+    return (bits_between(det, cre_op, des_op) & 1) ? -1 : 1;
+}
+// sing_det_parity fci_utils.c:46-51; orbs = {occupied, virtual}
+inline int sing_det_parity(uint8_t *det, const uint8_t *orbs) {
+    zero_bit(det, orbs[0]);
+    int sign = excite_sign(orbs[1], orbs[0], det);
+    set_bit(det, orbs[1]);
+    return sign;
+}
+inline int sing_parity(const uint8_t *det, const uint8_t *orbs) { return excite_sign(orbs[1], orbs[0], det); }  // :54-57
+inline void sing_det(uint8_t *det, const uint8_t *orbs) {                                                          // :59-62
+    zero_bit(det, orbs[0]);
+    set_bit(det, orbs[1]);
+}
+// doub_det_parity fci_utils.c:67-75; orbs = {occ, occ, virt, virt}: both electrons are removed first, then each
+// replacement orbs[i] -> orbs[i + 2] contributes its sign on that doubly-annihilated string
+inline int doub_det_parity(uint8_t *det, const uint8_t *orbs) {
+    zero_bit(det, orbs[0]);
+    zero_bit(det, orbs[1]);
+    int sign = excite_sign(orbs[2], orbs[0], det) * excite_sign(orbs[3], orbs[1], det);
+    set_bit(det, orbs[2]);
+    set_bit(det, orbs[3]);
+    return sign;
+}
+inline int doub_parity(const uint8_t *det, const uint8_t *orbs) {  // :86-94: the string is left as it is
+    uint8_t tmp[8] = {0};
+    const unsigned hi = std::max(std::max(orbs[0], orbs[1]), std::max(orbs[2], orbs[3]));
+    memcpy(tmp, det, hi / 8 + 1);
+    zero_bit(tmp, orbs[0]);
+    zero_bit(tmp, orbs[1]);
+    return excite_sign(orbs[2], orbs[0], tmp) * excite_sign(orbs[3], orbs[1], tmp);
+}
+inline void doub_det(uint8_t *det, const uint8_t *orbs) {  // :77-84
+    zero_bit(det, orbs[0]);
+    zero_bit(det, orbs[1]);
+    set_bit(det, orbs[2]);
+    set_bit(det, orbs[3]);
+}
+// find_nth_virt fci_utils.c:138-148: the n-th orbital of the given spin that is not in the occupied list
+inline uint8_t find_nth_virt(const uint8_t *occ_orbs, int spin, uint8_t n_elec, uint8_t n_orb, uint8_t n) {
+    uint8_t virt = (uint8_t)(n_orb * spin + n);
+    for (unsigned i = n_elec / 2 * spin; i < n_elec && occ_orbs[i] <= virt; i++) virt++;
+    return virt;
+}
+// flip_spins fci_utils.c:150-165: exchange the alpha (bits [0, n_orb)) and beta (bits [n_orb, 2 n_orb)) strings
+inline void flip_spins(const uint8_t *det_in, uint8_t *det_out, uint8_t n_orb) {
+    const size_t nb = ceiling(2 * (size_t)n_orb, 8);
+    const uint64_t k = key_from_bytes(det_in, nb), half = (1ull << n_orb) - 1;
+    key_to_bytes(((k & half) << n_orb) | (k >> n_orb & half), det_out, nb);
+}
+// gen_hf_bitstring fci_utils.c:10-43, byte-string form
+inline void gen_hf_bitstring(unsigned n_orb, unsigned n_elec, uint8_t *det) {
+    key_to_bytes(gen_hf_bitstring(n_orb, n_elec), det, ceiling(2 * (size_t)n_orb, 8));
 }
 
 // ---- command line: argparse::Args semantics (Ext_Libs/argparse.hpp:347-393) ---------------------------------------
@@ -597,12 +685,9 @@ class DistVec {
         if (hh_sites_) throw std::runtime_error("DistVec::idx_to_hash: HubHolVec hashes live on the device (fries_hash_owner)");
         if (gen_orb_list(idx, orbs) != n_elec) {
             std::stringstream error;
-            error << "Determinant ";
-            for (size_t b = 0; b < ceiling(n_bits, 8); b++) {
-                char hex[3];
-                snprintf(hex, sizeof(hex), "%02x", idx[b]);
-                error << hex;
-            }
+            char det_txt[2 * 8 + 1];
+            print_str(idx, (uint8_t)ceiling(n_bits, 8), det_txt);
+            error << "Determinant " << det_txt;
             error << " created with an incorrect number of electrons";
             throw std::runtime_error(error.str());
         }

@@ -2,7 +2,52 @@
 // Matrix<T>, find_bits, hash_fxn, key <-> byte string.  stdin: n_bits n_elec n_scr scr[...] n_keys keys[...];
 // stdout: one line per key "hash n_bits_found" -- compared with the oracle by tests/test_hostapi_cpu.py.
 #include "../../fries_b200/host/fries_host.hpp"
-int main() {
+// mode "bits": stdin n_orb n_rec, then records "key o0 o1 v2 v3 a b"; stdout per record:
+// bits_between(a,b) sing_sign sing_key doub_sign doub_key sing_parity doub_parity flipped_key excite_sign(a,b)
+static int bits_mode() {
+    unsigned n_orb;
+    size_t n;
+    std::cin >> n_orb >> n;
+    const size_t nb = fries::ceiling(2 * n_orb, 8);
+    for (size_t r = 0; r < n; r++) {
+        uint64_t k;
+        unsigned o[4], a, b;
+        std::cin >> k >> o[0] >> o[1] >> o[2] >> o[3] >> a >> b;
+        uint8_t det[8], orbs[4] = {(uint8_t)o[0], (uint8_t)o[1], (uint8_t)o[2], (uint8_t)o[3]}, so[2] = {orbs[0], orbs[2]};
+        fries::key_to_bytes(k, det, 8);
+        std::cout << fries::bits_between(det, (uint8_t)a, (uint8_t)b) << " ";
+        uint8_t d1[8], d2[8], d3[8];
+        memcpy(d1, det, 8);
+        int s1 = fries::sing_det_parity(d1, so);
+        memcpy(d3, det, 8);
+        fries::sing_det(d3, so);
+        if (memcmp(d1, d3, 8)) return 6;
+        memcpy(d2, det, 8);
+        int s2 = fries::doub_det_parity(d2, orbs);
+        memcpy(d3, det, 8);
+        fries::doub_det(d3, orbs);
+        if (memcmp(d2, d3, 8)) return 7;
+        uint8_t fl[8] = {0};
+        fries::flip_spins(det, fl, (uint8_t)n_orb);
+        for (unsigned i = 0; i < 64; i++)
+            if (fries::read_bit(det, (uint8_t)i) != (int)(k >> i & 1)) return 8;
+        std::cout << s1 << " " << fries::key_from_bytes(d1, 8) << " " << s2 << " " << fries::key_from_bytes(d2, 8) << " "
+                  << fries::sing_parity(det, so) << " " << fries::doub_parity(det, orbs) << " " << fries::key_from_bytes(fl, nb) << " "
+                  << fries::excite_sign((uint8_t)a, (uint8_t)b, det) << "\n";
+    }
+    char txt[17];
+    uint8_t three[3] = {0x01, 0x23, 0xab};
+    fries::print_str(three, 3, txt);
+    if (std::string(txt) != "ab2301") return 9;
+    uint8_t x[3] = {0x81, 0, 0x10}, y[3] = {0x80, 0, 0x00}, bits[4];
+    if (fries::find_diff_bits(x, y, bits, 3) != 2 || bits[0] != 0 || bits[1] != 20) return 10;
+    uint8_t z[3] = {0x7e, 0, 0};
+    if (fries::find_diff_bits(x, z, bits, 3) != UINT8_MAX) return 11;
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "bits") return bits_mode();
     unsigned n_bits, n_elec, n_scr;
     size_t n_keys;
     std::cin >> n_bits >> n_elec >> n_scr;

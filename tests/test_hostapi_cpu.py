@@ -8,16 +8,22 @@ import subprocess
 import numpy as np
 
 import oraclelib
+import reflib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def test_host_hash_and_bits(tmp_path):
+def build(tmp_path):
     exe = str(tmp_path / "hostapi_check")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unused-function", os.path.join(HERE, "hostcheck", "hostapi_check.cpp"),
                            "-o", exe, "-L" + os.path.join(ROOT, "fries_b200"), "-lfries_b200",
                            "-Wl,-rpath," + os.path.join(ROOT, "fries_b200")])
+    return exe
+
+
+def test_host_hash_and_bits(tmp_path):
+    exe = build(tmp_path)
     rng = np.random.default_rng(5)
     for n_bits in (44, 52, 30):
         scr = rng.integers(0, 2**32, n_bits, dtype=np.uint64).astype(np.uint32)
@@ -31,3 +37,53 @@ def test_host_hash_and_bits(tmp_path):
             assert [int(x) for x in got[:, 0]] == [int(x) for x in h]
             assert [int(x) % n_procs for x in got[:, 0]] == [int(x) for x in o]
         assert [int(x) for x in got[:, 1]] == [bin(int(k)).count("1") for k in keys]
+
+
+def test_host_bit_string_functions(tmp_path):
+    """det_store.h / math_utils.h / fci_utils.h twins on byte strings against the compiled reference (oracle/_ref) where it
+    is built, else against the oracle: bits_between, excite_sign, sing/doub_det_parity, sing/doub_parity, sing/doub_det,
+    flip_spins, read_bit, print_str, find_diff_bits"""
+    exe = build(tmp_path)
+    rng = np.random.default_rng(9)
+    L = reflib.lib() if reflib.available() else None
+    O = oraclelib.lib()
+    for n_orb in (10, 22, 26, 31):
+        recs = []
+        for _ in range(400):
+            k = int(rng.integers(0, 2**(2 * n_orb), dtype=np.uint64))
+            occ = [i for i in range(2 * n_orb) if k >> i & 1]
+            virt = [i for i in range(2 * n_orb) if not k >> i & 1]
+            if len(occ) < 2 or len(virt) < 2:
+                continue
+            o = sorted(int(x) for x in rng.choice(occ, 2, replace=False))
+            v = sorted(int(x) for x in rng.choice(virt, 2, replace=False))
+            a, b = (int(x) for x in rng.choice(2 * n_orb, 2, replace=False))
+            recs.append((k, o[0], o[1], v[0], v[1], a, b))
+        txt = f"{n_orb} {len(recs)}\n" + "\n".join(" ".join(map(str, r)) for r in recs) + "\n"
+        r = subprocess.run([exe, "bits"], input=txt, stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.returncode
+        rows = [[int(x) for x in ln.split()] for ln in r.stdout.splitlines()]
+        assert len(rows) == len(recs)
+        half = (1 << n_orb) - 1
+        for (k, o0, o1, v2, v3, a, b), got in zip(recs, rows):
+            nb = O.fo_bits_between(k, a, b)
+            so, do = np.array([o0, v2], np.uint8), np.array([o0, o1, v2, v3], np.uint8)
+            k_s = (k & ~(1 << o0)) | (1 << v2)
+            k_d = (k & ~((1 << o0) | (1 << o1))) | (1 << v2) | (1 << v3)
+            flipped = ((k & half) << n_orb) | (k >> n_orb & half)
+            if L is not None:
+                import ctypes as C
+                assert nb == L.ref_bits_between(k, a, b)
+                kk = C.c_uint64(k)
+                s1 = L.ref_sing_det_parity(C.byref(kk), so)
+                assert kk.value == k_s
+                kk = C.c_uint64(k)
+                s2 = L.ref_doub_det_parity(C.byref(kk), do)
+                assert kk.value == k_d
+                p1, p2 = L.ref_sing_parity(k, so), L.ref_doub_parity(k, do)
+            else:
+                inner = lambda key, x, y: bin(key & ((1 << max(x, y)) - 1) & ~((2 << min(x, y)) - 1)).count("1")
+                s1 = p1 = -1 if inner(k & ~(1 << o0), o0, v2) & 1 else 1
+                kz = k & ~((1 << o0) | (1 << o1))
+                s2 = p2 = (-1 if inner(kz, v2, o0) & 1 else 1) * (-1 if inner(kz, v3, o1) & 1 else 1)
+            assert got == [nb, s1, k_s, s2, k_d, p1, p2, flipped, -1 if nb & 1 else 1], (k, o0, o1, v2, v3, a, b, got)
