@@ -142,6 +142,43 @@ int main() {
             threw = std::string(e.what()).find("incorrect number of electrons") != std::string::npos;
         }
         CHECK(threw);
+        // ---- Molecule: the reference's molecule.hpp / heat_bathPP.hpp entry points on byte strings ----
+        {
+            MolInput mi;
+            mi.n_orb = n_orb;
+            mi.n_elec = n_elec;
+            mi.n_frz = 0;
+            mi.symm.resize(n_orb);
+            for (unsigned i = 0; i < n_orb; i++) mi.symm[i] = (uint8_t)(i % 4);
+            mi.hcore.assign((size_t)n_orb * n_orb, 0.0);
+            for (unsigned i = 0; i < n_orb; i++)
+                for (unsigned j = 0; j <= i; j++)
+                    mi.hcore[i * n_orb + j] = mi.hcore[j * n_orb + i] = i == j ? -2.0 + 0.3 * i : 0.01 * (i + j);
+            const size_t n_pair = (size_t)n_orb * (n_orb + 1) / 2;
+            mi.eris_packed.assign(n_pair * (n_pair + 1) / 2, 0.0);
+            for (size_t i = 0; i < mi.eris_packed.size(); i++) mi.eris_packed[i] = 0.05 + 0.001 * (double)(i % 97);
+            Molecule mol(ctx, mi);
+            uint8_t hf[3];
+            gen_hf_bitstring(n_orb, n_elec, hf);
+            std::vector<uint8_t> sing(2 * 256), doub(4 * 4096);
+            size_t ns = mol.sing_ex_symm(hf, (uint8_t(*)[2])sing.data(), 256);
+            size_t nd = mol.doub_ex_symm(hf, (uint8_t(*)[4])doub.data(), 4096);
+            CHECK(ns == mol.count_singex(key_from_bytes(hf, 3)) && nd == mol.count_doub_ex(key_from_bytes(hf, 3)));
+            CHECK(ns > 0 && nd > 0);
+            for (size_t e = 0; e < ns; e++) {
+                const uint8_t *o = &sing[2 * e];
+                CHECK(read_bit(hf, o[0]) && !read_bit(hf, o[1]) && o[0] / n_orb == o[1] / n_orb &&
+                      mi.symm[o[0] % n_orb] == mi.symm[o[1] % n_orb]);
+            }
+            for (size_t e = 0; e < nd; e++) {
+                const uint8_t *o = &doub[4 * e];
+                CHECK(read_bit(hf, o[0]) && read_bit(hf, o[1]) && !read_bit(hf, o[2]) && !read_bit(hf, o[3]));
+                CHECK((mi.symm[o[0] % n_orb] ^ mi.symm[o[1] % n_orb] ^ mi.symm[o[2] % n_orb] ^ mi.symm[o[3] % n_orb]) == 0);
+            }
+            CHECK(std::isfinite(mol.diag_matrel(hf)) && mol.diag_matrel(hf) == mol.diag_matrel(key_from_bytes(hf, 3)));
+            CHECK(std::isfinite(mol.sing_matr_el_nosgn(&sing[0], hf)) && std::isfinite(mol.doub_matr_el_nosgn(&doub[0])));
+            CHECK(mol.calc_unnorm_wt(&doub[0]) > 0 && mol.calc_norm_wt(&doub[0], hf) > 0);
+        }
     } catch (std::exception &e) {
         std::cout << "Exception : " << e.what() << std::endl;
         return 2;

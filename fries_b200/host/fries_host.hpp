@@ -485,6 +485,45 @@ struct Molecule {
         check(fries_mol_sing_ex(h, &det, 1, off, nullptr, 0));
         return off[1];
     }
+    // sing_ex_symm molecule.cpp:178-203 / doub_ex_symm :108-175 on the reference's byte strings: every symmetry-allowed
+    // excitation of `det` in the reference's order, rows {occ, virt} / {occ, occ, virt, virt}; returns their number
+    size_t sing_ex_symm(const uint8_t *det, uint8_t (*res_arr)[2], size_t cap) {
+        uint64_t key = key_from_bytes(det, ceiling(2 * (size_t)n_orb, 8)), off[2];
+        check(fries_mol_sing_ex(h, &key, 1, off, (uint8_t *)res_arr, cap));
+        return off[1];
+    }
+    size_t doub_ex_symm(const uint8_t *det, uint8_t (*res_arr)[4], size_t cap) {
+        uint64_t key = key_from_bytes(det, ceiling(2 * (size_t)n_orb, 8)), off[2];
+        check(fries_mol_doub_ex(h, &key, 1, off, (uint8_t *)res_arr, cap));
+        return off[1];
+    }
+    // sing_matr_el_nosgn molecule.cpp:76-105 (needs the determinant for the sum over occupied orbitals),
+    // doub_matr_el_nosgn :26-42
+    double sing_matr_el_nosgn(const uint8_t *ex_orbs, const uint8_t *det) {
+        uint64_t key = key_from_bytes(det, ceiling(2 * (size_t)n_orb, 8));
+        double out;
+        check(fries_mol_sing_el(h, &key, ex_orbs, 1, &out));
+        return out;
+    }
+    double doub_matr_el_nosgn(const uint8_t *ex_orbs) {
+        double out;
+        check(fries_mol_doub_el(h, ex_orbs, 1, &out));
+        return out;
+    }
+    double diag_matrel(const uint8_t *det) { return diag_matrel(key_from_bytes(det, ceiling(2 * (size_t)n_orb, 8))); }
+    // calc_unnorm_wt heat_bathPP.cpp:414-439 / calc_norm_wt :442-598: total HB-PP sampling weight of a double excitation
+    double calc_unnorm_wt(const uint8_t *orbs) {
+        uint64_t key = gen_hf_bitstring(n_orb, n_elec_total - n_frz);  // not used by the un-normalised weight; must be valid
+        double out;
+        check(fries_mol_hb_wt(h, 0, &key, orbs, 1, &out));
+        return out;
+    }
+    double calc_norm_wt(const uint8_t *orbs, const uint8_t *det) {
+        uint64_t key = key_from_bytes(det, ceiling(2 * (size_t)n_orb, 8));
+        double out;
+        check(fries_mol_hb_wt(h, 1, &key, orbs, 1, &out));
+        return out;
+    }
 };
 
 // DistVec<double> FRIES/vec_utils.hpp:121-953, single rank, resident on the GPU.
