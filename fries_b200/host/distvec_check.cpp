@@ -178,6 +178,83 @@ int main() {
             CHECK(std::isfinite(mol.diag_matrel(hf)) && mol.diag_matrel(hf) == mol.diag_matrel(key_from_bytes(hf, 3)));
             CHECK(std::isfinite(mol.sing_matr_el_nosgn(&sing[0], hf)) && std::isfinite(mol.doub_matr_el_nosgn(&doub[0])));
             CHECK(mol.calc_unnorm_wt(&doub[0]) > 0 && mol.calc_norm_wt(&doub[0], hf) > 0);
+            // apply_HBPP_sys / apply_HBPP_piv from one determinant (row 1 of all_dets): every sample is an excitation of it
+            Matrix<uint8_t> all_dets(2, 3);
+            memcpy(all_dets[1], hf, 3);
+            auto valid = [&](HBCompress &cs, const char *what) {
+                CHECK(cs.vec_len > 0 && cs.vec_len <= cs.vec1.size());
+                for (size_t k = 0; k < cs.vec_len; k++) {
+                    const uint8_t *o = cs.orb_indices1[k];
+                    bool single = o[2] == 0 && o[3] == 0;  // frisys_mol.cpp:451
+                    bool ok = cs.det_indices2[k] == 1 && cs.vec1[k] != 0 && std::isfinite(cs.vec1[k]) && read_bit(hf, o[0]) &&
+                              (single ? !read_bit(hf, o[1]) : (read_bit(hf, o[1]) && !read_bit(hf, o[2]) && !read_bit(hf, o[3])));
+                    if (!ok) {
+                        std::cout << what << ": sample " << k << " is not an excitation of the input determinant" << std::endl;
+                        n_fail++;
+                        break;
+                    }
+                }
+            };
+            {
+                HBCompressSys cs(4096, 32);
+                cs.vec1[0] = 1.0;
+                cs.det_indices1[0] = 1;
+                cs.vec_len = 1;
+                std::mt19937 g(3), g_ref(3);
+                apply_HBPP_sys(mol, all_dets, &cs, 0.9, true, g, 300);
+                g_ref.discard(5);  // one uniform per compression stage
+                CHECK(g() == g_ref());
+                valid(cs, "apply_HBPP_sys");
+                std::cout << "apply_HBPP_sys: " << cs.vec_len << " samples" << std::endl;
+            }
+            try {
+                HBCompressPiv cs(4096, 32);
+                cs.vec1[0] = 1.0;
+                cs.det_indices1[0] = 1;
+                cs.vec_len = 1;
+                std::mt19937 g(3);
+                apply_HBPP_piv(mol, all_dets, &cs, 0.9, true, g, 300);
+                valid(cs, "apply_HBPP_piv");
+                std::cout << "apply_HBPP_piv: " << cs.vec_len << " samples" << std::endl;
+            } catch (std::exception &e) {
+                std::cout << "apply_HBPP_piv: Exception : " << e.what() << std::endl;
+                n_fail++;
+            }
+        }
+        // comp_sub with more samples than sub-weights is the identity (tests/test_compression.cpp:64-118 in the reference)
+        {
+            const size_t count = 5, n_sub = 4;
+            std::vector<double> values{1.0, 2.0, 0.5, 3.0, 1.5}, new_vals(64), wt_remain(count);
+            std::vector<unsigned int> n_div(count, 0);
+            Matrix<double> sub_weights(count, n_sub);
+            Matrix<bool> keep_idx(count, n_sub);
+            for (size_t i = 0; i < count; i++)
+                for (size_t j = 0; j < n_sub; j++) sub_weights(i, j) = 0.25;
+            std::vector<size_t> new_idx(2 * 64);
+            size_t n = comp_sub(ctx, values.data(), count, n_div.data(), sub_weights, keep_idx, nullptr, 64, wt_remain.data(), 0.37,
+                                new_vals.data(), (size_t(*)[2])new_idx.data());
+            CHECK(n == count * n_sub);
+            double tot = 0;
+            for (size_t k = 0; k < n && k < 64; k++) {
+                CHECK(new_idx[2 * k] < count && new_idx[2 * k + 1] < n_sub);
+                CHECK(std::fabs(new_vals[k] - values[new_idx[2 * k]] * 0.25) <= 1e-14);
+                tot += new_vals[k];
+            }
+            CHECK(std::fabs(tot - 8.0) <= 1e-12);
+        }
+        // compress_vecs_sys / compress_vecs on the store: at most compress_size (+ preserved) elements stay, the norm of
+        // the row is conserved by the systematic scheme
+        {
+            std::vector<size_t> srt;
+            std::vector<bool> keep, del;
+            std::mt19937 g(5);
+            double before = vec.local_norm();
+            compress_vecs_sys(vec, 0, 1, 50, srt, keep, del, g);
+            CHECK(vec.curr_size() <= 50 && vec.curr_size() > 0);
+            CHECK(std::fabs(vec.local_norm() - before) <= 1e-9 * before);
+            compress_vecs(vec, 0, 1, 20, srt, keep, del, g);
+            CHECK(vec.curr_size() <= 20 && vec.curr_size() > 0);
+            CHECK(std::fabs(vec.local_norm() - before) <= 1e-9 * before);
         }
     } catch (std::exception &e) {
         std::cout << "Exception : " << e.what() << std::endl;

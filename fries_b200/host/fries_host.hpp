@@ -929,6 +929,108 @@ inline void piv_comp_parallel(Context &c, double *vec_vals, size_t vec_len, uint
     rn_gen.discard(used);
     for (size_t i = 0; i < vec_len; i++) keep_scratch[i] = keep[i];
 }
+// comp_sub compress_utils.cpp:797-820 (find_keep_sub + sys_sub; keep_idx and wt_remain are scratch in the reference and
+// unused here).  new_vals / new_idx must hold n_samp entries, as there.
+inline size_t comp_sub(Context &c, double *values, size_t count, unsigned int *n_div, Matrix<double> &sub_weights,
+                       Matrix<bool> &, uint16_t *sub_sizes, unsigned int n_samp, double *, double rand_num, double *new_vals,
+                       size_t new_idx[][2]) {
+    static_assert(sizeof(size_t) == sizeof(uint64_t), "new_idx is passed through as uint64_t pairs");
+    size_t n_out = 0;
+    check(fries_comp_sub(c.h, values, count, n_div, sub_weights.data(), sub_weights.cols(), sub_sizes, n_samp, rand_num, new_vals,
+                         (uint64_t *)new_idx, n_samp, &n_out, nullptr, nullptr));
+    return n_out;
+}
+// compress_vecs / compress_vecs_sys FRIES/vec_utils.cpp:10-70 (the three scratch arrays are unused here): rows
+// [start_idx, end_idx) of the resident store, pivotal / systematic; the generator advances as in the reference
+inline void compress_vecs_impl(DistVec &vectors, size_t start_idx, size_t end_idx, unsigned int compress_size, int method,
+                               std::mt19937 &rn_gen) {
+    const size_t rows = end_idx > start_idx ? end_idx - start_idx : 0;
+    std::vector<uint32_t> draws = detail::peek(rn_gen, rows * (method == 0 ? 2 * ((size_t)compress_size + 1) : 1) + 2);
+    size_t used = 0;
+    check(fries_vec_compress(vectors.h, (unsigned)start_idx, (unsigned)end_idx, compress_size, method, draws.data(), draws.size(),
+                             &used));
+    rn_gen.discard(used);
+    vectors.invalidate_host();
+}
+inline void compress_vecs(DistVec &vectors, size_t start_idx, size_t end_idx, unsigned int compress_size, std::vector<size_t> &,
+                          std::vector<bool> &, std::vector<bool> &, std::mt19937 &rn_gen) {
+    compress_vecs_impl(vectors, start_idx, end_idx, compress_size, 0, rn_gen);
+}
+inline void compress_vecs_sys(DistVec &vectors, size_t start_idx, size_t end_idx, unsigned int compress_size,
+                              std::vector<size_t> &, std::vector<bool> &, std::vector<bool> &, std::mt19937 &rn_gen) {
+    compress_vecs_impl(vectors, start_idx, end_idx, compress_size, 1, rn_gen);
+}
+
+// ---- heat_bathPP.hpp: HBCompress* (:247-310) and apply_HBPP_sys (:686-992) / apply_HBPP_piv (:1014-1419) ---------------
+// The caller-visible fields of the reference's structs; the sub-weight matrices and scratch arrays the reference keeps in
+// them live on the device here.
+struct HBCompress {
+    std::vector<double> vec1;                       // values before and after compression
+    size_t vec_len = 0;                             // number of elements before and after
+    std::vector<size_t> det_indices1, det_indices2;  // row of all_dets: of each input / of each sample
+    uint8_t (*orb_indices1)[4];                     // per sample: {occ, occ, virt, virt}, or {occ, virt, 0, 0} for a single
+    explicit HBCompress(size_t length) : vec1(length), det_indices1(length), det_indices2(length), orb_store_(4 * length) {
+        orb_indices1 = (uint8_t(*)[4])orb_store_.data();
+    }
+
+  private:
+    std::vector<uint8_t> orb_store_;
+};
+struct HBCompressSys : HBCompress {
+    HBCompressSys(size_t length, size_t) : HBCompress(length) {}
+};
+struct HBCompressPiv : HBCompress {
+    HBCompressPiv(size_t length, size_t) : HBCompress(length) {}
+};
+namespace detail {
+inline std::vector<uint64_t> hb_keys(Matrix<uint8_t> &all_dets, const HBCompress &cs) {
+    std::vector<uint64_t> keys(cs.vec_len ? cs.vec_len : 1);
+    for (size_t i = 0; i < cs.vec_len; i++) keys[i] = key_from_bytes(all_dets[cs.det_indices1[i]], all_dets.cols());
+    return keys;
+}
+inline void hb_store(HBCompress &cs, const std::vector<double> &val, const std::vector<uint64_t> &det,
+                     const std::vector<uint8_t> &orbs, size_t n_out) {
+    std::vector<size_t> parent(n_out);
+    for (size_t k = 0; k < n_out; k++) parent[k] = cs.det_indices1[det[k]];  // input position -> row of all_dets
+    for (size_t k = 0; k < n_out; k++) {
+        cs.vec1[k] = val[k];
+        cs.det_indices2[k] = parent[k];
+        memcpy(cs.orb_indices1[k], &orbs[4 * k], 4);
+    }
+    cs.vec_len = n_out;
+}
+}  // namespace detail
+// inputs: comp_scratch->vec1[0 .. vec_len), det_indices1; outputs: vec1, det_indices2, orb_indices1, vec_len.  One uniform
+// per compression stage is drawn from mt_obj, as in the reference (:729,765,811,859,910).
+inline void apply_HBPP_sys(Molecule &mol, Matrix<uint8_t> &all_dets, HBCompressSys *comp_scratch, double p_doub, bool new_hb,
+                           std::mt19937 &mt_obj, uint32_t n_samp) {
+    HBCompress &cs = *comp_scratch;
+    double u[5];
+    for (double &x : u) x = mt_obj() / (1. + UINT32_MAX);
+    std::vector<uint64_t> keys = detail::hb_keys(all_dets, cs), det(cs.vec1.size());
+    std::vector<double> val(cs.vec1.size());
+    std::vector<uint8_t> orbs(4 * cs.vec1.size());
+    size_t n_out = 0;
+    check(fries_apply_hbpp_sys(mol.h, keys.data(), cs.vec1.data(), cs.vec_len, p_doub, new_hb, u, n_samp, cs.vec1.size(),
+                               val.data(), det.data(), orbs.data(), cs.vec1.size(), &n_out));
+    detail::hb_store(cs, val, det, orbs, n_out);
+}
+// spin_parity = 0 only (the time-reversal-symmetric variant serves drivers outside the scope)
+inline void apply_HBPP_piv(Molecule &mol, Matrix<uint8_t> &all_dets, HBCompressPiv *comp_scratch, double p_doub, bool new_hb,
+                           std::mt19937 &mt_obj, uint32_t n_samp, int spin_parity = 0) {
+    if (spin_parity != 0) throw std::runtime_error("apply_HBPP_piv: spin_parity != 0 is not supported");
+    HBCompress &cs = *comp_scratch;
+    std::vector<uint32_t> draws = detail::peek(mt_obj, 10 * ((size_t)n_samp + 1) + 64);  // five compressions
+    std::vector<uint64_t> keys = detail::hb_keys(all_dets, cs), det(cs.vec1.size());
+    std::vector<double> val(cs.vec1.size());
+    std::vector<uint8_t> orbs(4 * cs.vec1.size());
+    size_t n_out = 0, used = 0;
+    check(fries_apply_hbpp_piv(mol.h, keys.data(), cs.vec1.data(), cs.vec_len, p_doub, new_hb, draws.data(), draws.size(), &used,
+                               n_samp, cs.vec1.size(), val.data(), det.data(), orbs.data(), cs.vec1.size(), &n_out));
+    mt_obj.discard(used);
+    detail::hb_store(cs, val, det, orbs, n_out);
+}
+
 // adjust_shift compress_utils.cpp:684-693 (scalar control logic of the drivers)
 inline void adjust_shift(double *shift, double one_norm, double *last_norm, double target_norm, double damp_factor) {
     if (*last_norm) {
