@@ -7,13 +7,27 @@ extern __shared__ double fr_dyn_smem[];
 #define FR_STAGE_MIN_CTAS 2  // two 512-thread CTAs per SM (<= 64 registers): the stage passes are latency bound
 #endif
 
-template <int S>
-__global__ void __launch_bounds__(FR_COMP_BLOCK, FR_STAGE_MIN_CTAS)
+// MINCTAS = 2 is the product's configuration.  MINCTAS = 1 (one CTA per SM, up to 128 registers: no spills, half the
+// resident warps) is compiled in as a measurement variant, selected with FRIES_STAGE_CTAS=1 in the environment; same
+// arithmetic, same results.
+template <int S, int MINCTAS>
+__global__ void __launch_bounds__(FR_COMP_BLOCK, MINCTAS)
 hbpp_stage_kernel(MolView gm, HbStageIO io, CompSubBufs bufs, unsigned n_samp, double rn) {
     HbProvider<S> prov;
     prov.m = mol_stage_shared(gm, fr_dyn_smem);
     prov.io = io;
     comp_sub_engine(prov, bufs, n_samp, rn);
+}
+static int stage_min_ctas() {
+    static int v = [] {
+        const char *e = getenv("FRIES_STAGE_CTAS");
+        return (e && e[0] == '1' && e[1] == 0) ? 1 : FR_STAGE_MIN_CTAS;
+    }();
+    return v;
+}
+template <int S>
+static const void *stage_kernel_ptr() {
+    return stage_min_ctas() == 1 ? (const void *)hbpp_stage_kernel<S, 1> : (const void *)hbpp_stage_kernel<S, FR_STAGE_MIN_CTAS>;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -191,19 +205,19 @@ static int launch_stage(fries_hbpp *hb, fries_mol *mol, HbStageIO &io, CompSubBu
     size_t smem = (size_t)mol->view.d.blob_doubles * 8;
     if (hb->grid == 0) {
         // one grid size for all stages: the smallest co-resident grid among them (set on first use)
-        int g = c->coop_grid((const void *)hbpp_stage_kernel<0>, FR_COMP_BLOCK, smem);
+        int g = c->coop_grid(stage_kernel_ptr<0>(), FR_COMP_BLOCK, smem);
         int t;
-        t = c->coop_grid((const void *)hbpp_stage_kernel<1>, FR_COMP_BLOCK, smem); g = t < g ? t : g;
-        t = c->coop_grid((const void *)hbpp_stage_kernel<2>, FR_COMP_BLOCK, smem); g = t < g ? t : g;
-        t = c->coop_grid((const void *)hbpp_stage_kernel<3>, FR_COMP_BLOCK, smem); g = t < g ? t : g;
-        t = c->coop_grid((const void *)hbpp_stage_kernel<4>, FR_COMP_BLOCK, smem); g = t < g ? t : g;
+        t = c->coop_grid(stage_kernel_ptr<1>(), FR_COMP_BLOCK, smem); g = t < g ? t : g;
+        t = c->coop_grid(stage_kernel_ptr<2>(), FR_COMP_BLOCK, smem); g = t < g ? t : g;
+        t = c->coop_grid(stage_kernel_ptr<3>(), FR_COMP_BLOCK, smem); g = t < g ? t : g;
+        t = c->coop_grid(stage_kernel_ptr<4>(), FR_COMP_BLOCK, smem); g = t < g ? t : g;
         hb->grid = g;
     }
     MolView gm = mol->view;
     void *args[] = {(void *)&gm, (void *)&io, (void *)&bufs, (void *)&n_samp, (void *)&rn};
     static const char *names[] = {"hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4"};
     ProfScope ps(c, names[S]);
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)hbpp_stage_kernel<S>, dim3(hb->grid), dim3(FR_COMP_BLOCK), args,
+    CUDA_TRY(cudaLaunchCooperativeKernel(stage_kernel_ptr<S>(), dim3(hb->grid), dim3(FR_COMP_BLOCK), args,
                                          smem, c->stream));
     c->launch_count++;
     return FRIES_OK;
