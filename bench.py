@@ -329,7 +329,8 @@ def run_ours(args, cfg):
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["workload"], "vec_nonz": cfg["vec_nonz"], "mat_nonz": cfg["mat_nonz"],
-                   "l2": "flushed between iterations (512 MB write)", "stored_dets": int(n_vec)},
+                   "l2": "flushed between iterations (512 MB write)", "stored_dets": int(n_vec),
+                   "stage_ctas_per_sm": 1 if os.environ.get("FRIES_STAGE_CTAS") == "1" else 2},
         "spawned_elements_per_sec": round(spawned / (ms * 1e-3), 1),
         "matrix_samples_per_sec": round(samples / (ms * 1e-3), 1),
         "gpu_launches": int(launches), "clocks": clk,
