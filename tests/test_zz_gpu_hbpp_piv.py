@@ -61,13 +61,19 @@ def run_case(idx):
     ctx.close()
 
 
+_hung = []
+
+
 @pytest.mark.parametrize("idx", range(len(CASES)))
 def test_apply_hbpp_piv(idx):
+    if _hung:  # one hang is enough evidence; do not spend the tier's time on the other cases
+        pytest.fail(f"skipped after case {_hung[0]} did not return")
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), str(idx)], cwd=ROOT, stdout=subprocess.PIPE,
-                           stderr=subprocess.STDOUT, text=True, timeout=150)
+                           stderr=subprocess.STDOUT, text=True, timeout=90)
     except subprocess.TimeoutExpired as e:  # the child is killed by subprocess.run
-        pytest.fail(f"apply_hbpp_piv case {idx}: no result within 150 s (child killed): {str(e.stdout)[-1500:]}")
+        _hung.append(idx)
+        pytest.fail(f"apply_hbpp_piv case {idx}: no result within 90 s (child killed): {str(e.stdout)[-1500:]}")
     assert r.returncode == 0, r.stdout[-3000:]
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     print("apply_hbpp_piv", res)
