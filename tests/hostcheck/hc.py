@@ -69,5 +69,9 @@ def lib():
         L.hc_hbpiv_collapse.argtypes = [C.c_void_p, C.c_int, f64p, u8p]
         L.hc_hbpiv_finalize.restype = C.c_size_t
         L.hc_hbpiv_finalize.argtypes = [C.c_void_p, C.c_double, f64p, u64p, u8p]
+        u16p = np.ctypeslib.ndpointer(np.uint16, flags="C")
+        L.hc_hbsys_rows.restype = C.c_size_t
+        L.hc_hbsys_rows.argtypes = [C.c_void_p, C.c_int, f64p, u32p, f64p, C.c_size_t, u16p]
+        L.hc_hbsys_accept.argtypes = [C.c_void_p, C.c_int, f64p, u64p, C.c_size_t]
         _lib = L
     return _lib

@@ -342,4 +342,56 @@ size_t hc_hbpiv_finalize(void *p, double cutoff, double *out_val, uint64_t *out_
     }
     return k;
 }
+
+// ---- apply_HBPP_sys: the stage providers in the systematic pipeline.  rows: values, n_div, the sub-weight matrix
+// (n_in x cols, the row of a uniform input is unused) and the row lengths, i.e. what the reference hands to comp_sub
+// (heat_bathPP.cpp:713-915); accept: comp_sub's output (value, input, sub index) becomes the next stage's input. ----
+}  // extern "C"
+template <int S>
+static size_t hbsys_rows(HcPiv *h, double *values, uint32_t *ndiv, double *subwts, size_t cols, uint16_t *nsub) {
+    HbProvider<S> prov;
+    prov.m = h->mol->v;
+    prov.io = hbpiv_io(h, S);
+    const size_t n = prov.count();
+    for (size_t i = 0; i < n; i++) {
+        double v, ri, wmax;
+        uint32_t nd, ns;
+        prov.prep(i, v, nd, ns, ri, wmax);
+        values[i] = v;
+        ndiv[i] = nd;
+        nsub[i] = (uint16_t)ns;
+        for (size_t j = 0; j < cols; j++) subwts[i * cols + j] = 0;
+        if (nd == 0) {
+            double mx = 0;
+            prov.visit(i, ri, [&](unsigned j, double w) {
+                if (j < cols) subwts[i * cols + j] = w;
+                if (w > mx) mx = w;
+            });
+            if (mx > wmax * (1 + 1e-12)) return (size_t)-1;  // wmax must bound the row (the engine skips rows by it)
+        }
+    }
+    return n;
+}
+extern "C" {
+size_t hc_hbsys_rows(void *p, int stage, double *values, uint32_t *ndiv, double *subwts, size_t cols, uint16_t *nsub) {
+    HcPiv *h = (HcPiv *)p;
+    switch (stage) {
+        case 0: return hbsys_rows<0>(h, values, ndiv, subwts, cols, nsub);
+        case 1: return hbsys_rows<1>(h, values, ndiv, subwts, cols, nsub);
+        case 2: return hbsys_rows<2>(h, values, ndiv, subwts, cols, nsub);
+        case 3: return hbsys_rows<3>(h, values, ndiv, subwts, cols, nsub);
+        default: return hbsys_rows<4>(h, values, ndiv, subwts, cols, nsub);
+    }
+}
+void hc_hbsys_accept(void *p, int stage, const double *new_vals, const uint64_t *new_idx, size_t n_out) {
+    HcPiv *h = (HcPiv *)p;
+    const int o = stage & 1;
+    if (n_out > h->cap) n_out = h->cap;
+    for (size_t k = 0; k < n_out; k++) {
+        h->oval[o][k] = new_vals[k];
+        h->owidx[o][k] = (uint32_t)new_idx[2 * k];
+        h->osub[o][k] = (uint32_t)new_idx[2 * k + 1];
+    }
+    h->n_in = n_out;
+}
 }
