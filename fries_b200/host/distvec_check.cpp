@@ -178,6 +178,25 @@ int main() {
             CHECK(std::isfinite(mol.diag_matrel(hf)) && mol.diag_matrel(hf) == mol.diag_matrel(key_from_bytes(hf, 3)));
             CHECK(std::isfinite(mol.sing_matr_el_nosgn(&sing[0], hf)) && std::isfinite(mol.doub_matr_el_nosgn(&doub[0])));
             CHECK(mol.calc_unnorm_wt(&doub[0]) > 0 && mol.calc_norm_wt(&doub[0], hf) > 0);
+            // calc_*_probs: normalised rows (sum 1) of the documented lengths, positive totals
+            {
+                uint8_t occ[6] = {0, 1, 2, 10, 11, 12};
+                double row[FRIES_MAX_SUB];
+                auto sums_to_one = [&](unsigned len) {
+                    double t = 0;
+                    for (unsigned j = 0; j < len; j++) t += row[j];
+                    return std::fabs(t - 1) <= 1e-12;
+                };
+                CHECK(mol.calc_o1_probs(row, n_elec, occ, 0) > 0 && sums_to_one(n_elec));
+                CHECK(mol.calc_o1_probs(row, n_elec, occ, 1) > 0 && sums_to_one(n_elec - 1));
+                CHECK(mol.calc_o2_probs(row, n_elec, occ, 4) > 0 && sums_to_one(n_elec) && row[4] == 0);
+                CHECK(mol.calc_o2_probs_half(row, n_elec, occ, 4) > 0 && sums_to_one(4));
+                CHECK(mol.calc_u1_probs(row, 1, occ, (uint8_t)n_elec, 0) > 0 && sums_to_one(n_orb - n_elec / 2));
+                uint16_t len = 0;
+                CHECK(mol.calc_u2_probs(row, 1, 11, 4, &len) > 0 && len > 0 && sums_to_one(len));
+                len = 0;
+                CHECK(mol.calc_u2_probs_half(row, 1, 11, 4, hf, &len) > 0 && len > 0 && sums_to_one(len));
+            }
             // apply_HBPP_sys / apply_HBPP_piv from one determinant (row 1 of all_dets): every sample is an excitation of it
             Matrix<uint8_t> all_dets(2, 3);
             memcpy(all_dets[1], hf, 3);

@@ -511,6 +511,44 @@ struct Molecule {
         return out;
     }
     double diag_matrel(const uint8_t *det) { return diag_matrel(key_from_bytes(det, ceiling(2 * (size_t)n_orb, 8))); }
+    // calc_o1_probs / calc_o2_probs / calc_o2_probs_half / calc_u1_probs / calc_u2_probs / calc_u2_probs_half
+    // (heat_bathPP.cpp:182-412) with the reference's arguments: the normalised row goes to prob_arr, the un-normalised
+    // total is returned (fries_mol_hb_rows; the determinant is rebuilt from the occupied list)
+  private:
+    double hb_row(int which, uint64_t key, int a0, int a1, int a2, double *prob_arr, uint16_t *prob_len) {
+        double rows[FRIES_MAX_SUB], norm;
+        int32_t args[4] = {a0, a1, a2, 0}, len;
+        check(fries_mol_hb_rows(h, which, &key, args, 1, rows, &len, &norm));
+        for (int32_t j = 0; j < len; j++) prob_arr[j] = rows[j];
+        if (prob_len) *prob_len = (uint16_t)len;
+        return norm;
+    }
+    static uint64_t key_of_occ(const uint8_t *occ_orbs, unsigned n) {
+        uint64_t k = 0;
+        for (unsigned i = 0; i < n; i++) k |= 1ull << occ_orbs[i];
+        return k;
+    }
+
+  public:
+    double calc_o1_probs(double *prob_arr, unsigned n_elec, const uint8_t *occ_orbs, int exclude_first) {
+        return hb_row(0, key_of_occ(occ_orbs, n_elec), exclude_first, 0, 0, prob_arr, nullptr);
+    }
+    double calc_o2_probs(double *prob_arr, unsigned n_elec, const uint8_t *occ_orbs, uint8_t o1_idx) {
+        return hb_row(1, key_of_occ(occ_orbs, n_elec), o1_idx, 0, 0, prob_arr, nullptr);
+    }
+    double calc_o2_probs_half(double *prob_arr, unsigned n_elec, const uint8_t *occ_orbs, uint8_t o1_idx) {
+        return hb_row(2, key_of_occ(occ_orbs, n_elec), o1_idx, 0, 0, prob_arr, nullptr);
+    }
+    double calc_u1_probs(double *prob_arr, uint8_t o1_orb, const uint8_t *occ_orbs, uint8_t n_elec, int exclude_first) {
+        return hb_row(3, key_of_occ(occ_orbs, n_elec), o1_orb, exclude_first, 0, prob_arr, nullptr);
+    }
+    double calc_u2_probs(double *prob_arr, uint8_t o1_orb, uint8_t o2_orb, uint8_t u1_orb, uint16_t *prob_len) {
+        return hb_row(4, gen_hf_bitstring(n_orb, n_elec_total - n_frz), o1_orb, o2_orb, u1_orb, prob_arr, prob_len);
+    }
+    double calc_u2_probs_half(double *prob_arr, uint8_t o1_orb, uint8_t o2_orb, uint8_t u1_orb, const uint8_t *det,
+                              uint16_t *prob_len) {
+        return hb_row(5, key_from_bytes(det, ceiling(2 * (size_t)n_orb, 8)), o1_orb, o2_orb, u1_orb, prob_arr, prob_len);
+    }
     // calc_unnorm_wt heat_bathPP.cpp:414-439 / calc_norm_wt :442-598: total HB-PP sampling weight of a double excitation
     double calc_unnorm_wt(const uint8_t *orbs) {
         uint64_t key = gen_hf_bitstring(n_orb, n_elec_total - n_frz);  // not used by the un-normalised weight; must be valid
