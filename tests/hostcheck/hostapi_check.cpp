@@ -46,8 +46,35 @@ static int bits_mode() {
     return 0;
 }
 
+// mode "parse": argv = parse fcidump <path> <point group> | parse hf <dir>; prints the MolInput: one header line
+// "n_orb n_elec n_frz eps hf_en", the irreps, then hcore and the packed integrals as hexadecimal floats
+static int parse_mode(int argc, char **argv) {
+    if (argc < 4) return 20;
+    fries::MolInput m;
+    try {
+        if (std::string(argv[2]) == "fcidump") {
+            if (argc < 5) return 20;
+            m = fries::parse_fcidump(argv[3], argv[4]);
+        } else {
+            m = fries::parse_hf_input(argv[3]);
+        }
+    } catch (std::exception &e) {
+        std::cout << "Exception : " << e.what() << std::endl;
+        return 21;
+    }
+    printf("%u %u %u %a %a\n", m.n_orb, m.n_elec, m.n_frz, m.eps, m.hf_en);
+    for (uint8_t x : m.symm) printf("%u ", (unsigned)x);
+    printf("\n");
+    for (double x : m.hcore) printf("%a ", x);
+    printf("\n");
+    for (double x : m.eris_packed) printf("%a ", x);
+    printf("\n");
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && std::string(argv[1]) == "bits") return bits_mode();
+    if (argc > 1 && std::string(argv[1]) == "parse") return parse_mode(argc, argv);
     unsigned n_bits, n_elec, n_scr;
     size_t n_keys;
     std::cin >> n_bits >> n_elec >> n_scr;

@@ -87,3 +87,35 @@ def test_host_bit_string_functions(tmp_path):
                 kz = k & ~((1 << o0) | (1 << o1))
                 s2 = p2 = (-1 if inner(kz, v2, o0) & 1 else 1) * (-1 if inner(kz, v3, o1) & 1 else 1)
             assert got == [nb, s1, k_s, s2, k_d, p1, p2, flipped, -1 if nb & 1 else 1], (k, o0, o1, v2, v3, a, b, got)
+
+
+def test_host_input_parsers(tmp_path):
+    """parse_fcidump (io_utils.cpp:17-96 + convert_symm :189-239) and parse_hf_input (:98-187, legacy directory with frozen
+    core) of the C++ mirror: the files the drivers read, written from a synthetic molecule, come back as the arrays the
+    library is created from (hcore, SymmERIs-packed integrals, irreps) -- bit for bit"""
+    from driver_utils import write_fcidump, write_hf_dir
+    from fries_b200.synth import SynthMol
+    exe = build(tmp_path)
+
+    def parse(args):
+        r = subprocess.run([exe, "parse"] + args, stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stdout[-300:]
+        head, symm, hcore, eris = r.stdout.splitlines()[:4]
+        h = head.split()
+        return ([int(x) for x in h[:3]], float.fromhex(h[3]), float.fromhex(h[4]), np.array([int(x) for x in symm.split()], np.uint8),
+                np.array([float.fromhex(x) for x in hcore.split()]), np.array([float.fromhex(x) for x in eris.split()]))
+
+    sm = SynthMol((8, 6, 0, [0, 0, 1, 2, 3, 0, 1, 2]), 4)
+    fd = str(tmp_path / "FCIDUMP")
+    write_fcidump(fd, sm, "D2")
+    dims, _, _, symm, hcore, eris = parse(["fcidump", fd, "D2"])
+    assert dims == [sm.n_orb, sm.n_elec_total, 0]
+    assert np.array_equal(symm, sm.symm) and np.array_equal(hcore, sm.hcore.reshape(-1)) and np.array_equal(eris, sm.eris_packed)
+
+    smf = SynthMol("ne", 2, True)  # two frozen electrons
+    assert smf.n_frz == 2
+    d = str(tmp_path / "hf") + "/"
+    write_hf_dir(d, smf, 0.001, -128.5)
+    dims, eps, hf_en, symm, hcore, eris = parse(["hf", d])
+    assert dims == [smf.n_orb, smf.n_elec_total, smf.n_frz] and eps == 0.001 and hf_en == -128.5
+    assert np.array_equal(symm, smf.symm) and np.array_equal(hcore, smf.hcore.reshape(-1)) and np.array_equal(eris, smf.eris_packed)
