@@ -50,6 +50,17 @@ static int bits_mode() {
 // "n_orb n_elec n_frz eps hf_en", the irreps, then hcore and the packed integrals as hexadecimal floats
 static int parse_mode(int argc, char **argv) {
     if (argc < 4) return 20;
+    if (std::string(argv[2]) == "hh") {  // Hubbard-Holstein parameter file + the Neel determinant of its lattice
+        try {
+            fries::HhInput h = fries::parse_hh_input(argv[3]);
+            printf("%u %u %u %a %a %a %a %a %llu\n", h.n_elec, h.lat_len, h.n_dim, h.eps, h.elec_int, h.ph_freq, h.elec_ph, h.hf_en,
+                   (unsigned long long)fries::gen_neel_det_1D(h.lat_len, h.n_elec));
+        } catch (std::exception &e) {
+            std::cout << "Exception : " << e.what() << std::endl;
+            return 21;
+        }
+        return 0;
+    }
     fries::MolInput m;
     try {
         if (std::string(argv[2]) == "fcidump") {

@@ -119,3 +119,24 @@ def test_host_input_parsers(tmp_path):
     dims, eps, hf_en, symm, hcore, eris = parse(["hf", d])
     assert dims == [smf.n_orb, smf.n_elec_total, smf.n_frz] and eps == 0.001 and hf_en == -128.5
     assert np.array_equal(symm, smf.symm) and np.array_equal(hcore, smf.hcore.reshape(-1)) and np.array_equal(eris, smf.eris_packed)
+
+
+def test_host_hubbard_input(tmp_path):
+    """parse_hh_input (io_utils.cpp:320-408; the key order of examples/hubbard_params.txt) and gen_neel_det_1D
+    (hub_holstein.cpp:139-171) against the oracle; a file with a missing key is refused with the reference's message"""
+    import ctypes
+    exe = build(tmp_path)
+    neel = oraclelib.lib().fo_gen_neel_det_1D
+    neel.restype, neel.argtypes = ctypes.c_uint64, [ctypes.c_uint, ctypes.c_uint]
+    f = str(tmp_path / "hubbard_params.txt")
+    for n_elec, lat_len in ((6, 6), (4, 10), (10, 10), (2, 4)):
+        open(f, "w").write(f"n_elec\n{n_elec}\nlat_len\n{lat_len}\nn_dim\n1\neps\n0.001\nU\n2\nomega\n0.5\ng\n0.25\ngs_energy\n-3.98791841486987\n")
+        r = subprocess.run([exe, "parse", "hh", f], stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stdout
+        t = r.stdout.split()
+        assert [int(x) for x in t[:3]] == [n_elec, lat_len, 1]
+        assert [float.fromhex(x) for x in t[3:8]] == [0.001, 2.0, 0.5, 0.25, -3.98791841486987]
+        assert int(t[8]) == neel(lat_len, n_elec)
+    open(f, "w").write("n_elec\n6\nlat_len\n6\nn_dim\n1\neps\n0.001\nomega\n0\n")
+    r = subprocess.run([exe, "parse", "hh", f], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 21 and "electron interaction parameter (U)" in r.stdout
