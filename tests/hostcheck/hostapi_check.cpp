@@ -83,7 +83,42 @@ static int parse_mode(int argc, char **argv) {
     return 0;
 }
 
+// mode "files <dir>": load_vec_txt of <dir>ini_ (dets / vals text files), hash.dat round trip, load_last_line of <dir>S.txt
+static int files_mode(int argc, char **argv) {
+    if (argc < 3) return 30;
+    const std::string dir = argv[2];
+    std::vector<uint64_t> dets;
+    std::vector<double> vals;
+    size_t n = fries::load_vec_txt(dir + "ini_", dets, vals);
+    printf("%zu\n", n);
+    for (size_t i = 0; i < n; i++) printf("%llu %a\n", (unsigned long long)dets[i], vals[i]);
+    std::vector<uint32_t> scr(44), back(44);
+    fries::load_proc_hash(dir, scr);           // written by the test
+    fries::save_proc_hash(dir + "copy_", scr);  // read back by the test
+    for (uint32_t x : scr) printf("%u ", x);
+    printf("\n");
+    double last = 0;
+    bool ok = fries::load_last_line(dir + "S.txt", &last);
+    printf("%d %a\n", (int)ok, last);
+    ok = fries::load_last_line(dir + "missing.txt", &last);
+    printf("%d\n", (int)ok);
+    return 0;
+}
+// mode "args ...": the drivers' command-line handling (argparse.hpp semantics)
+static int args_mode(int argc, char **argv) {
+    fries::Args a(argc - 1, argv + 1);
+    std::string path = a.str("fcidump_path");
+    double vec_nonz = a.num("vec_nonz");
+    double target = a.num("target", 0);
+    std::string rd = a.str("result_dir", "./");
+    a.validate();
+    printf("%s %g %g %s\n", path.c_str(), vec_nonz, target, rd.c_str());
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "files") return files_mode(argc, argv);
+    if (argc > 1 && std::string(argv[1]) == "args") return args_mode(argc, argv);
     if (argc > 1 && std::string(argv[1]) == "bits") return bits_mode();
     if (argc > 1 && std::string(argv[1]) == "parse") return parse_mode(argc, argv);
     unsigned n_bits, n_elec, n_scr;

@@ -140,3 +140,35 @@ def test_host_hubbard_input(tmp_path):
     open(f, "w").write("n_elec\n6\nlat_len\n6\nn_dim\n1\neps\n0.001\nomega\n0\n")
     r = subprocess.run([exe, "parse", "hh", f], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 21 and "electron interaction parameter (U)" in r.stdout
+
+
+def test_host_files_and_command_line(tmp_path):
+    """load_vec_txt (io_utils.cpp:410-482), hash.dat (:589-619), load_last_line (:636-663) and the argparse semantics of the
+    drivers (Ext_Libs/argparse.hpp:347-393: --key value, unknown flag = warning, missing required flag = exit(-1))"""
+    exe = build(tmp_path)
+    d = str(tmp_path) + "/"
+    rng = np.random.default_rng(3)
+    dets = rng.integers(1, 2**44, 50, dtype=np.uint64)
+    vals = rng.normal(size=52)  # two values too many: truncated to the determinants, with a warning
+    open(d + "ini_dets", "w").write("\n".join(str(int(x)) for x in dets) + "\n")
+    open(d + "ini_vals", "w").write("\n".join(repr(float(x)) for x in vals) + "\n")
+    scr = rng.integers(0, 2**32, 44, dtype=np.uint64).astype(np.uint32)
+    scr.tofile(d + "hash.dat")
+    open(d + "S.txt", "w").write("0.0\n-0.25\n-0.3125\n\n")
+    r = subprocess.run([exe, "files", d], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert int(lines[0]) == 50 and "fewer determinants" in r.stderr
+    got = [ln.split() for ln in lines[1:51]]
+    assert [int(g[0]) for g in got] == [int(x) for x in dets]
+    assert [float.fromhex(g[1]) for g in got] == [float(x) for x in vals[:50]]
+    assert [int(x) for x in lines[51].split()] == [int(x) for x in scr]
+    assert np.array_equal(np.fromfile(d + "copy_hash.dat", np.uint32), scr)
+    assert lines[52].split()[0] == "1" and float.fromhex(lines[52].split()[1]) == -0.3125 and lines[53] == "0"
+    # command line
+    r = subprocess.run([exe, "args", "--fcidump_path", "x/FCIDUMP", "--vec_nonz", "1000", "--target=-5", "--bogus", "1"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.split() == ["x/FCIDUMP", "1000", "-5", "./"]
+    assert "unrecognised commandline argument: bogus" in r.stderr
+    r = subprocess.run([exe, "args", "--vec_nonz", "1000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 255 and "Argument missing: --fcidump_path" in r.stderr
