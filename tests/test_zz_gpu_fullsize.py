@@ -1,0 +1,168 @@
+"""GPU tier, after the verified files: the hot path at BASELINE.json's FULL sizes, checked through size-independent properties
+(the oracle comparisons of tests/test_gpu_parity.py stop at sizes the CPU finishes in seconds).
+
+  * vector compression (find_preserve + sys_comp, compress_utils.cpp:29-127,278-327) on 2e6 elements (H2O configuration,
+    budget 1e6) and on 1.25e7 elements (synthetic configuration, SURVEY 8d C5 values sign x 10^(-4u)): the preserved set
+    is an upper set (sortedness), satisfies the fixed-point rule |x| >= residual / budget_left, exactly `budget` elements
+    survive, every resampled one has magnitude residual / budget_left and its old sign, the one-norm is conserved, and
+    a second compression to the same size keeps the large elements, the count and the norm;
+  * apply_HBPP_sys (heat_bathPP.cpp:686-992) with 1e6 samples on the H2O-sized molecule: at most n_samp samples, each one a
+    symmetry- and spin-allowed excitation of its parent with a value above the 1e-9 cutoff; the samples of the oracle
+    (which manages this size in seconds); the call is deterministic;
+  * the determinant store (vec_utils.hpp:418-476,606-641) with 1e6 determinants: merge of duplicates = numpy's multiset
+    sum, a second non-initiator add of the same elements doubles every value and creates nothing, a determinant that is not
+    stored is refused without the initiator flag, only elements that are zero in every row can be deleted.
+
+All of it goes through calls the verified tier covers at small sizes; the file was written after this round's GPU minutes
+were spent, so the cases are non-strict xfail until a green run is on record."""
+import numpy as np
+import pytest
+
+import oraclelib
+from fries_b200.synth import SynthMol
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
+              pytest.mark.xfail(strict=False, reason="first GPU run of the full-size property tests is pending")]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import fries_b200
+    c = fries_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n,budget,kind", [(2_000_000, 1_000_000, "lognormal"), (12_500_000, 5_000_000, "c5")])
+def test_vector_compression_properties(ctx, n, budget, kind):
+    import fries_b200
+    rng = np.random.default_rng(n)
+    if kind == "c5":
+        v = rng.choice([-1.0, 1.0], n) * 10.0 ** (-4 * rng.random(n))
+        v *= 1e8 / np.abs(v).sum()
+    else:
+        v = rng.lognormal(0, 2, n) * rng.choice([-1.0, 1.0], n)
+    loc, glob, left, keep = fries_b200.find_preserve(ctx, v, budget)
+    o_loc, o_glob, o_left, o_keep = oraclelib.find_preserve(v, budget)  # the checker manages the full size in seconds
+    assert np.array_equal(keep, o_keep) and left == o_left and loc == pytest.approx(o_loc, rel=1e-12)
+    kept = keep.astype(bool)
+    a = np.abs(v)
+    n_kept = int(kept.sum())
+    assert n_kept + left == budget and 0 < left < budget
+    assert glob == pytest.approx(a.sum(), rel=1e-10)
+    assert loc == pytest.approx(a[~kept].sum(), rel=1e-10)
+    # sortedness: the preserved set is an upper set; fixed point: kept >= t > not kept, t = residual / budget left
+    t = loc / left
+    assert a[kept].min() >= a[~kept].max()
+    assert a[kept].min() >= t * (1 - 1e-9) and a[~kept].max() < t * (1 + 1e-9)
+    out, dele, norms = fries_b200.sys_comp(ctx, v, [loc], left, keep, 0.37)
+    nz = out != 0
+    assert abs(int(nz.sum()) - budget) <= 2  # a grid point within an ulp of an interval boundary may move
+    assert np.array_equal(out[kept], v[kept])
+    res = nz & ~kept
+    assert np.allclose(np.abs(out[res]), t, rtol=1e-12, atol=0) and np.array_equal(np.sign(out[res]), np.sign(v[res]))
+    assert np.array_equal(dele.astype(bool), ~nz)
+    assert np.abs(out).sum() == pytest.approx(a.sum(), rel=1e-9)
+    # a second compression to the same size: the elements above the resampling unit are preserved again, exactly; the
+    # one-norm and the element count are conserved.  (Exact idempotence is not a property of the scheme in floating point:
+    # the sum of k copies of the unit divided by k may exceed the unit by an ulp, and those copies are then resampled.)
+    loc2, glob2, left2, keep2 = fries_b200.find_preserve(ctx, out, int(nz.sum()))
+    big = np.abs(out) > t * (1 + 1e-9)
+    assert np.all(keep2.astype(bool)[big]) and not np.any(keep2.astype(bool)[~nz])
+    out2, dele2, _ = fries_b200.sys_comp(ctx, out, [loc2], left2, keep2, 0.81)
+    assert np.array_equal(out2[big], out[big])
+    assert abs(int((out2 != 0).sum()) - int(nz.sum())) <= 2
+    assert np.abs(out2).sum() == pytest.approx(a.sum(), rel=1e-9)
+
+
+def test_apply_hbpp_sys_properties_h2o_1e6(ctx):
+    import fries_b200
+    sm = SynthMol("h2o", 3, True)
+    mol = fries_b200.Mol.from_synth(ctx, sm)
+    rng = np.random.default_rng(5)
+    n_det, n_samp = 50_000, 1_000_000
+    keys = np.concatenate([[sm.hf], sm.random_dets(n_det - 1, rng, 0)]).astype(np.uint64)
+    vals = rng.lognormal(0, 2, n_det) * rng.choice([-1.0, 1.0], n_det)
+    vals[0] = 50 * np.abs(vals).max()
+    u5 = rng.random(5)
+    cap = 2 * n_samp + n_det
+    gv, gd, go = mol.apply_hbpp_sys(keys, vals, 0.98, 1, u5, n_samp, cap)
+    n = len(gv)
+    assert 0.5 * n_samp < n <= n_samp
+    assert np.all(np.abs(gv) > 1e-9) and np.all(np.isfinite(gv)) and gd.max() < n_det
+    M = sm.n_orb
+    parent = keys[gd.astype(np.int64)]
+    o = go.astype(np.uint64)
+    bit = lambda col: (parent >> o[:, col]) & np.uint64(1)
+    single = (o[:, 2] == 0) & (o[:, 3] == 0)  # frisys_mol.cpp:451
+    symm = sm.symm.astype(np.int64)
+    irr = lambda col: symm[(o[:, col] % np.uint64(M)).astype(np.int64)]
+    spin = lambda col: (o[:, col] // np.uint64(M)).astype(np.int64)
+    s, d = single, ~single
+    assert s.any() and d.any()
+    assert np.all(bit(0)[s] == 1) and np.all(bit(1)[s] == 0)
+    assert np.all(spin(0)[s] == spin(1)[s]) and np.all(irr(0)[s] == irr(1)[s])
+    assert np.all(bit(0)[d] == 1) and np.all(bit(1)[d] == 1) and np.all(bit(2)[d] == 0) and np.all(bit(3)[d] == 0)
+    assert np.all(o[d, 0] < o[d, 1]) and np.all(o[d, 2] < o[d, 3])
+    assert np.all((irr(0) ^ irr(1) ^ irr(2) ^ irr(3))[d] == 0)
+    assert np.all((spin(0) + spin(1))[d] == (spin(2) + spin(3))[d])
+    # the oracle manages this size in seconds: the same samples (chunk size 1 as in tests/test_gpu_parity.py; five chained
+    # resampling stages, so one boundary tie early on moves a handful of downstream samples)
+    om = oraclelib.OracleMol(sm)
+    with oraclelib.keep_chunk(1):
+        ov, od, oo = om.apply_hbpp_sys(keys, vals, 0.98, 1, u5, n_samp, cap)
+    code = lambda dd, orbs: (dd.astype(np.uint64) << np.uint64(32)) | (orbs.astype(np.uint64) * (np.uint64(1) << (np.uint64(8) * np.arange(4, dtype=np.uint64)))).sum(axis=1)
+    gc, oc = code(gd, go), code(od, oo)
+    n_diff = len(np.setxor1d(gc, oc))
+    print(f"apply_hbpp_sys at 1e6 samples: {n} samples, {n_diff} differ from the oracle")
+    assert n_diff <= max(6, len(oc) // 5000)
+    if n_diff == 0:
+        assert np.array_equal(gd, od) and np.array_equal(go, oo) and np.allclose(gv, ov, rtol=1e-9, atol=0)
+    # deterministic: the same call returns the same samples, bit for bit
+    gv2, gd2, go2 = mol.apply_hbpp_sys(keys, vals, 0.98, 1, u5, n_samp, cap)
+    assert np.array_equal(gv, gv2) and np.array_equal(gd, gd2) and np.array_equal(go, go2)
+    mol.close()
+
+
+def test_store_merge_properties_1e6(ctx):
+    import fries_b200
+    n_orb, n_elec, n = 24, 10, 1_000_000
+    rng = np.random.default_rng(8)
+    a = np.argsort(rng.random((n, n_orb)), axis=1)[:, :n_elec // 2].astype(np.uint64)
+    b = np.argsort(rng.random((n, n_orb)), axis=1)[:, :n_elec // 2].astype(np.uint64)
+    keys = (np.uint64(1) << a).sum(axis=1) | ((np.uint64(1) << b).sum(axis=1) << np.uint64(n_orb))
+    keys = keys.astype(np.uint64)
+    vals = np.round(rng.normal(size=n) * 1024) / 1024  # dyadic: sums of duplicates are exact in any order
+    vals[vals == 0] = 1.0
+    scr = rng.integers(0, 2**32, 2 * n_orb, dtype=np.uint64).astype(np.uint32)
+    # two rows: row 1 holds a one for every stored determinant, so that the non-initiator adds below (origin = 1) are accepted
+    # whatever the order in which duplicates arrive (tests/test_gpu_parity.py::test_vec_add_merge_delete on origin == dest)
+    vec = fries_b200.Vec(ctx, 1 << 21, 2 * n_orb, n_elec, 2, scr, scr)
+    vec.add(keys, vals, np.ones(n, np.uint8), 0, 0)
+    uniq, inv = np.unique(keys, return_inverse=True)
+    want = np.bincount(inv, weights=vals, minlength=uniq.size)
+    vec.add(uniq, np.ones(uniq.size), np.ones(uniq.size, np.uint8), 0, 1)
+    gk, gv = vec.download()
+    assert vec.curr_size() == uniq.size
+    order = np.argsort(gk)
+    assert np.array_equal(gk[order], uniq) and np.array_equal(gv[0][order], want) and np.all(gv[1] == 1)
+    # the same elements once more, as non-initiators: every value of row 0 doubles, nothing new appears, order unchanged
+    vec.add(keys, vals, np.zeros(n, np.uint8), 1, 0)
+    gk2, gv2 = vec.download()
+    assert vec.curr_size() == uniq.size and np.array_equal(gk2, gk) and np.array_equal(gv2[0], 2 * gv[0])
+    # a determinant that is not stored is refused without the initiator flag
+    hf = np.array([(1 << (n_elec // 2)) - 1 | (((1 << (n_elec // 2)) - 1) << n_orb)], np.uint64)
+    if not np.any(uniq == hf[0]):
+        vec.add(hf, np.array([3.0]), np.zeros(1, np.uint8), 1, 0)
+        assert vec.curr_size() == uniq.size
+    # subtract twice: row 0 cancels exactly; nothing can be deleted while row 1 is nonzero
+    vec.add(keys, -2 * vals, np.zeros(n, np.uint8), 1, 0)
+    gk3, gv3 = vec.download()
+    assert not gv3[0].any() and np.all(gv3[1] == 1)
+    vec.delete(np.ones(vec.curr_size(), np.uint8))
+    assert vec.curr_size() == uniq.size
+    # clear row 1 (every determinant once: no order dependence), delete: the store is empty
+    vec.add(uniq, -np.ones(uniq.size), np.zeros(uniq.size, np.uint8), 1, 1)
+    vec.delete(np.ones(vec.curr_size(), np.uint8))
+    assert vec.curr_size() == 0
+    vec.close()
