@@ -15,7 +15,7 @@ _lib = None
 
 def build():
     src = os.path.join(HERE, "hostcheck.cu")
-    deps = [src] + [os.path.join(HERE, "..", "..", "fries_b200", "csrc", f) for f in ("mol.cuh", "common.cuh", "piv.cuh", "hbpp_prov.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "..", "fries_b200", "csrc", f) for f in ("mol.cuh", "common.cuh", "piv.cuh", "hbpp_prov.cuh", "hh_prov.cuh")]
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(SO), exist_ok=True)
@@ -73,5 +73,12 @@ def lib():
         L.hc_hbsys_rows.restype = C.c_size_t
         L.hc_hbsys_rows.argtypes = [C.c_void_p, C.c_int, f64p, u32p, f64p, C.c_size_t, u16p]
         L.hc_hbsys_accept.argtypes = [C.c_void_p, C.c_int, f64p, u64p, C.c_size_t]
+        L.hc_hh_hub_diag.restype = C.c_uint
+        L.hc_hh_hub_diag.argtypes = [C.c_uint64, C.c_uint]
+        L.hc_hh_neighbors.argtypes = [C.c_uint64, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.hc_hh_ref_ovlp.restype = C.c_double
+        L.hc_hh_ref_ovlp.argtypes = [u64p, f64p, C.c_size_t, C.c_uint64, C.c_uint, C.c_uint, C.c_uint, C.c_double]
+        L.hc_hh_total_ph.restype = C.c_uint
+        L.hc_hh_total_ph.argtypes = [C.c_uint64, C.c_uint, C.c_uint, C.c_uint]
         _lib = L
     return _lib

@@ -7,6 +7,7 @@
 #include "../../fries_b200/csrc/mol.cuh"
 #include "../../fries_b200/csrc/piv.cuh"
 #include "../../fries_b200/csrc/hbpp_prov.cuh"
+#include "../../fries_b200/csrc/hh_prov.cuh"
 #include <vector>
 
 struct HcMol {
@@ -393,5 +394,20 @@ void hc_hbsys_accept(void *p, int stage, const double *new_vals, const uint64_t 
         h->osub[o][k] = (uint32_t)new_idx[2 * k + 1];
     }
     h->n_in = n_out;
+}
+
+// ---- a19: Hubbard-Holstein arithmetic (hh_prov.cuh) ----
+unsigned hc_hh_hub_diag(uint64_t key, unsigned n_sites) { return hh_hub_diag(key, n_sites); }
+void hc_hh_neighbors(uint64_t key, unsigned n_sites, uint64_t *plus, uint64_t *minus) { hh_neighbors(key, n_sites, *plus, *minus); }
+double hc_hh_ref_ovlp(const uint64_t *keys, const double *vals, size_t n, uint64_t ref, unsigned n_elec, unsigned n_sites,
+                      unsigned ph_bits, double g_over_t) {
+    HhDims d{n_sites, n_elec, ph_bits};
+    double s = 0;
+    for (size_t i = 0; i < n; i++) s += hh_ref_ovlp_term(keys[i], vals[i], ref, d, g_over_t);
+    return s;
+}
+unsigned hc_hh_total_ph(uint64_t key, unsigned n_sites, unsigned n_elec, unsigned ph_bits) {
+    HhDims d{n_sites, n_elec, ph_bits};
+    return hh_total_ph(key, d);
 }
 }
