@@ -1069,6 +1069,12 @@ inline void apply_HBPP_piv(Molecule &mol, Matrix<uint8_t> &all_dets, HBCompressP
     detail::hb_store(cs, val, det, orbs, n_out);
 }
 
+// sum_mpi compress_utils.hpp:179-232: sum of one number per rank.  The host layer drives one GPU from one process (the
+// multi-GPU exchange lives inside the library, csrc/comm.cuh), so the sum over ranks is the local value.
+inline double sum_mpi(double local, int, int) { return local; }
+inline int sum_mpi(int local, int, int) { return local; }
+inline uint64_t sum_mpi(uint64_t local, int, int) { return local; }
+
 // adjust_shift compress_utils.cpp:684-693 (scalar control logic of the drivers)
 inline void adjust_shift(double *shift, double one_norm, double *last_norm, double target_norm, double damp_factor) {
     if (*last_norm) {
