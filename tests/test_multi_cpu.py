@@ -52,6 +52,28 @@ def _worker(rank, world, port, q):
         t = torch.tensor([total, vals.sum()], dtype=torch.float64)
         dist.all_reduce(t)
         assert abs(t[0] - t[1]) < 1e-9
+        # (c) the budget step of the distributed pivotal compression (multi.piv_comp_parallel): the residual norms are
+        # all-gathered, every rank evaluates rank 0's arithmetic (compress_utils.cpp:560-608) on the SAME shared draws
+        # with the library's host function, and all ranks must arrive at the same budgets and the same draw count
+        import fries_b200
+        shared = oraclelib.mt19937(77, 2 * world + 8)
+        for n_left, my_norm in ((1000, 3.0 + 2.5 * rank), (7, 0.125 * (rank + 1)), (5, 0.0)):
+            g = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(g, torch.tensor([my_norm], dtype=torch.float64))
+            norms = np.array([float(x.item()) for x in g])
+            budgets, used = fries_b200.piv_budget(norms, n_left, shared)
+            ob, oused = oraclelib.piv_budget(norms, n_left, shared)
+            assert used == oused and np.abs(budgets.astype(int) - ob.astype(int)).sum() <= 2
+            if norms.sum() > 0:
+                assert int(budgets.sum()) == n_left
+                assert np.all(np.abs(budgets - norms / norms.sum() * n_left) < 1 + 1e-9)
+            else:
+                assert not budgets.any() and used == 2 * min(world, n_left)
+            t = torch.tensor(np.concatenate([budgets.astype(np.float64), [float(used)]]))
+            lo, hi = t.clone(), t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert torch.equal(lo, hi)  # identical on every rank
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, repr(e)))
