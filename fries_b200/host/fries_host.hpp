@@ -1069,6 +1069,19 @@ inline void apply_HBPP_piv(Molecule &mol, Matrix<uint8_t> &all_dets, HBCompressP
     detail::hb_store(cs, val, det, orbs, n_out);
 }
 
+// seed_sys compress_utils.cpp:107-127: position of the first systematic-sampling grid point of rank my_rank, whose lower
+// ranks hold the one-norms norms[0 .. my_rank); returns that lower bound (scalar control logic, as adjust_shift)
+inline double seed_sys(const double *norms, double *rn, unsigned int n_samp, int n_procs = 1, int my_rank = 0) {
+    double lbound = 0;
+    for (int p = 0; p < my_rank; p++) lbound += norms[p];
+    double global_norm = lbound;
+    for (int p = my_rank; p < n_procs; p++) global_norm += norms[p];
+    const double unit = global_norm / n_samp;
+    *rn *= unit;
+    *rn += unit * (int)(lbound * n_samp / global_norm);
+    if (*rn < lbound) *rn += unit;
+    return lbound;
+}
 // sum_mpi compress_utils.hpp:179-232: sum of one number per rank.  The host layer drives one GPU from one process (the
 // multi-GPU exchange lives inside the library, csrc/comm.cuh), so the sum over ranks is the local value.
 inline double sum_mpi(double local, int, int) { return local; }

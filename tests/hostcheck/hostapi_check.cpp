@@ -116,7 +116,22 @@ static int args_mode(int argc, char **argv) {
     return 0;
 }
 
+// mode "seed": stdin records "n_procs rank n_samp rn norms..."; stdout "lbound rn" as hexadecimal floats
+static int seed_mode() {
+    int n_procs, rank;
+    unsigned n_samp;
+    double rn;
+    while (std::cin >> n_procs >> rank >> n_samp >> rn) {
+        std::vector<double> norms(n_procs);
+        for (double &x : norms) std::cin >> x;
+        double lb = fries::seed_sys(norms.data(), &rn, n_samp, n_procs, rank);
+        printf("%a %a\n", lb, rn);
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "seed") return seed_mode();
     if (argc > 1 && std::string(argv[1]) == "files") return files_mode(argc, argv);
     if (argc > 1 && std::string(argv[1]) == "args") return args_mode(argc, argv);
     if (argc > 1 && std::string(argv[1]) == "bits") return bits_mode();

@@ -172,3 +172,27 @@ def test_host_files_and_command_line(tmp_path):
     assert "unrecognised commandline argument: bogus" in r.stderr
     r = subprocess.run([exe, "args", "--vec_nonz", "1000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 255 and "Argument missing: --fcidump_path" in r.stderr
+
+
+def test_host_seed_sys(tmp_path):
+    """seed_sys (compress_utils.cpp:107-127) of the C++ mirror against the oracle for every rank of 1, 3 and 8"""
+    import ctypes
+    exe = build(tmp_path)
+    f = oraclelib.lib().fo_seed_sys
+    f.restype = ctypes.c_double
+    f.argtypes = [oraclelib.f64p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_uint]
+    rng = np.random.default_rng(2)
+    recs, want = [], []
+    for n_procs in (1, 3, 8):
+        for _ in range(20):
+            norms = rng.lognormal(0, 2, n_procs)
+            n_samp, u = int(rng.integers(1, 5000)), float(rng.random())
+            for rank in range(n_procs):
+                recs.append(f"{n_procs} {rank} {n_samp} {u!r} " + " ".join(repr(float(x)) for x in norms))
+                rn = ctypes.c_double(u)
+                lb = f(np.ascontiguousarray(norms), n_procs, rank, ctypes.byref(rn), n_samp)
+                want.append((lb, rn.value))
+    r = subprocess.run([exe, "seed"], input="\n".join(recs) + "\n", stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0
+    got = [tuple(float.fromhex(x) for x in ln.split()) for ln in r.stdout.splitlines()]
+    assert got == want
