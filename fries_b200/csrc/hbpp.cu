@@ -69,17 +69,7 @@ hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsign
         if (el != 0) ok++;
         if (sp.out_keys || sp.n_ranks > 1) {
             // spawn loop body frisys_mol.cpp:436-461
-            if (el != 0) {
-                double cv = sp.v0[d];
-                add = -sp.eps * el;
-                if (cv < 0) add *= -1;
-                nk = key;
-                if (is_doub)
-                    nk = (nk & ~((1ull << orbs[0]) | (1ull << orbs[1]))) | (1ull << orbs[2]) | (1ull << orbs[3]);
-                else
-                    nk = (nk & ~(1ull << orbs[0])) | (1ull << orbs[1]);
-                if (fabs(cv) >= sp.init_thresh) nk |= FRIES_INI_FLAG;
-            }
+            if (el != 0) nk = hbpp_spawn_element(key, orbs, is_doub, el, sp.v0[d], sp.eps, sp.init_thresh, add);
             if (sp.n_ranks <= 1) {
                 sp.out_keys[i] = nk;
                 sp.out_vals[i] = add;

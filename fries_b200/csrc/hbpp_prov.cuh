@@ -317,6 +317,21 @@ __host__ __device__ __forceinline__ double hbpp_finalize_sample(const MolView &m
     return el;
 }
 
+// spawn loop body frisys_mol.cpp:436-461 for one successful sample: the new determinant (with the initiator flag of its
+// parent in bit 63: |parent value| >= init_thresh) and the element -eps x value x sign(parent value) to add to it
+__host__ __device__ __forceinline__ uint64_t hbpp_spawn_element(uint64_t key, const uint8_t (&orbs)[4], bool is_doub, double el,
+                                                               double parent_val, double eps, double init_thresh, double &add) {
+    add = -eps * el;
+    if (parent_val < 0) add *= -1;
+    uint64_t nk = key;
+    if (is_doub)
+        nk = (nk & ~((1ull << orbs[0]) | (1ull << orbs[1]))) | (1ull << orbs[2]) | (1ull << orbs[3]);
+    else
+        nk = (nk & ~(1ull << orbs[0])) | (1ull << orbs[1]);
+    if (fabs(parent_val) >= init_thresh) nk |= FRIES_INI_FLAG;
+    return nk;
+}
+
 // ---- apply_HBPP_piv (heat_bathPP.cpp:1014-1419): one group of the "long" vector per input ----
 // set-up of input i: effective value, row shape and normalisation; returns the group's length (a uniform row of n_div
 // equal pieces, or the explicit row of n_sub weights; an input without continuation is one entry of value 0, which

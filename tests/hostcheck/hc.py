@@ -80,5 +80,8 @@ def lib():
         L.hc_hh_ref_ovlp.argtypes = [u64p, f64p, C.c_size_t, C.c_uint64, C.c_uint, C.c_uint, C.c_uint, C.c_double]
         L.hc_hh_total_ph.restype = C.c_uint
         L.hc_hh_total_ph.argtypes = [C.c_uint64, C.c_uint, C.c_uint, C.c_uint]
+        L.hc_spawn_element.restype = C.c_uint64
+        L.hc_spawn_element.argtypes = [C.c_uint64, u8p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                       C.POINTER(C.c_double)]
         _lib = L
     return _lib

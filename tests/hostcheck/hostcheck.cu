@@ -410,4 +410,11 @@ unsigned hc_hh_total_ph(uint64_t key, unsigned n_sites, unsigned n_elec, unsigne
     HhDims d{n_sites, n_elec, ph_bits};
     return hh_total_ph(key, d);
 }
+
+// ---- a17: the spawn loop body of one sample (hbpp_prov.cuh) ----
+uint64_t hc_spawn_element(uint64_t key, const uint8_t *orbs4, int is_doub, double el, double parent_val, double eps,
+                          double init_thresh, double *add) {
+    uint8_t o[4] = {orbs4[0], orbs4[1], orbs4[2], orbs4[3]};
+    return hbpp_spawn_element(key, o, is_doub != 0, el, parent_val, eps, init_thresh, *add);
+}
 }
