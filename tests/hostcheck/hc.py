@@ -15,7 +15,7 @@ _lib = None
 
 def build():
     src = os.path.join(HERE, "hostcheck.cu")
-    deps = [src] + [os.path.join(HERE, "..", "..", "fries_b200", "csrc", f) for f in ("mol.cuh", "common.cuh", "piv.cuh", "hbpp_prov.cuh", "hh_prov.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "..", "fries_b200", "csrc", f) for f in ("mol.cuh", "common.cuh", "piv.cuh", "hbpp_prov.cuh", "hh_prov.cuh", "hv_prov.cuh")]
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(SO), exist_ok=True)
@@ -83,5 +83,7 @@ def lib():
         L.hc_spawn_element.restype = C.c_uint64
         L.hc_spawn_element.argtypes = [C.c_uint64, u8p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                        C.POINTER(C.c_double)]
+        L.hc_hv_parent.restype = C.c_size_t
+        L.hc_hv_parent.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, u64p, f64p, C.c_size_t]
         _lib = L
     return _lib

@@ -8,6 +8,7 @@
 #include "../../fries_b200/csrc/piv.cuh"
 #include "../../fries_b200/csrc/hbpp_prov.cuh"
 #include "../../fries_b200/csrc/hh_prov.cuh"
+#include "../../fries_b200/csrc/hv_prov.cuh"
 #include <vector>
 
 struct HcMol {
@@ -416,5 +417,28 @@ uint64_t hc_spawn_element(uint64_t key, const uint8_t *orbs4, int is_doub, doubl
                           double init_thresh, double *add) {
     uint8_t o[4] = {orbs4[0], orbs4[1], orbs4[2], orbs4[3]};
     return hbpp_spawn_element(key, o, is_doub != 0, el, parent_val, eps, init_thresh, *add);
+}
+
+// ---- a16: the off-diagonal connections of one parent as the H.v kernels produce them: the 32 lanes' shares one after the
+// other (hv_prov.cuh); returns their number, fills out_keys / out_vals up to cap ----
+size_t hc_hv_parent(void *p, uint64_t key, double val, double h_fac, uint64_t *out_keys, double *out_vals, size_t cap) {
+    const MolView &m = ((HcMol *)p)->v;
+    ParentCtx pc;
+    parent_ctx(m, key, pc);
+    uint8_t occ[FRIES_MAX_ELEC + 1];
+    mol_occ_list(key, occ);
+    size_t n = 0;
+    unsigned counted = 0;
+    for (unsigned lane = 0; lane < 32; lane++)
+        counted += lane_excitations(m, pc, lane, [&](bool dbl, unsigned o0, unsigned o1, unsigned v0, unsigned v1) {
+            uint64_t nk;
+            double el = hv_connection(m, key, occ, dbl, o0, o1, v0, v1, val, h_fac, nk);
+            if (n < cap) {
+                out_keys[n] = nk;
+                out_vals[n] = el;
+            }
+            n++;
+        });
+    return counted == n ? n : (size_t)-1;
 }
 }
