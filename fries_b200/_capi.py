@@ -94,6 +94,7 @@ def _load():
         "fries_debug_set_bracket": (i, [i]),
         "fries_debug_set_perturb": (i, [d]),
         "fries_debug_last_fast": (i, [P(i)]),
+        "fries_debug_stage_ctas": (i, [P(i)]),
         "fries_comm_create": (i, [vp, i, i, P(vp), vp]),
         "fries_comm_connect": (i, [vp, vp]),
         "fries_comm_destroy": (i, [vp]),

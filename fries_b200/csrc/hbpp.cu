@@ -25,6 +25,10 @@ static int stage_min_ctas() {
     }();
     return v;
 }
+extern "C" int fries_debug_stage_ctas(int *ctas_per_sm) {
+    if (ctas_per_sm) *ctas_per_sm = stage_min_ctas();
+    return FRIES_OK;
+}
 template <int S>
 static const void *stage_kernel_ptr() {
     return stage_min_ctas() == 1 ? (const void *)hbpp_stage_kernel<S, 1> : (const void *)hbpp_stage_kernel<S, FR_STAGE_MIN_CTAS>;

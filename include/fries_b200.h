@@ -371,6 +371,9 @@ int fries_debug_set_bracket(int on);
 /* how many compressions of the last fries_comp_sub / fries_apply_hbpp_sys / fries_find_preserve call were decided by
  * the bracketed solve */
 int fries_debug_last_fast(int *n_fast);
+/* which build of the HB-PP stage kernels this process launches: 2 = two CTAs per SM (the product's configuration), 1 = the
+ * one-CTA-per-SM measurement variant (FRIES_STAGE_CTAS=1 in the environment when the library first asks) */
+int fries_debug_stage_ctas(int *ctas_per_sm);
 
 #ifdef __cplusplus
 }

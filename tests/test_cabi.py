@@ -47,3 +47,19 @@ def test_product_does_not_touch_the_oracle():
                 if re.search(r"oracle[/_]|oraclelib|reflib|hostcheck|libfries_ref|fries_oracle", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_stage_kernel_variant_selection():
+    """FRIES_STAGE_CTAS=1 selects the one-CTA-per-SM build of the stage kernels, anything else the product's two (read once
+    per process: child processes)"""
+    import subprocess
+    import sys
+    code = ("import ctypes, fries_b200._capi as c; v = ctypes.c_int(0); "
+            "assert c.lib.fries_debug_stage_ctas(ctypes.byref(v)) == 0; print(v.value)")
+    for env_val, want in ((None, "2"), ("1", "1"), ("0", "2"), ("12", "2")):
+        env = dict(os.environ)
+        env.pop("FRIES_STAGE_CTAS", None)
+        if env_val is not None:
+            env["FRIES_STAGE_CTAS"] = env_val
+        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 0 and r.stdout.strip() == want, (env_val, r.stdout)

@@ -18,6 +18,10 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
 
 def test_stage_kernels_one_cta_per_sm():
     env = dict(os.environ, FRIES_STAGE_CTAS="1")
+    code = ("import ctypes, fries_b200._capi as c; v = ctypes.c_int(0); "
+            "assert c.lib.fries_debug_stage_ctas(ctypes.byref(v)) == 0; print(v.value)")
+    sel = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, stdout=subprocess.PIPE, text=True)
+    assert sel.returncode == 0 and sel.stdout.strip() == "1"  # the children below launch the one-CTA build
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", "hbpp and not piv",
                         "tests/test_gpu_parity.py", "tests/test_gpu_golden.py", "tests/test_gpu_bracket.py",
                         "tests/test_hbpp_exact_limit.py"], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
