@@ -225,6 +225,11 @@ def run_ours(args, cfg):
     uni = mt_uniforms(1, 6 * (args.warmup + 2 * args.steps + 64)).reshape(-1, 6)
     ui = 0
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    if os.environ.get("FRIES_BENCH_NOFLUSH"):  # diagnostic only (how much of an iteration is cold-cache cost); says so in config
+        class _NoFlush:
+            def zero_(self):
+                pass
+        flush = _NoFlush()
 
     last = None
     for _ in range(args.warmup):
@@ -321,6 +326,22 @@ def run_ours(args, cfg):
                                    "candidate_rounds_us": [round((states[s, 18] - states[s, 13]) / 1e3, 1) for s in range(5)],
                                    "apply_cut_us": [round((states[s, 19] - states[s, 18]) / 1e3, 1) for s in range(5)]},
                 "iter_algorithmic_GBps": round((96 * n_vec + 200 * cfg["mat_nonz"] + 56 * stp.n_spawned) / (ms_per_step * 1e-3) / 1e9, 2)}
+    if os.environ.get("FRIES_TIMELINE"):
+        names = ["start", "A loop", "A cta-sum", "A grid-sum", "solve", "fixup", "set decided", "B loads", "B cta-sum", "B grid-sum",
+                 "grid seeded", "C loads", "C scan", "C tests", "C compact", "C rows", "C tile end", "C done", "C grid-sum",
+                 "D loads", "D scan", "D coded", "D heavy", "D tile end", "end", "A posted", "A reduced", "A solved", "A published"]
+        for s_ in range(5):
+            tl = vec.timeline(s_)
+            print(f"timeline stage {s_} (SM cycles, thread 0 of CTA 0): " +
+                  ", ".join(f"{nm} {int(tl[k])}" for k, nm in enumerate(names)), file=sys.stderr)
+    if os.environ.get("FRIES_CTA_MARKS"):
+        for s_ in (0, 3):
+            m = vec.cta_marks(s_)
+            for k, nm in enumerate(["start", "A done", "set decided", "B done", "C done", "end"]):
+                r = m[k]
+                order = r.argsort()
+                print(f"cta marks stage {s_} {nm}: min {r.min() / 1e3:.1f} us (cta {order[0]}), median {float(sorted(r)[len(r) // 2]) / 1e3:.1f}, "
+                      f"p90 {float(sorted(r)[int(len(r) * 0.9)]) / 1e3:.1f}, max {r.max() / 1e3:.1f} (cta {order[-1]}, {order[-2]}, {order[-3]})", file=sys.stderr)
     # the whole iteration against the roofline, by SURVEY 8d's byte contract B_iter = 96 N_v + 200 N_m + 56 N_s
     roofline["iter_frac"] = round(roofline["iter_algorithmic_GBps"] / peak, 5)
 
@@ -329,7 +350,7 @@ def run_ours(args, cfg):
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["workload"], "vec_nonz": cfg["vec_nonz"], "mat_nonz": cfg["mat_nonz"],
-                   "l2": "flushed between iterations (512 MB write)", "stored_dets": int(n_vec),
+                   "l2": ("NOT flushed (diagnostic run, FRIES_BENCH_NOFLUSH)" if os.environ.get("FRIES_BENCH_NOFLUSH") else "flushed between iterations (512 MB write)"), "stored_dets": int(n_vec),
                    "stage_ctas_per_sm": 1 if os.environ.get("FRIES_STAGE_CTAS") == "1" else 2},
         "spawned_elements_per_sec": round(spawned / (ms * 1e-3), 1),
         "matrix_samples_per_sec": round(samples / (ms * 1e-3), 1),

@@ -89,12 +89,15 @@ def _load():
         "fries_apply_hbpp_piv": (i, [vp, vp, vp, sz, d, i, vp, sz, P(sz), u, sz, vp, vp, vp, sz, P(sz)]),
         "fries_debug_hbpp_stage": (i, [vp, vp, vp, sz, d, i, vp, u, sz, i, vp, vp, vp, vp, P(sz)]),
         "fries_hbpp_states": (i, [vp, vp]),
+        "fries_hbpp_timeline": (i, [vp, i, vp]),
+        "fries_hbpp_cta_marks": (i, [vp, i, vp, P(i)]),
         "fries_hbpp_round_stamps": (i, [vp, i, vp]),
         "fries_debug_set_repeat": (i, [i]),
         "fries_debug_set_bracket": (i, [i]),
         "fries_debug_set_perturb": (i, [d]),
         "fries_debug_last_fast": (i, [P(i)]),
         "fries_debug_stage_ctas": (i, [P(i)]),
+        "fries_debug_stage_engine": (i, [P(i)]),
         "fries_comm_create": (i, [vp, i, i, P(vp), vp]),
         "fries_comm_connect": (i, [vp, vp]),
         "fries_comm_destroy": (i, [vp]),

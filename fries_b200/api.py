@@ -249,6 +249,20 @@ class Mol:
         n = n_out.value
         return ov[:n].copy(), od[:n].copy(), oo[:n].copy(), used.value
 
+    def debug_hbpp_stage(self, keys, vals, p_doub, new_hb, uniforms5, n_samp, spawn_cap, stage):
+        """diagnostics: the list that leaves the comp_sub call of `stage` (0..4) of apply_HBPP_sys ->
+        (values, parent index, 4-byte path of the parent item, chosen sub-index)"""
+        k, v, u = arr(keys, np.uint64), arr(vals, np.float64), arr(uniforms5, np.float64)
+        ov = np.zeros(spawn_cap)
+        od = np.zeros(spawn_cap, np.uint32)
+        op = np.zeros(spawn_cap, np.uint32)
+        os_ = np.zeros(spawn_cap, np.uint32)
+        n = C.c_size_t(0)
+        check(lib.fries_debug_hbpp_stage(self.h, ptr(k), ptr(v), k.size, p_doub, int(new_hb), ptr(u), n_samp, spawn_cap,
+                                         int(stage), ptr(ov), ptr(od), ptr(op), ptr(os_), C.byref(n)))
+        m = n.value
+        return ov[:m].copy(), od[:m].copy(), op[:m].copy(), os_[:m].copy()
+
     def apply_hbpp_sys(self, keys, vals, p_doub, new_hb, uniforms5, n_samp, spawn_cap):
         """apply_HBPP_sys heat_bathPP.cpp:686-992 -> (vals, parent index, orbs[n][4])"""
         k, v, u = arr(keys, np.uint64), arr(vals, np.float64), arr(uniforms5, np.float64)
@@ -409,6 +423,19 @@ class Vec:
         out = np.zeros((8, 20))
         check(lib.fries_hbpp_states(self.hb, ptr(out)))
         return out
+
+    def timeline(self, s):
+        """clock64 timeline (SM cycles from mark 0) of thread 0 of CTA 0 through the last compression of state s"""
+        out = np.zeros(48)
+        check(lib.fries_hbpp_timeline(self.hb, int(s), ptr(out)))
+        return out
+
+    def cta_marks(self, s):
+        """per-CTA phase-end times [8][grid] (ns) of stage s (needs FRIES_CTA_MARKS=1)"""
+        out = np.zeros((8, 1024))
+        g = C.c_int(0)
+        check(lib.fries_hbpp_cta_marks(self.hb, int(s), ptr(out), C.byref(g)))
+        return out.reshape(-1)[:8 * g.value].reshape(8, g.value)
 
     def frifull_iterate(self, params: FrifullParams, uniform: float) -> IterStats:
         st = IterStats()

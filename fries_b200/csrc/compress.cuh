@@ -31,7 +31,12 @@ struct CompState {
     unsigned long long gacc[40]; // grid-wide integer accumulators of the distributed candidate rounds (zeroed by the host)
     unsigned long long rts[16];  // %globaltimer of CTA 0 inside distributed rounds 0-3: start, before / after the grid
                                  // barrier, after the cross-rank exchange
+    long long tl[48];            // timeline of thread 0 of CTA 0 through comp_sub_engine2 (clock64, SM cycles): FR_TL marks
 };
+#define FR_TL(st, k)                                                        \
+    do {                                                                    \
+        if (blockIdx.x == 0 && threadIdx.x == 0) (st)->tl[k] = clock64();   \
+    } while (0)
 
 __device__ __forceinline__ unsigned long long fr_globaltimer() {
     unsigned long long t;

@@ -1,7 +1,7 @@
 // a10: apply_HBPP_sys (heat_bathPP.cpp:686-992) on the device.  See hbpp.cuh.
 #include "hbpp.cuh"
 
-extern __shared__ double fr_dyn_smem[];
+extern __shared__ __align__(16) double fr_dyn_smem[];
 
 #ifndef FR_STAGE_MIN_CTAS
 #define FR_STAGE_MIN_CTAS 2  // two 512-thread CTAs per SM (<= 64 registers): the stage passes are latency bound
@@ -17,6 +17,36 @@ hbpp_stage_kernel(MolView gm, HbStageIO io, CompSubBufs bufs, unsigned n_samp, d
     prov.m = mol_stage_shared(gm, fr_dyn_smem);
     prov.io = io;
     comp_sub_engine(prov, bufs, n_samp, rn);
+}
+// Second-generation engine (compress2.cuh): one 512-thread CTA per SM, up to 128 registers, four inputs per thread; the
+// table blob arrives by one bulk asynchronous copy.  This is the product's configuration; FRIES_ENGINE=1 in the
+// environment selects the first-generation kernels above (measurement / regression variant, same results up to FP ties).
+template <int S, int MINCTAS>
+__global__ void __launch_bounds__(FR2_NT, MINCTAS)
+hbpp_stage2_kernel(MolView gm, HbStageIO io, CompSubBufs2 bufs, unsigned n_samp, double rn) {
+    HbProvider<S> prov;
+    prov.m = mol_stage_shared_bulk(gm, fr_dyn_smem);
+    prov.io = io;
+    comp_sub_engine2(prov, bufs, n_samp, rn);
+}
+// FRIES_STAGE2_CTAS=2: two CTAs per SM (<= 64 registers) -- measurement variant of the second-generation kernels
+static int stage2_ctas() {
+    static int v = [] {
+        const char *e = getenv("FRIES_STAGE2_CTAS");
+        return (e && e[0] == '2' && e[1] == 0) ? 2 : 1;
+    }();
+    return v;
+}
+static int stage_engine() {
+    static int v = [] {
+        const char *e = getenv("FRIES_ENGINE");
+        return (e && e[0] == '1' && e[1] == 0) ? 1 : 2;
+    }();
+    return v;
+}
+extern "C" int fries_debug_stage_engine(int *generation) {
+    if (generation) *generation = stage_engine();
+    return FRIES_OK;
 }
 static int stage_min_ctas() {
     static int v = [] {
@@ -131,9 +161,13 @@ int fries_hbpp_alloc(fries_ctx *c, size_t cap, fries_hbpp **out, bool stages) {
         A(fin_val, cap); A(fin_det, cap); A(fin_orbs, cap);
     }
     A(part_d, FR_RED_PART_LEN); A(part_c, FR_RED_PART_LEN); A(st, 8); A(n_scalar, 4); A(scal, 64);
-    A(cand_x, FR_CAND_GCAP); A(cand_m, FR_CAND_GCAP); A(pred, 8);
+    A(cand_x, FR_CAND_GCAP); A(cand_m, FR_CAND_GCAP); A(cand_idx, FR_CAND_GCAP); A(pred, 8); A(gcomb, GC_STATE_WORDS);
 #undef A
     if (rc == FRIES_OK && cudaMemset(hb->scal.p, 0, 64 * sizeof(double)) != cudaSuccess) {
+        fries_set_error("fries_hbpp_alloc: cudaMemset failed");
+        rc = FRIES_ERR_CUDA;
+    }
+    if (rc == FRIES_OK && cudaMemset(hb->gcomb.p, 0, (size_t)GC_STATE_WORDS * 8) != cudaSuccess) {
         fries_set_error("fries_hbpp_alloc: cudaMemset failed");
         rc = FRIES_ERR_CUDA;
     }
@@ -208,9 +242,32 @@ static int launch_stage(fries_hbpp *hb, fries_mol *mol, HbStageIO &io, CompSubBu
         hb->grid = g;
     }
     MolView gm = mol->view;
-    void *args[] = {(void *)&gm, (void *)&io, (void *)&bufs, (void *)&n_samp, (void *)&rn};
     static const char *names[] = {"hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4"};
     ProfScope ps(c, names[S]);
+    if (stage_engine() == 2) {
+        const int ctas = stage2_ctas();
+        const void *kern = ctas == 2 ? (const void *)hbpp_stage2_kernel<S, 2> : (const void *)hbpp_stage2_kernel<S, 1>;
+        static bool attr_set[2] = {false, false};  // per instantiation <S, ctas>: opt in to more than 48 kB of shared memory
+        if (!attr_set[ctas - 1]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_set[ctas - 1] = true;
+        }
+        if (hb->grid2 == 0) {
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FR2_NT, smem));
+            FRIES_REQUIRE(per_sm >= ctas, "hbpp_stage2_kernel<%d>: %d CTAs per SM do not fit (%zu B of dynamic shared memory)", S,
+                          ctas, smem);
+            hb->grid2 = c->sm_count * ctas;
+        }
+        static const bool marks = getenv("FRIES_CTA_MARKS") != nullptr;
+        if (marks && !hb->cta_marks.p) FRIES_TRY(hb->cta_marks.alloc((size_t)5 * 8 * 1024));
+        CompSubBufs2 b2{bufs, hb->cand_idx.p, hb->gcomb.p, marks ? hb->cta_marks.p + (size_t)S * 8 * 1024 : nullptr};
+        void *args2[] = {(void *)&gm, (void *)&io, (void *)&b2, (void *)&n_samp, (void *)&rn};
+        CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(hb->grid2), dim3(FR2_NT), args2, smem, c->stream));
+        c->launch_count++;
+        return FRIES_OK;
+    }
+    void *args[] = {(void *)&gm, (void *)&io, (void *)&bufs, (void *)&n_samp, (void *)&rn};
     CUDA_TRY(cudaLaunchCooperativeKernel(stage_kernel_ptr<S>(), dim3(hb->grid), dim3(FR_COMP_BLOCK), args,
                                          smem, c->stream));
     c->launch_count++;
@@ -692,6 +749,36 @@ extern "C" int fries_hbpp_round_stamps(fries_hbpp *hb, int s, double *h_out16) {
     CUDA_TRY(cudaMemcpyAsync(&st, hb->st.p + s, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 16; k++) h_out16[k] = st.rts[k] >= st.rts[0] ? (double)(st.rts[k] - st.rts[0]) : -1.0;
+    return FRIES_OK;
+}
+
+// Diagnostics: the timeline of thread 0 of CTA 0 through state s's last run of comp_sub_engine2 (CompState::tl, SM cycles
+// relative to mark 0; -1 = mark not passed)
+extern "C" int fries_hbpp_timeline(fries_hbpp *hb, int s, double *h_out48) {
+    FRIES_REQUIRE(hb && h_out48 && s >= 0 && s < 8, "fries_hbpp_timeline: bad argument");
+    fries_ctx *c = hb->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CompState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, hb->st.p + s, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 48; k++) h_out48[k] = st.tl[k] >= st.tl[0] && st.tl[k] != 0 ? (double)(st.tl[k] - st.tl[0]) : -1.0;
+    return FRIES_OK;
+}
+
+// Diagnostics (FRIES_CTA_MARKS=1): %globaltimer of every CTA at the phase ends of stage s's last run, [8][grid] in ns
+// relative to the earliest CTA's first mark
+extern "C" int fries_hbpp_cta_marks(fries_hbpp *hb, int s, double *h_out, int *grid) {
+    FRIES_REQUIRE(hb && h_out && grid && s >= 0 && s < 5, "fries_hbpp_cta_marks: bad argument");
+    FRIES_REQUIRE(hb->cta_marks.p && hb->grid2 > 0, "fries_hbpp_cta_marks: set FRIES_CTA_MARKS=1 before the first iteration");
+    fries_ctx *c = hb->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<unsigned long long> m((size_t)8 * hb->grid2);
+    CUDA_TRY(cudaMemcpyAsync(m.data(), hb->cta_marks.p + (size_t)s * 8 * 1024, m.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    unsigned long long t0 = ~0ull;
+    for (int q = 0; q < hb->grid2; q++) t0 = m[q] < t0 ? m[q] : t0;
+    for (size_t q = 0; q < m.size(); q++) h_out[q] = m[q] >= t0 ? (double)(m[q] - t0) : -1.0;
+    *grid = hb->grid2;
     return FRIES_OK;
 }
 

@@ -9,6 +9,7 @@
 // path; read + written), not the n_states x 8 B row.
 #pragma once
 #include "compress.cuh"
+#include "compress2.cuh"
 #include "molhost.cuh"
 #include "hbpp_prov.cuh"
 
@@ -26,14 +27,16 @@ struct fries_hbpp {
     // bracketed threshold solve (compress.cuh): candidate list (shared by all compressions of an iteration, which
     // run one after the other) and one prediction per compression site: [0..4] HB-PP stages, [5] find_preserve
     DevBuf<double> cand_x;
-    DevBuf<uint32_t> cand_m;
+    DevBuf<uint32_t> cand_m, cand_idx;  // cand_idx: input index of every candidate (compress2.cuh)
     DevBuf<KeepPred> pred;
+    DevBuf<unsigned long long> gcomb;      // GridComb state of the second-generation stage kernels (gridcomb.cuh)
+    DevBuf<unsigned long long> cta_marks;  // diagnostics: [5 stages][8 marks][grid] (FRIES_CTA_MARKS=1)
     // frisys/frifull driver state (iter.cu)
     DevBuf<uint64_t> trial_keys, htrial_keys, spawn_keys;
     DevBuf<double> trial_vals, htrial_vals, spawn_vals, scal;
     DevBuf<uint8_t> keep_flags;
     size_t n_trial = 0, n_htrial = 0;
-    int grid = 0;
+    int grid = 0, grid2 = 0;  // cooperative grid of the stage kernels: first / second generation engine
     fries_comm *comm = nullptr;  // multi-rank: peer-mapped inboxes (comm.cuh); not owned
     // multi-rank routing: per-destination send segments (keys | vals) and counters
     int64_t *send_buf = nullptr, *recv_buf = nullptr;  // caller-owned device buffers [n_ranks][2 * seg_cap]

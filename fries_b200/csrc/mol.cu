@@ -97,6 +97,7 @@ extern "C" int fries_mol_create(fries_ctx *c, unsigned n_orb, unsigned n_elec_to
     d.off_symm = off; off += (M + 7) / 8;
     d.off_lookup = off; off += (FR_N_IRREPS * (M + 1) + 7) / 8;
     d.off_irr = off; off += (FR_N_IRREPS * 4 + 7) / 8;
+    off = (off + 1) & ~1u;  // a multiple of 16 bytes: the stage kernels fetch the blob with one cp.async.bulk (molhost.cuh)
     d.blob_doubles = off;
     // symmetry tables (integer bookkeeping; gen_symm_lookup molecule.cpp:1050-1065, SymmInfo molecule.hpp:265-280)
     std::vector<double> h_blob(off, 0.0);

@@ -387,42 +387,60 @@ __host__ __device__ __forceinline__ unsigned mol_elec_orb(const MolView &m, cons
     return idx < h ? fr_nth_bit32(o.a, idx) : m.d.n_orb + fr_nth_bit32(o.b, idx - h);
 }
 
+
+// Rows are streamed in chunks of FR_ROW_CHUNK entries: the table look-ups of a chunk are issued together (independent
+// shared-memory loads in flight), then the chunk's entries go to the visitor in order.  A visitor's arithmetic is a serial
+// FP64 chain (running norm, running prefix); with one look-up per iteration every entry paid the load latency inside
+// that chain (~100 cycles per entry and warp, measured round 2), which bounded every stage kernel.
+// gen(j) returns the raw weight of entry j and is called for j = 0 .. n - 1 in order (it may carry state, e.g. a bit
+// mask whose lowest set bit it consumes); a negative return value ends the row before entry j.
+#define FR_ROW_CHUNK 8
+template <class G, class F>
+__host__ __device__ __forceinline__ void fr_row_chunked(unsigned n, G &&gen, F &&f) {
+    for (unsigned j0 = 0; j0 < n; j0 += FR_ROW_CHUNK) {
+        double raw[FR_ROW_CHUNK];
+#pragma unroll
+        for (int q = 0; q < FR_ROW_CHUNK; q++) raw[q] = j0 + q < n ? gen(j0 + q) : -1.0;
+#pragma unroll
+        for (int q = 0; q < FR_ROW_CHUNK; q++) {
+            if (j0 + q >= n || raw[q] < 0) return;
+            if (!fr_emit(f, j0 + q, raw[q])) return;
+        }
+    }
+}
+
 // calc_o1_probs :182-200: one entry per electron (the first is skipped when exclude_first); norm = sum in index order
 template <class F>
 __host__ __device__ __forceinline__ void hbs_o1(const MolView &m, uint64_t key, int exclude_first, F &&f) {
     OccMask o = mol_occ_mask(m, key);
-    unsigned j = 0;
-    uint32_t am = o.a;
+    uint32_t am = o.a, bm = o.b;
     if (exclude_first > 0) am &= am - 1;
-    while (am) {
-        if (!fr_emit(f, j++, m.s_tens[fr_ctz(am)])) return;
-        am &= am - 1;
-    }
-    uint32_t bm = o.b;
-    while (bm) {
-        if (!fr_emit(f, j++, m.s_tens[fr_ctz(bm)])) return;
-        bm &= bm - 1;
-    }
+    const unsigned na = (unsigned)fr_popc((uint64_t)am), n = na + (unsigned)fr_popc((uint64_t)bm);
+    fr_row_chunked(n, [&](unsigned j) {
+        uint32_t &mk = j < na ? am : bm;
+        const unsigned q = (unsigned)fr_ctz(mk);
+        mk &= mk - 1;
+        return m.s_tens[q];
+    }, f);
 }
 // calc_o2_probs_half :236-270: entries for the electrons before o1_idx
 template <class F>
 __host__ __device__ __forceinline__ void hbs_o2_half(const MolView &m, uint64_t key, unsigned o1_idx, F &&f) {
     const unsigned ne = m.d.n_elec, M = m.d.n_orb, h = ne / 2;
     OccMask o = mol_occ_mask(m, key);
-    unsigned o1 = mol_elec_orb(m, o, o1_idx);
-    unsigned upper = h > o1_idx ? o1_idx : h, j = 0;
-    uint32_t am = o.a;
-    for (; j < upper; j++) {
-        unsigned q = fr_ctz(am);
-        am &= am - 1;
-        if (!fr_emit(f, j, o1 < M ? m.d_same[FR_TRI_NODIAG(q, o1)] : m.d_diff[(o1 - M) * M + q])) return;
-    }
-    uint32_t bm = o.b;
-    for (j = h; j < o1_idx; j++) {
-        unsigned q = fr_ctz(bm);
+    const unsigned o1 = mol_elec_orb(m, o, o1_idx);
+    // entries j < o1_idx: the alpha electrons before o1 (j < h), then the beta electrons before it (j >= h)
+    uint32_t am = o.a, bm = o.b;
+    fr_row_chunked(o1_idx, [&](unsigned j) {
+        if (j < h) {
+            const unsigned q = (unsigned)fr_ctz(am);
+            am &= am - 1;
+            return o1 < M ? m.d_same[FR_TRI_NODIAG(q, o1)] : m.d_diff[(o1 - M) * M + q];
+        }
+        const unsigned q = (unsigned)fr_ctz(bm);
         bm &= bm - 1;
-        if (!fr_emit(f, j, o1 < M ? m.d_diff[o1 * M + q] : m.d_same[FR_TRI_NODIAG(q, o1 - M)])) return;
-    }
+        return o1 < M ? m.d_diff[o1 * M + q] : m.d_same[FR_TRI_NODIAG(q, o1 - M)];
+    }, f);
 }
 // calc_o2_probs :203-233: ne entries in index order (entry o1_idx is 0)
 template <class F>
@@ -459,14 +477,13 @@ template <class F>
 __host__ __device__ __forceinline__ void hbs_u1(const MolView &m, uint64_t key, unsigned o1_orb, F &&f) {
     const unsigned M = m.d.n_orb;
     OccMask o = mol_occ_mask(m, key);
-    unsigned o1s = o1_orb % M;
+    const unsigned o1s = o1_orb % M;
     uint32_t vm = ~(o1_orb / M ? o.b : o.a) & (uint32_t)((1ull << M) - 1);
-    unsigned j = 0;
-    while (vm) {
-        unsigned k = fr_ctz(vm);
+    fr_row_chunked((unsigned)fr_popc((uint64_t)vm), [&](unsigned) {
+        const unsigned k = (unsigned)fr_ctz(vm);
         vm &= vm - 1;
-        if (!fr_emit(f, j++, m.exch_sqrt[k < o1s ? FR_TRI_NODIAG(k, o1s) : FR_TRI_NODIAG(o1s, k)])) return;
-    }
+        return m.exch_sqrt[k < o1s ? FR_TRI_NODIAG(k, o1s) : FR_TRI_NODIAG(o1s, k)];
+    }, f);
 }
 __host__ __device__ __forceinline__ double hbs_u2_weight(const MolView &m, unsigned o2s, unsigned u2) {
     if (o2s == u2) return m.diag_sqrt[o2s];
@@ -477,30 +494,28 @@ __host__ __device__ __forceinline__ double hbs_u2_weight(const MolView &m, unsig
 template <class F>
 __host__ __device__ __forceinline__ void hbs_u2(const MolView &m, unsigned o1_orb, unsigned o2_orb, unsigned u1_orb, F &&f) {
     const unsigned M = m.d.n_orb;
-    unsigned o2s = o2_orb % M, u1s = u1_orb % M;
-    bool same = (o1_orb / M) == (o2_orb / M);
-    unsigned irrep = m.symm[o1_orb % M] ^ m.symm[o2s] ^ m.symm[u1s];
-    unsigned num = mol_lookup(m, irrep, 0);
-    for (unsigned i = 0; i < num; i++) {
-        unsigned u2 = mol_lookup(m, irrep, i + 1);
-        if (!fr_emit(f, i, ((same && u2 != u1s) || !same) ? hbs_u2_weight(m, o2s, u2) : 0.0)) return;
-    }
+    const unsigned o2s = o2_orb % M, u1s = u1_orb % M;
+    const bool same = (o1_orb / M) == (o2_orb / M);
+    const unsigned irrep = m.symm[o1_orb % M] ^ m.symm[o2s] ^ m.symm[u1s];
+    fr_row_chunked(mol_lookup(m, irrep, 0), [&](unsigned i) {
+        const unsigned u2 = mol_lookup(m, irrep, i + 1);
+        return ((same && u2 != u1s) || !same) ? hbs_u2_weight(m, o2s, u2) : 0.0;
+    }, f);
 }
 // calc_u2_probs_half :368-412: stops at u2 >= u1 for same-spin pairs; occupied u2 get 0
 template <class F>
 __host__ __device__ __forceinline__ void hbs_u2_half(const MolView &m, unsigned o1_orb, unsigned o2_orb, unsigned u1_orb,
                                                      uint64_t det, F &&f) {
     const unsigned M = m.d.n_orb;
-    unsigned o2s = o2_orb % M, u1s = u1_orb % M, u2_spin = o2_orb / M;
-    bool same = (o1_orb / M) == u2_spin;
-    unsigned irrep = m.symm[o1_orb % M] ^ m.symm[o2s] ^ m.symm[u1s];
-    unsigned num = mol_lookup(m, irrep, 0);
-    for (unsigned i = 0; i < num; i++) {
-        unsigned u2 = mol_lookup(m, irrep, i + 1);
-        if (same && u2 >= u1s) break;
-        bool ok = ((same && u2 != u1s) || !same) && !fr_read_bit(det, u2 + M * u2_spin);
-        if (!fr_emit(f, i, ok ? hbs_u2_weight(m, o2s, u2) : 0.0)) return;
-    }
+    const unsigned o2s = o2_orb % M, u1s = u1_orb % M, u2_spin = o2_orb / M;
+    const bool same = (o1_orb / M) == u2_spin;
+    const unsigned irrep = m.symm[o1_orb % M] ^ m.symm[o2s] ^ m.symm[u1s];
+    fr_row_chunked(mol_lookup(m, irrep, 0), [&](unsigned i) {
+        const unsigned u2 = mol_lookup(m, irrep, i + 1);
+        if (same && u2 >= u1s) return -1.0;  // the row ends here (the weights themselves are never negative)
+        const bool ok = ((same && u2 != u1s) || !same) && !fr_read_bit(det, u2 + M * u2_spin);
+        return ok ? hbs_u2_weight(m, o2s, u2) : 0.0;
+    }, f);
 }
 
 // Array forms with the reference's signatures and return values (parity entry points, finalize-free code).

@@ -215,7 +215,7 @@ local_norm_kernel(VecView v, unsigned row, int squares, double *part_d, unsigned
     }
     unsigned long long dummy = 0;
     grid_reduce(grid, red, s, dummy);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *out = squares ? sqrt(s) : s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out = s;  // two_norm is the SUM of squares (vec_utils.hpp:695-701: no root)
 }
 
 // ---------------------------------------------------------------------------------------------------

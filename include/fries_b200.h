@@ -219,7 +219,7 @@ int fries_vec_del(fries_vec *vec, const uint8_t *h_flags, size_t n);
 int fries_vec_dot(fries_vec *vec, const uint64_t *h_keys, const double *h_vals, size_t n, unsigned row, double *out);
 /* DistVec::local_norm :683-689 of a row */
 int fries_vec_local_norm(fries_vec *vec, unsigned row, double *out);
-int fries_vec_two_norm(fries_vec *vec, unsigned row, double *out);   /* DistVec::two_norm :695-701 */
+int fries_vec_two_norm(fries_vec *vec, unsigned row, double *out);   /* DistVec::two_norm :695-701: the sum of squares (the reference takes no root) */
 /* row arithmetic on the stored elements (vec_utils.hpp:547-579).  op 0: add_vecs(dst, src, c)  dst += c * src;
  * 1: copy_vec(src, dst); 2: weight_vec(dst, src, expo = c)  dst *= (1 + |src|)^c; 3: zero_vec of row dst */
 int fries_vec_row_op(fries_vec *vec, int op, unsigned dst, unsigned src, double c);
@@ -374,6 +374,13 @@ int fries_debug_last_fast(int *n_fast);
 /* which build of the HB-PP stage kernels this process launches: 2 = two CTAs per SM (the product's configuration), 1 = the
  * one-CTA-per-SM measurement variant (FRIES_STAGE_CTAS=1 in the environment when the library first asks) */
 int fries_debug_stage_ctas(int *ctas_per_sm);
+/* generation of the compression engine the HB-PP stage kernels run (2 = csrc/compress2.cuh, the default; 1 with
+ * FRIES_ENGINE=1 in the environment: the first-generation kernels, kept as a regression / measurement variant) */
+int fries_debug_stage_engine(int *generation);
+/* diagnostics: clock64 timeline (SM cycles) of thread 0 of CTA 0 through the last compression of state s (0-4: HB-PP stages) */
+int fries_hbpp_timeline(fries_hbpp *hb, int s, double *h_out48);
+/* diagnostics (FRIES_CTA_MARKS=1 in the environment): per-CTA phase-end times of stage s, h_out[8][*grid] in ns */
+int fries_hbpp_cta_marks(fries_hbpp *hb, int s, double *h_out, int *grid);
 
 #ifdef __cplusplus
 }

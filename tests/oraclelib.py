@@ -139,6 +139,17 @@ class OracleMol:
                                         oo.reshape(-1))
         return ov[:n].copy(), od[:n].copy(), oo[:n].copy()
 
+    def debug_hbpp_stage(self, keys, vals, p_doub, new_hb, uniforms5, n_samp, spawn_length, stage):
+        """the list that leaves the comp_sub call of `stage` (0..4): (values, parent index, sub-index)"""
+        ov = np.zeros(spawn_length)
+        od = np.zeros(spawn_length, np.uint64)
+        oo = np.zeros((spawn_length, 4), np.uint8)
+        os_ = np.zeros(spawn_length, np.uint32)
+        n = lib().fo_debug_hbpp_stage(self.h, np.ascontiguousarray(keys, np.uint64), np.ascontiguousarray(vals, np.float64),
+                                      len(keys), p_doub, int(new_hb), np.ascontiguousarray(uniforms5, np.float64), n_samp,
+                                      spawn_length, int(stage), ov, od, oo.reshape(-1), os_)
+        return ov[:n].copy(), od[:n].copy(), os_[:n].copy()
+
     def apply_hbpp_piv(self, keys, vals, p_doub, new_hb, draws, n_samp, spawn_length):
         """heat_bathPP.cpp:1014-1419 -> (values, det indices, orbitals, draws consumed)"""
         ov = np.zeros(spawn_length)

@@ -13,16 +13,16 @@
     sum, a second non-initiator add of the same elements doubles every value and creates nothing, a determinant that is not
     stored is refused without the initiator flag, only elements that are zero in every row can be deleted.
 
-All of it goes through calls the verified tier covers at small sizes; the file was written after this round's GPU minutes
-were spent, so the cases are non-strict xfail until a green run is on record."""
+All of it goes through calls the verified tier covers at small sizes.  First GPU run: round 2 (vector compression and
+the store passed as written; the apply_HBPP_sys case compared the END of the five chained stages with the oracle, which
+cannot work at this size -- see test_apply_hbpp_sys_fullsize)."""
 import numpy as np
 import pytest
 
 import oraclelib
 from fries_b200.synth import SynthMol
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="first GPU run of the full-size property tests is pending")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 @pytest.fixture(scope="module")
@@ -75,12 +75,28 @@ def test_vector_compression_properties(ctx, n, budget, kind):
     assert np.abs(out2).sum() == pytest.approx(a.sum(), rel=1e-9)
 
 
-def test_apply_hbpp_sys_properties_h2o_1e6(ctx):
+def _code(det, sub):
+    return (det.astype(np.uint64) << np.uint64(32)) | sub.astype(np.uint64)
+
+
+@pytest.mark.parametrize("mol_name,seed,n_det,n_samp", [("h2o", 3, 50_000, 1_000_000), ("ne", 2, 200_000, 1_000_000)])
+def test_apply_hbpp_sys_fullsize(ctx, mol_name, seed, n_det, n_samp):
+    """apply_HBPP_sys (heat_bathPP.cpp:686-992) with 1e6 samples on the H2O- and Ne-sized molecules.
+
+    What can be compared at this size.  A systematic resampling of 1e6 samples decides every sample by comparing a grid point
+    with a prefix sum of ~1e6 terms; the oracle sums sequentially, the kernels in tiles, so a handful of grid points within
+    rounding distance of an interval boundary fall on the other side (FP-boundary ties: 3 of 1e6 in the first compressing
+    stage of the first GPU run of this input).  A moved sample changes the one-norm of the NEXT stage's input by ~1e-12,
+    hence its grid spacing, and a grid of 1e6 points shifted by 1e-12 relative moves most samples that sit within 1e-6 of
+    a boundary: the five stages are a chaotic map at the level of single samples, and their END results are comparable only
+    statistically.  So the test walks the stages: up to and including the first stage with a difference the lists must be
+    the oracle's (chunk 1) up to counted ties; after it only the invariants are checked (sample count, one-norm of
+    the list up to the ties' weight).  The distance to the UNMODIFIED reference arithmetic (find_keep_sub's chunk of 8,
+    compress_utils.cpp:160-178: oracle chunk 8, pinned bit for bit to the compiled reference) is reported the same way."""
     import fries_b200
-    sm = SynthMol("h2o", 3, True)
+    sm = SynthMol(mol_name, seed, True)
     mol = fries_b200.Mol.from_synth(ctx, sm)
     rng = np.random.default_rng(5)
-    n_det, n_samp = 50_000, 1_000_000
     keys = np.concatenate([[sm.hf], sm.random_dets(n_det - 1, rng, 0)]).astype(np.uint64)
     vals = rng.lognormal(0, 2, n_det) * rng.choice([-1.0, 1.0], n_det)
     vals[0] = 50 * np.abs(vals).max()
@@ -106,21 +122,37 @@ def test_apply_hbpp_sys_properties_h2o_1e6(ctx):
     assert np.all(o[d, 0] < o[d, 1]) and np.all(o[d, 2] < o[d, 3])
     assert np.all((irr(0) ^ irr(1) ^ irr(2) ^ irr(3))[d] == 0)
     assert np.all((spin(0) + spin(1))[d] == (spin(2) + spin(3))[d])
-    # the oracle manages this size in seconds: the same samples (chunk size 1 as in tests/test_gpu_parity.py; five chained
-    # resampling stages, so one boundary tie early on moves a handful of downstream samples)
-    om = oraclelib.OracleMol(sm)
-    with oraclelib.keep_chunk(1):
-        ov, od, oo = om.apply_hbpp_sys(keys, vals, 0.98, 1, u5, n_samp, cap)
-    code = lambda dd, orbs: (dd.astype(np.uint64) << np.uint64(32)) | (orbs.astype(np.uint64) * (np.uint64(1) << (np.uint64(8) * np.arange(4, dtype=np.uint64)))).sum(axis=1)
-    gc, oc = code(gd, go), code(od, oo)
-    n_diff = len(np.setxor1d(gc, oc))
-    print(f"apply_hbpp_sys at 1e6 samples: {n} samples, {n_diff} differ from the oracle")
-    assert n_diff <= max(6, len(oc) // 5000)
-    if n_diff == 0:
-        assert np.array_equal(gd, od) and np.array_equal(go, oo) and np.allclose(gv, ov, rtol=1e-9, atol=0)
     # deterministic: the same call returns the same samples, bit for bit
     gv2, gd2, go2 = mol.apply_hbpp_sys(keys, vals, 0.98, 1, u5, n_samp, cap)
     assert np.array_equal(gv, gv2) and np.array_equal(gd, gd2) and np.array_equal(go, go2)
+    # stage by stage against the oracle
+    om = oraclelib.OracleMol(sm)
+    report = {}
+    for chunk in (1, 8):
+        first = None
+        for stage in range(5):
+            sv, sd, _, ss = mol.debug_hbpp_stage(keys, vals, 0.98, 1, u5, n_samp, cap, stage)
+            with oraclelib.keep_chunk(chunk):
+                ov, od, os_ = om.debug_hbpp_stage(keys, vals, 0.98, 1, u5, n_samp, cap, stage)
+            gc, oc = _code(sd, ss), _code(od, os_)
+            n_diff = len(np.setxor1d(gc, oc)) if (len(gc) != len(oc) or not np.array_equal(gc, oc)) else 0
+            report[(chunk, stage)] = (len(gc), len(oc), n_diff)
+            if first is None:
+                if n_diff == 0:
+                    assert np.allclose(sv, ov, rtol=1e-9, atol=0)
+                    continue
+                first = stage
+                if chunk == 1:
+                    # FP-boundary ties of THIS stage (its inputs were identical): counted and bounded
+                    assert n_diff <= max(6, len(oc) // 5000), f"stage {stage}: {n_diff} of {len(oc)} entries differ from the oracle"
+                else:
+                    assert n_diff <= max(8, len(oc) // 50), f"stage {stage}: {n_diff} of {len(oc)} entries differ from chunk 8"
+            # every stage, diverged or not: the same number of entries and the same one-norm up to the moved samples
+            assert abs(len(gc) - len(oc)) <= max(6, len(oc) // 5000)
+            assert sv.sum() == pytest.approx(ov.sum(), rel=1e-4)
+        print(f"apply_hbpp_sys {mol_name} {n_det} parents, {n_samp} samples, oracle chunk {chunk}: first stage with a "
+              f"difference: {first}; (entries gpu, entries oracle, differing) per stage: "
+              f"{[report[(chunk, st)] for st in range(5)]}")
     mol.close()
 
 

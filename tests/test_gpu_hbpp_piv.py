@@ -1,13 +1,11 @@
 """GPU tier, LAST file on purpose: fries_apply_hbpp_piv (apply_HBPP_piv, heat_bathPP.cpp:1014-1419) against the oracle's
 restatement, which is pinned to the compiled reference (tests/test_oracle_piv.py, golden tests/golden/piv_golden.npz).
 
-The device pipeline was written after this round's GPU budget was spent: it compiles for sm_100a and is a composition of
-pieces that are verified on the GPU (stage providers, pivotal compression, finalize kernel) whose composition reproduces the
-oracle sample for sample when run on the host (tests/test_hostcheck_hbpp_piv.py), but its first GPU run is this test.  Until a green run is on record
-  * every case runs in a CHILD process under a hard wall-clock limit (a fault or a hang of an unverified kernel ends the
-    child, never the pytest process that carries the verified tier), and
-  * the cases are non-strict xfail, so that they report XPASS / XFAIL without deciding the tier;
-the file sorts last so that nothing runs after it.  `python tests/test_zz_gpu_hbpp_piv.py <case>` is the child."""
+The device pipeline is a composition of pieces that are verified on the GPU (stage providers, pivotal compression, finalize
+kernel) whose composition reproduces the oracle sample for sample when run on the host (tests/test_hostcheck_hbpp_piv.py).
+First GPU run: round 2, 4 of 4 cases green as written.  Every case still runs in a CHILD process under a hard wall-clock
+limit (the pipeline synchronises with the host between its launches; a hang ends the child, not the tier);
+the file sorts last so that nothing runs after it.  `python tests/test_gpu_hbpp_piv.py <case>` is the child."""
 import json
 import os
 import subprocess
@@ -20,8 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = [(("ne", 2, False), 1, 1, 50), (("ne", 2, True), 1, 300, 1000), (("h2o", 3, True), 0, 1000, 1500),
          (((8, 6, 0, [0, 0, 1, 2, 3, 0, 1, 2]), 4, True), 1, 40, 3000)]
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="first GPU run of fries_apply_hbpp_piv is pending (written without GPU access)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 def run_case(idx):

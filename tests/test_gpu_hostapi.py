@@ -3,7 +3,7 @@ occ_orbs / operator[] / operator() / orbs_at_pos / matr_el_at_pos / internal_dot
 add_elements / push_host; FRIES/vec_utils.hpp:200-953) checked by the self-checking program
 fries_b200/host/distvec_check.cpp.  The accessors are host code over C-ABI calls that the verified tier covers
 (fries_vec_download / upload / add / dot), written after this round's GPU budget was spent: the program is a child process
-and the case a non-strict xfail until a green run is on record.  Pure-host pieces: tests/test_hostapi_cpu.py (CPU tier)."""
+(first GPU run, round 2: one failure -- fries_vec_two_norm returned the root of the sum of squares, the reference returns the sum, vec_utils.hpp:695-701; fixed in csrc/vec.cu).  Pure-host pieces: tests/test_hostapi_cpu.py (CPU tier)."""
 import os
 import subprocess
 
@@ -12,8 +12,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "fries_b200", "host", "bin", "distvec_check")
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(200),
-              pytest.mark.xfail(strict=False, reason="first GPU run of distvec_check is pending (written without GPU access)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(200)]
 
 
 def test_distvec_raw_pointer_view():

@@ -2,8 +2,7 @@
 
 FRIES_STAGE_CTAS=1 selects the one-CTA-per-SM build of the five HB-PP stage kernels (116 registers, no spills, half the
 resident warps; csrc/hbpp.cu).  Same source, same arithmetic: the systematic-pipeline parity, golden and bracket tests must
-pass unchanged with it.  Child process (the variant is chosen when the library first launches a stage), non-strict xfail
-until its first GPU run is on record."""
+pass unchanged with it.  Child process (the variant is chosen when the library first launches a stage)."""
 import os
 import subprocess
 import sys
@@ -12,8 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="first GPU run of the FRIES_STAGE_CTAS=1 variant is pending")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def test_stage_kernels_one_cta_per_sm():

@@ -1,7 +1,7 @@
 """CPU tier: the pure-host pieces of the C++ mirror of the reference's interface (fries_b200/host/fries_host.hpp) --
 Matrix<T> (ndarr.hpp), find_bits (math_utils.c:62-98), HashTable::hash_fxn (det_hash.hpp:160-170) as used by
 DistVec::idx_to_hash / idx_to_proc -- against the oracle.  The accessors that touch the device store are exercised on the
-GPU by fries_b200/host/distvec_check.cpp (tests/test_zz_gpu_hostapi.py)."""
+GPU by fries_b200/host/distvec_check.cpp (tests/test_gpu_hostapi.py)."""
 import os
 import subprocess
 

@@ -4,7 +4,7 @@ host.  tests/hostcheck compiles the product's per-input arithmetic for the host 
 -- and restates the scans, the collapse and the buffer ping-pong of hbpp.cu; the pivotal compression between expand and
 collapse is the oracle's piv_comp_parallel here.  With the same compression the composition must reproduce the oracle's
 apply_HBPP_piv (pinned to the compiled reference, tests/test_oracle_piv.py): same samples, same draw count.  What stays
-for the GPU tier (tests/test_zz_gpu_hbpp_piv.py): launch geometry, the one-CTA scans, the resident compression."""
+for the GPU tier (tests/test_gpu_hbpp_piv.py): launch geometry, the one-CTA scans, the resident compression."""
 import numpy as np
 import pytest
 
