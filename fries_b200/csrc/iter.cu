@@ -251,39 +251,44 @@ static int h_apply_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned 
     size_t n_parents = (size_t)cnt.n;
     if (only_first && only_first < n_parents) n_parents = only_first;  // the dense subspace of a semi-stochastic run
     if (n_spawned) *n_spawned = 0;
-    if (n_parents == 0) return FRIES_OK;
+    // A rank that stores nothing (every non-owner rank when frifull_mol starts from the Hartree-Fock determinant) has no
+    // connection of its own but must still take part in every collective below: the round count, the publish / wait /
+    // merge of every window (it receives its share of the others' connections) and the barrier after each merge.
+    if (n_parents == 0 && vec->n_ranks <= 1) return FRIES_OK;
     size_t smem = (size_t)mol->view.d.blob_doubles * 8;
     VecView v = vec->view();
     int grid = c->sm_count * 8;
-    if (do_diag) {
-        ProfScope ps(c, "h_diag");
-        h_diag_kernel<<<grid, 256, smem, c->stream>>>(mol->view, v, vec->hf_en, src, dest, id_fac, h_fac);
-        c->launch_count++;
-    }
     HvScratch sc;
-    FRIES_TRY(sc.counts.alloc(n_parents));
-    FRIES_TRY(sc.offs.alloc(n_parents));
-    FRIES_TRY(sc.total.alloc(1));
-    {
-        ProfScope ps(c, "hv_count");
-        hv_count_kernel<<<grid, 256, smem, c->stream>>>(mol->view, v, src, n_parents, sc.counts.p);
-        c->launch_count++;
-    }
-    {
-        int sgrid = c->coop_grid((const void *)scan_counts_kernel, FR_COMP_BLOCK, 0);
-        const uint32_t *cp = sc.counts.p;
-        unsigned long long *op = sc.offs.p, *tp = sc.total.p;
-        double *pd = hb->part_d.p;
-        unsigned long long *pc = hb->part_c.p;
-        void *args[] = {(void *)&cp, (void *)&n_parents, (void *)&op, (void *)&tp, (void *)&pd, (void *)&pc};
-        ProfScope ps(c, "hv_scan");
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)scan_counts_kernel, dim3(sgrid), dim3(FR_COMP_BLOCK), args, 0,
-                                             c->stream));
-        c->launch_count++;
-    }
     unsigned long long total = 0;
-    CUDA_TRY(cudaMemcpyAsync(&total, sc.total.p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (n_parents > 0) {
+        if (do_diag) {
+            ProfScope ps(c, "h_diag");
+            h_diag_kernel<<<grid, 256, smem, c->stream>>>(mol->view, v, vec->hf_en, src, dest, id_fac, h_fac);
+            c->launch_count++;
+        }
+        FRIES_TRY(sc.counts.alloc(n_parents));
+        FRIES_TRY(sc.offs.alloc(n_parents));
+        FRIES_TRY(sc.total.alloc(1));
+        {
+            ProfScope ps(c, "hv_count");
+            hv_count_kernel<<<grid, 256, smem, c->stream>>>(mol->view, v, src, n_parents, sc.counts.p);
+            c->launch_count++;
+        }
+        {
+            int sgrid = c->coop_grid((const void *)scan_counts_kernel, FR_COMP_BLOCK, 0);
+            const uint32_t *cp = sc.counts.p;
+            unsigned long long *op = sc.offs.p, *tp = sc.total.p;
+            double *pd = hb->part_d.p;
+            unsigned long long *pc = hb->part_c.p;
+            void *args[] = {(void *)&cp, (void *)&n_parents, (void *)&op, (void *)&tp, (void *)&pd, (void *)&pc};
+            ProfScope ps(c, "hv_scan");
+            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)scan_counts_kernel, dim3(sgrid), dim3(FR_COMP_BLOCK), args, 0,
+                                                 c->stream));
+            c->launch_count++;
+        }
+        CUDA_TRY(cudaMemcpyAsync(&total, sc.total.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
     if (n_spawned) *n_spawned = total;
     HbSpawnArgs sp{nullptr, 0, 0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0, {nullptr}, 0};
     if (vec->n_ranks > 1) {
@@ -319,6 +324,13 @@ static int h_apply_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned 
         CUDA_TRY(cudaMemcpyAsync(&ov, hb->send_counts_ext + vec->n_ranks, 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         FRIES_REQUIRE(ov == 0, "h_apply: %llu connections did not fit a route segment", ov);
+        unsigned long long cerr = 0;  // set by a poll that timed out (comm.cuh): a peer died or left the protocol
+        CUDA_TRY(cudaMemcpyAsync(&cerr, fries_comm_view(hb->comm).error, 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (cerr) {
+            fries_set_error("h_apply: a cross-rank exchange timed out at epoch %llu (a peer left the protocol)", cerr);
+            return FRIES_ERR_STATE;
+        }
     } else
     for (unsigned long long lo = 0; lo < total; lo += hb->cap) {
         unsigned long long len = total - lo < hb->cap ? total - lo : hb->cap;
@@ -432,7 +444,8 @@ struct IterScalars {  // hb->scal layout (doubles)
     enum { R4 = 0, NUMER = 4, DENOM = 5, NEW_NORM = 6, STATS = 8, DENSE_NORM = 43 };
 };
 
-__global__ void iter_stats_kernel(const CompState *st, const VecCounters *cnt, const double *scal, double *out) {
+__global__ void iter_stats_kernel(const CompState *st, const VecCounters *cnt, const double *scal, double *out,
+                                  const unsigned long long *comm_err) {
     // out[0..]: glob_norm, numer, denom, n_kept, n_matrix_samples, curr_size, overflow flags, anomalies
     out[0] = st[6].glob_norm + scal[IterScalars::DENSE_NORM];  // frisys_mol.cpp:504: glob_norm += dense_norm()
     out[1] = scal[IterScalars::NUMER];
@@ -450,6 +463,7 @@ __global__ void iter_stats_kernel(const CompState *st, const VecCounters *cnt, c
     out[8] = (double)an;
     out[9] = (double)st[6].n_samp_left;
     out[10] = st[6].loc_norm;
+    out[11] = comm_err ? (double)*comm_err : 0.0;  // epoch of a cross-rank poll that timed out (comm.cuh)
 }
 
 __global__ void state_to_r4_kernel(const CompState *st, double *r4) {
@@ -526,7 +540,8 @@ static int dot_dev(fries_vec *vec, const uint64_t *tk, const double *tv, size_t 
 
 static int read_stats(fries_vec *vec, fries_hbpp *hb, fries_iter_stats *stats, const char *who) {
     fries_ctx *c = vec->ctx;
-    iter_stats_kernel<<<1, 1, 0, c->stream>>>(hb->st.p, vec->cnt.p, hb->scal.p, hb->scal.p + IterScalars::STATS);
+    iter_stats_kernel<<<1, 1, 0, c->stream>>>(hb->st.p, vec->cnt.p, hb->scal.p, hb->scal.p + IterScalars::STATS,
+                                              hb->comm ? fries_comm_view(hb->comm).error : nullptr);
     c->launch_count++;
     CUDA_TRY(cudaMemcpyAsync(c->h_pinned, hb->scal.p + IterScalars::STATS, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -539,6 +554,10 @@ static int read_stats(fries_vec *vec, fries_hbpp *hb, fries_iter_stats *stats, c
         stats->n_matrix_samples = (uint64_t)h[4];
         stats->n_spawned = (uint64_t)h[4];
         stats->curr_size = (uint64_t)h[5];
+    }
+    if (h[11] != 0) {
+        fries_set_error("%s: a cross-rank exchange timed out at epoch %g (a peer died or left the protocol)", who, h[11]);
+        return FRIES_ERR_STATE;
     }
     if (h[6] != 0) {
         fries_set_error("%s: insufficient memory allocated for matrix compression (%g samples dropped; raise spawn_cap)",

@@ -127,8 +127,10 @@ int main(int argc, char *argv[]) {
         }
         check(fries_frisys_mol_setup(sol_vec.h, mol.h, spawn_length, trial_dets.data(), trial_vals.data(), trial_dets.size(),
                                      htrial_dets.data(), htrial_vals.data(), htrial_dets.size(), &sol_vec.hb));
-        {   // frisys_mol.cpp:398-401: size of the pre-computed dense part of H = all connections of the dense determinants
-            size_t tot_dense_h = 0;
+        // frisys_mol.cpp:398-401: size of the pre-computed dense part of H = all connections of the dense determinants;
+        // the stochastic compression of H gets the rest of the budget (:421: matr_samp - tot_dense_h)
+        size_t tot_dense_h = 0;
+        {
             if (n_determ) {
                 std::vector<uint64_t> d;
                 std::vector<double> vv;
@@ -147,7 +149,12 @@ int main(int argc, char *argv[]) {
             // RNG consumption order of the reference: 5 uniforms inside apply_HBPP_sys, then one for sys_comp
             double u[6];
             for (int k = 0; k < 6; k++) u[k] = mt_obj() / (1. + UINT32_MAX);
-            fries_frisys_params p{eps, init_thresh, p_doub, new_hb, matr_samp, target_nonz, en_shift};
+            // the reference leaves `matr_samp - tot_dense_h` to unsigned wrap-around when the dense part alone exceeds the
+            // budget; here that is an error
+            if (tot_dense_h >= matr_samp)
+                throw std::runtime_error("the dense subspace's part of H (" + std::to_string(tot_dense_h) +
+                                         " elements) leaves nothing of --mat_nonz for the stochastic part");
+            fries_frisys_params p{eps, init_thresh, p_doub, new_hb, (uint32_t)(matr_samp - tot_dense_h), target_nonz, en_shift};
             fries_iter_stats st;
             check(fries_frisys_mol_iterate(sol_vec.h, mol.h, sol_vec.hb, &p, u, &st));
             nkept_file << st.n_kept << '\n';

@@ -26,11 +26,19 @@ def gather_bytes(dist, payload: bytes, world: int, device) -> list[bytes]:
     return [bytes(o.cpu().tolist()) for o in out]
 
 
+def bind_stream(ctx):
+    """One stream for the library's kernels and torch's own work (NCCL collectives, fills, copies): the context is bound to
+    torch's CURRENT stream.  A fries_ctx otherwise runs on a private non-blocking stream (csrc/ctx.cu), and an
+    all_to_all_single or a torch.zeros issued on torch's stream would not be ordered against the kernels around it."""
+    check(lib.fries_ctx_set_stream(ctx.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
 class Comm:
     """peer-mapped inboxes for the in-kernel cross-rank reductions (fries_comm)"""
 
     def __init__(self, ctx, dist, rank: int, world: int, device):
         self.ctx, self.rank, self.world = ctx, rank, world
+        bind_stream(ctx)
         h = C.c_void_p()
         handle = (C.c_uint8 * 64)()
         check(lib.fries_comm_create(ctx.h, world, rank, C.byref(h), handle))
@@ -69,6 +77,7 @@ def piv_comp_parallel(ctx, dist, rank: int, world: int, values_local, compress_s
     samples its own shard with local_draws.  Returns (values, delete flags, budget of this rank, norms before, one-norm
     after); plumbing only, the arithmetic is in libfries_b200.so."""
     from .api import piv_budget
+    bind_stream(ctx)  # the fills below run on torch's stream, the compression on the context's: make them one
     v = np.array(values_local, np.float64)  # a copy: the compression works in place
     d_vals = torch.tensor(v, device=device)
     d_keep = torch.zeros(max(v.size, 1), dtype=torch.uint8, device=device)

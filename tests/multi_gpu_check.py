@@ -201,6 +201,34 @@ def main():
               f"frifull_mol 4 iterations: stored={st.curr_size} spawned={st.n_spawned} energy={st.numer / st.denom:.6f}",
               flush=True)
     eng.close()
+    # ---- (3b) the same from ONE stored determinant: every rank but the owner starts empty, and must still take part in
+    # every collective of the routed H.v (round count, publish / wait / merge, barrier) -- frifull_mol's normal start ----
+    single = fries_b200.Vec(ctx, 1 << 21, sm.n_bits, sm.n_elec, 2, proc_scr, vec_scr)
+    single.set_diag_mol(mol, hf_en)
+    single.upload(hf, np.array([[1.0], [0.0]]))
+    n_single = single.h_apply(mol, 0, 1, 1.0, -0.01)
+    sk, sv = single.download()
+    single.close()
+    eng = MultiGpuFrisys(ctx, dist, rank, world, mol, sm, 1 << 21, 1 << 16, 60000, proc_scr, vec_scr, hf_en,
+                         (hf, np.ones(1)), (hk, hv[1]), route="p2p")
+    _, own = fries_b200.hash_owner(ctx, hf, proc_scr, world)
+    eng.load(hf, np.ones(1), own)
+    n_loc = eng.h_apply(0, 1, 1.0, -0.01)
+    n_all = torch.tensor([n_loc], device=dev)
+    dist.all_reduce(n_all)
+    assert int(n_all.item()) == n_single, (int(n_all.item()), n_single)
+    lk, lv = eng.vec.download()
+    ref = dict(zip(sk.tolist(), sv[1].tolist()))
+    mine = np.array([ref[k] for k in lk.tolist()])
+    assert np.allclose(lv[1], mine, rtol=1e-12, atol=1e-13)
+    n_glob = torch.tensor([lk.size], device=dev)
+    dist.all_reduce(n_glob)
+    assert int(n_glob.item()) == sk.size, (int(n_glob.item()), sk.size)
+    assert eng.comm.error_epoch() == 0
+    if rank == 0:
+        print(f"[multi] {world} ranks: routed H.v from one stored determinant == single-GPU H.v ({n_single} connections)",
+              flush=True)
+    eng.close()
     mol.close()
     dist.barrier()
     dist.destroy_process_group()
