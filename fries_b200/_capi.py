@@ -98,6 +98,7 @@ def _load():
         "fries_debug_last_fast": (i, [P(i)]),
         "fries_debug_stage_ctas": (i, [P(i)]),
         "fries_debug_stage_engine": (i, [P(i)]),
+        "fries_debug_vec_phase": (i, [vp, vp, vp, u, d, vp]),
         "fries_comm_create": (i, [vp, i, i, P(vp), vp]),
         "fries_comm_connect": (i, [vp, vp]),
         "fries_comm_destroy": (i, [vp]),

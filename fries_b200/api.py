@@ -424,6 +424,13 @@ class Vec:
         check(lib.fries_hbpp_states(self.hb, ptr(out)))
         return out
 
+    def debug_vec_phase(self, target_nonz, uniform):
+        """diagnostics / parity: find_preserve -> sys_comp -> deletion + compaction of the fused vector kernel
+        (csrc/vecphase.cu) on the stored vector -> (loc_norm, glob_norm, n_samp_left, n_kept); needs frisys_setup"""
+        out = np.zeros(4)
+        check(lib.fries_debug_vec_phase(self.h, self.mol.h, self.hb, int(target_nonz), float(uniform), ptr(out)))
+        return float(out[0]), float(out[1]), int(out[2]), int(out[3])
+
     def timeline(self, s):
         """clock64 timeline (SM cycles from mark 0) of thread 0 of CTA 0 through the last compression of state s"""
         out = np.zeros(48)

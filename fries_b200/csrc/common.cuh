@@ -387,4 +387,18 @@ struct SysGrid {
         while (k < n && fma((double)k, unit, rn0) < x) k++;
         return k;
     }
+    // The same two with the index kept as a double (exact below 2^53): no 64-bit integer <-> double conversions, which are
+    // multi-instruction sequences on the device and sat in every input's path of the count / emit passes.
+    __device__ __forceinline__ double point_d(double k) const { return k < (double)n ? fma(k, unit, rn0) : INFINITY; }
+    __device__ __forceinline__ double count_below_d(double x) const {
+        const double nd = (double)n;
+        if (n <= 0 || !(x > rn0)) return 0.0;
+        double q = (x - rn0) * inv;
+        double k = q >= nd ? nd : ceil(q);
+        if (k < 0) k = 0;
+        if (k > nd) k = nd;
+        while (k > 0 && !(fma(k - 1.0, unit, rn0) < x)) k -= 1.0;
+        while (k < nd && fma(k, unit, rn0) < x) k += 1.0;
+        return k;
+    }
 };

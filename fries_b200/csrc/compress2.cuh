@@ -26,11 +26,14 @@
 #define FR2_NW (FR2_NT / 32)
 
 #define FR2_CAND_STAGE 1024  // candidates a CTA stages in shared memory before it reserves their place in the global list
-struct Comp2Shared {
+struct StageShared {
     double cx[FR2_CAND_STAGE];             // staged candidates: magnitude, multiplicity, input index
     uint32_t cm[FR2_CAND_STAGE], ci[FR2_CAND_STAGE];
     unsigned n_stage;                      // staged so far (may run past the capacity: the excess went to the global list directly)
     unsigned long long stage_base;
+};
+struct Comp2Shared {
+    StageShared stg;
     double wsum[2][FR2_NW + 1];            // warp partials of the block scans / sums (double buffered)
     unsigned long long wcnt[2][FR2_NW + 1];
     double start[FR2_TILE];                // line position of every input of the current tile
@@ -329,7 +332,7 @@ __device__ __forceinline__ BracketResult bracket_solve2(cg::grid_group &grid, co
 // volatile read of it -- ~2500 same-address L2 operations per stage, which an L2 slice serves one at a time (~23 cycles
 // each, measured round 2): the appends of a stage queued for tens of microseconds and produced the long tail of pass A.
 // Now a candidate costs a shared-memory atomic; after the pass the CTA reserves its range with one global atomicAdd.
-__device__ __forceinline__ void cand_stage(Comp2Shared &sm, const CandList2 &cl, const CommView &cm, double x, uint32_t mult,
+__device__ __forceinline__ void cand_stage(StageShared &sm, const CandList2 &cl, const CommView &cm, double x, uint32_t mult,
                                            uint32_t i) {
     const unsigned k = atomicAdd(&sm.n_stage, 1u);
     if (k < FR2_CAND_STAGE) {
@@ -341,7 +344,7 @@ __device__ __forceinline__ void cand_stage(Comp2Shared &sm, const CandList2 &cl,
     }
 }
 // after the pass: every thread of the CTA calls this
-__device__ __forceinline__ void cand_stage_flush(Comp2Shared &sm, const CandList2 &cl, const CommView &cm) {
+__device__ __forceinline__ void cand_stage_flush(StageShared &sm, const CandList2 &cl, const CommView &cm) {
     __syncthreads();
     const unsigned ns = sm.n_stage < FR2_CAND_STAGE ? sm.n_stage : FR2_CAND_STAGE;
     if (threadIdx.x == 0) sm.stage_base = ns ? atomicAdd(cl.base.count, (unsigned long long)ns) : 0ull;
@@ -457,7 +460,7 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
         sm.bc[1] = b.pred ? (unsigned long long)__double_as_longlong(__ldcg(&b.pred->t)) : 0ull;
         sm.bc[2] = b.pred ? (unsigned long long)__double_as_longlong(__ldcg(&b.pred->h)) : 0ull;
         sm.bc[3] = (unsigned long long)grid_comb_begin(gcb).epoch;
-        sm.n_stage = 0;
+        sm.stg.n_stage = 0;
     }
     __syncthreads();
     const size_t n = (size_t)sm.bc[0];
@@ -492,13 +495,26 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
     bool appended = false;
     unsigned long long n_app = 0;
     for (size_t base = lo; base < hi; base += FR2_TILE) {
-#pragma unroll 1
+        // the thread's inputs of this tile, fetched level by level (independent loads in flight) before any row is generated
+        typename P::Pre pre[FR2_ITEMS];
+#pragma unroll
         for (int k = 0; k < FR2_ITEMS; k++) {
             const size_t i = base + (size_t)k * FR2_NT + tid;  // striped: this pass has no scan, the accesses coalesce
+            if (i < hi) prov.fetch1(i, pre[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < FR2_ITEMS; k++)
+            if (base + (size_t)k * FR2_NT + tid < hi) prov.fetch2(pre[k]);
+#pragma unroll
+        for (int k = 0; k < FR2_ITEMS; k++)
+            if (base + (size_t)k * FR2_NT + tid < hi) prov.fetch3(pre[k]);
+#pragma unroll 1
+        for (int k = 0; k < FR2_ITEMS; k++) {
+            const size_t i = base + (size_t)k * FR2_NT + tid;
             if (i >= hi) break;
             double v, rinv = 1.0, wmax = 1.0;
             uint32_t nd, ns;
-            prov.prep(i, v, nd, ns, rinv, wmax);
+            prov.prep_core(i, pre[k], v, nd, ns, rinv, wmax);
             b.rinv[i] = rinv;
             b.veff[i] = v;
             b.ndiv[i] = nd;
@@ -515,7 +531,7 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
                         kb = 1;
                         wr = 0;
                     } else {
-                        cand_stage(sm, cand, cm, xmax, nd, (uint32_t)i);
+                        cand_stage(sm.stg, cand, cm, xmax, nd, (uint32_t)i);
                         appended = true;
                         n_app++;
                     }
@@ -531,7 +547,7 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
                             } else {
                                 sub_remain += x;
                                 if (x >= t_lo) {
-                                    cand_stage(sm, cand, cm, x, 1u, (uint32_t)i);
+                                    cand_stage(sm.stg, cand, cm, x, 1u, (uint32_t)i);
                                     appended = true;
                                     n_app++;
                                 }
@@ -546,7 +562,7 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
         }
     }
     FR_TL(b.st, 1);  // pass A loop done (this thread)
-    if (try_fast) cand_stage_flush(sm, cand, cm);
+    if (try_fast) cand_stage_flush(sm.stg, cand, cm);
     cand_flush(cm, try_fast);
     double pre_d;
     unsigned long long pre_c;
@@ -644,9 +660,9 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
             // the inputs with a piece inside the bracket: this CTA's staged candidates (an input listed twice is rewritten
             // with the same result); if the staging area overflowed, the CTA's share of the global list as well
             unsigned long long kc_dummy = 0;
-            const unsigned nst = sm.n_stage < FR2_CAND_STAGE ? sm.n_stage : FR2_CAND_STAGE;
-            for (unsigned e = tid; e < nst; e += FR2_NT) fr2_apply_cut(prov, b, (size_t)sm.ci[e], br.x_cut, kc_dummy);
-            if (sm.n_stage > FR2_CAND_STAGE) {
+            const unsigned nst = sm.stg.n_stage < FR2_CAND_STAGE ? sm.stg.n_stage : FR2_CAND_STAGE;
+            for (unsigned e = tid; e < nst; e += FR2_NT) fr2_apply_cut(prov, b, (size_t)sm.stg.ci[e], br.x_cut, kc_dummy);
+            if (sm.stg.n_stage > FR2_CAND_STAGE) {
                 for (unsigned long long k = tid; k < my_cand; k += FR2_NT) {
                     const size_t i = (size_t)__ldcg(&b2.cand_idx[k]);
                     if (i >= lo && i < hi) fr2_apply_cut(prov, b, i, br.x_cut, kc_dummy);
@@ -853,11 +869,11 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
                         if (w4[k] == 0) {  // preserved (a uniform input with v != 0 has a residual unless it is preserved)
                             kk = nd4[k];
                         } else {
-                            long long k0 = sg.count_below(start), k1 = sg.count_below(lbound);
-                            kk = (uint32_t)(k1 > k0 ? k1 - k0 : 0);
+                            const double k0 = sg.count_below_d(start), k1 = sg.count_below_d(lbound);
+                            kk = (uint32_t)(k1 > k0 ? k1 - k0 : 0.0);
                         }
                     } else {
-                        const double g = sg.point(sg.count_below(start));
+                        const double g = sg.point_d(sg.count_below_d(start));
                         row = w4[k] < v4[k] || g < lbound;
                     }
                 }
@@ -885,8 +901,8 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
             const double v = b.veff[i], wr = b.wt_remain[i], start = sm.start[slot];
             const double lbound = start + wr;
             const uint32_t ns = b.nsub[i], kb = b.keep[i];
-            long long k0 = sg.count_below(start);
-            double g = sg.point(k0);
+            double k0 = sg.count_below_d(start);
+            double g = sg.point_d(k0);
             double sub_lb = lbound - wr;
             uint32_t k = 0, n_kept_out = 0, s1 = 0, s2 = 0;
             prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) -> bool {
@@ -900,8 +916,8 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
                         if (k == 0) s1 = j;
                         if (k == 1) s2 = j;
                         k++;
-                        k0++;
-                        g = sg.point(k0);
+                        k0 += 1.0;
+                        g = sg.point_d(k0);
                         if (g < sub_lb) anomalies++;
                     }
                 }
@@ -994,9 +1010,9 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
                     const double each = v / nd;
                     for (uint32_t j = 0; j < nd; j++) FR2_EMIT(each, j);
                 } else {
-                    long long k0 = sg.count_below(start);
+                    const double k0 = sg.count_below_d(start);
                     for (uint32_t t = 0; t < k; t++) {
-                        double g = sg.point(k0 + t);
+                        double g = sg.point_d(k0 + (double)t);
                         unsigned long long sub = (unsigned long long)((lbound - g) * nd / v);
                         if (sub >= nd) {
                             sub = nd - 1;
@@ -1007,8 +1023,8 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
                 }
             } else {
                 const uint32_t ns = b.nsub[i], kb = b.keep[i];
-                long long k0 = sg.count_below(start);
-                double g = sg.point(k0);
+                double k0 = sg.count_below_d(start);
+                double g = sg.point_d(k0);
                 double sub_lb = lbound - wr;
                 const unsigned long long o_end = o + k;
                 prov.visit(i, b.rinv[i], [&](uint32_t j, double wj) -> bool {
@@ -1019,8 +1035,8 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
                         sub_lb += v * wj;
                         if (g < sub_lb && wj != 0) {
                             FR2_EMIT(samp_val, j);
-                            k0++;
-                            g = sg.point(k0);
+                            k0 += 1.0;
+                            g = sg.point_d(k0);
                         }
                     }
                     return o < o_end;

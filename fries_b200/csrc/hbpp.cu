@@ -29,13 +29,18 @@ hbpp_stage2_kernel(MolView gm, HbStageIO io, CompSubBufs2 bufs, unsigned n_samp,
     prov.io = io;
     comp_sub_engine2(prov, bufs, n_samp, rn);
 }
-// FRIES_STAGE2_CTAS=2: two CTAs per SM (<= 64 registers) -- measurement variant of the second-generation kernels
-static int stage2_ctas() {
-    static int v = [] {
+// CTAs per SM of the second-generation kernels.  One (128 registers, no spills) when an SM holds a few thousand inputs:
+// the stage is a chain of short phases and extra warps add skeleton work.  Two (64 registers, ~1 kB of spill traffic per
+// thread, twice the warps) when the scratch was sized for millions of samples: the row loops are then bound by
+// per-warp latency chains and the second CTA hides them (measured round 2 at 1.25e7 samples: 9.8 -> 7.4 ms for the five
+// stages; at 2.6e5: 0.49 -> 0.51 ms).  FRIES_STAGE2_CTAS=1|2 in the environment overrides the choice.
+static int stage2_ctas(size_t cap) {
+    static int forced = [] {
         const char *e = getenv("FRIES_STAGE2_CTAS");
-        return (e && e[0] == '2' && e[1] == 0) ? 2 : 1;
+        return (e && (e[0] == '1' || e[0] == '2') && e[1] == 0) ? e[0] - '0' : 0;
     }();
-    return v;
+    if (forced) return forced;
+    return cap >= (size_t)4000000 ? 2 : 1;
 }
 static int stage_engine() {
     static int v = [] {
@@ -245,7 +250,7 @@ static int launch_stage(fries_hbpp *hb, fries_mol *mol, HbStageIO &io, CompSubBu
     static const char *names[] = {"hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4"};
     ProfScope ps(c, names[S]);
     if (stage_engine() == 2) {
-        const int ctas = stage2_ctas();
+        const int ctas = stage2_ctas(hb->cap);
         const void *kern = ctas == 2 ? (const void *)hbpp_stage2_kernel<S, 2> : (const void *)hbpp_stage2_kernel<S, 1>;
         static bool attr_set[2] = {false, false};  // per instantiation <S, ctas>: opt in to more than 48 kB of shared memory
         if (!attr_set[ctas - 1]) {

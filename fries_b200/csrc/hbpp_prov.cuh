@@ -74,12 +74,48 @@ struct HbProvider {
 
     // wmax: an upper bound of the sub-weights visit() will stream for this input (exactly the largest one where the
     // row is traversed here anyway); the engine skips the row of an input whose v * wmax is below the threshold bracket
+    // The inputs of prep(): three levels of dependent global loads (output list -> path state of the parent item -> parent
+    // determinant).  The second-generation engine fetches them level by level for all the inputs of a thread before it
+    // calls prep_core (compress2.cuh), so that a thread pays three load latencies per tile instead of three per input.
+    struct Pre {
+        double v;
+        uint32_t widx, sub, d, pp;
+        uint64_t key;
+    };
+    __host__ __device__ __forceinline__ void fetch1(size_t i, Pre &p) const {
+        if (S == 0) {
+            p.v = io.vals[i];
+            p.widx = p.sub = p.d = p.pp = 0;
+            p.key = 0;
+        } else {
+            p.widx = io.pw[i];
+            p.sub = io.ps[i];
+            p.v = io.pv[i];
+        }
+    }
+    __host__ __device__ __forceinline__ void fetch2(Pre &p) const {
+        if (S != 0) {
+            p.d = io.pdet[p.widx];
+            p.pp = io.ppath[p.widx];
+        }
+    }
+    __host__ __device__ __forceinline__ void fetch3(Pre &p) const {
+        if (S != 0) p.key = io.keys[p.d];
+    }
     __host__ __device__ void prep(size_t i, double &v, uint32_t &nd, uint32_t &ns, double &rinv, double &wmax) const {
+        Pre p;
+        fetch1(i, p);
+        fetch2(p);
+        fetch3(p);
+        prep_core(i, p, v, nd, ns, rinv, wmax);
+    }
+    __host__ __device__ void prep_core(size_t i, const Pre &pre, double &v, uint32_t &nd, uint32_t &ns, double &rinv,
+                                       double &wmax) const {
         const unsigned ne = m.d.n_elec, M = m.d.n_orb;
         rinv = 1.0;
         wmax = 1.0;
         if (S == 0) {  // singles vs doubles :713-727
-            double w = fabs(io.vals[i]);
+            double w = fabs(pre.v);
             wmax = fmax(io.p_doub, 1 - io.p_doub);
             v = w;
             nd = w > 0 ? 0u : 1u;
@@ -88,11 +124,11 @@ struct HbProvider {
             io.path[i] = 0;
             return;
         }
-        const uint32_t widx = io.pw[i], sub = io.ps[i];
-        const uint32_t d = io.pdet[widx], pp = io.ppath[widx];
-        v = io.pv[i];
+        const uint32_t sub = pre.sub;
+        const uint32_t d = pre.d, pp = pre.pp;
+        v = pre.v;
         io.det[i] = d;
-        const uint64_t key = io.keys[d];
+        const uint64_t key = pre.key;
         unsigned p0 = pp & 0xff, p1 = (pp >> 8) & 0xff, p2 = (pp >> 16) & 0xff, p3 = pp >> 24;
         if (S == 1) {  // first occupied orbital :738-763
             p0 = sub;

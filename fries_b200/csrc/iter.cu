@@ -7,6 +7,8 @@
 extern __shared__ double fr_dyn_smem[];
 
 int fries_vec_compact_flags_dev(fries_vec *vec, const uint8_t *d_flags);
+int fries_vec_phase_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, double eps, double shift, unsigned target_nonz,
+                        double uniform, bool do_death);  // vecphase.cu
 
 #define FR_NAN __longlong_as_double(0x7ff8000000000000ll)
 
@@ -594,6 +596,16 @@ extern "C" int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hb
         // -eps * <D'|H|D> * v_D with the values from before the spawn (row 0 is untouched so far), into row 1
         FRIES_TRY(h_apply_dev(vec, mol, hb, 0, 1, 0.0, -p->eps, false, nullptr, nd));
         v = vec->view();
+    }
+    // steps 7, 8, 10, 11 as one cooperative launch (vecphase.cu); FRIES_FUSED_VEC=0 in the environment keeps the seven
+    // separate launches below (regression / measurement variant, same arithmetic)
+    static const bool fused = [] {
+        const char *e = getenv("FRIES_FUSED_VEC");
+        return !(e && e[0] == '0' && e[1] == 0);
+    }();
+    if (fused && vec->n_vecs == 2 && vec->hh_sites == 0) {
+        FRIES_TRY(fries_vec_phase_dev(vec, mol, hb, p->eps, p->en_shift, p->target_nonz, u6[5], true));
+        return read_stats(vec, hb, stats, "fries_frisys_mol_iterate");
     }
     // step 7: death/cloning, add_vecs(0, 1), zero row 1
     {

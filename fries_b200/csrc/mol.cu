@@ -64,6 +64,12 @@ __global__ void hb_setup_rest_kernel(MolView m, const double *d_diff, const doub
     }
 }
 
+// square copies of exch_sqrt / d_same for the row generators (mol.cuh)
+__global__ void hb_square_kernel(MolDims d, double *blob) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x, M = d.n_orb;
+    if (t < M * M) mol_square_entry(d, blob, t / M, t % M);
+}
+
 extern "C" int fries_mol_create(fries_ctx *c, unsigned n_orb, unsigned n_elec_total, unsigned n_frz,
                                 const double *h_hcore, const double *h_eris_packed, const uint8_t *h_symm,
                                 fries_mol **out) {
@@ -87,18 +93,7 @@ extern "C" int fries_mol_create(fries_ctx *c, unsigned n_orb, unsigned n_elec_to
     d.n_elec = ne;
     d.n_frz = n_frz;
     d.tot_orb = T;
-    unsigned off = 0;
-    d.off_d_diff = off; off += M * M;
-    d.off_d_same = off; off += TT;
-    d.off_s_tens = off; off += M;
-    d.off_exch_sqrt = off; off += TT;
-    d.off_diag_sqrt = off; off += M;
-    d.off_exch_norms = off; off += M;
-    d.off_symm = off; off += (M + 7) / 8;
-    d.off_lookup = off; off += (FR_N_IRREPS * (M + 1) + 7) / 8;
-    d.off_irr = off; off += (FR_N_IRREPS * 4 + 7) / 8;
-    off = (off + 1) & ~1u;  // a multiple of 16 bytes: the stage kernels fetch the blob with one cp.async.bulk (molhost.cuh)
-    d.blob_doubles = off;
+    const unsigned off = mol_blob_layout(d);
     // symmetry tables (integer bookkeeping; gen_symm_lookup molecule.cpp:1050-1065, SymmInfo molecule.hpp:265-280)
     std::vector<double> h_blob(off, 0.0);
     uint8_t *symm = (uint8_t *)(h_blob.data() + d.off_symm);
@@ -138,7 +133,8 @@ extern "C" int fries_mol_create(fries_ctx *c, unsigned n_orb, unsigned n_elec_to
         hb_setup_rest_kernel<<<1, 1024, 0, c->stream>>>(mol->view, b + d.off_d_diff, b + d.off_d_same, b + d.off_s_tens,
                                                         b + d.off_exch_sqrt, b + d.off_diag_sqrt, b + d.off_exch_norms,
                                                         b + off);
-        c->launch_count += 2;
+        hb_square_kernel<<<(M * M + 127) / 128, 128, 0, c->stream>>>(d, b);
+        c->launch_count += 3;
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(&d.s_norm, b + off, 8, cudaMemcpyDeviceToHost, c->stream));

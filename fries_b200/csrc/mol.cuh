@@ -26,6 +26,7 @@ struct MolDims {
     uint32_t blob_doubles;  // size of the small-table blob in doubles (incl. the byte tables)
     uint32_t off_d_diff, off_d_same, off_s_tens, off_exch_sqrt, off_diag_sqrt, off_exch_norms, off_symm, off_lookup;
     uint32_t off_irr;   // [8] u32: spatial orbitals of each irrep as a bit mask
+    uint32_t off_xfull, off_dsfull;  // [M][M] square forms of exch_sqrt (diag_sqrt on the diagonal) and d_same (0 on it)
     double s_norm;
 };
 
@@ -37,6 +38,9 @@ struct MolView {
     const uint8_t *symm;    // [M] irreps
     const uint8_t *lookup;  // [8][M + 1] gen_symm_lookup molecule.cpp:1050-1065
     const uint32_t *irr_mask;  // [8] spatial orbitals of each irrep as a bit mask
+    // square, symmetric copies for the row generators: one load at [a * M + b] instead of an ordered triangular index (the
+    // index arithmetic was a third of a row entry's instructions); same values, so the rows are bit-identical
+    const double *xfull, *dsfull;
 };
 
 __host__ __device__ __forceinline__ void mol_bind_blob(MolView &m, const double *blob) {
@@ -49,6 +53,36 @@ __host__ __device__ __forceinline__ void mol_bind_blob(MolView &m, const double 
     m.symm = (const uint8_t *)(blob + m.d.off_symm);
     m.lookup = (const uint8_t *)(blob + m.d.off_lookup);
     m.irr_mask = (const uint32_t *)(blob + m.d.off_irr);
+    m.xfull = blob + m.d.off_xfull;
+    m.dsfull = blob + m.d.off_dsfull;
+}
+
+// offsets of the small tables inside the blob (one definition for fries_mol_create and the CPU test tier); returns the
+// blob's size in doubles, a multiple of 2 (16 bytes: the stage kernels fetch it with one cp.async.bulk, molhost.cuh)
+inline unsigned mol_blob_layout(MolDims &d) {
+    const unsigned M = d.n_orb, TT = M * (M - 1) / 2;
+    unsigned off = 0;
+    d.off_d_diff = off; off += M * M;
+    d.off_d_same = off; off += TT;
+    d.off_s_tens = off; off += M;
+    d.off_exch_sqrt = off; off += TT;
+    d.off_diag_sqrt = off; off += M;
+    d.off_exch_norms = off; off += M;
+    d.off_symm = off; off += (M + 7) / 8;
+    d.off_lookup = off; off += (FR_N_IRREPS * (M + 1) + 7) / 8;
+    d.off_irr = off; off += (FR_N_IRREPS * 4 + 7) / 8;
+    d.off_xfull = off; off += M * M;
+    d.off_dsfull = off; off += M * M;
+    off = (off + 1) & ~1u;
+    d.blob_doubles = off;
+    return off;
+}
+// entry (i, j) of the square forms from the triangular tables
+__host__ __device__ __forceinline__ void mol_square_entry(const MolDims &d, double *blob, unsigned i, unsigned j) {
+    const unsigned M = d.n_orb;
+    const unsigned lo = i < j ? i : j, hi = i < j ? j : i;
+    blob[d.off_xfull + i * M + j] = i == j ? blob[d.off_diag_sqrt + i] : blob[d.off_exch_sqrt + FR_TRI_NODIAG(lo, hi)];
+    blob[d.off_dsfull + i * M + j] = i == j ? 0.0 : blob[d.off_d_same + FR_TRI_NODIAG(lo, hi)];
 }
 
 __host__ __device__ __forceinline__ uint8_t mol_lookup(const MolView &m, unsigned irrep, unsigned col) {
@@ -435,11 +469,11 @@ __host__ __device__ __forceinline__ void hbs_o2_half(const MolView &m, uint64_t 
         if (j < h) {
             const unsigned q = (unsigned)fr_ctz(am);
             am &= am - 1;
-            return o1 < M ? m.d_same[FR_TRI_NODIAG(q, o1)] : m.d_diff[(o1 - M) * M + q];
+            return o1 < M ? m.dsfull[o1 * M + q] : m.d_diff[(o1 - M) * M + q];
         }
         const unsigned q = (unsigned)fr_ctz(bm);
         bm &= bm - 1;
-        return o1 < M ? m.d_diff[o1 * M + q] : m.d_same[FR_TRI_NODIAG(q, o1 - M)];
+        return o1 < M ? m.d_diff[o1 * M + q] : m.dsfull[(o1 - M) * M + q];
     }, f);
 }
 // calc_o2_probs :203-233: ne entries in index order (entry o1_idx is 0)
@@ -482,13 +516,11 @@ __host__ __device__ __forceinline__ void hbs_u1(const MolView &m, uint64_t key, 
     fr_row_chunked((unsigned)fr_popc((uint64_t)vm), [&](unsigned) {
         const unsigned k = (unsigned)fr_ctz(vm);
         vm &= vm - 1;
-        return m.exch_sqrt[k < o1s ? FR_TRI_NODIAG(k, o1s) : FR_TRI_NODIAG(o1s, k)];
+        return m.xfull[o1s * M + k];
     }, f);
 }
 __host__ __device__ __forceinline__ double hbs_u2_weight(const MolView &m, unsigned o2s, unsigned u2) {
-    if (o2s == u2) return m.diag_sqrt[o2s];
-    unsigned mn = o2s < u2 ? o2s : u2, mx = o2s > u2 ? o2s : u2;
-    return m.exch_sqrt[FR_TRI_NODIAG(mn, mx)];
+    return m.xfull[o2s * m.d.n_orb + u2];  // diag_sqrt on the diagonal, exch_sqrt off it
 }
 // calc_u2_probs :322-365: one entry per orbital of the irrep that completes the double (0 for u2 == u1, same spin)
 template <class F>

@@ -377,6 +377,11 @@ int fries_debug_stage_ctas(int *ctas_per_sm);
 /* generation of the compression engine the HB-PP stage kernels run (2 = csrc/compress2.cuh, the default; 1 with
  * FRIES_ENGINE=1 in the environment: the first-generation kernels, kept as a regression / measurement variant) */
 int fries_debug_stage_engine(int *generation);
+/* diagnostics / parity: the compression half of the fused vector kernel (csrc/vecphase.cu: find_preserve
+ * compress_utils.cpp:29-105 -> sys_comp :278-327 -> del_at_pos vec_utils.hpp:458-476 + compaction) on the stored vector,
+ * row 0; hb = the scratch of fries_frisys_mol_setup; h_state4: loc_norm, glob_norm, n_samp_left, n_kept */
+int fries_debug_vec_phase(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned target_nonz, double uniform,
+                          double *h_state4);
 /* diagnostics: clock64 timeline (SM cycles) of thread 0 of CTA 0 through the last compression of state s (0-4: HB-PP stages) */
 int fries_hbpp_timeline(fries_hbpp *hb, int s, double *h_out48);
 /* diagnostics (FRIES_CTA_MARKS=1 in the environment): per-CTA phase-end times of stage s, h_out[8][*grid] in ns */

@@ -27,17 +27,7 @@ void *hc_mol_create(unsigned n_orb, unsigned n_elec_total, unsigned n_frz, const
     unsigned M = n_orb, T = n_orb + n_frz / 2, TT = M * (M - 1) / 2;
     MolDims &d = h->v.d;
     d.n_orb = M; d.n_elec = n_elec_total - n_frz; d.n_frz = n_frz; d.tot_orb = T; d.s_norm = s_norm;
-    unsigned off = 0;
-    d.off_d_diff = off; off += M * M;
-    d.off_d_same = off; off += TT;
-    d.off_s_tens = off; off += M;
-    d.off_exch_sqrt = off; off += TT;
-    d.off_diag_sqrt = off; off += M;
-    d.off_exch_norms = off; off += M;
-    d.off_symm = off; off += (M + 7) / 8;
-    d.off_lookup = off; off += (FR_N_IRREPS * (M + 1) + 7) / 8;
-    d.off_irr = off; off += (FR_N_IRREPS * 4 + 7) / 8;
-    d.blob_doubles = off;
+    const unsigned off = mol_blob_layout(d);
     h->blob.assign(off, 0.0);
     {
         uint32_t *irr = (uint32_t *)&h->blob[d.off_irr];  // as fries_mol_create (mol.cu)
@@ -49,6 +39,8 @@ void *hc_mol_create(unsigned n_orb, unsigned n_elec_total, unsigned n_frz, const
     memcpy(&h->blob[d.off_exch_sqrt], exch_sqrt, TT * 8);
     memcpy(&h->blob[d.off_diag_sqrt], diag_sqrt, M * 8);
     memcpy(&h->blob[d.off_exch_norms], exch_norms, M * 8);
+    for (unsigned i = 0; i < M; i++)
+        for (unsigned j = 0; j < M; j++) mol_square_entry(d, h->blob.data(), i, j);
     uint8_t *sy = (uint8_t *)&h->blob[d.off_symm], *lk = (uint8_t *)&h->blob[d.off_lookup];
     memcpy(sy, symm, M);
     d.max_n_symm = 0;
