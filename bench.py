@@ -50,11 +50,10 @@ START_PARENTS = (1, 1000, 1500)  # parents kept before each H application (x vec
 
 def start_parents(cfg):
     return START_PARENTS[:2] + (max(START_PARENTS[2], START_PARENTS[2] * cfg["vec_nonz"] // 242000),)
-B_PER_VEC_EL = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the Ne-sized bench, from ONE `ncu --set full` capture
-# (profiles/r01c_ncu_full_hbpp_stage_raw.csv); not measured live
-NCU_TRAFFIC_NE = {"hbpp_stage0": 4.18e6, "hbpp_stage1": 11.92e6, "hbpp_stage2": 12.93e6, "hbpp_stage3": 10.24e6,
-                  "hbpp_stage4": 9.89e6}
+# per stored vector element; vec_phase = the four fused (death/cloning, find_preserve, sys_comp, delete + compact)
+B_PER_VEC_EL = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8, "vec_phase": 80}
+# roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel) cannot be measured inside this
+# program: it is null here and lives in the ncu summaries under profiles/ (named per round), captured from this command
 
 
 def mt_uniforms(seed, n):
@@ -285,7 +284,7 @@ def run_ours(args, cfg):
     ctx.set_profile(0)
     states = vec.states()
     names = ["hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4", "hbpp_finalize", "merge_insert",
-             "merge_accum", "death_axpy", "find_preserve", "sys_comp", "compact"]
+             "merge_accum", "vec_phase", "death_axpy", "find_preserve", "sys_comp", "compact"]
     kern = {}
     for nm in names:
         t, n = ctx.kernel_ms(nm)
@@ -309,8 +308,11 @@ def run_ours(args, cfg):
     roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5),
                 "peak_nominal": 8000.0, "frac_nominal": round(achieved / 8000.0, 5),  # report against both
-                "traffic": NCU_TRAFFIC_NE.get(top) if cfg["system"] == "ne" else None,
-                "traffic_source": "profiles/r01c_ncu_full_hbpp_stage_raw.csv (bytes per launch)",
+                "traffic": None,
+                "traffic_source": "not measurable in-process; ncu captures of this command: profiles/r02_*",
+                "kernel_table": {k: {"ms": round(kern[k], 4), "algorithmic_MB": round(units[k] / 1e6, 2),
+                                     "GBps": round(units[k] / (kern[k] * 1e-3) / 1e9, 1),
+                                     "frac": round(units[k] / (kern[k] * 1e-3) / 1e9 / peak, 4)} for k in kern if k in units},
                 "algorithmic_bytes_per_launch": units[top],
                 "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback B200_PROFILING.md",
                 "ms_per_launch": round(kern[top], 4),
@@ -347,11 +349,11 @@ def run_ours(args, cfg):
 
     out = {
         "metric": "fri_iterations_per_sec", "value": round(value, 3), "unit": "iter/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["workload"], "vec_nonz": cfg["vec_nonz"], "mat_nonz": cfg["mat_nonz"],
                    "l2": ("NOT flushed (diagnostic run, FRIES_BENCH_NOFLUSH)" if os.environ.get("FRIES_BENCH_NOFLUSH") else "flushed between iterations (512 MB write)"), "stored_dets": int(n_vec),
-                   "stage_ctas_per_sm": 1 if os.environ.get("FRIES_STAGE_CTAS") == "1" else 2},
+                   "engine": "compress2 + vecphase" if not os.environ.get("FRIES_ENGINE") else "round-1 kernels (FRIES_ENGINE=1)"},
         "spawned_elements_per_sec": round(spawned / (ms * 1e-3), 1),
         "matrix_samples_per_sec": round(samples / (ms * 1e-3), 1),
         "gpu_launches": int(launches), "clocks": clk,
@@ -538,41 +540,28 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # the start vector is produced by our own preparation code when a GPU is present, else by the oracle
-    from fries_b200.synth import SynthMol
-    if args.gpus > 1:  # the same weak-scaled workload as our arm at N GPUs (fries_b200/multi.py: run_multi_gpu_bench)
-        cfg = dict(cfg, vec_nonz=cfg["vec_nonz"] * args.gpus, mat_nonz=cfg["mat_nonz"] * args.gpus,
-                   target=cfg["target"] * args.gpus, max_dets=cfg["max_dets"] * args.gpus,
-                   workload=cfg["workload"] + f" x{args.gpus} (weak scaling: vec_nonz, mat_nonz, target x n_gpus)")
-    base_cfg = CONFIGS[args.config]
+    # the synthetic-integral generator is plain numpy: load the module by path, NOT through the fries_b200 package (whose
+    # __init__ loads libfries_b200.so) -- nothing of the product runs in this arm
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fries_synth_standalone", os.path.join(ROOT, "fries_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synth)
+    SynthMol = synth.SynthMol
+    # strong scaling: the workload is the same at every N, so this arm times the same thing whatever --gpus says
     sm = SynthMol(cfg["system"], cfg["seed"], frozen=False)
-    sec = err = None
-    ranks = 1
-    sample = ""
-    for attempt_cfg, scale in ((cfg, 1), (base_cfg, args.gpus)):
-        keys, vals = reference_start_vector(attempt_cfg, sm)
-        sec, ranks, err = reference_iter_seconds_best(attempt_cfg, sm, keys, vals, args.warmup, args.warmup + args.steps)
-        if sec is not None:
-            sample = (f"{args.steps} iterations of oracle/_ref/frisys_mol after {args.warmup} warm-up iterations on {ranks} "
-                      "rank(s) = host cores (the reference's own MPI code; no MPI installation here: its collectives run "
-                      "between processes over shared memory, oracle/mpi_shim)")
-            if scale > 1 and attempt_cfg is base_cfg:
-                # the reference could not load the full weak-scaled vector (its Adder holds 1e6 elements per rank,
-                # vec_utils.hpp:960): time ONE GPU's share of the workload and scale the time by the number of shares
-                sec *= scale
-                sample += (f"; bounded sample: 1/{scale} of the workload (one GPU's share: vec_nonz {base_cfg['vec_nonz']}, "
-                           f"mat_nonz {base_cfg['mat_nonz']}), step time = {scale} x the sample's (the reference's cost is "
-                           "linear in both sizes)")
-            break
-        if args.gpus == 1:
-            break
+    keys, vals = reference_start_vector(cfg, sm)
+    sec, ranks, err = reference_iter_seconds_best(cfg, sm, keys, vals, args.warmup, args.warmup + args.steps)
+    sample = (f"{args.steps} iterations of oracle/_ref/frisys_mol after {args.warmup} warm-up iterations on {ranks} "
+              "rank(s) = host cores (the reference's own MPI code; no MPI installation here: its collectives run "
+              "between processes over shared memory, oracle/mpi_shim)")
     if sec is None:
         print(json.dumps({"impl": "reference", "unavailable": err}), flush=True)
         return
     v = round(1.0 / sec, 4)
     out = {"impl": "reference", "metric": "fri_iterations_per_sec", "value": v, "unit": "iter/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "spawned_elements_per_sec": round(cfg["mat_nonz"] * v, 1),
            "config": {"workload": cfg["workload"], "vec_nonz": cfg["vec_nonz"], "mat_nonz": cfg["mat_nonz"]},
            "cpu_baseline": {"value": v, "unit": "iter/s", "cores": ranks, "kind": "reference", "sample": sample},
            "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -604,7 +593,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="ne", choices=sorted(CONFIGS))
+    # default: BASELINE.json configs[2], the configuration the metric "at 1/2/4/8 B200" is quoted on (H2O cc-pVDZ-sized,
+    # 1e6-element vector, 1e6 matrix samples; total size FIXED as N grows: strong scaling).  --config ne: configs[1].
+    ap.add_argument("--config", default="h2o", choices=sorted(CONFIGS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = CONFIGS[args.config]

@@ -54,7 +54,8 @@ struct VecPhaseArgs {
     int do_death;  // 0: compress only (diagnostics / parity test)
 };
 
-__global__ void __launch_bounds__(VP_NT, 1) vec_phase_kernel(MolView gm, VecPhaseArgs a) {
+template <int MINCTAS>
+__global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, VecPhaseArgs a) {
     cg::grid_group grid = cg::this_grid();
     (void)grid;
     MolView m = mol_stage_shared_bulk(gm, fr_dyn_smem);
@@ -371,16 +372,33 @@ __global__ void __launch_bounds__(VP_NT, 1) vec_phase_kernel(MolView gm, VecPhas
     double carry = blk_lb, new_norm = 0;
     unsigned long long n_samples = 0, n_surv = 0;
     const double nv = G / nrem;
+    double nx4[VP_ITEMS];  // software pipeline: the next tile's loads are issued before this tile's scan and barrier
+    uint8_t nf4[VP_ITEMS];
+    {
+        const size_t i0 = lo + (size_t)tid * VP_ITEMS;
+        fr2_ld4(v0, i0, hi, nx4);
+#pragma unroll
+        for (int k = 0; k < VP_ITEMS; k++) nf4[k] = i0 + k < hi ? a.flags[i0 + k] : 1;
+    }
     for (size_t base = lo; base < hi; base += VP_TILE) {
         const size_t i0 = base + (size_t)tid * VP_ITEMS;
         double x4[VP_ITEMS], m4[VP_ITEMS];
         uint8_t f4[VP_ITEMS];
-        fr2_ld4(v0, i0, hi, x4);
+#pragma unroll
+        for (int k = 0; k < VP_ITEMS; k++) {
+            x4[k] = nx4[k];
+            f4[k] = nf4[k];
+        }
+        if (base + VP_TILE < hi) {
+            const size_t j0 = i0 + VP_TILE;
+            fr2_ld4(v0, j0, hi, nx4);
+#pragma unroll
+            for (int k = 0; k < VP_ITEMS; k++) nf4[k] = j0 + k < hi ? a.flags[j0 + k] : 1;
+        }
         double tsum = 0;
 #pragma unroll
         for (int k = 0; k < VP_ITEMS; k++) {
             const size_t i = i0 + k;
-            f4[k] = i < hi ? a.flags[i] : 1;
             m4[k] = (i < hi && i >= nd && !f4[k]) ? fabs(x4[k]) : 0.0;
             tsum += m4[k];
         }
@@ -439,31 +457,36 @@ __global__ void __launch_bounds__(VP_NT, 1) vec_phase_kernel(MolView gm, VecPhas
         const size_t i0 = base + (size_t)tid * VP_ITEMS;
         uint8_t f4[VP_ITEMS];
         unsigned ts = 0;
+        uint64_t key4[VP_ITEMS];
+        double val4[VP_ITEMS], dg4[VP_ITEMS];
 #pragma unroll
-        for (int k = 0; k < VP_ITEMS; k++) {
-            f4[k] = i0 + k < hi ? a.flags[i0 + k] : 1;
-            ts += f4[k] ? 0u : 1u;
+        for (int k = 0; k < VP_ITEMS; k++) {  // everything the tile needs is in flight before the scan's barrier
+            const bool in = i0 + k < hi;
+            f4[k] = in ? a.flags[i0 + k] : 1;
+            key4[k] = in ? v.keys[i0 + k] : FRIES_EMPTY_KEY;
+            val4[k] = in ? v0[i0 + k] : 0.0;
+            dg4[k] = in ? v.diag[i0 + k] : 0.0;
         }
+#pragma unroll
+        for (int k = 0; k < VP_ITEMS; k++) ts += f4[k] ? 0u : 1u;
         unsigned ex, tot;
         fr2_scan_u(ts, ex, tot, sm_wcnt);
         unsigned long long o = ocarry + ex;
-        uint64_t key4[VP_ITEMS];
         uint64_t slot4[VP_ITEMS];
         uint32_t pos4[VP_ITEMS];
 #pragma unroll
         for (int k = 0; k < VP_ITEMS; k++) {
-            const size_t i = i0 + k;
-            key4[k] = FRIES_EMPTY_KEY;
             if (!f4[k]) {
-                const uint64_t key = v.keys[i];
-                key4[k] = key;
+                const uint64_t key = key4[k];
                 pos4[k] = (uint32_t)o;
                 a.keys_b[o] = key;
-                a.vals_b[o] = v0[i];
+                a.vals_b[o] = val4[k];
                 a.vals_b[v.cap + o] = 0.0;  // row 1 is zero after step 7
-                a.diag_b[o] = v.diag[i];
+                a.diag_b[o] = dg4[k];
                 slot4[k] = vec_hash(v, key, s_scr) & v.tmask;
                 o++;
+            } else {
+                key4[k] = FRIES_EMPTY_KEY;
             }
         }
         // four independent probe chains per thread
@@ -524,16 +547,23 @@ int fries_vec_phase_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, double e
     a.scal = hb->scal.p;
     a.do_death = do_death ? 1 : 0;
     const size_t smem = (size_t)mol->view.d.blob_doubles * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute((const void *)vec_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
+    // two CTAs per SM (<= 64 registers) once an SM holds several tiles: the blocked passes keep one tile per CTA in flight
+    static const int forced = [] {
+        const char *e = getenv("FRIES_VECPHASE_CTAS");
+        return (e && (e[0] == '1' || e[0] == '2') && e[1] == 0) ? e[0] - '0' : 0;
+    }();
+    const int ctas = forced ? forced : (vec->cap >= (size_t)1000000 ? 2 : 1);
+    const void *kern = ctas == 2 ? (const void *)vec_phase_kernel<2> : (const void *)vec_phase_kernel<1>;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[ctas - 1]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set[ctas - 1] = true;
     }
     MolView gm = mol->view;
     void *args[] = {(void *)&gm, (void *)&a};
     {
         ProfScope ps(c, "vec_phase");
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)vec_phase_kernel, dim3(c->sm_count), dim3(VP_NT), args, smem, c->stream));
+        CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(c->sm_count * ctas), dim3(VP_NT), args, smem, c->stream));
         c->launch_count++;
     }
     vec->cur = nb;

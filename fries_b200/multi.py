@@ -202,18 +202,24 @@ class MultiGpuFrisys:
 
 
 def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_workload, ClockSampler, cpu_baseline_block):
-    """bench.py body for --gpus N > 1: weak scaling (vec_nonz and mat_nonz grow with N), one JSON line on rank 0"""
+    """bench.py body for --gpus N > 1, one JSON line on rank 0.  Strong scaling for the molecular configurations (the
+    vector and the sample budget are those of the configuration at every N: BASELINE.json configs[2] is quoted "at 1/2/4/8
+    B200"); the synthetic configuration (configs[4], `synthetic_vector`) is weak-scaled: its sizes are per GPU."""
     import json
 
     from .api import hash_owner
 
     stream = torch.cuda.current_stream()
     gcfg = dict(cfg)
-    gcfg["vec_nonz"] = cfg["vec_nonz"] * world
-    gcfg["mat_nonz"] = cfg["mat_nonz"] * world
-    gcfg["target"] = cfg["target"] * world
-    gcfg["max_dets"] = cfg["max_dets"] * world
     synthetic = bool(cfg.get("synthetic_vector"))
+    weak = synthetic
+    if weak:
+        gcfg["vec_nonz"] = cfg["vec_nonz"] * world
+        gcfg["mat_nonz"] = cfg["mat_nonz"] * world
+        gcfg["target"] = cfg["target"] * world
+        gcfg["max_dets"] = cfg["max_dets"] * world
+    # capacity of one rank's store: its share plus head-room for the imbalance of the owner hash
+    max_dets_local = cfg["max_dets"] if weak else int(1.5 * cfg["max_dets"] / world) + 65536
     if synthetic:
         gcfg["skip_vector"] = True
     wl = prepare_workload(gcfg, ctx)  # every rank prepares the same global start vector (deterministic)
@@ -222,7 +228,7 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
         _, owner = hash_owner(ctx, wl["keys"], wl["proc_scr"], world)
     spawn_cap_local = 4 * gcfg["mat_nonz"] // world          # spawn_length = matr_samp * 4 / n_procs
     seg_cap = 2 * gcfg["mat_nonz"] // (world * world) + 8192
-    eng = MultiGpuFrisys(ctx, dist, rank, world, mol, sm, cfg["max_dets"], spawn_cap_local, seg_cap, wl["proc_scr"],
+    eng = MultiGpuFrisys(ctx, dist, rank, world, mol, sm, max_dets_local, spawn_cap_local, seg_cap, wl["proc_scr"],
                          wl["vec_scr"], wl["hf_en"], (wl["hf"], np.ones(1)), (wl["htrial_keys"], wl["htrial_vals"]),
                          route=os.environ.get("FRIES_ROUTE", "p2p"))
     if synthetic:
@@ -261,7 +267,7 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
                           new_hb=1 if cfg["dist"] == "HB_unnorm" else 0, matr_samp=gcfg["mat_nonz"],
                           target_nonz=gcfg["vec_nonz"], en_shift=0.0)
     rs = np.random.RandomState(1)
-    uni = (rs.randint(0, 2**32, 6 * (args.warmup + args.steps + 8), dtype=np.uint64) / (1.0 + 0xFFFFFFFF)).reshape(-1, 6)
+    uni = (rs.randint(0, 2**32, 6 * (args.warmup + 2 * args.steps + 16), dtype=np.uint64) / (1.0 + 0xFFFFFFFF)).reshape(-1, 6)
     ui = 0
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     last = None
@@ -287,6 +293,35 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
     ms = float(ms.item())
     ms_per_step = ms / args.steps
+    # e2e, the same definition as at N = 1: every step uploads this rank's shard of the vector from pinned host memory,
+    # iterates, and downloads the shard again; timed on the host between barriers, max over ranks
+    import time
+    cap_l = eng.vec.capacity
+    hk = torch.empty(cap_l, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+    hv = torch.empty(2 * cap_l, dtype=torch.float64).pin_memory().numpy()
+    n_now = eng.vec.download_into(hk, hv)
+    h2d = d2h = 0
+    dist.barrier()
+    torch.cuda.synchronize()
+    t_e2e = 0.0
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        check(lib.fries_vec_upload(eng.vec.h, hk.ctypes.data, hv.ctypes.data, n_now))
+        h2d += n_now * 8 * 3 + 48
+        last = eng.iterate(params, uni[ui]); ui += 1
+        n_now = eng.vec.download_into(hk, hv)
+        d2h += n_now * 8 * 3 + 128
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
+    te = torch.tensor([t_e2e, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+    tmax = te.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(te)  # bytes: summed over the ranks
+    e2e_value = args.steps / float(tmax[0].item())
+    h2d_tot, d2h_tot = float(te[1].item()), float(te[2].item())
     # per-kernel times (event pairs around every launch; kernels with in-kernel exchanges include the wait for peers)
     ctx.set_profile(2)
     for _ in range(5):
@@ -295,7 +330,7 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
     ctx.set_profile(0)
     kern = {}
     for nm in ["hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4", "hbpp_finalize", "merge_insert",
-               "merge_accum", "death_axpy", "find_preserve", "sys_comp", "compact"]:
+               "merge_accum", "vec_phase", "death_axpy", "find_preserve", "sys_comp", "compact"]:
         t, n = ctx.kernel_ms(nm)
         if n:
             kern[nm] = round(t / n, 4)
@@ -309,9 +344,10 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
             src = "MEASURED_PEAKS.json (burst copy)"
         except OSError:
             peak, src = 6650.0, "fallback B200_PROFILING.md"
-        bytes_alg = {"hbpp_finalize": 56, "merge_insert": 28, "merge_accum": 28}.get(top, 40) * cfg["mat_nonz"]
+        share = 1 if weak else world  # one GPU's share of the configuration's samples / elements
+        bytes_alg = {"hbpp_finalize": 56, "merge_insert": 28, "merge_accum": 28}.get(top, 40) * cfg["mat_nonz"] // share
         if top in ("death_axpy", "find_preserve", "sys_comp", "compact"):
-            bytes_alg = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8}[top] * cfg["vec_nonz"]
+            bytes_alg = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8}[top] * cfg["vec_nonz"] // share
         ach = bytes_alg / (kern[top] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 5), "traffic": None, "peak_source": src, "ms_per_launch": kern[top],
@@ -321,22 +357,32 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
     check(lib.fries_hbpp_round_stamps(eng.vec.hb, 3, ptr(rts)))
     err = eng.comm.error_epoch()
     if rank == 0:
+        # spawn route over NVLink: 16 B (determinant | flag, value) per spawned element that leaves its GPU, (N - 1) / N of
+        # them under a uniform owner hash; per GPU and direction, against the measured peer-copy rate (B200_PROFILING.md)
+        nvl_bytes_per_gpu = 16.0 * (spawned / args.steps) * (world - 1) / world / world
+        nvl_gbps = nvl_bytes_per_gpu / (ms_per_step * 1e-3) / 1e9
         out = {
             "metric": "fri_iterations_per_sec", "value": round(1000.0 / ms_per_step, 3), "unit": "iter/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["workload"] + f" x{world} (weak scaling: vec_nonz, mat_nonz, target x n_gpus)",
+            "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": cfg["workload"] + (f" x{world} (weak scaling: vec_nonz, mat_nonz, target x n_gpus)" if weak else ""),
                        "vec_nonz": gcfg["vec_nonz"], "mat_nonz": gcfg["mat_nonz"],
-                       "l2": "flushed between iterations (512 MB write)", "stored_dets": int(last.curr_size)},
+                       "l2": "flushed between iterations (512 MB write)", "stored_dets": int(last.curr_size),
+                       "engine": "compress2 stage kernels; round-1 vector kernels (multi-rank)"},
             "spawned_elements_per_sec": round(spawned / (ms * 1e-3), 1),
             "determinant_updates_per_sec": round(gcfg["vec_nonz"] * args.steps / (ms * 1e-3), 1),
             "gpu_launches": int(ctx.launch_count - launches0), "clocks": clk,
             "route": dict(eng.route_description,
-                          scalar_reductions="in-kernel, peer-mapped inboxes over NVLink (csrc/comm.cuh)"),
-            "e2e": {"value": round(1000.0 / ms_per_step, 3), "unit": "iter/s", "h2d_bytes_per_step": 48,
-                    "d2h_bytes_per_step": 128,
-                    "what": "fries_frisys_mol_spawn + all_to_all + fries_frisys_mol_finish per step; the vector is "
-                            "resident (uniforms in, iteration statistics out)"},
+                          scalar_reductions="in-kernel, peer-mapped inboxes over NVLink (csrc/comm.cuh)",
+                          nvlink_bytes_per_gpu_per_step=round(nvl_bytes_per_gpu, 1), nvlink_GBps_per_gpu=round(nvl_gbps, 3),
+                          nvlink_peak_GBps=770.0, nvlink_frac=round(nvl_gbps / 770.0, 5),
+                          nvlink_note="averaged over the whole step; the stores are issued by the finalize kernel only"),
+            "e2e": {"value": round(e2e_value, 3), "unit": "iter/s", "h2d_bytes_per_step": int(h2d_tot / args.steps),
+                    "d2h_bytes_per_step": int(d2h_tot / args.steps),
+                    "what": "per step and rank: fries_vec_upload of the rank's shard (pinned host memory) + "
+                            "fries_frisys_mol_spawn + route + fries_frisys_mol_finish + fries_vec_download; bytes summed "
+                            "over the ranks, time = max over ranks"},
             "roofline": roofline,
             "comm_error_epoch": err,
             "stage3_round_stamps_us": [round(x / 1e3, 1) for x in rts],
