@@ -13,7 +13,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <functional>
 #include <iostream>
@@ -463,6 +465,86 @@ struct Context {
     Context(const Context &) = delete;
 };
 
+// ---- several GPUs: one process per GPU, started by host/fries_launch (the reference: mpirun + MPI_COMM_WORLD) -------------
+// The launcher exports FRIES_NRANKS, FRIES_RANK and FRIES_RDV (a private directory); the ranks exchange small byte strings
+// (CUDA IPC handles, the seed) through files in that directory -- the only host-side "collective" the GPU path needs: all
+// per-iteration communication happens inside kernels over peer-mapped memory (csrc/comm.cuh).
+struct Ranks {
+    int n = 1, rank = 0;
+    std::string rdv;
+    Ranks() {
+        const char *a = std::getenv("FRIES_NRANKS"), *b = std::getenv("FRIES_RANK"), *c = std::getenv("FRIES_RDV");
+        if (a && b && c && std::atoi(a) > 1) {
+            n = std::atoi(a);
+            rank = std::atoi(b);
+            rdv = c;
+            if (rank < 0 || rank >= n) throw std::runtime_error("FRIES_RANK out of range");
+        }
+    }
+    // all-gather of `bytes` bytes per rank (MPI_Allgather): out = n x bytes in rank order
+    std::vector<uint8_t> allgather(const std::string &tag, const void *mine, size_t bytes) const {
+        std::vector<uint8_t> out(n * bytes);
+        if (n == 1) {
+            std::memcpy(out.data(), mine, bytes);
+            return out;
+        }
+        const std::string base = rdv + "/" + tag + ".";
+        {
+            const std::string tmp = base + std::to_string(rank) + ".tmp", fin = base + std::to_string(rank);
+            std::ofstream f(tmp, std::ios::binary);
+            f.write((const char *)mine, (std::streamsize)bytes);
+            f.close();
+            if (std::rename(tmp.c_str(), fin.c_str()) != 0) throw std::runtime_error("rendezvous: cannot write " + fin);
+        }
+        for (int r = 0; r < n; r++) {
+            const std::string fin = base + std::to_string(r);
+            for (long spin = 0;; spin++) {
+                std::ifstream f(fin, std::ios::binary);
+                if (f.is_open()) {
+                    f.read((char *)out.data() + (size_t)r * bytes, (std::streamsize)bytes);
+                    if ((size_t)f.gcount() == bytes) break;
+                }
+                if (spin > 600000) throw std::runtime_error("rendezvous: rank " + std::to_string(r) + " did not arrive (" + tag + ")");
+                struct timespec ts = {0, 200000};
+                nanosleep(&ts, nullptr);
+            }
+        }
+        return out;
+    }
+    void barrier(const std::string &tag) const {
+        uint8_t b = 1;
+        allgather(tag, &b, 1);
+    }
+    // MPI_Bcast from rank 0
+    template <class T>
+    T bcast0(const std::string &tag, T v) const {
+        std::vector<uint8_t> all = allgather(tag, &v, sizeof(T));
+        T r;
+        std::memcpy(&r, all.data(), sizeof(T));
+        return r;
+    }
+};
+
+// peer-mapped inboxes + spawn-route windows of the ranks (fries_comm, include/fries_b200.h)
+struct Comm {
+    fries_comm *h = nullptr;
+    Comm(Context &c, const Ranks &rk, size_t seg_cap) {
+        uint8_t handle[64];
+        check(fries_comm_create(c.h, rk.n, rk.rank, &h, handle));
+        std::vector<uint8_t> all = rk.allgather("comm", handle, 64);
+        check(fries_comm_connect(h, all.data()));
+        rk.barrier("comm_ok");
+        check(fries_comm_route_create(h, seg_cap, handle));
+        all = rk.allgather("route", handle, 64);
+        check(fries_comm_route_connect(h, all.data()));
+        rk.barrier("route_ok");
+    }
+    ~Comm() {
+        if (h) fries_comm_destroy(h);
+    }
+    Comm(const Comm &) = delete;
+};
+
 struct Molecule {
     fries_mol *h = nullptr;
     unsigned n_orb, n_elec_total, n_frz;
@@ -577,10 +659,31 @@ class DistVec {
     std::vector<uint8_t> buf_ini_;
     std::vector<uint32_t> proc_scr_, vec_scr_;  // hash.dat contents (HashTable scramblers, det_hash.hpp:41-58)
     unsigned hh_sites_ = 0, hh_ph_bits_ = 0;    // HubHolVec only
+    int n_ranks_ = 1, rank_ = 0;  // owner partitioning: hash_fxn(occ; proc_scrambler) % n_ranks (vec_utils.hpp:373-379)
+    Context *ctx_ = nullptr;
     DistVec(Context &c, size_t size, unsigned n_bits_, unsigned n_elec_, unsigned n_vecs_, const std::vector<uint32_t> &proc_scr,
-            const std::vector<uint32_t> &vec_scr)
-        : n_bits(n_bits_), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size), proc_scr_(proc_scr), vec_scr_(vec_scr) {
-        check(fries_vec_create(c.h, size, n_bits, n_elec, n_vecs, proc_scr.data(), vec_scr.data(), 1, 0, &h));
+            const std::vector<uint32_t> &vec_scr, int n_ranks = 1, int rank = 0)
+        : n_bits(n_bits_), n_elec(n_elec_), n_vecs(n_vecs_), max_size_(size), proc_scr_(proc_scr), vec_scr_(vec_scr),
+          n_ranks_(n_ranks), rank_(rank), ctx_(&c) {
+        check(fries_vec_create(c.h, size, n_bits, n_elec, n_vecs, proc_scr.data(), vec_scr.data(), n_ranks, rank, &h));
+    }
+    // the elements of (dets, vals) this rank owns (DistVec::add routes by idx_to_proc; at set-up every rank holds the list)
+    void owned(const std::vector<uint64_t> &dets, const std::vector<double> &vals, std::vector<uint64_t> &od,
+               std::vector<double> &ov) {
+        od.clear();
+        ov.clear();
+        if (n_ranks_ == 1) {
+            od = dets;
+            ov = vals;
+            return;
+        }
+        std::vector<int32_t> own(dets.size());
+        check(fries_hash_owner(ctx_->h, dets.data(), dets.size(), proc_scr_.data(), (int)n_bits, n_ranks_, nullptr, own.data()));
+        for (size_t i = 0; i < dets.size(); i++)
+            if (own[i] == rank_) {
+                od.push_back(dets[i]);
+                ov.push_back(vals[i]);
+            }
     }
     // HubHolVec FRIES/hh_vec.hpp:27-29
     DistVec(Context &c, size_t size, unsigned n_sites, unsigned ph_bits, unsigned n_elec_, unsigned n_vecs_,
@@ -601,10 +704,13 @@ class DistVec {
         return n;
     }
     // add x n + perform_add(origin) with curr_vec_idx = dest (vec_utils.hpp:418-440)
-    void add(const std::vector<uint64_t> &dets, const std::vector<double> &vals, uint8_t ini_flag, unsigned origin = 0,
+    void add(const std::vector<uint64_t> &dets_all, const std::vector<double> &vals_all, uint8_t ini_flag, unsigned origin = 0,
              unsigned dest = 0) {
+        std::vector<uint64_t> dets;
+        std::vector<double> vals;
+        owned(dets_all, vals_all, dets, vals);
         std::vector<uint8_t> ini(dets.size(), ini_flag);
-        check(fries_vec_add(h, dets.data(), vals.data(), ini.data(), dets.size(), origin, dest));
+        if (!dets.empty()) check(fries_vec_add(h, dets.data(), vals.data(), ini.data(), dets.size(), origin, dest));
         host_valid_ = false;
     }
     double local_norm(unsigned row) {
@@ -840,12 +946,20 @@ class DistVec {
         size_t nb = ceiling(n_bits, 8);
         std::vector<uint8_t> bytes(dets.size() * nb);
         for (size_t i = 0; i < dets.size(); i++) key_to_bytes(dets[i], &bytes[i * nb], nb);
-        std::ofstream fd(path + "dets0.dat", std::ios::binary);
+        const std::string r = std::to_string(rank_);  // one pair of files per rank, as the reference (:714-733)
+        std::ofstream fd(path + "dets" + r + ".dat", std::ios::binary);
         fd.write((const char *)bytes.data(), bytes.size());
-        std::ofstream fv(path + "vals0.dat", std::ios::binary);
+        std::ofstream fv(path + "vals" + r + ".dat", std::ios::binary);
         fv.write((const char *)vals.data(), vals.size() * sizeof(double));
-        std::ofstream fz(path + "dense.txt");
-        fz << n_dense << "," << '\n';
+        if (rank_ == 0) {  // one entry per rank (:735-745); several ranks: no dense subspace in this version
+            std::ofstream fz(path + "dense.txt");
+            if (n_ranks_ == 1) {
+                fz << n_dense << "," << '\n';
+            } else {
+                for (int r = 0; r < n_ranks_ - 1; r++) fz << 0 << ",";
+                fz << 0 << '\n';
+            }
+        }
     }
     // DistVec::init_dense vec_utils.hpp:858-897 (single rank): the determinants of the file (read_dets io_utils.cpp:565-586,
     // one integer per determinant) become the first stored elements, with value 0, and are never deleted
@@ -869,12 +983,13 @@ class DistVec {
     }
     // DistVec::load vec_utils.hpp:761-844 (single rank): re-hash, drop |v| <= 1e-9
     void load(const std::string &path) {
-        std::ifstream fd(path + "dets0.dat", std::ios::binary);
-        if (!fd.is_open()) throw std::runtime_error("Error: could not open saved binary vector file at " + path + "dets0.dat");
+        const std::string rs = std::to_string(rank_);  // a checkpoint is restarted on the rank count it was saved with
+        std::ifstream fd(path + "dets" + rs + ".dat", std::ios::binary);
+        if (!fd.is_open()) throw std::runtime_error("Error: could not open saved binary vector file at " + path + "dets" + rs + ".dat");
         std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(fd)), std::istreambuf_iterator<char>());
         size_t nb = ceiling(n_bits, 8), n = bytes.size() / nb;
-        std::ifstream fv(path + "vals0.dat", std::ios::binary);
-        if (!fv.is_open()) throw std::runtime_error("Error: could not open saved binary vector file at " + path + "vals0.dat");
+        std::ifstream fv(path + "vals" + rs + ".dat", std::ios::binary);
+        if (!fv.is_open()) throw std::runtime_error("Error: could not open saved binary vector file at " + path + "vals" + rs + ".dat");
         std::vector<double> all(n * n_vecs, 0.0);
         fv.read((char *)all.data(), all.size() * sizeof(double));
         {   // sizes of the dense subspaces (one per rank; single rank here): the first n_dense entries are kept as they are

@@ -40,6 +40,10 @@ int main(int argc, char *argv[]) {
         return 1;
     }
     try {
+        // several GPUs: started by fries_launch -n N, one process per GPU (rank r drives GPU r unless --device says otherwise)
+        Ranks rk;
+        const bool multi = rk.n > 1;
+        if (multi && !args.has("device")) device = rk.rank;
         Context ctx(device);
         double shift_damping = 0.05;
         unsigned shift_interval = 10, save_interval = 100;
@@ -53,21 +57,32 @@ int main(int argc, char *argv[]) {
         uint64_t hf_det = gen_hf_bitstring(n_orb, n_elec_unf);
         double hf_en = has_shift ? ham_shift - in_data.core_en : (legacy ? in_data.hf_en : mol.diag_matrel(hf_det));
 
-        unsigned seed = seed_from_clock_or_env();
-        std::cout << "seed on process 0 is " << seed << std::endl;
+        // one generator state on every rank: the reference draws on rank 0 and broadcasts (frisys_mol.cpp:132-139,528-530)
+        unsigned seed = rk.bcast0("seed", seed_from_clock_or_env());
+        if (rk.rank == 0) std::cout << "seed on process 0 is " << seed << std::endl;
         std::mt19937 mt_obj(seed);
 
-        unsigned spawn_length = matr_samp * 4;
+        unsigned spawn_length = matr_samp * 4 / rk.n;  // frisys_mol.cpp:109: spawn_length = matr_samp * 4 / n_procs
+        if (multi && (has_det_space || has_trial))
+            throw std::runtime_error("--det_space and --trial_vec need a single GPU in this version (run without fries_launch)");
         std::vector<uint32_t> proc_scrambler(2 * n_orb), vec_scrambler(2 * n_orb);
         if (has_load) {
             load_proc_hash(load_dir, proc_scrambler);
         } else {
             for (auto &x : proc_scrambler) x = mt_obj();
-            save_proc_hash(result_dir, proc_scrambler);
+            if (rk.rank == 0) save_proc_hash(result_dir, proc_scrambler);
         }
         for (auto &x : vec_scrambler) x = mt_obj();
 
-        DistVec sol_vec(ctx, max_n_dets, 2 * n_orb, n_elec_unf, 2, proc_scrambler, vec_scrambler);
+        DistVec sol_vec(ctx, max_n_dets, 2 * n_orb, n_elec_unf, 2, proc_scrambler, vec_scrambler, rk.n, rk.rank);
+        // the rank that owns the Hartree-Fock determinant writes the text files and stdout (frisys_mol.cpp:288,521)
+        int hf_proc = 0;
+        if (multi) {
+            int32_t own = 0;
+            check(fries_hash_owner(ctx.h, &hf_det, 1, proc_scrambler.data(), (int)(2 * n_orb), rk.n, nullptr, &own));
+            hf_proc = own;
+        }
+        const bool writer = rk.rank == hf_proc;
         check(fries_vec_set_diag_mol(sol_vec.h, mol.h, hf_en));
 
         // trial vector and H * trial
@@ -85,10 +100,11 @@ int main(int argc, char *argv[]) {
         if (!has_load) {
             if (has_det_space) {
                 n_determ = sol_vec.init_dense(det_space_path, result_dir);
-            } else {
+            } else if (rk.rank == 0) {
                 std::ofstream dense_f(result_dir + "dense.txt");
                 if (!dense_f.is_open()) throw std::runtime_error("Error opening file containing sizes of deterministic subspaces");
-                dense_f << 0 << ", " << '\n';
+                for (int r = 0; r < rk.n; r++) dense_f << 0 << ", ";  // one size per rank (frisys_mol.cpp:243-251)
+                dense_f << '\n';
             }
         }
         // initial vector
@@ -101,22 +117,24 @@ int main(int argc, char *argv[]) {
             std::vector<double> v;
             load_vec_txt(ini_path, d, v);
             sol_vec.add(d, v, 1);
-        } else {
+        } else if (!multi) {
             sol_vec.add(hf_det, 100.0, 1);  // DistVec::add + perform_add, as the reference does
             sol_vec.perform_add(0);
+        } else {
+            sol_vec.add(std::vector<uint64_t>{hf_det}, std::vector<double>{100.0}, 1);  // lands on its owner only
         }
         double glob_norm = sol_vec.local_norm();
         double last_one_norm = 0;
         (void)glob_norm;
 
         auto open_app = [&](const char *name) {
-            std::ofstream f(result_dir + name, std::ofstream::app);
+            std::ofstream f(writer ? result_dir + name : std::string("/dev/null"), std::ofstream::app);
             if (!f.is_open()) throw std::runtime_error("Could not open file for writing in directory " + result_dir);
             return f;
         };
         std::ofstream num_file = open_app("projnum.txt"), den_file = open_app("projden.txt"), shift_file = open_app("S.txt"),
                       norm_file = open_app("norm.txt"), nkept_file = open_app("nkept.txt"), ini_file = open_app("nini.txt");
-        {
+        if (writer) {
             std::ofstream param_f(result_dir + "params.txt");
             param_f << "FRI calculation\n" << (legacy ? "HF path: " : "FCIDUMP path: ") << (legacy ? hf_path : fcidump_path) << "\nepsilon (imaginary time step): " << eps
                     << "\nTarget norm " << target_norm << "\nInitiator threshold: " << init_thresh
@@ -127,6 +145,14 @@ int main(int argc, char *argv[]) {
         }
         check(fries_frisys_mol_setup(sol_vec.h, mol.h, spawn_length, trial_dets.data(), trial_vals.data(), trial_dets.size(),
                                      htrial_dets.data(), htrial_vals.data(), htrial_dets.size(), &sol_vec.hb));
+        // several GPUs: the peer-mapped inboxes and spawn-route windows (Adder::perform_add vec_utils.hpp:991-1019 becomes
+        // stores into the owner's window from inside the spawn kernel; csrc/comm.cuh)
+        std::unique_ptr<Comm> comm;
+        if (multi) {
+            const size_t seg_cap = 2 * (size_t)matr_samp / ((size_t)rk.n * rk.n) + 8192;
+            comm.reset(new Comm(ctx, rk, seg_cap));
+            check(fries_hbpp_set_route_p2p(sol_vec.hb, comm->h));
+        }
         // frisys_mol.cpp:398-401: size of the pre-computed dense part of H = all connections of the dense determinants;
         // the stochastic compression of H gets the rest of the budget (:421: matr_samp - tot_dense_h)
         size_t tot_dense_h = 0;
@@ -141,7 +167,7 @@ int main(int argc, char *argv[]) {
                 check(fries_mol_doub_ex(mol.h, d.data(), n_determ, off.data(), nullptr, 0));
                 tot_dense_h += off[n_determ];
             }
-            std::cout << "Elements in dense H: " << tot_dense_h << "\n";
+            if (writer) std::cout << "Elements in dense H: " << tot_dense_h << "\n";
         }
 
         for (unsigned iterat = 0; iterat < max_iter; iterat++) {
@@ -156,7 +182,12 @@ int main(int argc, char *argv[]) {
                                          " elements) leaves nothing of --mat_nonz for the stochastic part");
             fries_frisys_params p{eps, init_thresh, p_doub, new_hb, (uint32_t)(matr_samp - tot_dense_h), target_nonz, en_shift};
             fries_iter_stats st;
-            check(fries_frisys_mol_iterate(sol_vec.h, mol.h, sol_vec.hb, &p, u, &st));
+            if (!multi) {
+                check(fries_frisys_mol_iterate(sol_vec.h, mol.h, sol_vec.hb, &p, u, &st));
+            } else {  // spawn (elements go straight to their owners), then merge + vector half; the statistics are global
+                check(fries_frisys_mol_spawn(sol_vec.h, mol.h, sol_vec.hb, &p, u));
+                check(fries_frisys_mol_finish(sol_vec.h, mol.h, sol_vec.hb, &p, u, nullptr, &st));
+            }
             nkept_file << st.n_kept << '\n';
             if ((iterat + 1) % shift_interval == 0) {
                 // NOTE the shift used inside iteration k+1 is the one adjusted after iteration k, as in the reference
@@ -166,8 +197,9 @@ int main(int argc, char *argv[]) {
             }
             num_file << st.numer << '\n';
             den_file << st.denom << '\n';
-            std::cout << iterat << ", en est: " << st.numer / st.denom << ", shift: " << en_shift << ", norm: " << st.glob_norm
-                      << '\n';
+            if (writer)
+                std::cout << iterat << ", en est: " << st.numer / st.denom << ", shift: " << en_shift << ", norm: " << st.glob_norm
+                          << '\n';
             ini_file << n_ini << '\n';
             if ((iterat + 1) % save_interval == 0) {
                 sol_vec.save(result_dir);
@@ -176,12 +208,16 @@ int main(int argc, char *argv[]) {
                 den_file.flush();
                 shift_file.flush();
                 nkept_file.flush();
-                std::cout << "Total additions to nonzero: " << tot_add << "\n";
+                if (writer) std::cout << "Total additions to nonzero: " << tot_add << "\n";
             }
         }
         sol_vec.save(result_dir);
+        if (multi) rk.barrier("done");  // nobody unmaps its windows while a peer may still be inside an exchange
     } catch (std::exception &ex) {
         std::cerr << "\nException : " << ex.what() << "\n\n";
+        // the reference returns 0 here as well (frisys_mol.cpp:562-565); under fries_launch a failed rank must be seen, or
+        // its peers wait for it in the next exchange
+        if (std::getenv("FRIES_NRANKS") && std::atoi(std::getenv("FRIES_NRANKS")) > 1) return 1;
     }
     return 0;
 }

@@ -27,3 +27,76 @@ def test_multi_gpu_check_under_torchrun():
     assert any("distributed piv_comp_parallel" in ln for ln in lines), lines
     assert any("route p2p" in ln for ln in lines) and any("route nccl" in ln for ln in lines), lines
     assert any("routed H.v == single-GPU H.v" in ln for ln in lines), lines
+
+
+def test_frisys_mol_driver_on_two_gpus(tmp_path):
+    """frisys_mol's command line on 2 GPUs, started by host/bin/fries_launch -n 2 (the reference: mpirun -n 2): C++ only --
+    the CUDA IPC handshake, the per-rank files dets<r>.dat / vals<r>.dat (vec_utils.hpp:713-750) and hash.dat
+    (io_utils.cpp:589-605).  Energy within error bars of the single-GPU run and of the exact ground state; every stored
+    determinant is on the rank that owns it; the REFERENCE's driver restarts from the checkpoint on 2 ranks."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oraclelib
+    from driver_utils import OURS, REF, exact_ground_state, read_col, write_fcidump
+    from fries_b200.synth import SynthMol
+    from test_gpu_drivers import TINY, blocked_ratio
+    sm = SynthMol(*TINY)
+    om = oraclelib.OracleMol(sm)
+    e_corr, e_hf, n = exact_ground_state(sm, om)
+    fd = str(tmp_path / "FCIDUMP")
+    write_fcidump(fd, sm, "D2")
+    n_it = 6000
+    res = {}
+    for name, pre in (("two", [os.path.join(OURS, "fries_launch"), "-n", "2"]), ("one", [])):
+        rd = str(tmp_path / name) + "/"
+        os.makedirs(rd)
+        cmd = pre + [os.path.join(OURS, "frisys_mol"), "--fcidump_path", fd, "--distribution", "HB_unnorm", "--vec_nonz", "150",
+                     "--mat_nonz", "300", "--max_dets", "20000", "--epsilon", "0.05", "--target", "500", "--max_iter", str(n_it),
+                     "--result_dir", rd, "--point_group", "D2"]
+        r = subprocess.run(cmd, env=dict(os.environ, FRIES_SEED="3" if name == "two" else "5"), stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=600)
+        assert r.returncode == 0 and "Exception" not in r.stderr, (name, r.stderr[-800:])
+        num, den = read_col(rd + "projnum.txt"), read_col(rd + "projden.txt")
+        assert len(num) == n_it, (name, len(num))
+        res[name] = blocked_ratio(num, den, burn=1000)
+        assert len([ln for ln in r.stdout.splitlines() if ", en est: " in ln]) == n_it  # one writer: the owner of HF
+    (e2, s2), (e1, s1) = res["two"], res["one"]
+    print("exact", e_corr, "2 GPUs", res["two"], "1 GPU", res["one"])
+    assert abs(e2 - e1) < 5 * (s1 + s2) + 2e-4
+    assert abs(e2 - e_corr) < 5 * s2 + 2e-3 * abs(e_corr) + 2e-4
+    # per-rank files; ownership by the saved scrambler
+    rd = str(tmp_path / "two") + "/"
+    scr = np.fromfile(rd + "hash.dat", dtype=np.uint32)
+    assert scr.size == 2 * sm.n_orb
+    nb = (2 * sm.n_orb + 7) // 8
+    import fries_b200
+    ctx = fries_b200.Context(0)
+    total = 0
+    for rank in range(2):
+        raw = np.fromfile(rd + f"dets{rank}.dat", dtype=np.uint8).reshape(-1, nb)
+        keys = np.array([int.from_bytes(bytes(row), "little") for row in raw], np.uint64)
+        assert os.path.getsize(rd + f"vals{rank}.dat") == keys.size * 2 * 8
+        _, own = fries_b200.hash_owner(ctx, keys, scr, 2)
+        assert np.all(own == rank)
+        total += keys.size
+    assert total > 0
+    ctx.close()
+    # the reference restarts from this checkpoint on 2 ranks (its MPI collectives over oracle/mpi_shim)
+    ref = os.path.join(REF, "frisys_mol")
+    if os.path.exists(ref):
+        rr = str(tmp_path / "ref_restart") + "/"
+        os.makedirs(rr)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "mpi_shim", "shimrun.py"), "-n", "2", ref,
+                            "--fcidump_path", fd, "--distribution", "HB_unnorm", "--vec_nonz", "150", "--mat_nonz", "300",
+                            "--max_dets", "20000", "--epsilon", "0.05", "--target", "500", "--max_iter", "2000", "--result_dir", rr,
+                            "--point_group", "D2", "--load_dir", rd], env=dict(os.environ, FRIES_SEED="9"),
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert "Exception" not in r.stderr, r.stderr[-800:]
+        num, den = read_col(rr + "projnum.txt"), read_col(rr + "projden.txt")
+        assert len(num) == 2000
+        er, sr = blocked_ratio(num, den, burn=200)
+        print("reference restarted from the 2-GPU checkpoint:", er, sr)
+        assert abs(er - e_corr) < 5 * sr + 2e-3 * abs(e_corr) + 5e-4
