@@ -1,0 +1,2 @@
+#pragma once
+#include "fries_global.hpp"
