@@ -40,6 +40,13 @@ CONFIGS = {
                max_dets=25000000, initiator=1.0, dist="HB_unnorm", synthetic_vector=True, frozen=True,
                workload="synthetic 1.25e7-determinant vector per GPU, N2 cc-pVDZ-sized integrals (NORB=26 NELEC=10, "
                         "HB_unnorm, vec_nonz = mat_nonz = 1.25e7 per GPU): spawn -> merge -> compress"),
+    # BASELINE.json configs[3]: N2 stretched cc-pVDZ-sized frifull_mol -- full deterministic H.v + systematic vector
+    # compression (FRIES_bin/frifull_mol.cpp:256-320).  One GPU's share of the 8-GPU configuration: 2.5e4 parents per
+    # iteration, ~2.1e3 connections each, i.e. ~5e7 spawned H.v elements per iteration.
+    "n2full": dict(system="n2", seed=7, point_group="D2h", eps=0.001, target=2.5e4, vec_nonz=25000, mat_nonz=0,
+                   max_dets=40000000, initiator=0.0, dist="full", frozen=True, full_hv=True,
+                   workload="N2 stretched cc-pVDZ-sized frifull_mol (NORB=26 NELEC=10 frozen core, full deterministic H.v + "
+                            "systematic compression to vec_nonz 25000)"),
 }
 
 # SURVEY.md section 8d algorithmic bytes
@@ -181,6 +188,111 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def run_frifull(args, cfg, ctx, stream, local):
+    """--config n2full: frifull_mol iterations (compress the iterate to vec_nonz, then the full deterministic H.v into the
+    other row).  value = spawned H.v elements per second; the H.v kernels gather packed integrals from L2 (0.5 MB table),
+    so the roofline line is the spawned-element byte contract (56 B each) against HBM."""
+    import torch
+
+    import fries_b200
+    from fries_b200._capi import FrifullParams
+    wcfg = dict(cfg, mat_nonz=1, max_dets=4_000_000)  # the start vector's construction needs a far smaller store
+    wl = prepare_workload(wcfg, ctx)
+    sm, mol = wl["sm"], wl["mol"]
+    vec = fries_b200.Vec(ctx, cfg["max_dets"], sm.n_bits, sm.n_elec, 2, wl["proc_scr"], wl["vec_scr"])
+    vec.set_diag_mol(mol, wl["hf_en"])
+    vec.upload(wl["keys"], np.stack([wl["vals"], np.zeros_like(wl["vals"])]))
+    vec.frisys_setup(mol, 1 << 24, wl["hf"], np.ones(1), wl["htrial_keys"], wl["htrial_vals"])
+    fp = FrifullParams(eps=cfg["eps"], target_nonz=cfg["vec_nonz"], en_shift=0.0, adjust_shift=0, damp_factor=0.05,
+                       target_norm=0.0, last_one_norm=0.0)
+    uni = mt_uniforms(1, args.warmup + 2 * args.steps + 16)
+    ui = 0
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    last = None
+    for _ in range(args.warmup):
+        last = vec.frifull_iterate(fp, float(uni[ui])); ui += 1
+    clocks = ClockSampler(local)
+    clocks.start()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    spawned = 0
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record(stream)
+        last = vec.frifull_iterate(fp, float(uni[ui])); ui += 1
+        ev[k][1].record(stream)
+        spawned += last.n_spawned
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    ms_per_step = ms / args.steps
+    launches = ctx.launch_count - launches0
+    # e2e: the compressed iterate goes to the host and comes back every step (upload -> iterate -> download of the result)
+    hk = torch.empty(cfg["max_dets"], dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+    hv = torch.empty(2 * cfg["max_dets"], dtype=torch.float64).pin_memory().numpy()
+    n_now = vec.download_into(hk, hv)
+    t_e2e, h2d, d2h = 0.0, 0, 0
+    from fries_b200._capi import check, lib
+    for k in range(max(2, args.steps // 4)):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        check(lib.fries_vec_upload(vec.h, hk.ctypes.data, hv.ctypes.data, n_now))
+        h2d += n_now * 24 + 48
+        st = vec.frifull_iterate(fp, float(uni[ui])); ui += 1
+        n_now = vec.download_into(hk, hv)
+        d2h += n_now * 24 + 128
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
+    n_e2e = max(2, args.steps // 4)
+    ctx.set_profile(2)
+    for _ in range(3):
+        flush.zero_()
+        vec.frifull_iterate(fp, float(uni[ui])); ui += 1
+    ctx.set_profile(0)
+    kern = {}
+    for nm in ["h_diag", "hv_count", "hv_scan", "hv_fill", "merge_insert", "merge_accum", "find_preserve", "sys_comp", "compact"]:
+        t, n = ctx.kernel_ms(nm)
+        if n:
+            kern[nm] = round(t / 3, 4)  # per iteration (a kernel may run several windows)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    per_iter = spawned / args.steps
+    top = max(kern, key=kern.get) if kern else None
+    bytes_top = {"hv_fill": 16, "merge_insert": 28, "merge_accum": 28}.get(top, 56) * per_iter
+    out = {
+        "metric": "spawned_hv_elements_per_sec", "value": round(spawned / (ms * 1e-3), 1), "unit": "elements/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "vec_nonz": cfg["vec_nonz"], "l2": "flushed between iterations (512 MB write)",
+                   "stored_dets": int(last.curr_size), "spawned_per_iteration": int(per_iter)},
+        "fri_iterations_per_sec": round(1000.0 / ms_per_step, 3),
+        "gpu_launches": int(launches), "clocks": clk,
+        "e2e": {"value": round(per_iter * n_e2e / t_e2e, 1), "unit": "elements/s", "h2d_bytes_per_step": int(h2d / n_e2e),
+                "d2h_bytes_per_step": int(d2h / n_e2e),
+                "what": "fries_vec_upload (pinned host vector) + fries_frifull_mol_iterate + fries_vec_download per step"},
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": round(bytes_top / (kern[top] * 1e-3) / 1e9, 2) if top else None,
+                     "peak": peak, "unit": "GB/s", "frac": round(bytes_top / (kern[top] * 1e-3) / 1e9 / peak, 5) if top else None,
+                     "traffic": None, "algorithmic_bytes_per_launch": int(bytes_top), "kernels_ms_per_iteration": kern,
+                     "iter_algorithmic_GBps": round((96 * cfg["vec_nonz"] + 56 * per_iter) / (ms_per_step * 1e-3) / 1e9, 2),
+                     "note": "B_iter(frifull) = 96 N_v + 56 N_s (SURVEY 8d); the connection arithmetic gathers integrals from L2"},
+        "energy_est": last.numer / last.denom if last and last.denom else None,
+        "cpu_baseline": {"value": None, "unit": "elements/s", "cores": 1, "kind": "reference",
+                         "sample": "not run in this line: one reference frifull_mol iteration at this size takes ~40 s per core "
+                                   "(SURVEY 6: 1.3e6 spawned elements/s/core); see profiles/ for the recorded comparison"},
+    }
+    out["roofline"]["iter_frac"] = round(out["roofline"]["iter_algorithmic_GBps"] / peak, 5)
+    print(json.dumps(out), flush=True)
+    vec.close()
+    mol.close()
+    ctx.close()
+
+
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
@@ -211,6 +323,8 @@ def run_ours(args, cfg):
         return run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_workload, ClockSampler,
                                    cpu_baseline_block)
 
+    if cfg.get("full_hv"):
+        return run_frifull(args, cfg, ctx, stream, local)
     wl = prepare_workload(cfg, ctx)
     sm, mol = wl["sm"], wl["mol"]
     spawn_cap = 4 * cfg["mat_nonz"]  # spawn_length = matr_samp * 4 / n_procs (frisys_mol.cpp:109)

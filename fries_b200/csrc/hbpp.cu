@@ -73,7 +73,10 @@ static const void *stage_kernel_ptr() {
 // finalize :917-991 (+ the spawn loop body of frisys_mol.cpp:436-461 when sp.out_keys != nullptr).
 // One thread per sample; tables in shared memory, integrals through L2.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// four CTAs of 256 threads per SM (<= 64 registers): the kernel is a chain of dependent gathers per sample (output list ->
+// path -> determinant -> integrals in L2), so it wants resident warps; at the compiler's free choice (114 registers) only two
+// CTAs fit
+__global__ void __launch_bounds__(256, 4)
 hbpp_finalize_kernel(MolView gm, const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ n_ptr,
                      unsigned long long in_cap, const double *__restrict__ pv, const uint32_t *__restrict__ pw,
                      const uint32_t *__restrict__ ps, const uint32_t *__restrict__ pdet,
