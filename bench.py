@@ -451,9 +451,16 @@ def run_ours(args, cfg):
             print(f"timeline stage {s_} (SM cycles, thread 0 of CTA 0): " +
                   ", ".join(f"{nm} {int(tl[k])}" for k, nm in enumerate(names)), file=sys.stderr)
     if os.environ.get("FRIES_CTA_MARKS"):
-        for s_ in (0, 3):
-            m = vec.cta_marks(s_)
-            for k, nm in enumerate(["start", "A done", "set decided", "B done", "C done", "end"]):
+        for s_ in (0, 3, 4, 5, 6):
+            try:
+                m = vec.cta_marks(s_)
+            except Exception as ex:  # the fused vector kernel is not part of every configuration
+                print(f"cta marks {s_}: {ex}", file=sys.stderr)
+                continue
+            labels = (["start", "A done", "set decided", "B done", "C done", "end"] if s_ < 5 else
+                      ["start", "P1 done", "set decided", "P2 done", "line seeded", "P3 done", "offsets known", "P4 done"] if s_ == 5
+                      else ["P4 tile0 scanned", "P4 tile0 stored", "P4 tile0 indexed", "index cleared"])
+            for k, nm in enumerate(labels):
                 r = m[k]
                 order = r.argsort()
                 print(f"cta marks stage {s_} {nm}: min {r.min() / 1e3:.1f} us (cta {order[0]}), median {float(sorted(r)[len(r) // 2]) / 1e3:.1f}, "

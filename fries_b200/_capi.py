@@ -117,6 +117,7 @@ def _load():
         "fries_hh_batch": (i, [vp, i, vp, vp, sz, u, u, u, C.c_uint64, d, vp]),
         "fries_frisys_hh_setup": (i, [vp, sz, P(vp)]),
         "fries_frisys_hh_iterate": (i, [vp, vp, P(FrisysHhParams), vp, P(IterStats)]),
+        "fries_frifull_hh_iterate": (i, [vp, vp, P(FrisysHhParams), C.c_double, P(IterStats)]),
         "fries_vec_create": (i, [vp, sz, u, u, u, vp, vp, i, i, P(vp)]),
         "fries_vec_destroy": (i, [vp]),
         "fries_vec_add": (i, [vp, vp, vp, vp, sz, u, u]),

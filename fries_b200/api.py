@@ -345,10 +345,10 @@ class Vec:
         check(lib.fries_vec_del(self.h, ptr(f), f.size))
 
     def compress(self, start_row, end_row, compress_size, draws, method="piv") -> int:
-        """compress_vecs / compress_vecs_sys vec_utils.cpp:10-70 -> draws consumed"""
+        """compress_vecs / compress_vecs_sys / compress_vecs_multi vec_utils.cpp:10-127 -> draws consumed"""
         dr = arr(draws, np.uint32)
         used = C.c_size_t(0)
-        check(lib.fries_vec_compress(self.h, start_row, end_row, compress_size, 0 if method == "piv" else 1, ptr(dr),
+        check(lib.fries_vec_compress(self.h, start_row, end_row, compress_size, {"piv": 0, "sys": 1, "multi": 2}[method], ptr(dr),
                                      dr.size, C.byref(used)))
         return used.value
 
@@ -415,6 +415,12 @@ class Vec:
         u = arr(uniforms3, np.float64)
         st = IterStats()
         check(lib.fries_frisys_hh_iterate(self.h, self.hb, C.byref(params), ptr(u), C.byref(st)))
+        return st
+
+    def frifull_hh_iterate(self, params: FrisysHhParams, uniform: float) -> IterStats:
+        """loop body of FRIES_bin/frifull_hh.cpp:186-330"""
+        st = IterStats()
+        check(lib.fries_frifull_hh_iterate(self.h, self.hb, C.byref(params), float(uniform), C.byref(st)))
         return st
 
     def states(self):

@@ -307,6 +307,118 @@ __device__ __forceinline__ BracketResult bracket_solve2_local(const CandList &cl
     return res;
 }
 
+// The same solve for lists one CTA cannot hold in registers (up to FR2_STREAM_CAP candidates, single rank): the CTA streams
+// the list from L2 once per round (coalesced, eight independent loads in flight per thread) and keeps only one bit per
+// candidate -- "not counted yet".  Measured round 2, H2O-sized run: find_preserve brackets ~35000 candidates and the last
+// HB-PP stage ~18000; with the register variant limited to 4096 those fell to the grid-distributed rounds of bracket_solve
+// (a cooperative grid.sync per round: 18 us in the stage, ~30 us in the vector kernel, all other CTAs waiting).
+// Identical arithmetic (exact integer sums in units of ulp(t_lo)), three words per round because the counts of 65536
+// candidates no longer fit beside the high halves.
+#define FR2_STREAM_PER_THREAD 128
+#define FR2_STREAM_CAP ((unsigned long long)FR2_NT * FR2_STREAM_PER_THREAD)
+__device__ __forceinline__ BracketResult bracket_solve2_stream(const CandList &cl, double R0, long long nrem0, double t_lo,
+                                                               double t_hi, unsigned long long *shc, unsigned long long ncand) {
+    BracketResult res;
+    res.valid = false;
+    res.x_cut = t_hi;
+    res.R = R0;
+    res.nrem = 0;
+    res.kept_cand = 0;
+    res.rounds = 0;
+    res.n_cand = ncand;
+    if (nrem0 <= 0 || nrem0 > 0xffffffffll || ncand > FR2_STREAM_CAP) return res;
+    if (!(t_hi * (double)nrem0 >= R0)) return res;
+    const int E_lo = (int)((__double_as_longlong(t_lo) >> 52) & 0x7ff);
+    if (E_lo < 64 || E_lo > 1900) return res;
+    const double ulp_lo = __longlong_as_double((long long)(E_lo - 52) << 52);
+    const int per = (int)((ncand + FR2_NT - 1) / FR2_NT);
+    unsigned long long st0 = ~0ull, st1 = ~0ull;  // bit k: candidate threadIdx.x + k * FR2_NT is not counted yet
+    unsigned long long *acc = shc;                // [3 rotating buffers][3]
+    unsigned long long *acc_min = shc + 12;
+    if (threadIdx.x < 9) acc[threadIdx.x] = 0;
+    if (threadIdx.x == 9) *acc_min = 0x7ff0000000000000ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    unsigned long long cnt_tot = 0;
+    unsigned __int128 sum_tot = 0;
+    double R = R0;
+    unsigned long long nrem = (unsigned long long)nrem0;
+    double xmin = INFINITY;
+    for (unsigned round = 0; round < 4096; round++) {
+        unsigned long long *a = acc + 3 * (round % 3);
+        unsigned long long w_lo = 0, w_hi = 0, w_c = 0;
+        const double fac = (double)nrem;
+        bool big = false;
+        for (int k0 = 0; k0 < per; k0 += 8) {
+            double xx[8];
+            uint32_t mm[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int k = k0 + q;
+                const unsigned long long idx = threadIdx.x + (unsigned long long)k * FR2_NT;
+                const bool live = idx < ncand && (((k < 64 ? st0 >> k : st1 >> (k - 64)) & 1ull) != 0);
+                xx[q] = live ? __ldcg(cl.x + idx) : 0.0;
+                mm[q] = live ? __ldcg(cl.mult + idx) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int k = k0 + q;
+                if (mm[q] > 64u) big = true;
+                if (mm[q] != 0u && xx[q] * fac >= R) {
+                    if (k < 64) st0 &= ~(1ull << k);
+                    else st1 &= ~(1ull << (k - 64));
+                    const long long xb = __double_as_longlong(xx[q]);
+                    const unsigned long long ix = ((unsigned long long)(xb & 0xfffffffffffffll) | (1ull << 52))
+                                                  << ((int)((xb >> 52) & 0x7ff) - E_lo);
+                    const unsigned long long p = ix * mm[q];
+                    w_lo += p & 0xffffffffull;
+                    w_hi += p >> 32;
+                    w_c += mm[q];
+                    xmin = fmin(xmin, xx[q]);
+                }
+            }
+        }
+        if (round == 0 && __syncthreads_or(big)) return res;  // a multiplicity that does not fit: plain rounds
+        if (__any_sync(0xffffffffu, w_c != 0)) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                w_lo += __shfl_xor_sync(0xffffffffu, w_lo, o);
+                w_hi += __shfl_xor_sync(0xffffffffu, w_hi, o);
+                w_c += __shfl_xor_sync(0xffffffffu, w_c, o);
+            }
+            if (lane == 0) {
+                atomicAdd(&a[0], w_lo);
+                atomicAdd(&a[1], w_hi);
+                atomicAdd(&a[2], w_c);
+            }
+        }
+        if (threadIdx.x < 3) acc[3 * ((round + 1) % 3) + threadIdx.x] = 0;
+        __syncthreads();
+        res.rounds = round + 1;
+        const unsigned long long t_lo64 = a[0], hi_round = a[1], c_round = a[2];
+        if (c_round == 0) break;
+        cnt_tot += c_round;
+        sum_tot += ((unsigned __int128)hi_round << 32) + t_lo64;
+        if (cnt_tot >= (unsigned long long)nrem0) return res;  // budget exhausted inside the bracket
+        nrem = (unsigned long long)nrem0 - cnt_tot;
+        double kept_sum = (double)(unsigned long long)(sum_tot >> 64) * 18446744073709551616.0 +
+                          (double)(unsigned long long)sum_tot;
+        R = R0 - kept_sum * ulp_lo;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    if (lane == 0 && xmin < INFINITY) atomicMin(acc_min, (unsigned long long)__double_as_longlong(xmin));
+    __syncthreads();
+    xmin = __longlong_as_double((long long)*acc_min);
+    __syncthreads();
+    res.x_cut = xmin < t_hi ? xmin : t_hi;
+    res.R = R;
+    res.nrem = (unsigned)nrem;
+    res.kept_cand = cnt_tot;
+    res.valid = t_lo * (double)nrem < R;
+    return res;
+}
+
 // every CTA solves (multi-rank, or lists beyond one CTA's registers: the distributed rounds of bracket_solve)
 __device__ __forceinline__ BracketResult bracket_solve2(cg::grid_group &grid, const CandList &cl, unsigned long long *gacc,
                                                         double R0, long long nrem0, double t_lo, double t_hi, double *shd,
@@ -589,9 +701,12 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
             FR_TL(b.st, 25);  // posted
             gc_reduce<2>(gcb, gsh, tag, td, tc, true);
             FR_TL(b.st, 26);  // reduced
-            if (!multi && try_fast && tc[1] <= FR_CAND_CAP) {
-                BracketResult r = bracket_solve2_local(b.cand, td[0] - td[1], (long long)n_samp_in - (long long)tc[0], t_lo, t_hi,
-                                                       sh_sc, cm, nullptr, true, tc[1]);
+            if (!multi && try_fast && tc[1] <= FR2_STREAM_CAP) {
+                BracketResult r = tc[1] <= FR_CAND_CAP
+                                      ? bracket_solve2_local(b.cand, td[0] - td[1], (long long)n_samp_in - (long long)tc[0], t_lo,
+                                                             t_hi, sh_sc, cm, nullptr, true, tc[1])
+                                      : bracket_solve2_stream(b.cand, td[0] - td[1], (long long)n_samp_in - (long long)tc[0], t_lo,
+                                                              t_hi, sh_sc, tc[1]);
                 ex[0] = (unsigned long long)__double_as_longlong(r.x_cut);
                 ex[1] = (unsigned long long)__double_as_longlong(r.R);
                 ex[2] = (unsigned long long)r.nrem | ((unsigned long long)r.rounds << 32);

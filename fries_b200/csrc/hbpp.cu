@@ -268,7 +268,7 @@ static int launch_stage(fries_hbpp *hb, fries_mol *mol, HbStageIO &io, CompSubBu
             hb->grid2 = c->sm_count * ctas;
         }
         static const bool marks = getenv("FRIES_CTA_MARKS") != nullptr;
-        if (marks && !hb->cta_marks.p) FRIES_TRY(hb->cta_marks.alloc((size_t)5 * 8 * 1024));
+        if (marks && !hb->cta_marks.p) FRIES_TRY(hb->cta_marks.alloc((size_t)7 * 8 * 1024));
         CompSubBufs2 b2{bufs, hb->cand_idx.p, hb->gcomb.p, marks ? hb->cta_marks.p + (size_t)S * 8 * 1024 : nullptr};
         void *args2[] = {(void *)&gm, (void *)&io, (void *)&b2, (void *)&n_samp, (void *)&rn};
         CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(hb->grid2), dim3(FR2_NT), args2, smem, c->stream));
@@ -776,17 +776,25 @@ extern "C" int fries_hbpp_timeline(fries_hbpp *hb, int s, double *h_out48) {
 // Diagnostics (FRIES_CTA_MARKS=1): %globaltimer of every CTA at the phase ends of stage s's last run, [8][grid] in ns
 // relative to the earliest CTA's first mark
 extern "C" int fries_hbpp_cta_marks(fries_hbpp *hb, int s, double *h_out, int *grid) {
-    FRIES_REQUIRE(hb && h_out && grid && s >= 0 && s < 5, "fries_hbpp_cta_marks: bad argument");
+    FRIES_REQUIRE(hb && h_out && grid && s >= 0 && s < 7, "fries_hbpp_cta_marks: bad argument");  // 5, 6: the fused vector kernel (marks 0-7, 8-15)
     FRIES_REQUIRE(hb->cta_marks.p && hb->grid2 > 0, "fries_hbpp_cta_marks: set FRIES_CTA_MARKS=1 before the first iteration");
     fries_ctx *c = hb->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    std::vector<unsigned long long> m((size_t)8 * hb->grid2);
+    const int g = s >= 5 ? hb->grid_vp : hb->grid2;
+    FRIES_REQUIRE(g > 0 && g <= 1024, "fries_hbpp_cta_marks: that kernel has not run");
+    std::vector<unsigned long long> m((size_t)8 * g);
     CUDA_TRY(cudaMemcpyAsync(m.data(), hb->cta_marks.p + (size_t)s * 8 * 1024, m.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     unsigned long long t0 = ~0ull;
-    for (int q = 0; q < hb->grid2; q++) t0 = m[q] < t0 ? m[q] : t0;
+    if (s == 6) {  // the second block of the vector kernel's marks counts from the same origin as the first
+        std::vector<unsigned long long> m0((size_t)g);
+        CUDA_TRY(cudaMemcpyAsync(m0.data(), hb->cta_marks.p + (size_t)5 * 8 * 1024, m0.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (int q = 0; q < g; q++) t0 = m0[q] < t0 ? m0[q] : t0;
+    } else
+        for (int q = 0; q < g; q++) t0 = m[q] < t0 ? m[q] : t0;
     for (size_t q = 0; q < m.size(); q++) h_out[q] = m[q] >= t0 ? (double)(m[q] - t0) : -1.0;
-    *grid = hb->grid2;
+    *grid = g;
     return FRIES_OK;
 }
 

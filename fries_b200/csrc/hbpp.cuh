@@ -30,7 +30,8 @@ struct fries_hbpp {
     DevBuf<uint32_t> cand_m, cand_idx;  // cand_idx: input index of every candidate (compress2.cuh)
     DevBuf<KeepPred> pred;
     DevBuf<unsigned long long> gcomb;      // GridComb state of the second-generation stage kernels (gridcomb.cuh)
-    DevBuf<unsigned long long> cta_marks;  // diagnostics: [5 stages][8 marks][grid] (FRIES_CTA_MARKS=1)
+    DevBuf<unsigned long long> cta_marks;  // diagnostics: [5 stages + vec_phase][8 marks][grid] (FRIES_CTA_MARKS=1)
+    int grid_vp = 0;                       // grid of the last vec_phase launch
     // frisys/frifull driver state (iter.cu)
     DevBuf<uint64_t> trial_keys, htrial_keys, spawn_keys;
     DevBuf<double> trial_vals, htrial_vals, spawn_vals, scal;

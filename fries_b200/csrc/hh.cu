@@ -323,3 +323,127 @@ extern "C" int fries_frisys_hh_iterate(fries_vec *vec, fries_hbpp *hb, const fri
     }
     return FRIES_OK;
 }
+
+// ---- frifull_hh (FRIES_bin/frifull_hh.cpp:186-330): no matrix compression -- every state spawns all of its hops
+// (hub_all hub_holstein.cpp:83-98) and phonon moves (:224-257) ----------------------------------------------------------
+// One thread per parent; a parent owns `slots` = 4 * n_elec consecutive places of the spawn window (2 hops per electron at
+// most, one phonon creation and one annihilation per up electron and per down electron on a singly occupied site), unused
+// places carry the empty key.  Elements of value 0 (elec_ph = 0) are not spawned: the reference adds them as zeros.
+__global__ void hh_full_spawn_kernel(VecView v, HhDims d, size_t first, size_t count, unsigned slots, double eps, double hub_t,
+                                     double elec_ph, double init_thresh, uint64_t *out_keys, double *out_vals,
+                                     unsigned long long *n_spawned) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long ok = 0;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < count; q += stride) {
+        const size_t i = first + q;
+        uint64_t *ok_ = out_keys + q * slots;
+        double *ov = out_vals + q * slots;
+        unsigned w = 0;
+        const double cv = v.vals[i];
+        if (cv != 0) {
+            const uint64_t key = v.keys[i];
+            const uint64_t ini = fabs(cv) > init_thresh ? FRIES_INI_FLAG : 0ull;
+            auto put = [&](uint64_t nk, double el) {
+                if (el != 0 && w < slots) {
+                    ok_[w] = nk | ini;
+                    ov[w] = el;
+                    w++;
+                }
+            };
+            uint64_t plus, minus;
+            hh_neighbors(key, d.n_sites, plus, minus);
+            for (uint64_t mk = plus; mk; mk &= mk - 1) {
+                const unsigned orig = (unsigned)fr_ctz(mk);
+                put((key & ~(1ull << orig)) | (1ull << (orig + 1)), eps * hub_t * cv);
+            }
+            for (uint64_t mk = minus; mk; mk &= mk - 1) {
+                const unsigned orig = (unsigned)fr_ctz(mk);
+                put((key & ~(1ull << orig)) | (1ull << (orig - 1)), eps * hub_t * cv);
+            }
+            const uint64_t site_mask = (1ull << d.n_sites) - 1;
+            const uint64_t up = key & site_mask, dn = (key >> d.n_sites) & site_mask;
+            for (uint64_t mk = up; mk; mk &= mk - 1) {  // :224-238
+                const unsigned site = (unsigned)fr_ctz(mk);
+                const unsigned ph = hh_phonon(key, d, site);
+                const int docc = (int)((dn >> site) & 1ull);
+                const unsigned shift = 2 * d.n_sites + site * d.ph_bits;
+                if (ph > 0) put(key - (1ull << shift), -eps * elec_ph * sqrt((double)ph) * (docc + 1) * cv);
+                if (ph + 1 < (1u << d.ph_bits)) put(key + (1ull << shift), -eps * elec_ph * sqrt((double)(ph + 1)) * (docc + 1) * cv);
+            }
+            for (uint64_t mk = dn & ~up; mk; mk &= mk - 1) {  // :240-256: down electrons on singly occupied sites
+                const unsigned site = (unsigned)fr_ctz(mk);
+                const unsigned ph = hh_phonon(key, d, site);
+                const unsigned shift = 2 * d.n_sites + site * d.ph_bits;
+                if (ph > 0) put(key - (1ull << shift), -eps * elec_ph * sqrt((double)ph) * cv);
+                if (ph + 1 < (1u << d.ph_bits)) put(key + (1ull << shift), -eps * elec_ph * sqrt((double)(ph + 1)) * cv);
+            }
+        }
+        ok += w;
+        for (; w < slots; w++) {
+            ok_[w] = FRIES_EMPTY_KEY;
+            ov[w] = 0.0;
+        }
+    }
+    ok = warp_sum_u64(ok);
+    if ((threadIdx.x & 31) == 0 && ok) atomicAdd(n_spawned, ok);
+}
+
+extern "C" int fries_frifull_hh_iterate(fries_vec *vec, fries_hbpp *hb, const fries_frisys_hh_params *p, double uniform,
+                                        fries_iter_stats *stats) {
+    FRIES_REQUIRE(vec && hb && p && vec->hh_sites, "fries_frifull_hh_iterate: bad argument");
+    FRIES_REQUIRE(vec->n_ranks == 1, "fries_frifull_hh_iterate: single-rank entry point");
+    fries_ctx *c = vec->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    HhDims d{vec->hh_sites, vec->n_elec, vec->hh_ph_bits};
+    const unsigned slots = 4 * vec->n_elec;
+    FRIES_REQUIRE(hb->cap >= slots, "fries_frifull_hh_iterate: spawn window smaller than one state's %u moves", slots);
+    CUDA_TRY(cudaMemsetAsync(hb->st.p, 0, 8 * sizeof(CompState), c->stream));
+    const double hub_t = 1;
+    VecCounters cnt;
+    FRIES_TRY(vec->read_counters(&cnt));
+    const size_t n_parents = (size_t)cnt.n, win = hb->cap / slots;
+    // the parents are the states stored before the multiplication (:193-196); what the merges append has value 0 in row 0
+    for (size_t first = 0; first < n_parents; first += win) {
+        const size_t count = n_parents - first < win ? n_parents - first : win;
+        VecView v = vec->view();
+        {
+            ProfScope ps(c, "hh_full_spawn");
+            hh_full_spawn_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(v, d, first, count, slots, p->eps, hub_t, p->elec_ph,
+                                                                          p->init_thresh, hb->spawn_keys.p, hb->spawn_vals.p,
+                                                                          &hb->st.p[5].n_out);
+            c->launch_count++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        FRIES_TRY(fries_vec_merge_dev(vec, hb->spawn_keys.p, hb->spawn_vals.p, count * slots, nullptr, 0, 1));
+    }
+    VecView v = vec->view();
+    hh_diag_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(v, d, p->eps, p->hub_u, p->ph_freq, p->hf_en, p->en_shift);
+    c->launch_count++;
+    FRIES_TRY(fries_find_preserve_launch(c, v.vals, vec->cap, &vec->cnt.p->n, p->target_nonz, hb->keep_flags.p, hb->st.p + 6,
+                                         hb->part_d.p, hb->part_c.p, 0, nullptr, hb->pred.p + 5, hb->cand_x.p,
+                                         hb->cand_m.p));
+    hh_state_to_r4<<<1, 1, 0, c->stream>>>(hb->st.p + 6, hb->scal.p);
+    hh_energy_kernel<<<1, 1024, 0, c->stream>>>(v, d, p->ref_key, p->elec_ph / hub_t, hub_t, p->hub_u, p->hf_en, hb->scal.p + 4);
+    c->launch_count += 2;
+    FRIES_TRY(fries_sys_comp_launch(c, v.vals, vec->cap, &vec->cnt.p->n, hb->keep_flags.p, hb->scal.p, 0.0, 0.0, -1LL, uniform,
+                                    hb->st.p + 7, hb->part_d.p, hb->part_c.p, 0, nullptr));
+    FRIES_TRY(fries_vec_compact_flags_dev(vec, hb->keep_flags.p));
+    hh_stats_kernel<<<1, 1, 0, c->stream>>>(hb->st.p, vec->cnt.p, hb->scal.p, hb->scal.p + 8);
+    c->launch_count++;
+    CUDA_TRY(cudaMemcpyAsync(c->h_pinned, hb->scal.p + 8, 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const double *h = c->h_pinned;
+    if (stats) {
+        stats->glob_norm = h[0];
+        stats->numer = h[1];
+        stats->denom = h[2];
+        stats->n_kept = (uint64_t)h[3];
+        stats->n_matrix_samples = stats->n_spawned = (uint64_t)h[4];
+        stats->curr_size = (uint64_t)h[5];
+    }
+    if (h[7] != 0) {
+        fries_set_error("fries_frifull_hh_iterate: determinant store is full (capacity %zu)", vec->cap);
+        return FRIES_ERR_CAPACITY;
+    }
+    return FRIES_OK;
+}

@@ -564,12 +564,105 @@ extern "C" int fries_piv_comp(fries_ctx *c, double *h_values, size_t count, uint
 // method 1: find_preserve + sys_comp with one draw per row), then every element that is zero in ALL rows is deleted
 // (del_at_pos only removes such elements, vec_utils.hpp:458-476, so the reference's del_arr bookkeeping reduces to
 // this).  Single rank.
+// ---- compress_vecs_multi (FRIES/vec_utils.cpp:73-127): multinomial compression of a row with the alias method --------
+// p_i = |v_i / norm| (the sign kept aside), alias table of p (setup_alias, compress_utils.cpp:823-857: a sequential
+// two-stack construction -- on the host, as in the reference: the table decides which draws land where, so it has to be
+// that construction exactly), compress_size draws of two uniforms each (sample_alias :882-897), v_i <- norm * count_i *
+// sign_i / compress_size.
+__global__ void multi_normalise_kernel(double *vals, size_t n, double norm, uint8_t *positive) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double q = vals[i] / norm;
+        positive[i] = q > 0 ? 1 : 0;
+        vals[i] = fabs(q);
+    }
+}
+__global__ void multi_sample_kernel(const uint32_t *__restrict__ aliases, const double *__restrict__ alias_probs, size_t n,
+                                    const uint32_t *__restrict__ draws, uint32_t n_samp, uint32_t *counts) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_samp; k += gridDim.x * blockDim.x) {
+        const uint16_t chosen = (uint16_t)(draws[2 * k] / 4294967296.0 * (double)n);
+        const double u = draws[2 * k + 1] / 4294967296.0;
+        atomicAdd(&counts[u < alias_probs[chosen] ? (uint32_t)chosen : aliases[chosen]], 1u);
+    }
+}
+__global__ void multi_apply_kernel(double *vals, size_t n, double norm, const uint32_t *__restrict__ counts,
+                                   const uint8_t *__restrict__ positive, uint32_t compress_size) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        vals[i] = norm * (double)(uint16_t)counts[i] * (positive[i] ? 1 : -1) / (double)compress_size;
+}
+static void host_setup_alias(const double *probs, uint32_t *aliases, double *alias_probs, size_t n) {
+    std::vector<uint32_t> smaller, bigger;
+    smaller.reserve(n);
+    bigger.reserve(n);
+    for (size_t i = 0; i < n; i++) {
+        aliases[i] = (uint32_t)i;
+        alias_probs[i] = (double)n * probs[i];
+        (alias_probs[i] < 1 ? smaller : bigger).push_back((uint32_t)i);
+    }
+    while (!smaller.empty() && !bigger.empty()) {
+        const uint32_t sidx = smaller.back(), b = bigger.back();
+        aliases[sidx] = b;
+        alias_probs[b] += alias_probs[sidx] - 1;
+        if (alias_probs[b] < 1) {
+            smaller.back() = b;
+            bigger.pop_back();
+        } else {
+            smaller.pop_back();
+        }
+    }
+}
+static int compress_row_multi(fries_vec *vec, unsigned row, size_t n, uint32_t compress_size, const uint32_t *h_draws,
+                              size_t n_draws, size_t *used) {
+    fries_ctx *c = vec->ctx;
+    FRIES_REQUIRE(n <= 65535 && compress_size <= 65535,
+                  "fries_vec_compress (multi): the reference's sample_alias counts in uint16 (%zu states, %u samples)", n,
+                  compress_size);
+    FRIES_REQUIRE(*used + 4 * (size_t)compress_size <= n_draws, "fries_vec_compress (multi): out of draws (4 per sample and row)");
+    if (n == 0) {
+        *used += 4 * (size_t)compress_size;
+        return FRIES_OK;
+    }
+    double norm = 0;
+    FRIES_TRY(fries_vec_local_norm(vec, row, &norm));
+    double *d_vals = vec->vals[vec->cur].p + (size_t)row * vec->cap;
+    DevBuf<uint8_t> positive;
+    DevBuf<uint32_t> aliases, counts, draws;
+    DevBuf<double> aprobs;
+    FRIES_TRY(positive.alloc(n));
+    FRIES_TRY(aliases.alloc(n));
+    FRIES_TRY(counts.alloc(n));
+    FRIES_TRY(aprobs.alloc(n));
+    FRIES_TRY(draws.alloc(2 * (size_t)compress_size + 2));
+    const int grid = c->sm_count * 4;
+    multi_normalise_kernel<<<grid, 256, 0, c->stream>>>(d_vals, n, norm, positive.p);
+    c->launch_count++;
+    std::vector<double> hp(n), hap(n);
+    std::vector<uint32_t> hal(n);
+    CUDA_TRY(cudaMemcpyAsync(hp.data(), d_vals, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // one rank: the reference first spreads the samples over the ranks with a one-state alias table (vec_utils.cpp:101-109),
+    // which consumes two draws per sample and gives this rank all of them
+    *used += 2 * (size_t)compress_size;
+    host_setup_alias(hp.data(), hal.data(), hap.data(), n);
+    CUDA_TRY(cudaMemcpyAsync(aliases.p, hal.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(aprobs.p, hap.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(draws.p, h_draws + *used, 8 * (size_t)compress_size, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(counts.p, 0, n * 4, c->stream));
+    multi_sample_kernel<<<grid, 256, 0, c->stream>>>(aliases.p, aprobs.p, n, draws.p, compress_size, counts.p);
+    c->launch_count++;
+    multi_apply_kernel<<<grid, 256, 0, c->stream>>>(d_vals, n, norm, counts.p, positive.p, compress_size);
+    c->launch_count++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // the staging vectors go out of scope
+    *used += 2 * (size_t)compress_size;
+    return FRIES_OK;
+}
+
 extern "C" int fries_vec_compress(fries_vec *vec, unsigned start_row, unsigned end_row, uint32_t compress_size, int method,
                                   const uint32_t *h_draws, size_t n_draws, size_t *n_draws_used) {
     FRIES_REQUIRE(vec && (h_draws || n_draws == 0), "fries_vec_compress: NULL argument");
     FRIES_REQUIRE(start_row <= end_row && end_row <= vec->n_vecs, "fries_vec_compress: rows [%u, %u) of %u", start_row,
                   end_row, vec->n_vecs);
-    FRIES_REQUIRE(method == 0 || method == 1, "fries_vec_compress: method 0 (pivotal) or 1 (systematic)");
+    FRIES_REQUIRE(method >= 0 && method <= 2, "fries_vec_compress: method 0 (pivotal), 1 (systematic) or 2 (multinomial)");
     FRIES_REQUIRE(vec->n_ranks == 1, "fries_vec_compress: single rank");
     fries_ctx *c = vec->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -589,6 +682,10 @@ extern "C" int fries_vec_compress(fries_vec *vec, unsigned start_row, unsigned e
     FRIES_TRY(piv_scratch(c, grid, s));
     size_t used = 0;
     for (unsigned row = start_row; row < end_row; row++) {
+        if (method == 2) {
+            FRIES_TRY(compress_row_multi(vec, row, n, compress_size, h_draws, n_draws, &used));
+            continue;
+        }
         double *d_vals = vec->vals[vec->cur].p + (size_t)row * vec->cap;
         CUDA_TRY(cudaMemsetAsync(s.st, 0, sizeof(CompState), c->stream));
         FRIES_TRY(fries_find_preserve_launch(c, d_vals, n, nullptr, compress_size, keep.p, s.st, s.pd, s.pc, 0, nullptr));

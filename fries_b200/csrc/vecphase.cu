@@ -9,14 +9,16 @@
 //
 // Here: four passes over the vector, three barriers with payload (gridcomb.cuh), everything four elements per thread.
 //   P1  death / cloning (lazily computed diagonal elements), |v| statistics against the threshold bracket of the previous
-//       iteration (compress.cuh: bracket_solve), keep flags of everything above the bracket, candidates inside it staged
-//       in shared memory
-//   --  barrier A: sums; CTA 0 alone solves the threshold on the candidate list (compress2.cuh: bracket_solve2_local) and
-//       evaluates the two dot products through the still intact index; result in every CTA's line
-//   P2  keep flags of the candidates; residual one-norm of the chunk; the CTA's share of the index is cleared
-//   --  barrier B: residual norm + every chunk's place on the resampling line
-//   P3  systematic resampling in storage order (one block scan per 2048 elements); survivors counted
-//   --  barrier C (with fence: the cleared index): survivor prefix
+//       iteration (compress.cuh: bracket_solve), candidates inside the bracket staged in shared memory; grid-stride over
+//       the elements (the determinants whose diagonal is still to be computed are contiguous at the end of the store)
+//   --  barrier A: sums; the threshold is solved on the candidates -- by CTA 0 alone on a list of <= 4096
+//       (compress2.cuh: bracket_solve2_local; result in every CTA's line), else by every CTA on the candidates it staged,
+//       one more barrier per Newton round.  The preserved set is { |v| >= cut }: no keep flags are stored
+//   P2  residual one-norm of the chunk; the two dot products through the still intact index, trial entry t on CTA t % grid
+//   --  barrier B: residual norm + every chunk's place on the resampling line (+ <H trial|v>)
+//   P3  the CTA's share of the index cleared; systematic resampling in storage order (one block scan per 2048 elements);
+//       survivors counted
+//   --  barrier C (with fence: the cleared index): survivor prefix (+ <trial|v>)
 //   P4  stable compaction into the spare buffers + insertion into the index (four independent probe chains per thread)
 // Without a valid bracket (first iteration, jump of the vector) the plain rounds of find_preserve run instead of the solve.
 // Same arithmetic as the separate kernels (which stay: multi-rank, frifull_mol, the C-ABI's stand-alone entry points);
@@ -32,6 +34,7 @@ extern __shared__ __align__(16) double fr_dyn_smem[];
 #define VP_NT FR2_NT
 #define VP_ITEMS FR2_ITEMS
 #define VP_TILE FR2_TILE
+#define VP_CAND_MASK ((1ull << 40) - 1)
 
 struct VecPhaseArgs {
     VecView v;
@@ -52,7 +55,13 @@ struct VecPhaseArgs {
     CompState *st6, *st7;
     double *scal;  // IterScalars layout (iter.cu): [0..3] R4, [4] numer, [5] denom, [43] dense norm
     int do_death;  // 0: compress only (diagnostics / parity test)
+    unsigned long long *cta_marks;  // diagnostics (may be nullptr): [8][gridDim.x] %globaltimer at the phase ends
 };
+#define VP_MARK(k)                                                                                          \
+    do {                                                                                                    \
+        if (a.cta_marks && threadIdx.x == 0)                                                                \
+            a.cta_marks[((k) < 8 ? (size_t)(k) * gridDim.x : (size_t)8 * 1024 + (size_t)((k)-8) * gridDim.x) + blockIdx.x] = fr_globaltimer(); \
+    } while (0)
 
 template <int MINCTAS>
 __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, VecPhaseArgs a) {
@@ -98,22 +107,29 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
     CandList2 cand{a.cand, a.cand_idx};
     const unsigned n_samp_in = a.target_nonz;
 
+    VP_MARK(0);
     // ---- P1: death / cloning + statistics ----
     double s = 0, s_hi = 0;
     unsigned long long c_hi = 0, n_app = 0;
-    for (size_t base = lo; base < hi; base += VP_TILE) {
+    // Grid-stride over the elements (this pass has no scan): the determinants added by the previous iteration's spawn sit at
+    // the end of the store and are the ones whose diagonal element is still to be computed -- with a contiguous chunk per
+    // CTA the last three CTAs did all of that (P1 ended at 10 us on the median CTA and at 65 us on them; with whole tiles
+    // dealt round-robin still at 43 us; H2O-sized run, round 2).  Consecutive elements now go to consecutive threads of
+    // consecutive CTAs.
+    const size_t gthreads1 = (size_t)gridDim.x * VP_NT, gt1 = (size_t)blockIdx.x * VP_NT + tid;
+    for (size_t base = gt1; base < n; base += (size_t)VP_ITEMS * gthreads1) {
         double av[VP_ITEMS], bv[VP_ITEMS], dv[VP_ITEMS];
 #pragma unroll
         for (int k = 0; k < VP_ITEMS; k++) {
-            const size_t i = base + (size_t)k * VP_NT + tid;
-            av[k] = i < hi ? v0[i] : 0.0;
-            bv[k] = (i < hi && a.do_death) ? v1[i] : 0.0;
-            dv[k] = (i < hi && a.do_death) ? v.diag[i] : 0.0;
+            const size_t i = base + (size_t)k * gthreads1;
+            av[k] = i < n ? v0[i] : 0.0;
+            bv[k] = (i < n && a.do_death) ? v1[i] : 0.0;
+            dv[k] = (i < n && a.do_death) ? v.diag[i] : 0.0;
         }
 #pragma unroll 1
         for (int k = 0; k < VP_ITEMS; k++) {
-            const size_t i = base + (size_t)k * VP_NT + tid;
-            if (i >= hi) break;
+            const size_t i = base + (size_t)k * gthreads1;
+            if (i >= n) break;
             double x = av[k];
             if (a.do_death) {
                 if (x != 0) {
@@ -130,7 +146,6 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
                 v0[i] = x;
                 if (bv[k] != 0) v1[i] = 0;
             }
-            uint8_t flag = 0;
             if (i >= nd) {
                 const double mm = fabs(x);
                 s += mm;
@@ -138,27 +153,28 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
                     if (mm >= t_hi) {
                         c_hi++;
                         s_hi += mm;
-                        flag = 1;
                     } else {
                         cand_stage(stg, cand, cm1, mm, 1u, (uint32_t)i);
                         n_app++;
                     }
                 }
             }
-            a.flags[i] = flag;
         }
     }
     if (try_fast) cand_stage_flush(stg, cand, cm1);
+    VP_MARK(1);
     double pre_d;
-    unsigned long long pre_c, my_cand = 0;
+    unsigned long long pre_c, my_cand = 0, stage_overflows = 0;
     BracketResult br;
     br.valid = false;
     br.n_cand = 0;
     bool have_br = false;
     {
         double dd[2] = {s, s_hi};
+        // the candidate count, and above bit 40 the number of CTAs whose staging area overflowed
         unsigned long long cc[2] = {c_hi, n_app};
         fr2_sum<2>(dd, cc, sh_sd, sh_sc);
+        if (stg.n_stage > FR2_CAND_STAGE) cc[1] |= 1ull << 40;
         const unsigned tag = grid_comb_next_tag(gcur);
         gc_post<2>(gcb, tag, dd, cc, true);
         unsigned long long ex[6] = {0, 0, 0, 0, 0, 0};
@@ -166,7 +182,8 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
             double td[2];
             unsigned long long tc[2];
             gc_reduce<2>(gcb, gsh, tag, td, tc, true);
-            if (try_fast && tc[1] <= FR_CAND_CAP) {
+            // lists beyond one CTA's registers are solved by all CTAs on their own staged candidates (below)
+            if (try_fast && (tc[1] & VP_CAND_MASK) <= FR_CAND_CAP && (tc[1] >> 40) == 0) {
                 BracketResult r = bracket_solve2_local(a.cand, td[0] - td[1], (long long)n_samp_in - (long long)tc[0], t_lo, t_hi,
                                                        sh_sc, cm1, nullptr, true, tc[1]);
                 ex[0] = (unsigned long long)__double_as_longlong(r.x_cut);
@@ -176,36 +193,6 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
                 ex[4] = (r.valid ? 1ull : 0ull) | (1ull << 8);
                 ex[5] = r.n_cand;
             }
-            // step 10, through the index as it is before this iteration's deletions: fixed-order block sums
-            if (a.do_death) {
-                double dots[2];
-                for (int w = 0; w < 2; w++) {
-                    const uint64_t *tk = w ? a.trial_keys : a.htrial_keys;
-                    const double *tv = w ? a.trial_vals : a.htrial_vals;
-                    const unsigned long long nt = w ? a.n_trial : a.n_htrial;
-                    double acc[1] = {0.0};
-                    unsigned long long dum[1] = {0ull};
-                    for (unsigned long long t = tid; t < nt; t += VP_NT) {
-                        uint32_t pos = vec_lookup(v, tk[t], s_scr);
-                        if (pos != FRIES_NO_POS) acc[0] += tv[t] * __ldcg(&v0[pos]);
-                    }
-                    __syncthreads();
-                    fr2_sum<1>(acc, dum, sh_sd, sh_sc);
-                    dots[w] = acc[0];
-                    __syncthreads();
-                }
-                // DistVec::dense_norm vec_utils.hpp:903-917
-                double dn[1] = {0.0};
-                unsigned long long dum[1] = {0ull};
-                for (size_t i = tid; i < nd; i += VP_NT) dn[0] += fabs(__ldcg(&v0[i]));
-                fr2_sum<1>(dn, dum, sh_sd, sh_sc);
-                if (tid == 0) {
-                    a.scal[4] = dots[0];
-                    a.scal[5] = dots[1];
-                    a.scal[43] = dn[0];
-                }
-                __syncthreads();
-            }
             gc_publish<2, 6>(gcb, tag, td, tc, ex);
         }
         gc_wait<2, 6>(gcb, gsh, tag, dd, cc, pre_d, pre_c, ex, true);
@@ -213,7 +200,8 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
         s = dd[0];
         s_hi = dd[1];
         c_hi = cc[0];
-        my_cand = cc[1];
+        my_cand = cc[1] & VP_CAND_MASK;
+        stage_overflows = cc[1] >> 40;
         if ((ex[4] >> 8) == 1) {
             have_br = true;
             br.x_cut = __longlong_as_double((long long)ex[0]);
@@ -225,6 +213,7 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
             br.n_cand = ex[5];
         }
     }
+    VP_MARK(2);
     const double glob_total = s;
     unsigned nrem = n_samp_in;
     double R = 0, thr = INFINITY;
@@ -232,19 +221,88 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
     unsigned long long kept_total = 0, n_cand = 0;
     bool fast_done = false;
     if (try_fast) {
-        if (!have_br)  // the list is longer than one CTA holds: the distributed rounds of bracket_solve, by every CTA
-            br = bracket_solve(grid, a.cand, a.st6->gacc, glob_total - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi,
-                               sh_sd, sh_sc, cm1, nullptr, my_cand <= FR_CAND_GCAP);
-        n_cand = br.n_cand;
-        if (br.valid) {
-            const unsigned nst = stg.n_stage < FR2_CAND_STAGE ? stg.n_stage : FR2_CAND_STAGE;
-            for (unsigned e = tid; e < nst; e += VP_NT) a.flags[stg.ci[e]] = stg.cx[e] >= br.x_cut ? 1 : 0;
-            if (stg.n_stage > FR2_CAND_STAGE) {
-                for (unsigned long long k = tid; k < my_cand; k += VP_NT) {
-                    const size_t i = (size_t)__ldcg(&a.cand_idx[k]);
-                    if (i >= lo && i < hi) a.flags[i] = __ldcg(&a.cand.x[k]) >= br.x_cut ? 1 : 0;
+        if (!have_br && stage_overflows == 0) {
+            // The list is longer than one CTA holds in registers (find_preserve at 1e6 elements brackets 3e4 - 6e4
+            // candidates: the threshold moves by a few 1e-3 between iterations).  Every CTA runs the Newton rounds on the
+            // candidates it staged itself (shared memory), one barrier with payload per round for the exact integer sums --
+            // CTA 0 streaming the whole list from L2 took 75 us, cg's grid.sync rounds of bracket_solve ~30 us (measured
+            // round 2, H2O-sized run).  Same arithmetic as bracket_solve2_local; the cut is the smallest double that passes a
+            // round's test (x -> x * fac is monotone), which selects the same candidates as the smallest kept candidate does.
+            br.n_cand = my_cand;
+            br.valid = false;
+            br.x_cut = t_hi;
+            br.R = glob_total - s_hi;
+            br.nrem = 0;
+            br.kept_cand = 0;
+            br.rounds = 0;
+            const double R0 = glob_total - s_hi;
+            const long long nrem0 = (long long)n_samp_in - (long long)c_hi;
+            const int E_lo = (int)((__double_as_longlong(t_lo) >> 52) & 0x7ff);
+            if (nrem0 > 0 && nrem0 <= 0xffffffffll && t_hi * (double)nrem0 >= R0 && E_lo >= 64 && E_lo <= 1900) {
+                const double ulp_lo = __longlong_as_double((long long)(E_lo - 52) << 52);
+                const unsigned nst = stg.n_stage;  // <= FR2_CAND_STAGE on every CTA
+                unsigned live = 0;                 // bit q: staged candidate tid + q * VP_NT not counted yet
+                for (unsigned q = 0; q * VP_NT < FR2_CAND_STAGE; q++)
+                    if (tid + q * VP_NT < nst) live |= 1u << q;
+                unsigned long long cnt_tot = 0, nrem_r = (unsigned long long)nrem0;
+                unsigned __int128 sum_tot = 0;
+                double R_r = R0, cut = t_hi;
+                bool exhausted = false;
+                for (unsigned round = 0; round < 4096; round++) {
+                    const double fac = (double)nrem_r;
+                    unsigned long long w_lo = 0, w_hi = 0, w_c = 0;
+                    for (unsigned q = 0; q * VP_NT < FR2_CAND_STAGE; q++) {
+                        if (!((live >> q) & 1u)) continue;
+                        const double x = stg.cx[tid + q * VP_NT];
+                        if (x * fac >= R_r) {
+                            live &= ~(1u << q);
+                            const long long xb = __double_as_longlong(x);
+                            const unsigned long long ix = ((unsigned long long)(xb & 0xfffffffffffffll) | (1ull << 52))
+                                                          << ((int)((xb >> 52) & 0x7ff) - E_lo);
+                            w_lo += ix & 0xffffffffull;
+                            w_hi += ix >> 32;
+                            w_c++;
+                        }
+                    }
+                    double rd[2] = {(double)w_c, 0.0};
+                    unsigned long long rc[2] = {w_lo, w_hi};
+                    fr2_sum<2>(rd, rc, sh_sd, sh_sc);
+                    grid_comb<2>(gcb, gsh, gcur, rd, rc, false, false, pre_d, pre_c);
+                    br.rounds = round + 1;
+                    const unsigned long long c_round = (unsigned long long)rd[0];
+                    if (c_round == 0) break;
+                    // smallest x with x * fac >= R_r
+                    double b = R_r / fac;
+                    while (__longlong_as_double(__double_as_longlong(b) - 1) * fac >= R_r) b = __longlong_as_double(__double_as_longlong(b) - 1);
+                    while (b * fac < R_r) b = __longlong_as_double(__double_as_longlong(b) + 1);
+                    cut = fmin(cut, b);
+                    cnt_tot += c_round;
+                    sum_tot += ((unsigned __int128)rc[1] << 32) + rc[0];
+                    if (cnt_tot >= (unsigned long long)nrem0) {
+                        exhausted = true;  // budget exhausted inside the bracket
+                        break;
+                    }
+                    nrem_r = (unsigned long long)nrem0 - cnt_tot;
+                    const double kept_sum = (double)(unsigned long long)(sum_tot >> 64) * 18446744073709551616.0 +
+                                            (double)(unsigned long long)sum_tot;
+                    R_r = R0 - kept_sum * ulp_lo;
+                }
+                if (!exhausted) {
+                    br.x_cut = cut < t_hi ? cut : t_hi;
+                    br.R = R_r;
+                    br.nrem = (unsigned)nrem_r;
+                    br.kept_cand = cnt_tot;
+                    br.valid = t_lo * (double)nrem_r < R_r && cut > t_lo;
                 }
             }
+        } else if (!have_br) {  // a staging area overflowed: the grid-distributed rounds of bracket_solve on the global list
+            br = bracket_solve(grid, a.cand, a.st6->gacc, glob_total - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi,
+                               sh_sd, sh_sc, cm1, nullptr, my_cand <= FR_CAND_GCAP);
+        }
+        n_cand = br.n_cand;
+        if (br.valid) {
+            // the preserved set is { |v| >= x_cut }: everything above the bracket, and the candidates the solve kept
+            // (x_cut is the smallest of them, or the bracket's upper end) -- no per-element keep flag is stored
             kept_total = c_hi + br.kept_cand;
             thr = br.x_cut;
             nrem = br.nrem;
@@ -284,14 +342,12 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
             kept_total += ck[0];
             rounds++;
             if (glob_sampled == 0 && !recalc) {
-                // exact recomputation of the residual norm (:78-90) + the keep flags of the current threshold
+                // exact recomputation of the residual norm (:78-90); the preserved set is { |v| >= thr }
                 double t[1] = {0.0};
                 unsigned long long dum[1] = {0ull};
                 for (size_t i = (lo > nd ? lo : nd) + tid; i < hi; i += VP_NT) {
                     const double mm = fabs(v0[i]);
-                    const bool kp = mm >= thr;
-                    a.flags[i] = kp ? 1 : 0;
-                    if (!kp) t[0] += mm;
+                    if (!(mm >= thr)) t[0] += mm;
                 }
                 fr2_sum<1>(t, dum, sh_sd, sh_sc);
                 grid_comb<1>(gcb, gsh, gcur, t, dum, false, false, pre_d, pre_c);
@@ -309,7 +365,7 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
         keep_pred_update(a.pred, try_fast ? t_pred : 0.0, h_pred, nrem > 0 ? R / nrem : 0.0, n_cand);
     if (R < 1e-9) nrem = 0;  // compress_utils.cpp:94-96
 
-    // ---- P2: residual one-norm of the chunk (fixed order) + this CTA's share of the index cleared ----
+    // ---- P2: residual one-norm of the chunk (fixed order) ----
     double cs = 0;
     for (size_t base = lo; base < hi; base += VP_TILE) {
         const size_t i0 = base + (size_t)tid * VP_ITEMS;
@@ -318,28 +374,43 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
 #pragma unroll
         for (int k = 0; k < VP_ITEMS; k++) {
             const size_t i = i0 + k;
-            const bool live = i < hi && i >= nd && !a.flags[i];
+            const bool live = i < hi && i >= nd && !(fabs(w4[k]) >= thr);
             cs += live ? fabs(w4[k]) : 0.0;
         }
     }
-    {
-        // 16 bytes per store, every thread of the grid; tkeys (8 B) and tpos (4 B) separately
-        const size_t T = (size_t)v.tmask + 1, gthreads = (size_t)gridDim.x * VP_NT, gt = (size_t)blockIdx.x * VP_NT + tid;
-        ulonglong2 *tk2 = reinterpret_cast<ulonglong2 *>(v.tkeys);
-        const ulonglong2 e2 = make_ulonglong2(FRIES_EMPTY_KEY, FRIES_EMPTY_KEY);
-        for (size_t q = gt; q < T / 2; q += gthreads) tk2[q] = e2;
-        uint4 *tp4 = reinterpret_cast<uint4 *>(v.tpos);
-        const uint4 p4 = make_uint4(FRIES_NO_POS, FRIES_NO_POS, FRIES_NO_POS, FRIES_NO_POS);
-        for (size_t q = gt; q < T / 4; q += gthreads) tp4[q] = p4;
+    // step 10 (frisys_mol.cpp:517-520), through the index as it is before this iteration's deletions: trial entry t is looked
+    // up by CTA t % grid (one round of dependent loads per CTA instead of n_trial / 512 rounds on one CTA: 25 us there for the
+    // ~3400 entries of H * HF, H2O-sized run, round 2).  <H trial|v> travels with barrier B, <trial|v> with barrier C.
+    double dot_h = 0, dot_t = 0;
+    if (a.do_death) {
+        const unsigned long long tstep = (unsigned long long)VP_NT * gridDim.x;
+        for (unsigned long long t = blockIdx.x + (unsigned long long)tid * gridDim.x; t < a.n_htrial; t += tstep) {
+            const uint32_t pos = vec_lookup(v, a.htrial_keys[t], s_scr);
+            if (pos != FRIES_NO_POS) dot_h += a.htrial_vals[t] * __ldcg(&v0[pos]);
+        }
+        for (unsigned long long t = blockIdx.x + (unsigned long long)tid * gridDim.x; t < a.n_trial; t += tstep) {
+            const uint32_t pos = vec_lookup(v, a.trial_keys[t], s_scr);
+            if (pos != FRIES_NO_POS) dot_t += a.trial_vals[t] * __ldcg(&v0[pos]);
+        }
+        if (blockIdx.x == 0) {  // DistVec::dense_norm vec_utils.hpp:903-917 (semi-stochastic runs only)
+            double dn[1] = {0.0};
+            unsigned long long dum[1] = {0ull};
+            for (size_t i = tid; i < nd; i += VP_NT) dn[0] += fabs(__ldcg(&v0[i]));
+            if (nd > 0) fr2_sum<1>(dn, dum, sh_sd, sh_sc);
+            if (tid == 0) a.scal[43] = dn[0];
+        }
     }
+    VP_MARK(3);
     double blk_lb, loc_final;
     {
-        double dd[1] = {cs};
-        unsigned long long cc[1] = {0ull};
-        fr2_sum<1>(dd, cc, sh_sd, sh_sc);
-        grid_comb<1>(gcb, gsh, gcur, dd, cc, true, false, blk_lb, pre_c);
+        double dd[2] = {cs, dot_h};
+        unsigned long long cc[2] = {0ull, 0ull};
+        fr2_sum<2>(dd, cc, sh_sd, sh_sc);
+        grid_comb<2>(gcb, gsh, gcur, dd, cc, true, false, blk_lb, pre_c);
         loc_final = dd[0];
+        if (a.do_death && blockIdx.x == 0 && tid == 0) a.scal[4] = dd[1];
     }
+    VP_MARK(4);
     if (nrem == 0) loc_final = 0;
     const double G = loc_final;
     SysGrid sg;
@@ -369,16 +440,26 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
     }
 
     // ---- P3: systematic resampling in storage order ----
+    // (+ this CTA's share of the index cleared: not before barrier B, because P2 reads the index for the dot products;
+    // barrier C orders the clear before P4's insertions)
+    {
+        // 16 bytes per store, every thread of the grid; tkeys (8 B) and tpos (4 B) separately
+        const size_t T = (size_t)v.tmask + 1, gthreads = (size_t)gridDim.x * VP_NT, gt = (size_t)blockIdx.x * VP_NT + tid;
+        ulonglong2 *tk2 = reinterpret_cast<ulonglong2 *>(v.tkeys);
+        const ulonglong2 e2 = make_ulonglong2(FRIES_EMPTY_KEY, FRIES_EMPTY_KEY);
+        for (size_t q = gt; q < T / 2; q += gthreads) tk2[q] = e2;
+        uint4 *tp4 = reinterpret_cast<uint4 *>(v.tpos);
+        const uint4 p4 = make_uint4(FRIES_NO_POS, FRIES_NO_POS, FRIES_NO_POS, FRIES_NO_POS);
+        for (size_t q = gt; q < T / 4; q += gthreads) tp4[q] = p4;
+    }
+    VP_MARK(11);  // index cleared
     double carry = blk_lb, new_norm = 0;
     unsigned long long n_samples = 0, n_surv = 0;
     const double nv = G / nrem;
     double nx4[VP_ITEMS];  // software pipeline: the next tile's loads are issued before this tile's scan and barrier
-    uint8_t nf4[VP_ITEMS];
     {
         const size_t i0 = lo + (size_t)tid * VP_ITEMS;
         fr2_ld4(v0, i0, hi, nx4);
-#pragma unroll
-        for (int k = 0; k < VP_ITEMS; k++) nf4[k] = i0 + k < hi ? a.flags[i0 + k] : 1;
     }
     for (size_t base = lo; base < hi; base += VP_TILE) {
         const size_t i0 = base + (size_t)tid * VP_ITEMS;
@@ -387,14 +468,9 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
 #pragma unroll
         for (int k = 0; k < VP_ITEMS; k++) {
             x4[k] = nx4[k];
-            f4[k] = nf4[k];
+            f4[k] = (i0 + k < hi && !(fabs(nx4[k]) >= thr)) ? 0 : 1;  // preserved exactly (or beyond the chunk)
         }
-        if (base + VP_TILE < hi) {
-            const size_t j0 = i0 + VP_TILE;
-            fr2_ld4(v0, j0, hi, nx4);
-#pragma unroll
-            for (int k = 0; k < VP_ITEMS; k++) nf4[k] = j0 + k < hi ? a.flags[j0 + k] : 1;
-        }
+        if (base + VP_TILE < hi) fr2_ld4(v0, i0 + VP_TILE, hi, nx4);
         double tsum = 0;
 #pragma unroll
         for (int k = 0; k < VP_ITEMS; k++) {
@@ -437,9 +513,10 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
         carry += tot;
         __syncthreads();  // sm_wsum is rewritten by the next tile
     }
+    VP_MARK(5);
     unsigned long long blk_off, total;
     {
-        double dd[2] = {0.0, new_norm};
+        double dd[2] = {dot_t, new_norm};
         unsigned long long cc[2] = {n_surv, n_samples};
         fr2_sum<2>(dd, cc, sh_sd, sh_sc);
         double d0;
@@ -448,9 +525,11 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
         if (blockIdx.x == 0 && tid == 0) {
             a.st7->new_norm = dd[1];
             a.st7->n_out = cc[1];
+            if (a.do_death) a.scal[5] = dd[0];
         }
     }
 
+    VP_MARK(6);
     // ---- P4: stable compaction into the spare buffers + index insertion ----
     unsigned long long ocarry = blk_off;
     for (size_t base = lo; base < hi; base += VP_TILE) {
@@ -471,6 +550,7 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
         for (int k = 0; k < VP_ITEMS; k++) ts += f4[k] ? 0u : 1u;
         unsigned ex, tot;
         fr2_scan_u(ts, ex, tot, sm_wcnt);
+        if (base == lo) VP_MARK(8);  // first tile: loads + scan
         unsigned long long o = ocarry + ex;
         uint64_t slot4[VP_ITEMS];
         uint32_t pos4[VP_ITEMS];
@@ -489,6 +569,7 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
                 key4[k] = FRIES_EMPTY_KEY;
             }
         }
+        if (base == lo) VP_MARK(9);  // first tile: compacted copies stored, slots hashed
         // four independent probe chains per thread
         bool pending = true;
         while (pending) {
@@ -507,9 +588,11 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
                 }
             }
         }
+        if (base == lo) VP_MARK(10);  // first tile: inserted into the index
         ocarry += tot;
         __syncthreads();
     }
+    VP_MARK(7);
     if (blockIdx.x == 0 && tid == 0) v.cnt->n = total;
     grid_comb_end(gcb, gcur);
 }
@@ -559,6 +642,10 @@ int fries_vec_phase_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, double e
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set[ctas - 1] = true;
     }
+    static const bool marks = getenv("FRIES_CTA_MARKS") != nullptr;
+    if (marks && !hb->cta_marks.p) FRIES_TRY(hb->cta_marks.alloc((size_t)7 * 8 * 1024));
+    a.cta_marks = marks ? hb->cta_marks.p + (size_t)5 * 8 * 1024 : nullptr;
+    hb->grid_vp = c->sm_count * ctas;
     MolView gm = mol->view;
     void *args[] = {(void *)&gm, (void *)&a};
     {

@@ -751,6 +751,9 @@ class DistVec {
         buf_ini_.clear();
         host_valid_ = false;
     }
+    // compress_vecs / compress_vecs_sys / compress_vecs_multi FRIES/vec_utils.cpp:10-127 (method 0 / 1 / 2) on rows
+    // [start, end): the generator is advanced by exactly the draws the reference would have consumed
+    void compress_rows(unsigned start, unsigned end, uint32_t compress_size, int method, std::mt19937 &mt_obj);
     void add_vecs(uint8_t idx1, uint8_t idx2, double c = 1.0) { host_valid_ = false; check(fries_vec_row_op(h, 0, idx1, idx2, c)); }   // :547-557
     void copy_vec(uint8_t src, uint8_t dst) { host_valid_ = false; check(fries_vec_row_op(h, 1, dst, src, 0.0)); }                   // :561-565
     void weight_vec(uint8_t idx1, uint8_t idx2, double expo) { host_valid_ = false; check(fries_vec_row_op(h, 2, idx1, idx2, expo)); }  // :569-573
@@ -1043,6 +1046,15 @@ inline std::vector<uint32_t> peek(const std::mt19937 &mt, size_t n) {
     return d;
 }
 }  // namespace detail
+inline void DistVec::compress_rows(unsigned start, unsigned end, uint32_t compress_size, int method, std::mt19937 &mt_obj) {
+    const size_t rows = end > start ? end - start : 0;
+    const size_t per_row = method == 0 ? 2 * (size_t)compress_size + 2 : method == 1 ? 1 : 4 * (size_t)compress_size;
+    std::vector<uint32_t> draws = detail::peek(mt_obj, rows * per_row);
+    size_t used = 0;
+    host_valid_ = false;
+    check(fries_vec_compress(h, start, end, compress_size, method, draws.data(), rows * per_row, &used));
+    mt_obj.discard(used);
+}
 // piv_samp_serial compress_utils.cpp:390-530
 inline void piv_samp_serial(Context &c, double *vec_vals, size_t vec_len, double seg_norm, uint32_t n_samp,
                             std::vector<bool> &keep_exact, std::mt19937 &mt_obj) {

@@ -104,4 +104,25 @@ class DistVec {
     uintmax_t idx_to_hash(uint8_t *idx, uint8_t *orbs) { return dev().idx_to_hash(idx, orbs); }
     virtual int idx_to_proc(uint8_t *idx) { return dev().idx_to_proc(idx); }
     uint64_t tot_sgn_coh() { return dev().tot_sgn_coh(); }
+    // rows [start, end) compressed on the device (the free functions below)
+    void compress_rows_(size_t start, size_t end, unsigned compress_size, int method, std::mt19937 &rn_gen) {
+        dev().compress_rows((unsigned)start, (unsigned)end, compress_size, method, rn_gen);
+        snap_ok_ = false;
+    }
 };
+
+// FRIES/vec_utils.cpp:10-127 (declared vec_utils.hpp:1036-1071): compress rows [start_idx, end_idx) of a DistVec to
+// compress_size elements each -- pivotal, systematic, multinomial (alias method) -- and delete what is zero everywhere.
+// The scratch arguments of the reference are unused (the device has its own).
+inline void compress_vecs(DistVec<double> &vectors, size_t start_idx, size_t end_idx, unsigned int compress_size,
+                          std::vector<size_t> &, std::vector<bool> &, std::vector<bool> &, std::mt19937 &rn_gen) {
+    vectors.compress_rows_(start_idx, end_idx, compress_size, 0, rn_gen);
+}
+inline void compress_vecs_sys(DistVec<double> &vectors, size_t start_idx, size_t end_idx, unsigned int compress_size,
+                              std::vector<size_t> &, std::vector<bool> &, std::vector<bool> &, std::mt19937 &rn_gen) {
+    vectors.compress_rows_(start_idx, end_idx, compress_size, 1, rn_gen);
+}
+inline void compress_vecs_multi(DistVec<double> &vectors, size_t start_idx, size_t end_idx, unsigned int compress_size,
+                                std::vector<size_t> &, std::vector<bool> &, std::vector<bool> &, std::mt19937 &rn_gen) {
+    vectors.compress_rows_(start_idx, end_idx, compress_size, 2, rn_gen);
+}

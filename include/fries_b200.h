@@ -126,9 +126,12 @@ int fries_piv_comp(fries_ctx *ctx, double *h_values, size_t count, uint32_t comp
                    const uint32_t *h_draws, size_t *n_draws_used, double *h_loc_norms, int n_ranks, int rank,
                    int preserved, uint32_t n_samp_left);
 
-/* compress_vecs (method 0, pivotal) / compress_vecs_sys (method 1, systematic) FRIES/vec_utils.cpp:10-70 on the resident
- * store: rows [start_row, end_row) are each compressed to compress_size elements, then the elements that are zero in
- * every row are deleted.  Draws as above (method 1: one per row).  Single rank. */
+/* compress_vecs (method 0, pivotal) / compress_vecs_sys (method 1, systematic) FRIES/vec_utils.cpp:10-70 /
+ * compress_vecs_multi (method 2, multinomial with the alias method, :73-127; setup_alias / sample_alias
+ * FRIES/compress_utils.cpp:823-897) on the resident store: rows [start_row, end_row) are each compressed to compress_size
+ * elements (method 2: compress_size samples), then the elements that are zero in every row are deleted.  Draws as above
+ * (method 1: one per row; method 2: four per sample and row, <= 65535 stored elements and samples as in the reference's
+ * uint16 counters).  Single rank. */
 int fries_vec_compress(fries_vec *vec, unsigned start_row, unsigned end_row, uint32_t compress_size, int method,
                        const uint32_t *h_draws, size_t n_draws, size_t *n_draws_used);
 
@@ -306,6 +309,12 @@ int fries_frisys_hh_setup(fries_vec *vec, size_t spawn_cap, fries_hbpp **out);
  * stats: numer/denom as written to projnum.txt/projden.txt (denom = weight of the Neel state) */
 int fries_frisys_hh_iterate(fries_vec *vec, fries_hbpp *hb, const fries_frisys_hh_params *p, const double *h_uniforms3,
                             fries_iter_stats *stats);
+/* frifull_hh loop body FRIES_bin/frifull_hh.cpp:186-330: every stored state spawns all its hops (hub_all
+ * hub_holstein.cpp:83-98) and phonon moves (no matrix compression), then death / cloning, find_preserve, the projected
+ * energy against the Neel state and sys_comp with `uniform`.  Same parameter block (target_nonz = --vec_nonz); the
+ * scratch of fries_frisys_hh_setup with spawn_cap >= 4 * n_elec. */
+int fries_frifull_hh_iterate(fries_vec *vec, fries_hbpp *hb, const fries_frisys_hh_params *p, double uniform,
+                             fries_iter_stats *stats);
 
 /* ---- multi-GPU (one process per GPU; owner = hash_fxn(occ; proc_scrambler) % n_ranks, vec_utils.hpp:373-379) ----
  * Global reductions (sum_mpi compress_utils.hpp:179-231, the loc_norms Allgather) happen INSIDE the kernels through

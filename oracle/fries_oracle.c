@@ -210,6 +210,72 @@ void fo_sys_comp(double *values, size_t count, double *loc_norms, int n_procs, i
 /* adjust_shift compress_utils.cpp:684-693 */
 /* ---- pivotal family ------------------------------------------------------------------- */
 
+/* ---- alias method: setup_alias compress_utils.cpp:823-857, sample_alias (counts) :882-897 ------------------------------
+ * setup: a state whose scaled probability n * p is below 1 is "smaller", the others "bigger"; the last smaller is paired with
+ * the last bigger, which gives up 1 - (its probability) and moves to the smaller stack when that takes it below 1.  probs
+ * and alias_probs may be the same array (vec_utils.cpp:112 calls it in place). */
+void fo_setup_alias(const double *probs, uint32_t *aliases, double *alias_probs, size_t n) {
+    uint32_t *smaller = (uint32_t *)malloc((n + 1) * sizeof(uint32_t)), *bigger = (uint32_t *)malloc((n + 1) * sizeof(uint32_t));
+    size_t n_s = 0, n_b = 0;
+    for (size_t i = 0; i < n; i++) {
+        aliases[i] = (uint32_t)i;
+        alias_probs[i] = (double)n * probs[i];
+        if (alias_probs[i] < 1) smaller[n_s++] = (uint32_t)i;
+        else bigger[n_b++] = (uint32_t)i;
+    }
+    while (n_s > 0 && n_b > 0) {
+        uint32_t sm = smaller[n_s - 1], bg = bigger[n_b - 1];
+        aliases[sm] = bg;
+        alias_probs[bg] += alias_probs[sm] - 1;
+        if (alias_probs[bg] < 1) {
+            smaller[n_s - 1] = bg;
+            n_b--;
+        } else {
+            n_s--;
+        }
+    }
+    free(smaller);
+    free(bigger);
+}
+/* two draws per sample: the column, then the coin between the column's own state and its alias */
+void fo_sample_alias(const uint32_t *aliases, const double *alias_probs, size_t n, uint16_t *counts, uint32_t n_samp,
+                     const uint32_t *draws) {
+    for (uint32_t k = 0; k < n_samp; k++) {
+        uint16_t chosen = (uint16_t)(draws[2 * k] / (1. + UINT32_MAX) * n);
+        if (draws[2 * k + 1] / (1. + UINT32_MAX) < alias_probs[chosen]) counts[chosen]++;
+        else counts[aliases[chosen]]++;
+    }
+}
+/* one row of compress_vecs_multi vec_utils.cpp:73-127 on a single rank: normalise by the one-norm, remember the signs,
+ * spread the samples over the ranks (one state: consumes 2 draws per sample), alias-sample the elements, write
+ * norm * count * sign / compress_size.  Returns the draws consumed (4 per sample). */
+size_t fo_compress_multi_row(double *values, size_t n, uint32_t compress_size, const uint32_t *draws) {
+    double norm = 0;
+    for (size_t i = 0; i < n; i++) norm += fabs(values[i]);   /* DistVec::local_norm vec_utils.hpp:683-689 */
+    uint8_t *pos = (uint8_t *)malloc(n + 1);
+    for (size_t i = 0; i < n; i++) {
+        values[i] /= norm;
+        pos[i] = values[i] > 0;
+        values[i] = fabs(values[i]);
+    }
+    double one = 1.0 / 1.0, one_p;
+    uint32_t one_alias;
+    uint16_t loc = 0;
+    fo_setup_alias(&one, &one_alias, &one_p, 1);
+    fo_sample_alias(&one_alias, &one_p, 1, &loc, compress_size, draws);
+    size_t used = 2 * (size_t)compress_size;
+    uint32_t *aliases = (uint32_t *)malloc((n + 1) * sizeof(uint32_t));
+    uint16_t *counts = (uint16_t *)calloc(n + 1, sizeof(uint16_t));
+    fo_setup_alias(values, aliases, values, n);
+    fo_sample_alias(aliases, values, n, counts, loc, draws + used);
+    used += 2 * (size_t)loc;
+    for (size_t i = 0; i < n; i++) values[i] = norm * counts[i] * (pos[i] ? 1 : -1) / compress_size;
+    free(pos);
+    free(aliases);
+    free(counts);
+    return used;
+}
+
 /* std::mt19937 (the 32-bit Mersenne twister of the C++ standard; the reference draws uniforms as
  * mt() / (1. + UINT32_MAX), compress_utils.cpp:24,436,468): the first n outputs for a seed. */
 void fo_mt19937_fill(uint32_t seed, size_t n, uint32_t *out) {

@@ -57,6 +57,10 @@ size_t fo_comp_sub(const double *values, size_t count, const uint32_t *n_div, co
                    size_t n_sub, const uint16_t *sub_sizes, unsigned n_samp, double rn, double *new_vals,
                    uint64_t *new_idx, unsigned *n_samp_left, double *loc_norm); /* compress_utils.cpp:797-820 */
 /* ---- pivotal family: piv_samp_serial / piv_budget / adjust_probs / piv_comp_parallel ---- */
+void fo_setup_alias(const double *probs, uint32_t *aliases, double *alias_probs, size_t n);   /* compress_utils.cpp:823-857 */
+void fo_sample_alias(const uint32_t *aliases, const double *alias_probs, size_t n, uint16_t *counts, uint32_t n_samp,
+                     const uint32_t *draws);                                                  /* :882-897 */
+size_t fo_compress_multi_row(double *values, size_t n, uint32_t compress_size, const uint32_t *draws); /* vec_utils.cpp:73-127 */
 void fo_mt19937_fill(uint32_t seed, size_t n, uint32_t *out);     /* std::mt19937(seed): first n outputs */
 void fo_piv_samp_serial(double *v, size_t n, double seg_norm, uint32_t n_samp, uint8_t *keep, const uint32_t *draws,
                         size_t *used);                             /* compress_utils.cpp:389-520 */

@@ -578,6 +578,25 @@ void ref_vec_del(void *h, const uint8_t *flags) {
         if (flags[i]) r->vec->del_at_pos(i);
 }
 
+/* compress_vecs_multi vec_utils.cpp:73-127 on rows [start, end) with std::mt19937(seed); setup_alias / sample_alias
+ * compress_utils.cpp:823-897 on plain arrays */
+void ref_vec_compress_multi(void *h, unsigned start, unsigned end, unsigned compress_size, uint32_t seed) {
+    RefVec *r = (RefVec *)h;
+    size_t n = r->vec->curr_size();
+    std::vector<size_t> srt(n + 1);
+    std::vector<bool> keep(n + 1, false), del(n + 1, true);
+    std::mt19937 mt(seed);
+    compress_vecs_multi(*r->vec, start, end, compress_size, srt, keep, del, mt);
+}
+void ref_setup_alias(const double *probs, uint32_t *aliases, double *alias_probs, size_t n) {
+    std::vector<double> p(probs, probs + n);
+    setup_alias(p.data(), aliases, alias_probs, n);
+}
+void ref_sample_alias(uint32_t *aliases, double *alias_probs, size_t n, uint16_t *counts, uint32_t n_samp, uint32_t seed) {
+    std::mt19937 mt(seed);
+    sample_alias(aliases, alias_probs, n, counts, n_samp, mt);
+}
+
 /* ---- a16: h_op_offdiag + h_op_diag (SymmERIs variant molecule.cpp:448-665, :205-219) ------------
  * Computes dest = id_fac*v + h_fac*H*v for the list (keys, vals) and returns the result as a list.
  * The diagonal uses diag_matrel - 0 (no HF shift). */

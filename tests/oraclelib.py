@@ -67,6 +67,10 @@ def lib():
             "fo_mol_apply_hbpp_sys": (sz, [vp, u64p, f64p, sz, d, i, f64p, u, sz, f64p, u64p, u8p]),
             "fo_mol_h_apply_list": (sz, [vp, u64p, f64p, sz, d, d, u64p, f64p, sz]),
         }
+        u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+        sig["fo_setup_alias"] = (None, [f64p, u32p, f64p, sz])
+        sig["fo_sample_alias"] = (None, [u32p, f64p, sz, u16p, C.c_uint32, u32p])
+        sig["fo_compress_multi_row"] = (sz, [f64p, sz, C.c_uint32, u32p])
         sig["fo_set_keep_chunk"] = (None, [sz])
         sig["fo_debug_hbpp_stage"] = (sz, [vp, u64p, f64p, sz, d, i, f64p, u, sz, i, f64p, u64p, u8p, u32p])
         for name, (res, args) in sig.items():
@@ -232,6 +236,29 @@ def mt19937(seed, n):
     out = np.zeros(n, np.uint32)
     lib().fo_mt19937_fill(seed, n, out)
     return out
+
+
+def setup_alias(probs):
+    """setup_alias compress_utils.cpp:823-857 -> aliases, alias_probs"""
+    p = np.ascontiguousarray(probs, np.float64)
+    al, ap = np.zeros(p.size, np.uint32), np.zeros(p.size)
+    lib().fo_setup_alias(p, al, ap, p.size)
+    return al, ap
+
+
+def sample_alias(aliases, alias_probs, n_samp, draws):
+    """sample_alias (counts) compress_utils.cpp:882-897 with two draws per sample -> counts"""
+    counts = np.zeros(len(aliases), np.uint16)
+    lib().fo_sample_alias(np.ascontiguousarray(aliases, np.uint32), np.ascontiguousarray(alias_probs, np.float64), len(aliases),
+                          counts, n_samp, np.ascontiguousarray(draws, np.uint32))
+    return counts
+
+
+def compress_multi_row(values, compress_size, draws):
+    """one row of compress_vecs_multi vec_utils.cpp:73-127 (single rank) -> new values, draws consumed"""
+    v = np.array(values, np.float64)
+    used = lib().fo_compress_multi_row(v, v.size, compress_size, np.ascontiguousarray(draws, np.uint32))
+    return v, used
 
 
 def piv_samp_serial(values, seg_norm, n_samp, keep, draws):

@@ -102,6 +102,10 @@ def lib():
         L.ref_vec_nonini_occ_add.argtypes = [C.c_void_p]
         L.ref_vec_dump.argtypes = [C.c_void_p, u64p, f64p, C.c_uint]
         L.ref_vec_del.argtypes = [C.c_void_p, u8p]
+        L.ref_vec_compress_multi.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint32]
+        L.ref_setup_alias.argtypes = [f64p, u32p, f64p, C.c_size_t]
+        L.ref_sample_alias.argtypes = [u32p, f64p, C.c_size_t, np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS"), C.c_uint32,
+                                       C.c_uint32]
         L.ref_mol_h_apply.restype = C.c_size_t
         L.ref_mol_h_apply.argtypes = [C.c_void_p, u64p, f64p, C.c_size_t, C.c_double, C.c_double, C.c_size_t, u32p, u32p,
                                       u64p, f64p, C.c_size_t]

@@ -210,3 +210,38 @@ def test_frisys_hh_driver_energy_and_files(tmp_path):
     if "ref" in res:
         er, sr = res["ref"]
         assert abs(e - er) < 5 * (s + sr) + 1e-3, (e, s, er, sr)
+
+
+# ---- frifull_hh (FRIES_bin/frifull_hh.cpp): no matrix compression.  With a vector budget above the number of states that
+# occur the run is a deterministic power iteration: our driver must reproduce the reference driver's files to their precision.
+HOLSTEIN_PARAMS = "n_elec\n4\nlat_len\n4\nn_dim\n1\neps\n0.01\nU\n2\nomega\n1.0\ng\n0.5\ngs_energy\n-2.0\n"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "frifull_hh")), reason="oracle/_ref/frifull_hh not built")
+@pytest.mark.parametrize("case", ["hubbard", "holstein"])
+def test_frifull_hh_matches_reference(tmp_path, case):
+    pf = str(tmp_path / "params.txt")
+    if case == "hubbard":   # 400 determinants, 300 iterations with the shift engaged
+        open(pf, "w").write(HUBBARD_PARAMS)
+        opts, n_it = ["--target", 1000, "--max_dets", 2000, "--vec_nonz", 1000], 300
+    else:                   # electron-phonon coupling: phonon creation / annihilation moves; the space grows every iteration
+        open(pf, "w").write(HOLSTEIN_PARAMS)
+        opts, n_it = ["--target", 0, "--max_dets", 400000, "--vec_nonz", 300000], 6
+    outs = {}
+    for name, exe in (("ours", os.path.join(OURS, "frifull_hh")), ("ref", os.path.join(REF, "frifull_hh"))):
+        rd = str(tmp_path / name) + "/"
+        os.makedirs(rd)
+        r = run(exe, ["--params_path", pf] + opts + ["--max_iter", n_it, "--result_dir", rd], seed=3)
+        assert "Exception" not in r.stderr, r.stderr[-500:]
+        outs[name] = {f: read_col(rd + f) for f in ("projnum.txt", "projden.txt", "S.txt", "norm.txt")}
+        for f in ("dets0.dat", "vals0.dat", "hash.dat", "params.txt"):
+            assert os.path.exists(rd + f), (name, f)
+        lines = [ln for ln in r.stdout.splitlines() if ", en est: " in ln]
+        assert len(lines) == n_it and ", n_neel: " in lines[-1]
+    for f in ("projnum.txt", "projden.txt", "S.txt", "norm.txt"):
+        a, b = outs["ours"][f], outs["ref"][f]
+        assert a.shape == b.shape, (f, a.shape, b.shape)
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-6), (f, a[:5], b[:5])
+    if case == "hubbard":
+        en = outs["ours"]["projnum.txt"][-1] / outs["ours"]["projden.txt"][-1]
+        assert HUBBARD_EXACT - 1e-6 < en < -0.3   # power iteration from the Neel state: above E0, already most of the way

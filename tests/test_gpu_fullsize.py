@@ -198,3 +198,31 @@ def test_store_merge_properties_1e6(ctx):
     vec.delete(np.ones(vec.curr_size(), np.uint8))
     assert vec.curr_size() == 0
     vec.close()
+
+
+def test_h_apply_3000_parents_against_the_oracle(ctx):
+    """deterministic full H.v (h_op_offdiag molecule.cpp:448-665 + h_op_diag :205-219) at a production-like batch: 3000
+    parents of the N2-sized molecule, ~6e6 connections merged into ~1e6 determinants, against the oracle's H.v (which is
+    pinned to the compiled reference on small batches, tests/test_oracle_vs_ref.py): the same determinants, values to 1e-12."""
+    import fries_b200
+    sm = SynthMol("n2", 7, True)
+    mol = fries_b200.Mol.from_synth(ctx, sm)
+    om = oraclelib.OracleMol(sm)
+    rng = np.random.default_rng(21)
+    n_par = 3000
+    keys = np.unique(np.concatenate([[sm.hf], sm.random_dets(n_par - 1, rng, 0)]).astype(np.uint64))
+    vals = rng.normal(size=keys.size)
+    scr = rng.integers(0, 2**32, sm.n_bits, dtype=np.uint64).astype(np.uint32)
+    vec = fries_b200.Vec(ctx, 1 << 23, sm.n_bits, sm.n_elec, 2, scr, scr)
+    vec.set_diag_mol(mol, 0.0)
+    vec.add(keys, vals, np.ones(keys.size, np.uint8))
+    n_sp = vec.h_apply(mol, 0, 1, 1.0, -0.01)
+    gk, gv = vec.download()
+    ok, ov = om.h_apply(keys, vals, 1.0, -0.01)
+    go = np.argsort(gk)
+    assert np.array_equal(gk[go], ok)  # the oracle returns unique sorted determinants
+    scale = np.abs(ov).max()
+    assert np.allclose(gv[1][go], ov, rtol=1e-12, atol=1e-12 * scale)
+    print(f"H.v of {keys.size} parents: {n_sp} connections, {gk.size} determinants")
+    vec.close()
+    mol.close()

@@ -100,3 +100,54 @@ def test_frisys_mol_driver_on_two_gpus(tmp_path):
         er, sr = blocked_ratio(num, den, burn=200)
         print("reference restarted from the 2-GPU checkpoint:", er, sr)
         assert abs(er - e_corr) < 5 * sr + 2e-3 * abs(e_corr) + 5e-4
+
+
+def test_frifull_mol_driver_on_two_gpus(tmp_path):
+    """frifull_mol's command line on 2 GPUs (fries_launch -n 2; the reference: mpirun -n 2 frifull_mol): with a compression
+    budget above the size of the space the iteration is a deterministic power iteration, so the 2-GPU run must reproduce the
+    1-GPU run's files to their printed precision; the determinants of every rank's checkpoint belong to that rank."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oraclelib
+    from driver_utils import OURS, exact_ground_state, read_col, write_hf_dir
+    from fries_b200.synth import SynthMol
+    from test_gpu_drivers import TINY
+    sm = SynthMol(*TINY)
+    om = oraclelib.OracleMol(sm)
+    e_corr, e_hf, n = exact_ground_state(sm, om)
+    d = str(tmp_path / "hf") + "/"
+    write_hf_dir(d, sm, 0.05, float(e_hf))
+    outs = {}
+    for name, pre in (("two", [os.path.join(OURS, "fries_launch"), "-n", "2"]), ("one", [])):
+        rd = str(tmp_path / name) + "/"
+        os.makedirs(rd)
+        cmd = pre + [os.path.join(OURS, "frifull_mol"), "--hf_path", d, "--vec_nonz", str(4 * n), "--max_dets", str(8 * n),
+                     "--max_iter", "150", "--target", "110", "--result_dir", rd]
+        r = subprocess.run(cmd, env=dict(os.environ, FRIES_SEED="3"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                           timeout=600)
+        assert r.returncode == 0 and "Exception" not in r.stderr, (name, r.stderr[-800:])
+        outs[name] = {f: read_col(rd + f) for f in ("projnum.txt", "projden.txt", "S.txt", "norm.txt")}
+        assert len([ln for ln in r.stdout.splitlines() if ", en est: " in ln]) == 150  # one writer: the owner of HF
+    for f in ("projnum.txt", "projden.txt", "S.txt", "norm.txt"):
+        a, b = outs["two"][f], outs["one"][f]
+        assert a.shape == b.shape and a.size > 0, (f, a.shape, b.shape)
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-6), (f, a[:5], b[:5])
+    en = outs["two"]["projnum.txt"][-1] / outs["two"]["projden.txt"][-1]
+    assert e_corr - 1e-9 < en < 0
+    rd = str(tmp_path / "two") + "/"
+    scr = np.fromfile(rd + "hash.dat", dtype=np.uint32)
+    nb = (2 * sm.n_orb + 7) // 8
+    import fries_b200
+    ctx = fries_b200.Context(0)
+    total = 0
+    for rank in range(2):
+        raw = np.fromfile(rd + f"dets{rank}.dat", dtype=np.uint8).reshape(-1, nb)
+        keys = np.array([int.from_bytes(bytes(row), "little") for row in raw], np.uint64)
+        _, own = fries_b200.hash_owner(ctx, keys, scr, 2)
+        assert np.all(own == rank)
+        total += keys.size
+    assert total == n  # the whole space is populated after 150 applications of H
+    ctx.close()

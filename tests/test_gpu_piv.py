@@ -164,9 +164,9 @@ def test_piv_comp_is_unbiased(ctx):
     assert np.all(np.abs(mean - v) <= 5 * sd + 1e-9 * np.abs(v))
 
 
-@pytest.mark.parametrize("method", ["piv", "sys"])
+@pytest.mark.parametrize("method", ["piv", "sys", "multi"])
 def test_vec_compress_rows(ctx, method):
-    """compress_vecs / compress_vecs_sys (vec_utils.cpp:10-70) on the resident store: rows 1 and 2 of a 3-row vector are
+    """compress_vecs / compress_vecs_sys / compress_vecs_multi (vec_utils.cpp:10-127) on the resident store: rows 1 and 2 of a 3-row vector are
     compressed, row 0 is left alone, and elements that end up zero in all three rows disappear"""
     import fries_b200
     from fries_b200.synth import SynthMol
@@ -183,7 +183,7 @@ def test_vec_compress_rows(ctx, method):
     vec.upload(keys, vals)
     k0, v0 = vec.download()
     assert np.array_equal(k0, keys) and np.array_equal(v0, vals)
-    draws = ol.mt19937(99, 4 * m + 16)
+    draws = ol.mt19937(99, 8 * m + 16)
     used = vec.compress(1, 3, m, draws, method)
     # expected: the oracle row by row on consecutive draws
     exp = vals.copy()
@@ -192,6 +192,9 @@ def test_vec_compress_rows(ctx, method):
     for r in (1, 2):
         if method == "piv":
             ov, ok, u = ol.piv_comp(vals[r], m, draws[o_used:])
+            o_used += u
+        elif method == "multi":
+            ov, u = ol.compress_multi_row(vals[r], m, draws[o_used:])
             o_used += u
         else:
             loc, glob, left, keep = ol.find_preserve(vals[r], m)
@@ -207,6 +210,14 @@ def test_vec_compress_rows(ctx, method):
     full[:, pos] = gv
     assert np.array_equal(full[0], vals[0])
     for r in (1, 2):
+        if method == "multi":
+            # multinomial: every value is a whole number of norm / m quanta; the same draws land on the same elements (the
+            # row's one-norm is summed in another order on the device: the quantum may differ in the last place)
+            assert np.array_equal(full[r] != 0, exp[r] != 0) and 0 < (full[r] != 0).sum() <= m
+            assert np.allclose(full[r], exp[r], rtol=1e-12, atol=0)
+            quanta = np.abs(full[r]) / (np.abs(vals[r]).sum() / m)
+            assert np.allclose(quanta, np.round(quanta), atol=1e-9) and int(np.round(quanta).sum()) == m
+            continue
         assert (full[r] != 0).sum() == m
         if method == "piv":
             loc, glob, left, keep = ol.find_preserve(vals[r], m)
