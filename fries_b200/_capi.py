@@ -114,6 +114,8 @@ def _load():
         "fries_vec_create_hh": (i, [vp, sz, u, u, u, u, vp, vp, i, i, P(vp)]),
         "fries_vec_set_min_del_idx": (i, [vp, sz]),
         "fries_vec_set_dense": (i, [vp, sz]),
+        "fries_vec_set_dense_total": (i, [vp, sz]),
+        "fries_vec_set_deterministic": (i, [vp, i]),
         "fries_hh_batch": (i, [vp, i, vp, vp, sz, u, u, u, C.c_uint64, d, vp]),
         "fries_frisys_hh_setup": (i, [vp, sz, P(vp)]),
         "fries_frisys_hh_iterate": (i, [vp, vp, P(FrisysHhParams), vp, P(IterStats)]),

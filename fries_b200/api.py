@@ -344,6 +344,10 @@ class Vec:
         f = arr(flags, np.uint8)
         check(lib.fries_vec_del(self.h, ptr(f), f.size))
 
+    def set_deterministic(self, on=True):
+        """reproducible merges: append and add in batch order (csrc/vec_det.cu); single rank"""
+        check(lib.fries_vec_set_deterministic(self.h, 1 if on else 0))
+
     def compress(self, start_row, end_row, compress_size, draws, method="piv") -> int:
         """compress_vecs / compress_vecs_sys / compress_vecs_multi vec_utils.cpp:10-127 -> draws consumed"""
         dr = arr(draws, np.uint32)

@@ -245,13 +245,13 @@ struct HvScratch {
 
 // dest <- id_fac * src + h_fac * H * src.  Spawn buffers: hb->spawn_keys / spawn_vals (cap entries).
 static int h_apply_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned src, unsigned dest, double id_fac,
-                       double h_fac, bool do_diag, uint64_t *n_spawned, size_t only_first = 0) {
+                       double h_fac, bool do_diag, uint64_t *n_spawned, size_t only_first = (size_t)-1) {
     fries_ctx *c = vec->ctx;
     FRIES_REQUIRE(src < vec->n_vecs && dest < vec->n_vecs && src != dest, "h_apply: need two different rows");
     VecCounters cnt;
     FRIES_TRY(vec->read_counters(&cnt));
     size_t n_parents = (size_t)cnt.n;
-    if (only_first && only_first < n_parents) n_parents = only_first;  // the dense subspace of a semi-stochastic run
+    if (only_first < n_parents) n_parents = only_first;  // the dense subspace of a semi-stochastic run (may be empty on a rank)
     if (n_spawned) *n_spawned = 0;
     // A rank that stores nothing (every non-owner rank when frifull_mol starts from the Hartree-Fock determinant) has no
     // connection of its own but must still take part in every collective below: the round count, the publish / wait /
@@ -512,7 +512,7 @@ static int compress_vector_dev(fries_vec *vec, fries_hbpp *hb, unsigned row, uns
         dense_norm_kernel<<<1, 256, 0, c->stream>>>(v.vals + (size_t)row * v.cap, nd, hb->scal.p + IterScalars::DENSE_NORM);
         c->launch_count++;
         hb->dense_norm_set = true;
-    } else if (hb->dense_norm_set) {
+    } else if (hb->dense_norm_set || vec->n_ranks > 1) {  // (several ranks: the slot holds the global sum after every iteration)
         CUDA_TRY(cudaMemsetAsync(hb->scal.p + IterScalars::DENSE_NORM, 0, sizeof(double), c->stream));
         hb->dense_norm_set = false;
     }
@@ -654,12 +654,14 @@ __global__ void xrank_stats_kernel(CommView cm, double *scal, const VecCounters 
     comm_sum(cm, sh_x0, numer, b);
     comm_sum(cm, sh_x1, denom, b);
     unsigned long long n_glob = comm_sum_u64(cm, sh_xc);
-    comm_allgather(cm, cur, (double)st[5].n_out, 0.0, cnt->overflow, sh_x0, sh_x1, sh_xc);
-    double spawned;
+    comm_allgather(cm, cur, (double)st[5].n_out, scal[IterScalars::DENSE_NORM], cnt->overflow, sh_x0, sh_x1, sh_xc);
+    double spawned, dense_norm;
     comm_sum(cm, sh_x0, spawned, b);
+    comm_sum(cm, sh_x1, dense_norm, b);  // DistVec::dense_norm vec_utils.hpp:903-917 is a sum over the ranks
     if (threadIdx.x == 0) {
         scal[IterScalars::NUMER] = numer;
         scal[IterScalars::DENOM] = denom;
+        scal[IterScalars::DENSE_NORM] = dense_norm;
         out[0] = (double)n_glob;
         out[1] = spawned;
     }
@@ -676,12 +678,15 @@ extern "C" int fries_frisys_mol_spawn(fries_vec *vec, fries_mol *mol, fries_hbpp
     CUDA_TRY(cudaSetDevice(c->device));
     VecView v = vec->view();
     CUDA_TRY(cudaMemsetAsync(hb->send_counts_ext, 0, (vec->n_ranks + 1) * 8, c->stream));
-    FRIES_TRY(fries_hbpp_stages_dev(hb, mol, v.keys, v.vals, &vec->cnt.p->n, p->p_doub, p->new_hb, u6, p->matr_samp));
-    HbSpawnArgs sp{v.vals, p->eps, p->init_thresh, nullptr, nullptr, vec->n_ranks, v.scr_proc, (uint64_t *)hb->send_buf,
+    // semi-stochastic: only the columns outside this rank's share of the dense subspace are compressed (frisys_mol.cpp:414-419)
+    const size_t nd = vec->n_dense;
+    FRIES_TRY(fries_hbpp_stages_dev(hb, mol, v.keys + nd, v.vals + nd, stochastic_count(vec, hb), p->p_doub, p->new_hb, u6,
+                                    p->matr_samp));
+    HbSpawnArgs sp{v.vals + nd, p->eps, p->init_thresh, nullptr, nullptr, vec->n_ranks, v.scr_proc, (uint64_t *)hb->send_buf,
                    hb->send_counts_ext, (unsigned long long)hb->seg_cap, {nullptr}, vec->rank};
     if (hb->p2p)
         for (int q = 0; q < vec->n_ranks; q++) sp.peer_win[q] = hb->comm->route.win[q];
-    FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, v.keys, p->p_doub, p->new_hb, &sp));
+    FRIES_TRY(fries_hbpp_finalize_dev(hb, mol, v.keys + nd, p->p_doub, p->new_hb, &sp));
     // direct route: the elements are already in their owners' windows; publish counts + epoch flag to the peers
     if (hb->p2p) FRIES_TRY(fries_comm_route_publish(hb->comm, hb->send_counts_ext));
     return FRIES_OK;
@@ -717,6 +722,17 @@ extern "C" int fries_frisys_mol_finish(fries_vec *vec, fries_mol *mol, fries_hbp
     MergeSrc src{(const uint64_t *)hb->recv_buf, nullptr, (size_t)vec->n_ranks * hb->seg_cap, nullptr,
                  (const unsigned long long *)d_recv_counts, hb->seg_cap};
     FRIES_TRY(fries_vec_merge_src_dev(vec, src, 0, 1));
+    // elements that did not fit a send segment (read now: the dense multiplication below reuses the counters)
+    unsigned long long ov = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ov, hb->send_counts_ext + vec->n_ranks, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (vec->n_dense_total) {
+        // deterministic subspace multiplication (frisys_mol.cpp:479-485), collective: every rank routes the connections of
+        // its dense determinants to their owners and merges what it receives (row 0 still holds the values from before)
+        FRIES_REQUIRE(hb->p2p, "the dense subspace on several ranks needs the direct spawn route (fries_hbpp_set_route_p2p)");
+        FRIES_TRY(xrank_barrier(hb));  // the windows are single-buffered: every rank has merged the stochastic spawns
+        FRIES_TRY(h_apply_dev(vec, mol, hb, 0, 1, 0.0, -p->eps, false, nullptr, vec->n_dense));
+        v = vec->view();
+    }
     {
         ProfScope ps(c, "death_axpy");
         death_axpy_kernel<<<c->sm_count * 8, 256, smem, c->stream>>>(mol->view, v, vec->hf_en, p->eps, p->en_shift);
@@ -737,9 +753,6 @@ extern "C" int fries_frisys_mol_finish(fries_vec *vec, fries_mol *mol, fries_hbp
         stats->curr_size = (uint64_t)g[0];          // global number of stored determinants
         stats->n_spawned = stats->n_matrix_samples = (uint64_t)g[1];
     }
-    // elements that did not fit a send segment
-    unsigned long long ov = 0;
-    CUDA_TRY(cudaMemcpyAsync(&ov, hb->send_counts_ext + vec->n_ranks, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (rc == FRIES_OK && ov) {
         fries_set_error("fries_frisys_mol_finish: %llu spawned elements did not fit the send segments (seg_cap %zu)", ov,

@@ -2,12 +2,6 @@
 #include "vec.cuh"
 #include "compress.cuh"
 
-#define FR_VEC_BLOCK 256
-
-__device__ __forceinline__ void load_scr(uint32_t *s_scr, const uint32_t *g_scr) {
-    if (threadIdx.x < 64) s_scr[threadIdx.x] = g_scr[threadIdx.x];
-    __syncthreads();
-}
 
 // ---------------------------------------------------------------------------------------------------
 // merge phase A: find-or-insert.  DistVec::add_elements vec_utils.hpp:606-631 + HashTable::read
@@ -240,6 +234,10 @@ extern "C" int fries_vec_create(fries_ctx *c, size_t capacity, unsigned n_bits, 
     CUDA_TRY(cudaSetDevice(c->device));
     fries_vec *v = new fries_vec();
     v->ctx = c;
+    {
+        const char *e = getenv("FRIES_DETERMINISTIC");
+        v->deterministic = e && e[0] == '1' && e[1] == 0;
+    }
     v->cap = capacity;
     v->n_bits = n_bits;
     v->n_elec = n_elec;
@@ -300,12 +298,29 @@ extern "C" int fries_vec_create_hh(fries_ctx *c, size_t capacity, unsigned n_sit
 // the deterministic subspace -- never deleted, never compressed; their columns of H are applied exactly
 extern "C" int fries_vec_set_dense(fries_vec *vec, size_t n_dense) {
     FRIES_REQUIRE(vec, "fries_vec_set_dense: NULL vector");
-    FRIES_REQUIRE(vec->n_ranks == 1 || n_dense == 0, "fries_vec_set_dense: the dense subspace is single-rank in this build");
     VecCounters cnt;
     FRIES_TRY(vec->read_counters(&cnt));
     FRIES_REQUIRE(n_dense <= cnt.n, "fries_vec_set_dense: %zu exceeds the number of stored determinants", n_dense);
     vec->n_dense = n_dense;
     vec->min_del_idx = n_dense;
+    if (vec->n_ranks == 1) vec->n_dense_total = n_dense;
+    return FRIES_OK;
+}
+// several ranks: the size of the dense subspace over all ranks (the dense multiplication is collective: a rank without
+// dense determinants still receives its share of the others' connections)
+extern "C" int fries_vec_set_dense_total(fries_vec *vec, size_t n_dense_total) {
+    FRIES_REQUIRE(vec, "fries_vec_set_dense_total: NULL vector");
+    FRIES_REQUIRE(n_dense_total >= vec->n_dense, "fries_vec_set_dense_total: %zu is below this rank's %zu", n_dense_total,
+                  vec->n_dense);
+    vec->n_dense_total = n_dense_total;
+    return FRIES_OK;
+}
+
+// Reproducible merges: new determinants are appended and values added in the order of the batch, as the reference's
+// sequential add_elements does (vec_utils.hpp:606-641), instead of in the order the SMs get to them.  One rank only.
+extern "C" int fries_vec_set_deterministic(fries_vec *vec, int on) {
+    FRIES_REQUIRE(vec, "fries_vec_set_deterministic: NULL vector");
+    vec->deterministic = on != 0;
     return FRIES_OK;
 }
 
@@ -337,6 +352,11 @@ int fries_vec_merge_src_dev(fries_vec *vec, const MergeSrc &src, unsigned origin
     FRIES_REQUIRE(origin < vec->n_vecs && dest < vec->n_vecs, "merge: row index out of range");
     const size_t n_max = src.n_max;
     if (n_max == 0) return FRIES_OK;
+    if (vec->deterministic && vec->n_ranks == 1) {  // reproducible variant: batch-order append and additions (vec_det.cu)
+        FRIES_TRY(fries_vec_merge_det_dev(vec, src, origin, dest));
+        CUDA_TRY(cudaGetLastError());
+        return FRIES_OK;
+    }
     FRIES_TRY(vec->slot_scratch.ensure(n_max));
     VecView v = vec->view();
     size_t want = (n_max + FR_VEC_BLOCK - 1) / FR_VEC_BLOCK;

@@ -49,10 +49,14 @@ struct fries_vec {
     DevBuf<uint32_t> scr;  // [0..63] vec scrambler, [64..127] proc scrambler
     DevBuf<VecCounters> cnt;
     DevBuf<uint32_t> slot_scratch;
+    bool deterministic = false;          // reproducible merge (vec_det.cu): append and add in batch order
+    DevBuf<uint32_t> det_u32;            // its scratch
+    DevBuf<uint8_t> det_tmp;
     DevBuf<double> red_d;               // reduction partials
     DevBuf<unsigned long long> red_c;
     size_t min_del_idx = 0;
     size_t n_dense = 0;                  // semi-stochastic: the first n_dense stored determinants form the dense subspace
+    size_t n_dense_total = 0;            // ... summed over the ranks (fries_vec_set_dense_total)
     fries_mol *diag_mol = nullptr;
     double hf_en = 0;
     uint64_t last_spawned = 0;
@@ -112,6 +116,12 @@ __device__ __forceinline__ uint32_t vec_lookup(const VecView &v, uint64_t key, c
 
 // Where a merge reads its (key | INI, value) pairs from: one flat list with an optional device-side count, or
 // the receive buffer of the all-to-all: n_seg segments [keys[seg_cap] | vals[seg_cap]] with per-segment counts.
+#define FR_VEC_BLOCK 256
+__device__ __forceinline__ void load_scr(uint32_t *s_scr, const uint32_t *g_scr) {
+    if (threadIdx.x < 64) s_scr[threadIdx.x] = g_scr[threadIdx.x];
+    __syncthreads();
+}
+
 struct MergeSrc {
     const uint64_t *keys;
     const double *vals;
@@ -141,4 +151,5 @@ struct MergeSrc {
 int fries_vec_merge_dev(fries_vec *vec, const uint64_t *d_keys, const double *d_vals, size_t n_max,
                         const unsigned long long *d_n, unsigned origin, unsigned dest);
 int fries_vec_merge_src_dev(fries_vec *vec, const MergeSrc &src, unsigned origin, unsigned dest);
+int fries_vec_merge_det_dev(fries_vec *vec, const MergeSrc &src, unsigned origin, unsigned dest);  // vec_det.cu
 int fries_vec_compact_dev(fries_vec *vec);

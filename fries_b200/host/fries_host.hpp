@@ -954,34 +954,53 @@ class DistVec {
         fd.write((const char *)bytes.data(), bytes.size());
         std::ofstream fv(path + "vals" + r + ".dat", std::ios::binary);
         fv.write((const char *)vals.data(), vals.size() * sizeof(double));
-        if (rank_ == 0) {  // one entry per rank (:735-745); several ranks: no dense subspace in this version
+        if (rank_ == 0) {  // one entry per rank (:735-745): the sizes fixed by init_dense / load
             std::ofstream fz(path + "dense.txt");
             if (n_ranks_ == 1) {
                 fz << n_dense << "," << '\n';
             } else {
-                for (int r = 0; r < n_ranks_ - 1; r++) fz << 0 << ",";
-                fz << 0 << '\n';
+                for (int r = 0; r < n_ranks_; r++)
+                    fz << (r < (int)dense_sizes.size() ? dense_sizes[r] : 0) << (r + 1 < n_ranks_ ? "," : "\n");
             }
         }
     }
     // DistVec::init_dense vec_utils.hpp:858-897 (single rank): the determinants of the file (read_dets io_utils.cpp:565-586,
     // one integer per determinant) become the first stored elements, with value 0, and are never deleted
-    size_t n_dense = 0;
-    size_t init_dense(const std::string &read_path, const std::string &save_dir) {
+    size_t n_dense = 0;        // this rank's share of the dense subspace
+    size_t n_dense_total = 0;  // over all ranks
+    std::vector<long long> dense_sizes;  // one per rank
+    // Several ranks (rk given): every rank reads the file and keeps the determinants it owns -- the reference reads on rank 0
+    // and routes them through add / perform_add, with the same result: each rank's share comes first in its storage
+    // (:866-873) and dense.txt holds one size per rank (:876-893).
+    size_t init_dense(const std::string &read_path, const std::string &save_dir, const Ranks *rk = nullptr) {
         std::ifstream fdets(read_path);
         if (!fdets.is_open()) throw std::runtime_error("Could not open file: " + read_path);
-        std::vector<uint64_t> dets;
+        std::vector<uint64_t> all_dets, dets;
         long long in_det;
-        while (fdets >> in_det) dets.push_back((uint64_t)in_det);
+        while (fdets >> in_det) all_dets.push_back((uint64_t)in_det);
+        std::vector<double> none(all_dets.size(), 0.0), dummy;
+        owned(all_dets, none, dets, dummy);
         std::vector<double> zeros(dets.size() * n_vecs, 0.0);
         check(fries_vec_set_min_del_idx(h, dets.size()));  // an upload drops all-zero elements beyond this index
         upload(dets, zeros);
         n_dense = dets.size();
         check(fries_vec_set_dense(h, n_dense));
-        std::ofstream dense_f(save_dir + "dense.txt");
-        if (!dense_f.is_open())
-            throw std::runtime_error("Could not load deterministic subspace from file at path " + save_dir + "dense.txt");
-        dense_f << n_dense << "," << '\n';
+        std::vector<long long> sizes{(long long)n_dense};
+        if (rk && rk->n > 1) {
+            std::vector<uint8_t> raw = rk->allgather("dense_sizes", &sizes[0], sizeof(long long));
+            sizes.assign((const long long *)raw.data(), (const long long *)raw.data() + rk->n);
+        }
+        n_dense_total = 0;
+        for (long long z : sizes) n_dense_total += (size_t)z;
+        dense_sizes = sizes;
+        check(fries_vec_set_dense_total(h, n_dense_total));
+        if (!rk || rk->rank == 0) {
+            std::ofstream dense_f(save_dir + "dense.txt");
+            if (!dense_f.is_open())
+                throw std::runtime_error("Could not load deterministic subspace from file at path " + save_dir + "dense.txt");
+            for (long long z : sizes) dense_f << z << ",";
+            dense_f << '\n';
+        }
         return n_dense;
     }
     // DistVec::load vec_utils.hpp:761-844 (single rank): re-hash, drop |v| <= 1e-9
@@ -995,10 +1014,22 @@ class DistVec {
         if (!fv.is_open()) throw std::runtime_error("Error: could not open saved binary vector file at " + path + "vals" + rs + ".dat");
         std::vector<double> all(n * n_vecs, 0.0);
         fv.read((char *)all.data(), all.size() * sizeof(double));
-        {   // sizes of the dense subspaces (one per rank; single rank here): the first n_dense entries are kept as they are
+        {   // sizes of the dense subspaces, one per rank ("a, b, c, "): the first n_dense entries are kept as they are
             std::ifstream fz(path + "dense.txt");
             n_dense = 0;
-            if (fz.is_open()) fz >> n_dense;
+            n_dense_total = 0;
+            dense_sizes.clear();
+            if (fz.is_open()) {
+                std::string tok;
+                for (int r = 0; std::getline(fz, tok, ','); r++) {
+                    size_t start = tok.find_first_not_of(" \t\r\n");
+                    if (start == std::string::npos) break;
+                    const size_t z = (size_t)std::stoull(tok.substr(start));
+                    if (r == rank_) n_dense = z;
+                    n_dense_total += z;
+                    dense_sizes.push_back((long long)z);
+                }
+            }
             if (n_dense > n) n_dense = n;
         }
         std::vector<uint64_t> dets;
@@ -1015,6 +1046,7 @@ class DistVec {
         check(fries_vec_set_min_del_idx(h, n_dense));
         upload(dets, vals);
         if (n_dense) check(fries_vec_set_dense(h, n_dense));
+        check(fries_vec_set_dense_total(h, n_dense_total));
     }
 };
 

@@ -63,8 +63,6 @@ int main(int argc, char *argv[]) {
         std::mt19937 mt_obj(seed);
 
         unsigned spawn_length = matr_samp * 4 / rk.n;  // frisys_mol.cpp:109: spawn_length = matr_samp * 4 / n_procs
-        if (multi && (has_det_space || has_trial))
-            throw std::runtime_error("--det_space and --trial_vec need a single GPU in this version (run without fries_launch)");
         std::vector<uint32_t> proc_scrambler(2 * n_orb), vec_scrambler(2 * n_orb);
         if (has_load) {
             load_proc_hash(load_dir, proc_scrambler);
@@ -99,7 +97,7 @@ int main(int argc, char *argv[]) {
         size_t n_determ = 0;
         if (!has_load) {
             if (has_det_space) {
-                n_determ = sol_vec.init_dense(det_space_path, result_dir);
+                n_determ = sol_vec.init_dense(det_space_path, result_dir, &rk);  // collective: every rank keeps its share
             } else if (rk.rank == 0) {
                 std::ofstream dense_f(result_dir + "dense.txt");
                 if (!dense_f.is_open()) throw std::runtime_error("Error opening file containing sizes of deterministic subspaces");
@@ -166,6 +164,12 @@ int main(int argc, char *argv[]) {
                 tot_dense_h += off[n_determ];
                 check(fries_mol_doub_ex(mol.h, d.data(), n_determ, off.data(), nullptr, 0));
                 tot_dense_h += off[n_determ];
+            }
+            if (multi) {  // sum_mpi over the ranks (frisys_mol.cpp:398)
+                unsigned long long mine = tot_dense_h;
+                std::vector<uint8_t> raw = rk.allgather("dense_h", &mine, sizeof(mine));
+                tot_dense_h = 0;
+                for (int r = 0; r < rk.n; r++) tot_dense_h += ((const unsigned long long *)raw.data())[r];
             }
             if (writer) std::cout << "Elements in dense H: " << tot_dense_h << "\n";
         }

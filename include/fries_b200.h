@@ -291,7 +291,15 @@ int fries_vec_set_min_del_idx(fries_vec *vec, size_t idx); /* DistVec::set_min_d
  * 503-504,533-536): the first n_dense stored determinants are the deterministic subspace.  fries_frisys_mol_iterate
  * then compresses and resamples only the rest, applies the dense determinants' columns of H exactly, and reports the
  * one-norm including the dense part.  Single rank. */
+/* Reproducible merges (off by default; FRIES_DETERMINISTIC=1 in the environment turns it on for every new vector): new
+ * determinants are appended and values added in the order of the batch -- the order of the reference's sequential
+ * DistVec::add_elements (vec_utils.hpp:606-641) -- instead of the order in which the SMs reach them, so that two runs with
+ * one seed agree bit for bit.  Single rank; slower (a scan and a sort of the batch per merge). */
+int fries_vec_set_deterministic(fries_vec *vec, int on);
 int fries_vec_set_dense(fries_vec *vec, size_t n_dense);
+/* Several ranks: each rank's first n_dense stored determinants are its share of the subspace (DistVec::init_dense is
+ * collective, vec_utils.hpp:858-897); n_dense_total = the sum over the ranks (one entry per rank in dense.txt). */
+int fries_vec_set_dense_total(fries_vec *vec, size_t n_dense_total);
 /* what 0: hub_diag hub_holstein.cpp:101-136 -> out[n]; 1: find_neighbors_1D hh_vec.hpp:139-175 as two bit masks per
  * state (hop to orb+1, hop to orb-1) -> out[2n]; 2: per-state terms of calc_ref_ovlp hub_holstein.hpp:93-182 -> out[n] */
 int fries_hh_batch(fries_ctx *ctx, int what, const uint64_t *h_keys, const double *h_vals, size_t n, unsigned n_sites,

@@ -151,3 +151,65 @@ def test_frifull_mol_driver_on_two_gpus(tmp_path):
         total += keys.size
     assert total == n  # the whole space is populated after 150 applications of H
     ctx.close()
+
+
+def test_frisys_mol_det_space_on_two_gpus(tmp_path):
+    """Semi-stochastic frisys_mol on 2 GPUs (--det_space; DistVec::init_dense is collective, vec_utils.hpp:858-897; the
+    dense multiplication frisys_mol.cpp:479-485 routes every rank's exact connections to their owners): dense.txt holds one
+    size per rank, each rank's share of the subspace comes first in its checkpoint, the energy agrees with the exact one."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oraclelib
+    from driver_utils import OURS, exact_ground_state, read_col, write_fcidump, write_vec
+    from fries_b200.synth import SynthMol
+    from test_gpu_drivers import TINY, blocked_ratio
+    sm = SynthMol(*TINY)
+    om = oraclelib.OracleMol(sm)
+    e_corr, e_hf, n = exact_ground_state(sm, om)
+    fd = str(tmp_path / "FCIDUMP")
+    write_fcidump(fd, sm, "D2")
+    hf = np.array([sm.hf], np.uint64)
+    k, v = om.h_apply(hf, np.ones(1), 0.0, 1.0)
+    order = np.argsort(-np.abs(v), kind="stable")
+    dense = [int(sm.hf)] + [int(x) for x in k[order] if int(x) != int(sm.hf)][:24]
+    dp = str(tmp_path / "dense_dets.txt")
+    open(dp, "w").write("\n".join(str(d) for d in dense) + "\n")
+    ip = str(tmp_path / "ini_")
+    others = [(int(a), float(b)) for a, b in zip(k, v) if int(a) != int(sm.hf)]
+    write_vec(ip, [int(sm.hf)] + [a for a, _ in others], [100.0] + [-20.0 * b for _, b in others])
+    rd = str(tmp_path / "two") + "/"
+    os.makedirs(rd)
+    n_it = 5000
+    cmd = [os.path.join(OURS, "fries_launch"), "-n", "2", os.path.join(OURS, "frisys_mol"), "--fcidump_path", fd, "--distribution",
+           "HB_unnorm", "--vec_nonz", "150", "--mat_nonz", "3000", "--max_dets", "20000", "--epsilon", "0.05", "--target", "500",
+           "--max_iter", str(n_it), "--result_dir", rd, "--point_group", "D2", "--det_space", dp, "--ini_vec", ip]
+    r = subprocess.run(cmd, env=dict(os.environ, FRIES_SEED="7"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "Exception" not in r.stderr, r.stderr[-800:]
+    sizes = [int(x) for x in open(rd + "dense.txt").read().replace("\n", "").split(",") if x.strip()]
+    assert len(sizes) == 2 and sum(sizes) == len(dense), sizes
+    dense_h = [ln for ln in r.stdout.splitlines() if ln.startswith("Elements in dense H:")]
+    assert dense_h and int(dense_h[0].split(":")[1]) > 0
+    scr = np.fromfile(rd + "hash.dat", dtype=np.uint32)
+    nb = (2 * sm.n_orb + 7) // 8
+    import fries_b200
+    ctx = fries_b200.Context(0)
+    seen = []
+    for rank in range(2):
+        raw = np.fromfile(rd + f"dets{rank}.dat", dtype=np.uint8).reshape(-1, nb)
+        first = np.array([int.from_bytes(bytes(row), "little") for row in raw[:sizes[rank]]], np.uint64)
+        assert set(int(x) for x in first) <= set(dense)
+        if first.size:
+            _, own = fries_b200.hash_owner(ctx, first, scr, 2)
+            assert np.all(own == rank)
+        seen += [int(x) for x in first]
+    ctx.close()
+    assert sorted(seen) == sorted(dense)
+    num, den = read_col(rd + "projnum.txt"), read_col(rd + "projden.txt")
+    assert len(num) == n_it
+    e, s = blocked_ratio(num, den, burn=1000)
+    print("semi-stochastic on 2 GPUs: exact", e_corr, "ours", e, s)
+    assert abs(e - e_corr) < 5 * s + 2e-3 * abs(e_corr) + 2e-4, (e, s, e_corr)
