@@ -335,7 +335,7 @@ def run_ours(args, cfg):
     params = FrisysParams(eps=cfg["eps"], init_thresh=cfg["initiator"], p_doub=wl["p_doub"],
                           new_hb=1 if cfg["dist"] == "HB_unnorm" else 0, matr_samp=cfg["mat_nonz"],
                           target_nonz=cfg["vec_nonz"], en_shift=0.0)
-    uni = mt_uniforms(1, 6 * (args.warmup + 2 * args.steps + 64)).reshape(-1, 6)
+    uni = mt_uniforms(1, 6 * (args.warmup + 2 * args.steps + 128)).reshape(-1, 6)
     ui = 0
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     if os.environ.get("FRIES_BENCH_NOFLUSH"):  # diagnostic only (how much of an iteration is cold-cache cost); says so in config
@@ -397,6 +397,17 @@ def run_ours(args, cfg):
         stp = vec.frisys_iterate(params, uni[ui]); ui += 1
     ctx.set_profile(0)
     states = vec.states()
+    # how often the threshold brackets of the previous iteration held (a miss falls back to the plain Newton rounds)
+    hit_iters = 40
+    hits = np.zeros(7)
+    fp_rounds = []
+    for _ in range(hit_iters):
+        vec.frisys_iterate(params, uni[ui]); ui += 1
+        st_ = vec.states()
+        hits += st_[:7, 10]
+        fp_rounds.append(int(st_[6, 4]))
+    bracket_hits = {"iterations": hit_iters, "hbpp_stages": [int(x) for x in hits[:5]], "find_preserve": int(hits[6]),
+                    "find_preserve_rounds_max": max(fp_rounds)}
     names = ["hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4", "hbpp_finalize", "merge_insert",
              "merge_accum", "vec_phase", "death_axpy", "find_preserve", "sys_comp", "compact"]
     kern = {}
@@ -436,6 +447,7 @@ def run_ours(args, cfg):
                 "stage_bracket": {"fast": [int(x) for x in states[:5, 10]], "candidates": [int(x) for x in states[:5, 9]]},
                 "find_preserve_bracket": {"fast": int(states[6, 10]), "candidates": int(states[6, 9]),
                                           "rounds": int(states[6, 4])},
+                "bracket_hits": bracket_hits,
                 "stage_phase_us": {"what": "in-kernel %globaltimer of CTA 0: prep, preserved set, line scan, count, emit",
                                    "us": [[round((states[s, 13 + k] - states[s, 12 + k]) / 1e3, 1) for k in range(5)]
                                           for s in range(5)],

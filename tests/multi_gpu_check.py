@@ -80,7 +80,7 @@ def main():
     from fries_b200.multi import piv_comp_parallel
     from test_hostcheck_piv import same_up_to_closing_unit
     shared = oraclelib.mt19937(1234, 2 * world + 8)
-    local = oraclelib.mt19937(77 + rank, 2 * budget + 8)
+    local = oraclelib.mt19937(77 + rank, 2 * (budget + world) + 8)  # the C-ABI wants room for 2 * (compress_size + n_ranks)
     gv, gk, n_drawn, (keep, norms, n_left, used_b), new_norm = piv_comp_parallel(ctx, dist, rank, world, v[lo:hi], budget,
                                                                                 shared, local, dev)
     assert np.array_equal(keep, o_keep[lo:hi]) and n_left == o_left
