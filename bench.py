@@ -318,6 +318,9 @@ def run_ours(args, cfg):
     if os.environ.get("FRIES_NO_BRACKET"):  # diagnostics: the reference's plain rounds in every compression
         check(lib.fries_debug_set_bracket(0))
 
+    if world > 1 and cfg.get("full_hv"):
+        from fries_b200.multi import run_multi_gpu_frifull
+        return run_multi_gpu_frifull(args, cfg, ctx, dist, rank, world, local, prepare_workload, ClockSampler)
     if world > 1:
         from fries_b200.multi import run_multi_gpu_bench
         return run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_workload, ClockSampler,

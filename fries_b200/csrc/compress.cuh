@@ -210,7 +210,8 @@ struct KeepPred {
     double t;       // centre of the next bracket: the last fixed point extrapolated by the last ratio (0: none)
     double h;       // relative half-width of the bracket
     double t_last;  // fixed point of the previous run
-    double e;       // relative prediction error, largest of the recent runs (decays by 0.7 per run)
+    double e;       // relative prediction error, largest of the recent runs (decays by `decay` per run)
+    double decay;   // 0: the width follows the last error only
 };
 
 struct CandList {
@@ -482,11 +483,11 @@ __device__ __forceinline__ void keep_pred_update(KeepPred *p, double t_used, dou
     double e_keep = 0;
     if (t_used > 0 && t_fin > 0) {
         double err = fabs(t_fin / t_used - 1.0);
-        // the width follows the LARGEST recent error, not the last one: the threshold of a 2.4e5-element vector moves by
+        // the width follows the LARGEST recent error (decay 0.7 per run, fries_hbpp_alloc), not the last one: the threshold of a 2.4e5-element vector moves by
         // ~1e-3 between iterations with occasional larger steps, and a bracket sized by one quiet iteration missed the
         // next one often enough to matter (a miss = 10-14 plain rounds, ~70 us; a wider bracket = more candidates, which
         // cost microseconds).  Measured round 2, Ne-sized run.
-        e_keep = fmax(err, 0.7 * p->e);
+        e_keep = fmax(err, p->decay * p->e);
         double steer = h_prev * 2500.0 / (double)(ncand > 0 ? ncand : 1);
         steer = fmin(fmax(steer, 0.5 * h_prev), 1.5 * h_prev);
         h = fmax(6.0 * e_keep, steer);

@@ -25,6 +25,7 @@
 #define FR2_TILE (FR2_NT * FR2_ITEMS)
 #define FR2_NW (FR2_NT / 32)
 
+#define FR2_CAND_MASK ((1ull << 40) - 1)
 #define FR2_CAND_STAGE 1024  // candidates a CTA stages in shared memory before it reserves their place in the global list
 struct StageShared {
     double cx[FR2_CAND_STAGE];             // staged candidates: magnitude, multiplicity, input index
@@ -307,118 +308,6 @@ __device__ __forceinline__ BracketResult bracket_solve2_local(const CandList &cl
     return res;
 }
 
-// The same solve for lists one CTA cannot hold in registers (up to FR2_STREAM_CAP candidates, single rank): the CTA streams
-// the list from L2 once per round (coalesced, eight independent loads in flight per thread) and keeps only one bit per
-// candidate -- "not counted yet".  Measured round 2, H2O-sized run: find_preserve brackets ~35000 candidates and the last
-// HB-PP stage ~18000; with the register variant limited to 4096 those fell to the grid-distributed rounds of bracket_solve
-// (a cooperative grid.sync per round: 18 us in the stage, ~30 us in the vector kernel, all other CTAs waiting).
-// Identical arithmetic (exact integer sums in units of ulp(t_lo)), three words per round because the counts of 65536
-// candidates no longer fit beside the high halves.
-#define FR2_STREAM_PER_THREAD 128
-#define FR2_STREAM_CAP ((unsigned long long)FR2_NT * FR2_STREAM_PER_THREAD)
-__device__ __forceinline__ BracketResult bracket_solve2_stream(const CandList &cl, double R0, long long nrem0, double t_lo,
-                                                               double t_hi, unsigned long long *shc, unsigned long long ncand) {
-    BracketResult res;
-    res.valid = false;
-    res.x_cut = t_hi;
-    res.R = R0;
-    res.nrem = 0;
-    res.kept_cand = 0;
-    res.rounds = 0;
-    res.n_cand = ncand;
-    if (nrem0 <= 0 || nrem0 > 0xffffffffll || ncand > FR2_STREAM_CAP) return res;
-    if (!(t_hi * (double)nrem0 >= R0)) return res;
-    const int E_lo = (int)((__double_as_longlong(t_lo) >> 52) & 0x7ff);
-    if (E_lo < 64 || E_lo > 1900) return res;
-    const double ulp_lo = __longlong_as_double((long long)(E_lo - 52) << 52);
-    const int per = (int)((ncand + FR2_NT - 1) / FR2_NT);
-    unsigned long long st0 = ~0ull, st1 = ~0ull;  // bit k: candidate threadIdx.x + k * FR2_NT is not counted yet
-    unsigned long long *acc = shc;                // [3 rotating buffers][3]
-    unsigned long long *acc_min = shc + 12;
-    if (threadIdx.x < 9) acc[threadIdx.x] = 0;
-    if (threadIdx.x == 9) *acc_min = 0x7ff0000000000000ull;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    unsigned long long cnt_tot = 0;
-    unsigned __int128 sum_tot = 0;
-    double R = R0;
-    unsigned long long nrem = (unsigned long long)nrem0;
-    double xmin = INFINITY;
-    for (unsigned round = 0; round < 4096; round++) {
-        unsigned long long *a = acc + 3 * (round % 3);
-        unsigned long long w_lo = 0, w_hi = 0, w_c = 0;
-        const double fac = (double)nrem;
-        bool big = false;
-        for (int k0 = 0; k0 < per; k0 += 8) {
-            double xx[8];
-            uint32_t mm[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int k = k0 + q;
-                const unsigned long long idx = threadIdx.x + (unsigned long long)k * FR2_NT;
-                const bool live = idx < ncand && (((k < 64 ? st0 >> k : st1 >> (k - 64)) & 1ull) != 0);
-                xx[q] = live ? __ldcg(cl.x + idx) : 0.0;
-                mm[q] = live ? __ldcg(cl.mult + idx) : 0u;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int k = k0 + q;
-                if (mm[q] > 64u) big = true;
-                if (mm[q] != 0u && xx[q] * fac >= R) {
-                    if (k < 64) st0 &= ~(1ull << k);
-                    else st1 &= ~(1ull << (k - 64));
-                    const long long xb = __double_as_longlong(xx[q]);
-                    const unsigned long long ix = ((unsigned long long)(xb & 0xfffffffffffffll) | (1ull << 52))
-                                                  << ((int)((xb >> 52) & 0x7ff) - E_lo);
-                    const unsigned long long p = ix * mm[q];
-                    w_lo += p & 0xffffffffull;
-                    w_hi += p >> 32;
-                    w_c += mm[q];
-                    xmin = fmin(xmin, xx[q]);
-                }
-            }
-        }
-        if (round == 0 && __syncthreads_or(big)) return res;  // a multiplicity that does not fit: plain rounds
-        if (__any_sync(0xffffffffu, w_c != 0)) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                w_lo += __shfl_xor_sync(0xffffffffu, w_lo, o);
-                w_hi += __shfl_xor_sync(0xffffffffu, w_hi, o);
-                w_c += __shfl_xor_sync(0xffffffffu, w_c, o);
-            }
-            if (lane == 0) {
-                atomicAdd(&a[0], w_lo);
-                atomicAdd(&a[1], w_hi);
-                atomicAdd(&a[2], w_c);
-            }
-        }
-        if (threadIdx.x < 3) acc[3 * ((round + 1) % 3) + threadIdx.x] = 0;
-        __syncthreads();
-        res.rounds = round + 1;
-        const unsigned long long t_lo64 = a[0], hi_round = a[1], c_round = a[2];
-        if (c_round == 0) break;
-        cnt_tot += c_round;
-        sum_tot += ((unsigned __int128)hi_round << 32) + t_lo64;
-        if (cnt_tot >= (unsigned long long)nrem0) return res;  // budget exhausted inside the bracket
-        nrem = (unsigned long long)nrem0 - cnt_tot;
-        double kept_sum = (double)(unsigned long long)(sum_tot >> 64) * 18446744073709551616.0 +
-                          (double)(unsigned long long)sum_tot;
-        R = R0 - kept_sum * ulp_lo;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-    if (lane == 0 && xmin < INFINITY) atomicMin(acc_min, (unsigned long long)__double_as_longlong(xmin));
-    __syncthreads();
-    xmin = __longlong_as_double((long long)*acc_min);
-    __syncthreads();
-    res.x_cut = xmin < t_hi ? xmin : t_hi;
-    res.R = R;
-    res.nrem = (unsigned)nrem;
-    res.kept_cand = cnt_tot;
-    res.valid = t_lo * (double)nrem < R;
-    return res;
-}
-
 // every CTA solves (multi-rank, or lists beyond one CTA's registers: the distributed rounds of bracket_solve)
 __device__ __forceinline__ BracketResult bracket_solve2(cg::grid_group &grid, const CandList &cl, unsigned long long *gacc,
                                                         double R0, long long nrem0, double t_lo, double t_hi, double *shd,
@@ -476,6 +365,86 @@ __device__ __forceinline__ void cand_stage_flush(StageShared &sm, const CandList
             cl.base.mult[k] = sm.cm[e];
         }
     }
+}
+
+// The solve for lists beyond one CTA's registers, single rank: every CTA runs the Newton rounds on the candidates it staged
+// itself (shared memory; no CTA's staging area may have overflowed), one barrier with payload per round for the exact
+// integer sums.  CTA 0 streaming the whole list from L2 took 75 us for 6e4 candidates, cg's grid.sync rounds of
+// bracket_solve ~30 us (measured round 2, H2O-sized run); this is ~5 us per round.  Same arithmetic as
+// bracket_solve2_local; the cut is the smallest double that passes a round's test (x -> x * fac is monotone), which
+// selects the same candidates as the smallest kept candidate does.  Every thread of every CTA calls it.
+__device__ __forceinline__ BracketResult bracket_solve_staged(const StageShared &stg, const GridComb &gcb, GridCombShared &gsh,
+                                                              GridCombCursor &gcur, double R0, long long nrem0, double t_lo,
+                                                              double t_hi, double *sh_sd, unsigned long long *sh_sc,
+                                                              unsigned long long ncand) {
+    BracketResult br;
+    br.n_cand = ncand;
+    br.valid = false;
+    br.x_cut = t_hi;
+    br.R = R0;
+    br.nrem = 0;
+    br.kept_cand = 0;
+    br.rounds = 0;
+    const int tid = threadIdx.x;
+    const int E_lo = (int)((__double_as_longlong(t_lo) >> 52) & 0x7ff);
+    if (!(nrem0 > 0 && nrem0 <= 0xffffffffll && t_hi * (double)nrem0 >= R0 && E_lo >= 64 && E_lo <= 1900)) return br;
+    const double ulp_lo = __longlong_as_double((long long)(E_lo - 52) << 52);
+    const unsigned nst = stg.n_stage;  // <= FR2_CAND_STAGE on every CTA
+    unsigned live = 0;                 // bit q: staged candidate tid + q * FR2_NT not counted yet
+    bool big = false;
+    for (unsigned q = 0; q * FR2_NT < FR2_CAND_STAGE; q++)
+        if (tid + q * FR2_NT < nst) {
+            live |= 1u << q;
+            if (stg.cm[tid + q * FR2_NT] > 64u) big = true;  // its integer weight would not fit 60 bits: plain rounds
+        }
+    unsigned long long cnt_tot = 0, nrem_r = (unsigned long long)nrem0;
+    unsigned __int128 sum_tot = 0;
+    double R_r = R0, cut = t_hi, pre_d;
+    unsigned long long pre_c;
+    for (unsigned round = 0; round < 4096; round++) {
+        const double fac = (double)nrem_r;
+        unsigned long long w_lo = 0, w_hi = 0, w_c = 0;
+        for (unsigned q = 0; q * FR2_NT < FR2_CAND_STAGE; q++) {
+            if (!((live >> q) & 1u)) continue;
+            const double x = stg.cx[tid + q * FR2_NT];
+            if (x * fac >= R_r) {
+                live &= ~(1u << q);
+                const unsigned mu = stg.cm[tid + q * FR2_NT];
+                const long long xb = __double_as_longlong(x);
+                const unsigned long long ix = ((unsigned long long)(xb & 0xfffffffffffffll) | (1ull << 52))
+                                              << ((int)((xb >> 52) & 0x7ff) - E_lo);
+                const unsigned long long p = ix * mu;
+                w_lo += p & 0xffffffffull;
+                w_hi += p >> 32;
+                w_c += mu;
+            }
+        }
+        double rd[2] = {(double)w_c, (round == 0 && big) ? 1.0 : 0.0};
+        unsigned long long rc[2] = {w_lo, w_hi};
+        fr2_sum<2>(rd, rc, sh_sd, sh_sc);
+        grid_comb<2>(gcb, gsh, gcur, rd, rc, false, false, pre_d, pre_c);
+        br.rounds = round + 1;
+        if (round == 0 && rd[1] != 0.0) return br;  // some CTA holds a multiplicity that does not fit
+        const unsigned long long c_round = (unsigned long long)rd[0];
+        if (c_round == 0) break;
+        double bnd = R_r / fac;  // smallest x with x * fac >= R_r
+        while (__longlong_as_double(__double_as_longlong(bnd) - 1) * fac >= R_r) bnd = __longlong_as_double(__double_as_longlong(bnd) - 1);
+        while (bnd * fac < R_r) bnd = __longlong_as_double(__double_as_longlong(bnd) + 1);
+        cut = fmin(cut, bnd);
+        cnt_tot += c_round;
+        sum_tot += ((unsigned __int128)rc[1] << 32) + rc[0];
+        if (cnt_tot >= (unsigned long long)nrem0) return br;  // budget exhausted inside the bracket
+        nrem_r = (unsigned long long)nrem0 - cnt_tot;
+        const double kept_sum = (double)(unsigned long long)(sum_tot >> 64) * 18446744073709551616.0 +
+                                (double)(unsigned long long)sum_tot;
+        R_r = R0 - kept_sum * ulp_lo;
+    }
+    br.x_cut = cut < t_hi ? cut : t_hi;
+    br.R = R_r;
+    br.nrem = (unsigned)nrem_r;
+    br.kept_cand = cnt_tot;
+    br.valid = t_lo * (double)nrem_r < R_r && cut > t_lo;
+    return br;
 }
 
 struct CompSubBufs2 {
@@ -552,7 +521,10 @@ __device__ __forceinline__ void fr2_apply_cut(P &prov, const CompSubBufs &b, siz
     }
 }
 
-template <class P>
+// MULTI = false: a build without the cross-rank code (the exchanges, the remote candidate stores, the redundant solve) --
+// the single-rank kernels are ~30 % smaller, which the instruction cache notices (no-instruction stalls were 18 % of the
+// stall samples of a 450 kB stage kernel with two CTAs per SM in different phases, ncu round 2).
+template <bool MULTI, class P>
 __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_samp_in, double rn_uniform) {
     const CompSubBufs &b = b2.b;
     cg::grid_group grid = cg::this_grid();
@@ -591,7 +563,7 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
     __shared__ unsigned long long sh_seg[FR_MAX_RANKS];
     const CommView &cm = b.cm;
     CommCursor cur = comm_begin(cm);
-    const bool multi = cm.n_ranks > 1;
+    const bool multi = MULTI && cm.n_ranks > 1;
     CandList2 cand{b.cand, b2.cand_idx};
 
     FR_STAMP(b.st, 0);
@@ -678,15 +650,16 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
     cand_flush(cm, try_fast);
     double pre_d;
     unsigned long long pre_c;
-    unsigned long long my_cand = 0;
+    unsigned long long my_cand = 0, stage_overflows = 0;
     BracketResult br;
     br.valid = false;
     br.n_cand = 0;
     bool have_br = false;  // the solve ran on CTA 0 and its result came with the reduction
     {
         double dd[2] = {s, s_hi};
-        unsigned long long cc[2] = {c_hi, n_app};
+        unsigned long long cc[2] = {c_hi, n_app};  // above bit 40 of the count: CTAs whose staging area overflowed
         fr2_sum<2>(dd, cc, sh_sd, sh_sc);
+        if (sm.stg.n_stage > FR2_CAND_STAGE) cc[1] |= 1ull << 40;
         FR_TL(b.st, 2);  // CTA sum done
         FR2_CTA_MARK(b2, 1);
         // one barrier with payload: the sums, and -- single rank, list within one CTA's registers -- the threshold solve
@@ -701,12 +674,9 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
             FR_TL(b.st, 25);  // posted
             gc_reduce<2>(gcb, gsh, tag, td, tc, true);
             FR_TL(b.st, 26);  // reduced
-            if (!multi && try_fast && tc[1] <= FR2_STREAM_CAP) {
-                BracketResult r = tc[1] <= FR_CAND_CAP
-                                      ? bracket_solve2_local(b.cand, td[0] - td[1], (long long)n_samp_in - (long long)tc[0], t_lo,
-                                                             t_hi, sh_sc, cm, nullptr, true, tc[1])
-                                      : bracket_solve2_stream(b.cand, td[0] - td[1], (long long)n_samp_in - (long long)tc[0], t_lo,
-                                                              t_hi, sh_sc, tc[1]);
+            if (!multi && try_fast && (tc[1] & FR2_CAND_MASK) <= FR_CAND_CAP && (tc[1] >> 40) == 0) {
+                BracketResult r = bracket_solve2_local(b.cand, td[0] - td[1], (long long)n_samp_in - (long long)tc[0], t_lo, t_hi,
+                                                       sh_sc, cm, nullptr, true, tc[1]);
                 ex[0] = (unsigned long long)__double_as_longlong(r.x_cut);
                 ex[1] = (unsigned long long)__double_as_longlong(r.R);
                 ex[2] = (unsigned long long)r.nrem | ((unsigned long long)r.rounds << 32);
@@ -724,7 +694,8 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
         s = dd[0];
         s_hi = dd[1];
         c_hi = cc[0];
-        my_cand = cc[1];  // candidates this rank appended (may exceed the capacity: then the bracket is invalid)
+        my_cand = cc[1] & FR2_CAND_MASK;  // candidates this rank appended (may exceed the capacity: then the bracket is invalid)
+        stage_overflows = cc[1] >> 40;
         if ((ex[4] >> 8) == 1) {
             have_br = true;
             br.x_cut = __longlong_as_double((long long)ex[0]);
@@ -765,9 +736,12 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
     unsigned long long kept_total = 0, n_cand = 0;
     bool fast_done = false;
     if (try_fast) {
-        if (!have_br)
+        if (!have_br && multi)
             br = bracket_solve2(grid, b.cand, b.st->gacc, s - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi, sh_sd, sh_sc,
                                 cm, sh_seg, peers_ok, my_cand);
+        else if (!have_br && stage_overflows == 0)  // single rank, a list beyond one CTA's registers
+            br = bracket_solve_staged(sm.stg, gcb, gsh, gcur, s - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi, sh_sd,
+                                      sh_sc, my_cand);
         n_cand = br.n_cand;
         FR_STAMP(b.st, 6);
         FR_TL(b.st, 4);  // solve done
@@ -1185,7 +1159,7 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
     }
     FR2_CTA_MARK(b2, 5);
     grid_comb_end(gcb, gcur);
-    if (cm.n_ranks > 1) grid.sync();
+    if (multi) grid.sync();
     FR_STAMP(b.st, 5);
     FR_TL(b.st, 24);
     comm_end(cm, cur);

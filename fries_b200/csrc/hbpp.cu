@@ -21,13 +21,13 @@ hbpp_stage_kernel(MolView gm, HbStageIO io, CompSubBufs bufs, unsigned n_samp, d
 // Second-generation engine (compress2.cuh): one 512-thread CTA per SM, up to 128 registers, four inputs per thread; the
 // table blob arrives by one bulk asynchronous copy.  This is the product's configuration; FRIES_ENGINE=1 in the
 // environment selects the first-generation kernels above (measurement / regression variant, same results up to FP ties).
-template <int S, int MINCTAS>
+template <int S, int MINCTAS, bool MULTI>
 __global__ void __launch_bounds__(FR2_NT, MINCTAS)
 hbpp_stage2_kernel(MolView gm, HbStageIO io, CompSubBufs2 bufs, unsigned n_samp, double rn) {
     HbProvider<S> prov;
     prov.m = mol_stage_shared_bulk(gm, fr_dyn_smem);
     prov.io = io;
-    comp_sub_engine2(prov, bufs, n_samp, rn);
+    comp_sub_engine2<MULTI>(prov, bufs, n_samp, rn);
 }
 // CTAs per SM of the second-generation kernels.  One (128 registers, no spills) when an SM holds a few thousand inputs:
 // the stage is a chain of short phases and extra warps add skeleton work.  Two (64 registers, ~1 kB of spill traffic per
@@ -183,6 +183,17 @@ int fries_hbpp_alloc(fries_ctx *c, size_t cap, fries_hbpp **out, bool stages) {
         fries_set_error("fries_hbpp_alloc: cudaMemset failed");
         rc = FRIES_ERR_CUDA;
     }
+    if (rc == FRIES_OK) {  // bracket predictors: how long a prediction error is remembered (FRIES_PRED_DECAY: measurement knob)
+        KeepPred init[8];
+        memset(init, 0, sizeof(init));
+        const char *e = getenv("FRIES_PRED_DECAY");
+        const double decay = e ? atof(e) : 0.7;
+        for (int k = 0; k < 8; k++) init[k].decay = decay;
+        if (cudaMemcpy(hb->pred.p, init, sizeof(init), cudaMemcpyHostToDevice) != cudaSuccess) {
+            fries_set_error("fries_hbpp_alloc: cudaMemcpy failed");
+            rc = FRIES_ERR_CUDA;
+        }
+    }
     if (rc != FRIES_OK) {
         delete hb;
         return rc;
@@ -254,11 +265,14 @@ static int launch_stage(fries_hbpp *hb, fries_mol *mol, HbStageIO &io, CompSubBu
     ProfScope ps(c, names[S]);
     if (stage_engine() == 2) {
         const int ctas = stage2_ctas(hb->cap);
-        const void *kern = ctas == 2 ? (const void *)hbpp_stage2_kernel<S, 2> : (const void *)hbpp_stage2_kernel<S, 1>;
-        static bool attr_set[2] = {false, false};  // per instantiation <S, ctas>: opt in to more than 48 kB of shared memory
-        if (!attr_set[ctas - 1]) {
+        const bool multi = bufs.cm.n_ranks > 1;
+        const void *kern = multi ? (ctas == 2 ? (const void *)hbpp_stage2_kernel<S, 2, true> : (const void *)hbpp_stage2_kernel<S, 1, true>)
+                                 : (ctas == 2 ? (const void *)hbpp_stage2_kernel<S, 2, false> : (const void *)hbpp_stage2_kernel<S, 1, false>);
+        static bool attr_set[4] = {false, false, false, false};  // per instantiation: opt in to more than 48 kB of shared memory
+        const int ai = (ctas - 1) + (multi ? 2 : 0);
+        if (!attr_set[ai]) {
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_set[ctas - 1] = true;
+            attr_set[ai] = true;
         }
         if (hb->grid2 == 0) {
             int per_sm = 0;

@@ -428,7 +428,7 @@ __host__ __device__ __forceinline__ unsigned mol_elec_orb(const MolView &m, cons
 // that chain (~100 cycles per entry and warp, measured round 2), which bounded every stage kernel.
 // gen(j) returns the raw weight of entry j and is called for j = 0 .. n - 1 in order (it may carry state, e.g. a bit
 // mask whose lowest set bit it consumes); a negative return value ends the row before entry j.
-#define FR_ROW_CHUNK 8
+#define FR_ROW_CHUNK 4
 template <class G, class F>
 __host__ __device__ __forceinline__ void fr_row_chunked(unsigned n, G &&gen, F &&f) {
     for (unsigned j0 = 0; j0 < n; j0 += FR_ROW_CHUNK) {

@@ -222,79 +222,10 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
     bool fast_done = false;
     if (try_fast) {
         if (!have_br && stage_overflows == 0) {
-            // The list is longer than one CTA holds in registers (find_preserve at 1e6 elements brackets 3e4 - 6e4
-            // candidates: the threshold moves by a few 1e-3 between iterations).  Every CTA runs the Newton rounds on the
-            // candidates it staged itself (shared memory), one barrier with payload per round for the exact integer sums --
-            // CTA 0 streaming the whole list from L2 took 75 us, cg's grid.sync rounds of bracket_solve ~30 us (measured
-            // round 2, H2O-sized run).  Same arithmetic as bracket_solve2_local; the cut is the smallest double that passes a
-            // round's test (x -> x * fac is monotone), which selects the same candidates as the smallest kept candidate does.
-            br.n_cand = my_cand;
-            br.valid = false;
-            br.x_cut = t_hi;
-            br.R = glob_total - s_hi;
-            br.nrem = 0;
-            br.kept_cand = 0;
-            br.rounds = 0;
-            const double R0 = glob_total - s_hi;
-            const long long nrem0 = (long long)n_samp_in - (long long)c_hi;
-            const int E_lo = (int)((__double_as_longlong(t_lo) >> 52) & 0x7ff);
-            if (nrem0 > 0 && nrem0 <= 0xffffffffll && t_hi * (double)nrem0 >= R0 && E_lo >= 64 && E_lo <= 1900) {
-                const double ulp_lo = __longlong_as_double((long long)(E_lo - 52) << 52);
-                const unsigned nst = stg.n_stage;  // <= FR2_CAND_STAGE on every CTA
-                unsigned live = 0;                 // bit q: staged candidate tid + q * VP_NT not counted yet
-                for (unsigned q = 0; q * VP_NT < FR2_CAND_STAGE; q++)
-                    if (tid + q * VP_NT < nst) live |= 1u << q;
-                unsigned long long cnt_tot = 0, nrem_r = (unsigned long long)nrem0;
-                unsigned __int128 sum_tot = 0;
-                double R_r = R0, cut = t_hi;
-                bool exhausted = false;
-                for (unsigned round = 0; round < 4096; round++) {
-                    const double fac = (double)nrem_r;
-                    unsigned long long w_lo = 0, w_hi = 0, w_c = 0;
-                    for (unsigned q = 0; q * VP_NT < FR2_CAND_STAGE; q++) {
-                        if (!((live >> q) & 1u)) continue;
-                        const double x = stg.cx[tid + q * VP_NT];
-                        if (x * fac >= R_r) {
-                            live &= ~(1u << q);
-                            const long long xb = __double_as_longlong(x);
-                            const unsigned long long ix = ((unsigned long long)(xb & 0xfffffffffffffll) | (1ull << 52))
-                                                          << ((int)((xb >> 52) & 0x7ff) - E_lo);
-                            w_lo += ix & 0xffffffffull;
-                            w_hi += ix >> 32;
-                            w_c++;
-                        }
-                    }
-                    double rd[2] = {(double)w_c, 0.0};
-                    unsigned long long rc[2] = {w_lo, w_hi};
-                    fr2_sum<2>(rd, rc, sh_sd, sh_sc);
-                    grid_comb<2>(gcb, gsh, gcur, rd, rc, false, false, pre_d, pre_c);
-                    br.rounds = round + 1;
-                    const unsigned long long c_round = (unsigned long long)rd[0];
-                    if (c_round == 0) break;
-                    // smallest x with x * fac >= R_r
-                    double b = R_r / fac;
-                    while (__longlong_as_double(__double_as_longlong(b) - 1) * fac >= R_r) b = __longlong_as_double(__double_as_longlong(b) - 1);
-                    while (b * fac < R_r) b = __longlong_as_double(__double_as_longlong(b) + 1);
-                    cut = fmin(cut, b);
-                    cnt_tot += c_round;
-                    sum_tot += ((unsigned __int128)rc[1] << 32) + rc[0];
-                    if (cnt_tot >= (unsigned long long)nrem0) {
-                        exhausted = true;  // budget exhausted inside the bracket
-                        break;
-                    }
-                    nrem_r = (unsigned long long)nrem0 - cnt_tot;
-                    const double kept_sum = (double)(unsigned long long)(sum_tot >> 64) * 18446744073709551616.0 +
-                                            (double)(unsigned long long)sum_tot;
-                    R_r = R0 - kept_sum * ulp_lo;
-                }
-                if (!exhausted) {
-                    br.x_cut = cut < t_hi ? cut : t_hi;
-                    br.R = R_r;
-                    br.nrem = (unsigned)nrem_r;
-                    br.kept_cand = cnt_tot;
-                    br.valid = t_lo * (double)nrem_r < R_r && cut > t_lo;
-                }
-            }
+            // the list is longer than one CTA holds in registers (find_preserve at 1e6 elements brackets 1e4 - 6e4
+            // candidates): every CTA runs the rounds on the candidates it staged itself (compress2.cuh)
+            br = bracket_solve_staged(stg, gcb, gsh, gcur, glob_total - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi,
+                                      sh_sd, sh_sc, my_cand);
         } else if (!have_br) {  // a staging area overflowed: the grid-distributed rounds of bracket_solve on the global list
             br = bracket_solve(grid, a.cand, a.st6->gacc, glob_total - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi,
                                sh_sd, sh_sc, cm1, nullptr, my_cand <= FR_CAND_GCAP);

@@ -400,3 +400,128 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
     eng.close()
     dist.barrier()
     dist.destroy_process_group()
+
+
+def run_multi_gpu_frifull(args, cfg, ctx, dist, rank, world, local, prepare_workload, ClockSampler):
+    """bench.py --config n2full --gpus N > 1 (BASELINE.json configs[3]: frifull_mol on a partitioned vector).  Weak scaling:
+    vec_nonz parents PER GPU, i.e. N times the single-GPU line's compression budget; every connection is routed to its owner
+    over NVLink from inside hv_fill_kernel.  value = spawned H.v elements per second over all GPUs."""
+    import json
+    import time
+
+    from ._capi import FrifullParams
+    from .api import hash_owner
+
+    stream = torch.cuda.current_stream()
+    gcfg = dict(cfg, mat_nonz=1, max_dets=4_000_000, vec_nonz=cfg["vec_nonz"] * world, target=cfg["target"] * world)
+    wl = prepare_workload(gcfg, ctx)  # the same global start vector on every rank (deterministic)
+    sm, mol = wl["sm"], wl["mol"]
+    _, owner = hash_owner(ctx, wl["keys"], wl["proc_scr"], world)
+    seg_cap = 1 << 22  # connections per routed window and rank
+    eng = MultiGpuFrisys(ctx, dist, rank, world, mol, sm, cfg["max_dets"], 1 << 16, seg_cap, wl["proc_scr"], wl["vec_scr"],
+                         wl["hf_en"], (wl["hf"], np.ones(1)), (wl["htrial_keys"], wl["htrial_vals"]), route="p2p")
+    eng.load(wl["keys"], wl["vals"], owner)
+    fp = FrifullParams(eps=cfg["eps"], target_nonz=gcfg["vec_nonz"], en_shift=0.0, adjust_shift=0, damp_factor=0.05,
+                       target_norm=0.0, last_one_norm=0.0)
+    rs = np.random.RandomState(1)
+    uni = rs.randint(0, 2**32, args.warmup + 2 * args.steps + 16, dtype=np.uint64) / (1.0 + 0xFFFFFFFF)
+    ui = 0
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    last = None
+    for _ in range(args.warmup):
+        last = eng.frifull_iterate(fp, float(uni[ui])); ui += 1
+    clocks = ClockSampler(local)
+    clocks.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    spawned = 0
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record(stream)
+        last = eng.frifull_iterate(fp, float(uni[ui])); ui += 1
+        ev[k][1].record(stream)
+        spawned += last.n_spawned  # global (summed over the ranks inside the call)
+    dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    ms_per_step = ms / args.steps
+    launches = ctx.launch_count - launches0
+    # e2e: every step uploads this rank's shard from pinned host memory, iterates, downloads the shard
+    cap_l = eng.vec.capacity
+    hk = torch.empty(cap_l, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+    hv = torch.empty(2 * cap_l, dtype=torch.float64).pin_memory().numpy()
+    n_now = eng.vec.download_into(hk, hv)
+    n_e2e = max(2, args.steps // 4)
+    t_e2e, h2d, d2h, sp_e2e = 0.0, 0, 0, 0
+    for k in range(n_e2e):
+        flush.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        check(lib.fries_vec_upload(eng.vec.h, hk.ctypes.data, hv.ctypes.data, n_now))
+        h2d += n_now * 24 + 48
+        st = eng.frifull_iterate(fp, float(uni[ui])); ui += 1
+        n_now = eng.vec.download_into(hk, hv)
+        d2h += n_now * 24 + 128
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
+        sp_e2e += st.n_spawned
+    te = torch.tensor([t_e2e, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+    tmax = te.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(te)
+    ctx.set_profile(2)
+    for _ in range(2):
+        flush.zero_()
+        eng.frifull_iterate(fp, float(uni[ui])); ui += 1
+    ctx.set_profile(0)
+    kern = {}
+    for nm in ["h_diag", "hv_count", "hv_scan", "hv_fill", "merge_insert", "merge_accum", "find_preserve", "sys_comp", "compact"]:
+        t, n = ctx.kernel_ms(nm)
+        if n:
+            kern[nm] = round(t / 2, 4)
+    err = eng.comm.error_epoch()
+    if rank == 0:
+        try:
+            peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                     "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+        except OSError:
+            peak = 6650.0
+        per_iter = spawned / args.steps
+        top = max(kern, key=kern.get) if kern else None
+        bytes_top = {"hv_fill": 16, "merge_insert": 28, "merge_accum": 28}.get(top, 56) * per_iter / world
+        nvl_bytes = 16.0 * per_iter * (world - 1) / world / world  # per GPU and direction
+        nvl_gbps = nvl_bytes / (ms_per_step * 1e-3) / 1e9
+        out = {
+            "metric": "spawned_hv_elements_per_sec", "value": round(spawned / (ms * 1e-3), 1), "unit": "elements/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["workload"] + f" x{world} (weak scaling: vec_nonz per GPU)", "vec_nonz": gcfg["vec_nonz"],
+                       "l2": "flushed between iterations (512 MB write)", "stored_dets": int(last.curr_size),
+                       "spawned_per_iteration": int(per_iter)},
+            "fri_iterations_per_sec": round(1000.0 / ms_per_step, 3),
+            "gpu_launches": int(launches), "clocks": clk,
+            "e2e": {"value": round(sp_e2e / float(tmax[0].item()), 1), "unit": "elements/s",
+                    "h2d_bytes_per_step": int(float(te[1].item()) / n_e2e), "d2h_bytes_per_step": int(float(te[2].item()) / n_e2e),
+                    "what": "per step and rank: fries_vec_upload of the rank's shard (pinned host memory) + "
+                            "fries_frifull_mol_iterate + fries_vec_download; bytes summed over the ranks, time = max over ranks"},
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": round(bytes_top / (kern[top] * 1e-3) / 1e9, 2) if top else None,
+                         "peak": peak, "unit": "GB/s", "frac": round(bytes_top / (kern[top] * 1e-3) / 1e9 / peak, 5) if top else None,
+                         "traffic": None, "algorithmic_bytes_per_launch": int(bytes_top), "kernels_ms_per_iteration_rank0": kern,
+                         "what": "rank 0, one GPU's share; a kernel's time includes the waits of its in-kernel exchanges"},
+            "route": {"collective": "none: hv_fill_kernel stores every connection into its owner's peer-mapped window "
+                                    "(csrc/comm.cuh RouteView), windows of 2^22 connections per rank",
+                      "nvlink_bytes_per_gpu_per_step": round(nvl_bytes, 1), "nvlink_GBps_per_gpu": round(nvl_gbps, 3),
+                      "nvlink_peak_GBps": 770.0, "nvlink_frac": round(nvl_gbps / 770.0, 5)},
+            "comm_error_epoch": err,
+            "energy_est": last.numer / last.denom if last and last.denom else None,
+            "cpu_baseline": {"value": None, "unit": "elements/s", "cores": 1, "kind": "reference",
+                             "sample": "not run in this line (see the N = 1 line and bench.py --impl reference)"},
+        }
+        print(json.dumps(out), flush=True)
+    eng.close()
