@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfries_b200.so")
+LIB_PATH = os.environ.get("FRIES_B200_LIB") or os.path.join(HERE, "libfries_b200.so")  # (the override: A/B of two builds)
 
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
 INI_FLAG = 1 << 63

@@ -33,10 +33,15 @@ struct CompState {
                                  // barrier, after the cross-rank exchange
     long long tl[48];            // timeline of thread 0 of CTA 0 through comp_sub_engine2 (clock64, SM cycles): FR_TL marks
 };
+// (compiled in with -DFRIES_TIMELINE_BUILD only: 37 marks are ~300 instructions of a stage kernel's hot path)
+#ifdef FRIES_TIMELINE_BUILD
 #define FR_TL(st, k)                                                        \
     do {                                                                    \
         if (blockIdx.x == 0 && threadIdx.x == 0) (st)->tl[k] = clock64();   \
     } while (0)
+#else
+#define FR_TL(st, k) ((void)0)
+#endif
 
 __device__ __forceinline__ unsigned long long fr_globaltimer() {
     unsigned long long t;

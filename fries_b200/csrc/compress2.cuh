@@ -447,6 +447,16 @@ __device__ __forceinline__ BracketResult bracket_solve_staged(const StageShared 
     return br;
 }
 
+// single rank, out of line (rare at the sizes where code size matters): the grid-distributed rounds of compress.cuh on the
+// global candidate list
+static __device__ __noinline__ BracketResult bracket_solve_global(const CandList cl, unsigned long long *gacc, double R0,
+                                                                  long long nrem0, double t_lo, double t_hi, double *shd,
+                                                                  unsigned long long *shc, const CommView cm,
+                                                                  unsigned long long n_local) {
+    cg::grid_group grid = cg::this_grid();
+    return bracket_solve(grid, cl, gacc, R0, nrem0, t_lo, t_hi, shd, shc, cm, nullptr, n_local <= FR_CAND_GCAP);
+}
+
 struct CompSubBufs2 {
     CompSubBufs b;      // per-input state, outputs, reduction scratch, prediction (compress.cuh)
     uint32_t *cand_idx; // [FR_CAND_GCAP]
@@ -607,7 +617,7 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
             double wr = v;
             uint32_t kb = 0;
             const double xmax = nd > 0 ? v / nd : v * wmax;
-            if (try_fast && xmax >= t_lo) {
+            if (__builtin_expect(try_fast && xmax >= t_lo, 0)) {  // a few thousand of 1e6 inputs
                 if (nd > 0) {
                     if (xmax >= t_hi) {
                         c_hi += nd;
@@ -742,6 +752,9 @@ __device__ void comp_sub_engine2(P &prov, const CompSubBufs2 &b2, unsigned n_sam
         else if (!have_br && stage_overflows == 0)  // single rank, a list beyond one CTA's registers
             br = bracket_solve_staged(sm.stg, gcb, gsh, gcur, s - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi, sh_sd,
                                       sh_sc, my_cand);
+        else if (!have_br)  // some CTA staged more than its area holds (1e7 inputs: 3e5 - 5e5 candidates): the global list
+            br = bracket_solve_global(b.cand, b.st->gacc, s - s_hi, (long long)n_samp_in - (long long)c_hi, t_lo, t_hi, sh_sd, sh_sc,
+                                      cm, my_cand);
         n_cand = br.n_cand;
         FR_STAMP(b.st, 6);
         FR_TL(b.st, 4);  // solve done

@@ -226,18 +226,22 @@ __device__ __forceinline__ void gc_wait(const GridComb &g, GridCombShared &sh, u
 // d, c: this CTA's partials (uniform over the CTA; K <= 2 pairs).  On return: grid totals in d, c (bit-identical in every
 // CTA) and, with `prefix`, the exclusive prefix of (d[0], c[0]) over the CTAs before this one.  Every thread of every CTA
 // calls it; 32 <= blockDim.x, a multiple of 32.
+// CTA 0's part of a plain call, out of line: ~300 instructions that only one CTA of the grid executes, and a kernel makes
+// five to ten calls (the instruction cache of the other CTAs' SMs should not have to step over them)
+template <int K>
+__device__ __noinline__ void gc_cta0(const GridComb g, GridCombShared *sh, unsigned tag, bool fence) {
+    double td[K];
+    unsigned long long tc[K];
+    gc_reduce<K>(g, *sh, tag, td, tc, fence);
+    gc_publish<K, 0>(g, tag, td, tc, nullptr);
+}
 template <int K>
 __device__ __forceinline__ void grid_comb(const GridComb &g, GridCombShared &sh, GridCombCursor &cur, double (&d)[K],
                                           unsigned long long (&c)[K], bool prefix, bool fence, double &pre_d,
                                           unsigned long long &pre_c) {
     const unsigned tag = cur.epoch + 1 ? cur.epoch + 1 : 1;  // tags start at 1 (the state starts zeroed) and skip 0 on wrap
     gc_post<K>(g, tag, d, c, fence);
-    if (blockIdx.x == 0) {
-        double td[K];
-        unsigned long long tc[K];
-        gc_reduce<K>(g, sh, tag, td, tc, fence);
-        gc_publish<K, 0>(g, tag, td, tc, nullptr);
-    }
+    if (blockIdx.x == 0) gc_cta0<K>(g, &sh, tag, fence);
     gc_wait<K, 0>(g, sh, tag, d, c, pre_d, pre_c, nullptr, fence);
     if (!prefix) {
         pre_d = 0;

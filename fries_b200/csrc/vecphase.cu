@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(VP_NT, MINCTAS) vec_phase_kernel(MolView gm, V
             if (a.do_death) {
                 if (x != 0) {
                     double d = dv[k];
-                    if (isnan(d)) {  // DistVec::matr_el_at_pos vec_utils.hpp:672-677: computed on first use
+                    if (__builtin_expect(isnan(d), 0)) {  // DistVec::matr_el_at_pos vec_utils.hpp:672-677: computed on first use
                         uint8_t occ[FRIES_MAX_ELEC + 1];
                         mol_occ_list(v.keys[i], occ);
                         d = mol_diag(m, occ) - a.hf_en;
