@@ -60,7 +60,27 @@ def start_parents(cfg):
 # per stored vector element; vec_phase = the four fused (death/cloning, find_preserve, sys_comp, delete + compact)
 B_PER_VEC_EL = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8, "vec_phase": 80}
 # roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel) cannot be measured inside this
-# program: it is null here and lives in the ncu summaries under profiles/ (named per round), captured from this command
+# program: captured_traffic() reads it from the committed ncu --set full capture of this command under profiles/ when there is
+# one for the dominant kernel at this configuration, and the line says which file; otherwise null
+
+
+def captured_traffic(config_name, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the committed `ncu --set full` capture of this command
+    (profiles/r02c_ncu_full_<kernel>_<config>_raw.csv, exported with `ncu -i ... --page raw --csv`) -> (bytes, file) or
+    (None, reason).  Read from the capture, never typed in: a kernel without a capture of its own reports null."""
+    import csv
+    tag = {"hbpp_stage4": "stage4", "vec_phase": "vecphase"}.get(kernel)
+    path = os.path.join(ROOT, "profiles", f"r02c_ncu_full_{tag}_{config_name}_raw.csv") if tag else None
+    if not path or not os.path.exists(path):
+        return None, "no ncu --set full capture of this kernel at this configuration under profiles/ (captures: r02c_ncu_full_*)"
+    rows = list(csv.reader(open(path)))
+    h, u, v = rows[0], rows[1], rows[2]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        i = h.index(key)
+        tot += float(v[i]) * scale[u[i]]
+    return int(tot), os.path.relpath(path, ROOT)
 
 
 def mt_uniforms(seed, n):
@@ -436,8 +456,8 @@ def run_ours(args, cfg):
     roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5),
                 "peak_nominal": 8000.0, "frac_nominal": round(achieved / 8000.0, 5),  # report against both
-                "traffic": None,
-                "traffic_source": "not measurable in-process; ncu captures of this command: profiles/r02_*",
+                "traffic": captured_traffic(args.config, top)[0],
+                "traffic_source": captured_traffic(args.config, top)[1],
                 "kernel_table": {k: {"ms": round(kern[k], 4), "algorithmic_MB": round(units[k] / 1e6, 2),
                                      "GBps": round(units[k] / (kern[k] * 1e-3) / 1e9, 1),
                                      "frac": round(units[k] / (kern[k] * 1e-3) / 1e9 / peak, 4)} for k in kern if k in units},
