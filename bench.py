@@ -284,7 +284,7 @@ def run_frifull(args, cfg, ctx, stream, local):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     per_iter = spawned / args.steps
     top = max(kern, key=kern.get) if kern else None
-    bytes_top = {"hv_fill": 16, "merge_insert": 28, "merge_accum": 28}.get(top, 56) * per_iter
+    bytes_top = {"hv_fill": 16, "merge_insert": 28 if "merge_accum" in kern else 56, "merge_accum": 28}.get(top, 56) * per_iter
     out = {
         "metric": "spawned_hv_elements_per_sec", "value": round(spawned / (ms * 1e-3), 1), "unit": "elements/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
@@ -441,7 +441,7 @@ def run_ours(args, cfg):
     n_vec = stp.curr_size
     units = {nm: cfg["mat_nonz"] * B_PER_SAMPLE_STAGE for nm in names if nm.startswith("hbpp_stage")}
     units["hbpp_finalize"] = stp.n_matrix_samples * (B_PER_SAMPLE_STAGE + 16)
-    units["merge_insert"] = stp.n_spawned * 28
+    units["merge_insert"] = stp.n_spawned * (28 if "merge_accum" in kern else 56)  # one pass since the end of round 2: both halves
     units["merge_accum"] = stp.n_spawned * 28
     for nm, b in B_PER_VEC_EL.items():
         units[nm] = n_vec * b

@@ -17,6 +17,7 @@ namespace cg = cooperative_groups;
 #define FRIES_HASH_PRIME 1099511628211ull  // FRIES/det_hash.hpp:164
 #define FRIES_EMPTY_KEY (~0ull)
 #define FRIES_NO_POS 0xffffffffu
+#define FRIES_OVF_POS 0xfffffffeu  // index entry of a determinant the full store could not place (merge_fused_kernel)
 
 void fries_set_error(const char *fmt, ...);
 

@@ -293,6 +293,7 @@ static int h_apply_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned 
     }
     if (n_spawned) *n_spawned = total;
     HbSpawnArgs sp{nullptr, 0, 0, nullptr, nullptr, 1, nullptr, nullptr, nullptr, 0, {nullptr}, 0};
+    vec->merge_many_new = only_first == (size_t)-1;  // the full H.v (not the dense subspace of a semi-stochastic run)
     if (vec->n_ranks > 1) {
         // Several ranks: every window of <= seg_cap connections is routed into the owners' receive windows
         // (direct route, comm.cuh) and merged there; all ranks run the same number of windows (the maximum).
@@ -347,6 +348,7 @@ static int h_apply_dev(fries_vec *vec, fries_mol *mol, fries_hbpp *hb, unsigned 
         FRIES_TRY(fries_vec_merge_dev(vec, hb->spawn_keys.p, hb->spawn_vals.p, (size_t)len, nullptr, 0, dest));
         v = vec->view();
     }
+    vec->merge_many_new = false;
     CUDA_TRY(cudaStreamSynchronize(c->stream));  // scratch is freed on return
     FRIES_TRY(vec->read_counters(&cnt));
     if (cnt.overflow) {

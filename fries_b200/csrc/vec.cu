@@ -43,7 +43,7 @@ merge_insert_kernel(VecView v, MergeSrc src, uint32_t *__restrict__ slot_out) {
                             v.diag[pos] = __longlong_as_double(0x7ff8000000000000ll);
                             v.tpos[slot] = (uint32_t)pos;
                         } else {
-                            v.tpos[slot] = FRIES_NO_POS;
+                            v.tpos[slot] = FRIES_OVF_POS;
                             atomicAdd(&v.cnt->overflow, 1ull);
                         }
                         result = (uint32_t)slot;
@@ -71,13 +71,89 @@ merge_accum_kernel(VecView v, MergeSrc src, const uint32_t *__restrict__ slot_in
         uint32_t slot = slot_in[i];
         if (slot == FRIES_NO_POS) continue;
         uint32_t pos = v.tpos[slot];
-        if (pos == FRIES_NO_POS) continue;
+        if (pos >= FRIES_OVF_POS) continue;
         valid++;
         uint64_t k;
         double val;
         src.get(i, k, val);
         bool ini = (k >> 63) != 0;
         bool nonz = v.vals[(size_t)origin * v.cap + pos] != 0;
+        if (ini || nonz) atomicAdd(&v.vals[(size_t)dest * v.cap + pos], val);
+        if (!ini && nonz) nonini++;
+    }
+    nonini = warp_sum_u64(nonini);
+    valid = warp_sum_u64(valid);
+    if ((threadIdx.x & 31) == 0) {
+        if (nonini) atomicAdd(&v.cnt->nonini_occ_add, nonini);
+        if (valid) atomicAdd(&v.cnt->n_spawn_valid, valid);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// merge, both phases in one pass (origin != dest: the row the initiator rule reads is not the row being added to, which is
+// every merge of an FRI iteration).  An element that finds its determinant in the index adds right away; if the entry was
+// made by another element of this batch a moment ago, its position may still be on its way: the inserting thread
+// initialises the storage, fences, then publishes the position, and the finder spins on the entry until it is there (the
+// inserter never waits for anybody, so the spin ends; a full store publishes FRIES_OVF_POS instead).
+// Saves the second pass over the batch and its 4 B per element of slot scratch (0.037 of 0.065 ms at 1e6 spawned elements).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FR_VEC_BLOCK)
+merge_fused_kernel(VecView v, MergeSrc src, unsigned origin, unsigned dest) {
+    __shared__ uint32_t s_scr[64];
+    load_scr(s_scr, v.scr_vec);
+    const size_t n = src.count();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long nonini = 0, valid = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t k = FRIES_EMPTY_KEY;
+        double val = 0;
+        const bool have = src.get(i, k, val);
+        if (!(have && k != FRIES_EMPTY_KEY && val != 0)) continue;  // DistVec::add ignores zero values (:418-423)
+        const bool ini = (k >> 63) != 0;
+        const uint64_t key = k & ~FRIES_INI_FLAG;
+        uint64_t slot = vec_hash(v, key, s_scr) & v.tmask;
+        uint32_t pos = FRIES_NO_POS;
+        bool found = false;
+        while (true) {
+            const uint64_t cur = *((volatile uint64_t *)&v.tkeys[slot]);
+            if (cur == key) {
+                found = true;
+                break;
+            }
+            if (cur == FRIES_EMPTY_KEY) {
+                if (!ini) break;
+                const unsigned long long old = atomicCAS((unsigned long long *)&v.tkeys[slot], FRIES_EMPTY_KEY, key);
+                if (old == FRIES_EMPTY_KEY) {
+                    // this thread owns the new entry: allocate a storage position (append), initialise, publish
+                    const unsigned long long p = atomicAdd(&v.cnt->n, 1ull);
+                    if (p < v.cap) {
+                        v.keys[p] = key;
+                        for (unsigned r = 0; r < v.n_vecs; r++) v.vals[(size_t)r * v.cap + p] = 0.0;
+                        v.diag[p] = __longlong_as_double(0x7ff8000000000000ll);
+                        __threadfence();
+                        *((volatile uint32_t *)&v.tpos[slot]) = (uint32_t)p;
+                        pos = (uint32_t)p;
+                    } else {
+                        *((volatile uint32_t *)&v.tpos[slot]) = FRIES_OVF_POS;
+                        atomicAdd(&v.cnt->overflow, 1ull);
+                        pos = FRIES_OVF_POS;
+                    }
+                    break;
+                }
+                if (old == key) {
+                    found = true;
+                    break;
+                }
+            }
+            slot = (slot + 1) & v.tmask;
+        }
+        if (found) {
+            do pos = *((volatile uint32_t *)&v.tpos[slot]);
+            while (pos == FRIES_NO_POS);
+        }
+        if (pos >= FRIES_OVF_POS) continue;
+        valid++;
+        const bool nonz = v.vals[(size_t)origin * v.cap + pos] != 0;
         if (ini || nonz) atomicAdd(&v.vals[(size_t)dest * v.cap + pos], val);
         if (!ini && nonz) nonini++;
     }
@@ -357,10 +433,27 @@ int fries_vec_merge_src_dev(fries_vec *vec, const MergeSrc &src, unsigned origin
         CUDA_TRY(cudaGetLastError());
         return FRIES_OK;
     }
-    FRIES_TRY(vec->slot_scratch.ensure(n_max));
     VecView v = vec->view();
     size_t want = (n_max + FR_VEC_BLOCK - 1) / FR_VEC_BLOCK;
     int grid = (int)(want < (size_t)c->sm_count * 8 ? want : (size_t)c->sm_count * 8);
+    static const bool two_pass = [] {  // FRIES_MERGE_TWO_PASS=1: the separate insert / accumulate kernels (A/B, regression)
+        const char *e = getenv("FRIES_MERGE_TWO_PASS");
+        return e && e[0] == '1' && e[1] == 0;
+    }();
+    // One pass where it pays (same-box A/B, round 2): an index beyond the L2 (1.25e7-determinant store: 2.25 -> 1.54 ms) and
+    // few insertions per element; with the index in L2 the second pass is cheap (H2O-sized: 0.063 against 0.085 ms in one
+    // pass), and the full H.v inserts a determinant for every few elements, each insertion with its fence (5.1 -> 6.3 ms).
+    const bool index_in_l2 = (size_t)vec->tsize * 12 <= ((size_t)96 << 20);
+    if (origin != dest && !two_pass && !index_in_l2 && !vec->merge_many_new) {
+        ProfScope ps(c, "merge_insert");
+        merge_fused_kernel<<<grid, FR_VEC_BLOCK, 0, c->stream>>>(v, src, origin, dest);
+        c->launch_count++;
+        clamp_count_kernel<<<1, 1, 0, c->stream>>>(vec->cnt.p, (unsigned long long)vec->cap);
+        c->launch_count++;
+        CUDA_TRY(cudaGetLastError());
+        return FRIES_OK;
+    }
+    FRIES_TRY(vec->slot_scratch.ensure(n_max));
     {
         ProfScope ps(c, "merge_insert");
         merge_insert_kernel<<<grid, FR_VEC_BLOCK, 0, c->stream>>>(v, src, vec->slot_scratch.p);

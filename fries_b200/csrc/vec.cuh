@@ -49,6 +49,7 @@ struct fries_vec {
     DevBuf<uint32_t> scr;  // [0..63] vec scrambler, [64..127] proc scrambler
     DevBuf<VecCounters> cnt;
     DevBuf<uint32_t> slot_scratch;
+    bool merge_many_new = false;         // hint of the caller (full H.v): most elements of the next merges create determinants
     bool deterministic = false;          // reproducible merge (vec_det.cu): append and add in batch order
     DevBuf<uint32_t> det_u32;            // its scratch
     DevBuf<uint8_t> det_tmp;
@@ -108,7 +109,10 @@ __device__ __forceinline__ uint32_t vec_lookup(const VecView &v, uint64_t key, c
     uint64_t slot = vec_hash(v, key, s_scr) & v.tmask;
     while (true) {
         uint64_t cur = v.tkeys[slot];
-        if (cur == key) return v.tpos[slot];
+        if (cur == key) {
+            const uint32_t p = v.tpos[slot];
+            return p >= FRIES_OVF_POS ? FRIES_NO_POS : p;  // (an entry the full store could not place)
+        }
         if (cur == FRIES_EMPTY_KEY) return FRIES_NO_POS;
         slot = (slot + 1) & v.tmask;
     }

@@ -108,7 +108,7 @@ __global__ void merge_det_assign_kernel(VecView v, const uint32_t *__restrict__ 
             v.diag[pos] = __longlong_as_double(0x7ff8000000000000ll);
             v.tpos[s] = (uint32_t)pos;
         } else {
-            v.tpos[s] = FRIES_NO_POS;
+            v.tpos[s] = FRIES_OVF_POS;
             atomicAdd(&v.cnt->overflow, 1ull);
         }
     }

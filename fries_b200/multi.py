@@ -345,7 +345,7 @@ def run_multi_gpu_bench(args, cfg, ctx, dist, rank, world, local, prepare_worklo
         except OSError:
             peak, src = 6650.0, "fallback B200_PROFILING.md"
         share = 1 if weak else world  # one GPU's share of the configuration's samples / elements
-        bytes_alg = {"hbpp_finalize": 56, "merge_insert": 28, "merge_accum": 28}.get(top, 40) * cfg["mat_nonz"] // share
+        bytes_alg = {"hbpp_finalize": 56, "merge_insert": 28 if "merge_accum" in kern else 56, "merge_accum": 28}.get(top, 40) * cfg["mat_nonz"] // share
         if top in ("death_axpy", "find_preserve", "sys_comp", "compact"):
             bytes_alg = {"death_axpy": 32, "find_preserve": 24, "sys_comp": 16, "compact": 8}[top] * cfg["vec_nonz"] // share
         ach = bytes_alg / (kern[top] * 1e-3) / 1e9
@@ -494,7 +494,7 @@ def run_multi_gpu_frifull(args, cfg, ctx, dist, rank, world, local, prepare_work
             peak = 6650.0
         per_iter = spawned / args.steps
         top = max(kern, key=kern.get) if kern else None
-        bytes_top = {"hv_fill": 16, "merge_insert": 28, "merge_accum": 28}.get(top, 56) * per_iter / world
+        bytes_top = {"hv_fill": 16, "merge_insert": 28 if "merge_accum" in kern else 56, "merge_accum": 28}.get(top, 56) * per_iter / world
         nvl_bytes = 16.0 * per_iter * (world - 1) / world / world  # per GPU and direction
         nvl_gbps = nvl_bytes / (ms_per_step * 1e-3) / 1e9
         out = {
