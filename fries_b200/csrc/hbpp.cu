@@ -34,13 +34,16 @@ hbpp_stage2_kernel(MolView gm, HbStageIO io, CompSubBufs2 bufs, unsigned n_samp,
 // thread, twice the warps) when the scratch was sized for millions of samples: the row loops are then bound by
 // per-warp latency chains and the second CTA hides them (measured round 2 at 1.25e7 samples: 9.8 -> 7.4 ms for the five
 // stages; at 2.6e5: 0.49 -> 0.51 ms).  FRIES_STAGE2_CTAS=1|2 in the environment overrides the choice.
-static int stage2_ctas(size_t cap) {
+// (end of round 2, same-box A/B at 2.6e5 samples, scratch for 1.04e6: two CTAs gain 4 % on stage 2 and 11 % on stage 3 -- the
+// stages with the longest rows -- and lose 3-15 % on the others: those two switch at 1e6)
+static int stage2_ctas(size_t cap, int stage) {
     static int forced = [] {
         const char *e = getenv("FRIES_STAGE2_CTAS");
         return (e && (e[0] == '1' || e[0] == '2') && e[1] == 0) ? e[0] - '0' : 0;
     }();
     if (forced) return forced;
-    return cap >= (size_t)4000000 ? 2 : 1;
+    if (cap >= (size_t)4000000) return 2;
+    return (cap >= (size_t)1000000 && (stage == 2 || stage == 3)) ? 2 : 1;
 }
 static int stage_engine() {
     static int v = [] {
@@ -269,7 +272,7 @@ static int launch_stage(fries_hbpp *hb, fries_mol *mol, HbStageIO &io, CompSubBu
     static const char *names[] = {"hbpp_stage0", "hbpp_stage1", "hbpp_stage2", "hbpp_stage3", "hbpp_stage4"};
     ProfScope ps(c, names[S]);
     if (stage_engine() == 2) {
-        const int ctas = stage2_ctas(hb->cap);
+        const int ctas = stage2_ctas(hb->cap, S);
         const bool multi = bufs.cm.n_ranks > 1;
         const void *kern = multi ? (ctas == 2 ? (const void *)hbpp_stage2_kernel<S, 2, true> : (const void *)hbpp_stage2_kernel<S, 1, true>)
                                  : (ctas == 2 ? (const void *)hbpp_stage2_kernel<S, 2, false> : (const void *)hbpp_stage2_kernel<S, 1, false>);
@@ -279,18 +282,19 @@ static int launch_stage(fries_hbpp *hb, fries_mol *mol, HbStageIO &io, CompSubBu
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr_set[ai] = true;
         }
-        if (hb->grid2 == 0) {
+        if (hb->grid2_s[S] != c->sm_count * ctas) {
             int per_sm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FR2_NT, smem));
             FRIES_REQUIRE(per_sm >= ctas, "hbpp_stage2_kernel<%d>: %d CTAs per SM do not fit (%zu B of dynamic shared memory)", S,
                           ctas, smem);
-            hb->grid2 = c->sm_count * ctas;
+            hb->grid2_s[S] = c->sm_count * ctas;
+            hb->grid2 = hb->grid2_s[S];
         }
         static const bool marks = getenv("FRIES_CTA_MARKS") != nullptr;
         if (marks && !hb->cta_marks.p) FRIES_TRY(hb->cta_marks.alloc((size_t)7 * 8 * 1024));
         CompSubBufs2 b2{bufs, hb->cand_idx.p, hb->gcomb.p, marks ? hb->cta_marks.p + (size_t)S * 8 * 1024 : nullptr};
         void *args2[] = {(void *)&gm, (void *)&io, (void *)&b2, (void *)&n_samp, (void *)&rn};
-        CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(hb->grid2), dim3(FR2_NT), args2, smem, c->stream));
+        CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(hb->grid2_s[S]), dim3(FR2_NT), args2, smem, c->stream));
         c->launch_count++;
         return FRIES_OK;
     }
@@ -799,7 +803,7 @@ extern "C" int fries_hbpp_cta_marks(fries_hbpp *hb, int s, double *h_out, int *g
     FRIES_REQUIRE(hb->cta_marks.p && hb->grid2 > 0, "fries_hbpp_cta_marks: set FRIES_CTA_MARKS=1 before the first iteration");
     fries_ctx *c = hb->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    const int g = s >= 5 ? hb->grid_vp : hb->grid2;
+    const int g = s >= 5 ? hb->grid_vp : hb->grid2_s[s];
     FRIES_REQUIRE(g > 0 && g <= 1024, "fries_hbpp_cta_marks: that kernel has not run");
     std::vector<unsigned long long> m((size_t)8 * g);
     CUDA_TRY(cudaMemcpyAsync(m.data(), hb->cta_marks.p + (size_t)s * 8 * 1024, m.size() * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -38,6 +38,7 @@ struct fries_hbpp {
     DevBuf<uint8_t> keep_flags;
     size_t n_trial = 0, n_htrial = 0;
     int grid = 0, grid2 = 0;  // cooperative grid of the stage kernels: first / second generation engine
+    int grid2_s[5] = {0, 0, 0, 0, 0};  // ... of every stage (one or two CTAs per SM, hbpp.cu: stage2_ctas)
     fries_comm *comm = nullptr;  // multi-rank: peer-mapped inboxes (comm.cuh); not owned
     // multi-rank routing: per-destination send segments (keys | vals) and counters
     int64_t *send_buf = nullptr, *recv_buf = nullptr;  // caller-owned device buffers [n_ranks][2 * seg_cap]
